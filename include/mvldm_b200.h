@@ -1,0 +1,166 @@
+/*
+ * mvldm_b200 — C ABI of the B200-native MV-LDM denoising hot path.
+ *
+ * Plain pointers and sizes only (no torch types).  Every entry point returns 0 on success and a non-zero
+ * code on failure; mvldm_last_error() then returns a thread-local message (reference error behaviour is
+ * Python exceptions/asserts, e.g. src/model/diffusion_wrapper.py:149,673 — the Python host raises
+ * RuntimeError from this string).  All device work is enqueued asynchronously on the caller's
+ * cudaStream_t (passed as void*); nothing here synchronises the device, so every call is CUDA-graph
+ * capturable.  There is no CPU fallback: a missing GPU / unsupported shape is an error.
+ *
+ * Each function names the reference interface it replaces (paths relative to the reference repo).
+ */
+#ifndef MVLDM_B200_H_
+#define MVLDM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVLDM_MAX_LEVELS 4
+#define MVLDM_MAX_SEGS 3
+
+typedef struct mvldm_handle_s* mvldm_handle;
+
+/* dtype codes for mvldm_set_weight */
+enum { MVLDM_F32 = 0, MVLDM_BF16 = 1, MVLDM_F16 = 2 };
+/* kernel family: tcgen05/TMA kernels (product) or the plain CUDA-core kernels kept as an on-device
+ * cross-check for the tests (never selected implicitly) */
+enum { MVLDM_IMPL_TC = 0, MVLDM_IMPL_SIMT = 1 };
+
+/* Replaces: MultiViewUNetCfg + UNet2DModelCfg + SpatialTransformer3DCfg
+ * (src/model/denoiser/mvunet.py:22-40, src/model/denoiser/mvdream/attention.py:23-32) and the
+ * UNet2DConditionModel constructor arguments at mvunet.py:54-63. */
+typedef struct {
+  int32_t in_channels;                          /* 4 latent + 1 mask + ray channels (diffusion_wrapper.py:98-129) */
+  int32_t out_channels;
+  int32_t num_levels;                           /* len(block_out_channels) */
+  int32_t block_out_channels[MVLDM_MAX_LEVELS]; /* config/model/denoiser/mv_unet.yaml:10 */
+  int32_t layers_per_block;                     /* diffusers default 2 */
+  int32_t norm_groups;                          /* 32 */
+  int32_t num_heads;                            /* multi_view_attention.num_heads */
+  int32_t max_attn_res;                         /* mvunet.py:137,190: multi-view block only if h,w <= 32 */
+  int32_t impl;                                 /* MVLDM_IMPL_* */
+  int32_t use_cuda_graph;                       /* capture one graph per (B,V,h,w) and replay it */
+} mvldm_config;
+
+const char* mvldm_last_error(void);
+int mvldm_version(void);
+
+/* Replaces MultiViewUNet.__init__ (mvunet.py:43-88): builds the layer table, no weights yet. */
+int mvldm_create(const mvldm_config* cfg, int device, mvldm_handle* out);
+int mvldm_destroy(mvldm_handle h);
+
+/* Weight ingestion.  Keys are the reference module's state_dict keys without the Lightning
+ * "denoiser." prefix, e.g. "unet.down_blocks.0.resnets.1.conv1.weight",
+ * "cross_attn_blocks_mid.0.transformer_blocks.0.attn1.to_q.weight".  `ptr` is a DEVICE pointer to a
+ * contiguous tensor of `dtype`; it is copied, the caller keeps ownership.
+ * Replaces nn.Module.load_state_dict for the denoiser (scripts/generate_mvldm.py:66). */
+int mvldm_num_weights(mvldm_handle h);
+const char* mvldm_weight_name(mvldm_handle h, int index);
+int mvldm_weight_shape(mvldm_handle h, int index, int64_t shape[4], int* ndim);
+int mvldm_set_weight(mvldm_handle h, const char* key, const void* ptr, const int64_t* shape, int ndim,
+                     int dtype, void* stream);
+/* Packs every layer into its kernel layout (bf16, tap-major conv filters, fused QKV with padded heads,
+ * conv2+shortcut K-concatenation, GEGLU column interleave).  Fails if a key is missing. */
+int mvldm_finalize_weights(mvldm_handle h, void* stream);
+
+/* Bytes of device workspace the handle holds for a (B scenes, V views, h x w latent) call. */
+int64_t mvldm_workspace_bytes(mvldm_handle h, int B, int V, int H, int W);
+
+/* Replaces Denoiser.forward / MultiViewUNet.forward (src/model/denoiser/denoiser.py:22-29,
+ * mvunet.py:90-208).  latents: device fp32 [B,V,in_channels,H,W] contiguous; timesteps: device int64
+ * [B*V] (the [B] form of mvunet.py:102-105 is expanded by the host); out: device fp32
+ * [B,V,out_channels,H,W]. */
+int mvldm_forward(mvldm_handle h, void* stream, const float* latents, const int64_t* timesteps, int B, int V,
+                  int H, int W, float* out);
+/* Number of kernels the last mvldm_forward on this handle launched (graph replays count their nodes). */
+int mvldm_last_launch_count(mvldm_handle h);
+
+/* Copy an intermediate activation of the last (non-graph) forward into `out` as fp32 NCHW
+ * [B*V, C, h, w] for per-layer parity tests; names follow oracle taps ("down0.res1", "mid.mv", ...).
+ * Returns the element count through *numel (out may be NULL to query). */
+int mvldm_debug_tap(mvldm_handle h, void* stream, const char* name, float* out, int64_t* numel);
+int mvldm_enable_taps(mvldm_handle h, int enable);
+
+/* Replaces the three torch.cat of DiffusionWrapper.step (diffusion_wrapper.py:429-432,438):
+ * inputs[b, v] = [latent(4) | mask(1) | rays(R)], context views first.  All fp32 device pointers:
+ * x_t [B,v_t,4,hw], context_latents [B,v_c,4,hw] (may be NULL iff v_c == 0), rays [B,v_c_total+v_t,R,hw]
+ * where the first `ray_view_offset` views of `rays` are skipped.  Mask = 0 for context, 1 for target
+ * (diffusion_wrapper.py:476-477).  out [B, v_c+v_t, 5+R, hw]. */
+int mvldm_build_inputs(void* stream, const float* x_t, const float* context_latents, const float* rays,
+                       int B, int v_c, int v_t, int ray_views, int ray_view_offset, int R, int hw, float* out);
+
+/* Replaces the CFG compose (diffusion_wrapper.py:444/447) fused with DDIMScheduler.step
+ * (diffusers, eta=0, epsilon prediction, no clipping; called at diffusion_wrapper.py:451):
+ *   eps = eps_u + s*(eps_c[:, v_c:] - eps_u)   (eps_u == NULL: eps = eps_c[:, v_c:])
+ *   x0  = (x_t - sqrt(1-a_t) eps) / sqrt(a_t);   x_prev = sqrt(a_prev) x0 + sqrt(1-a_prev) eps
+ * eps_c [B, v_c+v_t, chw], eps_u [B, v_t, chw] or NULL, x_t/x_prev [B, v_t, chw], all fp32. */
+int mvldm_ddim_step(void* stream, const float* eps_c, const float* eps_u, float cfg_scale, int B, int v_c,
+                    int v_t, int chw, const float* x_t, float sqrt_a_t, float sqrt_1m_a_t, float sqrt_a_prev,
+                    float sqrt_1m_a_prev, float* x_prev, float* eps_out /* may be NULL */);
+
+/* Replaces DiffusionWrapper.ray_encode / generate_image_rays (diffusion_wrapper.py:169-190,301-322) with
+ * get_world_rays / sample_image_grid (src/geometry/projection.py:91-138) for use_ray_encoding=false,
+ * srt_ray_encoding=false: extr [n,4,4] cam-to-world, intr [n,3,3] normalised (fp32, device);
+ * out [n,6,h,w] = origin (or origin x direction when plucker) then unit direction. */
+int mvldm_raymap(void* stream, const float* extr, const float* intr, int n_views, int h, int w, int plucker,
+                 float* out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Op-level entry points: the kernels behind mvldm_forward, exposed so tests can check each against
+ * the oracle.  bf16 tensors are raw uint16 device buffers in NHWC ([images, h, w, channels]).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* ptr;      /* bf16 NHWC source [n_img, sh, sw, ctot] */
+  int32_t c;            /* channels consumed per tap (multiple of 64 for the tcgen05 path) */
+  int32_t ctot;         /* channel count (row pitch) of the source tensor */
+  int32_t sh, sw;       /* source spatial size */
+  int32_t stride;       /* 1 or 2 */
+  int32_t ntaps;        /* 1 or 9 */
+  int8_t dh[9], dw[9];  /* tap t reads source pixel (oh*stride + dh[t], ow*stride + dw[t]), zero outside */
+  int32_t coff[9];      /* ... at channel coff[t] + c */
+} mvldm_aseg;
+
+typedef struct {
+  /* A (implicit): K = sum over segments of ntaps*c, ordered segment-major, tap, channel */
+  int32_t nseg;
+  mvldm_aseg seg[MVLDM_MAX_SEGS];
+  int32_t n_img, oh, ow;        /* M = n_img*oh*ow output pixels */
+  /* B: bf16 [N, K] row-major (K contiguous) */
+  const void* w;
+  int32_t n, k;
+  /* epilogue: acc + bias[n] + rowvec[img, n] + residual[m, n] */
+  const float* bias;            /* [N] or NULL */
+  const float* rowvec;          /* [n_img, rowvec_ld] or NULL */
+  int32_t rowvec_ld;
+  const void* residual;         /* bf16 [M, res_ld] or NULL */
+  int32_t res_ld;
+  int32_t mode;                 /* 0 bf16 [M,ldo]; 1 GEGLU (16-col interleave) -> bf16 [M, N/2]; 2 fp32 NCHW, n_valid channels */
+  void* out;
+  int32_t ldo;
+  int32_t n_valid;
+} mvldm_gemm_desc;
+
+int mvldm_op_gemm(void* stream, int impl, const mvldm_gemm_desc* d);
+
+/* Self-attention over packed, head-padded q|k|v: qkv bf16 [batches*seq, 3*heads*dpad] (q block, k block,
+ * v block; head h at columns h*dpad, first d of dpad valid), out bf16 [batches*seq, heads*dpad] (pad
+ * columns zero).  softmax(q k^T d^-1/2) v with fp32 scores (mvdream/attention.py:174-205). */
+int mvldm_op_attention(void* stream, int impl, const void* qkv, void* out, int batches, int seq, int heads,
+                       int d, int dpad);
+
+/* GroupNorm (+SiLU) over NHWC bf16, optionally over the channel concat of two sources
+ * (torch.cat at mvunet.py:176 + ResnetBlock2D.norm1): out bf16 [n_img, hw, c0+c1]. */
+int mvldm_op_groupnorm(void* stream, const void* x0, int c0, const void* x1, int c1, int n_img, int hw,
+                       int groups, float eps, const float* gamma, const float* beta, int silu, void* out,
+                       float* scratch /* >= n_img*groups*2*64 floats */);
+int mvldm_op_layernorm(void* stream, const void* x, int rows, int c, float eps, const float* gamma,
+                       const float* beta, void* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVLDM_B200_H_ */

@@ -1,0 +1,80 @@
+// Shared declarations for the mvldm_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/mvldm_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+namespace mvldm {
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+[[noreturn]] void fail(const char* file, int line, const std::string& msg);
+
+#define MV_CHECK(cond, msg)                                        \
+  do {                                                             \
+    if (!(cond)) ::mvldm::fail(__FILE__, __LINE__, std::string(msg)); \
+  } while (0)
+
+#define MV_CUDA(expr)                                                                       \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      ::mvldm::fail(__FILE__, __LINE__, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// launch counter (mvldm_last_launch_count): every kernel launch in this library goes through MV_LAUNCHED()
+extern thread_local int g_launch_count;
+#define MV_LAUNCHED()                 \
+  do {                                \
+    ++::mvldm::g_launch_count;        \
+    MV_CUDA(cudaPeekAtLastError());   \
+  } while (0)
+
+// ---- kernels (host launchers) -----------------------------------------------------------------
+// gemm_simt.cu / gemm_tc.cu
+void gemm_simt(cudaStream_t s, const mvldm_gemm_desc& d);
+void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d);
+// attn_simt.cu / attn_tc.cu
+void attention_simt(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, int heads, int d, int dpad);
+void attention_tc(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, int heads, int d, int dpad);
+
+// elementwise.cu
+void im2col_input(cudaStream_t s, const float* latents, int n_img, int cin, int h, int w, int kpad, bf16* out);
+void timestep_sinusoid(cudaStream_t s, const int64_t* t, int n, int dim, float* out);
+// out[r, n] = act(sum_k in[r,k] * W[n,k] + b[n]); in fp32 [rows, k], W bf16 [n, k]; act: 0 none, 1 silu
+void small_linear(cudaStream_t s, const float* in, int rows, int k, const bf16* w, const float* b, int n, int act,
+                  float* out);
+void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, int n_img, int hw, int groups,
+               float eps, const float* gamma, const float* beta, bool silu, bf16* out, float* scratch);
+size_t groupnorm_scratch_floats(int n_img, int groups);
+void layernorm(cudaStream_t s, const bf16* x, int rows, int c, float eps, const float* gamma, const float* beta,
+               bf16* out);
+void upsample_nearest2x(cudaStream_t s, const bf16* x, int n_img, int h, int w, int c, bf16* out);
+void nhwc_to_nchw_f32(cudaStream_t s, const bf16* x, int n_img, int hw, int c, float* out);
+void build_inputs(cudaStream_t s, const float* x_t, const float* ctx, const float* rays, int B, int v_c, int v_t,
+                  int ray_views, int ray_off, int R, int hw, float* out);
+void ddim_step(cudaStream_t s, const float* eps_c, const float* eps_u, float scale, int B, int v_c, int v_t, int chw,
+               const float* x_t, float sa, float s1a, float sp, float s1p, float* x_prev, float* eps_out);
+void raymap(cudaStream_t s, const float* extr, const float* intr, int n, int h, int w, bool plucker, float* out);
+// weight packing helpers (device side): dst bf16 [rows, ld]; all sources fp32
+void convert_f32(cudaStream_t s, const void* src, int dtype, int64_t n, float* dst);
+// dst[rowmap ? rowmap[r] : r, dst_col0 + j] = src[r, j]; rowmap is a device array of `rows` ints or NULL
+void pack_rows(cudaStream_t s, const float* src, int rows, int cols, int src_ld, bf16* dst, int dst_ld, int dst_col0,
+               const int* rowmap);
+void pack_conv3x3(cudaStream_t s, const float* w, int cout, int cin, int ks, bf16* dst, int dst_ld, int dst_col0);
+void fill_zero(cudaStream_t s, void* p, size_t bytes);
+
+}  // namespace mvldm

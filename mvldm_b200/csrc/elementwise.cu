@@ -1,0 +1,469 @@
+// HBM/L2-bound helper kernels of the MV-LDM hot path: input concat/im2col, timestep embedding,
+// GroupNorm(+SiLU), LayerNorm, nearest upsample, CFG+DDIM update, ray maps, weight packing.
+// All activations are bf16 NHWC ([image, h, w, channel]); statistics and scalars are fp32.
+#include "common.cuh"
+
+namespace mvldm {
+
+thread_local int g_launch_count = 0;
+
+namespace {
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+
+struct alignas(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void load8(const bf16* p, float* f) {
+  bf16x8 r = *reinterpret_cast<const bf16x8*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(r.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void store8(bf16* p, const float* f) {
+  bf16x8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<bf16x8*>(p) = r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// deterministic block sum (fixed shuffle tree, fixed warp order); result broadcast to all threads
+__device__ __forceinline__ float block_sum(float v, float* red /* >= 33 floats */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < nw ? red[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv_in operand: explicit im2col of the fp32 NCHW denoiser input (K1 + K3 of SURVEY.md §2.2).
+// out[m, tap*cin + c] = latents[img, c, y+r-1, x+s-1] (zero outside / for k >= 9*cin), m = (img, y, x)
+// ---------------------------------------------------------------------------------------------
+__global__ void im2col_input_kernel(const float* __restrict__ x, int n_img, int cin, int h, int w, int kpad,
+                                    bf16* __restrict__ out) {
+  const int64_t total = (int64_t)n_img * h * w * kpad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % kpad);
+    const int64_t m = i / kpad;
+    float v = 0.f;
+    if (k < 9 * cin) {
+      const int tap = k / cin, c = k - tap * cin;
+      const int px = (int)(m % w), py = (int)((m / w) % h), img = (int)(m / ((int64_t)w * h));
+      const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w) v = x[(((int64_t)img * cin + c) * h + yy) * w + xx];
+    }
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+// diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): [cos | sin], fp32
+__global__ void sinusoid_kernel(const int64_t* __restrict__ t, int n, int dim, float* __restrict__ out) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * half) return;
+  const int r = i / half, j = i - r * half;
+  const float freq = expf(-logf(10000.f) * (float)j / (float)half);
+  const float arg = (float)t[r] * freq;
+  out[(int64_t)r * dim + j] = cosf(arg);
+  out[(int64_t)r * dim + half + j] = sinf(arg);
+}
+
+// small-M linear: one warp per output column, weights streamed once with 16-byte loads.
+template <int RB>
+__global__ void small_linear_kernel(const float* __restrict__ in, int rows, int k, const bf16* __restrict__ w,
+                                    const float* __restrict__ b, int n, int act, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (col >= n) return;
+  const bf16* wr = w + (int64_t)col * k;
+  for (int r0 = 0; r0 < rows; r0 += RB) {
+    float acc[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) acc[r] = 0.f;
+    for (int kk = lane * 8; kk < k; kk += 256) {
+      float wf[8];
+      load8(wr + kk, wf);
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        if (r0 + r < rows) {
+          const float4 a0 = *reinterpret_cast<const float4*>(in + (int64_t)(r0 + r) * k + kk);
+          const float4 a1 = *reinterpret_cast<const float4*>(in + (int64_t)(r0 + r) * k + kk + 4);
+          acc[r] += a0.x * wf[0] + a0.y * wf[1] + a0.z * wf[2] + a0.w * wf[3] + a1.x * wf[4] + a1.y * wf[5] +
+                    a1.z * wf[6] + a1.w * wf[7];
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      float v = warp_sum(acc[r]);
+      if (lane == 0 && r0 + r < rows) {
+        v += b ? b[col] : 0.f;
+        if (act == 1) v = v / (1.f + expf(-v));
+        out[(int64_t)(r0 + r) * n + col] = v;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm.  Pass 1: one CTA per (image, group) -> (mean, rstd), two-pass variance, fixed reduction
+// order (bit-stable, no atomics).  Pass 2: elementwise normalise * gamma + beta (+SiLU), 16-byte vectors.
+// The two sources implement GroupNorm over torch.cat((hidden, skip), dim=1) without materialising the cat.
+// ---------------------------------------------------------------------------------------------
+__global__ void gn_stats_kernel(const bf16* __restrict__ x0, int c0, const bf16* __restrict__ x1, int c1, int hw,
+                                int groups, float eps, float* __restrict__ stats) {
+  __shared__ float red[33];
+  const int img = blockIdx.x / groups, g = blockIdx.x % groups;
+  const int C = c0 + c1, cg = C / groups;
+  const int cnt = hw * cg;
+  const int ch0 = g * cg;
+  auto at = [&](int idx) -> float {
+    const int p = idx / cg, c = ch0 + idx % cg;
+    return c < c0 ? __bfloat162float(x0[((int64_t)img * hw + p) * c0 + c])
+                  : __bfloat162float(x1[((int64_t)img * hw + p) * c1 + (c - c0)]);
+  };
+  float s = 0.f;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) s += at(i);
+  const float mean = block_sum(s, red) / (float)cnt;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const float d = at(i) - mean;
+    q += d * d;
+  }
+  const float var = block_sum(q, red) / (float)cnt;
+  if (threadIdx.x == 0) {
+    stats[2 * blockIdx.x] = mean;
+    stats[2 * blockIdx.x + 1] = rsqrtf(var + eps);
+  }
+}
+
+__global__ void gn_apply_kernel(const bf16* __restrict__ x0, int c0, const bf16* __restrict__ x1, int c1, int n_img,
+                                int hw, int groups, const float* __restrict__ stats, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int silu, bf16* __restrict__ out) {
+  const int C = c0 + c1, cg = C / groups, cv = C / 8;
+  const int64_t total = (int64_t)n_img * hw * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 8;
+    const int64_t pix = i / cv;
+    const int img = (int)(pix / hw);
+    float f[8];
+    if (c < c0)
+      load8(x0 + pix * c0 + c, f);
+    else
+      load8(x1 + pix * c1 + (c - c0), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c + j) / cg;
+      const float mean = stats[2 * (img * groups + g)], rstd = stats[2 * (img * groups + g) + 1];
+      float v = (f[j] - mean) * rstd * gamma[c + j] + beta[c + j];
+      f[j] = silu ? silu_f(v) : v;
+    }
+    store8(out + pix * C + c, f);
+  }
+}
+
+// LayerNorm over the channel dim, one warp per token, row cached in registers (C <= 32*8*MAXV).
+template <int MAXV>
+__global__ void layernorm_kernel(const bf16* __restrict__ x, int rows, int c, float eps, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, bf16* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nv = c / 8;
+  float f[MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nv) {
+      load8(x + (int64_t)row * c + v * 8, f[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[i][j];
+    }
+  }
+  const float mean = warp_sum(s) / (float)c;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (lane + 32 * i < nv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = f[i][j] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)c + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nv) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (f[i][j] - mean) * rstd * gamma[v * 8 + j] + beta[v * 8 + j];
+      store8(out + (int64_t)row * c + v * 8, o);
+    }
+  }
+}
+
+__global__ void upsample2x_kernel(const bf16* __restrict__ x, int n_img, int h, int w, int c, bf16* __restrict__ out) {
+  const int cv = c / 8;
+  const int64_t total = (int64_t)n_img * 4 * h * w * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    int64_t p = i / cv;
+    const int ox = (int)(p % (2 * w));
+    p /= 2 * w;
+    const int oy = (int)(p % (2 * h));
+    const int img = (int)(p / (2 * h));
+    const int4 val = *reinterpret_cast<const int4*>(x + (((int64_t)img * h + oy / 2) * w + ox / 2) * c + v * 8);
+    *reinterpret_cast<int4*>(out + i * 8) = val;
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, int n_img, int hw, int c, float* __restrict__ out) {
+  const int64_t total = (int64_t)n_img * hw * c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int p = (int)(i % hw);
+    const int ch = (int)((i / hw) % c);
+    const int img = (int)(i / ((int64_t)hw * c));
+    out[i] = __bfloat162float(x[((int64_t)img * hw + p) * c + ch]);
+  }
+}
+
+// inputs[b, v, :, p] = [latent(4) | mask | rays(R)], context views first (diffusion_wrapper.py:429-432)
+__global__ void build_inputs_kernel(const float* __restrict__ x_t, const float* __restrict__ ctx,
+                                    const float* __restrict__ rays, int B, int v_c, int v_t, int ray_views, int ray_off,
+                                    int R, int hw, float* __restrict__ out) {
+  const int V = v_c + v_t, C = 5 + R;
+  const int64_t total = (int64_t)B * V * C * hw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int p = (int)(i % hw);
+    const int ch = (int)((i / hw) % C);
+    const int v = (int)((i / ((int64_t)hw * C)) % V);
+    const int b = (int)(i / ((int64_t)hw * C * V));
+    float val;
+    if (ch < 4)
+      val = v < v_c ? ctx[(((int64_t)b * v_c + v) * 4 + ch) * hw + p] : x_t[(((int64_t)b * v_t + (v - v_c)) * 4 + ch) * hw + p];
+    else if (ch == 4)
+      val = v < v_c ? 0.f : 1.f;
+    else
+      val = rays[(((int64_t)b * ray_views + ray_off + v) * R + (ch - 5)) * hw + p];
+    out[i] = val;
+  }
+}
+
+// CFG compose + DDIM update (eta = 0, epsilon prediction), K14 + K15
+__global__ void ddim_step_kernel(const float* __restrict__ eps_c, const float* __restrict__ eps_u, float scale, int B,
+                                 int v_c, int v_t, int chw, const float* __restrict__ x_t, float sa, float s1a, float sp,
+                                 float s1p, float* __restrict__ x_prev, float* __restrict__ eps_out) {
+  const int64_t per_scene = (int64_t)v_t * chw;
+  const int64_t total = (int64_t)B * per_scene;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / per_scene, r = i - b * per_scene;
+    float e = eps_c[(b * (v_c + v_t) + v_c) * chw + r];
+    if (eps_u) {
+      const float u = eps_u[i];
+      e = u + scale * (e - u);
+    }
+    const float x = x_t[i];
+    const float x0 = (x - s1a * e) / sa;
+    x_prev[i] = sp * x0 + s1p * e;
+    if (eps_out) eps_out[i] = e;
+  }
+}
+
+// K17: pixel-centre grid -> K^-1 -> normalise -> rotate; origin broadcast; optional Pluecker moment
+__global__ void raymap_kernel(const float* __restrict__ extr, const float* __restrict__ intr, int n, int h, int w,
+                              int plucker, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * h * w) return;
+  const int p = i % (h * w), v = i / (h * w);
+  const float* K = intr + v * 9;
+  const float* E = extr + v * 16;
+  const float a = K[0], b = K[1], c = K[2], d = K[3], e = K[4], f = K[5], g = K[6], hh = K[7], k = K[8];
+  const float A = e * k - f * hh, Bc = -(d * k - f * g), Cc = d * hh - e * g;
+  const float det = a * A + b * Bc + c * Cc;
+  const float inv[9] = {A / det,  -(b * k - c * hh) / det, (b * f - c * e) / det,
+                        Bc / det, (a * k - c * g) / det,   -(a * f - c * d) / det,
+                        Cc / det, -(a * hh - b * g) / det, (a * e - b * d) / det};
+  const float px = ((float)(p % w) + 0.5f) / (float)w, py = ((float)(p / w) + 0.5f) / (float)h;
+  float dx = inv[0] * px + inv[1] * py + inv[2];
+  float dy = inv[3] * px + inv[4] * py + inv[5];
+  float dz = inv[6] * px + inv[7] * py + inv[8];
+  const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+  dx /= nrm; dy /= nrm; dz /= nrm;
+  const float wx = E[0] * dx + E[1] * dy + E[2] * dz;
+  const float wy = E[4] * dx + E[5] * dy + E[6] * dz;
+  const float wz = E[8] * dx + E[9] * dy + E[10] * dz;
+  float ox = E[3], oy = E[7], oz = E[11];
+  if (plucker) {
+    const float mx = oy * wz - oz * wy, my = oz * wx - ox * wz, mz = ox * wy - oy * wx;
+    ox = mx; oy = my; oz = mz;
+  }
+  float* o = out + (int64_t)v * 6 * h * w + p;
+  const int s = h * w;
+  o[0] = ox; o[s] = oy; o[2 * s] = oz; o[3 * s] = wx; o[4 * s] = wy; o[5 * s] = wz;
+}
+
+__global__ void convert_kernel(const void* __restrict__ src, int dtype, int64_t n, float* __restrict__ dst) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v;
+    if (dtype == MVLDM_F32) v = reinterpret_cast<const float*>(src)[i];
+    else if (dtype == MVLDM_BF16) v = __bfloat162float(reinterpret_cast<const bf16*>(src)[i]);
+    else v = __half2float(reinterpret_cast<const __half*>(src)[i]);
+    dst[i] = v;
+  }
+}
+
+// dst[rowmap ? rowmap[r] : r, dst_col0 + j] = src[r, j]
+__global__ void pack_rows_kernel(const float* __restrict__ src, int rows, int cols, int src_ld, bf16* __restrict__ dst,
+                                 int dst_ld, int dst_col0, const int* __restrict__ rowmap) {
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), j = (int)(i % cols);
+    const int dr = rowmap ? rowmap[r] : r;
+    dst[(int64_t)dr * dst_ld + dst_col0 + j] = __float2bfloat16(src[(int64_t)r * src_ld + j]);
+  }
+}
+
+// conv filter [cout, cin, ks, ks] -> dst[cout, dst_col0 + tap*cin + c]  (tap-major K, matches the implicit-GEMM A order)
+__global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin, int ks, bf16* __restrict__ dst,
+                                 int dst_ld, int dst_col0) {
+  const int taps = ks * ks;
+  const int64_t total = (int64_t)cout * cin * taps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cin);
+    const int tap = (int)((i / cin) % taps);
+    const int o = (int)(i / ((int64_t)cin * taps));
+    dst[(int64_t)o * dst_ld + dst_col0 + tap * cin + c] = __float2bfloat16(w[((int64_t)o * cin + c) * taps + tap]);
+  }
+}
+
+inline int grid_for(int64_t total, int threads) {
+  int64_t b = (total + threads - 1) / threads;
+  const int64_t cap = 148 * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+void im2col_input(cudaStream_t s, const float* latents, int n_img, int cin, int h, int w, int kpad, bf16* out) {
+  MV_CHECK(kpad >= 9 * cin, "im2col: kpad too small");
+  const int64_t total = (int64_t)n_img * h * w * kpad;
+  im2col_input_kernel<<<grid_for(total, 256), 256, 0, s>>>(latents, n_img, cin, h, w, kpad, out);
+  MV_LAUNCHED();
+}
+
+void timestep_sinusoid(cudaStream_t s, const int64_t* t, int n, int dim, float* out) {
+  const int total = n * (dim / 2);
+  sinusoid_kernel<<<ceil_div(total, 128), 128, 0, s>>>(t, n, dim, out);
+  MV_LAUNCHED();
+}
+
+void small_linear(cudaStream_t s, const float* in, int rows, int k, const bf16* w, const float* b, int n, int act,
+                  float* out) {
+  MV_CHECK(k % 8 == 0, "small_linear: K must be a multiple of 8");
+  small_linear_kernel<8><<<ceil_div(n, 8), 256, 0, s>>>(in, rows, k, w, b, n, act, out);
+  MV_LAUNCHED();
+}
+
+size_t groupnorm_scratch_floats(int n_img, int groups) { return (size_t)n_img * groups * 2; }
+
+void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, int n_img, int hw, int groups,
+               float eps, const float* gamma, const float* beta, bool silu, bf16* out, float* scratch) {
+  const int C = c0 + c1;
+  MV_CHECK(C % groups == 0, "groupnorm: channels not divisible by groups");
+  MV_CHECK(c0 % 8 == 0 && c1 % 8 == 0, "groupnorm: channel counts must be multiples of 8");
+  gn_stats_kernel<<<n_img * groups, 256, 0, s>>>(x0, c0, x1, c1, hw, groups, eps, scratch);
+  MV_LAUNCHED();
+  const int64_t total = (int64_t)n_img * hw * (C / 8);
+  gn_apply_kernel<<<grid_for(total, 256), 256, 0, s>>>(x0, c0, x1, c1, n_img, hw, groups, scratch, gamma, beta,
+                                                        silu ? 1 : 0, out);
+  MV_LAUNCHED();
+}
+
+void layernorm(cudaStream_t s, const bf16* x, int rows, int c, float eps, const float* gamma, const float* beta,
+               bf16* out) {
+  MV_CHECK(c % 8 == 0 && c <= 32 * 8 * 8, "layernorm: unsupported channel count");
+  const int warps = 8;
+  if (c <= 32 * 8 * 2)
+    layernorm_kernel<2><<<ceil_div(rows, warps), warps * 32, 0, s>>>(x, rows, c, eps, gamma, beta, out);
+  else if (c <= 32 * 8 * 5)
+    layernorm_kernel<5><<<ceil_div(rows, warps), warps * 32, 0, s>>>(x, rows, c, eps, gamma, beta, out);
+  else
+    layernorm_kernel<8><<<ceil_div(rows, warps), warps * 32, 0, s>>>(x, rows, c, eps, gamma, beta, out);
+  MV_LAUNCHED();
+}
+
+void upsample_nearest2x(cudaStream_t s, const bf16* x, int n_img, int h, int w, int c, bf16* out) {
+  MV_CHECK(c % 8 == 0, "upsample: channels must be a multiple of 8");
+  const int64_t total = (int64_t)n_img * 4 * h * w * (c / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, n_img, h, w, c, out);
+  MV_LAUNCHED();
+}
+
+void nhwc_to_nchw_f32(cudaStream_t s, const bf16* x, int n_img, int hw, int c, float* out) {
+  const int64_t total = (int64_t)n_img * hw * c;
+  nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, n_img, hw, c, out);
+  MV_LAUNCHED();
+}
+
+void build_inputs(cudaStream_t s, const float* x_t, const float* ctx, const float* rays, int B, int v_c, int v_t,
+                  int ray_views, int ray_off, int R, int hw, float* out) {
+  const int64_t total = (int64_t)B * (v_c + v_t) * (5 + R) * hw;
+  build_inputs_kernel<<<grid_for(total, 256), 256, 0, s>>>(x_t, ctx, rays, B, v_c, v_t, ray_views, ray_off, R, hw, out);
+  MV_LAUNCHED();
+}
+
+void ddim_step(cudaStream_t s, const float* eps_c, const float* eps_u, float scale, int B, int v_c, int v_t, int chw,
+               const float* x_t, float sa, float s1a, float sp, float s1p, float* x_prev, float* eps_out) {
+  const int64_t total = (int64_t)B * v_t * chw;
+  ddim_step_kernel<<<grid_for(total, 256), 256, 0, s>>>(eps_c, eps_u, scale, B, v_c, v_t, chw, x_t, sa, s1a, sp, s1p,
+                                                         x_prev, eps_out);
+  MV_LAUNCHED();
+}
+
+void raymap(cudaStream_t s, const float* extr, const float* intr, int n, int h, int w, bool plucker, float* out) {
+  raymap_kernel<<<ceil_div(n * h * w, 128), 128, 0, s>>>(extr, intr, n, h, w, plucker ? 1 : 0, out);
+  MV_LAUNCHED();
+}
+
+void convert_f32(cudaStream_t s, const void* src, int dtype, int64_t n, float* dst) {
+  convert_kernel<<<grid_for(n, 256), 256, 0, s>>>(src, dtype, n, dst);
+  MV_LAUNCHED();
+}
+
+void pack_rows(cudaStream_t s, const float* src, int rows, int cols, int src_ld, bf16* dst, int dst_ld, int dst_col0,
+               const int* rowmap) {
+  pack_rows_kernel<<<grid_for((int64_t)rows * cols, 256), 256, 0, s>>>(src, rows, cols, src_ld, dst, dst_ld, dst_col0,
+                                                                       rowmap);
+  MV_LAUNCHED();
+}
+
+void pack_conv3x3(cudaStream_t s, const float* w, int cout, int cin, int ks, bf16* dst, int dst_ld, int dst_col0) {
+  pack_conv_kernel<<<grid_for((int64_t)cout * cin * ks * ks, 256), 256, 0, s>>>(w, cout, cin, ks, dst, dst_ld, dst_col0);
+  MV_LAUNCHED();
+}
+
+void fill_zero(cudaStream_t s, void* p, size_t bytes) { MV_CUDA(cudaMemsetAsync(p, 0, bytes, s)); }
+
+}  // namespace mvldm

@@ -1,0 +1,316 @@
+// tcgen05 / TMEM / TMA implicit-GEMM for sm_100a: conv3x3 (stride 1/2), 1x1 conv and Linear over bf16 NHWC
+// activations, fp32 accumulation in tensor memory, fused epilogues (bias, per-image time-embedding row,
+// residual add, GEGLU, fp32-NCHW head output).
+//
+//   D[128 x BN] (TMEM, fp32) += A[128 x 64] (smem, K-major SW128) * W[BN x 64]^T (smem, K-major SW128)
+//
+// A is never materialised: for every (segment, filter tap, 64-channel block) one TMA box
+// [64 ch, bw, bh, bn] (bw*bh*bn = 128 output pixels) is fetched from the NHWC source at the tap's pixel
+// offset; out-of-image coordinates are zero-filled by the TMA unit, which is exactly the conv's zero
+// padding.  Stride-2 convs use the tensor map's traversal stride.  Up to three K-segments let one
+// accumulator take conv2(3x3) + the 1x1 shortcut over the (possibly concatenated) block input.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM owner + MMA issuer
+// (one elected lane), warps 2..5 = epilogue (each owns the 32 TMEM lanes of its warp%4 quarter).
+// Pipelines: smem full/empty ring of mbarriers (TMA <-> MMA), one accumulator-ready mbarrier (MMA -> epilogue).
+// Two CTAs fit per SM, so one CTA's epilogue overlaps the other's main loop.
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace mvldm {
+
+CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                           const uint32_t* box, const uint32_t* elem_strides) {
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  });
+  MV_CHECK(encode != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  CUtensorMap m;
+  CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                      strides_bytes, box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MV_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return m;
+}
+
+namespace {
+
+constexpr int BM = 128, BK = 64;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+
+struct TcSeg {
+  int ncblk, ntaps, stride;
+  int dh[9], dw[9], coff[9];
+};
+
+struct TcParams {
+  CUtensorMap tmA[MVLDM_MAX_SEGS];
+  CUtensorMap tmB;
+  TcSeg seg[MVLDM_MAX_SEGS];
+  int nseg;
+  int M, N, num_kb;
+  int hw, ow;  // output pixels per image / row width (tile -> image coordinates)
+  const float* bias;
+  const float* rowvec;
+  int rowvec_ld;
+  const bf16* residual;
+  int res_ld;
+  int mode;
+  void* out;
+  int ldo, n_valid;
+};
+
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[STAGES];
+  __shared__ __align__(8) uint64_t bar_accum;
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-B alignment
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.nseg; ++i) tc::tma_prefetch_desc(&p.tmA[i]);
+    tc::tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(tc::smem_u32(&bar_full[s]), 1);
+      tc::mbar_init(tc::smem_u32(&bar_empty[s]), 1);
+    }
+    tc::mbar_init(tc::smem_u32(&bar_accum), 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tc::smem_u32(&tmem_base_slot));
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_d = tmem_base_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const int img0 = m0 / p.hw;
+      const int y0 = (m0 - img0 * p.hw) / p.ow;
+      int kb = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const TcSeg& sg = p.seg[s];
+        for (int t = 0; t < sg.ntaps; ++t) {
+          for (int cb = 0; cb < sg.ncblk; ++cb, ++kb) {
+            const int stage = kb % STAGES;
+            const uint32_t par = ((kb / STAGES) & 1) ^ 1;
+            tc::mbar_wait(tc::smem_u32(&bar_empty[stage]), par);
+            const uint32_t full = tc::smem_u32(&bar_full[stage]);
+            tc::mbar_expect_tx(full, STAGE_BYTES);
+            const uint32_t sa = smem_base + stage * STAGE_BYTES;
+            tc::tma_load_4d(sa, &p.tmA[s], full, sg.coff[t] + cb * BK, sg.dw[t], y0 * sg.stride + sg.dh[t], img0);
+            tc::tma_load_2d(sa + A_BYTES, &p.tmB, full, kb * BK, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::umma_idesc_bf16(BM, BN, false, false);
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int stage = kb % STAGES;
+        tc::mbar_wait(tc::smem_u32(&bar_full[stage]), (kb / STAGES) & 1);
+        tc::tc_fence_after();
+        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+        const uint64_t adesc = tc::umma_desc_k_sw128(sa);
+        const uint64_t bdesc = tc::umma_desc_k_sw128(sa + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)  // +32 bytes (=2 in descriptor units) per K=16 slice inside the swizzle atom
+          tc::umma_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        tc::umma_commit(tc::smem_u32(&bar_empty[stage]));  // frees the smem slot when these MMAs retire
+      }
+      tc::umma_commit(tc::smem_u32(&bar_accum));
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue =================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    const bool ok = m < p.M;
+    const int img = m / p.hw;
+    tc::mbar_wait(tc::smem_u32(&bar_accum), 0);
+    tc::tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      __syncwarp();
+      tc::tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + c0, r);
+      tc::tmem_ld_wait();
+      if (ok) {
+      const int n = n0 + c0;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(p.bias + n + j);
+          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+      }
+      if (p.rowvec) {
+        const float* rv = p.rowvec + (int64_t)img * p.rowvec_ld + n;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(rv + j);
+          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+      }
+      if (p.mode == 0) {
+        if (p.residual) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (int64_t)m * p.res_ld + n);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 u = rp[j];
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+              v[j * 8 + e * 2] += f.x;
+              v[j * 8 + e * 2 + 1] += f.y;
+            }
+          }
+        }
+        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (int64_t)m * p.ldo + n);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          op[j] = make_uint4(pack_bf16(v[j * 8], v[j * 8 + 1]), pack_bf16(v[j * 8 + 2], v[j * 8 + 3]),
+                             pack_bf16(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16(v[j * 8 + 6], v[j * 8 + 7]));
+      } else if (p.mode == 1) {
+        // columns [0,16) = values, [16,32) = gates of the same 16 hidden channels
+        float g[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) g[j] = v[j] * gelu_exact(v[16 + j]);
+        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (int64_t)m * p.ldo + n / 2);
+        op[0] = make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]), pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7]));
+        op[1] = make_uint4(pack_bf16(g[8], g[9]), pack_bf16(g[10], g[11]), pack_bf16(g[12], g[13]), pack_bf16(g[14], g[15]));
+      } else {
+        const int pix = m - img * p.hw;
+        float* op = reinterpret_cast<float*>(p.out) + (int64_t)img * p.n_valid * p.hw + pix;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n + j < p.n_valid) op[(int64_t)(n + j) * p.hw] = v[j];
+      }
+      }
+    }
+    tc::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<TMEM_COLS>(tmem_d);
+  }
+}
+
+template <int BN, int STAGES>
+void launch(cudaStream_t s, const TcParams& p) {
+  constexpr int smem = STAGES * (A_BYTES + BN * BK * 2) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    MV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid(ceil_div(p.M, BM), p.N / BN);
+  gemm_tc_kernel<BN, STAGES><<<grid, 192, smem, s>>>(p);
+  MV_LAUNCHED();
+}
+
+}  // namespace
+
+void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d) {
+  TcParams p{};
+  const int hw = d.oh * d.ow;
+  p.M = d.n_img * hw;
+  p.N = d.n;
+  p.hw = hw;
+  p.ow = d.ow;
+  MV_CHECK(d.nseg >= 1 && d.nseg <= MVLDM_MAX_SEGS, "gemm_tc: bad segment count");
+  MV_CHECK(d.ow <= BM && BM % d.ow == 0, "gemm_tc: output width must divide 128");
+  MV_CHECK(hw % BM == 0 || BM % hw == 0, "gemm_tc: pixels per image must divide or be a multiple of 128");
+  // 128-pixel tile = bw x bh x bn box of whole rows / whole images
+  const int bw = d.ow;
+  const int bh = std::min(d.oh, BM / bw);
+  const int bn = BM / (bw * bh);
+  int ktot = 0;
+  for (int i = 0; i < d.nseg; ++i) {
+    const mvldm_aseg& a = d.seg[i];
+    MV_CHECK(a.c % BK == 0 && a.ctot % 8 == 0, "gemm_tc: segment channels must be a multiple of 64");
+    MV_CHECK(a.stride == 1 || a.stride == 2, "gemm_tc: stride must be 1 or 2");
+    MV_CHECK(a.sh == d.oh * a.stride && a.sw == d.ow * a.stride, "gemm_tc: source / output size mismatch");
+    MV_CHECK((reinterpret_cast<uintptr_t>(a.ptr) & 15) == 0, "gemm_tc: source pointer must be 16-byte aligned");
+    TcSeg& t = p.seg[i];
+    t.ncblk = a.c / BK;
+    t.ntaps = a.ntaps;
+    t.stride = a.stride;
+    for (int j = 0; j < a.ntaps; ++j) {
+      t.dh[j] = a.dh[j];
+      t.dw[j] = a.dw[j];
+      t.coff[j] = a.coff[j];
+      MV_CHECK(a.coff[j] % 8 == 0, "gemm_tc: tap channel offset must be a multiple of 8");
+    }
+    const uint64_t dims[4] = {(uint64_t)a.ctot, (uint64_t)a.sw, (uint64_t)a.sh, (uint64_t)d.n_img};
+    const uint64_t strides[3] = {(uint64_t)a.ctot * 2, (uint64_t)a.sw * a.ctot * 2, (uint64_t)a.sh * a.sw * a.ctot * 2};
+    const uint32_t box[4] = {(uint32_t)BK, (uint32_t)(bw * a.stride), (uint32_t)(bh * a.stride), (uint32_t)bn};
+    const uint32_t es[4] = {1, (uint32_t)a.stride, (uint32_t)a.stride, 1};
+    p.tmA[i] = make_tmap_bf16(a.ptr, 4, dims, strides, box, es);
+    ktot += a.c * a.ntaps;
+  }
+  p.nseg = d.nseg;
+  MV_CHECK(ktot == d.k, "gemm_tc: K mismatch between segments and weights");
+  p.num_kb = d.k / BK;
+  int BN = 0;
+  if (d.n % 128 == 0) BN = 128;
+  else if (d.n % 64 == 0) BN = 64;
+  else if (d.n % 32 == 0) BN = 32;
+  MV_CHECK(BN != 0, "gemm_tc: N must be a multiple of 32");
+  MV_CHECK(d.mode != 2 || d.n == 32, "gemm_tc: NCHW head output expects N padded to 32");
+  {
+    const uint64_t dims[2] = {(uint64_t)d.k, (uint64_t)d.n};
+    const uint64_t strides[1] = {(uint64_t)d.k * 2};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+    const uint32_t es[2] = {1, 1};
+    p.tmB = make_tmap_bf16(d.w, 2, dims, strides, box, es);
+  }
+  p.bias = d.bias;
+  p.rowvec = d.rowvec;
+  p.rowvec_ld = d.rowvec_ld;
+  p.residual = reinterpret_cast<const bf16*>(d.residual);
+  p.res_ld = d.res_ld;
+  p.mode = d.mode;
+  p.out = d.out;
+  p.ldo = d.ldo;
+  p.n_valid = d.n_valid;
+  if (d.mode == 0) MV_CHECK(d.ldo % 8 == 0 && (!d.residual || d.res_ld % 8 == 0), "gemm_tc: row pitch must be a multiple of 8");
+  if (BN == 128) launch<128, 3>(s, p);
+  else if (BN == 64) launch<64, 4>(s, p);
+  else launch<32, 4>(s, p);
+}
+
+}  // namespace mvldm

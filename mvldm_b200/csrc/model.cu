@@ -1,0 +1,884 @@
+// MultiViewUNet (Variant A) forward on B200: weight registry + packing, activation arena, and the
+// straight-line launch sequence that replaces reference src/model/denoiser/mvunet.py:90-208 and
+// src/model/denoiser/mvdream/attention.py:357-439 (+ diffusers ResnetBlock2D / Down/Upsample2D /
+// Timesteps / TimestepEmbedding).
+//
+// Data layout in HBM: every activation is bf16 NHWC [image=(scene,view), h, w, C], i.e. a row-major
+// [tokens, C] matrix, so conv3x3 / 1x1 / Linear are all `tokens x K` by `K x N` GEMMs (gemm_tc.cu) and the
+// "b c h w -> b (h w) c" rearranges of the reference are no-ops.  Weights are bf16 [N, K] (K contiguous,
+// tap-major for 3x3 filters).  Statistics, biases, time embeddings and the softmax are fp32.
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mvldm {
+
+namespace {
+thread_local std::string g_last_error;
+}
+
+void fail(const char* file, int line, const std::string& msg) {
+  throw Error(std::string(file) + ":" + std::to_string(line) + ": " + msg);
+}
+
+__global__ void vec_add_kernel(float* dst, const float* a, const float* b, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = a[i] + (b ? b[i] : 0.f);
+}
+
+struct DevBuf {  // owning device allocation
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  explicit DevBuf(size_t n) { alloc(n); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  void alloc(size_t n) {
+    release();
+    if (n) MV_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+struct Act {  // bf16 NHWC activation view
+  bf16* p = nullptr;
+  int n = 0, h = 0, w = 0, c = 0;
+  int64_t tokens() const { return (int64_t)n * h * w; }
+};
+
+struct Packed {  // bf16 [n, k] weight + fp32 bias
+  bf16* w = nullptr;
+  float* bias = nullptr;
+  int n = 0, k = 0;
+};
+
+struct ResnetW {
+  std::string key;
+  int cin = 0, cout = 0, temb_off = 0;
+  bool shortcut = false;
+  const float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr;
+  Packed conv1, conv2;  // conv2 carries the 1x1 shortcut as extra K columns when present
+};
+
+struct MvW {
+  std::string key;
+  int c = 0, d = 0, dpad = 0;
+  const float *gn_g = nullptr, *gn_b = nullptr, *ln_g[3] = {}, *ln_b[3] = {};
+  Packed proj_in, qkv1, out1, qkv2, out2, ff1, ff2, proj_out;
+};
+
+struct Arena {
+  char* base = nullptr;
+  size_t off = 0, cap = 0, peak = 0;
+  bool measuring = true;
+  void* take(size_t bytes) {
+    bytes = (bytes + 1023) & ~size_t(1023);  // 1 KB granularity keeps every buffer TMA/UMMA aligned
+    void* r = measuring ? reinterpret_cast<void*>(size_t(0x100000) + off) : (void*)(base + off);
+    off += bytes;
+    if (off > peak) peak = off;
+    if (!measuring) MV_CHECK(off <= cap, "activation arena overflow");
+    return r;
+  }
+};
+
+struct Plan {
+  int B = 0, V = 0, H = 0, W = 0;
+  DevBuf arena_mem;
+  size_t arena_bytes = 0;
+  DevBuf in_latents, in_t, out_eps;
+  cudaGraphExec_t graph = nullptr;
+  int graph_launches = 0;
+  ~Plan() {
+    if (graph) cudaGraphExecDestroy(graph);
+  }
+};
+
+struct TapRec {
+  Act a;
+};
+
+}  // namespace mvldm
+
+using namespace mvldm;
+
+struct mvldm_handle_s {
+  mvldm_config cfg{};
+  int device = 0;
+  int temb_dim = 0, temb_total = 0;
+  bool finalized = false;
+
+  // registry
+  std::vector<std::string> names;
+  std::map<std::string, std::vector<int64_t>> shapes;
+  std::map<std::string, std::unique_ptr<DevBuf>> raw;  // fp32 copies of the state dict
+  std::vector<std::unique_ptr<DevBuf>> packed_store;
+
+  // packed layers
+  Packed conv_in, conv_out, time1, time2, temb_all;
+  std::vector<std::vector<ResnetW>> down_res, up_res;
+  ResnetW mid_res;
+  std::vector<Packed> down_conv, up_conv;
+  std::vector<MvW> mv_enc, mv_dec;
+  MvW mv_mid;
+  const float *norm_out_g = nullptr, *norm_out_b = nullptr;
+  int kpad_in = 0;
+
+  std::map<std::vector<int>, std::unique_ptr<Plan>> plans;
+  int last_launches = 0;
+  bool taps_enabled = false;
+  std::map<std::string, TapRec> taps;
+
+  // ---- run state ----
+  cudaStream_t stream = nullptr;
+  Arena arena;
+  bool dry = true;
+
+  // =========================== registry ===========================
+  void reg(const std::string& k, std::vector<int64_t> shape) {
+    names.push_back(k);
+    shapes[k] = std::move(shape);
+  }
+  void reg_conv(const std::string& k, int cout, int cin, int ks) {
+    reg(k + ".weight", {cout, cin, ks, ks});
+    reg(k + ".bias", {cout});
+  }
+  void reg_lin(const std::string& k, int cout, int cin, bool bias = true) {
+    reg(k + ".weight", {cout, cin});
+    if (bias) reg(k + ".bias", {cout});
+  }
+  void reg_norm(const std::string& k, int c) {
+    reg(k + ".weight", {c});
+    reg(k + ".bias", {c});
+  }
+  ResnetW reg_resnet(const std::string& k, int cin, int cout) {
+    reg_norm(k + ".norm1", cin);
+    reg_conv(k + ".conv1", cout, cin, 3);
+    reg_lin(k + ".time_emb_proj", cout, temb_dim);
+    reg_norm(k + ".norm2", cout);
+    reg_conv(k + ".conv2", cout, cout, 3);
+    if (cin != cout) reg_conv(k + ".conv_shortcut", cout, cin, 1);
+    ResnetW r;
+    r.key = k;
+    r.cin = cin;
+    r.cout = cout;
+    r.shortcut = cin != cout;
+    r.temb_off = temb_total;
+    temb_total += cout;
+    return r;
+  }
+  MvW reg_mv(const std::string& k, int c) {
+    reg_norm(k + ".norm", c);
+    reg_conv(k + ".proj_in", c, c, 1);
+    const std::string tb = k + ".transformer_blocks.0";
+    for (const char* a : {"attn1", "attn2"}) {
+      reg_lin(tb + "." + a + ".to_q", c, c, false);
+      reg_lin(tb + "." + a + ".to_k", c, c, false);
+      reg_lin(tb + "." + a + ".to_v", c, c, false);
+      reg_lin(tb + "." + a + ".to_out.0", c, c);
+    }
+    reg_lin(tb + ".ff.net.0.proj", 8 * c, c);
+    reg_lin(tb + ".ff.net.2", c, 4 * c);
+    for (const char* n : {"norm1", "norm2", "norm3"}) reg_norm(tb + "." + n, c);
+    reg_conv(k + ".proj_out", c, c, 1);
+    MvW m;
+    m.key = k;
+    m.c = c;
+    MV_CHECK(c % cfg.num_heads == 0, "channels not divisible by num_heads");
+    m.d = c / cfg.num_heads;
+    m.dpad = (m.d + 63) / 64 * 64;
+    MV_CHECK(m.dpad <= 192, "head dim > 192 unsupported");
+    return m;
+  }
+
+  void build_registry() {
+    const int L = cfg.num_levels;
+    const int* boc = cfg.block_out_channels;
+    temb_dim = boc[0] * 4;
+    reg_conv("unet.conv_in", boc[0], cfg.in_channels, 3);
+    reg_lin("unet.time_embedding.linear_1", temb_dim, boc[0]);
+    reg_lin("unet.time_embedding.linear_2", temb_dim, temb_dim);
+    int cout = boc[0];
+    down_res.resize(L);
+    up_res.resize(L);
+    for (int l = 0; l < L; ++l) {
+      const int cin = cout;
+      cout = boc[l];
+      for (int i = 0; i < cfg.layers_per_block; ++i)
+        down_res[l].push_back(reg_resnet("unet.down_blocks." + std::to_string(l) + ".resnets." + std::to_string(i),
+                                         i == 0 ? cin : cout, cout));
+      if (l != L - 1) reg_conv("unet.down_blocks." + std::to_string(l) + ".downsamplers.0.conv", cout, cout, 3);
+    }
+    mid_res = reg_resnet("unet.mid_block.resnets.0", boc[L - 1], boc[L - 1]);
+    int out_c = boc[L - 1];
+    for (int l = 0; l < L; ++l) {
+      const int prev = out_c;
+      out_c = boc[L - 1 - l];
+      const int in_c = boc[L - 1 - std::min(l + 1, L - 1)];
+      for (int i = 0; i < cfg.layers_per_block + 1; ++i) {
+        const int skip = (i == cfg.layers_per_block) ? in_c : out_c;
+        const int rin = (i == 0) ? prev : out_c;
+        up_res[l].push_back(reg_resnet("unet.up_blocks." + std::to_string(l) + ".resnets." + std::to_string(i),
+                                       rin + skip, out_c));
+      }
+      if (l != L - 1) reg_conv("unet.up_blocks." + std::to_string(l) + ".upsamplers.0.conv", out_c, out_c, 3);
+    }
+    reg_norm("unet.conv_norm_out", boc[0]);
+    reg_conv("unet.conv_out", cfg.out_channels, boc[0], 3);
+    for (int l = 0; l < L; ++l) mv_enc.push_back(reg_mv("cross_attn_blocks_encoder." + std::to_string(l), boc[l]));
+    mv_mid = reg_mv("cross_attn_blocks_mid.0", boc[L - 1]);
+    for (int l = 0; l < L; ++l) mv_dec.push_back(reg_mv("cross_attn_blocks_decoder." + std::to_string(l), boc[L - 1 - l]));
+  }
+
+  // =========================== packing ===========================
+  const float* rawf(const std::string& k) {
+    auto it = raw.find(k);
+    MV_CHECK(it != raw.end(), "weight not set: " + k);
+    return reinterpret_cast<const float*>(it->second->p);
+  }
+  template <class T>
+  T* store(size_t count) {
+    packed_store.emplace_back(new DevBuf(count * sizeof(T)));
+    MV_CUDA(cudaMemsetAsync(packed_store.back()->p, 0, count * sizeof(T), stream));
+    return reinterpret_cast<T*>(packed_store.back()->p);
+  }
+  float* bias_sum(const std::string& a, const std::string& b, int n, int npad = 0) {
+    float* dst = store<float>(std::max(n, npad));
+    vec_add_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(dst, rawf(a), b.empty() ? nullptr : rawf(b), n);
+    MV_LAUNCHED();
+    return dst;
+  }
+  const int* upload_map(const std::vector<int>& m) {
+    int* d = store<int>(m.size());
+    MV_CUDA(cudaMemcpyAsync(d, m.data(), m.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    MV_CUDA(cudaStreamSynchronize(stream));  // m may be a temporary
+    return d;
+  }
+  Packed pack_conv(const std::string& k, int cout, int cin, int ks, int extra_k = 0, int npad = 0) {
+    Packed p;
+    p.n = std::max(cout, npad);
+    p.k = ks * ks * cin + extra_k;
+    p.w = store<bf16>((size_t)p.n * p.k);
+    pack_conv3x3(stream, rawf(k + ".weight"), cout, cin, ks, p.w, p.k, 0);
+    p.bias = bias_sum(k + ".bias", "", cout, p.n);
+    return p;
+  }
+  Packed pack_linear(const std::string& k, int n, int kk, bool bias) {
+    Packed p;
+    p.n = n;
+    p.k = kk;
+    p.w = store<bf16>((size_t)n * kk);
+    pack_rows(stream, rawf(k + ".weight"), n, kk, kk, p.w, kk, 0, nullptr);
+    if (bias) p.bias = bias_sum(k + ".bias", "", n);
+    return p;
+  }
+  void pack_resnet(ResnetW& r) {
+    r.g1 = rawf(r.key + ".norm1.weight");
+    r.b1 = rawf(r.key + ".norm1.bias");
+    r.g2 = rawf(r.key + ".norm2.weight");
+    r.b2 = rawf(r.key + ".norm2.bias");
+    r.conv1 = pack_conv(r.key + ".conv1", r.cout, r.cin, 3);
+    if (r.shortcut) {
+      r.conv2 = pack_conv(r.key + ".conv2", r.cout, r.cout, 3, r.cin);
+      pack_rows(stream, rawf(r.key + ".conv_shortcut.weight"), r.cout, r.cin, r.cin, r.conv2.w, r.conv2.k, 9 * r.cout,
+                nullptr);
+      r.conv2.bias = bias_sum(r.key + ".conv2.bias", r.key + ".conv_shortcut.bias", r.cout);
+    } else {
+      r.conv2 = pack_conv(r.key + ".conv2", r.cout, r.cout, 3);
+    }
+    // rows [temb_off, temb_off + cout) of the batched time_emb_proj
+    pack_rows(stream, rawf(r.key + ".time_emb_proj.weight"), r.cout, temb_dim, temb_dim,
+              temb_all.w + (size_t)r.temb_off * temb_dim, temb_dim, 0, nullptr);
+    MV_CUDA(cudaMemcpyAsync(temb_all.bias + r.temb_off, rawf(r.key + ".time_emb_proj.bias"), r.cout * sizeof(float),
+                            cudaMemcpyDeviceToDevice, stream));
+  }
+  Packed pack_qkv(const std::string& a, const MvW& m) {
+    const int H = cfg.num_heads;
+    Packed p;
+    p.n = 3 * H * m.dpad;
+    p.k = m.c;
+    p.w = store<bf16>((size_t)p.n * p.k);
+    const char* which[3] = {".to_q", ".to_k", ".to_v"};
+    for (int t = 0; t < 3; ++t) {
+      std::vector<int> map(m.c);
+      for (int r = 0; r < m.c; ++r) map[r] = (t * H + r / m.d) * m.dpad + r % m.d;
+      pack_rows(stream, rawf(a + which[t] + ".weight"), m.c, m.c, m.c, p.w, p.k, 0, upload_map(map));
+    }
+    return p;
+  }
+  Packed pack_attn_out(const std::string& a, const MvW& m) {
+    const int H = cfg.num_heads;
+    Packed p;
+    p.n = m.c;
+    p.k = H * m.dpad;
+    p.w = store<bf16>((size_t)p.n * p.k);
+    for (int h = 0; h < H; ++h)
+      pack_rows(stream, rawf(a + ".to_out.0.weight") + h * m.d, m.c, m.d, m.c, p.w, p.k, h * m.dpad, nullptr);
+    p.bias = bias_sum(a + ".to_out.0.bias", "", m.c);
+    return p;
+  }
+  void pack_mv(MvW& m) {
+    const std::string tb = m.key + ".transformer_blocks.0";
+    m.gn_g = rawf(m.key + ".norm.weight");
+    m.gn_b = rawf(m.key + ".norm.bias");
+    const char* ln[3] = {".norm1", ".norm2", ".norm3"};
+    for (int i = 0; i < 3; ++i) {
+      m.ln_g[i] = rawf(tb + ln[i] + ".weight");
+      m.ln_b[i] = rawf(tb + ln[i] + ".bias");
+    }
+    m.proj_in = pack_conv(m.key + ".proj_in", m.c, m.c, 1);
+    m.proj_out = pack_conv(m.key + ".proj_out", m.c, m.c, 1);
+    m.qkv1 = pack_qkv(tb + ".attn1", m);
+    m.out1 = pack_attn_out(tb + ".attn1", m);
+    m.qkv2 = pack_qkv(tb + ".attn2", m);
+    m.out2 = pack_attn_out(tb + ".attn2", m);
+    // GEGLU: interleave value / gate rows in blocks of 16 so one 32-column accumulator chunk holds both
+    const int c4 = 4 * m.c;
+    m.ff1.n = 2 * c4;
+    m.ff1.k = m.c;
+    m.ff1.w = store<bf16>((size_t)m.ff1.n * m.ff1.k);
+    std::vector<int> map(2 * c4);
+    for (int ch = 0; ch < c4; ++ch) {
+      map[ch] = (ch / 16) * 32 + ch % 16;
+      map[c4 + ch] = (ch / 16) * 32 + 16 + ch % 16;
+    }
+    pack_rows(stream, rawf(tb + ".ff.net.0.proj.weight"), 2 * c4, m.c, m.c, m.ff1.w, m.c, 0, upload_map(map));
+    {
+      std::vector<float> hb(2 * c4), pb(2 * c4);
+      MV_CUDA(cudaMemcpyAsync(hb.data(), rawf(tb + ".ff.net.0.proj.bias"), hb.size() * sizeof(float),
+                              cudaMemcpyDeviceToHost, stream));
+      MV_CUDA(cudaStreamSynchronize(stream));
+      for (int i = 0; i < 2 * c4; ++i) pb[map[i]] = hb[i];
+      m.ff1.bias = store<float>(2 * c4);
+      MV_CUDA(cudaMemcpyAsync(m.ff1.bias, pb.data(), pb.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+      MV_CUDA(cudaStreamSynchronize(stream));
+    }
+    m.ff2 = pack_linear(tb + ".ff.net.2", m.c, c4, true);
+  }
+
+  void finalize(cudaStream_t s) {
+    stream = s;
+    for (auto& n : names) MV_CHECK(raw.count(n), "mvldm_finalize_weights: missing weight " + n);
+    MV_CUDA(cudaStreamSynchronize(s));
+    packed_store.clear();
+    const int L = cfg.num_levels;
+    const int* boc = cfg.block_out_channels;
+    kpad_in = (9 * cfg.in_channels + 63) / 64 * 64;
+    {  // conv_in on the explicit im2col operand, K padded to a multiple of 64
+      conv_in.n = boc[0];
+      conv_in.k = kpad_in;
+      conv_in.w = store<bf16>((size_t)conv_in.n * conv_in.k);
+      pack_conv3x3(stream, rawf("unet.conv_in.weight"), boc[0], cfg.in_channels, 3, conv_in.w, conv_in.k, 0);
+      conv_in.bias = bias_sum("unet.conv_in.bias", "", boc[0]);
+    }
+    conv_out = pack_conv("unet.conv_out", cfg.out_channels, boc[0], 3, 0, 32);
+    time1 = pack_linear("unet.time_embedding.linear_1", temb_dim, boc[0], true);
+    time2 = pack_linear("unet.time_embedding.linear_2", temb_dim, temb_dim, true);
+    temb_all.n = temb_total;
+    temb_all.k = temb_dim;
+    temb_all.w = store<bf16>((size_t)temb_total * temb_dim);
+    temb_all.bias = store<float>(temb_total);
+    for (auto& lv : down_res)
+      for (auto& r : lv) pack_resnet(r);
+    pack_resnet(mid_res);
+    for (auto& lv : up_res)
+      for (auto& r : lv) pack_resnet(r);
+    down_conv.clear();
+    up_conv.clear();
+    for (int l = 0; l < L - 1; ++l) {
+      down_conv.push_back(pack_conv("unet.down_blocks." + std::to_string(l) + ".downsamplers.0.conv", boc[l], boc[l], 3));
+      up_conv.push_back(pack_conv("unet.up_blocks." + std::to_string(l) + ".upsamplers.0.conv", boc[L - 1 - l],
+                                  boc[L - 1 - l], 3));
+    }
+    for (auto& m : mv_enc) pack_mv(m);
+    pack_mv(mv_mid);
+    for (auto& m : mv_dec) pack_mv(m);
+    norm_out_g = rawf("unet.conv_norm_out.weight");
+    norm_out_b = rawf("unet.conv_norm_out.bias");
+    MV_CUDA(cudaStreamSynchronize(s));
+    // keep only the norm affine params of the fp32 copies
+    for (auto it = raw.begin(); it != raw.end();) {
+      const std::string& k = it->first;
+      const bool keep = k.find("norm") != std::string::npos;
+      it = keep ? std::next(it) : raw.erase(it);
+    }
+    plans.clear();
+    finalized = true;
+  }
+
+  // =========================== forward ===========================
+  Act new_act(int n, int h, int w, int c) {
+    Act a;
+    a.n = n; a.h = h; a.w = w; a.c = c;
+    a.p = reinterpret_cast<bf16*>(arena.take((size_t)a.tokens() * c * sizeof(bf16)));
+    return a;
+  }
+  float* new_f32(size_t count) { return reinterpret_cast<float*>(arena.take(count * sizeof(float))); }
+  void tap(const std::string& name, const Act& a) {
+    if (taps_enabled && !dry) taps[name].a = a;
+  }
+
+  static mvldm_aseg seg_conv3x3(const Act& a, int stride = 1) {
+    mvldm_aseg s{};
+    s.ptr = a.p; s.c = a.c; s.ctot = a.c; s.sh = a.h; s.sw = a.w; s.stride = stride; s.ntaps = 9;
+    for (int t = 0; t < 9; ++t) {
+      s.dh[t] = (int8_t)(t / 3 - 1);
+      s.dw[t] = (int8_t)(t % 3 - 1);
+      s.coff[t] = 0;
+    }
+    return s;
+  }
+  static mvldm_aseg seg_1x1(const Act& a) {
+    mvldm_aseg s{};
+    s.ptr = a.p; s.c = a.c; s.ctot = a.c; s.sh = a.h; s.sw = a.w; s.stride = 1; s.ntaps = 1;
+    return s;
+  }
+  void run_gemm(mvldm_gemm_desc& d) {
+    if (dry) return;
+    if (cfg.impl == MVLDM_IMPL_TC) gemm_tc(stream, d);
+    else gemm_simt(stream, d);
+  }
+  // out = A-segments x W^T (+bias +rowvec +residual), bf16 NHWC
+  void gemm(std::initializer_list<mvldm_aseg> segs, const Packed& w, const Act& out, const float* rowvec = nullptr,
+            int rowvec_ld = 0, const Act* residual = nullptr, int mode = 0) {
+    mvldm_gemm_desc d{};
+    for (const auto& s : segs) d.seg[d.nseg++] = s;
+    d.n_img = out.n; d.oh = out.h; d.ow = out.w;
+    d.w = w.w; d.n = w.n; d.k = w.k;
+    d.bias = w.bias;
+    d.rowvec = rowvec; d.rowvec_ld = rowvec_ld;
+    if (residual) { d.residual = residual->p; d.res_ld = residual->c; }
+    d.mode = mode; d.out = out.p; d.ldo = out.c; d.n_valid = w.n;
+    run_gemm(d);
+  }
+  void gn(const Act& x0, const Act* x1, const float* g, const float* b, float eps, bool silu, const Act& out) {
+    float* scratch = new_f32(groupnorm_scratch_floats(x0.n, cfg.norm_groups));
+    if (dry) return;
+    groupnorm(stream, x0.p, x0.c, x1 ? x1->p : nullptr, x1 ? x1->c : 0, x0.n, x0.h * x0.w, cfg.norm_groups, eps, g, b,
+              silu, out.p, scratch);
+  }
+  void attn(const Act& qkv, const Act& out, int batches, int seq, const MvW& m) {
+    if (dry) return;
+    if (cfg.impl == MVLDM_IMPL_TC) attention_tc(stream, qkv.p, out.p, batches, seq, cfg.num_heads, m.d, m.dpad);
+    else attention_simt(stream, qkv.p, out.p, batches, seq, cfg.num_heads, m.d, m.dpad);
+  }
+
+  Act resnet(const ResnetW& r, const Act& x0, const Act* x1, const float* temb) {
+    const int n = x0.n, h = x0.h, w = x0.w;
+    MV_CHECK(x0.c + (x1 ? x1->c : 0) == r.cin, "resnet channel mismatch");
+    Act out = new_act(n, h, w, r.cout);
+    const size_t mark = arena.off;
+    Act a = new_act(n, h, w, r.cin);
+    gn(x0, x1, r.g1, r.b1, 1e-5f, true, a);
+    Act hdn = new_act(n, h, w, r.cout);
+    gemm({seg_conv3x3(a)}, r.conv1, hdn, temb + r.temb_off, temb_total);
+    Act a2 = new_act(n, h, w, r.cout);
+    gn(hdn, nullptr, r.g2, r.b2, 1e-5f, true, a2);
+    if (r.shortcut) {
+      if (x1) gemm({seg_conv3x3(a2), seg_1x1(x0), seg_1x1(*x1)}, r.conv2, out);
+      else gemm({seg_conv3x3(a2), seg_1x1(x0)}, r.conv2, out);
+    } else {
+      MV_CHECK(!x1, "identity-shortcut resnet cannot take a concat input");
+      gemm({seg_conv3x3(a2)}, r.conv2, out, nullptr, 0, &x0);
+    }
+    if (!taps_enabled) arena.off = mark;
+    return out;
+  }
+
+  Act mv_block(const MvW& m, const Act& x, int B, int V) {
+    const int n = x.n, h = x.h, w = x.w, C = m.c, H = cfg.num_heads;
+    const int hw = h * w;
+    Act out = new_act(n, h, w, C);
+    const size_t mark = arena.off;
+    Act g = new_act(n, h, w, C);
+    gn(x, nullptr, m.gn_g, m.gn_b, 1e-6f, false, g);
+    Act t = new_act(n, h, w, C);
+    gemm({seg_1x1(g)}, m.proj_in, t);
+    Act nrm = new_act(n, h, w, C);
+    Act qkv = new_act(n, h, w, 3 * H * m.dpad);
+    Act o = new_act(n, h, w, H * m.dpad);
+    // joint attention over all V*h*w tokens of a scene ("(b f) l c -> b (f l) c")
+    if (!dry) layernorm(stream, t.p, (int)t.tokens(), C, 1e-5f, m.ln_g[0], m.ln_b[0], nrm.p);
+    gemm({seg_1x1(nrm)}, m.qkv1, qkv);
+    attn(qkv, o, B, V * hw, m);
+    Act t2 = new_act(n, h, w, C);
+    gemm({seg_1x1(o)}, m.out1, t2, nullptr, 0, &t);
+    tap(m.key + ".attn1", t2);
+    // per-view attention
+    if (!dry) layernorm(stream, t2.p, (int)t2.tokens(), C, 1e-5f, m.ln_g[1], m.ln_b[1], nrm.p);
+    gemm({seg_1x1(nrm)}, m.qkv2, qkv);
+    attn(qkv, o, B * V, hw, m);
+    Act t3 = new_act(n, h, w, C);
+    gemm({seg_1x1(o)}, m.out2, t3, nullptr, 0, &t2);
+    tap(m.key + ".attn2", t3);
+    // GEGLU feed-forward
+    if (!dry) layernorm(stream, t3.p, (int)t3.tokens(), C, 1e-5f, m.ln_g[2], m.ln_b[2], nrm.p);
+    Act f = new_act(n, h, w, 4 * C);
+    gemm({seg_1x1(nrm)}, m.ff1, f, nullptr, 0, nullptr, 1);
+    Act t4 = new_act(n, h, w, C);
+    gemm({seg_1x1(f)}, m.ff2, t4, nullptr, 0, &t3);
+    gemm({seg_1x1(t4)}, m.proj_out, out, nullptr, 0, &x);
+    if (!taps_enabled) arena.off = mark;
+    return out;
+  }
+
+  void run(const float* latents, const int64_t* tsteps, int B, int V, int Hh, int Ww, float* out_eps) {
+    const int L = cfg.num_levels, n = B * V;
+    const int* boc = cfg.block_out_channels;
+    arena.off = 0;
+    // ---- time embedding (K2): sinusoid -> linear -> SiLU -> linear -> SiLU -> all 21 time_emb_proj at once
+    float* sinus = new_f32((size_t)n * boc[0]);
+    float* e1 = new_f32((size_t)n * temb_dim);
+    float* e2 = new_f32((size_t)n * temb_dim);
+    float* temb = new_f32((size_t)n * temb_total);
+    if (!dry) {
+      timestep_sinusoid(stream, tsteps, n, boc[0], sinus);
+      small_linear(stream, sinus, n, boc[0], time1.w, time1.bias, temb_dim, 1, e1);
+      small_linear(stream, e1, n, temb_dim, time2.w, time2.bias, temb_dim, 1, e2);  // SiLU(emb): every consumer applies it
+      small_linear(stream, e2, n, temb_dim, temb_all.w, temb_all.bias, temb_total, 0, temb);
+    }
+    // ---- conv_in on the im2col'd fp32 input
+    Act col = new_act(n, Hh, Ww, kpad_in);
+    if (!dry) im2col_input(stream, latents, n, cfg.in_channels, Hh, Ww, kpad_in, col.p);
+    Act x = new_act(n, Hh, Ww, boc[0]);
+    gemm({seg_1x1(col)}, conv_in, x);
+    tap("conv_in", x);
+    std::vector<Act> skips{x};
+    // ---- down
+    for (int l = 0; l < L; ++l) {
+      for (int i = 0; i < cfg.layers_per_block; ++i) {
+        x = resnet(down_res[l][i], x, nullptr, temb);
+        tap("down" + std::to_string(l) + ".res" + std::to_string(i), x);
+        skips.push_back(x);
+      }
+      if (x.h <= cfg.max_attn_res && x.w <= cfg.max_attn_res) {
+        x = mv_block(mv_enc[l], x, B, V);
+        tap("down" + std::to_string(l) + ".mv", x);
+      }
+      if (l != L - 1) {
+        Act y = new_act(n, x.h / 2, x.w / 2, x.c);
+        gemm({seg_conv3x3(x, 2)}, down_conv[l], y);
+        x = y;
+        tap("down" + std::to_string(l) + ".ds", x);
+        skips.push_back(x);
+      }
+    }
+    // ---- mid
+    x = resnet(mid_res, x, nullptr, temb);
+    tap("mid.res0", x);
+    x = mv_block(mv_mid, x, B, V);
+    tap("mid.mv", x);
+    // ---- up
+    for (int l = 0; l < L; ++l) {
+      for (int i = 0; i < cfg.layers_per_block + 1; ++i) {
+        Act skip = skips.back();
+        skips.pop_back();
+        x = resnet(up_res[l][i], x, &skip, temb);
+        tap("up" + std::to_string(l) + ".res" + std::to_string(i), x);
+      }
+      if (x.h <= cfg.max_attn_res && x.w <= cfg.max_attn_res) {
+        x = mv_block(mv_dec[l], x, B, V);
+        tap("up" + std::to_string(l) + ".mv", x);
+      }
+      if (l != L - 1) {
+        Act u = new_act(n, x.h * 2, x.w * 2, x.c);
+        if (!dry) upsample_nearest2x(stream, x.p, n, x.h, x.w, x.c, u.p);
+        Act y = new_act(n, u.h, u.w, u.c);
+        gemm({seg_conv3x3(u)}, up_conv[l], y);
+        x = y;
+        tap("up" + std::to_string(l) + ".us", x);
+      }
+    }
+    // ---- head: GN -> SiLU -> conv3x3 -> fp32 NCHW
+    Act a = new_act(n, x.h, x.w, x.c);
+    gn(x, nullptr, norm_out_g, norm_out_b, 1e-5f, true, a);
+    mvldm_gemm_desc d{};
+    d.nseg = 1;
+    d.seg[0] = seg_conv3x3(a);
+    d.n_img = n; d.oh = x.h; d.ow = x.w;
+    d.w = conv_out.w; d.n = conv_out.n; d.k = conv_out.k;
+    d.bias = conv_out.bias;
+    d.mode = 2; d.out = out_eps; d.n_valid = cfg.out_channels;
+    run_gemm(d);
+  }
+
+  Plan& plan_for(int B, int V, int H, int W) {
+    std::vector<int> key{B, V, H, W, taps_enabled ? 1 : 0};
+    auto it = plans.find(key);
+    if (it != plans.end()) return *it->second;
+    std::unique_ptr<Plan> p(new Plan());
+    p->B = B; p->V = V; p->H = H; p->W = W;
+    dry = true;
+    arena = Arena();
+    arena.measuring = true;
+    run(nullptr, nullptr, B, V, H, W, nullptr);
+    p->arena_bytes = arena.peak;
+    p->arena_mem.alloc(p->arena_bytes);
+    p->in_latents.alloc((size_t)B * V * cfg.in_channels * H * W * sizeof(float));
+    p->in_t.alloc((size_t)B * V * sizeof(int64_t));
+    p->out_eps.alloc((size_t)B * V * cfg.out_channels * H * W * sizeof(float));
+    Plan& ref = *p;
+    plans[key] = std::move(p);
+    return ref;
+  }
+
+  void forward(cudaStream_t s, const float* latents, const int64_t* tsteps, int B, int V, int H, int W, float* out) {
+    MV_CHECK(finalized, "mvldm_forward before mvldm_finalize_weights");
+    MV_CHECK(B > 0 && V > 0, "empty batch");
+    const int down = 1 << (cfg.num_levels - 1);
+    MV_CHECK(H % down == 0 && W % down == 0, "latent size must be divisible by 2^(levels-1)");
+    Plan& p = plan_for(B, V, H, W);
+    stream = s;
+    arena = Arena();
+    arena.measuring = false;
+    arena.base = reinterpret_cast<char*>(p.arena_mem.p);
+    arena.cap = p.arena_bytes;
+    dry = false;
+    g_launch_count = 0;
+    const size_t in_bytes = (size_t)B * V * cfg.in_channels * H * W * sizeof(float);
+    const size_t out_bytes = (size_t)B * V * cfg.out_channels * H * W * sizeof(float);
+    const bool graph = cfg.use_cuda_graph && !taps_enabled;
+    if (!graph) {
+      taps.clear();
+      run(latents, tsteps, B, V, H, W, out);
+      last_launches = g_launch_count;
+      return;
+    }
+    // graph path: stage through fixed buffers so the captured pointers stay valid for any caller tensors
+    MV_CUDA(cudaMemcpyAsync(p.in_latents.p, latents, in_bytes, cudaMemcpyDeviceToDevice, s));
+    MV_CUDA(cudaMemcpyAsync(p.in_t.p, tsteps, (size_t)B * V * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    if (!p.graph) {
+      cudaStreamCaptureStatus st;
+      MV_CUDA(cudaStreamIsCapturing(s, &st));
+      if (st != cudaStreamCaptureStatusNone) {  // caller is already capturing: just record into their graph
+        run((const float*)p.in_latents.p, (const int64_t*)p.in_t.p, B, V, H, W, (float*)p.out_eps.p);
+        last_launches = g_launch_count;
+        MV_CUDA(cudaMemcpyAsync(out, p.out_eps.p, out_bytes, cudaMemcpyDeviceToDevice, s));
+        return;
+      }
+      cudaGraph_t g = nullptr;
+      MV_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      try {
+        run((const float*)p.in_latents.p, (const int64_t*)p.in_t.p, B, V, H, W, (float*)p.out_eps.p);
+      } catch (...) {
+        cudaStreamEndCapture(s, &g);
+        if (g) cudaGraphDestroy(g);
+        throw;
+      }
+      MV_CUDA(cudaStreamEndCapture(s, &g));
+      p.graph_launches = g_launch_count;
+      cudaError_t e = cudaGraphInstantiate(&p.graph, g, 0);
+      cudaGraphDestroy(g);
+      MV_CUDA(e);
+    }
+    MV_CUDA(cudaGraphLaunch(p.graph, s));
+    last_launches = p.graph_launches;
+    MV_CUDA(cudaMemcpyAsync(out, p.out_eps.p, out_bytes, cudaMemcpyDeviceToDevice, s));
+  }
+};
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+#define MV_API_BEGIN try {
+#define MV_API_END                           \
+  }                                          \
+  catch (const std::exception& e) {          \
+    mvldm::g_last_error = e.what();          \
+    return 1;                                \
+  }                                          \
+  catch (...) {                              \
+    mvldm::g_last_error = "unknown error";   \
+    return 1;                                \
+  }                                          \
+  return 0;
+
+extern "C" {
+
+const char* mvldm_last_error(void) { return mvldm::g_last_error.c_str(); }
+int mvldm_version(void) { return 100; }
+
+int mvldm_create(const mvldm_config* cfg, int device, mvldm_handle* out) {
+  MV_API_BEGIN
+  MV_CHECK(cfg && out, "null argument");
+  MV_CHECK(cfg->num_levels >= 1 && cfg->num_levels <= MVLDM_MAX_LEVELS, "num_levels out of range");
+  int ndev = 0;
+  MV_CUDA(cudaGetDeviceCount(&ndev));
+  MV_CHECK(device >= 0 && device < ndev, "no such CUDA device (mvldm_b200 has no CPU fallback)");
+  MV_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MV_CUDA(cudaGetDeviceProperties(&prop, device));
+  MV_CHECK(prop.major == 10, "mvldm_b200 is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) +
+                                 std::to_string(prop.minor));
+  std::unique_ptr<mvldm_handle_s> h(new mvldm_handle_s());
+  h->cfg = *cfg;
+  h->device = device;
+  for (int l = 0; l < cfg->num_levels; ++l) {
+    MV_CHECK(cfg->block_out_channels[l] % 64 == 0, "block_out_channels must be multiples of 64");
+    MV_CHECK(cfg->block_out_channels[l] % cfg->norm_groups == 0, "channels not divisible by norm_groups");
+  }
+  h->build_registry();
+  *out = h.release();
+  MV_API_END
+}
+
+int mvldm_destroy(mvldm_handle h) {
+  MV_API_BEGIN
+  if (h) {
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    delete h;
+  }
+  MV_API_END
+}
+
+int mvldm_num_weights(mvldm_handle h) { return h ? (int)h->names.size() : -1; }
+const char* mvldm_weight_name(mvldm_handle h, int i) {
+  return (h && i >= 0 && i < (int)h->names.size()) ? h->names[i].c_str() : nullptr;
+}
+int mvldm_weight_shape(mvldm_handle h, int i, int64_t shape[4], int* ndim) {
+  MV_API_BEGIN
+  MV_CHECK(h && i >= 0 && i < (int)h->names.size(), "bad weight index");
+  const auto& s = h->shapes[h->names[i]];
+  *ndim = (int)s.size();
+  for (size_t j = 0; j < s.size(); ++j) shape[j] = s[j];
+  MV_API_END
+}
+
+int mvldm_set_weight(mvldm_handle h, const char* key, const void* ptr, const int64_t* shape, int ndim, int dtype,
+                     void* stream) {
+  MV_API_BEGIN
+  MV_CHECK(h && key && ptr && shape, "null argument");
+  MV_CUDA(cudaSetDevice(h->device));
+  auto it = h->shapes.find(key);
+  MV_CHECK(it != h->shapes.end(), std::string("unknown weight key: ") + key);
+  MV_CHECK((int)it->second.size() == ndim, std::string("rank mismatch for ") + key);
+  int64_t numel = 1;
+  for (int i = 0; i < ndim; ++i) {
+    MV_CHECK(it->second[i] == shape[i], std::string("shape mismatch for ") + key);
+    numel *= shape[i];
+  }
+  MV_CHECK(dtype >= MVLDM_F32 && dtype <= MVLDM_F16, "bad dtype");
+  auto& buf = h->raw[key];
+  if (!buf || buf->bytes != (size_t)numel * sizeof(float)) buf.reset(new DevBuf((size_t)numel * sizeof(float)));
+  convert_f32((cudaStream_t)stream, ptr, dtype, numel, reinterpret_cast<float*>(buf->p));
+  h->finalized = false;
+  MV_API_END
+}
+
+int mvldm_finalize_weights(mvldm_handle h, void* stream) {
+  MV_API_BEGIN
+  MV_CHECK(h, "null handle");
+  MV_CUDA(cudaSetDevice(h->device));
+  h->finalize((cudaStream_t)stream);
+  MV_API_END
+}
+
+int64_t mvldm_workspace_bytes(mvldm_handle h, int B, int V, int H, int W) {
+  try {
+    MV_CHECK(h && h->finalized, "finalize weights first");
+    return (int64_t)h->plan_for(B, V, H, W).arena_bytes;
+  } catch (const std::exception& e) {
+    mvldm::g_last_error = e.what();
+    return -1;
+  }
+}
+
+int mvldm_forward(mvldm_handle h, void* stream, const float* latents, const int64_t* timesteps, int B, int V, int H,
+                  int W, float* out) {
+  MV_API_BEGIN
+  MV_CHECK(h && latents && timesteps && out, "null argument");
+  MV_CUDA(cudaSetDevice(h->device));
+  h->forward((cudaStream_t)stream, latents, timesteps, B, V, H, W, out);
+  MV_API_END
+}
+
+int mvldm_last_launch_count(mvldm_handle h) { return h ? h->last_launches : -1; }
+
+int mvldm_enable_taps(mvldm_handle h, int enable) {
+  MV_API_BEGIN
+  MV_CHECK(h, "null handle");
+  h->taps_enabled = enable != 0;
+  MV_API_END
+}
+
+int mvldm_debug_tap(mvldm_handle h, void* stream, const char* name, float* out, int64_t* numel) {
+  MV_API_BEGIN
+  MV_CHECK(h && name && numel, "null argument");
+  auto it = h->taps.find(name);
+  MV_CHECK(it != h->taps.end(), std::string("no such tap (enable taps and run a forward first): ") + name);
+  const Act& a = it->second.a;
+  *numel = a.tokens() * a.c;
+  if (out) nhwc_to_nchw_f32((cudaStream_t)stream, a.p, a.n, a.h * a.w, a.c, out);
+  MV_API_END
+}
+
+int mvldm_build_inputs(void* stream, const float* x_t, const float* ctx, const float* rays, int B, int v_c, int v_t,
+                       int ray_views, int ray_off, int R, int hw, float* out) {
+  MV_API_BEGIN
+  MV_CHECK(x_t && rays && out && (ctx || v_c == 0), "null argument");
+  MV_CHECK(ray_off + v_c + v_t <= ray_views, "ray views out of range");
+  build_inputs((cudaStream_t)stream, x_t, ctx, rays, B, v_c, v_t, ray_views, ray_off, R, hw, out);
+  MV_API_END
+}
+
+int mvldm_ddim_step(void* stream, const float* eps_c, const float* eps_u, float cfg_scale, int B, int v_c, int v_t,
+                    int chw, const float* x_t, float sa, float s1a, float sp, float s1p, float* x_prev, float* eps_out) {
+  MV_API_BEGIN
+  MV_CHECK(eps_c && x_t && x_prev, "null argument");
+  MV_CHECK(sa > 0.f, "sqrt(alpha_t) must be positive");
+  ddim_step((cudaStream_t)stream, eps_c, eps_u, cfg_scale, B, v_c, v_t, chw, x_t, sa, s1a, sp, s1p, x_prev, eps_out);
+  MV_API_END
+}
+
+int mvldm_raymap(void* stream, const float* extr, const float* intr, int n, int h, int w, int plucker, float* out) {
+  MV_API_BEGIN
+  MV_CHECK(extr && intr && out, "null argument");
+  raymap((cudaStream_t)stream, extr, intr, n, h, w, plucker != 0, out);
+  MV_API_END
+}
+
+int mvldm_op_gemm(void* stream, int impl, const mvldm_gemm_desc* d) {
+  MV_API_BEGIN
+  MV_CHECK(d, "null argument");
+  if (impl == MVLDM_IMPL_TC) gemm_tc((cudaStream_t)stream, *d);
+  else gemm_simt((cudaStream_t)stream, *d);
+  MV_API_END
+}
+
+int mvldm_op_attention(void* stream, int impl, const void* qkv, void* out, int batches, int seq, int heads, int d,
+                       int dpad) {
+  MV_API_BEGIN
+  MV_CHECK(qkv && out, "null argument");
+  if (impl == MVLDM_IMPL_TC)
+    attention_tc((cudaStream_t)stream, (const bf16*)qkv, (bf16*)out, batches, seq, heads, d, dpad);
+  else
+    attention_simt((cudaStream_t)stream, (const bf16*)qkv, (bf16*)out, batches, seq, heads, d, dpad);
+  MV_API_END
+}
+
+int mvldm_op_groupnorm(void* stream, const void* x0, int c0, const void* x1, int c1, int n_img, int hw, int groups,
+                       float eps, const float* gamma, const float* beta, int silu, void* out, float* scratch) {
+  MV_API_BEGIN
+  MV_CHECK(x0 && gamma && beta && out && scratch, "null argument");
+  groupnorm((cudaStream_t)stream, (const bf16*)x0, c0, (const bf16*)x1, c1, n_img, hw, groups, eps, gamma, beta,
+            silu != 0, (bf16*)out, scratch);
+  MV_API_END
+}
+
+int mvldm_op_layernorm(void* stream, const void* x, int rows, int c, float eps, const float* gamma, const float* beta,
+                       void* out) {
+  MV_API_BEGIN
+  MV_CHECK(x && gamma && beta && out, "null argument");
+  layernorm((cudaStream_t)stream, (const bf16*)x, rows, c, eps, gamma, beta, (bf16*)out);
+  MV_API_END
+}
+
+}  // extern "C"
