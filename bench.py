@@ -1,0 +1,290 @@
+"""Benchmark of the MV-LDM denoising hot path (BASELINE.json metric: DDIM denoise steps/s at 8 views, 32x32 latent).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--cfg] [--scenes-per-gpu S] [--impl reference]
+
+One "step" = one `DiffusionWrapper.step` (reference src/model/diffusion_wrapper.py:413-453) for one scene of
+8 views (2 context + 6 target): input concat + denoiser forward (+ a second, unconditional forward with --cfg)
++ CFG compose + DDIM update.  N > 1 (launched by torchrun, one rank per GPU): scenes are independent, every
+rank runs its own scene(s) with no data-path collective (weak scaling); value = all ranks' scene-steps / max
+over ranks of the device time.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput, `e2e` = the same steps through the public
+`DenoisingPath.step` API with pinned-host inputs copied in and the result copied out every step.
+`--impl reference` times the reference's CPU implementation of the same step (the oracle: the reference's
+arithmetic restated in torch-CPU fp32; the reference itself needs diffusers/lightning/hydra, which cannot be
+installed here) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+V_C, V_T, H, W = 2, 6, 32, 32
+NUM_DDIM_STEPS = 25
+METRIC = "ddim_denoise_steps_per_sec_8views_32x32_latent"
+UNIT = "steps/s"
+
+
+def forward_gflop(v: int) -> float:
+    """Variant A, 2*MAC, head dims un-padded: B*(137.9 V + 3.069 V^2) GFLOP per forward."""
+    return 137.9 * v + 3.069 * v * v
+
+
+def step_gflop(use_cfg: bool) -> float:
+    return forward_gflop(V_C + V_T) + (forward_gflop(V_T) if use_cfg else 0.0)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_tflops": d["bf16_tflops_sustained"], "hbm_gbs": d["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json, sustained)"}
+    return {"bf16_tflops": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_steps_per_sec(steps: int, warmup: int, use_cfg: bool):
+    from oracle import mvldm_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.OracleCfg()
+    sd = O.init_weights(cfg, 0)
+    ctx, x_t, extr, intr = O.synthetic_scene(1, V_C, V_T)
+    sched = O.DDIMOracle()
+    sched.set_timesteps(NUM_DDIM_STEPS)
+    rays = O.raymap(extr, intr, H, W)
+    cin = torch.cat([ctx, torch.zeros(1, V_C, 1, H, W)], 2)
+    mask = torch.ones(1, V_T, 1, H, W)
+    ts = sched.timesteps
+    with torch.no_grad():
+        for i in range(warmup):
+            x_t, _ = O.ddim_step(sd, cfg, sched, x_t, ts[i % len(ts)], cin, rays, mask, use_cfg, 3.0)
+        t0 = time.perf_counter()
+        for i in range(steps):
+            x_t, _ = O.ddim_step(sd, cfg, sched, x_t, ts[(warmup + i) % len(ts)], cin, rays, mask, use_cfg, 3.0)
+        dt = time.perf_counter() - t0
+    return steps / dt, dt / steps, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))   # bounded: ~1-2 s per CPU step
+    v, ms, cores = cpu_steps_per_sec(steps, warmup, args.cfg)
+    sample = f"{steps} DDIM steps (of {args.steps} requested; bounded for CPU), 1 scene x 8 views, fp32, torch-CPU oracle"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "views": V_C + V_T, "latent": [H, W], "use_cfg": args.cfg,
+                   "scenes_per_gpu": 1},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def workload_name(args):
+    return (f"25-step DDIM sampling, {args.scenes_per_gpu} scene(s)/GPU x 8 views (2 context + 6 target) at 256x256 "
+            f"(32x32x4 latent), Variant-A MultiViewUNet (764M params), {'CFG 3.0 (2 forwards/step)' if args.cfg else 'no CFG (1 forward/step)'}")
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch.distributed as dist
+    import mvldm_b200 as mv
+    from oracle import mvldm_oracle as O     # only for the seeded synthetic weights/scene and the cpu_baseline leg
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: mvldm_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    S = args.scenes_per_gpu
+    cfg = O.OracleCfg()
+    m = mv.MultiViewUNet(mv.default_cfg(), cfg.in_channels, cfg.out_channels, use_cuda_graph=not args.no_graph)
+    m.load_state_dict(O.init_weights(cfg, 0))
+    m = m.to(dev).eval()
+    sched = mv.DDIMScheduler(clip_sample=False)
+    path = mv.DenoisingPath(m, sched, use_cfg=args.cfg, cfg_scale=3.0)
+    path.set_timesteps(NUM_DDIM_STEPS)
+    ts_list = [int(t) for t in sched.timesteps]
+    ctx, x_T, extr, intr = O.synthetic_scene(S, V_C, V_T, seed=1 + rank)
+    ctx_in = torch.cat([ctx, torch.zeros(S, V_C, 1, H, W)], 2)
+    rays = mv.ray_encode(extr.to(dev), intr.to(dev), H, W)
+    d_ctx, d_x = ctx_in.to(dev), x_T.to(dev)
+
+    # ---- device-resident throughput -------------------------------------------------------------
+    x = d_x
+    for i in range(args.warmup):
+        x = path.step(m, x, ts_list[i % NUM_DDIM_STEPS], d_ctx, rays)
+    launches_per_step = m.last_launch_count() * (2 if args.cfg else 1) + (2 if args.cfg else 1) + 1
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            x = path.step(m, x, ts_list[(args.warmup + i) % NUM_DDIM_STEPS], d_ctx, rays)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = clk.summary()
+    assert torch.isfinite(x).all()
+
+    # ---- end to end through the public API with host buffers ---------------------------------------
+    h_x, h_ctx, h_rays = x_T.pin_memory(), ctx_in.pin_memory(), rays.cpu().pin_memory()
+    h_out = torch.empty_like(h_x).pin_memory()
+    h2d = h_x.numel() * 4 + h_ctx.numel() * 4 + h_rays.numel() * 4
+    d2h = h_out.numel() * 4
+
+    def e2e_step(i):
+        dx = h_x.to(dev, non_blocking=True)
+        dc = h_ctx.to(dev, non_blocking=True)
+        dr = h_rays.to(dev, non_blocking=True)
+        y = path.step(m, dx, ts_list[i % NUM_DDIM_STEPS], dc, dr)
+        h_out.copy_(y, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller consumes the result on the host
+        h_x.copy_(h_out)
+
+    for i in range(args.warmup):
+        e2e_step(i)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        e2e_step(args.warmup + i)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    value = world * S * args.steps / (ms * 1e-3)
+    e2e = world * S * args.steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peaks = load_peaks()
+        gf = step_gflop(args.cfg) * S
+        achieved_tf = gf * args.steps / (ms * 1e-3) / 1e3
+        roof = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved_tf / peaks["bf16_tflops"], "traffic": None,
+                "how": ("whole step: algorithmic FLOPs of one DDIM step (BASELINE.md: 137.9 V + 3.069 V^2 GFLOP per forward, "
+                        "head dims un-padded) x steps / CUDA-event time of the timed region; per-kernel figures: profiles/"),
+                "peak_source": peaks["source"]}
+        cpu = None
+        if not args.no_cpu_baseline:
+            n = 3
+            v, s_per, cores = cpu_steps_per_sec(n, 1, args.cfg)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{n} DDIM steps after 1 warm-up, 1 scene x 8 views, fp32 torch-CPU oracle ({s_per:.2f} s/step)"}
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(args), "views": V_C + V_T, "latent": [H, W], "use_cfg": args.cfg,
+                       "scenes_per_gpu": S, "cuda_graph": not args.no_graph,
+                       "l2_policy": "inputs larger than L2: 1.53 GB of bf16 weights are streamed every step (L2 = 126 MB)",
+                       "weights": "random-init, seed 0, proj_out re-randomised (SURVEY.md §0.5)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": roof, "cpu_baseline": cpu,
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=25)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cfg", action="store_true", help="classifier-free guidance: second forward over the target views")
+    ap.add_argument("--scenes-per-gpu", type=int, default=1)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -28,7 +28,7 @@ typedef struct mvldm_handle_s* mvldm_handle;
 enum { MVLDM_F32 = 0, MVLDM_BF16 = 1, MVLDM_F16 = 2 };
 /* kernel family: tcgen05/TMA kernels (product) or the plain CUDA-core kernels kept as an on-device
  * cross-check for the tests (never selected implicitly) */
-enum { MVLDM_IMPL_TC = 0, MVLDM_IMPL_SIMT = 1 };
+enum { MVLDM_IMPL_TC = 0, MVLDM_IMPL_SIMT = 1, MVLDM_IMPL_TC_GEMM_SIMT_ATTN = 2 };
 
 /* Replaces: MultiViewUNetCfg + UNet2DModelCfg + SpatialTransformer3DCfg
  * (src/model/denoiser/mvunet.py:22-40, src/model/denoiser/mvdream/attention.py:23-32) and the

@@ -1,0 +1,19 @@
+"""mvldm_b200 — B200-native (sm_100a) implementation of the MV-LDM denoising hot path.
+
+Python here is plumbing: the reference-facing interfaces (`Denoiser`, `MultiViewUNet`, `get_denoiser`,
+`DDIMScheduler`, `get_scheduler`, `DenoisingPath.step/sample`) forward to the C-ABI library
+`libmvldm_b200.so` (hand-written CUDA; see include/mvldm_b200.h).
+"""
+from . import _lib
+from .denoiser import (DENOISER, Denoiser, DenoiserCfg, MultiViewUNet, MultiViewUNetCfg, SpatialTransformer3DCfg,
+                       UNet2DModelCfg, default_cfg, get_denoiser)
+from .sampler import DenoisingPath, build_inputs, ray_encode
+from .scheduler import (SCHEDULER, DDIMScheduler, DDIMSchedulerCfg, SchedulerCfg, fused_cfg_ddim_step, get_scheduler)
+from .sharding import gather_scenes, scene_slice
+
+__all__ = [
+    "DENOISER", "Denoiser", "DenoiserCfg", "MultiViewUNet", "MultiViewUNetCfg", "SpatialTransformer3DCfg",
+    "UNet2DModelCfg", "default_cfg", "get_denoiser", "DenoisingPath", "build_inputs", "ray_encode", "SCHEDULER",
+    "DDIMScheduler", "DDIMSchedulerCfg", "SchedulerCfg", "fused_cfg_ddim_step", "get_scheduler", "gather_scenes",
+    "scene_slice",
+]

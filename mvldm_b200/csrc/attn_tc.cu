@@ -1,7 +1,276 @@
-// placeholder until the tcgen05 flash kernel lands (next commit)
+// Flash-style self-attention on tcgen05 / TMEM / TMA for sm_100a: the joint multi-view attention (one
+// sequence = all V*h*w tokens of a scene) and the per-view attention of BasicTransformerBlock3D
+// (reference src/model/denoiser/mvdream/attention.py:174-205,362-368).  The N x N score matrix the reference
+// materialises in fp32 (2.1 GB per level-0 block at 8 views) never leaves the SM.
+//
+// One CTA = 128 queries of one (batch, head).  Per 128-key (64 for head_dim_pad 192) tile:
+//   S = Q K^T          tcgen05.mma  SS  (Q, K in smem via TMA, K-major SW128)      -> TMEM fp32, double-buffered
+//   softmax            4 warps, one query row per thread: tcgen05.ld S, running max with lazy rescale, exp2,
+//                      row sum in fp32, P -> bf16 written back over S in TMEM (tcgen05.st)
+//   O += P V           tcgen05.mma  TS  (P from TMEM, V from smem as an MN-major SW128 operand) -> TMEM fp32
+// Scores are fp32 and the softmax is fp32 exactly as ATTN_PRECISION=fp32 (attention.py:185-203); P is
+// rounded to bf16 before P.V as autocast does at :203.
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2..5 softmax/epilogue.
+// The running maximum is only moved when it grows by more than 2^8 (exact: any reference point is a valid
+// softmax shift; P <= 256 stays well inside bf16 range), so the O accumulator is almost never touched.
 #include "common.cuh"
+#include "tc_common.cuh"
+
 namespace mvldm {
-void attention_tc(cudaStream_t, const bf16*, bf16*, int, int, int, int, int) {
-  MV_CHECK(false, "attention_tc: not built yet");
+namespace {
+
+constexpr int BM = 128;
+
+struct AttnParams {
+  CUtensorMap tmQ;   // box [64, 128, 1] over (cols, seq, batch)
+  CUtensorMap tmKV;  // box [64, BN, 1]
+  bf16* out;
+  int seq, heads, d, dpad;
+  float scale_log2;  // d^-1/2 * log2(e)
+};
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// DPAD: padded head dim (64/128/192); BN: keys per tile; ST: K/V ring stages
+template <int DPAD, int BN, int ST>
+__global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
+  constexpr int NC = DPAD / 64;                // 64-column chunks per row
+  constexpr int Q_BYTES = NC * BM * 128;
+  constexpr int KV_CHUNK = BN * 128;           // one 64-column chunk of a K or V tile
+  constexpr int STAGE_BYTES = 2 * NC * KV_CHUNK;
+  constexpr uint32_t S_COL0 = 0, S_COL1 = BN, O_COL = 2 * BN;
+  static_assert(2 * BN + DPAD <= 512, "TMEM budget");
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_q, bar_kv_full[ST], bar_kv_empty[ST], bar_s[2], bar_p[2], bar_o;
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_smem = smem_base;
+  const uint32_t kv_smem = smem_base + Q_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BM;
+  const int batch = blockIdx.y / p.heads, head = blockIdx.y % p.heads;
+  const int T = (p.seq + BN - 1) / BN;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&p.tmQ);
+    tc::tma_prefetch_desc(&p.tmKV);
+    tc::mbar_init(tc::smem_u32(&bar_q), 1);
+    for (int s = 0; s < ST; ++s) {
+      tc::mbar_init(tc::smem_u32(&bar_kv_full[s]), 1);
+      tc::mbar_init(tc::smem_u32(&bar_kv_empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(tc::smem_u32(&bar_s[b]), 1);
+      tc::mbar_init(tc::smem_u32(&bar_p[b]), 128);
+    }
+    tc::mbar_init(tc::smem_u32(&bar_o), 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 1) tc::tmem_alloc<512>(tc::smem_u32(&tmem_slot));
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const uint32_t bq = tc::smem_u32(&bar_q);
+      tc::mbar_expect_tx(bq, Q_BYTES);
+      for (int c = 0; c < NC; ++c) tma_load_3d(q_smem + c * BM * 128, &p.tmQ, bq, head * DPAD + c * 64, q0, batch);
+      const int kcol = (p.heads + head) * DPAD, vcol = (2 * p.heads + head) * DPAD;
+      for (int j = 0; j < T; ++j) {
+        const int stage = j % ST;
+        tc::mbar_wait(tc::smem_u32(&bar_kv_empty[stage]), ((j / ST) & 1) ^ 1);
+        const uint32_t full = tc::smem_u32(&bar_kv_full[stage]);
+        tc::mbar_expect_tx(full, STAGE_BYTES);
+        const uint32_t ks = kv_smem + stage * STAGE_BYTES, vs = ks + NC * KV_CHUNK;
+        for (int c = 0; c < NC; ++c) tma_load_3d(ks + c * KV_CHUNK, &p.tmKV, full, kcol + c * 64, j * BN, batch);
+        for (int c = 0; c < NC; ++c) tma_load_3d(vs + c * KV_CHUNK, &p.tmKV, full, vcol + c * 64, j * BN, batch);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = tc::umma_idesc_bf16(BM, BN, false, false);
+      constexpr uint32_t idesc_pv = tc::umma_idesc_bf16(BM, DPAD, false, true);
+      auto issue_qk = [&](int j) {
+        const int stage = j % ST;
+        tc::mbar_wait(tc::smem_u32(&bar_kv_full[stage]), (j / ST) & 1);
+        tc::tc_fence_after();
+        const uint32_t ks = kv_smem + stage * STAGE_BYTES;
+        const uint32_t s_tmem = tmem + ((j & 1) ? S_COL1 : S_COL0);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const uint64_t qd = tc::umma_desc_k_sw128(q_smem + c * BM * 128);
+          const uint64_t kd = tc::umma_desc_k_sw128(ks + c * KV_CHUNK);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc::umma_ss(s_tmem, qd + 2 * k, kd + 2 * k, idesc_qk, (c | k) != 0);
+        }
+        tc::umma_commit(tc::smem_u32(&bar_s[j & 1]));
+      };
+      tc::mbar_wait(tc::smem_u32(&bar_q), 0);
+      issue_qk(0);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) issue_qk(j + 1);  // S(j+1) is computed while the softmax warps work on S(j)
+        tc::mbar_wait(tc::smem_u32(&bar_p[j & 1]), (j >> 1) & 1);
+        tc::tc_fence_after();
+        const int stage = j % ST;
+        const uint32_t vs = kv_smem + stage * STAGE_BYTES + NC * KV_CHUNK;
+        const uint32_t p_tmem = tmem + ((j & 1) ? S_COL1 : S_COL0);
+        const uint64_t vd = tc::umma_desc_mn_sw128(vs, KV_CHUNK);
+#pragma unroll
+        for (int kk = 0; kk < BN / 16; ++kk)  // 16 keys per MMA: 8 packed-bf16 TMEM columns of P, 16 V rows (2 KB)
+          tc::umma_ts(tmem + O_COL, p_tmem + kk * 8, vd + kk * 128, idesc_pv, (j | kk) != 0);
+        tc::umma_commit(tc::smem_u32(&bar_kv_empty[stage]));
+        tc::umma_commit(tc::smem_u32(&bar_o));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= softmax + epilogue: one query row per thread =================
+    const int quarter = warp & 3;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int row = q0 + quarter * 32 + lane;
+    float m_ref = -INFINITY, l_sum = 0.f;
+    for (int j = 0; j < T; ++j) {
+      const uint32_t s_tmem = tmem + lane_addr + ((j & 1) ? S_COL1 : S_COL0);
+      tc::mbar_wait(tc::smem_u32(&bar_s[j & 1]), (j >> 1) & 1);
+      tc::tc_fence_after();
+      uint32_t r[BN];
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) tc::tmem_ld32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
+      tc::tmem_ld_wait();
+      if (j == T - 1 && (p.seq % BN) != 0) {  // ragged tail: keys past the sequence end do not exist
+        const int valid = p.seq - j * BN;
+#pragma unroll
+        for (int i = 0; i < BN; ++i)
+          if (i >= valid) r[i] = 0xff800000u;  // -inf
+      }
+      float mt = __uint_as_float(r[0]);
+#pragma unroll
+      for (int i = 1; i < BN; ++i) mt = fmaxf(mt, __uint_as_float(r[i]));
+      // lazy running max: move the reference only when it would otherwise let P exceed 2^8
+      const bool grow = (mt - m_ref) * p.scale_log2 > 8.f;  // also true on the first tile (m_ref = -inf)
+      if (__any_sync(0xffffffffu, grow) && j > 0) {
+        const float m_new = grow ? mt : m_ref;
+        const float f = ex2((m_ref - m_new) * p.scale_log2);
+        tc::mbar_wait(tc::smem_u32(&bar_o), (j - 1) & 1);  // P V of the previous tile has landed in O
+        tc::tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < DPAD / 32; ++c) {
+          uint32_t o[32];
+          tc::tmem_ld32(tmem + lane_addr + O_COL + c * 32, o);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+          tc::tmem_st16(tmem + lane_addr + O_COL + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&o[0]));
+          tc::tmem_st16(tmem + lane_addr + O_COL + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&o[16]));
+        }
+        l_sum *= f;
+        m_ref = m_new;
+      } else if (grow) {
+        m_ref = mt;  // first tile: nothing accumulated yet
+      }
+      const float mb = m_ref * p.scale_log2;
+      uint32_t pk[BN / 2];
+#pragma unroll
+      for (int i = 0; i < BN; i += 2) {
+        const float p0 = ex2(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb));
+        const float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -mb));
+        l_sum += p0 + p1;
+        pk[i / 2] = pack_bf16(p0, p1);
+      }
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) tc::tmem_st16(s_tmem + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[c * 16]));
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      tc::mbar_arrive(tc::smem_u32(&bar_p[j & 1]));
+    }
+    // ---- epilogue: O / l -> bf16, head-padded row
+    tc::mbar_wait(tc::smem_u32(&bar_o), (T - 1) & 1);
+    tc::tc_fence_after();
+    const float inv = 1.f / l_sum;
+    bf16* dst = p.out + ((int64_t)batch * p.seq + row) * (p.heads * DPAD) + head * DPAD;
+#pragma unroll
+    for (int c = 0; c < DPAD / 32; ++c) {
+      uint32_t o[32];
+      __syncwarp();
+      tc::tmem_ld32(tmem + lane_addr + O_COL + c * 32, o);
+      tc::tmem_ld_wait();
+      if (row < p.seq) {
+        uint4* op = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          op[v] = make_uint4(pack_bf16(__uint_as_float(o[v * 8]) * inv, __uint_as_float(o[v * 8 + 1]) * inv),
+                             pack_bf16(__uint_as_float(o[v * 8 + 2]) * inv, __uint_as_float(o[v * 8 + 3]) * inv),
+                             pack_bf16(__uint_as_float(o[v * 8 + 4]) * inv, __uint_as_float(o[v * 8 + 5]) * inv),
+                             pack_bf16(__uint_as_float(o[v * 8 + 6]) * inv, __uint_as_float(o[v * 8 + 7]) * inv));
+      }
+    }
+    tc::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<512>(tmem);
+  }
+}
+
+template <int DPAD, int BN, int ST>
+void launch(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, int heads, int d) {
+  AttnParams p{};
+  const int ld = 3 * heads * DPAD;
+  const uint64_t dims[3] = {(uint64_t)ld, (uint64_t)seq, (uint64_t)batches};
+  const uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)seq * ld * 2};
+  const uint32_t es[3] = {1, 1, 1};
+  const uint32_t boxq[3] = {64, BM, 1}, boxkv[3] = {64, (uint32_t)BN, 1};
+  p.tmQ = make_tmap_bf16(qkv, 3, dims, strides, boxq, es);
+  p.tmKV = make_tmap_bf16(qkv, 3, dims, strides, boxkv, es);
+  p.out = out;
+  p.seq = seq;
+  p.heads = heads;
+  p.d = d;
+  p.dpad = DPAD;
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
+  constexpr int smem = (DPAD / 64) * BM * 128 + ST * 2 * (DPAD / 64) * BN * 128 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    MV_CUDA(cudaFuncSetAttribute(attn_tc_kernel<DPAD, BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid(ceil_div(seq, BM), batches * heads);
+  attn_tc_kernel<DPAD, BN, ST><<<grid, 192, smem, s>>>(p);
+  MV_LAUNCHED();
+}
+
+}  // namespace
+
+void attention_tc(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, int heads, int d, int dpad) {
+  MV_CHECK(d <= dpad && seq >= 1 && batches >= 1, "attention_tc: bad arguments");
+  MV_CHECK((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+           "attention_tc: pointers must be 16-byte aligned");
+  if (dpad == 64) launch<64, 128, 3>(s, qkv, out, batches, seq, heads, d);
+  else if (dpad == 128) launch<128, 128, 2>(s, qkv, out, batches, seq, heads, d);
+  else if (dpad == 192) launch<192, 64, 2>(s, qkv, out, batches, seq, heads, d);
+  else MV_CHECK(false, "attention_tc: head_dim_pad must be 64, 128 or 192");
+}
+
 }  // namespace mvldm

@@ -138,6 +138,7 @@ struct mvldm_handle_s {
 
   // ---- run state ----
   cudaStream_t stream = nullptr;
+  cudaStream_t capture_stream = nullptr;  // graphs are recorded here: the caller's stream may be the legacy NULL stream
   Arena arena;
   bool dry = true;
 
@@ -442,8 +443,8 @@ struct mvldm_handle_s {
   }
   void run_gemm(mvldm_gemm_desc& d) {
     if (dry) return;
-    if (cfg.impl == MVLDM_IMPL_TC) gemm_tc(stream, d);
-    else gemm_simt(stream, d);
+    if (cfg.impl == MVLDM_IMPL_SIMT) gemm_simt(stream, d);
+    else gemm_tc(stream, d);
   }
   // out = A-segments x W^T (+bias +rowvec +residual), bf16 NHWC
   void gemm(std::initializer_list<mvldm_aseg> segs, const Packed& w, const Act& out, const float* rowvec = nullptr,
@@ -664,15 +665,19 @@ struct mvldm_handle_s {
         return;
       }
       cudaGraph_t g = nullptr;
-      MV_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      if (!capture_stream) MV_CUDA(cudaStreamCreateWithFlags(&capture_stream, cudaStreamNonBlocking));
+      stream = capture_stream;
+      MV_CUDA(cudaStreamBeginCapture(capture_stream, cudaStreamCaptureModeThreadLocal));
       try {
         run((const float*)p.in_latents.p, (const int64_t*)p.in_t.p, B, V, H, W, (float*)p.out_eps.p);
       } catch (...) {
-        cudaStreamEndCapture(s, &g);
+        cudaStreamEndCapture(capture_stream, &g);
         if (g) cudaGraphDestroy(g);
+        stream = s;
         throw;
       }
-      MV_CUDA(cudaStreamEndCapture(s, &g));
+      MV_CUDA(cudaStreamEndCapture(capture_stream, &g));
+      stream = s;
       p.graph_launches = g_launch_count;
       cudaError_t e = cudaGraphInstantiate(&p.graph, g, 0);
       cudaGraphDestroy(g);
@@ -734,6 +739,7 @@ int mvldm_destroy(mvldm_handle h) {
   if (h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
     delete h;
   }
   MV_API_END

@@ -49,8 +49,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Bounded spin: a protocol bug traps (launch failure) instead of hanging the GPU.
+#ifndef MVLDM_SPIN_LIMIT
+#define MVLDM_SPIN_LIMIT (1u << 26)
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++spins > MVLDM_SPIN_LIMIT) __trap();
   }
 }
 

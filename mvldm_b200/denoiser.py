@@ -1,0 +1,359 @@
+"""Host-side mirror of the reference denoiser interface, backed by the sm_100a C-ABI library.
+
+Mirrors (same names, argument meaning and error behaviour):
+  * ``Denoiser``                      reference src/model/denoiser/denoiser.py:12-29
+  * ``MultiViewUNetCfg`` / ``UNet2DModelCfg``  reference src/model/denoiser/mvunet.py:22-40
+  * ``SpatialTransformer3DCfg``       reference src/model/denoiser/mvdream/attention.py:23-32
+  * ``MultiViewUNet``                 reference src/model/denoiser/mvunet.py:43-208
+  * ``DENOISER`` / ``get_denoiser``   reference src/model/denoiser/__init__.py:7-18
+
+``MultiViewUNet`` is an ``nn.Module`` whose parameters carry exactly the reference's state-dict keys
+(``unet.*``, ``cross_attn_blocks_{encoder,mid,decoder}.*``), so Lightning checkpoints load unchanged and
+``.parameters()`` / ``AveragedModel`` keep working; its ``forward`` does no torch math — it hands the device
+pointers to ``mvldm_forward`` on the current CUDA stream.  Inference only (no autograd through the kernels).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from abc import ABC, abstractmethod
+from dataclasses import dataclass, field
+from typing import Dict, Generic, List, Literal, Optional, Tuple, TypeVar
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib
+
+T = TypeVar("T")
+
+
+@dataclass
+class UNet2DModelCfg:
+    name: Literal["unet"]
+    down_block_types: list | Tuple
+    mid_block_type: str
+    up_block_types: list | Tuple
+    only_cross_attention: bool
+    block_out_channels: list | Tuple
+
+
+@dataclass
+class SpatialTransformer3DCfg:
+    name: Literal["spatial_transformer_3d"]
+    num_heads: int
+    num_layers: int = 1
+    d_dot: int | None = None
+    d_mlp: int | None = None
+    d_mlp_multiplier: int | None = None
+    downscale: int = 1
+    pos_enc: bool = False
+
+
+MultiViewAttentionCfg = SpatialTransformer3DCfg
+
+
+@dataclass
+class MultiViewUNetCfg:
+    name: Literal["mv_unet"]
+    autoencoder: UNet2DModelCfg
+    multi_view_attention: MultiViewAttentionCfg
+    use_ray_encoding: bool = True
+    encoder_conditioning: bool = True
+    mid_conditioning: bool = True
+    decoder_conditioning: bool = True
+    pretrained_from: str | None = None
+
+
+def default_cfg(num_heads: int = 8) -> MultiViewUNetCfg:
+    """The released topology minus the hub download: config/model/denoiser/mv_unet.yaml:8-17 +
+    multi_view_attention/spatial_transformer_3d.yaml."""
+    return MultiViewUNetCfg(
+        name="mv_unet",
+        autoencoder=UNet2DModelCfg("unet", ["DownBlock2D"] * 4, "UNetMidBlock2D", ["UpBlock2D"] * 4, False,
+                                   [320, 640, 1280, 1280]),
+        multi_view_attention=SpatialTransformer3DCfg("spatial_transformer_3d", num_heads=num_heads),
+        use_ray_encoding=False)
+
+
+class Denoiser(nn.Module, ABC, Generic[T]):
+    cfg: T
+
+    def __init__(self, cfg: T) -> None:
+        super().__init__()
+        self.cfg = cfg
+
+    @abstractmethod
+    def forward(self, latents: Tensor, timestep: Tensor, cond_state: Optional[Tensor] = None) -> Tensor:
+        pass
+
+
+def param_shapes(block_out_channels, in_channels: int, out_channels: int, layers_per_block: int = 2
+                 ) -> "Dict[str, Tuple[int, ...]]":
+    """State-dict keys and shapes of the Variant-A MultiViewUNet; must equal the
+    registry the C library builds in ``mvldm_create`` (checked at handle creation)."""
+    P: Dict[str, Tuple[int, ...]] = {}
+    boc = list(block_out_channels)
+    T_ = boc[0] * 4
+
+    def conv(k, co, ci, ks):
+        P[k + ".weight"] = (co, ci, ks, ks)
+        P[k + ".bias"] = (co,)
+
+    def lin(k, co, ci, bias=True):
+        P[k + ".weight"] = (co, ci)
+        if bias:
+            P[k + ".bias"] = (co,)
+
+    def norm(k, c):
+        P[k + ".weight"] = (c,)
+        P[k + ".bias"] = (c,)
+
+    def resnet(k, ci, co):
+        norm(k + ".norm1", ci); conv(k + ".conv1", co, ci, 3); lin(k + ".time_emb_proj", co, T_)
+        norm(k + ".norm2", co); conv(k + ".conv2", co, co, 3)
+        if ci != co:
+            conv(k + ".conv_shortcut", co, ci, 1)
+
+    def mv(k, c):
+        norm(k + ".norm", c); conv(k + ".proj_in", c, c, 1)
+        tb = k + ".transformer_blocks.0"
+        for a in ("attn1", "attn2"):
+            for p in ("to_q", "to_k", "to_v"):
+                lin(f"{tb}.{a}.{p}", c, c, bias=False)
+            lin(f"{tb}.{a}.to_out.0", c, c)
+        lin(f"{tb}.ff.net.0.proj", 8 * c, c); lin(f"{tb}.ff.net.2", c, 4 * c)
+        for n in ("norm1", "norm2", "norm3"):
+            norm(f"{tb}.{n}", c)
+        conv(k + ".proj_out", c, c, 1)
+
+    L = len(boc)
+    conv("unet.conv_in", boc[0], in_channels, 3)
+    lin("unet.time_embedding.linear_1", T_, boc[0]); lin("unet.time_embedding.linear_2", T_, T_)
+    co = boc[0]
+    for l in range(L):
+        ci, co = co, boc[l]
+        for i in range(layers_per_block):
+            resnet(f"unet.down_blocks.{l}.resnets.{i}", ci if i == 0 else co, co)
+        if l != L - 1:
+            conv(f"unet.down_blocks.{l}.downsamplers.0.conv", co, co, 3)
+    resnet("unet.mid_block.resnets.0", boc[-1], boc[-1])
+    rev = boc[::-1]
+    oc = rev[0]
+    for l in range(L):
+        prev, oc = oc, rev[l]
+        ic = rev[min(l + 1, L - 1)]
+        for i in range(layers_per_block + 1):
+            resnet(f"unet.up_blocks.{l}.resnets.{i}", (prev if i == 0 else oc) + (ic if i == layers_per_block else oc), oc)
+        if l != L - 1:
+            conv(f"unet.up_blocks.{l}.upsamplers.0.conv", oc, oc, 3)
+    norm("unet.conv_norm_out", boc[0]); conv("unet.conv_out", out_channels, boc[0], 3)
+    for l in range(L):
+        mv(f"cross_attn_blocks_encoder.{l}", boc[l])
+    mv("cross_attn_blocks_mid.0", boc[-1])
+    for l in range(L):
+        mv(f"cross_attn_blocks_decoder.{l}", rev[l])
+    return P
+
+
+class _Node(nn.Module):
+    """Parameter container node; children are registered under the reference's attribute names."""
+
+    def enable_xformers_memory_efficient_attention(self, *a, **k):   # diffusion_wrapper.py:144-147
+        return None
+
+
+class _Handle:
+    """Owns the C-side handle; never copied (AveragedModel deep-copies the module: the copy re-creates it)."""
+
+    def __init__(self):
+        self.ptr = None
+        self.device = None
+        self.synced_versions = None
+
+    def __deepcopy__(self, memo):
+        return _Handle()
+
+    def close(self):
+        if self.ptr is not None:
+            try:
+                _lib.load().mvldm_destroy(self.ptr)
+            except Exception:
+                pass
+            self.ptr = None
+
+    def __del__(self):
+        self.close()
+
+
+class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
+    """Drop-in for reference ``MultiViewUNet`` (mvunet.py:43-208), Variant A (``pretrained_from=None``)."""
+
+    def __init__(self, cfg: MultiViewUNetCfg, in_channels: int, out_channels: int, *, impl: int = _lib.IMPL_TC,
+                 use_cuda_graph: bool = True) -> None:
+        super().__init__(cfg)
+        if cfg.pretrained_from is not None:
+            raise ValueError("mvldm_b200 builds the pretrained_from=None topology (SURVEY.md §0 Variant A); the SD-2.1 "
+                             "hub topology is not supported yet")
+        if cfg.multi_view_attention.name != "spatial_transformer_3d":
+            raise ValueError("only multi_view_attention.name == 'spatial_transformer_3d' is supported")
+        if cfg.multi_view_attention.num_layers != 1 or cfg.multi_view_attention.d_dot is not None:
+            raise ValueError("multi_view_attention: num_layers must be 1 and d_dot None")
+        if not (cfg.encoder_conditioning and cfg.mid_conditioning and cfg.decoder_conditioning):
+            raise ValueError("encoder/mid/decoder_conditioning must all be true")
+        ae = cfg.autoencoder
+        if any(t != "DownBlock2D" for t in ae.down_block_types) or any(t != "UpBlock2D" for t in ae.up_block_types) \
+                or ae.mid_block_type != "UNetMidBlock2D":
+            raise ValueError("only DownBlock2D / UNetMidBlock2D / UpBlock2D topologies are supported")
+        self.use_ray_encoding = cfg.use_ray_encoding
+        self.pretrained_from = cfg.pretrained_from
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.impl, self.use_cuda_graph = impl, use_cuda_graph
+        self._shapes = param_shapes(ae.block_out_channels, in_channels, out_channels)
+        for key, shape in self._shapes.items():
+            self._register(key, self._init_param(key, shape))
+        self._h = _Handle()
+        self._dirty = True
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.mark_dirty())
+
+    def mark_dirty(self) -> None:
+        """Tell the module its parameters changed in place (the packed device copy is rebuilt on the next call).
+        Done automatically after load_state_dict / .to() / .cuda(), and before every call in training mode."""
+        self._dirty = True
+
+    def _apply(self, fn, *args, **kwargs):
+        self._dirty = True
+        return super()._apply(fn, *args, **kwargs)
+
+    # ---- parameters -------------------------------------------------------------------
+    def _init_param(self, key: str, shape) -> nn.Parameter:
+        leaf = key.rsplit(".", 1)[1]
+        is_norm = ".norm" in key or key.endswith("conv_norm_out.weight") or key.endswith("conv_norm_out.bias")
+        if is_norm:
+            t = torch.ones(shape) if leaf == "weight" else torch.zeros(shape)
+        elif key.endswith("proj_out.weight") or key.endswith("proj_out.bias"):
+            t = torch.zeros(shape)                       # zero_module(): mvdream/attention.py:90-96,406-411
+        else:
+            wshape = self._shapes[key.rsplit(".", 1)[0] + ".weight"]
+            bound = 1.0 / math.sqrt(math.prod(wshape[1:]))
+            t = (torch.rand(shape) * 2 - 1) * bound
+        return nn.Parameter(t)
+
+    def _register(self, key: str, p: nn.Parameter) -> None:
+        parts = key.split(".")
+        node: nn.Module = self
+        for name in parts[:-1]:
+            if name not in node._modules:
+                node.add_module(name, _Node())
+            node = node._modules[name]
+        node.register_parameter(parts[-1], p)
+
+    # ---- library handle -----------------------------------------------------------------
+    def _ensure_handle(self, device: torch.device):
+        h = self._h
+        if h.ptr is not None and h.device == device:
+            return h
+        h.close()
+        lib = _lib.load()
+        boc = list(self.cfg.autoencoder.block_out_channels)
+        c = _lib.Config()
+        c.in_channels, c.out_channels, c.num_levels = self.in_channels, self.out_channels, len(boc)
+        for i, v in enumerate(boc):
+            c.block_out_channels[i] = v
+        c.layers_per_block, c.norm_groups = 2, 32
+        c.num_heads = self.cfg.multi_view_attention.num_heads
+        c.max_attn_res = 32
+        c.impl = self.impl
+        c.use_cuda_graph = 1 if self.use_cuda_graph else 0
+        ptr = ctypes.c_void_p()
+        _lib.check(lib.mvldm_create(ctypes.byref(c), device.index or 0, ctypes.byref(ptr)))
+        h.ptr, h.device, h.synced_versions = ptr, device, None
+        # the C registry and the Python parameter table must describe the same state dict
+        n = lib.mvldm_num_weights(ptr)
+        names = [lib.mvldm_weight_name(ptr, i).decode() for i in range(n)]
+        if set(names) != set(self._shapes):
+            raise RuntimeError("mvldm_b200: library/Python state-dict key mismatch")
+        return h
+
+    def _versions(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def refresh_weights(self, force: bool = True) -> None:
+        """(Re-)pack the module's parameters into the library's kernel layouts."""
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("mvldm_b200: the denoiser must live on a CUDA device (no CPU fallback)")
+        h = self._ensure_handle(dev)
+        vers = self._versions() if (force or self._dirty or self.training) else h.synced_versions
+        if not force and h.synced_versions is not None and h.synced_versions == vers:
+            self._dirty = False
+            return
+        lib = _lib.load()
+        stream = _lib.current_stream_ptr(dev)
+        dt = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
+        with torch.cuda.device(dev):
+            for key, p in self.state_dict(keep_vars=True).items():
+                t = p.detach().contiguous()
+                shape = (ctypes.c_int64 * t.dim())(*t.shape)
+                _lib.check(lib.mvldm_set_weight(h.ptr, key.encode(), t.data_ptr(), shape, t.dim(), dt[t.dtype], stream))
+            _lib.check(lib.mvldm_finalize_weights(h.ptr, stream))
+        h.synced_versions = vers
+        self._dirty = False
+
+    # ---- Denoiser.forward -----------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, latents: Tensor, timestep: Tensor, cond_state: Optional[Tensor] = None) -> Tensor:
+        if cond_state is not None:
+            raise ValueError("cond_state is unused by the DownBlock2D/UpBlock2D topology (mvunet.py:122)")
+        if latents.dim() != 5:
+            raise ValueError("latents must be [batch, view, channel, height, width]")
+        if not latents.is_cuda:
+            raise RuntimeError("mvldm_b200: inputs must be CUDA tensors (no CPU fallback)")
+        b, v, c, h, w = latents.shape
+        if c != self.in_channels:
+            raise ValueError(f"expected {self.in_channels} input channels, got {c}")
+        if timestep.dtype != torch.int64:
+            raise TypeError("timestep must be int64 (jaxtyping Int64 at mvunet.py:94)")
+        self.refresh_weights(force=False)
+        hd = self._h
+        # mvunet.py:102-105: [B] -> repeat over views, [B, V] -> flatten
+        t = timestep.to(latents.device)
+        t = t[:, None].expand(b, v) if t.dim() < 2 else t
+        t = t.reshape(-1).contiguous()
+        lat = latents.detach().to(torch.float32).contiguous()
+        out = torch.empty((b, v, self.out_channels, h, w), device=latents.device, dtype=torch.float32)
+        lib = _lib.load()
+        with torch.cuda.device(latents.device):
+            _lib.check(lib.mvldm_forward(hd.ptr, _lib.current_stream_ptr(latents.device), lat.data_ptr(), t.data_ptr(),
+                                         b, v, h, w, out.data_ptr()))
+        return out
+
+    # ---- diagnostics ---------------------------------------------------------------------
+    def last_launch_count(self) -> int:
+        return _lib.load().mvldm_last_launch_count(self._h.ptr) if self._h.ptr else 0
+
+    def enable_taps(self, on: bool = True) -> None:
+        dev = next(self.parameters()).device
+        _lib.check(_lib.load().mvldm_enable_taps(self._ensure_handle(dev).ptr, 1 if on else 0))
+
+    def tap(self, name: str) -> Tensor:
+        lib = _lib.load()
+        dev = next(self.parameters()).device
+        n = ctypes.c_int64()
+        _lib.check(lib.mvldm_debug_tap(self._h.ptr, _lib.current_stream_ptr(dev), name.encode(), None, ctypes.byref(n)))
+        out = torch.empty(n.value, device=dev, dtype=torch.float32)
+        _lib.check(lib.mvldm_debug_tap(self._h.ptr, _lib.current_stream_ptr(dev), name.encode(), out.data_ptr(),
+                                       ctypes.byref(n)))
+        return out
+
+    def workspace_bytes(self, b: int, v: int, h: int, w: int) -> int:
+        self.refresh_weights(force=False)
+        return int(_lib.load().mvldm_workspace_bytes(self._h.ptr, b, v, h, w))
+
+
+DENOISER = {"mv_unet": MultiViewUNet}
+DenoiserCfg = MultiViewUNetCfg
+
+
+def get_denoiser(denoiser_cfg: DenoiserCfg, in_channels: int, out_channels: int) -> Denoiser:
+    return DENOISER[denoiser_cfg.name](denoiser_cfg, in_channels, out_channels)

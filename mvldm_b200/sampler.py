@@ -1,0 +1,92 @@
+"""The denoising loop of the reference's ``DiffusionWrapper`` on the CUDA path.
+
+Mirrors reference ``src/model/diffusion_wrapper.py``: ``ray_encode`` / ``generate_image_rays`` (:169-190,
+:301-322), ``step`` (:413-453) and the loop of ``sample`` (:455-490) between the two VAE calls (latents in,
+latents out).  Input concat, the denoiser forward(s), CFG and the DDIM update all run in this package's
+kernels; this module only sequences them.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from .scheduler import DDIMScheduler, fused_cfg_ddim_step
+
+
+def ray_encode(extrinsics: Tensor, intrinsics: Tensor, h: int, w: int, use_plucker: bool = False) -> Tensor:
+    """extrinsics [B,V,4,4] (cam-to-world), intrinsics [B,V,3,3] (normalised) -> ray encodings [B,V,6,h,w]
+    for use_ray_encoding=false / srt_ray_encoding=false (the released settings, baseline.yaml:50-51)."""
+    if not extrinsics.is_cuda:
+        raise RuntimeError("mvldm_b200: ray_encode needs CUDA tensors (no CPU fallback)")
+    B, V = extrinsics.shape[:2]
+    e = extrinsics.detach().to(torch.float32).contiguous()
+    k = intrinsics.detach().to(torch.float32).contiguous()
+    out = torch.empty((B, V, 6, h, w), device=e.device, dtype=torch.float32)
+    with torch.cuda.device(e.device):
+        _lib.check(_lib.load().mvldm_raymap(_lib.current_stream_ptr(e.device), e.data_ptr(), k.data_ptr(), B * V, h, w,
+                                            1 if use_plucker else 0, out.data_ptr()))
+    return out
+
+
+def build_inputs(x_t: Tensor, context_latents: Optional[Tensor], rays: Tensor, ray_view_offset: int = 0) -> Tensor:
+    """[latent | mask | rays] per view, context views first (diffusion_wrapper.py:429-432 / :438)."""
+    B, v_t, _, h, w = x_t.shape
+    v_c = 0 if context_latents is None else context_latents.shape[1]
+    R = rays.shape[2]
+    out = torch.empty((B, v_c + v_t, 5 + R, h, w), device=x_t.device, dtype=torch.float32)
+    x = x_t.detach().to(torch.float32).contiguous()
+    c = context_latents.detach().to(torch.float32).contiguous() if v_c else None
+    r = rays.detach().to(torch.float32).contiguous()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().mvldm_build_inputs(_lib.current_stream_ptr(x.device), x.data_ptr(),
+                                                  c.data_ptr() if v_c else None, r.data_ptr(), B, v_c, v_t,
+                                                  rays.shape[1], ray_view_offset, R, h * w, out.data_ptr()))
+    return out
+
+
+class DenoisingPath:
+    """``step`` / ``sample`` of the reference wrapper with the same knobs (use_cfg, cfg_scale, use_plucker)."""
+
+    def __init__(self, denoiser, scheduler: DDIMScheduler, use_cfg: bool = False, cfg_scale: float = 3.0,
+                 use_plucker: bool = False):
+        self.denoiser, self.scheduler = denoiser, scheduler
+        self.use_cfg, self.cfg_scale, self.use_plucker = use_cfg, cfg_scale, use_plucker
+
+    def set_timesteps(self, num: int) -> None:
+        self.scheduler.set_timesteps(num)
+
+    def step(self, model, x_t: Tensor, ts, context_inputs: Tensor, ray_encodings: Tensor,
+             target_mask: Optional[Tensor] = None) -> Tensor:
+        """diffusion_wrapper.py:413-453.  ``context_inputs`` is [B, v_c, 5, h, w] (latent + zero mask) as in the
+        reference; ``target_mask`` is accepted for signature parity (it is all ones, :476)."""
+        B, v_c = context_inputs.shape[:2]
+        v_t = x_t.shape[1]
+        ts = int(ts)
+        dev = x_t.device
+        x_in = self.scheduler.scale_model_input(x_t, ts)
+        t_c = torch.zeros((B, v_c), dtype=torch.long, device=dev)
+        t_t = torch.full((B, v_t), ts, dtype=torch.long, device=dev)
+        inputs = build_inputs(x_in, context_inputs[:, :, :4], ray_encodings)
+        pred_c = model.forward(inputs, torch.cat([t_c, t_t], dim=1))
+        pred_u = None
+        if self.use_cfg:
+            pred_u = model.forward(build_inputs(x_in, None, ray_encodings, ray_view_offset=v_c), t_t)
+        return fused_cfg_ddim_step(self.scheduler, pred_c, pred_u, self.cfg_scale, v_c, ts, x_t)
+
+    @torch.no_grad()
+    def sample(self, context_latents: Tensor, x_T: Tensor, extrinsics: Tensor, intrinsics: Tensor,
+               record: Optional[list] = None) -> Tensor:
+        """The loop of DiffusionWrapper.sample (diffusion_wrapper.py:473-488) on latents."""
+        B, v_c, _, h, w = context_latents.shape
+        x_t = x_T * self.scheduler.init_noise_sigma
+        ctx = torch.cat([context_latents, torch.zeros_like(context_latents[:, :, :1])], dim=2)
+        rays = ray_encode(extrinsics, intrinsics, h, w, self.use_plucker)
+        for ts in self.scheduler.timesteps:
+            x_t = self.step(self.denoiser, x_t, ts, ctx, rays)
+            if record is not None:
+                record.append((int(ts), x_t.clone()))
+        return x_t

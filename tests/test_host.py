@@ -1,0 +1,117 @@
+"""CPU: host-side mirror of the reference interfaces, the C-ABI surface, and scene sharding (gloo)."""
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+import mvldm_b200 as mv
+from helpers import GOLD, ROOT
+from mvldm_b200 import _lib
+from oracle import mvldm_oracle as O
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "mvldm_b200.h")).read()
+    declared = set(re.findall(r"\b(mvldm_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libmvldm_b200.so does not export {name}"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert lib.mvldm_version() >= 100
+
+
+def test_struct_layouts_match_header():
+    import ctypes
+    assert ctypes.sizeof(_lib.Config) == 4 * (3 + 4 + 6)
+    assert ctypes.sizeof(_lib.ASeg) == 8 + 6 * 4 + 9 + 9 + 2 + 9 * 4      # ptr, 6 ints, 2x9 int8 (+2 pad), 9 ints
+    assert _lib.GemmDesc.seg.offset == 8 and ctypes.sizeof(_lib.GemmDesc) % 8 == 0
+
+
+def test_no_gpu_is_an_error_not_a_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = mv.MultiViewUNet(mv.default_cfg(), 11, 4)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 2, 11, 32, 32), torch.zeros(1, dtype=torch.int64))
+    with pytest.raises(RuntimeError):
+        mv.DDIMScheduler(clip_sample=False).step(torch.zeros(1, 1, 4, 8, 8), 0, torch.zeros(1, 1, 4, 8, 8))
+
+
+def test_state_dict_keys_match_reference_module(oracle_cfg):
+    m = mv.MultiViewUNet(mv.default_cfg(), 11, 4)
+    sd = m.state_dict()
+    ref = O.param_shapes(oracle_cfg)      # == the reference module's keys (make_golden loads them strict=True)
+    assert set(sd) == set(ref)
+    assert all(tuple(sd[k].shape) == ref[k][0] for k in ref)
+    # zero-init proj_out like the reference (mvdream/attention.py:406-411)
+    assert float(sd["cross_attn_blocks_mid.0.proj_out.weight"].abs().max()) == 0.0
+    assert mv.get_denoiser(mv.default_cfg(), 11, 4).__class__ is mv.MultiViewUNet
+    assert "mv_unet" in mv.DENOISER
+
+
+def test_unsupported_configs_raise():
+    cfg = mv.default_cfg()
+    cfg.pretrained_from = "stabilityai/stable-diffusion-2-1"
+    with pytest.raises(ValueError):
+        mv.MultiViewUNet(cfg, 11, 4)
+    cfg = mv.default_cfg()
+    cfg.autoencoder.down_block_types = ["CrossAttnDownBlock2D"] * 4
+    with pytest.raises(ValueError):
+        mv.MultiViewUNet(cfg, 11, 4)
+
+
+def test_scheduler_mirror_matches_golden():
+    g = np.load(os.path.join(GOLD, "g4_ddim.npz"))
+    cfg = mv.SchedulerCfg("ddim", 1000, 25, None, mv.DDIMSchedulerCfg(clip_sample=False))
+    s = mv.get_scheduler(cfg)
+    np.testing.assert_array_equal(s.alphas_cumprod.numpy(), g["alphas_cumprod"])
+    assert s.init_noise_sigma == 1.0 and s.config.prediction_type == "epsilon"
+    for n in (25, 50, 70):
+        s.set_timesteps(n)
+        np.testing.assert_array_equal(s.timesteps.numpy(), g[f"timesteps_{n}"])
+        co = np.array([s.coefficients(int(t)) for t in s.timesteps])
+        np.testing.assert_allclose(co, g[f"coef_{n}"], rtol=0, atol=0)
+    x = torch.randn(3, 2, 4, 8, 8)
+    n = torch.randn_like(x)
+    t = torch.tensor([0, 500, 999])
+    ref = O.DDIMOracle().add_noise(x, n, t)
+    torch.testing.assert_close(s.add_noise(x, n, t), ref)
+    assert s.scale_model_input(x, 3) is x
+    with pytest.raises(NotImplementedError):
+        mv.DDIMScheduler(clip_sample=True)
+    with pytest.raises(ValueError):
+        mv.DDIMScheduler(clip_sample=False).coefficients(10)      # set_timesteps not called
+
+
+def test_scene_slices_partition():
+    for n in (1, 7, 64):
+        for ws in (1, 2, 4, 8):
+            sl = [mv.scene_slice(n, r, ws) for r in range(ws)]
+            assert sl[0][0] == 0 and sl[-1][1] == n
+            assert all(sl[i][1] == sl[i + 1][0] for i in range(ws - 1))
+            assert max(b - a for a, b in sl) - min(b - a for a, b in sl) <= 1
+    with pytest.raises(ValueError):
+        mv.scene_slice(4, 2, 2)
+
+
+def _gather_worker(rank, ws, port, n):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=ws)
+    a, b = mv.scene_slice(n, rank, ws)
+    local = torch.arange(a, b, dtype=torch.float32)[:, None].repeat(1, 3)
+    full = mv.gather_scenes(local, n)
+    assert full.shape == (n, 3) and torch.equal(full[:, 0], torch.arange(n, dtype=torch.float32))
+    dist.destroy_process_group()
+
+
+def test_gather_scenes_gloo_world2():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_gather_worker, args=(2, port, 5), nprocs=2, join=True)
