@@ -46,7 +46,9 @@ extern thread_local int g_launch_count;
 // ---- kernels (host launchers) -----------------------------------------------------------------
 // gemm_simt.cu / gemm_tc.cu
 void gemm_simt(cudaStream_t s, const mvldm_gemm_desc& d);
-void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d);
+// workspace: fp32 split-K scratch (gemm_tc_workspace_bytes(d) bytes) or NULL/0 to force a single pass
+size_t gemm_tc_workspace_bytes(const mvldm_gemm_desc& d);
+void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t workspace_bytes);
 // attn_simt.cu / attn_tc.cu
 void attention_simt(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, int heads, int d, int dpad);
 void attention_tc(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, int heads, int d, int dpad);

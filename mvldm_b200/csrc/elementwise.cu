@@ -124,59 +124,104 @@ __global__ void small_linear_kernel(const float* __restrict__ in, int rows, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// GroupNorm.  Pass 1: one CTA per (image, group) -> (mean, rstd), two-pass variance, fixed reduction
-// order (bit-stable, no atomics).  Pass 2: elementwise normalise * gamma + beta (+SiLU), 16-byte vectors.
+// GroupNorm over NHWC bf16.  Pass 1 (gn_partial): grid (pixel chunks, images); every thread owns one
+// 8-channel vector column and walks the chunk's pixels with 16-byte loads, per-channel (sum, sum of squares)
+// are combined through shared memory in a fixed order and folded to per-group partials
+// [image][chunk][group][2] (no atomics: bit-stable).  Pass 2 (gn_apply): the first warp folds the partials of
+// its image to (mean, rstd) in double, then the CTA normalises * gamma + beta (+SiLU) with 16-byte vectors.
 // The two sources implement GroupNorm over torch.cat((hidden, skip), dim=1) without materialising the cat.
 // ---------------------------------------------------------------------------------------------
-__global__ void gn_stats_kernel(const bf16* __restrict__ x0, int c0, const bf16* __restrict__ x1, int c1, int hw,
-                                int groups, float eps, float* __restrict__ stats) {
-  __shared__ float red[33];
-  const int img = blockIdx.x / groups, g = blockIdx.x % groups;
-  const int C = c0 + c1, cg = C / groups;
-  const int cnt = hw * cg;
-  const int ch0 = g * cg;
-  auto at = [&](int idx) -> float {
-    const int p = idx / cg, c = ch0 + idx % cg;
-    return c < c0 ? __bfloat162float(x0[((int64_t)img * hw + p) * c0 + c])
-                  : __bfloat162float(x1[((int64_t)img * hw + p) * c1 + (c - c0)]);
-  };
-  float s = 0.f;
-  for (int i = threadIdx.x; i < cnt; i += blockDim.x) s += at(i);
-  const float mean = block_sum(s, red) / (float)cnt;
-  float q = 0.f;
-  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-    const float d = at(i) - mean;
-    q += d * d;
+constexpr int GN_MAXC = 2560;
+constexpr int GN_MAXP = 64;
+
+__global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict__ x0, int c0, const bf16* __restrict__ x1,
+                                                         int c1, int hw, int groups, int pix, float* __restrict__ partials) {
+  __shared__ float red_s[GN_MAXC], red_q[GN_MAXC];
+  const int C = c0 + c1, ncv = C / 8, cg = C / groups;
+  const int img = blockIdx.y, chunk = blockIdx.x, P = gridDim.x;
+  const int t = threadIdx.x;
+  const int lanes_p = ncv <= 256 ? 256 / ncv : 1;
+  const int pl = ncv <= 256 ? t / ncv : 0;
+  const int64_t pix0 = (int64_t)img * hw + (int64_t)chunk * pix;
+  if (pl < lanes_p) {
+    for (int cv = ncv <= 256 ? t % ncv : t; cv < ncv; cv += 256) {
+      float sa[8], qa[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sa[j] = qa[j] = 0.f;
+      const int c = cv * 8;
+      for (int pp = pl; pp < pix; pp += lanes_p) {
+        float f[8];
+        if (c < c0) load8(x0 + (pix0 + pp) * c0 + c, f);
+        else load8(x1 + (pix0 + pp) * c1 + (c - c0), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          sa[j] += f[j];
+          qa[j] = fmaf(f[j], f[j], qa[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        red_s[pl * C + c + j] = sa[j];
+        red_q[pl * C + c + j] = qa[j];
+      }
+      if (ncv <= 256) break;
+    }
   }
-  const float var = block_sum(q, red) / (float)cnt;
-  if (threadIdx.x == 0) {
-    stats[2 * blockIdx.x] = mean;
-    stats[2 * blockIdx.x + 1] = rsqrtf(var + eps);
+  __syncthreads();
+  if (t < groups) {
+    float S = 0.f, Q = 0.f;
+    for (int l = 0; l < lanes_p; ++l)
+      for (int c = t * cg; c < (t + 1) * cg; ++c) {
+        S += red_s[l * C + c];
+        Q += red_q[l * C + c];
+      }
+    float* o = partials + (((int64_t)img * P + chunk) * groups + t) * 2;
+    o[0] = S;
+    o[1] = Q;
   }
 }
 
-__global__ void gn_apply_kernel(const bf16* __restrict__ x0, int c0, const bf16* __restrict__ x1, int c1, int n_img,
-                                int hw, int groups, const float* __restrict__ stats, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, int silu, bf16* __restrict__ out) {
+__global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x0, int c0, const bf16* __restrict__ x1,
+                                                       int c1, int hw, int groups, float eps, int P,
+                                                       const float* __restrict__ partials, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, int silu, bf16* __restrict__ out) {
+  __shared__ float s_mean[64], s_rstd[64];
   const int C = c0 + c1, cg = C / groups, cv = C / 8;
-  const int64_t total = (int64_t)n_img * hw * cv;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  const int img = blockIdx.y;
+  if (threadIdx.x < groups) {
+    double S = 0.0, Q = 0.0;
+    for (int k = 0; k < P; ++k) {
+      const float* o = partials + (((int64_t)img * P + k) * groups + threadIdx.x) * 2;
+      S += (double)o[0];
+      Q += (double)o[1];
+    }
+    const double cnt = (double)hw * cg;
+    const double mean = S / cnt;
+    double var = Q / cnt - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const int64_t per_img = (int64_t)hw * cv;
+  const int64_t lo = per_img * blockIdx.x / gridDim.x, hi = per_img * (blockIdx.x + 1) / gridDim.x;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const int c = (int)(i % cv) * 8;
-    const int64_t pix = i / cv;
-    const int img = (int)(pix / hw);
+    const int64_t pixel = (int64_t)img * hw + i / cv;
     float f[8];
-    if (c < c0)
-      load8(x0 + pix * c0 + c, f);
-    else
-      load8(x1 + pix * c1 + (c - c0), f);
+    if (c < c0) load8(x0 + pixel * c0 + c, f);
+    else load8(x1 + pixel * c1 + (c - c0), f);
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int g = (c + j) / cg;
-      const float mean = stats[2 * (img * groups + g)], rstd = stats[2 * (img * groups + g) + 1];
-      float v = (f[j] - mean) * rstd * gamma[c + j] + beta[c + j];
+      const float v = (f[j] - s_mean[g]) * s_rstd[g] * gg[j] + bb[j];
       f[j] = silu ? silu_f(v) : v;
     }
-    store8(out + pix * C + c, f);
+    store8(out + pixel * C + c, f);
   }
 }
 
@@ -386,18 +431,20 @@ void small_linear(cudaStream_t s, const float* in, int rows, int k, const bf16* 
   MV_LAUNCHED();
 }
 
-size_t groupnorm_scratch_floats(int n_img, int groups) { return (size_t)n_img * groups * 2; }
+size_t groupnorm_scratch_floats(int n_img, int groups) { return (size_t)n_img * GN_MAXP * groups * 2; }
 
 void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, int n_img, int hw, int groups,
                float eps, const float* gamma, const float* beta, bool silu, bf16* out, float* scratch) {
   const int C = c0 + c1;
-  MV_CHECK(C % groups == 0, "groupnorm: channels not divisible by groups");
-  MV_CHECK(c0 % 8 == 0 && c1 % 8 == 0, "groupnorm: channel counts must be multiples of 8");
-  gn_stats_kernel<<<n_img * groups, 256, 0, s>>>(x0, c0, x1, c1, hw, groups, eps, scratch);
+  MV_CHECK(C % groups == 0 && groups <= 64, "groupnorm: channels not divisible by groups (<= 64 groups)");
+  MV_CHECK(c0 % 8 == 0 && c1 % 8 == 0 && C <= GN_MAXC, "groupnorm: channel counts must be multiples of 8, <= 2560");
+  // pixel chunks per image: enough CTAs to cover the machine twice, at least 4 pixels each
+  int P = 1;
+  while (P < GN_MAXP && n_img * P < 296 && hw % (2 * P) == 0 && hw / (2 * P) >= 4) P *= 2;
+  gn_partial_kernel<<<dim3(P, n_img), 256, 0, s>>>(x0, c0, x1, c1, hw, groups, hw / P, scratch);
   MV_LAUNCHED();
-  const int64_t total = (int64_t)n_img * hw * (C / 8);
-  gn_apply_kernel<<<grid_for(total, 256), 256, 0, s>>>(x0, c0, x1, c1, n_img, hw, groups, scratch, gamma, beta,
-                                                        silu ? 1 : 0, out);
+  gn_apply_kernel<<<dim3(P, n_img), 256, 0, s>>>(x0, c0, x1, c1, hw, groups, eps, P, scratch, gamma, beta, silu ? 1 : 0,
+                                                  out);
   MV_LAUNCHED();
 }
 

@@ -58,7 +58,9 @@ struct TcParams {
   TcSeg seg[MVLDM_MAX_SEGS];
   int nseg;
   int M, N, num_kb;
-  int hw, ow;  // output pixels per image / row width (tile -> image coordinates)
+  int kb_per_split;  // k-blocks per grid.z slice (== num_kb when not split)
+  float* partial;    // split-K: fp32 partial tiles [splits][M][N]; NULL when not split
+  int hw, ow;        // output pixels per image / row width (tile -> image coordinates)
   const float* bias;
   const float* rowvec;
   int rowvec_ld;
@@ -90,6 +92,8 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tc
   const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-B alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int nkb = min(p.num_kb - kb_begin, p.kb_per_split);
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.nseg; ++i) tc::tma_prefetch_desc(&p.tmA[i]);
@@ -112,19 +116,29 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tc
     if (lane == 0) {
       const int img0 = m0 / p.hw;
       const int y0 = (m0 - img0 * p.hw) / p.ow;
-      int kb = 0;
-      for (int s = 0; s < p.nseg; ++s) {
+      // locate (segment, tap, channel block) of this CTA's first k-block
+      int s = 0, t = 0, cb = kb_begin;
+      while (cb >= p.seg[s].ntaps * p.seg[s].ncblk) {
+        cb -= p.seg[s].ntaps * p.seg[s].ncblk;
+        ++s;
+      }
+      t = cb / p.seg[s].ncblk;
+      cb -= t * p.seg[s].ncblk;
+      for (int i = 0; i < nkb; ++i) {
         const TcSeg& sg = p.seg[s];
-        for (int t = 0; t < sg.ntaps; ++t) {
-          for (int cb = 0; cb < sg.ncblk; ++cb, ++kb) {
-            const int stage = kb % STAGES;
-            const uint32_t par = ((kb / STAGES) & 1) ^ 1;
-            tc::mbar_wait(tc::smem_u32(&bar_empty[stage]), par);
-            const uint32_t full = tc::smem_u32(&bar_full[stage]);
-            tc::mbar_expect_tx(full, STAGE_BYTES);
-            const uint32_t sa = smem_base + stage * STAGE_BYTES;
-            tc::tma_load_4d(sa, &p.tmA[s], full, sg.coff[t] + cb * BK, sg.dw[t], y0 * sg.stride + sg.dh[t], img0);
-            tc::tma_load_2d(sa + A_BYTES, &p.tmB, full, kb * BK, n0);
+        const int stage = i % STAGES;
+        const uint32_t par = ((i / STAGES) & 1) ^ 1;
+        tc::mbar_wait(tc::smem_u32(&bar_empty[stage]), par);
+        const uint32_t full = tc::smem_u32(&bar_full[stage]);
+        tc::mbar_expect_tx(full, STAGE_BYTES);
+        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+        tc::tma_load_4d(sa, &p.tmA[s], full, sg.coff[t] + cb * BK, sg.dw[t], y0 * sg.stride + sg.dh[t], img0);
+        tc::tma_load_2d(sa + A_BYTES, &p.tmB, full, (kb_begin + i) * BK, n0);
+        if (++cb == sg.ncblk) {
+          cb = 0;
+          if (++t == sg.ntaps) {
+            t = 0;
+            ++s;
           }
         }
       }
@@ -133,7 +147,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tc
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc = tc::umma_idesc_bf16(BM, BN, false, false);
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      for (int kb = 0; kb < nkb; ++kb) {
         const int stage = kb % STAGES;
         tc::mbar_wait(tc::smem_u32(&bar_full[stage]), (kb / STAGES) & 1);
         tc::tc_fence_after();
@@ -163,7 +177,13 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tc
       __syncwarp();
       tc::tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + c0, r);
       tc::tmem_ld_wait();
-      if (ok) {
+      if (ok && p.partial) {  // split-K: raw fp32 partial, reduced (+ epilogue) by splitk_reduce_kernel
+        float4* pp = reinterpret_cast<float4*>(p.partial + ((int64_t)blockIdx.z * p.M + m) * p.N + n0 + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          pp[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                              __uint_as_float(r[4 * j + 3]));
+      } else if (ok) {
       const int n = n0 + c0;
       float v[32];
 #pragma unroll
@@ -229,22 +249,81 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tc
   }
 }
 
+// split-K second pass: out[m, n] = sum_z partial[z][m][n] (fixed order: bit-stable) + bias + rowvec + residual -> bf16
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N,
+                                                            int hw, const float* __restrict__ bias,
+                                                            const float* __restrict__ rowvec, int rowvec_ld,
+                                                            const bf16* __restrict__ residual, int res_ld,
+                                                            bf16* __restrict__ out, int ldo) {
+  const int nv = N / 8;
+  const int64_t total = (int64_t)M * nv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / nv), n = (int)(i % nv) * 8;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int z = 0; z < splits; ++z) {
+      const float4* pp = reinterpret_cast<const float4*>(partial + ((int64_t)z * M + m) * N + n);
+      const float4 a = pp[0], b = pp[1];
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (bias) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += bias[n + j];
+    }
+    if (rowvec) {
+      const float* rv = rowvec + (int64_t)(m / hw) * rowvec_ld + n;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += rv[j];
+    }
+    if (residual) {
+      const uint4 u = *reinterpret_cast<const uint4*>(residual + (int64_t)m * res_ld + n);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+        v[2 * e] += f.x;
+        v[2 * e + 1] += f.y;
+      }
+    }
+    *reinterpret_cast<uint4*>(out + (int64_t)m * ldo + n) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+}
+
 template <int BN, int STAGES>
-void launch(cudaStream_t s, const TcParams& p) {
+void launch(cudaStream_t s, const TcParams& p, int splits) {
   constexpr int smem = STAGES * (A_BYTES + BN * BK * 2) + 1024;
   static bool configured = false;
   if (!configured) {
     MV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid(ceil_div(p.M, BM), p.N / BN);
+  dim3 grid(ceil_div(p.M, BM), p.N / BN, splits);
   gemm_tc_kernel<BN, STAGES><<<grid, 192, smem, s>>>(p);
   MV_LAUNCHED();
 }
 
+int pick_bn(int n) { return n % 128 == 0 ? 128 : (n % 64 == 0 ? 64 : (n % 32 == 0 ? 32 : 0)); }
+
+// Split-K keeps all 148 SMs streaming weights when M*N gives only a handful of tiles (the 4x4 / 8x8 levels at
+// batch 1 are weight-bandwidth-bound: e.g. 59 MB of filter for 7.5 GFLOP).
+int pick_splits(const mvldm_gemm_desc& d) {
+  const int BN = pick_bn(d.n);
+  if (BN == 0 || d.mode != 0) return 1;
+  const int tiles = ceil_div(d.n_img * d.oh * d.ow, BM) * (d.n / BN);
+  const int num_kb = d.k / BK;
+  if (tiles >= 100 || num_kb < 32) return 1;
+  const int splits = std::min(148 / tiles, num_kb / 8);
+  return splits >= 2 ? splits : 1;
+}
+
 }  // namespace
 
-void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d) {
+size_t gemm_tc_workspace_bytes(const mvldm_gemm_desc& d) {
+  const int splits = pick_splits(d);
+  return splits > 1 ? (size_t)splits * d.n_img * d.oh * d.ow * d.n * sizeof(float) : 0;
+}
+
+void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t workspace_bytes) {
   TcParams p{};
   const int hw = d.oh * d.ow;
   p.M = d.n_img * hw;
@@ -285,11 +364,13 @@ void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d) {
   p.nseg = d.nseg;
   MV_CHECK(ktot == d.k, "gemm_tc: K mismatch between segments and weights");
   p.num_kb = d.k / BK;
-  int BN = 0;
-  if (d.n % 128 == 0) BN = 128;
-  else if (d.n % 64 == 0) BN = 64;
-  else if (d.n % 32 == 0) BN = 32;
+  const int BN = pick_bn(d.n);
   MV_CHECK(BN != 0, "gemm_tc: N must be a multiple of 32");
+  int splits = pick_splits(d);
+  if (splits > 1 && gemm_tc_workspace_bytes(d) > workspace_bytes) splits = 1;  // no scratch: plain single-pass GEMM
+  p.kb_per_split = ceil_div(p.num_kb, splits);
+  splits = ceil_div(p.num_kb, p.kb_per_split);
+  p.partial = splits > 1 ? reinterpret_cast<float*>(workspace) : nullptr;
   MV_CHECK(d.mode != 2 || d.n == 32, "gemm_tc: NCHW head output expects N padded to 32");
   {
     const uint64_t dims[2] = {(uint64_t)d.k, (uint64_t)d.n};
@@ -308,9 +389,16 @@ void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d) {
   p.ldo = d.ldo;
   p.n_valid = d.n_valid;
   if (d.mode == 0) MV_CHECK(d.ldo % 8 == 0 && (!d.residual || d.res_ld % 8 == 0), "gemm_tc: row pitch must be a multiple of 8");
-  if (BN == 128) launch<128, 3>(s, p);
-  else if (BN == 64) launch<64, 4>(s, p);
-  else launch<32, 4>(s, p);
+  if (BN == 128) launch<128, 3>(s, p, splits);
+  else if (BN == 64) launch<64, 4>(s, p, splits);
+  else launch<32, 4>(s, p, splits);
+  if (splits > 1) {
+    const int64_t total = (int64_t)p.M * (p.N / 8);
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+    splitk_reduce_kernel<<<blocks, 256, 0, s>>>(p.partial, splits, p.M, p.N, p.hw, p.bias, p.rowvec, p.rowvec_ld,
+                                                 p.residual, p.res_ld, reinterpret_cast<bf16*>(p.out), p.ldo);
+    MV_LAUNCHED();
+  }
 }
 
 }  // namespace mvldm

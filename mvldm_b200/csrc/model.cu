@@ -93,7 +93,7 @@ struct Plan {
   int B = 0, V = 0, H = 0, W = 0;
   DevBuf arena_mem;
   size_t arena_bytes = 0;
-  DevBuf in_latents, in_t, out_eps;
+  DevBuf in_latents, in_t, out_eps, splitk;
   cudaGraphExec_t graph = nullptr;
   int graph_launches = 0;
   ~Plan() {
@@ -141,6 +141,8 @@ struct mvldm_handle_s {
   cudaStream_t capture_stream = nullptr;  // graphs are recorded here: the caller's stream may be the legacy NULL stream
   Arena arena;
   bool dry = true;
+  size_t splitk_need = 0, splitk_bytes = 0;  // split-K fp32 scratch shared by all GEMMs of a forward
+  void* splitk_ws = nullptr;
 
   // =========================== registry ===========================
   void reg(const std::string& k, std::vector<int64_t> shape) {
@@ -442,9 +444,12 @@ struct mvldm_handle_s {
     return s;
   }
   void run_gemm(mvldm_gemm_desc& d) {
-    if (dry) return;
+    if (dry) {
+      if (cfg.impl != MVLDM_IMPL_SIMT) splitk_need = std::max(splitk_need, gemm_tc_workspace_bytes(d));
+      return;
+    }
     if (cfg.impl == MVLDM_IMPL_SIMT) gemm_simt(stream, d);
-    else gemm_tc(stream, d);
+    else gemm_tc(stream, d, splitk_ws, splitk_bytes);
   }
   // out = A-segments x W^T (+bias +rowvec +residual), bf16 NHWC
   void gemm(std::initializer_list<mvldm_aseg> segs, const Packed& w, const Act& out, const float* rowvec = nullptr,
@@ -619,9 +624,11 @@ struct mvldm_handle_s {
     dry = true;
     arena = Arena();
     arena.measuring = true;
+    splitk_need = 0;
     run(nullptr, nullptr, B, V, H, W, nullptr);
     p->arena_bytes = arena.peak;
     p->arena_mem.alloc(p->arena_bytes);
+    p->splitk.alloc(splitk_need);
     p->in_latents.alloc((size_t)B * V * cfg.in_channels * H * W * sizeof(float));
     p->in_t.alloc((size_t)B * V * sizeof(int64_t));
     p->out_eps.alloc((size_t)B * V * cfg.out_channels * H * W * sizeof(float));
@@ -641,6 +648,8 @@ struct mvldm_handle_s {
     arena.measuring = false;
     arena.base = reinterpret_cast<char*>(p.arena_mem.p);
     arena.cap = p.arena_bytes;
+    splitk_ws = p.splitk.p;
+    splitk_bytes = p.splitk.bytes;
     dry = false;
     g_launch_count = 0;
     const size_t in_bytes = (size_t)B * V * cfg.in_channels * H * W * sizeof(float);
@@ -854,8 +863,17 @@ int mvldm_raymap(void* stream, const float* extr, const float* intr, int n, int 
 int mvldm_op_gemm(void* stream, int impl, const mvldm_gemm_desc* d) {
   MV_API_BEGIN
   MV_CHECK(d, "null argument");
-  if (impl == MVLDM_IMPL_TC) gemm_tc((cudaStream_t)stream, *d);
-  else gemm_simt((cudaStream_t)stream, *d);
+  if (impl == MVLDM_IMPL_TC) {
+    static DevBuf scratch;  // op-level entry point (tests): grown on demand, never shrunk
+    const size_t need = gemm_tc_workspace_bytes(*d);
+    if (need > scratch.bytes) {
+      MV_CUDA(cudaDeviceSynchronize());
+      scratch.alloc(need);
+    }
+    gemm_tc((cudaStream_t)stream, *d, scratch.p, scratch.bytes);
+  } else {
+    gemm_simt((cudaStream_t)stream, *d);
+  }
   MV_API_END
 }
 

@@ -32,6 +32,8 @@ def _conv_ref(xb, wp, b, cout, cin, stride):
     (8, 64, 96, 4, 1),      # N = 96 -> 32-wide tiles
     (1, 64, 64, 4, 1),      # a single 16-pixel image: tile mostly out of range
     (4, 64, 64, 32, 2), (4, 128, 128, 16, 2), (8, 64, 64, 8, 2),
+    (8, 1280, 256, 4, 1),   # weight-streaming shape: few tiles, K = 11520 -> split-K + fixed-order reduce
+    (8, 640, 128, 8, 1),    # 4 x 1 tiles, K = 5760 -> split-K
 ])
 def test_conv3x3(impl, n, cin, cout, hw, stride):
     torch.manual_seed(n * 1000 + cin + cout + hw + stride)
@@ -93,6 +95,31 @@ def test_conv_plus_shortcut_segments_and_head(impl):
     assert rel_err(out, ref) < 1e-5           # fp32 out: only summation order differs
 
 
+def test_splitk_epilogue_and_segments():
+    """split-K path with bias + per-image row vector + residual, and with the 3-segment conv+shortcut operand"""
+    torch.manual_seed(6)
+    n, hw, cin, co = 8, 4, 1280, 256
+    x = nhwc_bf16(torch.randn(n, cin, hw, hw)).cuda()
+    sk = nhwc_bf16(torch.randn(n, 640, hw, hw)).cuda()
+    wc = torch.randn(co, cin, 3, 3) / (3 * cin ** 0.5)
+    ws = torch.randn(co, 640, 1, 1) / 640 ** 0.5
+    b, rv = torch.randn(co).cuda(), torch.randn(n, co).cuda()
+    res = torch.randn(n * hw * hw, co).to(torch.bfloat16).cuda()
+    tof = lambda T: T.float().cpu().permute(0, 3, 1, 2)  # noqa: E731
+    nhwc = lambda T: T.permute(0, 2, 3, 1).reshape(-1, co)  # noqa: E731
+    base = F.conv2d(tof(x), wc.to(torch.bfloat16).float(), padding=1)
+    for impl in (0, 1):
+        out = run_gemm(impl, [conv_seg(x)], n, hw, hw, pack_conv_weight(wc).cuda(), bias=b, rowvec=rv, residual=res)
+        ref = nhwc(base + b.cpu()[None, :, None, None] + rv.cpu()[:, :, None, None]) + res.float().cpu()
+        assert rel_err(out.float(), ref) < BF16_TOL
+        wp = torch.cat([pack_conv_weight(wc), pack_conv_weight(ws)], 1).contiguous().cuda()
+        out = run_gemm(impl, [conv_seg(x), conv_seg(sk, 1, 1)], n, hw, hw, wp)
+        ref = nhwc(base + F.conv2d(tof(sk), ws.to(torch.bfloat16).float()))
+        assert rel_err(out.float(), ref) < BF16_TOL
+    a = run_gemm(0, [conv_seg(x)], n, hw, hw, pack_conv_weight(wc).cuda())
+    assert torch.equal(a, run_gemm(0, [conv_seg(x)], n, hw, hw, pack_conv_weight(wc).cuda()))   # bit-stable
+
+
 def test_tcgen05_matches_simt_bitwise_close():
     """Same operands through both kernel families: differences are fp32 summation order only."""
     torch.manual_seed(3)
@@ -125,7 +152,7 @@ def test_groupnorm(n, c0, c1, hw, silu, eps):
     C = c0 + c1
     g, b = torch.randn(C).cuda(), torch.randn(C).cuda()
     out = torch.empty(n, hw, C, dtype=torch.bfloat16, device="cuda")
-    scratch = torch.empty(n * 32 * 2, device="cuda")
+    scratch = torch.empty(n * 32 * 2 * 64, device="cuda")
     _lib.check(lib.mvldm_op_groupnorm(stream_ptr(), x0.data_ptr(), c0, x1.data_ptr() if c1 else None, c1, n, hw, 32,
                                       eps, g.data_ptr(), b.data_ptr(), silu, out.data_ptr(), scratch.data_ptr()))
     xx = torch.cat([x0, x1], -1) if c1 else x0            # groups straddle the concat boundary for 960 / 1920

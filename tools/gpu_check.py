@@ -104,7 +104,7 @@ def norm_ops():
         C = c0 + c1
         g = torch.randn(C).cuda(); b = torch.randn(C).cuda()
         out = torch.empty(n, hw, C, dtype=torch.bfloat16, device=dev)
-        scratch = torch.empty(n * 32 * 2, device=dev)
+        scratch = torch.empty(n * 32 * 2 * 64, device=dev)
         _lib.check(lib.mvldm_op_groupnorm(stream_ptr(), x0.data_ptr(), c0, x1.data_ptr() if c1 else None, c1, n, hw, 32, 1e-5,
                                           g.data_ptr(), b.data_ptr(), 1, out.data_ptr(), scratch.data_ptr()))
         xx = torch.cat([x0, x1], -1) if c1 else x0
