@@ -82,7 +82,7 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[STAGES];
   __shared__ __align__(8) uint64_t bar_empty[STAGES];
@@ -302,24 +302,46 @@ void launch(cudaStream_t s, const TcParams& p, int splits) {
   MV_LAUNCHED();
 }
 
-int pick_bn(int n) { return n % 128 == 0 ? 128 : (n % 64 == 0 ? 64 : (n % 32 == 0 ? 32 : 0)); }
+// ---- tile / split-K selection ---------------------------------------------------------------------
+// Measured on B200 (profiles/r01_*): one SM ingests at most ~67 GB/s of TMA traffic from L2, so a GEMM here is
+// bound by  (bytes the busiest SM has to pull) / 67 GB/s  long before the tensor pipe saturates.  The model
+// below picks the N-tile (arithmetic intensity per SM) and the split-K factor (SMs kept busy) that minimise
+//   max(load time, MMA time) + split-K reduction time.
+struct TileChoice {
+  int bn, splits;
+};
 
-// Split-K keeps all 148 SMs streaming weights when M*N gives only a handful of tiles (the 4x4 / 8x8 levels at
-// batch 1 are weight-bandwidth-bound: e.g. 59 MB of filter for 7.5 GFLOP).
-int pick_splits(const mvldm_gemm_desc& d) {
-  const int BN = pick_bn(d.n);
-  if (BN == 0 || d.mode != 0) return 1;
-  const int tiles = ceil_div(d.n_img * d.oh * d.ow, BM) * (d.n / BN);
-  const int num_kb = d.k / BK;
-  if (tiles >= 100 || num_kb < 32) return 1;
-  const int splits = std::min(148 / tiles, num_kb / 8);
-  return splits >= 2 ? splits : 1;
+TileChoice pick_tiles(const mvldm_gemm_desc& d) {
+  static const int kBN[5] = {256, 160, 128, 64, 32};
+  static const int kSplits[12] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 24, 32};
+  const int M = d.n_img * d.oh * d.ow, mt = ceil_div(M, BM), num_kb = d.k / BK;
+  TileChoice best{0, 1};
+  double best_t = 1e30;
+  for (int bn : kBN) {
+    if (d.n % bn != 0) continue;
+    if (d.mode == 2 && bn != 32) continue;
+    for (int sp : kSplits) {
+      if (sp > 1 && (d.mode != 0 || num_kb / sp < 4)) break;
+      const int kb_per = ceil_div(num_kb, sp), splits = ceil_div(num_kb, kb_per);
+      const double ctas = (double)mt * (d.n / bn) * splits;
+      const double rounds = std::ceil(ctas / 148.0);
+      const double t_load = rounds * kb_per * (A_BYTES + bn * 128.0) / 67e9;
+      const double t_mma = rounds * kb_per * 4.0 * (bn / 2.0) / 1.9e9;
+      const double t_red = splits > 1 ? (splits + 1.0) * M * (double)d.n * 4.0 / 3e12 + 3e-6 : 0.0;
+      const double t = std::max(t_load, t_mma) + t_red + 2e-6 * rounds;
+      if (t < best_t) {
+        best_t = t;
+        best = TileChoice{bn, splits};
+      }
+    }
+  }
+  return best;
 }
 
 }  // namespace
 
 size_t gemm_tc_workspace_bytes(const mvldm_gemm_desc& d) {
-  const int splits = pick_splits(d);
+  const int splits = pick_tiles(d).splits;
   return splits > 1 ? (size_t)splits * d.n_img * d.oh * d.ow * d.n * sizeof(float) : 0;
 }
 
@@ -364,9 +386,10 @@ void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t w
   p.nseg = d.nseg;
   MV_CHECK(ktot == d.k, "gemm_tc: K mismatch between segments and weights");
   p.num_kb = d.k / BK;
-  const int BN = pick_bn(d.n);
+  const TileChoice tile = pick_tiles(d);
+  const int BN = tile.bn;
   MV_CHECK(BN != 0, "gemm_tc: N must be a multiple of 32");
-  int splits = pick_splits(d);
+  int splits = tile.splits;
   if (splits > 1 && gemm_tc_workspace_bytes(d) > workspace_bytes) splits = 1;  // no scratch: plain single-pass GEMM
   p.kb_per_split = ceil_div(p.num_kb, splits);
   splits = ceil_div(p.num_kb, p.kb_per_split);
@@ -389,7 +412,9 @@ void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t w
   p.ldo = d.ldo;
   p.n_valid = d.n_valid;
   if (d.mode == 0) MV_CHECK(d.ldo % 8 == 0 && (!d.residual || d.res_ld % 8 == 0), "gemm_tc: row pitch must be a multiple of 8");
-  if (BN == 128) launch<128, 3>(s, p, splits);
+  if (BN == 256) launch<256, 4>(s, p, splits);
+  else if (BN == 160) launch<160, 4>(s, p, splits);
+  else if (BN == 128) launch<128, 3>(s, p, splits);
   else if (BN == 64) launch<64, 4>(s, p, splits);
   else launch<32, 4>(s, p, splits);
   if (splits > 1) {
