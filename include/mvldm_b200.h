@@ -79,6 +79,13 @@ int mvldm_forward(mvldm_handle h, void* stream, const float* latents, const int6
 /* Number of kernels the last mvldm_forward on this handle launched (graph replays count their nodes). */
 int mvldm_last_launch_count(mvldm_handle h);
 
+/* Per-op device timing for bench.py's roofline: while enabled, mvldm_forward runs eagerly (no graph) with a
+ * CUDA-event pair around every op on the launching stream; mvldm_profile_json synchronises and returns
+ * {"categories": {name: {launches, us, gflop, mbytes}}, "ops": [...]} for the last forward (string owned by
+ * the handle, valid until the next call). */
+int mvldm_set_profiling(mvldm_handle h, int enable);
+const char* mvldm_profile_json(mvldm_handle h);
+
 /* Copy an intermediate activation of the last (non-graph) forward into `out` as fp32 NCHW
  * [B*V, C, h, w] for per-layer parity tests; names follow oracle taps ("down0.res1", "mid.mv", ...).
  * Returns the element count through *numel (out may be NULL to query). */

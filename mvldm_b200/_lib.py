@@ -57,6 +57,8 @@ SYMBOLS = {
     "mvldm_workspace_bytes": (c_int64, [c_void_p, c_int, c_int, c_int, c_int]),
     "mvldm_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mvldm_last_launch_count": (c_int, [c_void_p]),
+    "mvldm_set_profiling": (c_int, [c_void_p, c_int]),
+    "mvldm_profile_json": (c_char_p, [c_void_p]),
     "mvldm_debug_tap": (c_int, [c_void_p, c_void_p, c_char_p, c_void_p, POINTER(c_int64)]),
     "mvldm_enable_taps": (c_int, [c_void_p, c_int]),
     "mvldm_build_inputs": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -136,6 +136,41 @@ struct mvldm_handle_s {
   bool taps_enabled = false;
   std::map<std::string, TapRec> taps;
 
+  // ---- per-launch profiling (eager mode only): CUDA-event pairs around every op, read back after a sync ----
+  struct ProfRec {
+    const char* cat;
+    std::string what;
+    double flops, bytes;
+    cudaEvent_t e0, e1;
+  };
+  bool profiling = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> event_pool;
+  size_t events_used = 0;
+  std::string prof_json;
+  cudaEvent_t next_event() {
+    if (events_used == event_pool.size()) {
+      cudaEvent_t e;
+      MV_CUDA(cudaEventCreate(&e));
+      event_pool.push_back(e);
+    }
+    return event_pool[events_used++];
+  }
+  struct ProfScope {
+    mvldm_handle_s* h;
+    bool on;
+    ProfScope(mvldm_handle_s* h_, const char* cat, const std::string& what, double flops, double bytes)
+        : h(h_), on(h_->profiling && !h_->dry) {
+      if (!on) return;
+      ProfRec r{cat, what, flops, bytes, h->next_event(), h->next_event()};
+      h->prof.push_back(r);
+      cudaEventRecord(r.e0, h->stream);
+    }
+    ~ProfScope() {
+      if (on) cudaEventRecord(h->prof.back().e1, h->stream);
+    }
+  };
+
   // ---- run state ----
   cudaStream_t stream = nullptr;
   cudaStream_t capture_stream = nullptr;  // graphs are recorded here: the caller's stream may be the legacy NULL stream
@@ -443,7 +478,13 @@ struct mvldm_handle_s {
     s.ptr = a.p; s.c = a.c; s.ctot = a.c; s.sh = a.h; s.sw = a.w; s.stride = 1; s.ntaps = 1;
     return s;
   }
-  void run_gemm(mvldm_gemm_desc& d) {
+  void run_gemm(mvldm_gemm_desc& d, double algo_flops = -1.0) {
+    const double M = (double)d.n_img * d.oh * d.ow;
+    const char* cat = d.nseg > 0 && d.seg[0].ntaps == 9 ? "gemm_conv3x3" : "gemm_linear";
+    ProfScope ps(this, cat,
+                 "M" + std::to_string((long long)M) + " N" + std::to_string(d.n) + " K" + std::to_string(d.k),
+                 algo_flops >= 0 ? algo_flops : 2.0 * M * d.n * d.k,
+                 2.0 * ((double)d.n * d.k + M * d.n * (d.mode == 1 ? 0.5 : 1.0)));
     if (dry) {
       if (cfg.impl != MVLDM_IMPL_SIMT) splitk_need = std::max(splitk_need, gemm_tc_workspace_bytes(d));
       return;
@@ -453,7 +494,7 @@ struct mvldm_handle_s {
   }
   // out = A-segments x W^T (+bias +rowvec +residual), bf16 NHWC
   void gemm(std::initializer_list<mvldm_aseg> segs, const Packed& w, const Act& out, const float* rowvec = nullptr,
-            int rowvec_ld = 0, const Act* residual = nullptr, int mode = 0) {
+            int rowvec_ld = 0, const Act* residual = nullptr, int mode = 0, double algo_flops = -1.0) {
     mvldm_gemm_desc d{};
     for (const auto& s : segs) d.seg[d.nseg++] = s;
     d.n_img = out.n; d.oh = out.h; d.ow = out.w;
@@ -462,15 +503,27 @@ struct mvldm_handle_s {
     d.rowvec = rowvec; d.rowvec_ld = rowvec_ld;
     if (residual) { d.residual = residual->p; d.res_ld = residual->c; }
     d.mode = mode; d.out = out.p; d.ldo = out.c; d.n_valid = w.n;
-    run_gemm(d);
+    run_gemm(d, algo_flops);
   }
   void gn(const Act& x0, const Act* x1, const float* g, const float* b, float eps, bool silu, const Act& out) {
     float* scratch = new_f32(groupnorm_scratch_floats(x0.n, cfg.norm_groups));
+    ProfScope ps(this, "groupnorm", "tokens" + std::to_string(x0.tokens()) + " C" + std::to_string(out.c), 0.0,
+                 4.0 * (double)out.tokens() * out.c);
     if (dry) return;
     groupnorm(stream, x0.p, x0.c, x1 ? x1->p : nullptr, x1 ? x1->c : 0, x0.n, x0.h * x0.w, cfg.norm_groups, eps, g, b,
               silu, out.p, scratch);
   }
+  void ln(const Act& x, const float* g, const float* b, const Act& out) {
+    ProfScope ps(this, "layernorm", "tokens" + std::to_string(x.tokens()) + " C" + std::to_string(x.c), 0.0,
+                 4.0 * (double)x.tokens() * x.c);
+    if (dry) return;
+    layernorm(stream, x.p, (int)x.tokens(), x.c, 1e-5f, g, b, out.p);
+  }
   void attn(const Act& qkv, const Act& out, int batches, int seq, const MvW& m) {
+    // algorithmic FLOPs: QK^T and PV over the un-padded head dim, 4 * seq^2 * C per batch
+    ProfScope ps(this, seq > out.h * out.w ? "attention_joint" : "attention_per_view",
+                 "batches" + std::to_string(batches) + " seq" + std::to_string(seq) + " d" + std::to_string(m.d),
+                 4.0 * batches * (double)seq * seq * m.c, 2.0 * (double)out.tokens() * (4.0 * cfg.num_heads * m.dpad));
     if (dry) return;
     if (cfg.impl == MVLDM_IMPL_TC) attention_tc(stream, qkv.p, out.p, batches, seq, cfg.num_heads, m.d, m.dpad);
     else attention_simt(stream, qkv.p, out.p, batches, seq, cfg.num_heads, m.d, m.dpad);
@@ -511,21 +564,21 @@ struct mvldm_handle_s {
     Act qkv = new_act(n, h, w, 3 * H * m.dpad);
     Act o = new_act(n, h, w, H * m.dpad);
     // joint attention over all V*h*w tokens of a scene ("(b f) l c -> b (f l) c")
-    if (!dry) layernorm(stream, t.p, (int)t.tokens(), C, 1e-5f, m.ln_g[0], m.ln_b[0], nrm.p);
-    gemm({seg_1x1(nrm)}, m.qkv1, qkv);
+    ln(t, m.ln_g[0], m.ln_b[0], nrm);
+    gemm({seg_1x1(nrm)}, m.qkv1, qkv, nullptr, 0, nullptr, 0, 6.0 * (double)t.tokens() * C * C);
     attn(qkv, o, B, V * hw, m);
     Act t2 = new_act(n, h, w, C);
-    gemm({seg_1x1(o)}, m.out1, t2, nullptr, 0, &t);
+    gemm({seg_1x1(o)}, m.out1, t2, nullptr, 0, &t, 0, 2.0 * (double)t.tokens() * C * C);
     tap(m.key + ".attn1", t2);
     // per-view attention
-    if (!dry) layernorm(stream, t2.p, (int)t2.tokens(), C, 1e-5f, m.ln_g[1], m.ln_b[1], nrm.p);
-    gemm({seg_1x1(nrm)}, m.qkv2, qkv);
+    ln(t2, m.ln_g[1], m.ln_b[1], nrm);
+    gemm({seg_1x1(nrm)}, m.qkv2, qkv, nullptr, 0, nullptr, 0, 6.0 * (double)t.tokens() * C * C);
     attn(qkv, o, B * V, hw, m);
     Act t3 = new_act(n, h, w, C);
-    gemm({seg_1x1(o)}, m.out2, t3, nullptr, 0, &t2);
+    gemm({seg_1x1(o)}, m.out2, t3, nullptr, 0, &t2, 0, 2.0 * (double)t.tokens() * C * C);
     tap(m.key + ".attn2", t3);
     // GEGLU feed-forward
-    if (!dry) layernorm(stream, t3.p, (int)t3.tokens(), C, 1e-5f, m.ln_g[2], m.ln_b[2], nrm.p);
+    ln(t3, m.ln_g[2], m.ln_b[2], nrm);
     Act f = new_act(n, h, w, 4 * C);
     gemm({seg_1x1(nrm)}, m.ff1, f, nullptr, 0, nullptr, 1);
     Act t4 = new_act(n, h, w, C);
@@ -545,6 +598,8 @@ struct mvldm_handle_s {
     float* e2 = new_f32((size_t)n * temb_dim);
     float* temb = new_f32((size_t)n * temb_total);
     if (!dry) {
+      ProfScope ps(this, "time_embedding", "rows" + std::to_string(n), 2.0 * n * ((double)boc[0] * temb_dim + (double)temb_dim * temb_dim + (double)temb_dim * temb_total),
+                   2.0 * ((double)boc[0] * temb_dim + (double)temb_dim * temb_dim + (double)temb_dim * temb_total));
       timestep_sinusoid(stream, tsteps, n, boc[0], sinus);
       small_linear(stream, sinus, n, boc[0], time1.w, time1.bias, temb_dim, 1, e1);
       small_linear(stream, e1, n, temb_dim, time2.w, time2.bias, temb_dim, 1, e2);  // SiLU(emb): every consumer applies it
@@ -552,9 +607,12 @@ struct mvldm_handle_s {
     }
     // ---- conv_in on the im2col'd fp32 input
     Act col = new_act(n, Hh, Ww, kpad_in);
-    if (!dry) im2col_input(stream, latents, n, cfg.in_channels, Hh, Ww, kpad_in, col.p);
+    if (!dry) {
+      ProfScope ps(this, "input_im2col", "", 0.0, (double)col.tokens() * (kpad_in * 2 + cfg.in_channels * 4));
+      im2col_input(stream, latents, n, cfg.in_channels, Hh, Ww, kpad_in, col.p);
+    }
     Act x = new_act(n, Hh, Ww, boc[0]);
-    gemm({seg_1x1(col)}, conv_in, x);
+    gemm({seg_1x1(col)}, conv_in, x, nullptr, 0, nullptr, 0, 2.0 * (double)x.tokens() * boc[0] * 9 * cfg.in_channels);
     tap("conv_in", x);
     std::vector<Act> skips{x};
     // ---- down
@@ -595,7 +653,10 @@ struct mvldm_handle_s {
       }
       if (l != L - 1) {
         Act u = new_act(n, x.h * 2, x.w * 2, x.c);
-        if (!dry) upsample_nearest2x(stream, x.p, n, x.h, x.w, x.c, u.p);
+        if (!dry) {
+          ProfScope ps(this, "upsample", "", 0.0, 2.5 * (double)u.tokens() * u.c);
+          upsample_nearest2x(stream, x.p, n, x.h, x.w, x.c, u.p);
+        }
         Act y = new_act(n, u.h, u.w, u.c);
         gemm({seg_conv3x3(u)}, up_conv[l], y);
         x = y;
@@ -612,7 +673,7 @@ struct mvldm_handle_s {
     d.w = conv_out.w; d.n = conv_out.n; d.k = conv_out.k;
     d.bias = conv_out.bias;
     d.mode = 2; d.out = out_eps; d.n_valid = cfg.out_channels;
-    run_gemm(d);
+    run_gemm(d, 2.0 * (double)x.tokens() * cfg.out_channels * conv_out.k);
   }
 
   Plan& plan_for(int B, int V, int H, int W) {
@@ -654,9 +715,11 @@ struct mvldm_handle_s {
     g_launch_count = 0;
     const size_t in_bytes = (size_t)B * V * cfg.in_channels * H * W * sizeof(float);
     const size_t out_bytes = (size_t)B * V * cfg.out_channels * H * W * sizeof(float);
-    const bool graph = cfg.use_cuda_graph && !taps_enabled;
+    const bool graph = cfg.use_cuda_graph && !taps_enabled && !profiling;
     if (!graph) {
       taps.clear();
+      prof.clear();
+      events_used = 0;
       run(latents, tsteps, B, V, H, W, out);
       last_launches = g_launch_count;
       return;
@@ -697,6 +760,41 @@ struct mvldm_handle_s {
     MV_CUDA(cudaMemcpyAsync(out, p.out_eps.p, out_bytes, cudaMemcpyDeviceToDevice, s));
   }
 };
+
+// Folds the event pairs of the last profiled forward into a JSON string (synchronises the device).
+static const char* profile_report(mvldm_handle_s* h) {
+  MV_CUDA(cudaDeviceSynchronize());
+  struct Agg {
+    int n = 0;
+    double ms = 0, flops = 0, bytes = 0;
+  };
+  std::map<std::string, Agg> agg;
+  std::string ops = "[";
+  for (size_t i = 0; i < h->prof.size(); ++i) {
+    const auto& r = h->prof[i];
+    float ms = 0.f;
+    MV_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    Agg& a = agg[r.cat];
+    a.n++; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s{\"cat\":\"%s\",\"what\":\"%s\",\"us\":%.2f,\"gflop\":%.3f}", i ? "," : "", r.cat,
+             r.what.c_str(), ms * 1e3, r.flops * 1e-9);
+    ops += buf;
+  }
+  ops += "]";
+  std::string out = "{\"categories\":{";
+  bool first = true;
+  for (auto& kv : agg) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s\"%s\":{\"launches\":%d,\"us\":%.2f,\"gflop\":%.3f,\"mbytes\":%.3f}", first ? "" : ",",
+             kv.first.c_str(), kv.second.n, kv.second.ms * 1e3, kv.second.flops * 1e-9, kv.second.bytes * 1e-6);
+    out += buf;
+    first = false;
+  }
+  out += "},\"ops\":" + ops + "}";
+  h->prof_json = out;
+  return h->prof_json.c_str();
+}
 
 // =============================================================================================
 // C ABI
@@ -749,6 +847,7 @@ int mvldm_destroy(mvldm_handle h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
+    for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
     delete h;
   }
   MV_API_END
@@ -816,6 +915,23 @@ int mvldm_forward(mvldm_handle h, void* stream, const float* latents, const int6
 }
 
 int mvldm_last_launch_count(mvldm_handle h) { return h ? h->last_launches : -1; }
+
+int mvldm_set_profiling(mvldm_handle h, int enable) {
+  MV_API_BEGIN
+  MV_CHECK(h, "null handle");
+  h->profiling = enable != 0;
+  MV_API_END
+}
+
+const char* mvldm_profile_json(mvldm_handle h) {
+  try {
+    MV_CHECK(h, "null handle");
+    return profile_report(h);
+  } catch (const std::exception& e) {
+    mvldm::g_last_error = e.what();
+    return nullptr;
+  }
+}
 
 int mvldm_enable_taps(mvldm_handle h, int enable) {
   MV_API_BEGIN

@@ -332,6 +332,18 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
     def last_launch_count(self) -> int:
         return _lib.load().mvldm_last_launch_count(self._h.ptr) if self._h.ptr else 0
 
+    def set_profiling(self, on: bool = True) -> None:
+        """Eager launches with a CUDA-event pair around every op (see mvldm_set_profiling)."""
+        dev = next(self.parameters()).device
+        _lib.check(_lib.load().mvldm_set_profiling(self._ensure_handle(dev).ptr, 1 if on else 0))
+
+    def profile(self) -> dict:
+        import json
+        s = _lib.load().mvldm_profile_json(self._h.ptr)
+        if s is None:
+            _lib.check(1)
+        return json.loads(s.decode())
+
     def enable_taps(self, on: bool = True) -> None:
         dev = next(self.parameters()).device
         _lib.check(_lib.load().mvldm_enable_taps(self._ensure_handle(dev).ptr, 1 if on else 0))
