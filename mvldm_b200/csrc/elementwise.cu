@@ -149,10 +149,24 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict_
 #pragma unroll
       for (int j = 0; j < 8; ++j) sa[j] = qa[j] = 0.f;
       const int c = cv * 8;
-      for (int pp = pl; pp < pix; pp += lanes_p) {
+      const bf16* src = c < c0 ? x0 + pix0 * c0 + c : x1 + pix0 * c1 + (c - c0);
+      const int64_t pitch = c < c0 ? c0 : c1;
+      int pp = pl;
+      for (; pp + 3 * lanes_p < pix; pp += 4 * lanes_p) {  // 4 independent 16-byte loads in flight per thread
+        float f[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) load8(src + (int64_t)(pp + u * lanes_p) * pitch, f[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            sa[j] += f[u][j];
+            qa[j] = fmaf(f[u][j], f[u][j], qa[j]);
+          }
+      }
+      for (; pp < pix; pp += lanes_p) {
         float f[8];
-        if (c < c0) load8(x0 + (pix0 + pp) * c0 + c, f);
-        else load8(x1 + (pix0 + pp) * c1 + (c - c0), f);
+        load8(src + (int64_t)pp * pitch, f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           sa[j] += f[j];
@@ -186,15 +200,28 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
                                                        const float* __restrict__ partials, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, int silu, bf16* __restrict__ out) {
   __shared__ float s_mean[64], s_rstd[64];
+  __shared__ double s_part[4][64][2];
   const int C = c0 + c1, cg = C / groups, cv = C / 8;
   const int img = blockIdx.y;
-  if (threadIdx.x < groups) {
-    double S = 0.0, Q = 0.0;
-    for (int k = 0; k < P; ++k) {
-      const float* o = partials + (((int64_t)img * P + k) * groups + threadIdx.x) * 2;
-      S += (double)o[0];
-      Q += (double)o[1];
+  {  // fold the chunk partials: 4 slices of chunks in parallel (independent loads), then a fixed-order sum
+    const int g = threadIdx.x & 63, slice = threadIdx.x >> 6;
+    if (g < groups) {
+      double S = 0.0, Q = 0.0;
+#pragma unroll 4
+      for (int k = slice; k < P; k += 4) {
+        const float2 o = *reinterpret_cast<const float2*>(partials + (((int64_t)img * P + k) * groups + g) * 2);
+        S += (double)o.x;
+        Q += (double)o.y;
+      }
+      s_part[slice][g][0] = S;
+      s_part[slice][g][1] = Q;
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    const double S = ((s_part[0][g][0] + s_part[1][g][0]) + s_part[2][g][0]) + s_part[3][g][0];
+    const double Q = ((s_part[0][g][1] + s_part[1][g][1]) + s_part[2][g][1]) + s_part[3][g][1];
     const double cnt = (double)hw * cg;
     const double mean = S / cnt;
     double var = Q / cnt - mean * mean;
@@ -205,6 +232,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
   __syncthreads();
   const int64_t per_img = (int64_t)hw * cv;
   const int64_t lo = per_img * blockIdx.x / gridDim.x, hi = per_img * (blockIdx.x + 1) / gridDim.x;
+#pragma unroll 2
   for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const int c = (int)(i % cv) * 8;
     const int64_t pixel = (int64_t)img * hw + i / cv;
@@ -440,7 +468,7 @@ void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, i
   MV_CHECK(c0 % 8 == 0 && c1 % 8 == 0 && C <= GN_MAXC, "groupnorm: channel counts must be multiples of 8, <= 2560");
   // pixel chunks per image: enough CTAs to cover the machine twice, at least 4 pixels each
   int P = 1;
-  while (P < GN_MAXP && n_img * P < 296 && hw % (2 * P) == 0 && hw / (2 * P) >= 4) P *= 2;
+  while (P < GN_MAXP && n_img * P < 592 && hw % (2 * P) == 0 && hw / (2 * P) >= 4) P *= 2;
   gn_partial_kernel<<<dim3(P, n_img), 256, 0, s>>>(x0, c0, x1, c1, hw, groups, hw / P, scratch);
   MV_LAUNCHED();
   gn_apply_kernel<<<dim3(P, n_img), 256, 0, s>>>(x0, c0, x1, c1, hw, groups, eps, P, scratch, gamma, beta, silu ? 1 : 0,
@@ -451,7 +479,7 @@ void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, i
 void layernorm(cudaStream_t s, const bf16* x, int rows, int c, float eps, const float* gamma, const float* beta,
                bf16* out) {
   MV_CHECK(c % 8 == 0 && c <= 32 * 8 * 8, "layernorm: unsupported channel count");
-  const int warps = 8;
+  const int warps = 4;
   if (c <= 32 * 8 * 2)
     layernorm_kernel<2><<<ceil_div(rows, warps), warps * 32, 0, s>>>(x, rows, c, eps, gamma, beta, out);
   else if (c <= 32 * 8 * 5)

@@ -324,11 +324,14 @@ TileChoice pick_tiles(const mvldm_gemm_desc& d) {
       if (sp > 1 && (d.mode != 0 || num_kb / sp < 4)) break;
       const int kb_per = ceil_div(num_kb, sp), splits = ceil_div(num_kb, kb_per);
       const double ctas = (double)mt * (d.n / bn) * splits;
-      const double rounds = std::ceil(ctas / 148.0);
-      const double t_load = rounds * kb_per * (A_BYTES + bn * 128.0) / 67e9;
-      const double t_mma = rounds * kb_per * 4.0 * (bn / 2.0) / 1.9e9;
+      const double per_sm = std::ceil(ctas / 148.0);                       // CTAs the busiest SM runs
+      const double main = kb_per * std::max((A_BYTES + bn * 128.0) / 67e9, 4.0 * (bn / 2.0) / 1.9e9);
+      const double epi = bn * (d.mode == 1 ? 12e-9 : 6e-9);               // TMEM -> registers -> global, per CTA
+      const double serial = 1.5e-6 + main + epi;                           // launch ramp + main loop + epilogue
+      // tiles up to 128 wide fit two CTAs per SM: one CTA's ramp/epilogue hides behind the other's main loop
+      const double t_sm = bn <= 128 ? std::max(per_sm * main, std::ceil(per_sm / 2.0) * serial) : per_sm * serial;
       const double t_red = splits > 1 ? (splits + 1.0) * M * (double)d.n * 4.0 / 3e12 + 3e-6 : 0.0;
-      const double t = std::max(t_load, t_mma) + t_red + 2e-6 * rounds;
+      const double t = t_sm + t_red;
       if (t < best_t) {
         best_t = t;
         best = TileChoice{bn, splits};
