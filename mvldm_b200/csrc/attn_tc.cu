@@ -88,6 +88,8 @@ __global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -257,8 +259,7 @@ void launch(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, in
     configured = true;
   }
   dim3 grid(ceil_div(seq, BM), batches * heads);
-  attn_tc_kernel<DPAD, BN, ST><<<grid, 192, smem, s>>>(p);
-  MV_LAUNCHED();
+  launch_pdl(attn_tc_kernel<DPAD, BN, ST>, grid, dim3(192), smem, s, p);
 }
 
 }  // namespace

@@ -43,6 +43,33 @@ extern thread_local int g_launch_count;
     MV_CUDA(cudaPeekAtLastError());   \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// Every forward-path kernel is launched with programmaticStreamSerialization: it may be scheduled while its
+// predecessor is still draining, runs its prologue (barrier init, TMEM alloc, descriptor prefetch), then
+// blocks in pdl_wait() until the predecessor's memory is visible.  No kernel touches global memory before
+// pdl_wait(), so RAW and WAR hazards through the reused activation arena are preserved.
+extern bool g_use_pdl;  // MVLDM_PDL=0 disables (plain stream order)
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  MV_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  MV_LAUNCHED();
+}
+#endif
+
 // ---- kernels (host launchers) -----------------------------------------------------------------
 // gemm_simt.cu / gemm_tc.cu
 void gemm_simt(cudaStream_t s, const mvldm_gemm_desc& d);
@@ -62,6 +89,7 @@ void small_linear(cudaStream_t s, const float* in, int rows, int k, const bf16* 
 void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, int n_img, int hw, int groups,
                float eps, const float* gamma, const float* beta, bool silu, bf16* out, float* scratch);
 size_t groupnorm_scratch_floats(int n_img, int groups);
+void groupnorm_init();  // one-time kernel attribute / cluster-size probing (call outside stream capture)
 void layernorm(cudaStream_t s, const bf16* x, int rows, int c, float eps, const float* gamma, const float* beta,
                bf16* out);
 void upsample_nearest2x(cudaStream_t s, const bf16* x, int n_img, int h, int w, int c, bf16* out);

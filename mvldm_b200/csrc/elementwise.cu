@@ -1,11 +1,19 @@
 // HBM/L2-bound helper kernels of the MV-LDM hot path: input concat/im2col, timestep embedding,
 // GroupNorm(+SiLU), LayerNorm, nearest upsample, CFG+DDIM update, ray maps, weight packing.
 // All activations are bf16 NHWC ([image, h, w, channel]); statistics and scalars are fp32.
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mvldm {
 
 thread_local int g_launch_count = 0;
+bool g_use_pdl = []() {
+  const char* e = getenv("MVLDM_PDL");
+  return !(e && e[0] == '0');
+}();
 
 namespace {
 
@@ -59,6 +67,8 @@ __device__ __forceinline__ float block_sum(float v, float* red /* >= 33 floats *
 // ---------------------------------------------------------------------------------------------
 __global__ void im2col_input_kernel(const float* __restrict__ x, int n_img, int cin, int h, int w, int kpad,
                                     bf16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t total = (int64_t)n_img * h * w * kpad;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int k = (int)(i % kpad);
@@ -76,6 +86,8 @@ __global__ void im2col_input_kernel(const float* __restrict__ x, int n_img, int 
 
 // diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): [cos | sin], fp32
 __global__ void sinusoid_kernel(const int64_t* __restrict__ t, int n, int dim, float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * half) return;
@@ -90,6 +102,8 @@ __global__ void sinusoid_kernel(const int64_t* __restrict__ t, int n, int dim, f
 template <int RB>
 __global__ void small_linear_kernel(const float* __restrict__ in, int rows, int k, const bf16* __restrict__ w,
                                     const float* __restrict__ b, int n, int act, float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (col >= n) return;
@@ -136,6 +150,8 @@ constexpr int GN_MAXP = 64;
 
 __global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict__ x0, int c0, const bf16* __restrict__ x1,
                                                          int c1, int hw, int groups, int pix, float* __restrict__ partials) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float red_s[GN_MAXC], red_q[GN_MAXC];
   const int C = c0 + c1, ncv = C / 8, cg = C / groups;
   const int img = blockIdx.y, chunk = blockIdx.x, P = gridDim.x;
@@ -199,6 +215,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
                                                        int c1, int hw, int groups, float eps, int P,
                                                        const float* __restrict__ partials, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, int silu, bf16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float s_mean[64], s_rstd[64];
   __shared__ double s_part[4][64][2];
   const int C = c0 + c1, cg = C / groups, cv = C / 8;
@@ -253,10 +271,129 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Single-launch GroupNorm: one thread-block CLUSTER per image.  Each CTA of the cluster owns a slice of the
+// image's pixels, keeps it in shared memory, reduces it to per-group (sum, sum of squares), the CTAs exchange
+// those 32 pairs through distributed shared memory (fixed rank order -> bit-stable), and every CTA then
+// normalises its slice straight from shared memory.  HBM/L2 traffic = read once + write once.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_cluster_kernel(const bf16* __restrict__ x0, int c0, const bf16* __restrict__ x1,
+                                                         int c1, int hw, int groups, float eps,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         int silu, int cache, bf16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) uint8_t gn_smem[];
+  __shared__ float red_s[GN_MAXC], red_q[GN_MAXC];
+  __shared__ float my_part[64][2];
+  __shared__ float s_mean[64], s_rstd[64];
+  bf16* slice = reinterpret_cast<bf16*>(gn_smem);
+
+  const int C = c0 + c1, ncv = C / 8, cgn = C / groups;
+  const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int img = blockIdx.y, pix = hw / CL, t = threadIdx.x;
+  const int lanes_p = ncv <= 256 ? 256 / ncv : 1;
+  const int pl = ncv <= 256 ? t / ncv : 0;
+  const int64_t pix0 = (int64_t)img * hw + (int64_t)rank * pix;
+  if (pl < lanes_p) {
+    for (int cv = ncv <= 256 ? t % ncv : t; cv < ncv; cv += 256) {
+      float sa[8], qa[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sa[j] = qa[j] = 0.f;
+      const int c = cv * 8;
+      const bf16* src = c < c0 ? x0 + pix0 * c0 + c : x1 + pix0 * c1 + (c - c0);
+      const int64_t pitch = c < c0 ? c0 : c1;
+      int pp = pl;
+      for (; pp + 3 * lanes_p < pix; pp += 4 * lanes_p) {
+        bf16x8 raw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) raw[u] = *reinterpret_cast<const bf16x8*>(src + (int64_t)(pp + u * lanes_p) * pitch);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (cache) *reinterpret_cast<bf16x8*>(slice + (int64_t)(pp + u * lanes_p) * C + c) = raw[u];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(raw[u].v[j]);
+            sa[2 * j] += f.x; sa[2 * j + 1] += f.y;
+            qa[2 * j] = fmaf(f.x, f.x, qa[2 * j]); qa[2 * j + 1] = fmaf(f.y, f.y, qa[2 * j + 1]);
+          }
+        }
+      }
+      for (; pp < pix; pp += lanes_p) {
+        const bf16x8 raw = *reinterpret_cast<const bf16x8*>(src + (int64_t)pp * pitch);
+        if (cache) *reinterpret_cast<bf16x8*>(slice + (int64_t)pp * C + c) = raw;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(raw.v[j]);
+          sa[2 * j] += f.x; sa[2 * j + 1] += f.y;
+          qa[2 * j] = fmaf(f.x, f.x, qa[2 * j]); qa[2 * j + 1] = fmaf(f.y, f.y, qa[2 * j + 1]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        red_s[pl * C + c + j] = sa[j];
+        red_q[pl * C + c + j] = qa[j];
+      }
+      if (ncv <= 256) break;
+    }
+  }
+  __syncthreads();
+  if (t < groups) {
+    float S = 0.f, Q = 0.f;
+    for (int l = 0; l < lanes_p; ++l)
+      for (int c = t * cgn; c < (t + 1) * cgn; ++c) {
+        S += red_s[l * C + c];
+        Q += red_q[l * C + c];
+      }
+    my_part[t][0] = S;
+    my_part[t][1] = Q;
+  }
+  cluster.sync();
+  if (t < groups) {
+    double S = 0.0, Q = 0.0;
+    for (int r = 0; r < CL; ++r) {  // fixed rank order
+      const float* peer = cluster.map_shared_rank(&my_part[0][0], r);
+      S += (double)peer[2 * t];
+      Q += (double)peer[2 * t + 1];
+    }
+    const double cnt = (double)hw * cgn;
+    const double mean = S / cnt;
+    double var = Q / cnt - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    s_mean[t] = (float)mean;
+    s_rstd[t] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  cluster.sync();  // also keeps every CTA's my_part alive until all peers have read it
+  const int total = pix * ncv;
+#pragma unroll 2
+  for (int i = t; i < total; i += 256) {
+    const int c = (i % ncv) * 8, pp = i / ncv;
+    float f[8];
+    if (cache) load8(slice + (int64_t)pp * C + c, f);
+    else if (c < c0) load8(x0 + (pix0 + pp) * c0 + c, f);
+    else load8(x1 + (pix0 + pp) * c1 + (c - c0), f);
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c + j) / cgn;
+      const float v = (f[j] - s_mean[g]) * s_rstd[g] * gg[j] + bb[j];
+      f[j] = silu ? silu_f(v) : v;
+    }
+    store8(out + (pix0 + pp) * C + c, f);
+  }
+}
+
 // LayerNorm over the channel dim, one warp per token, row cached in registers (C <= 32*8*MAXV).
 template <int MAXV>
 __global__ void layernorm_kernel(const bf16* __restrict__ x, int rows, int c, float eps, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, bf16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -298,6 +435,8 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, int rows, int c, fl
 }
 
 __global__ void upsample2x_kernel(const bf16* __restrict__ x, int n_img, int h, int w, int c, bf16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int cv = c / 8;
   const int64_t total = (int64_t)n_img * 4 * h * w * cv;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -442,58 +581,103 @@ inline int grid_for(int64_t total, int threads) {
 void im2col_input(cudaStream_t s, const float* latents, int n_img, int cin, int h, int w, int kpad, bf16* out) {
   MV_CHECK(kpad >= 9 * cin, "im2col: kpad too small");
   const int64_t total = (int64_t)n_img * h * w * kpad;
-  im2col_input_kernel<<<grid_for(total, 256), 256, 0, s>>>(latents, n_img, cin, h, w, kpad, out);
-  MV_LAUNCHED();
+  launch_pdl(im2col_input_kernel, dim3(grid_for(total, 256)), dim3(256), 0, s, latents, n_img, cin, h, w, kpad, out);
 }
 
 void timestep_sinusoid(cudaStream_t s, const int64_t* t, int n, int dim, float* out) {
   const int total = n * (dim / 2);
-  sinusoid_kernel<<<ceil_div(total, 128), 128, 0, s>>>(t, n, dim, out);
-  MV_LAUNCHED();
+  launch_pdl(sinusoid_kernel, dim3(ceil_div(total, 128)), dim3(128), 0, s, t, n, dim, out);
 }
 
 void small_linear(cudaStream_t s, const float* in, int rows, int k, const bf16* w, const float* b, int n, int act,
                   float* out) {
   MV_CHECK(k % 8 == 0, "small_linear: K must be a multiple of 8");
-  small_linear_kernel<8><<<ceil_div(n, 8), 256, 0, s>>>(in, rows, k, w, b, n, act, out);
-  MV_LAUNCHED();
+  launch_pdl(small_linear_kernel<8>, dim3(ceil_div(n, 8)), dim3(256), 0, s, in, rows, k, w, b, n, act, out);
 }
 
 size_t groupnorm_scratch_floats(int n_img, int groups) { return (size_t)n_img * GN_MAXP * groups * 2; }
+
+namespace {
+// largest cluster size (16 needs the non-portable opt-in) the device will co-schedule for this kernel, or 0
+int gn_cluster_limit() {
+  static int limit = -1;
+  if (limit >= 0) return limit;
+  limit = 0;
+  if (cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess) return limit;
+  cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  for (int cl : {16, 8}) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(cl, 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = 160 * 1024;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = cl; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gn_cluster_kernel, &cfg) == cudaSuccess && n >= 1) {
+      limit = cl;
+      break;
+    }
+  }
+  cudaGetLastError();
+  return limit;
+}
+}  // namespace
+
+void groupnorm_init() { gn_cluster_limit(); }
 
 void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, int n_img, int hw, int groups,
                float eps, const float* gamma, const float* beta, bool silu, bf16* out, float* scratch) {
   const int C = c0 + c1;
   MV_CHECK(C % groups == 0 && groups <= 64, "groupnorm: channels not divisible by groups (<= 64 groups)");
   MV_CHECK(c0 % 8 == 0 && c1 % 8 == 0 && C <= GN_MAXC, "groupnorm: channel counts must be multiples of 8, <= 2560");
-  // pixel chunks per image: enough CTAs to cover the machine twice, at least 4 pixels each
+  // ---- single-launch cluster path: one cluster per image ----
+  int cl = gn_cluster_limit();
+  while (cl > 1 && (hw % cl != 0)) cl /= 2;
+  if (cl >= 2) {
+    const size_t slice_bytes = (size_t)(hw / cl) * C * sizeof(bf16);
+    const int cache = slice_bytes <= 160 * 1024 ? 1 : 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(cl, n_img, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = cache ? slice_bytes : 0;
+    cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = g_use_pdl ? 2 : 1;
+    MV_CUDA(cudaLaunchKernelEx(&cfg, gn_cluster_kernel, x0, c0, x1, c1, hw, groups, eps, gamma, beta, silu ? 1 : 0, cache,
+                               out));
+    MV_LAUNCHED();
+    return;
+  }
+  // ---- two-launch path (no cluster support / odd sizes) ----
   int P = 1;
   while (P < GN_MAXP && n_img * P < 592 && hw % (2 * P) == 0 && hw / (2 * P) >= 4) P *= 2;
-  gn_partial_kernel<<<dim3(P, n_img), 256, 0, s>>>(x0, c0, x1, c1, hw, groups, hw / P, scratch);
-  MV_LAUNCHED();
-  gn_apply_kernel<<<dim3(P, n_img), 256, 0, s>>>(x0, c0, x1, c1, hw, groups, eps, P, scratch, gamma, beta, silu ? 1 : 0,
-                                                  out);
-  MV_LAUNCHED();
+  launch_pdl(gn_partial_kernel, dim3(P, n_img), dim3(256), 0, s, x0, c0, x1, c1, hw, groups, hw / P, scratch);
+  launch_pdl(gn_apply_kernel, dim3(P, n_img), dim3(256), 0, s, x0, c0, x1, c1, hw, groups, eps, P, (const float*)scratch,
+             gamma, beta, silu ? 1 : 0, out);
 }
 
 void layernorm(cudaStream_t s, const bf16* x, int rows, int c, float eps, const float* gamma, const float* beta,
                bf16* out) {
   MV_CHECK(c % 8 == 0 && c <= 32 * 8 * 8, "layernorm: unsupported channel count");
   const int warps = 4;
-  if (c <= 32 * 8 * 2)
-    layernorm_kernel<2><<<ceil_div(rows, warps), warps * 32, 0, s>>>(x, rows, c, eps, gamma, beta, out);
-  else if (c <= 32 * 8 * 5)
-    layernorm_kernel<5><<<ceil_div(rows, warps), warps * 32, 0, s>>>(x, rows, c, eps, gamma, beta, out);
-  else
-    layernorm_kernel<8><<<ceil_div(rows, warps), warps * 32, 0, s>>>(x, rows, c, eps, gamma, beta, out);
-  MV_LAUNCHED();
+  const dim3 grid(ceil_div(rows, warps)), block(warps * 32);
+  if (c <= 32 * 8 * 2) launch_pdl(layernorm_kernel<2>, grid, block, 0, s, x, rows, c, eps, gamma, beta, out);
+  else if (c <= 32 * 8 * 5) launch_pdl(layernorm_kernel<5>, grid, block, 0, s, x, rows, c, eps, gamma, beta, out);
+  else launch_pdl(layernorm_kernel<8>, grid, block, 0, s, x, rows, c, eps, gamma, beta, out);
 }
 
 void upsample_nearest2x(cudaStream_t s, const bf16* x, int n_img, int h, int w, int c, bf16* out) {
   MV_CHECK(c % 8 == 0, "upsample: channels must be a multiple of 8");
   const int64_t total = (int64_t)n_img * 4 * h * w * (c / 8);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, n_img, h, w, c, out);
-  MV_LAUNCHED();
+  launch_pdl(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), 0, s, x, n_img, h, w, c, out);
 }
 
 void nhwc_to_nchw_f32(cudaStream_t s, const bf16* x, int n_img, int hw, int c, float* out) {

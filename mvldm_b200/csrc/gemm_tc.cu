@@ -110,6 +110,9 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tc
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_d = tmem_base_slot;
+  // everything above overlaps the previous kernel's tail; from here on we read its output
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -255,6 +258,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
                                                             const float* __restrict__ rowvec, int rowvec_ld,
                                                             const bf16* __restrict__ residual, int res_ld,
                                                             bf16* __restrict__ out, int ldo) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int nv = N / 8;
   const int64_t total = (int64_t)M * nv;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -298,8 +303,7 @@ void launch(cudaStream_t s, const TcParams& p, int splits) {
     configured = true;
   }
   dim3 grid(ceil_div(p.M, BM), p.N / BN, splits);
-  gemm_tc_kernel<BN, STAGES><<<grid, 192, smem, s>>>(p);
-  MV_LAUNCHED();
+  launch_pdl(gemm_tc_kernel<BN, STAGES>, grid, dim3(192), smem, s, p);
 }
 
 // ---- tile / split-K selection ---------------------------------------------------------------------
@@ -423,9 +427,8 @@ void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t w
   if (splits > 1) {
     const int64_t total = (int64_t)p.M * (p.N / 8);
     const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
-    splitk_reduce_kernel<<<blocks, 256, 0, s>>>(p.partial, splits, p.M, p.N, p.hw, p.bias, p.rowvec, p.rowvec_ld,
-                                                 p.residual, p.res_ld, reinterpret_cast<bf16*>(p.out), p.ldo);
-    MV_LAUNCHED();
+    launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, s, (const float*)p.partial, splits, p.M, p.N, p.hw, p.bias,
+               p.rowvec, p.rowvec_ld, p.residual, p.res_ld, reinterpret_cast<bf16*>(p.out), p.ldo);
   }
 }
 

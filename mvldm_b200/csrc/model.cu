@@ -406,6 +406,7 @@ struct mvldm_handle_s {
     for (auto& n : names) MV_CHECK(raw.count(n), "mvldm_finalize_weights: missing weight " + n);
     MV_CUDA(cudaStreamSynchronize(s));
     packed_store.clear();
+    groupnorm_init();
     const int L = cfg.num_levels;
     const int* boc = cfg.block_out_channels;
     kpad_in = (9 * cfg.in_channels + 63) / 64 * 64;
