@@ -48,7 +48,7 @@ extern thread_local int g_launch_count;
 // predecessor is still draining, runs its prologue (barrier init, TMEM alloc, descriptor prefetch), then
 // blocks in pdl_wait() until the predecessor's memory is visible.  No kernel touches global memory before
 // pdl_wait(), so RAW and WAR hazards through the reused activation arena are preserved.
-extern bool g_use_pdl;  // MVLDM_PDL=0 disables (plain stream order)
+extern bool g_use_pdl;  // MVLDM_PDL=1 enables; default is plain stream order
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

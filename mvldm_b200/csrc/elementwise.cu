@@ -10,9 +10,9 @@
 namespace mvldm {
 
 thread_local int g_launch_count = 0;
-bool g_use_pdl = []() {
+bool g_use_pdl = []() {  // opt-in: measured 2% slower than plain stream order inside the captured graph (profiles/)
   const char* e = getenv("MVLDM_PDL");
-  return !(e && e[0] == '0');
+  return e && e[0] == '1';
 }();
 
 namespace {
@@ -603,6 +603,10 @@ int gn_cluster_limit() {
   static int limit = -1;
   if (limit >= 0) return limit;
   limit = 0;
+  {  // opt-in: the 16-CTA cluster launch measured 3x slower than the two-launch path on B200 (profiles/)
+    const char* e = getenv("MVLDM_GN_CLUSTER");
+    if (!(e && e[0] == '1')) return limit;
+  }
   if (cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess) return limit;
   cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   for (int cl : {16, 8}) {

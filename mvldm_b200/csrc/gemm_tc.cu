@@ -58,7 +58,8 @@ struct TcParams {
   TcSeg seg[MVLDM_MAX_SEGS];
   int nseg;
   int M, N, num_kb;
-  int kb_per_split;  // k-blocks per grid.z slice (== num_kb when not split)
+  int mt, nt, splits;  // work items = mt * nt * splits, m fastest
+  int kb_per_split;    // k-blocks per split (== num_kb when not split)
   float* partial;    // split-K: fp32 partial tiles [splits][M][N]; NULL when not split
   int hw, ow;        // output pixels per image / row width (tile -> image coordinates)
   const float* bias;
@@ -78,22 +79,25 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// Persistent: grid = min(#work items, #SMs); every CTA walks work items w = blockIdx.x, +gridDim.x, ... where a work
+// item is (m-tile, n-tile, k-split), m fastest so that the CTAs running concurrently share the same weight tile
+// in L2.  The smem ring runs continuously across work items and the accumulator is double-buffered in TMEM, so
+// the epilogue of item i (TMEM -> registers -> global) overlaps the main loop of item i+1.
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  constexpr int ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));  // one accumulator buffer
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[STAGES];
   __shared__ __align__(8) uint64_t bar_empty[STAGES];
-  __shared__ __align__(8) uint64_t bar_accum;
+  __shared__ __align__(8) uint64_t bar_acc_full[2];
+  __shared__ __align__(8) uint64_t bar_acc_empty[2];
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-B alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int kb_begin = blockIdx.z * p.kb_per_split;
-  const int nkb = min(p.num_kb - kb_begin, p.kb_per_split);
+  const int num_work = p.mt * p.nt * p.splits;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.nseg; ++i) tc::tma_prefetch_desc(&p.tmA[i]);
@@ -102,14 +106,17 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tc
       tc::mbar_init(tc::smem_u32(&bar_full[s]), 1);
       tc::mbar_init(tc::smem_u32(&bar_empty[s]), 1);
     }
-    tc::mbar_init(tc::smem_u32(&bar_accum), 1);
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(tc::smem_u32(&bar_acc_full[b]), 1);
+      tc::mbar_init(tc::smem_u32(&bar_acc_empty[b]), 128);
+    }
     tc::mbar_fence_init();
   }
-  if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tc::smem_u32(&tmem_base_slot));
+  if (warp == 1) tc::tmem_alloc<2 * ACC_COLS>(tc::smem_u32(&tmem_base_slot));
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_d = tmem_base_slot;
+  const uint32_t tmem_base = tmem_base_slot;
   // everything above overlaps the previous kernel's tail; from here on we read its output
   pdl_wait();
   pdl_launch_dependents();
@@ -117,31 +124,37 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tc
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      const int img0 = m0 / p.hw;
-      const int y0 = (m0 - img0 * p.hw) / p.ow;
-      // locate (segment, tap, channel block) of this CTA's first k-block
-      int s = 0, t = 0, cb = kb_begin;
-      while (cb >= p.seg[s].ntaps * p.seg[s].ncblk) {
-        cb -= p.seg[s].ntaps * p.seg[s].ncblk;
-        ++s;
-      }
-      t = cb / p.seg[s].ncblk;
-      cb -= t * p.seg[s].ncblk;
-      for (int i = 0; i < nkb; ++i) {
-        const TcSeg& sg = p.seg[s];
-        const int stage = i % STAGES;
-        const uint32_t par = ((i / STAGES) & 1) ^ 1;
-        tc::mbar_wait(tc::smem_u32(&bar_empty[stage]), par);
-        const uint32_t full = tc::smem_u32(&bar_full[stage]);
-        tc::mbar_expect_tx(full, STAGE_BYTES);
-        const uint32_t sa = smem_base + stage * STAGE_BYTES;
-        tc::tma_load_4d(sa, &p.tmA[s], full, sg.coff[t] + cb * BK, sg.dw[t], y0 * sg.stride + sg.dh[t], img0);
-        tc::tma_load_2d(sa + A_BYTES, &p.tmB, full, (kb_begin + i) * BK, n0);
-        if (++cb == sg.ncblk) {
-          cb = 0;
-          if (++t == sg.ntaps) {
-            t = 0;
-            ++s;
+      int it = 0;  // k-block counter across work items: smem stage = it % STAGES
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int mtile = w % p.mt, ntile = (w / p.mt) % p.nt, z = w / (p.mt * p.nt);
+        const int m0 = mtile * BM, n0 = ntile * BN;
+        const int kb_begin = z * p.kb_per_split;
+        const int nkb = min(p.num_kb - kb_begin, p.kb_per_split);
+        const int img0 = m0 / p.hw;
+        const int y0 = (m0 - img0 * p.hw) / p.ow;
+        // locate (segment, tap, channel block) of the first k-block
+        int s = 0, t = 0, cb = kb_begin;
+        while (cb >= p.seg[s].ntaps * p.seg[s].ncblk) {
+          cb -= p.seg[s].ntaps * p.seg[s].ncblk;
+          ++s;
+        }
+        t = cb / p.seg[s].ncblk;
+        cb -= t * p.seg[s].ncblk;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const TcSeg& sg = p.seg[s];
+          const int stage = it % STAGES;
+          tc::mbar_wait(tc::smem_u32(&bar_empty[stage]), ((it / STAGES) & 1) ^ 1);
+          const uint32_t full = tc::smem_u32(&bar_full[stage]);
+          tc::mbar_expect_tx(full, STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          tc::tma_load_4d(sa, &p.tmA[s], full, sg.coff[t] + cb * BK, sg.dw[t], y0 * sg.stride + sg.dh[t], img0);
+          tc::tma_load_2d(sa + A_BYTES, &p.tmB, full, (kb_begin + i) * BK, n0);
+          if (++cb == sg.ncblk) {
+            cb = 0;
+            if (++t == sg.ntaps) {
+              t = 0;
+              ++s;
+            }
           }
         }
       }
@@ -150,29 +163,44 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tc
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc = tc::umma_idesc_bf16(BM, BN, false, false);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int stage = kb % STAGES;
-        tc::mbar_wait(tc::smem_u32(&bar_full[stage]), (kb / STAGES) & 1);
+      int it = 0, wi = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wi) {
+        const int z = w / (p.mt * p.nt);
+        const int nkb = min(p.num_kb - z * p.kb_per_split, p.kb_per_split);
+        const int ab = wi & 1;
+        tc::mbar_wait(tc::smem_u32(&bar_acc_empty[ab]), ((wi >> 1) & 1) ^ 1);  // epilogue has drained this buffer
         tc::tc_fence_after();
-        const uint32_t sa = smem_base + stage * STAGE_BYTES;
-        const uint64_t adesc = tc::umma_desc_k_sw128(sa);
-        const uint64_t bdesc = tc::umma_desc_k_sw128(sa + A_BYTES);
+        const uint32_t tmem_d = tmem_base + ab * ACC_COLS;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int stage = it % STAGES;
+          tc::mbar_wait(tc::smem_u32(&bar_full[stage]), (it / STAGES) & 1);
+          tc::tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint64_t adesc = tc::umma_desc_k_sw128(sa);
+          const uint64_t bdesc = tc::umma_desc_k_sw128(sa + A_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)  // +32 bytes (=2 in descriptor units) per K=16 slice inside the swizzle atom
-          tc::umma_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-        tc::umma_commit(tc::smem_u32(&bar_empty[stage]));  // frees the smem slot when these MMAs retire
+          for (int k = 0; k < BK / 16; ++k)  // +32 bytes (=2 in descriptor units) per K=16 slice inside the swizzle atom
+            tc::umma_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          tc::umma_commit(tc::smem_u32(&bar_empty[stage]));  // frees the smem slot when these MMAs retire
+        }
+        tc::umma_commit(tc::smem_u32(&bar_acc_full[ab]));
       }
-      tc::umma_commit(tc::smem_u32(&bar_accum));
     }
     __syncwarp();
   } else {
     // ================= epilogue =================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
+    int wi = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wi) {
+    const int mtile = w % p.mt, ntile = (w / p.mt) % p.nt, z = w / (p.mt * p.nt);
+    const int m0 = mtile * BM, n0 = ntile * BN;
+    const int ab = wi & 1;
+    const uint32_t tmem_d = tmem_base + ab * ACC_COLS;
     const int m = m0 + row;
     const bool ok = m < p.M;
     const int img = m / p.hw;
-    tc::mbar_wait(tc::smem_u32(&bar_accum), 0);
+    tc::mbar_wait(tc::smem_u32(&bar_acc_full[ab]), (wi >> 1) & 1);
     tc::tc_fence_after();
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -181,7 +209,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tc
       tc::tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + c0, r);
       tc::tmem_ld_wait();
       if (ok && p.partial) {  // split-K: raw fp32 partial, reduced (+ epilogue) by splitk_reduce_kernel
-        float4* pp = reinterpret_cast<float4*>(p.partial + ((int64_t)blockIdx.z * p.M + m) * p.N + n0 + c0);
+        float4* pp = reinterpret_cast<float4*>(p.partial + ((int64_t)z * p.M + m) * p.N + n0 + c0);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           pp[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
@@ -244,11 +272,13 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tc
       }
     }
     tc::tc_fence_before();
+    tc::mbar_arrive(tc::smem_u32(&bar_acc_empty[ab]));  // this thread is done reading the accumulator buffer
+    }
   }
   __syncthreads();
   if (warp == 1) {
     tc::tc_fence_after();
-    tc::tmem_dealloc<TMEM_COLS>(tmem_d);
+    tc::tmem_dealloc<2 * ACC_COLS>(tmem_base);
   }
 }
 
@@ -302,8 +332,18 @@ void launch(cudaStream_t s, const TcParams& p, int splits) {
     MV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid(ceil_div(p.M, BM), p.N / BN, splits);
-  launch_pdl(gemm_tc_kernel<BN, STAGES>, grid, dim3(192), smem, s, p);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    MV_CUDA(cudaGetDevice(&dev));
+    MV_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  TcParams q = p;
+  q.mt = ceil_div(p.M, BM);
+  q.nt = p.N / BN;
+  q.splits = splits;
+  dim3 grid(std::min(q.mt * q.nt * q.splits, num_sms));
+  launch_pdl(gemm_tc_kernel<BN, STAGES>, grid, dim3(192), smem, s, q);
 }
 
 // ---- tile / split-K selection ---------------------------------------------------------------------
@@ -328,12 +368,11 @@ TileChoice pick_tiles(const mvldm_gemm_desc& d) {
       if (sp > 1 && (d.mode != 0 || num_kb / sp < 4)) break;
       const int kb_per = ceil_div(num_kb, sp), splits = ceil_div(num_kb, kb_per);
       const double ctas = (double)mt * (d.n / bn) * splits;
-      const double per_sm = std::ceil(ctas / 148.0);                       // CTAs the busiest SM runs
+      const double per_sm = std::ceil(ctas / 148.0);                       // work items the busiest SM runs
       const double main = kb_per * std::max((A_BYTES + bn * 128.0) / 67e9, 4.0 * (bn / 2.0) / 1.9e9);
-      const double epi = bn * (d.mode == 1 ? 12e-9 : 6e-9);               // TMEM -> registers -> global, per CTA
-      const double serial = 1.5e-6 + main + epi;                           // launch ramp + main loop + epilogue
-      // tiles up to 128 wide fit two CTAs per SM: one CTA's ramp/epilogue hides behind the other's main loop
-      const double t_sm = bn <= 128 ? std::max(per_sm * main, std::ceil(per_sm / 2.0) * serial) : per_sm * serial;
+      const double epi = bn * (d.mode == 1 ? 12e-9 : 6e-9);               // TMEM -> registers -> global, per item
+      // persistent CTA: ramp once, items back to back (epilogue hidden behind the next main loop), last epilogue exposed
+      const double t_sm = 1.5e-6 + per_sm * std::max(main, epi) + epi;
       const double t_red = splits > 1 ? (splits + 1.0) * M * (double)d.n * 4.0 / 3e12 + 3e-6 : 0.0;
       const double t = t_sm + t_red;
       if (t < best_t) {
@@ -420,10 +459,10 @@ void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t w
   p.n_valid = d.n_valid;
   if (d.mode == 0) MV_CHECK(d.ldo % 8 == 0 && (!d.residual || d.res_ld % 8 == 0), "gemm_tc: row pitch must be a multiple of 8");
   if (BN == 256) launch<256, 4>(s, p, splits);
-  else if (BN == 160) launch<160, 4>(s, p, splits);
-  else if (BN == 128) launch<128, 3>(s, p, splits);
-  else if (BN == 64) launch<64, 4>(s, p, splits);
-  else launch<32, 4>(s, p, splits);
+  else if (BN == 160) launch<160, 6>(s, p, splits);
+  else if (BN == 128) launch<128, 6>(s, p, splits);
+  else if (BN == 64) launch<64, 8>(s, p, splits);
+  else launch<32, 8>(s, p, splits);
   if (splits > 1) {
     const int64_t total = (int64_t)p.M * (p.N / 8);
     const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
