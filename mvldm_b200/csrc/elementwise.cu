@@ -388,6 +388,120 @@ __global__ void __launch_bounds__(256) gn_cluster_kernel(const bf16* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Single-launch GroupNorm: groups are independent, so one CTA owns (image, block of whole groups): it streams
+// its [hw x cb] channel slab once (kept in shared memory when it fits), reduces per-channel partials across
+// pixel lanes and then per group in a fixed order (bit-stable), and normalises the slab.  cb = lcm(group
+// width, 8) channels so that every access is a 16-byte vector.
+// ---------------------------------------------------------------------------------------------
+constexpr int GNB_THREADS = 512;
+
+__global__ void __launch_bounds__(GNB_THREADS) gn_block_kernel(const bf16* __restrict__ x0, int c0,
+                                                               const bf16* __restrict__ x1, int c1, int hw, int groups,
+                                                               float eps, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, int silu, int cb,
+                                                               int cache, bf16* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t gnb_smem[];
+  __shared__ float red_s[GNB_THREADS * 8], red_q[GNB_THREADS * 8];
+  __shared__ float s_mean[16], s_rstd[16];
+  pdl_wait();
+  pdl_launch_dependents();
+  bf16* slab = reinterpret_cast<bf16*>(gnb_smem);
+  const int C = c0 + c1, cgn = C / groups, nv = cb / 8, gb = cb / cgn;
+  const int img = blockIdx.y, ch0 = blockIdx.x * cb, t = threadIdx.x;
+  const int lanes_p = GNB_THREADS / nv;
+  const int cv = t % nv, pl = t / nv;
+  const int c = ch0 + cv * 8;
+  const bf16* src = c < c0 ? x0 + (int64_t)img * hw * c0 + c : x1 + (int64_t)img * hw * c1 + (c - c0);
+  const int64_t pitch = c < c0 ? c0 : c1;
+  if (pl < lanes_p) {
+    float sa[8], qa[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sa[j] = qa[j] = 0.f;
+    int pp = pl;
+    for (; pp + 3 * lanes_p < hw; pp += 4 * lanes_p) {
+      bf16x8 raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) raw[u] = *reinterpret_cast<const bf16x8*>(src + (int64_t)(pp + u * lanes_p) * pitch);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (cache) *reinterpret_cast<bf16x8*>(slab + (int64_t)(pp + u * lanes_p) * cb + cv * 8) = raw[u];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(raw[u].v[j]);
+          sa[2 * j] += f.x; sa[2 * j + 1] += f.y;
+          qa[2 * j] = fmaf(f.x, f.x, qa[2 * j]); qa[2 * j + 1] = fmaf(f.y, f.y, qa[2 * j + 1]);
+        }
+      }
+    }
+    for (; pp < hw; pp += lanes_p) {
+      const bf16x8 raw = *reinterpret_cast<const bf16x8*>(src + (int64_t)pp * pitch);
+      if (cache) *reinterpret_cast<bf16x8*>(slab + (int64_t)pp * cb + cv * 8) = raw;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(raw.v[j]);
+        sa[2 * j] += f.x; sa[2 * j + 1] += f.y;
+        qa[2 * j] = fmaf(f.x, f.x, qa[2 * j]); qa[2 * j + 1] = fmaf(f.y, f.y, qa[2 * j + 1]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // [pixel lane][channel in block]
+      red_s[pl * cb + cv * 8 + j] = sa[j];
+      red_q[pl * cb + cv * 8 + j] = qa[j];
+    }
+  }
+  __syncthreads();
+  {  // one warp per group: lanes stride over (pixel lane, channel) in a fixed order, then a fixed shuffle tree
+    const int warp = t >> 5, lane = t & 31;
+    if (warp < gb) {
+      float S = 0.f, Q = 0.f;
+      const int n = lanes_p * cgn;
+      for (int i = lane; i < n; i += 32) {
+        const int l = i / cgn, cc = warp * cgn + i % cgn;
+        S += red_s[l * cb + cc];
+        Q += red_q[l * cb + cc];
+      }
+      S = warp_sum(S);
+      Q = warp_sum(Q);
+      if (lane == 0) {
+        const double cnt = (double)hw * cgn;
+        const double mean = (double)S / cnt;
+        double var = (double)Q / cnt - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        s_mean[warp] = (float)mean;
+        s_rstd[warp] = (float)(1.0 / sqrt(var + (double)eps));
+      }
+    }
+  }
+  __syncthreads();
+  if (pl < lanes_p) {
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (cv * 8 + j) / cgn;
+      sc[j] = s_rstd[g] * gg[j];
+      sh[j] = bb[j] - s_mean[g] * sc[j];
+    }
+    bf16* dst = out + (int64_t)img * hw * C + c;
+#pragma unroll 4
+    for (int pp = pl; pp < hw; pp += lanes_p) {
+      float f[8];
+      if (cache) load8(slab + (int64_t)pp * cb + cv * 8, f);
+      else load8(src + (int64_t)pp * pitch, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = fmaf(f[j], sc[j], sh[j]);
+        f[j] = silu ? silu_f(v) : v;
+      }
+      store8(dst + (int64_t)pp * C, f);
+    }
+  }
+}
+
 // LayerNorm over the channel dim, one warp per token, row cached in registers (C <= 32*8*MAXV).
 template <int MAXV>
 __global__ void layernorm_kernel(const bf16* __restrict__ x, int rows, int c, float eps, const float* __restrict__ gamma,
@@ -630,14 +744,35 @@ int gn_cluster_limit() {
 }
 }  // namespace
 
-void groupnorm_init() { gn_cluster_limit(); }
+void groupnorm_init() {
+  gn_cluster_limit();
+  MV_CUDA(cudaFuncSetAttribute(gn_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+}
 
 void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, int n_img, int hw, int groups,
                float eps, const float* gamma, const float* beta, bool silu, bf16* out, float* scratch) {
   const int C = c0 + c1;
   MV_CHECK(C % groups == 0 && groups <= 64, "groupnorm: channels not divisible by groups (<= 64 groups)");
   MV_CHECK(c0 % 8 == 0 && c1 % 8 == 0 && C <= GN_MAXC, "groupnorm: channel counts must be multiples of 8, <= 2560");
-  // ---- single-launch cluster path: one cluster per image ----
+  // ---- single-launch path: one CTA per (image, block of whole groups) ----
+  {
+    const int cgn = C / groups;
+    int cb = cgn;
+    while (cb % 8 != 0) cb += cgn;  // lcm(group width, 8)
+    if (C % cb == 0 && cb / 8 <= 16 && cb / cgn <= 16 && c0 % 8 == 0) {
+      const size_t slab = (size_t)hw * cb * sizeof(bf16);
+      const int cache = slab <= 160 * 1024 ? 1 : 0;
+      static bool configured = false;
+      if (!configured) {
+        MV_CUDA(cudaFuncSetAttribute(gn_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        configured = true;
+      }
+      launch_pdl(gn_block_kernel, dim3(C / cb, n_img), dim3(GNB_THREADS), cache ? slab : 0, s, x0, c0, x1, c1, hw, groups,
+                 eps, gamma, beta, silu ? 1 : 0, cb, cache, out);
+      return;
+    }
+  }
+  // ---- cluster path (opt-in): one cluster per image ----
   int cl = gn_cluster_limit();
   while (cl > 1 && (hw % cl != 0)) cl /= 2;
   if (cl >= 2) {

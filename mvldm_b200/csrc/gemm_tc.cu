@@ -61,6 +61,7 @@ struct TcParams {
   int mt, nt, splits;  // work items = mt * nt * splits, m fastest
   int kb_per_split;    // k-blocks per split (== num_kb when not split)
   float* partial;    // split-K: fp32 partial tiles [splits][M][N]; NULL when not split
+  int* counters;     // split-K fused reduction: [2][mt*nt] arrive / done counters (all zero between launches), or NULL
   int hw, ow;        // output pixels per image / row width (tile -> image coordinates)
   const float* bias;
   const float* rowvec;
@@ -273,6 +274,65 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     }
     tc::tc_fence_before();
     tc::mbar_arrive(tc::smem_u32(&bar_acc_empty[ab]));  // this thread is done reading the accumulator buffer
+    if (p.counters) {
+      // ---- split-K reduction fused into the GEMM: all splits of a tile are co-resident (one work item per CTA),
+      // so they can meet at a global counter; each then reduces 1/splits of the tile's rows in fixed z order
+      // (bit-stable) and applies the epilogue.
+      const int tile = mtile + ntile * p.mt;
+      const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        atomicAdd(&p.counters[tile], 1);
+        uint32_t spins = 0;
+        while (*reinterpret_cast<volatile int*>(&p.counters[tile]) < p.splits) {
+          if (++spins > (1u << 26)) __trap();
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      __threadfence();
+      const int rows_per = (BM + p.splits - 1) / p.splits;
+      const int r0 = z * rows_per, r1 = min(BM, r0 + rows_per);
+      constexpr int NV = BN / 8;
+      for (int i = et; i < (r1 - r0) * NV; i += 128) {
+        const int mm = m0 + r0 + i / NV, n = n0 + (i % NV) * 8;
+        if (mm >= p.M) continue;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int zz = 0; zz < p.splits; ++zz) {
+          const float4* pp = reinterpret_cast<const float4*>(p.partial + ((int64_t)zz * p.M + mm) * p.N + n);
+          const float4 a = __ldcg(pp), b = __ldcg(pp + 1);
+          v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+        }
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += p.bias[n + j];
+        }
+        if (p.rowvec) {
+          const float* rv = p.rowvec + (int64_t)(mm / p.hw) * p.rowvec_ld + n;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += rv[j];
+        }
+        if (p.residual) {
+          const uint4 u = *reinterpret_cast<const uint4*>(p.residual + (int64_t)mm * p.res_ld + n);
+          const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wds[e]));
+            v[2 * e] += f.x;
+            v[2 * e + 1] += f.y;
+          }
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (int64_t)mm * p.ldo + n) =
+            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {  // the last split to finish re-arms the counters for the next launch
+        if (atomicAdd(&p.counters[p.mt * p.nt + tile], 1) == p.splits - 1) {
+          p.counters[tile] = 0;
+          p.counters[p.mt * p.nt + tile] = 0;
+        }
+      }
+    }
     }
   }
   __syncthreads();
@@ -386,9 +446,11 @@ TileChoice pick_tiles(const mvldm_gemm_desc& d) {
 
 }  // namespace
 
+constexpr size_t kCounterBytes = 2 * 4096 * sizeof(int);  // arrive/done counters live at the head of the workspace
+
 size_t gemm_tc_workspace_bytes(const mvldm_gemm_desc& d) {
   const int splits = pick_tiles(d).splits;
-  return splits > 1 ? (size_t)splits * d.n_img * d.oh * d.ow * d.n * sizeof(float) : 0;
+  return splits > 1 ? kCounterBytes + (size_t)splits * d.n_img * d.oh * d.ow * d.n * sizeof(float) : 0;
 }
 
 void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t workspace_bytes) {
@@ -439,7 +501,11 @@ void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t w
   if (splits > 1 && gemm_tc_workspace_bytes(d) > workspace_bytes) splits = 1;  // no scratch: plain single-pass GEMM
   p.kb_per_split = ceil_div(p.num_kb, splits);
   splits = ceil_div(p.num_kb, p.kb_per_split);
-  p.partial = splits > 1 ? reinterpret_cast<float*>(workspace) : nullptr;
+  p.partial = splits > 1 ? reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kCounterBytes) : nullptr;
+  // fused reduction needs every split of a tile resident at once: one work item per CTA, grid <= #SMs
+  const int work = ceil_div(p.M, BM) * (d.n / BN) * splits;
+  const bool fused = splits > 1 && work <= 148 && ceil_div(p.M, BM) * (d.n / BN) <= 4096;
+  p.counters = fused ? reinterpret_cast<int*>(workspace) : nullptr;
   MV_CHECK(d.mode != 2 || d.n == 32, "gemm_tc: NCHW head output expects N padded to 32");
   {
     const uint64_t dims[2] = {(uint64_t)d.k, (uint64_t)d.n};
@@ -463,7 +529,7 @@ void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t w
   else if (BN == 128) launch<128, 6>(s, p, splits);
   else if (BN == 64) launch<64, 8>(s, p, splits);
   else launch<32, 8>(s, p, splits);
-  if (splits > 1) {
+  if (splits > 1 && !fused) {
     const int64_t total = (int64_t)p.M * (p.N / 8);
     const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
     launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, s, (const float*)p.partial, splits, p.M, p.N, p.hw, p.bias,

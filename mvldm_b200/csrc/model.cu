@@ -691,6 +691,7 @@ struct mvldm_handle_s {
     p->arena_bytes = arena.peak;
     p->arena_mem.alloc(p->arena_bytes);
     p->splitk.alloc(splitk_need);
+    if (splitk_need) MV_CUDA(cudaMemset(p->splitk.p, 0, splitk_need));  // fused split-K counters start (and end) at zero
     p->in_latents.alloc((size_t)B * V * cfg.in_channels * H * W * sizeof(float));
     p->in_t.alloc((size_t)B * V * sizeof(int64_t));
     p->out_eps.alloc((size_t)B * V * cfg.out_channels * H * W * sizeof(float));
@@ -986,6 +987,7 @@ int mvldm_op_gemm(void* stream, int impl, const mvldm_gemm_desc* d) {
     if (need > scratch.bytes) {
       MV_CUDA(cudaDeviceSynchronize());
       scratch.alloc(need);
+      MV_CUDA(cudaMemset(scratch.p, 0, need));
     }
     gemm_tc((cudaStream_t)stream, *d, scratch.p, scratch.bytes);
   } else {
