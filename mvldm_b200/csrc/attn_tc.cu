@@ -30,13 +30,6 @@ struct AttnParams {
   float scale_log2;  // d^-1/2 * log2(e)
 };
 
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -96,7 +89,7 @@ __global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__
     if (lane == 0) {
       const uint32_t bq = tc::smem_u32(&bar_q);
       tc::mbar_expect_tx(bq, Q_BYTES);
-      for (int c = 0; c < NC; ++c) tma_load_3d(q_smem + c * BM * 128, &p.tmQ, bq, head * DPAD + c * 64, q0, batch);
+      for (int c = 0; c < NC; ++c) tc::tma_load_3d(q_smem + c * BM * 128, &p.tmQ, bq, head * DPAD + c * 64, q0, batch);
       const int kcol = (p.heads + head) * DPAD, vcol = (2 * p.heads + head) * DPAD;
       for (int j = 0; j < T; ++j) {
         const int stage = j % ST;
@@ -104,8 +97,8 @@ __global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__
         const uint32_t full = tc::smem_u32(&bar_kv_full[stage]);
         tc::mbar_expect_tx(full, STAGE_BYTES);
         const uint32_t ks = kv_smem + stage * STAGE_BYTES, vs = ks + NC * KV_CHUNK;
-        for (int c = 0; c < NC; ++c) tma_load_3d(ks + c * KV_CHUNK, &p.tmKV, full, kcol + c * 64, j * BN, batch);
-        for (int c = 0; c < NC; ++c) tma_load_3d(vs + c * KV_CHUNK, &p.tmKV, full, vcol + c * 64, j * BN, batch);
+        for (int c = 0; c < NC; ++c) tc::tma_load_3d(ks + c * KV_CHUNK, &p.tmKV, full, kcol + c * 64, j * BN, batch);
+        for (int c = 0; c < NC; ++c) tc::tma_load_3d(vs + c * KV_CHUNK, &p.tmKV, full, vcol + c * 64, j * BN, batch);
       }
     }
   } else if (warp == 1) {

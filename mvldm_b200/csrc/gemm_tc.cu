@@ -47,19 +47,23 @@ namespace {
 constexpr int BM = 128, BK = 64;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
 
+constexpr int KC = 2;  // 64-channel chunks per pipeline step: one TMA box per operand carries up to KC chunks
+
 struct TcSeg {
   int ncblk, ntaps, stride;
+  int spt;      // steps per tap = ceil(ncblk / KC)
+  int kchunk0;  // index of this segment's first 64-wide K chunk in the weight matrix
   int dh[9], dw[9], coff[9];
 };
 
 struct TcParams {
-  CUtensorMap tmA[MVLDM_MAX_SEGS];
-  CUtensorMap tmB;
+  CUtensorMap tmA[MVLDM_MAX_SEGS][KC];  // [segment][chunks per box - 1]: 5-D (64 ch, w, h, image, chunk)
+  CUtensorMap tmB[KC];                   // 3-D (64 k, n, chunk)
   TcSeg seg[MVLDM_MAX_SEGS];
   int nseg;
-  int M, N, num_kb;
-  int mt, nt, splits;  // work items = mt * nt * splits, m fastest
-  int kb_per_split;    // k-blocks per split (== num_kb when not split)
+  int M, N, num_steps;
+  int mt, nt, splits;   // work items = mt * nt * splits, m fastest
+  int steps_per_split;  // pipeline steps per split (== num_steps when not split)
   float* partial;    // split-K: fp32 partial tiles [splits][M][N]; NULL when not split
   int* counters;     // split-K fused reduction: [2][mt*nt] arrive / done counters (all zero between launches), or NULL
   int hw, ow;        // output pixels per image / row width (tile -> image coordinates)
@@ -87,7 +91,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int B_BYTES = BN * BK * 2;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGE_BYTES = KC * (A_BYTES + B_BYTES);  // smem reserved per stage
+  constexpr int B_OFF = KC * A_BYTES;
   constexpr int ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));  // one accumulator buffer
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[STAGES];
@@ -101,8 +106,8 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   const int num_work = p.mt * p.nt * p.splits;
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < p.nseg; ++i) tc::tma_prefetch_desc(&p.tmA[i]);
-    tc::tma_prefetch_desc(&p.tmB);
+    for (int i = 0; i < p.nseg; ++i) tc::tma_prefetch_desc(&p.tmA[i][KC - 1]);
+    tc::tma_prefetch_desc(&p.tmB[KC - 1]);
     for (int s = 0; s < STAGES; ++s) {
       tc::mbar_init(tc::smem_u32(&bar_full[s]), 1);
       tc::mbar_init(tc::smem_u32(&bar_empty[s]), 1);
@@ -129,28 +134,30 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
         const int mtile = w % p.mt, ntile = (w / p.mt) % p.nt, z = w / (p.mt * p.nt);
         const int m0 = mtile * BM, n0 = ntile * BN;
-        const int kb_begin = z * p.kb_per_split;
-        const int nkb = min(p.num_kb - kb_begin, p.kb_per_split);
+        const int st_begin = z * p.steps_per_split;
+        const int nst = min(p.num_steps - st_begin, p.steps_per_split);
         const int img0 = m0 / p.hw;
         const int y0 = (m0 - img0 * p.hw) / p.ow;
-        // locate (segment, tap, channel block) of the first k-block
-        int s = 0, t = 0, cb = kb_begin;
-        while (cb >= p.seg[s].ntaps * p.seg[s].ncblk) {
-          cb -= p.seg[s].ntaps * p.seg[s].ncblk;
+        // locate (segment, tap, channel block) of the first step
+        int s = 0, t = 0, cb = st_begin;
+        while (cb >= p.seg[s].ntaps * p.seg[s].spt) {
+          cb -= p.seg[s].ntaps * p.seg[s].spt;
           ++s;
         }
-        t = cb / p.seg[s].ncblk;
-        cb -= t * p.seg[s].ncblk;
-        for (int i = 0; i < nkb; ++i, ++it) {
+        t = cb / p.seg[s].spt;
+        cb = (cb - t * p.seg[s].spt) * KC;
+        for (int i = 0; i < nst; ++i, ++it) {
           const TcSeg& sg = p.seg[s];
+          const int kc = min(KC, sg.ncblk - cb);
           const int stage = it % STAGES;
           tc::mbar_wait(tc::smem_u32(&bar_empty[stage]), ((it / STAGES) & 1) ^ 1);
           const uint32_t full = tc::smem_u32(&bar_full[stage]);
-          tc::mbar_expect_tx(full, STAGE_BYTES);
+          tc::mbar_expect_tx(full, kc * (A_BYTES + B_BYTES));
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          tc::tma_load_4d(sa, &p.tmA[s], full, sg.coff[t] + cb * BK, sg.dw[t], y0 * sg.stride + sg.dh[t], img0);
-          tc::tma_load_2d(sa + A_BYTES, &p.tmB, full, (kb_begin + i) * BK, n0);
-          if (++cb == sg.ncblk) {
+          tc::tma_load_5d(sa, &p.tmA[s][kc - 1], full, 0, sg.dw[t], y0 * sg.stride + sg.dh[t], img0, sg.coff[t] / BK + cb);
+          tc::tma_load_3d(sa + B_OFF, &p.tmB[kc - 1], full, 0, n0, sg.kchunk0 + t * sg.ncblk + cb);
+          cb += kc;
+          if (cb == sg.ncblk) {
             cb = 0;
             if (++t == sg.ntaps) {
               t = 0;
@@ -167,22 +174,41 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
       int it = 0, wi = 0;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wi) {
         const int z = w / (p.mt * p.nt);
-        const int nkb = min(p.num_kb - z * p.kb_per_split, p.kb_per_split);
+        const int st_begin = z * p.steps_per_split;
+        const int nst = min(p.num_steps - st_begin, p.steps_per_split);
+        int s = 0, t = 0, cb = st_begin;  // same walk as the producer, to know how many chunks each step carries
+        while (cb >= p.seg[s].ntaps * p.seg[s].spt) {
+          cb -= p.seg[s].ntaps * p.seg[s].spt;
+          ++s;
+        }
+        t = cb / p.seg[s].spt;
+        cb = (cb - t * p.seg[s].spt) * KC;
         const int ab = wi & 1;
         tc::mbar_wait(tc::smem_u32(&bar_acc_empty[ab]), ((wi >> 1) & 1) ^ 1);  // epilogue has drained this buffer
         tc::tc_fence_after();
         const uint32_t tmem_d = tmem_base + ab * ACC_COLS;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        for (int i = 0; i < nst; ++i, ++it) {
+          const int kc = min(KC, p.seg[s].ncblk - cb);
           const int stage = it % STAGES;
           tc::mbar_wait(tc::smem_u32(&bar_full[stage]), (it / STAGES) & 1);
           tc::tc_fence_after();
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          const uint64_t adesc = tc::umma_desc_k_sw128(sa);
-          const uint64_t bdesc = tc::umma_desc_k_sw128(sa + A_BYTES);
+          for (int c = 0; c < kc; ++c) {
+            const uint64_t adesc = tc::umma_desc_k_sw128(sa + c * A_BYTES);
+            const uint64_t bdesc = tc::umma_desc_k_sw128(sa + B_OFF + c * B_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)  // +32 bytes (=2 in descriptor units) per K=16 slice inside the swizzle atom
-            tc::umma_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k)  // +32 bytes (=2 in descriptor units) per K=16 slice inside the swizzle atom
+              tc::umma_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (i | c | k) != 0);
+          }
           tc::umma_commit(tc::smem_u32(&bar_empty[stage]));  // frees the smem slot when these MMAs retire
+          cb += kc;
+          if (cb == p.seg[s].ncblk) {
+            cb = 0;
+            if (++t == p.seg[s].ntaps) {
+              t = 0;
+              ++s;
+            }
+          }
         }
         tc::umma_commit(tc::smem_u32(&bar_acc_full[ab]));
       }
@@ -386,7 +412,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 
 template <int BN, int STAGES>
 void launch(cudaStream_t s, const TcParams& p, int splits) {
-  constexpr int smem = STAGES * (A_BYTES + BN * BK * 2) + 1024;
+  constexpr int smem = STAGES * KC * (A_BYTES + BN * BK * 2) + 1024;
   static bool configured = false;
   if (!configured) {
     MV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -415,22 +441,32 @@ struct TileChoice {
   int bn, splits;
 };
 
+int count_steps(const mvldm_gemm_desc& d) {
+  int steps = 0;
+  for (int i = 0; i < d.nseg; ++i) steps += d.seg[i].ntaps * ceil_div(d.seg[i].c / BK, KC);
+  return steps;
+}
+
 TileChoice pick_tiles(const mvldm_gemm_desc& d) {
   static const int kBN[5] = {256, 160, 128, 64, 32};
   static const int kSplits[12] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 24, 32};
-  const int M = d.n_img * d.oh * d.ow, mt = ceil_div(M, BM), num_kb = d.k / BK;
+  const int M = d.n_img * d.oh * d.ow, mt = ceil_div(M, BM), num_steps = count_steps(d);
+  const double kb_per_step = (double)(d.k / BK) / num_steps;  // 64-chunks an average step carries (<= KC)
   TileChoice best{0, 1};
   double best_t = 1e30;
   for (int bn : kBN) {
     if (d.n % bn != 0) continue;
     if (d.mode == 2 && bn != 32) continue;
     for (int sp : kSplits) {
-      if (sp > 1 && (d.mode != 0 || num_kb / sp < 4)) break;
-      const int kb_per = ceil_div(num_kb, sp), splits = ceil_div(num_kb, kb_per);
+      if (sp > 1 && (d.mode != 0 || num_steps / sp < 3)) break;
+      const int st_per = ceil_div(num_steps, sp), splits = ceil_div(num_steps, st_per);
       const double ctas = (double)mt * (d.n / bn) * splits;
-      const double per_sm = std::ceil(ctas / 148.0);                       // work items the busiest SM runs
-      const double main = kb_per * std::max((A_BYTES + bn * 128.0) / 67e9, 4.0 * (bn / 2.0) / 1.9e9);
-      const double epi = bn * (d.mode == 1 ? 12e-9 : 6e-9);               // TMEM -> registers -> global, per item
+      const double per_sm = std::ceil(ctas / 148.0);  // work items the busiest SM runs
+      // measured (tools/micro/tma_ingest.cu): ~4.3 TMA boxes/us per SM whatever their size, <= ~150 GB/s per SM
+      const double step_bytes = kb_per_step * (A_BYTES + bn * 128.0);
+      const double t_step = std::max(std::max(2.0 / 4.3e6, step_bytes / 150e9), kb_per_step * 4.0 * (bn / 2.0) / 1.9e9);
+      const double main = st_per * t_step;
+      const double epi = bn * (d.mode == 1 ? 12e-9 : 6e-9);  // TMEM -> registers -> global, per item
       // persistent CTA: ramp once, items back to back (epilogue hidden behind the next main loop), last epilogue exposed
       const double t_sm = 1.5e-6 + per_sm * std::max(main, epi) + epi;
       const double t_red = splits > 1 ? (splits + 1.0) * M * (double)d.n * 4.0 / 3e12 + 3e-6 : 0.0;
@@ -467,10 +503,13 @@ void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t w
   const int bw = d.ow;
   const int bh = std::min(d.oh, BM / bw);
   const int bn = BM / (bw * bh);
+  const TileChoice tile = pick_tiles(d);
+  const int BN = tile.bn;
+  MV_CHECK(BN != 0, "gemm_tc: N must be a multiple of 32");
   int ktot = 0;
   for (int i = 0; i < d.nseg; ++i) {
     const mvldm_aseg& a = d.seg[i];
-    MV_CHECK(a.c % BK == 0 && a.ctot % 8 == 0, "gemm_tc: segment channels must be a multiple of 64");
+    MV_CHECK(a.c % BK == 0 && a.ctot % BK == 0, "gemm_tc: segment channels must be a multiple of 64");
     MV_CHECK(a.stride == 1 || a.stride == 2, "gemm_tc: stride must be 1 or 2");
     MV_CHECK(a.sh == d.oh * a.stride && a.sw == d.ow * a.stride, "gemm_tc: source / output size mismatch");
     MV_CHECK((reinterpret_cast<uintptr_t>(a.ptr) & 15) == 0, "gemm_tc: source pointer must be 16-byte aligned");
@@ -478,42 +517,48 @@ void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t w
     t.ncblk = a.c / BK;
     t.ntaps = a.ntaps;
     t.stride = a.stride;
+    t.spt = ceil_div(t.ncblk, KC);
+    t.kchunk0 = ktot / BK;
     for (int j = 0; j < a.ntaps; ++j) {
       t.dh[j] = a.dh[j];
       t.dw[j] = a.dw[j];
       t.coff[j] = a.coff[j];
-      MV_CHECK(a.coff[j] % 8 == 0, "gemm_tc: tap channel offset must be a multiple of 8");
+      MV_CHECK(a.coff[j] % BK == 0, "gemm_tc: tap channel offset must be a multiple of 64");
     }
-    const uint64_t dims[4] = {(uint64_t)a.ctot, (uint64_t)a.sw, (uint64_t)a.sh, (uint64_t)d.n_img};
-    const uint64_t strides[3] = {(uint64_t)a.ctot * 2, (uint64_t)a.sw * a.ctot * 2, (uint64_t)a.sh * a.sw * a.ctot * 2};
-    const uint32_t box[4] = {(uint32_t)BK, (uint32_t)(bw * a.stride), (uint32_t)(bh * a.stride), (uint32_t)bn};
-    const uint32_t es[4] = {1, (uint32_t)a.stride, (uint32_t)a.stride, 1};
-    p.tmA[i] = make_tmap_bf16(a.ptr, 4, dims, strides, box, es);
+    // 5-D view (64 channels, w, h, image, 64-channel chunk): the chunk is the slowest box dimension so that one
+    // box lands as [chunk][pixel][128 B] = consecutive K-major SW128 operand tiles
+    const uint64_t dims[5] = {(uint64_t)BK, (uint64_t)a.sw, (uint64_t)a.sh, (uint64_t)d.n_img, (uint64_t)(a.ctot / BK)};
+    const uint64_t strides[4] = {(uint64_t)a.ctot * 2, (uint64_t)a.sw * a.ctot * 2, (uint64_t)a.sh * a.sw * a.ctot * 2,
+                                 (uint64_t)BK * 2};
+    const uint32_t es[5] = {1, (uint32_t)a.stride, (uint32_t)a.stride, 1, 1};
+    for (int kc = 1; kc <= KC; ++kc) {
+      const uint32_t box[5] = {(uint32_t)BK, (uint32_t)(bw * a.stride), (uint32_t)(bh * a.stride), (uint32_t)bn, (uint32_t)kc};
+      p.tmA[i][kc - 1] = make_tmap_bf16(a.ptr, 5, dims, strides, box, es);
+    }
     ktot += a.c * a.ntaps;
   }
   p.nseg = d.nseg;
   MV_CHECK(ktot == d.k, "gemm_tc: K mismatch between segments and weights");
-  p.num_kb = d.k / BK;
-  const TileChoice tile = pick_tiles(d);
-  const int BN = tile.bn;
-  MV_CHECK(BN != 0, "gemm_tc: N must be a multiple of 32");
+  p.num_steps = count_steps(d);
+  MV_CHECK(d.mode != 2 || d.n == 32, "gemm_tc: NCHW head output expects N padded to 32");
+  {
+    const uint64_t dims[3] = {(uint64_t)BK, (uint64_t)d.n, (uint64_t)(d.k / BK)};
+    const uint64_t strides[2] = {(uint64_t)d.k * 2, (uint64_t)BK * 2};
+    const uint32_t es[3] = {1, 1, 1};
+    for (int kc = 1; kc <= KC; ++kc) {
+      const uint32_t box[3] = {(uint32_t)BK, (uint32_t)BN, (uint32_t)kc};
+      p.tmB[kc - 1] = make_tmap_bf16(d.w, 3, dims, strides, box, es);
+    }
+  }
   int splits = tile.splits;
   if (splits > 1 && gemm_tc_workspace_bytes(d) > workspace_bytes) splits = 1;  // no scratch: plain single-pass GEMM
-  p.kb_per_split = ceil_div(p.num_kb, splits);
-  splits = ceil_div(p.num_kb, p.kb_per_split);
+  p.steps_per_split = ceil_div(p.num_steps, splits);
+  splits = ceil_div(p.num_steps, p.steps_per_split);
   p.partial = splits > 1 ? reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kCounterBytes) : nullptr;
   // fused reduction needs every split of a tile resident at once: one work item per CTA, grid <= #SMs
   const int work = ceil_div(p.M, BM) * (d.n / BN) * splits;
   const bool fused = splits > 1 && work <= 148 && ceil_div(p.M, BM) * (d.n / BN) <= 4096;
   p.counters = fused ? reinterpret_cast<int*>(workspace) : nullptr;
-  MV_CHECK(d.mode != 2 || d.n == 32, "gemm_tc: NCHW head output expects N padded to 32");
-  {
-    const uint64_t dims[2] = {(uint64_t)d.k, (uint64_t)d.n};
-    const uint64_t strides[1] = {(uint64_t)d.k * 2};
-    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
-    const uint32_t es[2] = {1, 1};
-    p.tmB = make_tmap_bf16(d.w, 2, dims, strides, box, es);
-  }
   p.bias = d.bias;
   p.rowvec = d.rowvec;
   p.rowvec_ld = d.rowvec_ld;
@@ -524,11 +569,11 @@ void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t w
   p.ldo = d.ldo;
   p.n_valid = d.n_valid;
   if (d.mode == 0) MV_CHECK(d.ldo % 8 == 0 && (!d.residual || d.res_ld % 8 == 0), "gemm_tc: row pitch must be a multiple of 8");
-  if (BN == 256) launch<256, 4>(s, p, splits);
-  else if (BN == 160) launch<160, 6>(s, p, splits);
-  else if (BN == 128) launch<128, 6>(s, p, splits);
-  else if (BN == 64) launch<64, 8>(s, p, splits);
-  else launch<32, 8>(s, p, splits);
+  if (BN == 256) launch<256, 2>(s, p, splits);        // 2 x 96 KB
+  else if (BN == 160) launch<160, 3>(s, p, splits);   // 3 x 72 KB
+  else if (BN == 128) launch<128, 3>(s, p, splits);   // 3 x 64 KB
+  else if (BN == 64) launch<64, 4>(s, p, splits);     // 4 x 48 KB
+  else launch<32, 5>(s, p, splits);                   // 5 x 40 KB
   if (splits > 1 && !fused) {
     const int64_t total = (int64_t)p.M * (p.N / 8);
     const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
