@@ -235,15 +235,47 @@ def run_gpu(args):
     value = world * S * args.steps / (ms * 1e-3)
     e2e = world * S * args.steps / (ms_e2e * 1e-3)
 
+    # ---- per-kernel roofline: CUDA-event pairs around every launch of one more (eager) forward, on its stream
+    prof = None
+    if rank == 0:
+        inp = mv.build_inputs(d_x, d_ctx[:, :, :4], rays)
+        tt = torch.cat([torch.zeros(S, V_C, dtype=torch.long, device=dev),
+                        torch.full((S, V_T), ts_list[0], dtype=torch.long, device=dev)], 1)
+        m.set_profiling(True)
+        best = None
+        for _ in range(3):
+            torch.cuda.synchronize()
+            torch.cuda._sleep(int(60e6))       # park the GPU so the host enqueues the whole forward ahead of it
+            m(inp, tt)
+            pr = m.profile()["categories"]
+            tot = sum(c["us"] for c in pr.values())
+            if best is None or tot < best[0]:
+                best = (tot, pr)
+        m.set_profiling(False)
+        prof = best[1]
+    if world > 1:
+        dist.barrier(device_ids=[local])
+
     if rank == 0:
         peaks = load_peaks()
         gf = step_gflop(args.cfg) * S
-        achieved_tf = gf * args.steps / (ms * 1e-3) / 1e3
-        roof = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved_tf / peaks["bf16_tflops"], "traffic": None,
-                "how": ("whole step: algorithmic FLOPs of one DDIM step (BASELINE.md: 137.9 V + 3.069 V^2 GFLOP per forward, "
-                        "head dims un-padded) x steps / CUDA-event time of the timed region; per-kernel figures: profiles/"),
-                "peak_source": peaks["source"]}
+        step_tf = gf * args.steps / (ms * 1e-3) / 1e3
+        conv = prof["gemm_conv3x3"]
+        lin = prof["gemm_linear"]
+        att = prof["attention_joint"]
+        tf = lambda c: c["gflop"] / c["us"] * 1e-3  # noqa: E731  (GFLOP / us = PFLOP/s -> TFLOP/s below)
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM): the conv3x3 launches of one forward "
+                                             f"({conv['launches']} launches, {conv['gflop']:.0f} of {forward_gflop(V_C + V_T) * S:.0f} GFLOP)",
+                "achieved": tf(conv) * 1e3, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": tf(conv) * 1e3 / peaks["bf16_tflops"], "traffic": None,
+                "how": ("algorithmic FLOPs (2*M*N*K, un-padded) of the launches / sum of their durations; every launch is "
+                        "bracketed by a CUDA-event pair on the launching stream inside the library (mvldm_set_profiling), "
+                        "GPU parked behind a spin kernel so the pairs see back-to-back execution; ncu: profiles/"),
+                "peak_source": peaks["source"],
+                "other_kernels_tflops": {"gemm_linear": tf(lin) * 1e3, "attention_joint": tf(att) * 1e3},
+                "us_per_forward": {k: round(c["us"], 1) for k, c in prof.items()},
+                "whole_step": {"achieved": step_tf, "frac": step_tf / peaks["bf16_tflops"],
+                               "how": "algorithmic GFLOP of the step (BASELINE.md) / CUDA-event time of the timed region"}}
         cpu = None
         if not args.no_cpu_baseline:
             n = 3

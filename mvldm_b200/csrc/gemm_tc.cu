@@ -485,6 +485,7 @@ TileChoice pick_tiles(const mvldm_gemm_desc& d) {
 constexpr size_t kCounterBytes = 2 * 4096 * sizeof(int);  // arrive/done counters live at the head of the workspace
 
 size_t gemm_tc_workspace_bytes(const mvldm_gemm_desc& d) {
+  if (count_steps(d) == 0) return 0;
   const int splits = pick_tiles(d).splits;
   return splits > 1 ? kCounterBytes + (size_t)splits * d.n_img * d.oh * d.ow * d.n * sizeof(float) : 0;
 }
@@ -503,6 +504,8 @@ void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t w
   const int bw = d.ow;
   const int bh = std::min(d.oh, BM / bw);
   const int bn = BM / (bw * bh);
+  for (int i = 0; i < d.nseg; ++i)
+    MV_CHECK(d.seg[i].c >= BK && d.seg[i].c % BK == 0, "gemm_tc: segment channels must be a multiple of 64");
   const TileChoice tile = pick_tiles(d);
   const int BN = tile.bn;
   MV_CHECK(BN != 0, "gemm_tc: N must be a multiple of 32");
