@@ -4,9 +4,9 @@
 // materialises in fp32 (2.1 GB per level-0 block at 8 views) never leaves the SM.
 //
 // One CTA = 128 queries of one (batch, head).  Per 128-key (64 for head_dim_pad 192) tile:
-//   S = Q K^T          tcgen05.mma  SS  (Q, K in smem via TMA, K-major SW128)      -> TMEM fp32, double-buffered
-//   softmax            4 warps, one query row per thread: tcgen05.ld S, running max with lazy rescale, exp2,
-//                      row sum in fp32, P -> bf16 written back over S in TMEM (tcgen05.st)
+//   S = Q K^T          tcgen05.mma  SS  (Q, K in smem via TMA, K-major SW128)      -> TMEM fp32
+//   softmax            4 warps, one query row per thread: tcgen05.ld S in 32-column chunks, exp2 against a lazily
+//                      moved running reference, row sum in fp32, P -> bf16 into its own TMEM columns (tcgen05.st)
 //   O += P V           tcgen05.mma  TS  (P from TMEM, V from smem as an MN-major SW128 operand) -> TMEM fp32
 // Scores are fp32 and the softmax is fp32 exactly as ATTN_PRECISION=fp32 (attention.py:185-203); P is
 // rounded to bf16 before P.V as autocast does at :203.
@@ -40,17 +40,21 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-// DPAD: padded head dim (64/128/192); BN: keys per tile; ST: K/V ring stages
-template <int DPAD, int BN, int ST>
-__global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
+// DPAD: padded head dim (64/128/192); BN: keys per tile; ST: K/V ring stages; OCC: CTAs per SM the budget allows
+template <int DPAD, int BN, int ST, int OCC>
+__global__ void __launch_bounds__(192, OCC) attn_tc_kernel(const __grid_constant__ AttnParams p) {
   constexpr int NC = DPAD / 64;                // 64-column chunks per row
   constexpr int Q_BYTES = NC * BM * 128;
   constexpr int KV_CHUNK = BN * 128;           // one 64-column chunk of a K or V tile
   constexpr int STAGE_BYTES = 2 * NC * KV_CHUNK;
-  constexpr uint32_t S_COL0 = 0, S_COL1 = BN, O_COL = 2 * BN;
-  static_assert(2 * BN + DPAD <= 512, "TMEM budget");
+  // TMEM columns: S (fp32 scores) | P (bf16 pairs) | O (fp32 accumulator).  For DPAD = 64 this is exactly 256
+  // columns, so two CTAs share an SM: while one CTA's softmax warps wait for the tensor pipe the other's run,
+  // which keeps the MUFU (exp2) pipe - the real bound of this kernel - busy.
+  constexpr uint32_t S_COL = 0, P_COL = BN, O_COL = BN + BN / 2;
+  constexpr int TMEM_COLS = (BN + BN / 2 + DPAD) <= 256 ? 256 : 512;
+  static_assert(BN + BN / 2 + DPAD <= 512, "TMEM budget");
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_q, bar_kv_full[ST], bar_kv_empty[ST], bar_s[2], bar_p[2], bar_o;
+  __shared__ __align__(8) uint64_t bar_q, bar_kv_full[ST], bar_kv_empty[ST], bar_s, bar_p, bar_o;
   __shared__ uint32_t tmem_slot;
 
   const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -69,14 +73,12 @@ __global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__
       tc::mbar_init(tc::smem_u32(&bar_kv_full[s]), 1);
       tc::mbar_init(tc::smem_u32(&bar_kv_empty[s]), 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      tc::mbar_init(tc::smem_u32(&bar_s[b]), 1);
-      tc::mbar_init(tc::smem_u32(&bar_p[b]), 128);
-    }
+    tc::mbar_init(tc::smem_u32(&bar_s), 1);
+    tc::mbar_init(tc::smem_u32(&bar_p), 128);
     tc::mbar_init(tc::smem_u32(&bar_o), 1);
     tc::mbar_fence_init();
   }
-  if (warp == 1) tc::tmem_alloc<512>(tc::smem_u32(&tmem_slot));
+  if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tc::smem_u32(&tmem_slot));
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -111,31 +113,29 @@ __global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__
         tc::mbar_wait(tc::smem_u32(&bar_kv_full[stage]), (j / ST) & 1);
         tc::tc_fence_after();
         const uint32_t ks = kv_smem + stage * STAGE_BYTES;
-        const uint32_t s_tmem = tmem + ((j & 1) ? S_COL1 : S_COL0);
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           const uint64_t qd = tc::umma_desc_k_sw128(q_smem + c * BM * 128);
           const uint64_t kd = tc::umma_desc_k_sw128(ks + c * KV_CHUNK);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc::umma_ss(s_tmem, qd + 2 * k, kd + 2 * k, idesc_qk, (c | k) != 0);
+          for (int k = 0; k < 4; ++k) tc::umma_ss(tmem + S_COL, qd + 2 * k, kd + 2 * k, idesc_qk, (c | k) != 0);
         }
-        tc::umma_commit(tc::smem_u32(&bar_s[j & 1]));
+        tc::umma_commit(tc::smem_u32(&bar_s));
       };
       tc::mbar_wait(tc::smem_u32(&bar_q), 0);
       issue_qk(0);
       for (int j = 0; j < T; ++j) {
-        if (j + 1 < T) issue_qk(j + 1);  // S(j+1) is computed while the softmax warps work on S(j)
-        tc::mbar_wait(tc::smem_u32(&bar_p[j & 1]), (j >> 1) & 1);
+        tc::mbar_wait(tc::smem_u32(&bar_p), j & 1);  // softmax has read S(j) and written P(j)
         tc::tc_fence_after();
         const int stage = j % ST;
         const uint32_t vs = kv_smem + stage * STAGE_BYTES + NC * KV_CHUNK;
-        const uint32_t p_tmem = tmem + ((j & 1) ? S_COL1 : S_COL0);
         const uint64_t vd = tc::umma_desc_mn_sw128(vs, KV_CHUNK);
 #pragma unroll
         for (int kk = 0; kk < BN / 16; ++kk)  // 16 keys per MMA: 8 packed-bf16 TMEM columns of P, 16 V rows (2 KB)
-          tc::umma_ts(tmem + O_COL, p_tmem + kk * 8, vd + kk * 128, idesc_pv, (j | kk) != 0);
+          tc::umma_ts(tmem + O_COL, tmem + P_COL + kk * 8, vd + kk * 128, idesc_pv, (j | kk) != 0);
         tc::umma_commit(tc::smem_u32(&bar_kv_empty[stage]));
         tc::umma_commit(tc::smem_u32(&bar_o));
+        if (j + 1 < T) issue_qk(j + 1);  // S is free again (in-order tensor pipe: after P V(j))
       }
     }
     __syncwarp();
@@ -144,60 +144,68 @@ __global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__
     const int quarter = warp & 3;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int row = q0 + quarter * 32 + lane;
+    const float sc = p.scale_log2;
     float m_ref = -INFINITY, l_sum = 0.f;
     for (int j = 0; j < T; ++j) {
-      const uint32_t s_tmem = tmem + lane_addr + ((j & 1) ? S_COL1 : S_COL0);
-      tc::mbar_wait(tc::smem_u32(&bar_s[j & 1]), (j >> 1) & 1);
+      tc::mbar_wait(tc::smem_u32(&bar_s), j & 1);
       tc::tc_fence_after();
-      uint32_t r[BN];
+      const int valid = (j == T - 1) ? p.seq - j * BN : BN;  // ragged tail: keys past the sequence end do not exist
+      // P is computed against the running reference m_ref from earlier tiles, so no separate max pass sits in front
+      // of the exponentials.  If this tile raises the row maximum by more than 2^8 (always on the first tile) the
+      // reference is moved, O and l are rescaled, and the tile is redone - rare after the first few tiles.
+      for (int pass = 0; pass < 2; ++pass) {
+        const float mb = m_ref * sc;
+        float mt = -INFINITY, l0 = 0.f, l1 = 0.f;
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) tc::tmem_ld32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
-      tc::tmem_ld_wait();
-      if (j == T - 1 && (p.seq % BN) != 0) {  // ragged tail: keys past the sequence end do not exist
-        const int valid = p.seq - j * BN;
-#pragma unroll
-        for (int i = 0; i < BN; ++i)
-          if (i >= valid) r[i] = 0xff800000u;  // -inf
-      }
-      float mt = __uint_as_float(r[0]);
-#pragma unroll
-      for (int i = 1; i < BN; ++i) mt = fmaxf(mt, __uint_as_float(r[i]));
-      // lazy running max: move the reference only when it would otherwise let P exceed 2^8
-      const bool grow = (mt - m_ref) * p.scale_log2 > 8.f;  // also true on the first tile (m_ref = -inf)
-      if (__any_sync(0xffffffffu, grow) && j > 0) {
-        const float m_new = grow ? mt : m_ref;
-        const float f = ex2((m_ref - m_new) * p.scale_log2);
-        tc::mbar_wait(tc::smem_u32(&bar_o), (j - 1) & 1);  // P V of the previous tile has landed in O
-        tc::tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < DPAD / 32; ++c) {
-          uint32_t o[32];
-          tc::tmem_ld32(tmem + lane_addr + O_COL + c * 32, o);
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tc::tmem_ld32(tmem + lane_addr + S_COL + c * 32, r);
           tc::tmem_ld_wait();
+          if (valid < BN) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-          tc::tmem_st16(tmem + lane_addr + O_COL + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&o[0]));
-          tc::tmem_st16(tmem + lane_addr + O_COL + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&o[16]));
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= valid) r[i] = 0xff800000u;  // -inf
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float s0 = __uint_as_float(r[i]), s1 = __uint_as_float(r[i + 1]);
+            mt = fmaxf(mt, fmaxf(s0, s1));
+            const float p0 = ex2(fmaf(s0, sc, -mb)), p1 = ex2(fmaf(s1, sc, -mb));
+            l0 += p0;
+            l1 += p1;
+            pk[i / 2] = pack_bf16(p0, p1);
+          }
+          tc::tmem_st16(tmem + lane_addr + P_COL + c * 16, pk);
         }
-        l_sum *= f;
-        m_ref = m_new;
-      } else if (grow) {
-        m_ref = mt;  // first tile: nothing accumulated yet
-      }
-      const float mb = m_ref * p.scale_log2;
-      uint32_t pk[BN / 2];
+        const bool grow = (mt - m_ref) * sc > 8.f;  // true on the first tile (m_ref = -inf)
+        if (!__any_sync(0xffffffffu, grow)) {
+          l_sum += l0 + l1;
+          break;
+        }
+        // move the reference (per row; rows that did not grow keep theirs and rescale by 1)
+        const float m_new = grow ? mt : m_ref;
+        if (j > 0) {
+          const float f = ex2((m_ref - m_new) * sc);
+          tc::mbar_wait(tc::smem_u32(&bar_o), (j - 1) & 1);  // P V of the previous tile has landed in O
+          tc::tc_fence_after();
 #pragma unroll
-      for (int i = 0; i < BN; i += 2) {
-        const float p0 = ex2(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb));
-        const float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -mb));
-        l_sum += p0 + p1;
-        pk[i / 2] = pack_bf16(p0, p1);
-      }
+          for (int c = 0; c < DPAD / 32; ++c) {
+            uint32_t o[32];
+            tc::tmem_ld32(tmem + lane_addr + O_COL + c * 32, o);
+            tc::tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) tc::tmem_st16(s_tmem + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[c * 16]));
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tc::tmem_st16(tmem + lane_addr + O_COL + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&o[0]));
+            tc::tmem_st16(tmem + lane_addr + O_COL + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&o[16]));
+          }
+          l_sum *= f;
+        }
+        m_ref = m_new;  // second pass recomputes P(j) against the new reference (it cannot grow again)
+      }
       tc::tmem_st_wait();
       tc::tc_fence_before();
-      tc::mbar_arrive(tc::smem_u32(&bar_p[j & 1]));
+      tc::mbar_arrive(tc::smem_u32(&bar_p));
     }
     // ---- epilogue: O / l -> bf16, head-padded row
     tc::mbar_wait(tc::smem_u32(&bar_o), (T - 1) & 1);
@@ -225,11 +233,11 @@ __global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__
   __syncthreads();
   if (warp == 1) {
     tc::tc_fence_after();
-    tc::tmem_dealloc<512>(tmem);
+    tc::tmem_dealloc<TMEM_COLS>(tmem);
   }
 }
 
-template <int DPAD, int BN, int ST>
+template <int DPAD, int BN, int ST, int OCC>
 void launch(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, int heads, int d) {
   AttnParams p{};
   const int ld = 3 * heads * DPAD;
@@ -248,11 +256,11 @@ void launch(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, in
   constexpr int smem = (DPAD / 64) * BM * 128 + ST * 2 * (DPAD / 64) * BN * 128 + 1024;
   static bool configured = false;
   if (!configured) {
-    MV_CUDA(cudaFuncSetAttribute(attn_tc_kernel<DPAD, BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MV_CUDA(cudaFuncSetAttribute(attn_tc_kernel<DPAD, BN, ST, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   dim3 grid(ceil_div(seq, BM), batches * heads);
-  launch_pdl(attn_tc_kernel<DPAD, BN, ST>, grid, dim3(192), smem, s, p);
+  launch_pdl(attn_tc_kernel<DPAD, BN, ST, OCC>, grid, dim3(192), smem, s, p);
 }
 
 }  // namespace
@@ -261,9 +269,9 @@ void attention_tc(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int s
   MV_CHECK(d <= dpad && seq >= 1 && batches >= 1, "attention_tc: bad arguments");
   MV_CHECK((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
            "attention_tc: pointers must be 16-byte aligned");
-  if (dpad == 64) launch<64, 128, 3>(s, qkv, out, batches, seq, heads, d);
-  else if (dpad == 128) launch<128, 128, 2>(s, qkv, out, batches, seq, heads, d);
-  else if (dpad == 192) launch<192, 64, 2>(s, qkv, out, batches, seq, heads, d);
+  if (dpad == 64) launch<64, 128, 2, 2>(s, qkv, out, batches, seq, heads, d);        // 80 KB smem, 256 TMEM cols: 2 CTAs/SM
+  else if (dpad == 128) launch<128, 128, 2, 1>(s, qkv, out, batches, seq, heads, d);
+  else if (dpad == 192) launch<192, 64, 2, 1>(s, qkv, out, batches, seq, heads, d);
   else MV_CHECK(false, "attention_tc: head_dim_pad must be 64, 128 or 192");
 }
 
