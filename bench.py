@@ -263,7 +263,7 @@ def run_gpu(args):
         conv = prof["gemm_conv3x3"]
         lin = prof["gemm_linear"]
         att = prof["attention_joint"]
-        tf = lambda c: c["gflop"] / c["us"] * 1e-3  # noqa: E731  (GFLOP / us = PFLOP/s -> TFLOP/s below)
+        tf = lambda c: c["gflop"] / c["us"]  # noqa: E731  (GFLOP / us = PFLOP/s; x1e3 below -> TFLOP/s)
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM): the conv3x3 launches of one forward "
                                              f"({conv['launches']} launches, {conv['gflop']:.0f} of {forward_gflop(V_C + V_T) * S:.0f} GFLOP)",
                 "achieved": tf(conv) * 1e3, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",

@@ -159,6 +159,11 @@ int mvldm_op_gemm(void* stream, int impl, const mvldm_gemm_desc* d);
 int mvldm_op_attention(void* stream, int impl, const void* qkv, void* out, int batches, int seq, int heads,
                        int d, int dpad);
 
+/* Debug: clock64() stamps of CTA (0,0) of the last attention launch made with MVLDM_ATTN_TRACE set in the
+ * environment; out[slot*512 + tile], slots 0-2 softmax thread (wait S, got S, P handed over), 3-5 MMA thread
+ * (got P, PV issued, next QK issued). */
+int mvldm_debug_attn_trace(int64_t* out, int n);
+
 /* GroupNorm (+SiLU) over NHWC bf16, optionally over the channel concat of two sources
  * (torch.cat at mvunet.py:176 + ResnetBlock2D.norm1): out bf16 [n_img, hw, c0+c1]. */
 int mvldm_op_groupnorm(void* stream, const void* x0, int c0, const void* x1, int c1, int n_img, int hw,

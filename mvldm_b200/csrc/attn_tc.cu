@@ -14,6 +14,8 @@
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2..5 softmax/epilogue.
 // The running maximum is only moved when it grows by more than 2^8 (exact: any reference point is a valid
 // softmax shift; P <= 256 stays well inside bf16 range), so the O accumulator is almost never touched.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -22,12 +24,19 @@ namespace {
 
 constexpr int BM = 128;
 
+// optional in-kernel timeline (tools/attn_trace.py): CTA (0,0) stamps clock64() at the pipeline hand-offs
+__device__ long long g_attn_trace[8 * 512];
+__device__ __forceinline__ void trace(bool on, int slot, int j) {
+  if (on && j < 512) g_attn_trace[slot * 512 + j] = clock64();
+}
+
 struct AttnParams {
   CUtensorMap tmQ;   // box [64, 128, 1] over (cols, seq, batch)
   CUtensorMap tmKV;  // box [64, BN, 1]
   bf16* out;
   int seq, heads, d, dpad;
   float scale_log2;  // d^-1/2 * log2(e)
+  int trace;
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -64,6 +73,7 @@ __global__ void __launch_bounds__(192, OCC) attn_tc_kernel(const __grid_constant
   const int q0 = blockIdx.x * BM;
   const int batch = blockIdx.y / p.heads, head = blockIdx.y % p.heads;
   const int T = (p.seq + BN - 1) / BN;
+  const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0;
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&p.tmQ);
@@ -127,6 +137,7 @@ __global__ void __launch_bounds__(192, OCC) attn_tc_kernel(const __grid_constant
       for (int j = 0; j < T; ++j) {
         tc::mbar_wait(tc::smem_u32(&bar_p), j & 1);  // softmax has read S(j) and written P(j)
         tc::tc_fence_after();
+        trace(tr, 3, j);
         const int stage = j % ST;
         const uint32_t vs = kv_smem + stage * STAGE_BYTES + NC * KV_CHUNK;
         const uint64_t vd = tc::umma_desc_mn_sw128(vs, KV_CHUNK);
@@ -135,7 +146,9 @@ __global__ void __launch_bounds__(192, OCC) attn_tc_kernel(const __grid_constant
           tc::umma_ts(tmem + O_COL, tmem + P_COL + kk * 8, vd + kk * 128, idesc_pv, (j | kk) != 0);
         tc::umma_commit(tc::smem_u32(&bar_kv_empty[stage]));
         tc::umma_commit(tc::smem_u32(&bar_o));
+        trace(tr, 4, j);
         if (j + 1 < T) issue_qk(j + 1);  // S is free again (in-order tensor pipe: after P V(j))
+        trace(tr, 5, j);
       }
     }
     __syncwarp();
@@ -147,20 +160,20 @@ __global__ void __launch_bounds__(192, OCC) attn_tc_kernel(const __grid_constant
     const float sc = p.scale_log2;
     float m_ref = -INFINITY, l_sum = 0.f;
     for (int j = 0; j < T; ++j) {
+      trace(tr && threadIdx.x == 64, 0, j);
       tc::mbar_wait(tc::smem_u32(&bar_s), j & 1);
       tc::tc_fence_after();
+      trace(tr && threadIdx.x == 64, 1, j);
       const int valid = (j == T - 1) ? p.seq - j * BN : BN;  // ragged tail: keys past the sequence end do not exist
       // P is computed against the running reference m_ref from earlier tiles, so no separate max pass sits in front
       // of the exponentials.  If this tile raises the row maximum by more than 2^8 (always on the first tile) the
       // reference is moved, O and l are rescaled, and the tile is redone - rare after the first few tiles.
+#pragma unroll 1
       for (int pass = 0; pass < 2; ++pass) {
         const float mb = m_ref * sc;
         float mt = -INFINITY, l0 = 0.f, l1 = 0.f;
-#pragma unroll
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t r[32];
-          tc::tmem_ld32(tmem + lane_addr + S_COL + c * 32, r);
-          tc::tmem_ld_wait();
+        // one 32-column chunk: mask the ragged tail, exp2 against the reference, row sum, pack to bf16, hand to TMEM
+        auto chunk = [&](uint32_t(&r)[32], int c) {
           if (valid < BN) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
@@ -177,6 +190,19 @@ __global__ void __launch_bounds__(192, OCC) attn_tc_kernel(const __grid_constant
             pk[i / 2] = pack_bf16(p0, p1);
           }
           tc::tmem_st16(tmem + lane_addr + P_COL + c * 16, pk);
+        };
+        // software pipeline over two register buffers: the TMEM load of chunk c+1 is in flight while chunk c is
+        // exponentiated (tcgen05.wait::ld is issued before the next load, so it only covers the current chunk)
+        uint32_t ra[32], rb[32];
+        tc::tmem_ld32(tmem + lane_addr + S_COL, ra);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; c += 2) {
+          tc::tmem_ld_wait();
+          tc::tmem_ld32(tmem + lane_addr + S_COL + (c + 1) * 32, rb);
+          chunk(ra, c);
+          tc::tmem_ld_wait();
+          if (c + 2 < BN / 32) tc::tmem_ld32(tmem + lane_addr + S_COL + (c + 2) * 32, ra);
+          chunk(rb, c + 1);
         }
         const bool grow = (mt - m_ref) * sc > 8.f;  // true on the first tile (m_ref = -inf)
         if (!__any_sync(0xffffffffu, grow)) {
@@ -189,7 +215,7 @@ __global__ void __launch_bounds__(192, OCC) attn_tc_kernel(const __grid_constant
           const float f = ex2((m_ref - m_new) * sc);
           tc::mbar_wait(tc::smem_u32(&bar_o), (j - 1) & 1);  // P V of the previous tile has landed in O
           tc::tc_fence_after();
-#pragma unroll
+#pragma unroll 1
           for (int c = 0; c < DPAD / 32; ++c) {
             uint32_t o[32];
             tc::tmem_ld32(tmem + lane_addr + O_COL + c * 32, o);
@@ -206,22 +232,23 @@ __global__ void __launch_bounds__(192, OCC) attn_tc_kernel(const __grid_constant
       tc::tmem_st_wait();
       tc::tc_fence_before();
       tc::mbar_arrive(tc::smem_u32(&bar_p));
+      trace(tr && threadIdx.x == 64, 2, j);
     }
     // ---- epilogue: O / l -> bf16, head-padded row
     tc::mbar_wait(tc::smem_u32(&bar_o), (T - 1) & 1);
     tc::tc_fence_after();
     const float inv = 1.f / l_sum;
     bf16* dst = p.out + ((int64_t)batch * p.seq + row) * (p.heads * DPAD) + head * DPAD;
-#pragma unroll
-    for (int c = 0; c < DPAD / 32; ++c) {
-      uint32_t o[32];
+#pragma unroll 1
+    for (int c = 0; c < DPAD / 16; ++c) {  // rolled, 16 columns at a time: keeps the kernel at two CTAs per SM
+      uint32_t o[16];
       __syncwarp();
-      tc::tmem_ld32(tmem + lane_addr + O_COL + c * 32, o);
+      tc::tmem_ld16(tmem + lane_addr + O_COL + c * 16, o);
       tc::tmem_ld_wait();
       if (row < p.seq) {
-        uint4* op = reinterpret_cast<uint4*>(dst + c * 32);
+        uint4* op = reinterpret_cast<uint4*>(dst + c * 16);
 #pragma unroll
-        for (int v = 0; v < 4; ++v)
+        for (int v = 0; v < 2; ++v)
           op[v] = make_uint4(pack_bf16(__uint_as_float(o[v * 8]) * inv, __uint_as_float(o[v * 8 + 1]) * inv),
                              pack_bf16(__uint_as_float(o[v * 8 + 2]) * inv, __uint_as_float(o[v * 8 + 3]) * inv),
                              pack_bf16(__uint_as_float(o[v * 8 + 4]) * inv, __uint_as_float(o[v * 8 + 5]) * inv),
@@ -253,6 +280,7 @@ void launch(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, in
   p.d = d;
   p.dpad = DPAD;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
+  p.trace = getenv("MVLDM_ATTN_TRACE") != nullptr;
   constexpr int smem = (DPAD / 64) * BM * 128 + ST * 2 * (DPAD / 64) * BN * 128 + 1024;
   static bool configured = false;
   if (!configured) {
@@ -264,6 +292,10 @@ void launch(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, in
 }
 
 }  // namespace
+
+void attention_trace_read(long long* host, int n) {
+  MV_CUDA(cudaMemcpyFromSymbol(host, g_attn_trace, sizeof(long long) * n));
+}
 
 void attention_tc(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, int heads, int d, int dpad) {
   MV_CHECK(d <= dpad && seq >= 1 && batches >= 1, "attention_tc: bad arguments");

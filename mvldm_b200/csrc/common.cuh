@@ -78,6 +78,7 @@ size_t gemm_tc_workspace_bytes(const mvldm_gemm_desc& d);
 void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t workspace_bytes);
 // attn_simt.cu / attn_tc.cu
 void attention_simt(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, int heads, int d, int dpad);
+void attention_trace_read(long long* host, int n);  // debug timeline of CTA (0,0), see MVLDM_ATTN_TRACE
 void attention_tc(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, int heads, int d, int dpad);
 
 // elementwise.cu

@@ -403,13 +403,14 @@ __global__ void __launch_bounds__(GNB_THREADS) gn_block_kernel(const bf16* __res
                                                                int cache, bf16* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t gnb_smem[];
   __shared__ float red_s[GNB_THREADS * 8], red_q[GNB_THREADS * 8];
+  __shared__ float chan_s[GNB_THREADS], chan_q[GNB_THREADS];
   __shared__ float s_mean[16], s_rstd[16];
   pdl_wait();
   pdl_launch_dependents();
   bf16* slab = reinterpret_cast<bf16*>(gnb_smem);
   const int C = c0 + c1, cgn = C / groups, nv = cb / 8, gb = cb / cgn;
   const int img = blockIdx.y, ch0 = blockIdx.x * cb, t = threadIdx.x;
-  const int lanes_p = GNB_THREADS / nv;
+  const int lanes_p = min(GNB_THREADS / nv, hw);  // pixel lanes (no more than there are pixels)
   const int cv = t % nv, pl = t / nv;
   const int c = ch0 + cv * 8;
   const bf16* src = c < c0 ? x0 + (int64_t)img * hw * c0 + c : x1 + (int64_t)img * hw * c1 + (c - c0);
@@ -451,25 +452,36 @@ __global__ void __launch_bounds__(GNB_THREADS) gn_block_kernel(const bf16* __res
     }
   }
   __syncthreads();
-  {  // one warp per group: lanes stride over (pixel lane, channel) in a fixed order, then a fixed shuffle tree
+  {  // fixed-order fold: (1) per channel over the pixel lanes, `parts` threads per channel; (2) per group, one warp
+    const int parts = GNB_THREADS / cb;
+    const int ch = t % cb, part = t / cb;
+    if (part < parts) {
+      float S = 0.f, Q = 0.f;
+      for (int l = part; l < lanes_p; l += parts) {
+        S += red_s[l * cb + ch];
+        Q += red_q[l * cb + ch];
+      }
+      chan_s[part * cb + ch] = S;
+      chan_q[part * cb + ch] = Q;
+    }
+    __syncthreads();
     const int warp = t >> 5, lane = t & 31;
     if (warp < gb) {
       float S = 0.f, Q = 0.f;
-      const int n = lanes_p * cgn;
+      const int n = parts * cgn;
       for (int i = lane; i < n; i += 32) {
-        const int l = i / cgn, cc = warp * cgn + i % cgn;
-        S += red_s[l * cb + cc];
-        Q += red_q[l * cb + cc];
+        const int pt = i / cgn, cc = warp * cgn + i % cgn;
+        S += chan_s[pt * cb + cc];
+        Q += chan_q[pt * cb + cc];
       }
       S = warp_sum(S);
       Q = warp_sum(Q);
       if (lane == 0) {
-        const double cnt = (double)hw * cgn;
-        const double mean = (double)S / cnt;
-        double var = (double)Q / cnt - mean * mean;
-        var = var < 0.0 ? 0.0 : var;
-        s_mean[warp] = (float)mean;
-        s_rstd[warp] = (float)(1.0 / sqrt(var + (double)eps));
+        const float cnt = (float)hw * (float)cgn;
+        const float mean = S / cnt;
+        const float var = fmaxf(Q / cnt - mean * mean, 0.f);
+        s_mean[warp] = mean;
+        s_rstd[warp] = rsqrtf(var + eps);
       }
     }
   }
@@ -540,9 +552,13 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, int rows, int c, fl
   for (int i = 0; i < MAXV; ++i) {
     const int v = lane + 32 * i;
     if (v < nv) {
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8), g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + v * 8), b1 = *reinterpret_cast<const float4*>(beta + v * 8 + 4);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = (f[i][j] - mean) * rstd * gamma[v * 8 + j] + beta[v * 8 + j];
+      for (int j = 0; j < 8; ++j) o[j] = (f[i][j] - mean) * rstd * gg[j] + bb[j];
       store8(out + (int64_t)row * c + v * 8, o);
     }
   }
