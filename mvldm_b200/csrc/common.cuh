@@ -50,8 +50,13 @@ extern thread_local int g_launch_count;
 // pdl_wait(), so RAW and WAR hazards through the reused activation arena are preserved.
 extern bool g_use_pdl;  // MVLDM_PDL=1 enables; default is plain stream order
 #ifdef __CUDACC__
+#ifdef MVLDM_ENABLE_PDL  // compile-time opt-in (measured slower, profiles/r01_notes.md); otherwise the hooks vanish
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_launch_dependents() {}
+#endif
 
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
@@ -64,7 +69,11 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
+#ifdef MVLDM_ENABLE_PDL
   cfg.numAttrs = g_use_pdl ? 1 : 0;
+#else
+  cfg.numAttrs = 0;
+#endif
   MV_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
   MV_LAUNCHED();
 }
@@ -75,6 +84,7 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 void gemm_simt(cudaStream_t s, const mvldm_gemm_desc& d);
 // workspace: fp32 split-K scratch (gemm_tc_workspace_bytes(d) bytes) or NULL/0 to force a single pass
 size_t gemm_tc_workspace_bytes(const mvldm_gemm_desc& d);
+void gemm_trace_read(long long* host, int n);  // debug timeline of CTA 0 (env MVLDM_GEMM_TRACE)
 void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t workspace_bytes);
 // attn_simt.cu / attn_tc.cu
 void attention_simt(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, int heads, int d, int dpad);

@@ -16,6 +16,7 @@
 // Two CTAs fit per SM, so one CTA's epilogue overlaps the other's main loop.
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -45,6 +46,12 @@ CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, con
 namespace {
 
 constexpr int BM = 128, BK = 64;
+
+// optional in-kernel timeline of CTA 0 (env MVLDM_GEMM_TRACE, tools/gemm_trace.py): clock64() at the hand-offs
+__device__ long long g_gemm_trace[16];
+__device__ __forceinline__ void gtrace(bool on, int slot) {
+  if (on) g_gemm_trace[slot] = clock64();
+}
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
 
 constexpr int KC = 2;  // 64-channel chunks per pipeline step: one TMA box per operand carries up to KC chunks
@@ -75,6 +82,8 @@ struct TcParams {
   int mode;
   void* out;
   int ldo, n_valid;
+  int trace;
+  int opt;  // bit 0: bias/rowvec table in smem, bit 1: residual row prefetch, bit 2: 4-way unrolled fused reduce
 };
 
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
@@ -88,6 +97,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // item is (m-tile, n-tile, k-split), m fastest so that the CTAs running concurrently share the same weight tile
 // in L2.  The smem ring runs continuously across work items and the accumulator is double-buffered in TMEM, so
 // the epilogue of item i (TMEM -> registers -> global) overlaps the main loop of item i+1.
+// 256-bit global store: one instruction covers a full 32-byte sector per thread (rows are >= 64 B apart, so 16-byte
+// stores would touch every sector twice)
+__device__ __forceinline__ void st_global_v8(void* ptr, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                             uint32_t a5, uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a0), "r"(a1), "r"(a2), "r"(a3),
+               "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+               : "memory");
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int B_BYTES = BN * BK * 2;
@@ -100,10 +118,14 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   __shared__ __align__(8) uint64_t bar_acc_full[2];
   __shared__ __align__(8) uint64_t bar_acc_empty[2];
   __shared__ uint32_t tmem_base_slot;
+  constexpr int CV_IMGS = 8;                      // images one 128-pixel tile can span in the table below (hw >= 16)
+  __shared__ __align__(16) float s_colvec[CV_IMGS][BN];        // bias[n] + rowvec[image, n] of the current work item
 
   const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-B alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_work = p.mt * p.nt * p.splits;
+  const bool tr = p.trace && blockIdx.x == 0;
+  gtrace(tr && threadIdx.x == 0, 0);  // kernel entry
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.nseg; ++i) tc::tma_prefetch_desc(&p.tmA[i][KC - 1]);
@@ -126,6 +148,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   // everything above overlaps the previous kernel's tail; from here on we read its output
   pdl_wait();
   pdl_launch_dependents();
+  gtrace(tr && threadIdx.x == 0, 1);  // prologue done (barriers, TMEM)
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -156,6 +179,8 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           tc::tma_load_5d(sa, &p.tmA[s][kc - 1], full, 0, sg.dw[t], y0 * sg.stride + sg.dh[t], img0, sg.coff[t] / BK + cb);
           tc::tma_load_3d(sa + B_OFF, &p.tmB[kc - 1], full, 0, n0, sg.kchunk0 + t * sg.ncblk + cb);
+          if (it == 0) gtrace(tr, 2);            // first loads issued
+          if (i == nst - 1) gtrace(tr, 3);       // last loads of the (last) item issued
           cb += kc;
           if (cb == sg.ncblk) {
             cb = 0;
@@ -192,6 +217,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
           const int stage = it % STAGES;
           tc::mbar_wait(tc::smem_u32(&bar_full[stage]), (it / STAGES) & 1);
           tc::tc_fence_after();
+          if (it == 0) gtrace(tr, 4);            // first tile landed
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           for (int c = 0; c < kc; ++c) {
             const uint64_t adesc = tc::umma_desc_k_sw128(sa + c * A_BYTES);
@@ -211,6 +237,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
           }
         }
         tc::umma_commit(tc::smem_u32(&bar_acc_full[ab]));
+        gtrace(tr, 5);                           // all MMAs of the item issued
       }
     }
     __syncwarp();
@@ -227,46 +254,87 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     const int m = m0 + row;
     const bool ok = m < p.M;
     const int img = m / p.hw;
+    // ---- while the main loop of this item runs: stage everything the epilogue needs that is not the accumulator
+    const int img0 = m0 / p.hw;
+    const int imgs_in_tile = (BM + p.hw - 1) / p.hw;
+    const bool use_table = (p.opt & 1) && (!p.partial || p.counters) && (p.bias || p.rowvec) && imgs_in_tile <= CV_IMGS;
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // previous item's readers of s_colvec are done
+    if (use_table) {
+      const int et = threadIdx.x - 64;
+      for (int i = et; i < imgs_in_tile * BN; i += 128) {
+        const int b = i / BN, c = i - b * BN;
+        float v = p.bias ? p.bias[n0 + c] : 0.f;
+        if (p.rowvec && (int64_t)(img0 + b) * p.hw < p.M) v += p.rowvec[(int64_t)(img0 + b) * p.rowvec_ld + n0 + c];
+        s_colvec[b][c] = v;
+      }
+    }
+    // residual (bf16 row of this thread): chunk c+1 is fetched while chunk c is converted and stored
+    const bool use_res = ok && !p.partial && p.mode == 0 && p.residual;
+    const uint4* res_row = use_res ? reinterpret_cast<const uint4*>(p.residual + (int64_t)m * p.res_ld + n0) : nullptr;
+    uint4 res_next[4];
+    if (use_res) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) res_next[j] = res_row[j];
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const float* cvrow = s_colvec[img - img0];
     tc::mbar_wait(tc::smem_u32(&bar_acc_full[ab]), (wi >> 1) & 1);
     tc::tc_fence_after();
-#pragma unroll 1
+    gtrace(tr && threadIdx.x == 64, 6);          // accumulator ready
+#pragma unroll 1  // rolled: the unrolled epilogue (x8 chunks x 3 modes) cost 0.5 ms per forward in code size / registers
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
+      uint4 res_cur[4];
+      if (use_res) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) res_cur[j] = res_next[j];
+        if (c0 + 32 < BN) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) res_next[j] = res_row[(c0 + 32) / 8 + j];
+        }
+      }
       __syncwarp();
       tc::tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + c0, r);
       tc::tmem_ld_wait();
       if (ok && p.partial) {  // split-K: raw fp32 partial, reduced (+ epilogue) by splitk_reduce_kernel
-        float4* pp = reinterpret_cast<float4*>(p.partial + ((int64_t)z * p.M + m) * p.N + n0 + c0);
+        float* pp = p.partial + ((int64_t)z * p.M + m) * p.N + n0 + c0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          pp[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                              __uint_as_float(r[4 * j + 3]));
+        for (int j = 0; j < 4; ++j)
+          st_global_v8(pp + 8 * j, r[8 * j], r[8 * j + 1], r[8 * j + 2], r[8 * j + 3], r[8 * j + 4], r[8 * j + 5], r[8 * j + 6],
+                       r[8 * j + 7]);
       } else if (ok) {
       const int n = n0 + c0;
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      if (p.bias) {
+      if (use_table) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 b = *reinterpret_cast<const float4*>(p.bias + n + j);
+          const float4 b = *reinterpret_cast<const float4*>(cvrow + c0 + j);  // smem, same address across the warp's rows of one image
           v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
         }
-      }
-      if (p.rowvec) {
-        const float* rv = p.rowvec + (int64_t)img * p.rowvec_ld + n;
+      } else {
+        if (p.bias) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b = *reinterpret_cast<const float4*>(rv + j);
-          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(p.bias + n + j);
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (p.rowvec) {
+          const float* rv = p.rowvec + (int64_t)img * p.rowvec_ld + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(rv + j);
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
         }
       }
       if (p.mode == 0) {
         if (p.residual) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (int64_t)m * p.res_ld + n);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint4 u = rp[j];
+            const uint4 u = res_cur[j];
             const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -276,19 +344,21 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
             }
           }
         }
-        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (int64_t)m * p.ldo + n);
+        bf16* op = reinterpret_cast<bf16*>(p.out) + (int64_t)m * p.ldo + n;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          op[j] = make_uint4(pack_bf16(v[j * 8], v[j * 8 + 1]), pack_bf16(v[j * 8 + 2], v[j * 8 + 3]),
-                             pack_bf16(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16(v[j * 8 + 6], v[j * 8 + 7]));
+        for (int j = 0; j < 2; ++j)
+          st_global_v8(op + 16 * j, pack_bf16(v[j * 16], v[j * 16 + 1]), pack_bf16(v[j * 16 + 2], v[j * 16 + 3]),
+                       pack_bf16(v[j * 16 + 4], v[j * 16 + 5]), pack_bf16(v[j * 16 + 6], v[j * 16 + 7]),
+                       pack_bf16(v[j * 16 + 8], v[j * 16 + 9]), pack_bf16(v[j * 16 + 10], v[j * 16 + 11]),
+                       pack_bf16(v[j * 16 + 12], v[j * 16 + 13]), pack_bf16(v[j * 16 + 14], v[j * 16 + 15]));
       } else if (p.mode == 1) {
         // columns [0,16) = values, [16,32) = gates of the same 16 hidden channels
         float g[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) g[j] = v[j] * gelu_exact(v[16 + j]);
-        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (int64_t)m * p.ldo + n / 2);
-        op[0] = make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]), pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7]));
-        op[1] = make_uint4(pack_bf16(g[8], g[9]), pack_bf16(g[10], g[11]), pack_bf16(g[12], g[13]), pack_bf16(g[14], g[15]));
+        st_global_v8(reinterpret_cast<bf16*>(p.out) + (int64_t)m * p.ldo + n / 2, pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]),
+                     pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7]), pack_bf16(g[8], g[9]), pack_bf16(g[10], g[11]),
+                     pack_bf16(g[12], g[13]), pack_bf16(g[14], g[15]));
       } else {
         const int pix = m - img * p.hw;
         float* op = reinterpret_cast<float*>(p.out) + (int64_t)img * p.n_valid * p.hw + pix;
@@ -300,6 +370,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     }
     tc::tc_fence_before();
     tc::mbar_arrive(tc::smem_u32(&bar_acc_empty[ab]));  // this thread is done reading the accumulator buffer
+    gtrace(tr && threadIdx.x == 64, 7);          // epilogue stores issued
     if (p.counters) {
       // ---- split-K reduction fused into the GEMM: all splits of a tile are co-resident (one work item per CTA),
       // so they can meet at a global counter; each then reduces 1/splits of the tile's rows in fixed z order
@@ -317,40 +388,84 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       __threadfence();
+      gtrace(tr && threadIdx.x == 64, 9);   // all splits of this tile have arrived
       const int rows_per = (BM + p.splits - 1) / p.splits;
       const int r0 = z * rows_per, r1 = min(BM, r0 + rows_per);
       constexpr int NV = BN / 8;
-      for (int i = et; i < (r1 - r0) * NV; i += 128) {
-        const int mm = m0 + r0 + i / NV, n = n0 + (i % NV) * 8;
-        if (mm >= p.M) continue;
-        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int zz = 0; zz < p.splits; ++zz) {
-          const float4* pp = reinterpret_cast<const float4*>(p.partial + ((int64_t)zz * p.M + mm) * p.N + n);
-          const float4 a = __ldcg(pp), b = __ldcg(pp + 1);
-          v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
-        }
-        if (p.bias) {
+      const int items = (r1 - r0) * NV;
+      const int64_t zstride = (int64_t)p.M * p.N;
+      for (int i0 = et; i0 < items; i0 += 128 * 4) {
+        // 4 independent items per thread.  Dead slots (past the end / past M) alias the thread's first item so that
+        // every load below is unconditional and the 4 x 2 x splits requests are all in flight together; only the
+        // final store is predicated.
+        int mmv[4], nnv[4];
+        bool live[4];
+        float v[4][8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] += p.bias[n + j];
-        }
-        if (p.rowvec) {
-          const float* rv = p.rowvec + (int64_t)(mm / p.hw) * p.rowvec_ld + n;
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * 128;
+          const int mm = m0 + r0 + i / NV;
+          live[u] = i < items && mm < p.M;
+          const int ii = live[u] ? i : i0;
+          mmv[u] = min(m0 + r0 + ii / NV, p.M - 1);
+          nnv[u] = (ii % NV) * 8;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] += rv[j];
+          for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
         }
-        if (p.residual) {
-          const uint4 u = *reinterpret_cast<const uint4*>(p.residual + (int64_t)mm * p.res_ld + n);
-          const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
+        uint4 rres[4];
+        float4 cv0[4], cv1[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          rres[u] = p.residual ? *reinterpret_cast<const uint4*>(p.residual + (int64_t)mmv[u] * p.res_ld + n0 + nnv[u])
+                               : make_uint4(0u, 0u, 0u, 0u);
+          if (use_table) {
+            const float* cr = s_colvec[mmv[u] / p.hw - img0] + nnv[u];
+            cv0[u] = *reinterpret_cast<const float4*>(cr);
+            cv1[u] = *reinterpret_cast<const float4*>(cr + 4);
+          } else {
+            float t8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              t8[j] = p.bias ? p.bias[n0 + nnv[u] + j] : 0.f;
+              if (p.rowvec) t8[j] += p.rowvec[(int64_t)(mmv[u] / p.hw) * p.rowvec_ld + n0 + nnv[u] + j];
+            }
+            cv0[u] = make_float4(t8[0], t8[1], t8[2], t8[3]);
+            cv1[u] = make_float4(t8[4], t8[5], t8[6], t8[7]);
+          }
+        }
+#pragma unroll 4
+        for (int zz = 0; zz < p.splits; ++zz) {  // fixed z order: bit-stable
+          float4 a[4], b4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4* pp = reinterpret_cast<const float4*>(p.partial + zz * zstride + (int64_t)mmv[u] * p.N + n0 + nnv[u]);
+            a[u] = __ldcg(pp);
+            b4[u] = __ldcg(pp + 1);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            v[u][0] += a[u].x; v[u][1] += a[u].y; v[u][2] += a[u].z; v[u][3] += a[u].w;
+            v[u][4] += b4[u].x; v[u][5] += b4[u].y; v[u][6] += b4[u].z; v[u][7] += b4[u].w;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v[u][0] += cv0[u].x; v[u][1] += cv0[u].y; v[u][2] += cv0[u].z; v[u][3] += cv0[u].w;
+          v[u][4] += cv1[u].x; v[u][5] += cv1[u].y; v[u][6] += cv1[u].z; v[u][7] += cv1[u].w;
+          const uint32_t wds[4] = {rres[u].x, rres[u].y, rres[u].z, rres[u].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wds[e]));
-            v[2 * e] += f.x;
-            v[2 * e + 1] += f.y;
+            v[u][2 * e] += f.x;
+            v[u][2 * e + 1] += f.y;
           }
+          if (live[u])
+            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (int64_t)mmv[u] * p.ldo + n0 + nnv[u]) =
+                make_uint4(pack_bf16(v[u][0], v[u][1]), pack_bf16(v[u][2], v[u][3]), pack_bf16(v[u][4], v[u][5]),
+                           pack_bf16(v[u][6], v[u][7]));
         }
-        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (int64_t)mm * p.ldo + n) =
-            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
       }
+      gtrace(tr && threadIdx.x == 64, 10);  // this CTA's slice reduced and stored
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (et == 0) {  // the last split to finish re-arms the counters for the next launch
         if (atomicAdd(&p.counters[p.mt * p.nt + tile], 1) == p.splits - 1) {
@@ -366,6 +481,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     tc::tc_fence_after();
     tc::tmem_dealloc<2 * ACC_COLS>(tmem_base);
   }
+  gtrace(tr && threadIdx.x == 0, 8);  // exit
 }
 
 // split-K second pass: out[m, n] = sum_z partial[z][m][n] (fixed order: bit-stable) + bias + rowvec + residual -> bf16
@@ -484,6 +600,8 @@ TileChoice pick_tiles(const mvldm_gemm_desc& d) {
 
 constexpr size_t kCounterBytes = 2 * 4096 * sizeof(int);  // arrive/done counters live at the head of the workspace
 
+void gemm_trace_read(long long* host, int n) { MV_CUDA(cudaMemcpyFromSymbol(host, g_gemm_trace, sizeof(long long) * n)); }
+
 size_t gemm_tc_workspace_bytes(const mvldm_gemm_desc& d) {
   if (count_steps(d) == 0) return 0;
   const int splits = pick_tiles(d).splits;
@@ -562,6 +680,14 @@ void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t w
   const int work = ceil_div(p.M, BM) * (d.n / BN) * splits;
   const bool fused = splits > 1 && work <= 148 && ceil_div(p.M, BM) * (d.n / BN) <= 4096;
   p.counters = fused ? reinterpret_cast<int*>(workspace) : nullptr;
+  p.trace = getenv("MVLDM_GEMM_TRACE") != nullptr;
+  {
+    static const int opt = [] {
+      const char* e = getenv("MVLDM_GEMM_OPT");
+      return e ? atoi(e) : 7;
+    }();
+    p.opt = opt;
+  }
   p.bias = d.bias;
   p.rowvec = d.rowvec;
   p.rowvec_ld = d.rowvec_ld;
