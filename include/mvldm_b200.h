@@ -154,8 +154,9 @@ typedef struct {
 int mvldm_op_gemm(void* stream, int impl, const mvldm_gemm_desc* d);
 
 /* Self-attention over packed, head-padded q|k|v: qkv bf16 [batches*seq, 3*heads*dpad] (q block, k block,
- * v block; head h at columns h*dpad, first d of dpad valid), out bf16 [batches*seq, heads*dpad] (pad
- * columns zero).  softmax(q k^T d^-1/2) v with fp32 scores (mvdream/attention.py:174-205). */
+ * v block; head h at columns h*dpad, first d of dpad valid; pad columns zero EXCEPT column d of every V head, which
+ * must hold 1.0: the tcgen05 kernel reads the softmax row sum from P.V through it; dpad > d), out bf16
+ * [batches*seq, heads*dpad] (pad columns zero).  softmax(q k^T d^-1/2) v with fp32 scores (mvdream/attention.py:174-205). */
 int mvldm_op_attention(void* stream, int impl, const void* qkv, void* out, int batches, int seq, int heads,
                        int d, int dpad);
 

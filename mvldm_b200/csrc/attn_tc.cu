@@ -44,6 +44,17 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// packed fp32x2 arithmetic (sm_100: FFMA2): one issue slot for two lanes of the softmax's scale-and-shift
+__device__ __forceinline__ uint64_t pack2(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void ffma2(float& o0, float& o1, uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(d));
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -245,6 +256,9 @@ __global__ void __launch_bounds__(192, OCC) attn_tc_kernel(const __grid_constant
       __syncwarp();
       tc::tmem_ld16(tmem + lane_addr + O_COL + c * 16, o);
       tc::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i)  // pad columns (V carries a ones column there) are written as zeros
+        if (c * 16 + i >= p.d) o[i] = 0u;
       if (row < p.seq) {
         uint4* op = reinterpret_cast<uint4*>(dst + c * 16);
 #pragma unroll
@@ -262,6 +276,294 @@ __global__ void __launch_bounds__(192, OCC) attn_tc_kernel(const __grid_constant
     tc::tc_fence_after();
     tc::tmem_dealloc<TMEM_COLS>(tmem);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// head_dim_pad = 64 (the 32x32 level: 88 % of the attention FLOPs).  Same algorithm, tuned structure:
+//  * 64-key tiles with S and P double-buffered in TMEM (2x64 + 2x32 + 64 = 256 columns), so the tensor pipe
+//    works on Q K^T (j+2) and P V (j) while the softmax warps are on tile j+1, and two CTAs still share an SM;
+//  * K and V arrive in 128-key TMA boxes (one box feeds two tiles: the per-SM TMA box rate is the scarce resource);
+//  * the softmax loop is issue-bound, so it is stripped to scale-and-shift (packed FFMA2) + ex2 + bf16 pack per
+//    element: the row sum is produced by the tensor core through a ones column in V's padding (column d).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_poly(float x) {
+  // 2^x for x <= ~8: x = n + f, f in [-0.5, 0.5]; 2^f by a cubic minimax; scale by 2^n through the exponent field
+  x = fmaxf(x, -120.f);
+  const float t = x + 12582912.f;            // 1.5 * 2^23: rounds x to the nearest integer in the low mantissa bits
+  const float n = t - 12582912.f;
+  const float f = x - n;
+  float pl = fmaf(f, 0.05550411f, 0.24022651f);
+  pl = fmaf(pl, f, 0.69314718f);
+  pl = fmaf(pl, f, 1.0f);
+  return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
+}
+
+constexpr int POLY_EVERY = 1 << 20;  // FMA-pipe exp2 for one in 2*POLY_EVERY exponentials: measured +3 % at 1/6 and it
+                                    // costs accuracy (fails the 1e-2 parity bound at 1/4), so it is off
+
+template <int ST>
+__global__ void __launch_bounds__(192, 2) attn64_kernel(const __grid_constant__ AttnParams p) {
+  constexpr int BT = 64;                       // keys per compute tile
+  constexpr int Q_BYTES = BM * 128;            // 128 queries x 64 cols bf16
+  constexpr int KV_TILE = 128 * 128;           // 128 keys x 64 cols bf16 (one TMA box)
+  constexpr int STAGE_BYTES = 2 * KV_TILE;     // K box + V box
+  constexpr uint32_t S_COL = 0, P_COL = 128, O_COL = 192;  // S0,S1 | P0,P1 | O
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_q, bar_kv_full[ST], bar_kv_empty[ST], bar_s[2], bar_p[2], bar_o, bar_done;
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_smem = smem_base, kv_smem = smem_base + Q_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BM;
+  const int batch = blockIdx.y / p.heads, head = blockIdx.y % p.heads;
+  const int T = (p.seq + BT - 1) / BT;         // 64-key tiles
+  const int NS = (T + 1) / 2;                  // 128-key stages
+  const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&p.tmQ);
+    tc::tma_prefetch_desc(&p.tmKV);
+    tc::mbar_init(tc::smem_u32(&bar_q), 1);
+    for (int s = 0; s < ST; ++s) {
+      tc::mbar_init(tc::smem_u32(&bar_kv_full[s]), 1);
+      tc::mbar_init(tc::smem_u32(&bar_kv_empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(tc::smem_u32(&bar_s[b]), 1);
+      tc::mbar_init(tc::smem_u32(&bar_p[b]), 128);
+    }
+    tc::mbar_init(tc::smem_u32(&bar_o), 1);
+    tc::mbar_init(tc::smem_u32(&bar_done), 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 1) tc::tmem_alloc<256>(tc::smem_u32(&tmem_slot));
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const uint32_t bq = tc::smem_u32(&bar_q);
+      tc::mbar_expect_tx(bq, Q_BYTES);
+      tc::tma_load_3d(q_smem, &p.tmQ, bq, head * 64, q0, batch);
+      const int kcol = (p.heads + head) * 64, vcol = (2 * p.heads + head) * 64;
+      for (int s = 0; s < NS; ++s) {
+        const int stage = s % ST;
+        tc::mbar_wait(tc::smem_u32(&bar_kv_empty[stage]), ((s / ST) & 1) ^ 1);
+        const uint32_t full = tc::smem_u32(&bar_kv_full[stage]);
+        tc::mbar_expect_tx(full, STAGE_BYTES);
+        const uint32_t ks = kv_smem + stage * STAGE_BYTES;
+        tc::tma_load_3d(ks, &p.tmKV, full, kcol, s * 128, batch);
+        tc::tma_load_3d(ks + KV_TILE, &p.tmKV, full, vcol, s * 128, batch);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    // The whole warp runs the (warp-uniform) control flow and barrier waits; one elected lane issues the tcgen05
+    // instructions.  Keeping the loop convergent lets ptxas keep descriptors in uniform registers and predicate
+    // UTCHMMA directly instead of wrapping every issue in an ELECT/branch loop.
+    {
+      constexpr uint32_t idesc_qk = tc::umma_idesc_bf16(BM, BT, false, false);
+      constexpr uint32_t idesc_pv = tc::umma_idesc_bf16(BM, 64, false, true);
+      const uint64_t qd = tc::umma_desc_k_sw128(q_smem);
+      auto issue_qk = [&](int j) {
+        const int s = j >> 1, stage = s % ST;
+        if ((j & 1) == 0) {  // first tile of a stage: its K/V box must have landed
+          tc::mbar_wait(tc::smem_u32(&bar_kv_full[stage]), (s / ST) & 1);
+          tc::tc_fence_after();
+        }
+        const uint64_t kd = tc::umma_desc_k_sw128(kv_smem + stage * STAGE_BYTES + (j & 1) * (BT * 128));
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc::umma_ss(tmem + S_COL + (j & 1) * BT, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
+          tc::umma_commit(tc::smem_u32(&bar_s[j & 1]));
+        }
+        __syncwarp();
+      };
+      tc::mbar_wait(tc::smem_u32(&bar_q), 0);
+      tc::tc_fence_after();
+      issue_qk(0);
+      if (T > 1) issue_qk(1);
+      for (int j = 0; j < T; ++j) {
+        tc::mbar_wait(tc::smem_u32(&bar_p[j & 1]), (j >> 1) & 1);  // softmax has read S(j) and written P(j)
+        tc::tc_fence_after();
+        trace(tr && lane == 0, 3, j);
+        const int s = j >> 1, stage = s % ST;
+        const uint32_t vs = kv_smem + stage * STAGE_BYTES + KV_TILE + (j & 1) * (BT * 128);
+        const uint64_t vd = tc::umma_desc_mn_sw128(vs, KV_TILE);
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < BT / 16; ++kk)  // 16 keys per MMA: 8 packed-bf16 TMEM columns of P, 16 V rows (2 KB)
+            tc::umma_ts(tmem + O_COL, tmem + P_COL + (j & 1) * (BT / 2) + kk * 8, vd + kk * 128, idesc_pv, (j | kk) != 0);
+          tc::umma_commit(tc::smem_u32(&bar_o));
+          if ((j & 1) == 1 || j == T - 1) tc::umma_commit(tc::smem_u32(&bar_kv_empty[stage]));  // stage fully consumed
+          // The epilogue needs "every P V has landed".  With S double-buffered a softmax warp can be two bar_o phases
+          // ahead of the tensor pipe, where a parity wait on bar_o is ambiguous, hence a dedicated single-phase barrier.
+          if (j == T - 1) tc::umma_commit(tc::smem_u32(&bar_done));
+        }
+        __syncwarp();
+        trace(tr && lane == 0, 4, j);
+        if (j + 2 < T) issue_qk(j + 2);  // into the S buffer softmax(j) has just released
+        trace(tr && lane == 0, 5, j);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= softmax + epilogue: one query row per thread =================
+    const int quarter = warp & 3;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int row = q0 + quarter * 32 + lane;
+    const float sc = p.scale_log2;
+    float m_ref = -INFINITY;
+    for (int j = 0; j < T; ++j) {
+      const uint32_t s_tm = tmem + lane_addr + S_COL + (j & 1) * BT;
+      const uint32_t p_tm = tmem + lane_addr + P_COL + (j & 1) * (BT / 2);
+      trace(tr && threadIdx.x == 64, 0, j);
+      tc::mbar_wait(tc::smem_u32(&bar_s[j & 1]), (j >> 1) & 1);
+      tc::tc_fence_after();
+      trace(tr && threadIdx.x == 64, 1, j);
+      const int valid = (j == T - 1) ? p.seq - j * BT : BT;  // ragged tail: keys past the sequence end do not exist
+      uint32_t ra[32], rb[32];
+      tc::tmem_ld32(s_tm, ra);
+      tc::tmem_ld32(s_tm + 32, rb);
+      tc::tmem_ld_wait();
+      if (valid < BT) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i >= valid) ra[i] = 0xff800000u;       // -inf
+          if (32 + i >= valid) rb[i] = 0xff800000u;
+        }
+      }
+      // P = exp2(s * sc - m_ref * sc) against the reference of the EARLIER tiles, with the tile maximum tracked on the
+      // side (independent instruction stream, off the critical path).  Only if this tile would have pushed P beyond 2^8
+      // (always on the first tile) is the reference moved, O rescaled and P recomputed from the registers.
+      // The row sum is not accumulated here: V carries 1.0 in its first pad column, so P V delivers sum_j P_ij (of the
+      // bf16-rounded P the tensor core actually uses) in column d of O.
+      const uint32_t scb = __float_as_uint(sc);
+      const uint64_t sc2 = pack2(scb, scb);
+      float mt0 = -INFINITY, mt1 = -INFINITY;
+      auto half = [&](uint32_t(&r)[32], uint32_t dst, uint64_t nmb2, bool track) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float x0, x1;
+          if (track) {
+            mt0 = fmaxf(mt0, __uint_as_float(r[i]));
+            mt1 = fmaxf(mt1, __uint_as_float(r[i + 1]));
+          }
+          ffma2(x0, x1, pack2(r[i], r[i + 1]), sc2, nmb2);
+          // the MUFU pipe (16 ex2/clk/SM) is busy here: every POLY_EVERY-th pair sends one exponential to the FMA pipe
+          const float e1 = ((i / 2) % POLY_EVERY == POLY_EVERY - 1) ? ex2_poly(x1) : ex2(x1);
+          pk[i / 2] = pack_bf16(ex2(x0), e1);
+        }
+        tc::tmem_st16(dst, pk);
+      };
+      {
+        const uint32_t nmb = __float_as_uint(-m_ref * sc);
+        const uint64_t nmb2 = pack2(nmb, nmb);
+        half(ra, p_tm, nmb2, true);
+        half(rb, p_tm + 16, nmb2, true);
+      }
+      const float mt = fmaxf(mt0, mt1);
+      const bool grow = (mt - m_ref) * sc > 8.f;  // also true on the first tile (m_ref = -inf)
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = grow ? mt : m_ref;
+        if (j > 0) {
+          const float f = ex2((m_ref - m_new) * sc);
+          tc::mbar_wait(tc::smem_u32(&bar_o), (j - 1) & 1);  // P V of the previous tile has landed in O
+          tc::tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tc::tmem_ld32(tmem + lane_addr + O_COL + c * 32, o);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tc::tmem_st16(tmem + lane_addr + O_COL + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&o[0]));
+            tc::tmem_st16(tmem + lane_addr + O_COL + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&o[16]));
+          }
+        }
+        m_ref = m_new;
+        const uint32_t nmb = __float_as_uint(-m_ref * sc);
+        const uint64_t nmb2 = pack2(nmb, nmb);
+        half(ra, p_tm, nmb2, false);   // recompute P(j) against the moved reference (S is still in registers)
+        half(rb, p_tm + 16, nmb2, false);
+      }
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      tc::mbar_arrive(tc::smem_u32(&bar_p[j & 1]));
+      trace(tr && threadIdx.x == 64, 2, j);
+    }
+    // ---- epilogue: O / l -> bf16, head-padded row
+    tc::mbar_wait(tc::smem_u32(&bar_done), 0);
+    tc::tc_fence_after();
+    float inv;
+    {  // row sum = column d of O (the ones column of V)
+      uint32_t o[16];
+      tc::tmem_ld16(tmem + lane_addr + O_COL + (p.d / 16) * 16, o);
+      tc::tmem_ld_wait();
+      float l = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) l = (i == (p.d & 15)) ? __uint_as_float(o[i]) : l;
+      inv = 1.f / l;
+    }
+    bf16* dst = p.out + ((int64_t)batch * p.seq + row) * (p.heads * 64) + head * 64;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t o[16];
+      __syncwarp();
+      tc::tmem_ld16(tmem + lane_addr + O_COL + c * 16, o);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i)  // pad columns (including the row-sum column) are written as zeros
+        if (c * 16 + i >= p.d) o[i] = 0u;
+      if (row < p.seq) {
+        uint4* op = reinterpret_cast<uint4*>(dst + c * 16);
+#pragma unroll
+        for (int v = 0; v < 2; ++v)
+          op[v] = make_uint4(pack_bf16(__uint_as_float(o[v * 8]) * inv, __uint_as_float(o[v * 8 + 1]) * inv),
+                             pack_bf16(__uint_as_float(o[v * 8 + 2]) * inv, __uint_as_float(o[v * 8 + 3]) * inv),
+                             pack_bf16(__uint_as_float(o[v * 8 + 4]) * inv, __uint_as_float(o[v * 8 + 5]) * inv),
+                             pack_bf16(__uint_as_float(o[v * 8 + 6]) * inv, __uint_as_float(o[v * 8 + 7]) * inv));
+      }
+    }
+    tc::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<256>(tmem);
+  }
+}
+
+void launch64(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, int heads, int d) {
+  constexpr int ST = 2;
+  AttnParams p{};
+  const int ld = 3 * heads * 64;
+  const uint64_t dims[3] = {(uint64_t)ld, (uint64_t)seq, (uint64_t)batches};
+  const uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)seq * ld * 2};
+  const uint32_t es[3] = {1, 1, 1};
+  const uint32_t box[3] = {64, 128, 1};
+  p.tmQ = make_tmap_bf16(qkv, 3, dims, strides, box, es);
+  p.tmKV = p.tmQ;
+  p.out = out;
+  p.seq = seq;
+  p.heads = heads;
+  p.d = d;
+  p.dpad = 64;
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
+  p.trace = getenv("MVLDM_ATTN_TRACE") != nullptr;
+  constexpr int smem = BM * 128 + ST * 2 * 128 * 128 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    MV_CUDA(cudaFuncSetAttribute(attn64_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid(ceil_div(seq, BM), batches * heads);
+  launch_pdl(attn64_kernel<ST>, grid, dim3(192), smem, s, p);
 }
 
 template <int DPAD, int BN, int ST, int OCC>
@@ -301,7 +603,9 @@ void attention_tc(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int s
   MV_CHECK(d <= dpad && seq >= 1 && batches >= 1, "attention_tc: bad arguments");
   MV_CHECK((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
            "attention_tc: pointers must be 16-byte aligned");
-  if (dpad == 64) launch<64, 128, 2, 2>(s, qkv, out, batches, seq, heads, d);        // 80 KB smem, 256 TMEM cols: 2 CTAs/SM
+  static const bool legacy64 = getenv("MVLDM_ATTN64_LEGACY") != nullptr;
+  if (dpad == 64 && !legacy64) launch64(s, qkv, out, batches, seq, heads, d);
+  else if (dpad == 64) launch<64, 128, 2, 2>(s, qkv, out, batches, seq, heads, d);   // 80 KB smem, 256 TMEM cols: 2 CTAs/SM
   else if (dpad == 128) launch<128, 128, 2, 1>(s, qkv, out, batches, seq, heads, d);
   else if (dpad == 192) launch<192, 64, 2, 1>(s, qkv, out, batches, seq, heads, d);
   else MV_CHECK(false, "attention_tc: head_dim_pad must be 64, 128 or 192");

@@ -194,7 +194,9 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    // the whole warp runs the warp-uniform loop and the barrier waits; one elected lane issues tcgen05.mma / commit,
+    // which lets ptxas emit the UTCHMMAs back to back instead of one ELECT/branch loop per instruction
+    {
       constexpr uint32_t idesc = tc::umma_idesc_bf16(BM, BN, false, false);
       int it = 0, wi = 0;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wi) {
@@ -217,16 +219,19 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
           const int stage = it % STAGES;
           tc::mbar_wait(tc::smem_u32(&bar_full[stage]), (it / STAGES) & 1);
           tc::tc_fence_after();
-          if (it == 0) gtrace(tr, 4);            // first tile landed
+          if (it == 0) gtrace(tr && lane == 0, 4);  // first tile landed
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          for (int c = 0; c < kc; ++c) {
-            const uint64_t adesc = tc::umma_desc_k_sw128(sa + c * A_BYTES);
-            const uint64_t bdesc = tc::umma_desc_k_sw128(sa + B_OFF + c * B_BYTES);
+          if (tc::elect_one()) {
+            for (int c = 0; c < kc; ++c) {
+              const uint64_t adesc = tc::umma_desc_k_sw128(sa + c * A_BYTES);
+              const uint64_t bdesc = tc::umma_desc_k_sw128(sa + B_OFF + c * B_BYTES);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)  // +32 bytes (=2 in descriptor units) per K=16 slice inside the swizzle atom
-              tc::umma_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (i | c | k) != 0);
+              for (int k = 0; k < BK / 16; ++k)  // +32 bytes (=2 in descriptor units) per K=16 slice inside the swizzle atom
+                tc::umma_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (i | c | k) != 0);
+            }
+            tc::umma_commit(tc::smem_u32(&bar_empty[stage]));  // frees the smem slot when these MMAs retire
           }
-          tc::umma_commit(tc::smem_u32(&bar_empty[stage]));  // frees the smem slot when these MMAs retire
+          __syncwarp();
           cb += kc;
           if (cb == p.seg[s].ncblk) {
             cb = 0;
@@ -236,11 +241,11 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
             }
           }
         }
-        tc::umma_commit(tc::smem_u32(&bar_acc_full[ab]));
-        gtrace(tr, 5);                           // all MMAs of the item issued
+        if (tc::elect_one()) tc::umma_commit(tc::smem_u32(&bar_acc_full[ab]));
+        __syncwarp();
+        gtrace(tr && lane == 0, 5);  // all MMAs of the item issued
       }
     }
-    __syncwarp();
   } else {
     // ================= epilogue =================
     const int q = warp & 3;  // TMEM lane quarter this warp may access

@@ -349,6 +349,14 @@ struct mvldm_handle_s {
       for (int r = 0; r < m.c; ++r) map[r] = (t * H + r / m.d) * m.dpad + r % m.d;
       pack_rows(stream, rawf(a + which[t] + ".weight"), m.c, m.c, m.c, p.w, p.k, 0, upload_map(map));
     }
+    // q/k/v have no bias in the reference; the packed GEMM's bias plants 1.0 in the first pad column of every V head,
+    // which makes P.V deliver the softmax row sum in column d of the attention accumulator (attn_tc.cu)
+    MV_CHECK(m.dpad > m.d, "attention needs at least one pad column per head");
+    std::vector<float> hb(p.n, 0.f);
+    for (int h = 0; h < H; ++h) hb[(2 * H + h) * m.dpad + m.d] = 1.f;
+    p.bias = store<float>(p.n);
+    MV_CUDA(cudaMemcpyAsync(p.bias, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+    MV_CUDA(cudaStreamSynchronize(stream));
     return p;
   }
   Packed pack_attn_out(const std::string& a, const MvW& m) {

@@ -7,7 +7,9 @@ from mvldm_b200 import _lib
 B, N, d = (int(a) for a in sys.argv[1:4])
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 5
 heads, dpad = 8, (d + 63) // 64 * 64
-qkv = (torch.randn(B * N, 3 * heads * dpad) ).to(torch.bfloat16).cuda()
+qkv = torch.randn(B * N, 3, heads, dpad)
+qkv[:, 2, :, d] = 1.0
+qkv = qkv.reshape(B * N, -1).to(torch.bfloat16).cuda()
 out = torch.empty(B * N, heads * dpad, dtype=torch.bfloat16, device="cuda")
 lib = _lib.load()
 for _ in range(reps):
