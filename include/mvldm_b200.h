@@ -76,6 +76,18 @@ int64_t mvldm_workspace_bytes(mvldm_handle h, int B, int V, int H, int W);
  * [B,V,out_channels,H,W]. */
 int mvldm_forward(mvldm_handle h, void* stream, const float* latents, const int64_t* timesteps, int B, int V,
                   int H, int W, float* out);
+/* View-group sharding: a scene whose views are split over several GPUs.  This rank holds V_local
+ * contiguous views of ONE scene (B = 1) out of V_total; every op is per view except the joint multi-view
+ * attention, which needs all views' K and V.  At each of the 9 multi-view blocks the library packs the local K|V
+ * (bf16 [V_local*h*w, 2*heads*dpad]) into `kv_send`, calls `exchange`, and expects `kv_recv` to then hold the
+ * ranks' slabs in view order (bf16 [V_total*h*w, 2*heads*dpad]); the host implements `exchange` with an NCCL
+ * all-gather (ring over NVLink) enqueued on `stream`.  Not graph-captured (the callback re-enters the host).
+ * kv_send must hold V_local*h*w*2*heads*64*2 bytes at the finest level, kv_recv V_total/V_local times that. */
+typedef int (*mvldm_kv_exchange_fn)(void* user, const void* kv_send, void* kv_recv, int64_t bytes_per_rank, void* stream);
+int mvldm_forward_sharded(mvldm_handle h, void* stream, const float* latents, const int64_t* timesteps, int V_local,
+                          int V_total, int H, int W, float* out, void* kv_send, void* kv_recv, int64_t kv_recv_bytes,
+                          mvldm_kv_exchange_fn exchange, void* user);
+
 /* Number of kernels the last mvldm_forward on this handle launched (graph replays count their nodes). */
 int mvldm_last_launch_count(mvldm_handle h);
 
@@ -159,6 +171,11 @@ int mvldm_op_gemm(void* stream, int impl, const mvldm_gemm_desc* d);
  * [batches*seq, heads*dpad] (pad columns zero).  softmax(q k^T d^-1/2) v with fp32 scores (mvdream/attention.py:174-205). */
 int mvldm_op_attention(void* stream, int impl, const void* qkv, void* out, int batches, int seq, int heads,
                        int d, int dpad);
+/* Same (tcgen05 path only) with queries and keys/values in different buffers and of different lengths:
+ * q bf16 [batches*seq_q, ld_q] (head h at column q_col0 + h*dpad), kv bf16 [batches*seq_kv, ld_kv] (K heads at
+ * k_col0 + h*dpad, V heads at v_col0 + h*dpad, ones column as above). */
+int mvldm_op_attention_kv(void* stream, const void* q, int ld_q, int q_col0, const void* kv, int ld_kv, int k_col0,
+                          int v_col0, void* out, int batches, int seq_q, int seq_kv, int heads, int d, int dpad);
 
 /* Debug: clock64() stamps of CTA (0,0) of the last attention launch made with MVLDM_ATTN_TRACE set in the
  * environment; out[slot*512 + tile], slots 0-2 softmax thread (wait S, got S, P handed over), 3-5 MMA thread

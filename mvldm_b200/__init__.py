@@ -9,11 +9,11 @@ from .denoiser import (DENOISER, Denoiser, DenoiserCfg, MultiViewUNet, MultiView
                        UNet2DModelCfg, default_cfg, get_denoiser)
 from .sampler import DenoisingPath, build_inputs, ray_encode
 from .scheduler import (SCHEDULER, DDIMScheduler, DDIMSchedulerCfg, SchedulerCfg, fused_cfg_ddim_step, get_scheduler)
-from .sharding import gather_scenes, scene_slice
+from .sharding import ViewGroupExchange, gather_scenes, scene_slice, view_slice
 
 __all__ = [
     "DENOISER", "Denoiser", "DenoiserCfg", "MultiViewUNet", "MultiViewUNetCfg", "SpatialTransformer3DCfg",
     "UNet2DModelCfg", "default_cfg", "get_denoiser", "DenoisingPath", "build_inputs", "ray_encode", "SCHEDULER",
     "DDIMScheduler", "DDIMSchedulerCfg", "SchedulerCfg", "fused_cfg_ddim_step", "get_scheduler", "gather_scenes",
-    "scene_slice",
+    "scene_slice", "view_slice", "ViewGroupExchange",
 ]

@@ -75,6 +75,12 @@ SYMBOLS = {
     "mvldm_op_layernorm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
 }
 
+KV_EXCHANGE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p)
+SYMBOLS["mvldm_forward_sharded"] = (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                            c_void_p, c_void_p, c_int64, KV_EXCHANGE_FN, c_void_p])
+SYMBOLS["mvldm_op_attention_kv"] = (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
+                                            c_int, c_int, c_int, c_int, c_int])
+
 _lib = None
 
 

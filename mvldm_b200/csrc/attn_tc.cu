@@ -34,7 +34,10 @@ struct AttnParams {
   CUtensorMap tmQ;   // box [64, 128, 1] over (cols, seq, batch)
   CUtensorMap tmKV;  // box [64, BN, 1]
   bf16* out;
-  int seq, heads, d, dpad;
+  int seq;             // queries per batch (rows of the Q source and of the output)
+  int seq_kv;          // keys per batch (rows of the K/V source); == seq for plain self-attention
+  int q_col0, k_col0, v_col0;  // first column of head 0 inside the Q source / the K/V source
+  int heads, d, dpad;
   float scale_log2;  // d^-1/2 * log2(e)
   int trace;
 };
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(192, OCC) attn_tc_kernel(const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BM;
   const int batch = blockIdx.y / p.heads, head = blockIdx.y % p.heads;
-  const int T = (p.seq + BN - 1) / BN;
+  const int T = (p.seq_kv + BN - 1) / BN;
   const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0;
 
   if (warp == 0 && lane == 0) {
@@ -112,8 +115,8 @@ __global__ void __launch_bounds__(192, OCC) attn_tc_kernel(const __grid_constant
     if (lane == 0) {
       const uint32_t bq = tc::smem_u32(&bar_q);
       tc::mbar_expect_tx(bq, Q_BYTES);
-      for (int c = 0; c < NC; ++c) tc::tma_load_3d(q_smem + c * BM * 128, &p.tmQ, bq, head * DPAD + c * 64, q0, batch);
-      const int kcol = (p.heads + head) * DPAD, vcol = (2 * p.heads + head) * DPAD;
+      for (int c = 0; c < NC; ++c) tc::tma_load_3d(q_smem + c * BM * 128, &p.tmQ, bq, p.q_col0 + head * DPAD + c * 64, q0, batch);
+      const int kcol = p.k_col0 + head * DPAD, vcol = p.v_col0 + head * DPAD;
       for (int j = 0; j < T; ++j) {
         const int stage = j % ST;
         tc::mbar_wait(tc::smem_u32(&bar_kv_empty[stage]), ((j / ST) & 1) ^ 1);
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(192, OCC) attn_tc_kernel(const __grid_constant
       tc::mbar_wait(tc::smem_u32(&bar_s), j & 1);
       tc::tc_fence_after();
       trace(tr && threadIdx.x == 64, 1, j);
-      const int valid = (j == T - 1) ? p.seq - j * BN : BN;  // ragged tail: keys past the sequence end do not exist
+      const int valid = (j == T - 1) ? p.seq_kv - j * BN : BN;  // ragged tail: keys past the sequence end do not exist
       // P is computed against the running reference m_ref from earlier tiles, so no separate max pass sits in front
       // of the exponentials.  If this tile raises the row maximum by more than 2^8 (always on the first tile) the
       // reference is moved, O and l are rescaled, and the tile is redone - rare after the first few tiles.
@@ -317,7 +320,7 @@ __global__ void __launch_bounds__(192, 2) attn64_kernel(const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BM;
   const int batch = blockIdx.y / p.heads, head = blockIdx.y % p.heads;
-  const int T = (p.seq + BT - 1) / BT;         // 64-key tiles
+  const int T = (p.seq_kv + BT - 1) / BT;      // 64-key tiles
   const int NS = (T + 1) / 2;                  // 128-key stages
   const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0;
 
@@ -348,8 +351,8 @@ __global__ void __launch_bounds__(192, 2) attn64_kernel(const __grid_constant__ 
     if (lane == 0) {
       const uint32_t bq = tc::smem_u32(&bar_q);
       tc::mbar_expect_tx(bq, Q_BYTES);
-      tc::tma_load_3d(q_smem, &p.tmQ, bq, head * 64, q0, batch);
-      const int kcol = (p.heads + head) * 64, vcol = (2 * p.heads + head) * 64;
+      tc::tma_load_3d(q_smem, &p.tmQ, bq, p.q_col0 + head * 64, q0, batch);
+      const int kcol = p.k_col0 + head * 64, vcol = p.v_col0 + head * 64;
       for (int s = 0; s < NS; ++s) {
         const int stage = s % ST;
         tc::mbar_wait(tc::smem_u32(&bar_kv_empty[stage]), ((s / ST) & 1) ^ 1);
@@ -425,7 +428,7 @@ __global__ void __launch_bounds__(192, 2) attn64_kernel(const __grid_constant__ 
       tc::mbar_wait(tc::smem_u32(&bar_s[j & 1]), (j >> 1) & 1);
       tc::tc_fence_after();
       trace(tr && threadIdx.x == 64, 1, j);
-      const int valid = (j == T - 1) ? p.seq - j * BT : BT;  // ragged tail: keys past the sequence end do not exist
+      const int valid = (j == T - 1) ? p.seq_kv - j * BT : BT;  // ragged tail: keys past the sequence end do not exist
       uint32_t ra[32], rb[32];
       tc::tmem_ld32(s_tm, ra);
       tc::tmem_ld32(s_tm + 32, rb);
@@ -539,58 +542,80 @@ __global__ void __launch_bounds__(192, 2) attn64_kernel(const __grid_constant__ 
   }
 }
 
-void launch64(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, int heads, int d) {
-  constexpr int ST = 2;
-  AttnParams p{};
-  const int ld = 3 * heads * 64;
-  const uint64_t dims[3] = {(uint64_t)ld, (uint64_t)seq, (uint64_t)batches};
-  const uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)seq * ld * 2};
+struct AttnSrc {  // where the operands live: Q rows [batches*seq_q, ld_q], K/V rows [batches*seq_kv, ld_kv]
+  const bf16* q;
+  int ld_q, q_col0;
+  const bf16* kv;
+  int ld_kv, k_col0, v_col0;
+  int seq_q, seq_kv;
+};
+
+void fill_params(AttnParams& p, const AttnSrc& a, bf16* out, int batches, int heads, int d, int dpad, int bn_rows) {
   const uint32_t es[3] = {1, 1, 1};
-  const uint32_t box[3] = {64, 128, 1};
-  p.tmQ = make_tmap_bf16(qkv, 3, dims, strides, box, es);
-  p.tmKV = p.tmQ;
+  {
+    const uint64_t dims[3] = {(uint64_t)a.ld_q, (uint64_t)a.seq_q, (uint64_t)batches};
+    const uint64_t strides[2] = {(uint64_t)a.ld_q * 2, (uint64_t)a.seq_q * a.ld_q * 2};
+    const uint32_t box[3] = {64, BM, 1};
+    p.tmQ = make_tmap_bf16(a.q, 3, dims, strides, box, es);
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)a.ld_kv, (uint64_t)a.seq_kv, (uint64_t)batches};
+    const uint64_t strides[2] = {(uint64_t)a.ld_kv * 2, (uint64_t)a.seq_kv * a.ld_kv * 2};
+    const uint32_t box[3] = {64, (uint32_t)bn_rows, 1};
+    p.tmKV = make_tmap_bf16(a.kv, 3, dims, strides, box, es);
+  }
   p.out = out;
-  p.seq = seq;
+  p.seq = a.seq_q;
+  p.seq_kv = a.seq_kv;
+  p.q_col0 = a.q_col0;
+  p.k_col0 = a.k_col0;
+  p.v_col0 = a.v_col0;
   p.heads = heads;
   p.d = d;
-  p.dpad = 64;
+  p.dpad = dpad;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
   p.trace = getenv("MVLDM_ATTN_TRACE") != nullptr;
-  constexpr int smem = BM * 128 + ST * 2 * 128 * 128 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    MV_CUDA(cudaFuncSetAttribute(attn64_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
-  dim3 grid(ceil_div(seq, BM), batches * heads);
-  launch_pdl(attn64_kernel<ST>, grid, dim3(192), smem, s, p);
 }
 
 template <int DPAD, int BN, int ST, int OCC>
-void launch(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, int heads, int d) {
+void launch(cudaStream_t s, const AttnSrc& a, bf16* out, int batches, int heads, int d) {
   AttnParams p{};
-  const int ld = 3 * heads * DPAD;
-  const uint64_t dims[3] = {(uint64_t)ld, (uint64_t)seq, (uint64_t)batches};
-  const uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)seq * ld * 2};
-  const uint32_t es[3] = {1, 1, 1};
-  const uint32_t boxq[3] = {64, BM, 1}, boxkv[3] = {64, (uint32_t)BN, 1};
-  p.tmQ = make_tmap_bf16(qkv, 3, dims, strides, boxq, es);
-  p.tmKV = make_tmap_bf16(qkv, 3, dims, strides, boxkv, es);
-  p.out = out;
-  p.seq = seq;
-  p.heads = heads;
-  p.d = d;
-  p.dpad = DPAD;
-  p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
-  p.trace = getenv("MVLDM_ATTN_TRACE") != nullptr;
+  fill_params(p, a, out, batches, heads, d, DPAD, BN);
   constexpr int smem = (DPAD / 64) * BM * 128 + ST * 2 * (DPAD / 64) * BN * 128 + 1024;
   static bool configured = false;
   if (!configured) {
     MV_CUDA(cudaFuncSetAttribute(attn_tc_kernel<DPAD, BN, ST, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid(ceil_div(seq, BM), batches * heads);
+  dim3 grid(ceil_div(a.seq_q, BM), batches * heads);
   launch_pdl(attn_tc_kernel<DPAD, BN, ST, OCC>, grid, dim3(192), smem, s, p);
+}
+
+void launch64(cudaStream_t s, const AttnSrc& a, bf16* out, int batches, int heads, int d) {
+  constexpr int ST = 2;
+  AttnParams p{};
+  fill_params(p, a, out, batches, heads, d, 64, 128);
+  constexpr int smem = BM * 128 + ST * 2 * 128 * 128 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    MV_CUDA(cudaFuncSetAttribute(attn64_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid(ceil_div(a.seq_q, BM), batches * heads);
+  launch_pdl(attn64_kernel<ST>, grid, dim3(192), smem, s, p);
+}
+
+void dispatch(cudaStream_t s, const AttnSrc& a, bf16* out, int batches, int heads, int d, int dpad) {
+  MV_CHECK(d < dpad && a.seq_q >= 1 && a.seq_kv >= 1 && batches >= 1, "attention_tc: bad arguments (need dpad > d)");
+  MV_CHECK((reinterpret_cast<uintptr_t>(a.q) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.kv) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(out) & 15) == 0 && a.ld_q % 8 == 0 && a.ld_kv % 8 == 0,
+           "attention_tc: pointers must be 16-byte aligned, row pitches multiples of 8");
+  static const bool legacy64 = getenv("MVLDM_ATTN64_LEGACY") != nullptr;
+  if (dpad == 64 && !legacy64) launch64(s, a, out, batches, heads, d);
+  else if (dpad == 64) launch<64, 128, 2, 2>(s, a, out, batches, heads, d);   // 80 KB smem, 256 TMEM cols: 2 CTAs/SM
+  else if (dpad == 128) launch<128, 128, 2, 1>(s, a, out, batches, heads, d);
+  else if (dpad == 192) launch<192, 64, 2, 1>(s, a, out, batches, heads, d);
+  else MV_CHECK(false, "attention_tc: head_dim_pad must be 64, 128 or 192");
 }
 
 }  // namespace
@@ -600,15 +625,13 @@ void attention_trace_read(long long* host, int n) {
 }
 
 void attention_tc(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, int heads, int d, int dpad) {
-  MV_CHECK(d <= dpad && seq >= 1 && batches >= 1, "attention_tc: bad arguments");
-  MV_CHECK((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
-           "attention_tc: pointers must be 16-byte aligned");
-  static const bool legacy64 = getenv("MVLDM_ATTN64_LEGACY") != nullptr;
-  if (dpad == 64 && !legacy64) launch64(s, qkv, out, batches, seq, heads, d);
-  else if (dpad == 64) launch<64, 128, 2, 2>(s, qkv, out, batches, seq, heads, d);   // 80 KB smem, 256 TMEM cols: 2 CTAs/SM
-  else if (dpad == 128) launch<128, 128, 2, 1>(s, qkv, out, batches, seq, heads, d);
-  else if (dpad == 192) launch<192, 64, 2, 1>(s, qkv, out, batches, seq, heads, d);
-  else MV_CHECK(false, "attention_tc: head_dim_pad must be 64, 128 or 192");
+  const int ld = 3 * heads * dpad;
+  dispatch(s, AttnSrc{qkv, ld, 0, qkv, ld, heads * dpad, 2 * heads * dpad, seq, seq}, out, batches, heads, d, dpad);
+}
+
+void attention_tc_kv(cudaStream_t s, const bf16* q, int ld_q, int q_col0, const bf16* kv, int ld_kv, int k_col0, int v_col0,
+                     bf16* out, int batches, int seq_q, int seq_kv, int heads, int d, int dpad) {
+  dispatch(s, AttnSrc{q, ld_q, q_col0, kv, ld_kv, k_col0, v_col0, seq_q, seq_kv}, out, batches, heads, d, dpad);
 }
 
 }  // namespace mvldm

@@ -90,6 +90,9 @@ void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t w
 void attention_simt(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, int heads, int d, int dpad);
 void attention_trace_read(long long* host, int n);  // debug timeline of CTA (0,0), see MVLDM_ATTN_TRACE
 void attention_tc(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, int heads, int d, int dpad);
+// queries and keys/values from different buffers / of different lengths (view-group sharding: local Q, gathered K/V)
+void attention_tc_kv(cudaStream_t s, const bf16* q, int ld_q, int q_col0, const bf16* kv, int ld_kv, int k_col0, int v_col0,
+                     bf16* out, int batches, int seq_q, int seq_kv, int heads, int d, int dpad);
 
 // elementwise.cu
 void im2col_input(cudaStream_t s, const float* latents, int n_img, int cin, int h, int w, int kpad, bf16* out);

@@ -176,6 +176,13 @@ struct mvldm_handle_s {
   cudaStream_t capture_stream = nullptr;  // graphs are recorded here: the caller's stream may be the legacy NULL stream
   Arena arena;
   bool dry = true;
+  // view-group sharding (mvldm_forward_sharded): local Q against all-gathered K/V in the joint attention
+  bool sharded = false;
+  int v_total = 0;
+  void *kv_send = nullptr, *kv_recv = nullptr;
+  size_t kv_recv_bytes = 0;
+  mvldm_kv_exchange_fn exchange = nullptr;
+  void* exchange_user = nullptr;
   size_t splitk_need = 0, splitk_bytes = 0;  // split-K fp32 scratch shared by all GEMMs of a forward
   void* splitk_ws = nullptr;
 
@@ -538,6 +545,24 @@ struct mvldm_handle_s {
     else attention_simt(stream, qkv.p, out.p, batches, seq, cfg.num_heads, m.d, m.dpad);
   }
 
+  // This rank's views supply the queries; K and V of every view of the scene are all-gathered by the host callback.
+  void joint_attention_sharded(const Act& qkv, const Act& out, int seq_local, const MvW& m) {
+    const int H = cfg.num_heads, hd = H * m.dpad;
+    const size_t bytes = (size_t)seq_local * 2 * hd * sizeof(bf16);
+    const int world = v_total / (int)(qkv.n);
+    ProfScope ps(this, "attention_joint_sharded", "seq_q" + std::to_string(seq_local) + " seq_kv" + std::to_string(seq_local * world),
+                 4.0 * (double)seq_local * seq_local * world * m.c, 0.0);
+    if (dry) return;
+    MV_CHECK(bytes * world <= kv_recv_bytes, "mvldm_forward_sharded: kv_recv buffer too small");
+    // K|V columns of the packed q|k|v rows -> contiguous slab
+    MV_CUDA(cudaMemcpy2DAsync(kv_send, (size_t)2 * hd * sizeof(bf16), qkv.p + hd, (size_t)3 * hd * sizeof(bf16),
+                              (size_t)2 * hd * sizeof(bf16), seq_local, cudaMemcpyDeviceToDevice, stream));
+    const int rc = exchange(exchange_user, kv_send, kv_recv, (int64_t)bytes, stream);
+    MV_CHECK(rc == 0, "mvldm_forward_sharded: K/V exchange callback failed");
+    attention_tc_kv(stream, qkv.p, 3 * hd, 0, reinterpret_cast<const bf16*>(kv_recv), 2 * hd, 0, hd, out.p, 1, seq_local,
+                    seq_local * world, H, m.d, m.dpad);
+  }
+
   Act resnet(const ResnetW& r, const Act& x0, const Act* x1, const float* temb) {
     const int n = x0.n, h = x0.h, w = x0.w;
     MV_CHECK(x0.c + (x1 ? x1->c : 0) == r.cin, "resnet channel mismatch");
@@ -575,7 +600,8 @@ struct mvldm_handle_s {
     // joint attention over all V*h*w tokens of a scene ("(b f) l c -> b (f l) c")
     ln(t, m.ln_g[0], m.ln_b[0], nrm);
     gemm({seg_1x1(nrm)}, m.qkv1, qkv, nullptr, 0, nullptr, 0, 6.0 * (double)t.tokens() * C * C);
-    attn(qkv, o, B, V * hw, m);
+    if (sharded) joint_attention_sharded(qkv, o, V * hw, m);
+    else attn(qkv, o, B, V * hw, m);
     Act t2 = new_act(n, h, w, C);
     gemm({seg_1x1(o)}, m.out1, t2, nullptr, 0, &t, 0, 2.0 * (double)t.tokens() * C * C);
     tap(m.key + ".attn1", t2);
@@ -771,6 +797,7 @@ struct mvldm_handle_s {
   }
 };
 
+// (forward_sharded is a thin eager wrapper around run(); see mvldm_forward_sharded below)
 // Folds the event pairs of the last profiled forward into a JSON string (synchronises the device).
 static const char* profile_report(mvldm_handle_s* h) {
   MV_CUDA(cudaDeviceSynchronize());
@@ -924,6 +951,43 @@ int mvldm_forward(mvldm_handle h, void* stream, const float* latents, const int6
   MV_API_END
 }
 
+int mvldm_forward_sharded(mvldm_handle h, void* stream, const float* latents, const int64_t* timesteps, int V_local,
+                          int V_total, int H, int W, float* out, void* kv_send, void* kv_recv, int64_t kv_recv_bytes,
+                          mvldm_kv_exchange_fn exchange, void* user) {
+  MV_API_BEGIN
+  MV_CHECK(h && latents && timesteps && out && kv_send && kv_recv && exchange, "null argument");
+  MV_CHECK(h->finalized, "mvldm_forward_sharded before mvldm_finalize_weights");
+  MV_CHECK(h->cfg.impl == MVLDM_IMPL_TC, "view-group sharding needs the tcgen05 kernels");
+  MV_CHECK(V_local > 0 && V_total % V_local == 0, "V_total must be a multiple of V_local (equal view groups)");
+  MV_CUDA(cudaSetDevice(h->device));
+  Plan& p = h->plan_for(1, V_local, H, W);
+  h->stream = (cudaStream_t)stream;
+  h->arena = Arena();
+  h->arena.measuring = false;
+  h->arena.base = reinterpret_cast<char*>(p.arena_mem.p);
+  h->arena.cap = p.arena_bytes;
+  h->splitk_ws = p.splitk.p;
+  h->splitk_bytes = p.splitk.bytes;
+  h->dry = false;
+  h->sharded = true;
+  h->v_total = V_total;
+  h->kv_send = kv_send;
+  h->kv_recv = kv_recv;
+  h->kv_recv_bytes = (size_t)kv_recv_bytes;
+  h->exchange = exchange;
+  h->exchange_user = user;
+  g_launch_count = 0;
+  try {
+    h->run(latents, timesteps, 1, V_local, H, W, out);
+  } catch (...) {
+    h->sharded = false;
+    throw;
+  }
+  h->sharded = false;
+  h->last_launches = g_launch_count;
+  MV_API_END
+}
+
 int mvldm_last_launch_count(mvldm_handle h) { return h ? h->last_launches : -1; }
 
 int mvldm_set_profiling(mvldm_handle h, int enable) {
@@ -1028,6 +1092,15 @@ int mvldm_debug_attn_trace(int64_t* out, int n) {
   MV_CHECK(out && n > 0 && n <= 8 * 512, "bad arguments");
   MV_CUDA(cudaDeviceSynchronize());
   attention_trace_read(reinterpret_cast<long long*>(out), n);
+  MV_API_END
+}
+
+int mvldm_op_attention_kv(void* stream, const void* q, int ld_q, int q_col0, const void* kv, int ld_kv, int k_col0,
+                          int v_col0, void* out, int batches, int seq_q, int seq_kv, int heads, int d, int dpad) {
+  MV_API_BEGIN
+  MV_CHECK(q && kv && out, "null argument");
+  attention_tc_kv((cudaStream_t)stream, (const bf16*)q, ld_q, q_col0, (const bf16*)kv, ld_kv, k_col0, v_col0, (bf16*)out,
+                  batches, seq_q, seq_kv, heads, d, dpad);
   MV_API_END
 }
 

@@ -328,6 +328,28 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
                                          b, v, h, w, out.data_ptr()))
         return out
 
+    @torch.no_grad()
+    def forward_view_sharded(self, latents: Tensor, timestep: Tensor, v_total: int, exchange) -> Tensor:
+        """View-group sharded forward: `latents` [1, V_local, C, h, w] are THIS rank's contiguous views of one scene of
+        `v_total` views; `exchange` is a `ViewGroupExchange`.  Returns this rank's [1, V_local, C_out, h, w]."""
+        b, v, c, h, w = latents.shape
+        if b != 1:
+            raise ValueError("view-group sharding handles one scene at a time (batch must be 1)")
+        if not latents.is_cuda:
+            raise RuntimeError("mvldm_b200: inputs must be CUDA tensors (no CPU fallback)")
+        self.refresh_weights(force=False)
+        t = timestep.to(latents.device)
+        t = (t[:, None].expand(b, v) if t.dim() < 2 else t).reshape(-1).contiguous()
+        lat = latents.detach().to(torch.float32).contiguous()
+        out = torch.empty((b, v, self.out_channels, h, w), device=latents.device, dtype=torch.float32)
+        lib = _lib.load()
+        with torch.cuda.device(latents.device):
+            _lib.check(lib.mvldm_forward_sharded(
+                self._h.ptr, _lib.current_stream_ptr(latents.device), lat.data_ptr(), t.data_ptr(), v, v_total, h, w,
+                out.data_ptr(), exchange.send.data_ptr(), exchange.recv.data_ptr(),
+                exchange.recv.numel() * exchange.recv.element_size(), exchange.callback, None))
+        return out
+
     # ---- diagnostics ---------------------------------------------------------------------
     def last_launch_count(self) -> int:
         return _lib.load().mvldm_last_launch_count(self._h.ptr) if self._h.ptr else 0

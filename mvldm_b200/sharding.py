@@ -1,6 +1,11 @@
-"""Scene-batch sharding over the GPUs of one box: scenes never interact, so each rank takes
-a contiguous slice of the scene batch and runs the unmodified single-GPU path; no data-path collective.
-Only the final latents are gathered."""
+"""Multi-GPU partitioning of the denoising path, one process per GPU.
+
+* Scene-batch sharding: scenes never interact, so each rank takes a contiguous slice of the scene batch and runs
+  the unmodified single-GPU path; no data-path collective, only the final latents are gathered.
+* View-group sharding: one scene whose views are split in contiguous groups over the ranks.  Everything is per
+  view except the joint multi-view attention, where every rank needs all views' K and V: `ViewGroupExchange` is the
+  host side of `mvldm_forward_sharded` - an NCCL all-gather (ring over NVLink/NVSwitch) of the packed K|V slab at
+  each of the 9 multi-view blocks, in view order so the softmax sums in the same order on every rank."""
 from __future__ import annotations
 
 from typing import List, Tuple
@@ -30,3 +35,44 @@ def gather_scenes(local: torch.Tensor, num_scenes: int, group=None) -> torch.Ten
     bufs: List[torch.Tensor] = [torch.empty_like(pad) for _ in range(ws)]
     dist.all_gather(bufs, pad, group=group)
     return torch.cat([bufs[r][: b - a] for r, (a, b) in enumerate(sizes)], dim=0)
+
+
+def view_slice(num_views: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """[start, stop) of the views owned by `rank`; view groups must be equal (the K/V all-gather is unpadded)."""
+    if num_views % world_size != 0:
+        raise ValueError("num_views must be a multiple of world_size for view-group sharding")
+    per = num_views // world_size
+    return rank * per, (rank + 1) * per
+
+
+class ViewGroupExchange:
+    """Owns the K|V send / receive buffers and the callback the library invokes at every joint attention."""
+
+    def __init__(self, v_local: int, v_total: int, h: int, w: int, heads: int, device, group=None):
+        from . import _lib
+        self.group = group
+        self.world = v_total // v_local
+        per_rank = v_local * h * w * 2 * heads * 64          # bf16 elements at the finest level (head_dim_pad 64)
+        self.send = torch.empty(per_rank, dtype=torch.bfloat16, device=device)
+        self.recv = torch.empty(per_rank * self.world, dtype=torch.bfloat16, device=device)
+        self.calls = 0
+        self.bytes_sent = 0
+
+        def _cb(user, send_ptr, recv_ptr, nbytes, stream):
+            try:
+                self.all_gather(nbytes // 2)
+                return 0
+            except Exception:                                  # never unwind through the C frame
+                import traceback
+                traceback.print_exc()
+                return 1
+        self.callback = _lib.KV_EXCHANGE_FN(_cb)               # keep a reference: ctypes callbacks are not owned by C
+
+    def all_gather(self, n_elems: int) -> None:
+        """recv[r * n : (r + 1) * n] = rank r's send[:n]  (rank order == view order)"""
+        self.calls += 1
+        self.bytes_sent += n_elems * 2
+        if self.world == 1 or not dist.is_initialized():
+            self.recv[:n_elems].copy_(self.send[:n_elems])
+            return
+        dist.all_gather_into_tensor(self.recv[: n_elems * self.world], self.send[:n_elems], group=self.group)

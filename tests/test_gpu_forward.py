@@ -138,3 +138,71 @@ def test_ddim_trajectory_25_steps(use_cfg, gpu_models, oracle_weights, oracle_cf
     # bit-stable: the same trajectory twice
     x0b = path.sample(ctx, x_T, extr, intr)
     assert torch.equal(x0, x0b)
+
+
+def test_attention_split_q_kv_sources():
+    """the generalised attention entry (local queries against a separately stored, longer K/V): equals the packed
+    self-attention restricted to those queries"""
+    import ctypes
+    from helpers import pack_qkv, stream_ptr
+    from mvldm_b200 import _lib
+    torch.manual_seed(3)
+    heads, d, dpad, N, Nq = 8, 40, 64, 1024, 384
+    q, k, v = (torch.randn(1, N, heads * d) for _ in range(3))
+    qkv = pack_qkv(q, k, v, heads, dpad).cuda()
+    full = torch.empty((N, heads * dpad), dtype=torch.bfloat16, device="cuda")
+    lib = _lib.load()
+    _lib.check(lib.mvldm_op_attention(stream_ptr(), 0, qkv.data_ptr(), full.data_ptr(), 1, N, heads, d, dpad))
+    kv = qkv[:, heads * dpad:].contiguous()                        # [N, 2*heads*dpad]
+    qloc = qkv[256:256 + Nq].contiguous()                          # this "rank's" rows (q in the first third of columns)
+    part = torch.empty((Nq, heads * dpad), dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.mvldm_op_attention_kv(stream_ptr(), qloc.data_ptr(), 3 * heads * dpad, 0, kv.data_ptr(), 2 * heads * dpad,
+                                         0, heads * dpad, part.data_ptr(), 1, Nq, N, heads, d, dpad))
+    assert torch.equal(part, full[256:256 + Nq])
+
+
+def _view_shard_worker(rank, ws, port, sd, inp, ts, ref):
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=ws,
+                            device_id=torch.device("cuda", rank))
+    m = mv.MultiViewUNet(mv.default_cfg(), 11, 4)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    V = inp.shape[1]
+    a, b = mv.view_slice(V, rank, ws)
+    ex = mv.ViewGroupExchange(b - a, V, 32, 32, 8, torch.device("cuda", rank))
+    y = m.forward_view_sharded(inp[:, a:b].cuda(), ts[:, a:b].cuda(), V, ex)
+    torch.cuda.synchronize()
+    err = rel_err(y, ref[:, a:b])
+    assert ex.calls == 9, ex.calls                                  # one K/V exchange per multi-view block
+    assert err < FWD_TOL, err
+    dist.destroy_process_group()
+
+
+def test_view_group_sharded_forward_two_gpus(oracle_weights):
+    """SURVEY.md §8e: one scene's 8 views split over 2 GPUs, K/V all-gathered (NCCL) at every multi-view block;
+    each rank's views must match the single-GPU forward / the reference golden"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import socket
+    import torch.multiprocessing as mp
+    g = np.load(os.path.join(GOLD, "g2_forward_v8.npz"))
+    inp, ts, ref = torch.tensor(g["inputs"]), torch.tensor(g["timesteps"]), torch.tensor(g["eps"])
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_view_shard_worker, args=(2, port, oracle_weights, inp, ts, ref), nprocs=2, join=True)
+
+
+def test_view_group_sharded_forward_single_gpu_world1(gpu_models):
+    """world size 1 exercises the whole sharded code path (pack K|V, callback, split-source attention) on one GPU"""
+    g = np.load(os.path.join(GOLD, "g1_forward_v4.npz"))
+    inp, ts = torch.tensor(g["inputs"]).cuda(), torch.tensor(g["timesteps"]).cuda()
+    m = gpu_models(0)
+    ex = mv.ViewGroupExchange(4, 4, 32, 32, 8, torch.device("cuda", 0))
+    y = m.forward_view_sharded(inp, ts, 4, ex)
+    assert ex.calls == 9
+    assert rel_err(y, torch.tensor(g["eps"])) < FWD_TOL
+    assert rel_err(y, m(inp, ts)) < 1e-2

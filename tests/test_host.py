@@ -115,3 +115,30 @@ def test_gather_scenes_gloo_world2():
     port = s.getsockname()[1]
     s.close()
     mp.spawn(_gather_worker, args=(2, port, 5), nprocs=2, join=True)
+
+
+def _kv_worker(rank, ws, port):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=ws)
+    ex = mv.ViewGroupExchange(v_local=1, v_total=ws, h=2, w=2, heads=8, device="cpu")
+    n = 4 * 2 * 8 * 64
+    assert ex.send.numel() == n and ex.recv.numel() == n * ws
+    ex.send[:] = float(rank + 1)
+    ex.all_gather(100)                                   # a coarser level uses a prefix of the buffers
+    for r in range(ws):
+        assert torch.all(ex.recv[r * 100:(r + 1) * 100] == float(r + 1))     # rank order == view order
+    assert ex.calls == 1 and ex.bytes_sent == 200
+    assert mv.view_slice(8, rank, ws) == (rank * 4, rank * 4 + 4)
+    dist.destroy_process_group()
+
+
+def test_view_group_exchange_gloo_world2():
+    """host side of view-group sharding: the K|V all-gather lands the ranks' slabs in view order"""
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_kv_worker, args=(2, port), nprocs=2, join=True)
+    with pytest.raises(ValueError):
+        mv.view_slice(7, 0, 2)
