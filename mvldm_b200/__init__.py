@@ -7,6 +7,7 @@ Python here is plumbing: the reference-facing interfaces (`Denoiser`, `MultiView
 from . import _lib
 from .denoiser import (DENOISER, Denoiser, DenoiserCfg, MultiViewUNet, MultiViewUNetCfg, SpatialTransformer3DCfg,
                        UNet2DModelCfg, default_cfg, get_denoiser)
+from .anchored import AnchoredPlan, anchored_plan, sample_anchored
 from .sampler import DenoisingPath, build_inputs, ray_encode
 from .scheduler import (SCHEDULER, DDIMScheduler, DDIMSchedulerCfg, SchedulerCfg, fused_cfg_ddim_step, get_scheduler)
 from .sharding import ViewGroupExchange, gather_scenes, scene_slice, view_slice
@@ -15,5 +16,5 @@ __all__ = [
     "DENOISER", "Denoiser", "DenoiserCfg", "MultiViewUNet", "MultiViewUNetCfg", "SpatialTransformer3DCfg",
     "UNet2DModelCfg", "default_cfg", "get_denoiser", "DenoisingPath", "build_inputs", "ray_encode", "SCHEDULER",
     "DDIMScheduler", "DDIMSchedulerCfg", "SchedulerCfg", "fused_cfg_ddim_step", "get_scheduler", "gather_scenes",
-    "scene_slice", "view_slice", "ViewGroupExchange",
+    "scene_slice", "view_slice", "ViewGroupExchange", "AnchoredPlan", "anchored_plan", "sample_anchored",
 ]

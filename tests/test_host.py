@@ -142,3 +142,23 @@ def test_view_group_exchange_gloo_world2():
     mp.spawn(_kv_worker, args=(2, port), nprocs=2, join=True)
     with pytest.raises(ValueError):
         mv.view_slice(7, 0, 2)
+
+
+def test_anchored_plan_matches_reference_index_logic():
+    """BASELINE config 3 / SURVEY.md §3.1 + App. D (index logic of diffusion_wrapper.py:689-885 emulated on frame ids):
+    80 frames -> 3 anchors at 20/40/60, 26 sample() calls, 75 of 77 non-anchor frames generated, 2 dropped;
+    278 frames -> 4 anchors, 92 calls."""
+    p = mv.anchored_plan(list(range(80)), 4)
+    assert p.anchors == [20, 40, 60]
+    assert p.num_sample_calls == 26 and len(p.chunks) == 25
+    covered = sorted(t for _, c in p.chunks for t in c)
+    assert len(covered) == 75 == len(set(covered)) and len(p.dropped) == 2
+    assert not set(covered) & set(p.anchors)
+    assert all(len(c) == 3 for _, c in p.chunks)
+    p = mv.anchored_plan(list(range(278)), 4)
+    assert p.anchors == [69, 138, 207, 276] and p.num_sample_calls == 92
+    # every chunk is conditioned on an anchor of the plan; nearest-anchor assignment for an isolated example
+    p = mv.anchored_plan(list(range(20)), 4)
+    assert p.anchors == [5, 10, 15] and all(a in p.anchors for a, _ in p.chunks)
+    with pytest.raises(ValueError):
+        mv.anchored_plan([0, 1], 4)
