@@ -401,19 +401,26 @@ __global__ void __launch_bounds__(GNB_THREADS) gn_block_kernel(const bf16* __res
                                                                float eps, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, int silu, int cb,
                                                                int cache, bf16* __restrict__ out) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();  // CS CTAs along x share one (image, channel block): pixel split
   extern __shared__ __align__(16) uint8_t gnb_smem[];
   __shared__ float red_s[GNB_THREADS * 8], red_q[GNB_THREADS * 8];
   __shared__ float chan_s[GNB_THREADS], chan_q[GNB_THREADS];
+  __shared__ float my_part[16][2];
   __shared__ float s_mean[16], s_rstd[16];
   pdl_wait();
   pdl_launch_dependents();
   bf16* slab = reinterpret_cast<bf16*>(gnb_smem);
+  const int CS = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
+  const int hw_all = hw;
+  hw = hw_all / CS;                                // pixels this CTA owns
   const int C = c0 + c1, cgn = C / groups, nv = cb / 8, gb = cb / cgn;
-  const int img = blockIdx.y, ch0 = blockIdx.x * cb, t = threadIdx.x;
+  const int img = blockIdx.y, ch0 = (blockIdx.x / CS) * cb, t = threadIdx.x;
   const int lanes_p = min(GNB_THREADS / nv, hw);  // pixel lanes (no more than there are pixels)
   const int cv = t % nv, pl = t / nv;
   const int c = ch0 + cv * 8;
-  const bf16* src = c < c0 ? x0 + (int64_t)img * hw * c0 + c : x1 + (int64_t)img * hw * c1 + (c - c0);
+  const int64_t pix0 = (int64_t)img * hw_all + (int64_t)crank * hw;
+  const bf16* src = c < c0 ? x0 + pix0 * c0 + c : x1 + pix0 * c1 + (c - c0);
   const int64_t pitch = c < c0 ? c0 : c1;
   if (pl < lanes_p) {
     float sa[8], qa[8];
@@ -477,15 +484,26 @@ __global__ void __launch_bounds__(GNB_THREADS) gn_block_kernel(const bf16* __res
       S = warp_sum(S);
       Q = warp_sum(Q);
       if (lane == 0) {
-        const float cnt = (float)hw * (float)cgn;
-        const float mean = S / cnt;
-        const float var = fmaxf(Q / cnt - mean * mean, 0.f);
-        s_mean[warp] = mean;
-        s_rstd[warp] = rsqrtf(var + eps);
+        my_part[warp][0] = S;
+        my_part[warp][1] = Q;
       }
     }
   }
-  __syncthreads();
+  if (CS > 1) cluster.sync(); else __syncthreads();
+  if (t < gb) {  // fold the cluster's partials in rank order (bit-stable) through distributed shared memory
+    float S = 0.f, Q = 0.f;
+    for (int r = 0; r < CS; ++r) {
+      const float* peer = CS > 1 ? cluster.map_shared_rank(&my_part[0][0], r) : &my_part[0][0];
+      S += peer[2 * t];
+      Q += peer[2 * t + 1];
+    }
+    const float cnt = (float)hw_all * (float)cgn;
+    const float mean = S / cnt;
+    const float var = fmaxf(Q / cnt - mean * mean, 0.f);
+    s_mean[t] = mean;
+    s_rstd[t] = rsqrtf(var + eps);
+  }
+  if (CS > 1) cluster.sync(); else __syncthreads();  // also keeps my_part alive until every peer has read it
   if (pl < lanes_p) {
     const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
     const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
@@ -498,7 +516,7 @@ __global__ void __launch_bounds__(GNB_THREADS) gn_block_kernel(const bf16* __res
       sc[j] = s_rstd[g] * gg[j];
       sh[j] = bb[j] - s_mean[g] * sc[j];
     }
-    bf16* dst = out + (int64_t)img * hw * C + c;
+    bf16* dst = out + pix0 * C + c;
 #pragma unroll 4
     for (int pp = pl; pp < hw; pp += lanes_p) {
       float f[8];
@@ -783,8 +801,29 @@ void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, i
         MV_CUDA(cudaFuncSetAttribute(gn_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         configured = true;
       }
-      launch_pdl(gn_block_kernel, dim3(C / cb, n_img), dim3(GNB_THREADS), cache ? slab : 0, s, x0, c0, x1, c1, hw, groups,
-                 eps, gamma, beta, silu ? 1 : 0, cb, cache, out);
+      // pixel split over a small cluster when one CTA per (image, channel block) would leave SMs idle
+      static const int max_cs = [] {
+        const char* e = getenv("MVLDM_GN_CS");
+        return e ? atoi(e) : 2;
+      }();
+      int cs = 1;
+      while (cs < max_cs && (C / cb) * n_img * cs < 148 && hw % (2 * cs) == 0 && hw / (2 * cs) >= 64) cs *= 2;
+      const size_t slab_cs = slab / cs;
+      const int cache_cs = slab_cs <= 160 * 1024 ? 1 : 0;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((C / cb) * cs, n_img, 1);
+      cfg.blockDim = dim3(GNB_THREADS, 1, 1);
+      cfg.dynamicSmemBytes = cache_cs ? slab_cs : 0;
+      cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = cs > 1 ? 1 : 0;
+      MV_CUDA(cudaLaunchKernelEx(&cfg, gn_block_kernel, x0, c0, x1, c1, hw, groups, eps, gamma, beta, silu ? 1 : 0, cb,
+                                 cache_cs, out));
+      MV_LAUNCHED();
+      (void)cache;
       return;
     }
   }
