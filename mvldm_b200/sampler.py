@@ -55,6 +55,7 @@ class DenoisingPath:
                  use_plucker: bool = False):
         self.denoiser, self.scheduler = denoiser, scheduler
         self.use_cfg, self.cfg_scale, self.use_plucker = use_cfg, cfg_scale, use_plucker
+        self._t_cache = {}     # (B, v_c, v_t, ts, device) -> (timesteps [B, v_c+v_t], target timesteps [B, v_t])
 
     def set_timesteps(self, num: int) -> None:
         self.scheduler.set_timesteps(num)
@@ -68,10 +69,13 @@ class DenoisingPath:
         ts = int(ts)
         dev = x_t.device
         x_in = self.scheduler.scale_model_input(x_t, ts)
-        t_c = torch.zeros((B, v_c), dtype=torch.long, device=dev)
-        t_t = torch.full((B, v_t), ts, dtype=torch.long, device=dev)
+        key = (B, v_c, v_t, ts, dev)
+        if key not in self._t_cache:   # timestep 0 for context views, ts for target views (diffusion_wrapper.py:419-428)
+            t_t = torch.full((B, v_t), ts, dtype=torch.long, device=dev)
+            self._t_cache[key] = (torch.cat([torch.zeros((B, v_c), dtype=torch.long, device=dev), t_t], dim=1), t_t)
+        t_all, t_t = self._t_cache[key]
         inputs = build_inputs(x_in, context_inputs[:, :, :4], ray_encodings)
-        pred_c = model.forward(inputs, torch.cat([t_c, t_t], dim=1))
+        pred_c = model.forward(inputs, t_all)
         pred_u = None
         if self.use_cfg:
             pred_u = model.forward(build_inputs(x_in, None, ray_encodings, ray_view_offset=v_c), t_t)
