@@ -68,6 +68,7 @@ def stats(t):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-trajectory", action="store_true")
+    ap.add_argument("--skip-variant-b", action="store_true")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_grad_enabled(False)
@@ -125,6 +126,38 @@ def main():
         for k, v in taps.items():
             out["tap/" + k] = stats(v)
         np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+
+    # ---- G6: Variant B (SD-2.1 topology, random init): per-view Transformer2DModels + the quirks of mvunet.py ----
+    # mvunet.py hard-codes `.cuda()` on the zero context (lines 125-128,155-157); there is no GPU here, so Tensor.cuda
+    # is made a no-op for this call only (the reference source itself is untouched).
+    if not args.skip_variant_b:
+        cfg_b = O.OracleCfg(variant_b=True)
+        sd_b = O.init_weights(cfg_b, seed=0)
+        ucfg = UNet2DModelCfg("unet", ["CrossAttnDownBlock2D"] * 3 + ["DownBlock2D"], "UNetMidBlock2DCrossAttn",
+                              ["UpBlock2D"] + ["CrossAttnUpBlock2D"] * 3, False, [320, 640, 1280, 1280])
+        mcfg = MultiViewUNetCfg("mv_unet", ucfg, SpatialTransformer3DCfg("spatial_transformer_3d", num_heads=8),
+                                use_ray_encoding=False, pretrained_from="stabilityai/stable-diffusion-2-1")
+        ref_b = MultiViewUNet(mcfg, 11, 4)
+        ref_b.load_state_dict(sd_b, strict=True)
+        ref_b.eval()
+        ctx, x_T, extr, intr = O.synthetic_scene(1, 2, 2)
+        rays = reference_rays(extr, intr, 32, 32, False)
+        inp, _ = O.build_inputs(x_T, torch.cat([ctx, torch.zeros(1, 2, 1, 32, 32)], 2), rays, torch.ones(1, 2, 1, 32, 32))
+        ts = torch.tensor([[0, 0, 500, 500]])
+        orig_cuda = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        try:
+            t0 = time.time()
+            y_ref = ref_b.forward(inp, ts)
+        finally:
+            torch.Tensor.cuda = orig_cuda
+        y_ora = O.unet_forward(sd_b, inp, ts, cfg_b)
+        err = (y_ref - y_ora).abs().max().item()
+        print(f"g6_forward_variant_b_v4: ref {time.time() - t0:.1f}s  max|ref-oracle| = {err:.3e}  std {y_ref.std().item():.4f}")
+        assert err < 1e-4 * y_ref.abs().max().item() + 1e-5
+        np.savez_compressed(os.path.join(GOLD, "g6_forward_variant_b_v4.npz"), inputs=inp.numpy(), timesteps=ts.numpy(),
+                            eps=y_ref.numpy())
+        del ref_b, sd_b
 
     if args.skip_trajectory:
         return

@@ -51,6 +51,12 @@ class OracleCfg:
     num_heads: int = 8             # spatial_transformer_3d.yaml:5
     temb_dim_mult: int = 4         # time_embed_dim = 4 * block_out_channels[0]
     max_attn_res: int = 32         # mvunet.py:137,190  (h<=32 and w<=32)
+    # Variant B: SD-2.1 topology = per-view Transformer2DModel after every resnet of down blocks
+    # 0-2 and inside the mid block (attention_head_dim = heads, head dim 64, cross_attention_dim 1024); the up-block
+    # transformers exist in the state dict but are never executed (mvunet.py:178)
+    variant_b: bool = False
+    t2d_heads: Tuple[int, ...] = (5, 10, 20, 20)
+    cross_attention_dim: int = 1024
 
     @property
     def temb_dim(self) -> int:
@@ -118,6 +124,21 @@ def param_shapes(cfg: OracleCfg) -> "Dict[str, Tuple[Tuple[int, ...], str]]":
             norm(f"{tb}.{n}", c)
         conv(k + ".proj_out", c, c, 1)
 
+    def t2d(k, c):
+        norm(k + ".norm", c)
+        lin(k + ".proj_in", c, c)
+        tb = k + ".transformer_blocks.0"
+        for n in ("norm1", "norm2", "norm3"):
+            norm(f"{tb}.{n}", c)
+        for a, kv in (("attn1", c), ("attn2", cfg.cross_attention_dim)):
+            lin(f"{tb}.{a}.to_q", c, c, bias=False)
+            lin(f"{tb}.{a}.to_k", c, kv, bias=False)
+            lin(f"{tb}.{a}.to_v", c, kv, bias=False)
+            lin(f"{tb}.{a}.to_out.0", c, c)
+        lin(f"{tb}.ff.net.0.proj", 8 * c, c)
+        lin(f"{tb}.ff.net.2", c, 4 * c)
+        lin(k + ".proj_out", c, c)
+
     conv("unet.conv_in", boc[0], cfg.in_channels, 3)
     lin("unet.time_embedding.linear_1", T, boc[0])
     lin("unet.time_embedding.linear_2", T, T)
@@ -127,9 +148,14 @@ def param_shapes(cfg: OracleCfg) -> "Dict[str, Tuple[Tuple[int, ...], str]]":
         cin, cout = cout, c
         for i in range(cfg.layers_per_block):
             resnet(f"unet.down_blocks.{l}.resnets.{i}", cin if i == 0 else cout, cout)
+            if cfg.variant_b and l != len(boc) - 1:
+                t2d(f"unet.down_blocks.{l}.attentions.{i}", cout)
         if l != len(boc) - 1:
             conv(f"unet.down_blocks.{l}.downsamplers.0.conv", cout, cout, 3)
     resnet("unet.mid_block.resnets.0", boc[-1], boc[-1])
+    if cfg.variant_b:
+        t2d("unet.mid_block.attentions.0", boc[-1])
+        resnet("unet.mid_block.resnets.1", boc[-1], boc[-1])
     # up
     rev = list(reversed(boc))
     out_c = rev[0]
@@ -140,6 +166,8 @@ def param_shapes(cfg: OracleCfg) -> "Dict[str, Tuple[Tuple[int, ...], str]]":
             skip = in_c if i == cfg.layers_per_block else out_c
             rin = prev if i == 0 else out_c
             resnet(f"unet.up_blocks.{l}.resnets.{i}", rin + skip, out_c)
+            if cfg.variant_b and l != 0:
+                t2d(f"unet.up_blocks.{l}.attentions.{i}", out_c)   # present in the checkpoint, never executed
         if l != len(boc) - 1:
             conv(f"unet.up_blocks.{l}.upsamplers.0.conv", out_c, out_c, 3)
     norm("unet.conv_norm_out", boc[0])
@@ -269,8 +297,41 @@ def mv_block(sd, k: str, x: Tensor, b: int, v: int, heads: int, groups: int,
     return y + x_in
 
 
+def transformer2d(sd, k: str, x: Tensor, heads: int, groups: int, cross_dim: int) -> Tensor:
+    """diffusers ``Transformer2DModel`` (use_linear_projection=True, one ``BasicTransformerBlock``) as the reference
+    calls it at mvunet.py:131-134,158 with ``encoder_hidden_states = zeros(b*v, 1, 1024)``:
+    GN(eps 1e-6) -> Linear -> [LN -> self-attn (head dim 64) -> +; LN -> cross-attn to the zero token -> +;
+    LN -> GEGLU FF -> +] -> Linear -> + input."""
+    bv, c, h, w = x.shape
+    y = F.group_norm(x, groups, sd[k + ".norm.weight"], sd[k + ".norm.bias"], eps=1e-6)
+    y = y.permute(0, 2, 3, 1).reshape(bv, h * w, c)
+    y = F.linear(y, sd[k + ".proj_in.weight"], sd[k + ".proj_in.bias"])
+    tb = k + ".transformer_blocks.0"
+
+    def ln(t, name):
+        return F.layer_norm(t, (c,), sd[f"{tb}.{name}.weight"], sd[f"{tb}.{name}.bias"], eps=1e-5)
+
+    y = _attention(sd, tb + ".attn1", ln(y, "norm1"), heads) + y
+    # cross-attention over ONE all-zero context token: k = v = 0 (bias-free projections), softmax over one key = 1,
+    # so the branch contributes exactly to_out.0(0) = its bias; computed explicitly here
+    ctx = torch.zeros(bv, 1, cross_dim, dtype=y.dtype, device=y.device)
+    q = F.linear(ln(y, "norm2"), sd[tb + ".attn2.to_q.weight"])
+    kk = F.linear(ctx, sd[tb + ".attn2.to_k.weight"])
+    vv = F.linear(ctx, sd[tb + ".attn2.to_v.weight"])
+    d = c // heads
+    sp = lambda t: t.reshape(bv, -1, heads, d).permute(0, 2, 1, 3)  # noqa: E731
+    a2 = torch.softmax(sp(q) @ sp(kk).transpose(-1, -2) * d ** -0.5, dim=-1) @ sp(vv)
+    a2 = a2.permute(0, 2, 1, 3).reshape(bv, h * w, c)
+    y = F.linear(a2, sd[tb + ".attn2.to_out.0.weight"], sd[tb + ".attn2.to_out.0.bias"]) + y
+    z = F.linear(ln(y, "norm3"), sd[tb + ".ff.net.0.proj.weight"], sd[tb + ".ff.net.0.proj.bias"])
+    a, gate = z.chunk(2, dim=-1)
+    y = F.linear(a * F.gelu(gate), sd[tb + ".ff.net.2.weight"], sd[tb + ".ff.net.2.bias"]) + y
+    y = F.linear(y, sd[k + ".proj_out.weight"], sd[k + ".proj_out.bias"])
+    return y.reshape(bv, h, w, c).permute(0, 3, 1, 2) + x
+
+
 # --------------------------------------------------------------------------------------
-# MultiViewUNet.forward (mvunet.py:90-208), Variant A
+# MultiViewUNet.forward (mvunet.py:90-208), Variant A (and Variant B with cfg.variant_b)
 # --------------------------------------------------------------------------------------
 def unet_forward(sd: Dict[str, Tensor], latents: Tensor, timestep: Tensor, cfg: OracleCfg,
                  taps: Optional[dict] = None) -> Tensor:
@@ -295,6 +356,8 @@ def unet_forward(sd: Dict[str, Tensor], latents: Tensor, timestep: Tensor, cfg: 
     for l in range(nb):
         for i in range(cfg.layers_per_block):
             x = resnet_block(sd, f"unet.down_blocks.{l}.resnets.{i}", x, emb, G)
+            if cfg.variant_b and l != nb - 1:    # CrossAttnDownBlock2D: per-view transformer after every resnet (:122-134)
+                x = transformer2d(sd, f"unet.down_blocks.{l}.attentions.{i}", x, cfg.t2d_heads[l], G, cfg.cross_attention_dim)
             tap(f"down{l}.res{i}", x)
             skips.append(x)                      # recorded BEFORE the multi-view block (:135)
         if x.shape[-2] <= cfg.max_attn_res and x.shape[-1] <= cfg.max_attn_res:
@@ -306,6 +369,9 @@ def unet_forward(sd: Dict[str, Tensor], latents: Tensor, timestep: Tensor, cfg: 
             tap(f"down{l}.ds", x)
             skips.append(x)
     x = resnet_block(sd, "unet.mid_block.resnets.0", x, emb, G)
+    if cfg.variant_b:                            # UNetMidBlock2DCrossAttn: attn, resnet (:152-159)
+        x = transformer2d(sd, "unet.mid_block.attentions.0", x, cfg.t2d_heads[-1], G, cfg.cross_attention_dim)
+        x = resnet_block(sd, "unet.mid_block.resnets.1", x, emb, G)
     tap("mid.res0", x)
     x = mv_block(sd, "cross_attn_blocks_mid.0", x, B, V, cfg.num_heads, G, taps)
     tap("mid.mv", x)

@@ -68,3 +68,18 @@ def test_trajectory_first_step_matches_reference(oracle_cfg, oracle_weights):
         x1, eps = O.ddim_step(oracle_weights, oracle_cfg, sched, x_T, 960, cin, rays, torch.ones(1, 6, 1, 32, 32))
     assert rel_err(eps, torch.tensor(g["eps_step0"])) < 1e-4
     assert rel_err(x1, torch.tensor(g["x_after_step0"])) < 1e-4
+
+
+def test_variant_b_matches_reference():
+    """Variant B (SD-2.1 topology, `pretrained_from` set): mvunet.py:118-131,150-160 — per-view Transformer2DModel after
+    each resnet of down blocks 0-2 and between the two mid resnets, cross-attending to one zero token; up-block
+    attentions exist in the state dict (920 keys) but never run."""
+    cfg = O.OracleCfg(variant_b=True)
+    shapes = O.param_shapes(cfg)
+    assert len(shapes) == 920
+    assert sum(k.startswith("unet.up_blocks.") and ".attentions." in k for k in shapes) > 0
+    g = np.load(os.path.join(GOLD, "g6_forward_variant_b_v4.npz"))
+    sd = O.init_weights(cfg, seed=0)
+    with torch.no_grad():
+        y = O.unet_forward(sd, torch.tensor(g["inputs"]), torch.tensor(g["timesteps"]), cfg)
+    assert rel_err(y, torch.tensor(g["eps"])) < 1e-4
