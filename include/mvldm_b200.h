@@ -44,6 +44,13 @@ typedef struct {
   int32_t max_attn_res;                         /* mvunet.py:137,190: multi-view block only if h,w <= 32 */
   int32_t impl;                                 /* MVLDM_IMPL_* */
   int32_t use_cuda_graph;                       /* capture one graph per (B,V,h,w) and replay it */
+  /* Variant B = `pretrained_from` set (mvunet.py:51-59): the SD-2.1 UNet2DConditionModel topology.  Down blocks
+   * 0..L-2 and the mid block carry a per-view Transformer2DModel after each resnet (mvunet.py:118-131,150-160) whose
+   * cross-attention sees one all-zero token; the up blocks' attentions exist in the state dict but are never run
+   * (mvunet.py:166-186 calls only the resnets), so their keys are accepted and dropped. */
+  int32_t variant;                              /* 0 = A (DownBlock2D/UpBlock2D), 1 = B (SD-2.1 topology) */
+  int32_t t2d_heads[MVLDM_MAX_LEVELS];          /* SD-2.1 attention_head_dim [5,10,20,20] (= heads; head dim 64) */
+  int32_t cross_attention_dim;                  /* 1024 */
 } mvldm_config;
 
 const char* mvldm_last_error(void);

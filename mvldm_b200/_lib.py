@@ -24,6 +24,7 @@ class Config(Structure):
         ("block_out_channels", c_int32 * MVLDM_MAX_LEVELS), ("layers_per_block", c_int32),
         ("norm_groups", c_int32), ("num_heads", c_int32), ("max_attn_res", c_int32), ("impl", c_int32),
         ("use_cuda_graph", c_int32),
+        ("variant", c_int32), ("t2d_heads", c_int32 * MVLDM_MAX_LEVELS), ("cross_attention_dim", c_int32),
     ]
 
 

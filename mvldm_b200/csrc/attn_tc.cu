@@ -606,12 +606,14 @@ void launch64(cudaStream_t s, const AttnSrc& a, bf16* out, int batches, int head
 }
 
 void dispatch(cudaStream_t s, const AttnSrc& a, bf16* out, int batches, int heads, int d, int dpad) {
-  MV_CHECK(d < dpad && a.seq_q >= 1 && a.seq_kv >= 1 && batches >= 1, "attention_tc: bad arguments (need dpad > d)");
+  MV_CHECK(d <= dpad && a.seq_q >= 1 && a.seq_kv >= 1 && batches >= 1, "attention_tc: bad arguments (need dpad >= d)");
   MV_CHECK((reinterpret_cast<uintptr_t>(a.q) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.kv) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(out) & 15) == 0 && a.ld_q % 8 == 0 && a.ld_kv % 8 == 0,
            "attention_tc: pointers must be 16-byte aligned, row pitches multiples of 8");
   static const bool legacy64 = getenv("MVLDM_ATTN64_LEGACY") != nullptr;
-  if (dpad == 64 && !legacy64) launch64(s, a, out, batches, heads, d);
+  // attn64 takes the row sum from V's ones column, which needs a pad column; d == 64 (Variant B's Transformer2D heads)
+  // runs the generic kernel, which sums the row in registers
+  if (dpad == 64 && d < dpad && !legacy64) launch64(s, a, out, batches, heads, d);
   else if (dpad == 64) launch<64, 128, 2, 2>(s, a, out, batches, heads, d);   // 80 KB smem, 256 TMEM cols: 2 CTAs/SM
   else if (dpad == 128) launch<128, 128, 2, 1>(s, a, out, batches, heads, d);
   else if (dpad == 192) launch<192, 64, 2, 1>(s, a, out, batches, heads, d);

@@ -8,6 +8,7 @@
 // "b c h w -> b (h w) c" rearranges of the reference are no-ops.  Weights are bf16 [N, K] (K contiguous,
 // tap-major for 3x3 filters).  Statistics, biases, time embeddings and the softmax are fp32.
 #include <map>
+#include <set>
 #include <memory>
 #include <vector>
 
@@ -68,9 +69,10 @@ struct ResnetW {
   Packed conv1, conv2;  // conv2 carries the 1x1 shortcut as extra K columns when present
 };
 
-struct MvW {
+struct MvW {  // SpatialTransformer3D block, or (t2d) a per-view diffusers Transformer2DModel of Variant B
   std::string key;
-  int c = 0, d = 0, dpad = 0;
+  int c = 0, d = 0, dpad = 0, heads = 0;
+  bool t2d = false;
   const float *gn_g = nullptr, *gn_b = nullptr, *ln_g[3] = {}, *ln_b[3] = {};
   Packed proj_in, qkv1, out1, qkv2, out2, ff1, ff2, proj_out;
 };
@@ -128,6 +130,11 @@ struct mvldm_handle_s {
   std::vector<Packed> down_conv, up_conv;
   std::vector<MvW> mv_enc, mv_dec;
   MvW mv_mid;
+  // Variant B only
+  std::vector<std::vector<MvW>> t2d_down;
+  MvW t2d_mid;
+  ResnetW mid_res1;
+  std::set<std::string> unused;  // keys of modules the reference forward never calls (up-block attentions)
   const float *norm_out_g = nullptr, *norm_out_b = nullptr;
   int kpad_in = 0;
 
@@ -236,9 +243,43 @@ struct mvldm_handle_s {
     MvW m;
     m.key = k;
     m.c = c;
+    m.heads = cfg.num_heads;
     MV_CHECK(c % cfg.num_heads == 0, "channels not divisible by num_heads");
     m.d = c / cfg.num_heads;
     m.dpad = (m.d + 63) / 64 * 64;
+    MV_CHECK(m.dpad <= 192, "head dim > 192 unsupported");
+    return m;
+  }
+  // diffusers Transformer2DModel (use_linear_projection) with one BasicTransformerBlock: SURVEY.md App. A.6
+  MvW reg_t2d(const std::string& k, int c, int heads, bool used) {
+    const size_t first = names.size();
+    reg_norm(k + ".norm", c);
+    reg_lin(k + ".proj_in", c, c);
+    const std::string tb = k + ".transformer_blocks.0";
+    reg_norm(tb + ".norm1", c);
+    reg_lin(tb + ".attn1.to_q", c, c, false);
+    reg_lin(tb + ".attn1.to_k", c, c, false);
+    reg_lin(tb + ".attn1.to_v", c, c, false);
+    reg_lin(tb + ".attn1.to_out.0", c, c);
+    reg_norm(tb + ".norm2", c);
+    reg_lin(tb + ".attn2.to_q", c, c, false);
+    reg_lin(tb + ".attn2.to_k", c, cfg.cross_attention_dim, false);
+    reg_lin(tb + ".attn2.to_v", c, cfg.cross_attention_dim, false);
+    reg_lin(tb + ".attn2.to_out.0", c, c);
+    reg_norm(tb + ".norm3", c);
+    reg_lin(tb + ".ff.net.0.proj", 8 * c, c);
+    reg_lin(tb + ".ff.net.2", c, 4 * c);
+    reg_lin(k + ".proj_out", c, c);
+    if (!used)
+      for (size_t i = first; i < names.size(); ++i) unused.insert(names[i]);
+    MvW m;
+    m.key = k;
+    m.c = c;
+    m.t2d = true;
+    m.heads = heads;
+    MV_CHECK(heads > 0 && c % heads == 0, "t2d_heads must divide the level's channels");
+    m.d = c / heads;
+    m.dpad = (m.d + 63) / 64 * 64;  // d == dpad (SD-2.1: 64) runs the in-register row-sum attention kernel
     MV_CHECK(m.dpad <= 192, "head dim > 192 unsupported");
     return m;
   }
@@ -253,15 +294,24 @@ struct mvldm_handle_s {
     int cout = boc[0];
     down_res.resize(L);
     up_res.resize(L);
+    t2d_down.resize(L);
     for (int l = 0; l < L; ++l) {
       const int cin = cout;
       cout = boc[l];
       for (int i = 0; i < cfg.layers_per_block; ++i)
         down_res[l].push_back(reg_resnet("unet.down_blocks." + std::to_string(l) + ".resnets." + std::to_string(i),
                                          i == 0 ? cin : cout, cout));
+      if (cfg.variant == 1 && l != L - 1)
+        for (int i = 0; i < cfg.layers_per_block; ++i)
+          t2d_down[l].push_back(reg_t2d("unet.down_blocks." + std::to_string(l) + ".attentions." + std::to_string(i), cout,
+                                        cfg.t2d_heads[l], true));
       if (l != L - 1) reg_conv("unet.down_blocks." + std::to_string(l) + ".downsamplers.0.conv", cout, cout, 3);
     }
     mid_res = reg_resnet("unet.mid_block.resnets.0", boc[L - 1], boc[L - 1]);
+    if (cfg.variant == 1) {
+      t2d_mid = reg_t2d("unet.mid_block.attentions.0", boc[L - 1], cfg.t2d_heads[L - 1], true);
+      mid_res1 = reg_resnet("unet.mid_block.resnets.1", boc[L - 1], boc[L - 1]);
+    }
     int out_c = boc[L - 1];
     for (int l = 0; l < L; ++l) {
       const int prev = out_c;
@@ -273,6 +323,10 @@ struct mvldm_handle_s {
         up_res[l].push_back(reg_resnet("unet.up_blocks." + std::to_string(l) + ".resnets." + std::to_string(i),
                                        rin + skip, out_c));
       }
+      if (cfg.variant == 1 && l != 0)  // CrossAttnUpBlock2D attentions: in the state dict, never executed
+        for (int i = 0; i < cfg.layers_per_block + 1; ++i)
+          reg_t2d("unet.up_blocks." + std::to_string(l) + ".attentions." + std::to_string(i), out_c,
+                  cfg.t2d_heads[L - 1 - l], false);
       if (l != L - 1) reg_conv("unet.up_blocks." + std::to_string(l) + ".upsamplers.0.conv", out_c, out_c, 3);
     }
     reg_norm("unet.conv_norm_out", boc[0]);
@@ -345,7 +399,7 @@ struct mvldm_handle_s {
                             cudaMemcpyDeviceToDevice, stream));
   }
   Packed pack_qkv(const std::string& a, const MvW& m) {
-    const int H = cfg.num_heads;
+    const int H = m.heads;
     Packed p;
     p.n = 3 * H * m.dpad;
     p.k = m.c;
@@ -358,16 +412,17 @@ struct mvldm_handle_s {
     }
     // q/k/v have no bias in the reference; the packed GEMM's bias plants 1.0 in the first pad column of every V head,
     // which makes P.V deliver the softmax row sum in column d of the attention accumulator (attn_tc.cu)
-    MV_CHECK(m.dpad > m.d, "attention needs at least one pad column per head");
+    // (d == dpad, Variant B's 64-wide heads: no pad column; attention_tc then sums the row in registers)
     std::vector<float> hb(p.n, 0.f);
-    for (int h = 0; h < H; ++h) hb[(2 * H + h) * m.dpad + m.d] = 1.f;
+    if (m.dpad > m.d)
+      for (int h = 0; h < H; ++h) hb[(2 * H + h) * m.dpad + m.d] = 1.f;
     p.bias = store<float>(p.n);
     MV_CUDA(cudaMemcpyAsync(p.bias, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
     MV_CUDA(cudaStreamSynchronize(stream));
     return p;
   }
   Packed pack_attn_out(const std::string& a, const MvW& m) {
-    const int H = cfg.num_heads;
+    const int H = m.heads;
     Packed p;
     p.n = m.c;
     p.k = H * m.dpad;
@@ -386,12 +441,21 @@ struct mvldm_handle_s {
       m.ln_g[i] = rawf(tb + ln[i] + ".weight");
       m.ln_b[i] = rawf(tb + ln[i] + ".bias");
     }
-    m.proj_in = pack_conv(m.key + ".proj_in", m.c, m.c, 1);
-    m.proj_out = pack_conv(m.key + ".proj_out", m.c, m.c, 1);
     m.qkv1 = pack_qkv(tb + ".attn1", m);
     m.out1 = pack_attn_out(tb + ".attn1", m);
-    m.qkv2 = pack_qkv(tb + ".attn2", m);
-    m.out2 = pack_attn_out(tb + ".attn2", m);
+    if (m.t2d) {
+      m.proj_in = pack_linear(m.key + ".proj_in", m.c, m.c, true);
+      m.proj_out = pack_linear(m.key + ".proj_out", m.c, m.c, true);
+      // attn2 cross-attends to ONE all-zero token (mvunet.py:125-128): K = V = W.0 = 0 exactly, softmax over one key
+      // is 1, so attn2(x) == to_out.0.bias for every token whatever its to_q/to_k/to_v/norm2 hold.  The bias rides
+      // on the attn1 output projection.
+      m.out1.bias = bias_sum(tb + ".attn1.to_out.0.bias", tb + ".attn2.to_out.0.bias", m.c);
+    } else {
+      m.proj_in = pack_conv(m.key + ".proj_in", m.c, m.c, 1);
+      m.proj_out = pack_conv(m.key + ".proj_out", m.c, m.c, 1);
+      m.qkv2 = pack_qkv(tb + ".attn2", m);
+      m.out2 = pack_attn_out(tb + ".attn2", m);
+    }
     // GEGLU: interleave value / gate rows in blocks of 16 so one 32-column accumulator chunk holds both
     const int c4 = 4 * m.c;
     m.ff1.n = 2 * c4;
@@ -418,7 +482,7 @@ struct mvldm_handle_s {
 
   void finalize(cudaStream_t s) {
     stream = s;
-    for (auto& n : names) MV_CHECK(raw.count(n), "mvldm_finalize_weights: missing weight " + n);
+    for (auto& n : names) MV_CHECK(unused.count(n) || raw.count(n), "mvldm_finalize_weights: missing weight " + n);
     MV_CUDA(cudaStreamSynchronize(s));
     packed_store.clear();
     groupnorm_init();
@@ -442,6 +506,12 @@ struct mvldm_handle_s {
     for (auto& lv : down_res)
       for (auto& r : lv) pack_resnet(r);
     pack_resnet(mid_res);
+    if (cfg.variant == 1) {
+      pack_resnet(mid_res1);
+      for (auto& lv : t2d_down)
+        for (auto& m : lv) pack_mv(m);
+      pack_mv(t2d_mid);
+    }
     for (auto& lv : up_res)
       for (auto& r : lv) pack_resnet(r);
     down_conv.clear();
@@ -539,15 +609,15 @@ struct mvldm_handle_s {
     // algorithmic FLOPs: QK^T and PV over the un-padded head dim, 4 * seq^2 * C per batch
     ProfScope ps(this, seq > out.h * out.w ? "attention_joint" : "attention_per_view",
                  "batches" + std::to_string(batches) + " seq" + std::to_string(seq) + " d" + std::to_string(m.d),
-                 4.0 * batches * (double)seq * seq * m.c, 2.0 * (double)out.tokens() * (4.0 * cfg.num_heads * m.dpad));
+                 4.0 * batches * (double)seq * seq * m.c, 2.0 * (double)out.tokens() * (4.0 * m.heads * m.dpad));
     if (dry) return;
-    if (cfg.impl == MVLDM_IMPL_TC) attention_tc(stream, qkv.p, out.p, batches, seq, cfg.num_heads, m.d, m.dpad);
-    else attention_simt(stream, qkv.p, out.p, batches, seq, cfg.num_heads, m.d, m.dpad);
+    if (cfg.impl == MVLDM_IMPL_TC) attention_tc(stream, qkv.p, out.p, batches, seq, m.heads, m.d, m.dpad);
+    else attention_simt(stream, qkv.p, out.p, batches, seq, m.heads, m.d, m.dpad);
   }
 
   // This rank's views supply the queries; K and V of every view of the scene are all-gathered by the host callback.
   void joint_attention_sharded(const Act& qkv, const Act& out, int seq_local, const MvW& m) {
-    const int H = cfg.num_heads, hd = H * m.dpad;
+    const int H = m.heads, hd = H * m.dpad;
     const size_t bytes = (size_t)seq_local * 2 * hd * sizeof(bf16);
     const int world = v_total / (int)(qkv.n);
     ProfScope ps(this, "attention_joint_sharded", "seq_q" + std::to_string(seq_local) + " seq_kv" + std::to_string(seq_local * world),
@@ -586,7 +656,7 @@ struct mvldm_handle_s {
   }
 
   Act mv_block(const MvW& m, const Act& x, int B, int V) {
-    const int n = x.n, h = x.h, w = x.w, C = m.c, H = cfg.num_heads;
+    const int n = x.n, h = x.h, w = x.w, C = m.c, H = m.heads;
     const int hw = h * w;
     Act out = new_act(n, h, w, C);
     const size_t mark = arena.off;
@@ -613,6 +683,34 @@ struct mvldm_handle_s {
     gemm({seg_1x1(o)}, m.out2, t3, nullptr, 0, &t2, 0, 2.0 * (double)t.tokens() * C * C);
     tap(m.key + ".attn2", t3);
     // GEGLU feed-forward
+    ln(t3, m.ln_g[2], m.ln_b[2], nrm);
+    Act f = new_act(n, h, w, 4 * C);
+    gemm({seg_1x1(nrm)}, m.ff1, f, nullptr, 0, nullptr, 1);
+    Act t4 = new_act(n, h, w, C);
+    gemm({seg_1x1(f)}, m.ff2, t4, nullptr, 0, &t3);
+    gemm({seg_1x1(t4)}, m.proj_out, out, nullptr, 0, &x);
+    if (!taps_enabled) arena.off = mark;
+    return out;
+  }
+
+  // Variant B: per-view diffusers Transformer2DModel (GN 1e-6 -> Linear -> [LN, self-attn, +] -> [+ attn2 bias]
+  // -> [LN, GEGLU FF, +] -> Linear -> + x); the attention never crosses views (mvunet.py:118-131).
+  Act t2d_block(const MvW& m, const Act& x) {
+    const int n = x.n, h = x.h, w = x.w, C = m.c, H = m.heads;
+    Act out = new_act(n, h, w, C);
+    const size_t mark = arena.off;
+    Act g = new_act(n, h, w, C);
+    gn(x, nullptr, m.gn_g, m.gn_b, 1e-6f, false, g);
+    Act t = new_act(n, h, w, C);
+    gemm({seg_1x1(g)}, m.proj_in, t);
+    Act nrm = new_act(n, h, w, C);
+    Act qkv = new_act(n, h, w, 3 * H * m.dpad);
+    Act o = new_act(n, h, w, H * m.dpad);
+    ln(t, m.ln_g[0], m.ln_b[0], nrm);
+    gemm({seg_1x1(nrm)}, m.qkv1, qkv, nullptr, 0, nullptr, 0, 6.0 * (double)t.tokens() * C * C);
+    attn(qkv, o, n, h * w, m);
+    Act t3 = new_act(n, h, w, C);  // attn1 residual + the constant attn2 output (see pack_mv)
+    gemm({seg_1x1(o)}, m.out1, t3, nullptr, 0, &t, 0, 2.0 * (double)t.tokens() * C * C);
     ln(t3, m.ln_g[2], m.ln_b[2], nrm);
     Act f = new_act(n, h, w, 4 * C);
     gemm({seg_1x1(nrm)}, m.ff1, f, nullptr, 0, nullptr, 1);
@@ -654,6 +752,7 @@ struct mvldm_handle_s {
     for (int l = 0; l < L; ++l) {
       for (int i = 0; i < cfg.layers_per_block; ++i) {
         x = resnet(down_res[l][i], x, nullptr, temb);
+        if (!t2d_down[l].empty()) x = t2d_block(t2d_down[l][i], x);
         tap("down" + std::to_string(l) + ".res" + std::to_string(i), x);
         skips.push_back(x);
       }
@@ -671,6 +770,10 @@ struct mvldm_handle_s {
     }
     // ---- mid
     x = resnet(mid_res, x, nullptr, temb);
+    if (cfg.variant == 1) {
+      x = t2d_block(t2d_mid, x);
+      x = resnet(mid_res1, x, nullptr, temb);
+    }
     tap("mid.res0", x);
     x = mv_block(mv_mid, x, B, V);
     tap("mid.mv", x);
@@ -873,6 +976,8 @@ int mvldm_create(const mvldm_config* cfg, int device, mvldm_handle* out) {
     MV_CHECK(cfg->block_out_channels[l] % 64 == 0, "block_out_channels must be multiples of 64");
     MV_CHECK(cfg->block_out_channels[l] % cfg->norm_groups == 0, "channels not divisible by norm_groups");
   }
+  MV_CHECK(cfg->variant == 0 || cfg->variant == 1, "variant must be 0 (A) or 1 (B)");
+  if (cfg->variant == 1) MV_CHECK(cfg->cross_attention_dim > 0, "variant B needs cross_attention_dim");
   h->build_registry();
   *out = h.release();
   MV_API_END
@@ -917,6 +1022,7 @@ int mvldm_set_weight(mvldm_handle h, const char* key, const void* ptr, const int
     numel *= shape[i];
   }
   MV_CHECK(dtype >= MVLDM_F32 && dtype <= MVLDM_F16, "bad dtype");
+  if (h->unused.count(key)) return 0;  // shape-checked, never read by the forward: not kept on the device
   auto& buf = h->raw[key];
   if (!buf || buf->bytes != (size_t)numel * sizeof(float)) buf.reset(new DevBuf((size_t)numel * sizeof(float)));
   convert_f32((cudaStream_t)stream, ptr, dtype, numel, reinterpret_cast<float*>(buf->p));

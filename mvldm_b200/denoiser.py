@@ -88,10 +88,18 @@ class Denoiser(nn.Module, ABC, Generic[T]):
         pass
 
 
-def param_shapes(block_out_channels, in_channels: int, out_channels: int, layers_per_block: int = 2
-                 ) -> "Dict[str, Tuple[int, ...]]":
-    """State-dict keys and shapes of the Variant-A MultiViewUNet; must equal the
-    registry the C library builds in ``mvldm_create`` (checked at handle creation)."""
+# stabilityai/stable-diffusion-2-1 unet/config.json, the only hub topology mvunet.py:124-128 can drive (it hard-codes a
+# 1024-wide context): attention_head_dim (= heads, a diffusers quirk; every head is 64 wide) and cross_attention_dim
+SD21_BLOCK_OUT_CHANNELS = (320, 640, 1280, 1280)
+SD21_HEADS = (5, 10, 20, 20)
+SD21_CROSS_ATTENTION_DIM = 1024
+
+
+def param_shapes(block_out_channels, in_channels: int, out_channels: int, layers_per_block: int = 2,
+                 variant_b: bool = False) -> "Dict[str, Tuple[int, ...]]":
+    """State-dict keys and shapes of the MultiViewUNet; must equal the registry the C
+    library builds in ``mvldm_create`` (checked at handle creation).  ``variant_b`` adds the SD-2.1 pieces:
+    ``unet.{down_blocks.0-2,mid_block,up_blocks.1-3}.attentions.*`` and ``unet.mid_block.resnets.1``."""
     P: Dict[str, Tuple[int, ...]] = {}
     boc = list(block_out_channels)
     T_ = boc[0] * 4
@@ -127,6 +135,18 @@ def param_shapes(block_out_channels, in_channels: int, out_channels: int, layers
             norm(f"{tb}.{n}", c)
         conv(k + ".proj_out", c, c, 1)
 
+    def t2d(k, c):
+        norm(k + ".norm", c); lin(k + ".proj_in", c, c)
+        tb = k + ".transformer_blocks.0"
+        for a, kv in (("attn1", c), ("attn2", SD21_CROSS_ATTENTION_DIM)):
+            lin(f"{tb}.{a}.to_q", c, c, bias=False)
+            lin(f"{tb}.{a}.to_k", c, kv, bias=False); lin(f"{tb}.{a}.to_v", c, kv, bias=False)
+            lin(f"{tb}.{a}.to_out.0", c, c)
+        lin(f"{tb}.ff.net.0.proj", 8 * c, c); lin(f"{tb}.ff.net.2", c, 4 * c)
+        for n in ("norm1", "norm2", "norm3"):
+            norm(f"{tb}.{n}", c)
+        lin(k + ".proj_out", c, c)
+
     L = len(boc)
     conv("unet.conv_in", boc[0], in_channels, 3)
     lin("unet.time_embedding.linear_1", T_, boc[0]); lin("unet.time_embedding.linear_2", T_, T_)
@@ -135,9 +155,13 @@ def param_shapes(block_out_channels, in_channels: int, out_channels: int, layers
         ci, co = co, boc[l]
         for i in range(layers_per_block):
             resnet(f"unet.down_blocks.{l}.resnets.{i}", ci if i == 0 else co, co)
+            if variant_b and l != L - 1:
+                t2d(f"unet.down_blocks.{l}.attentions.{i}", co)
         if l != L - 1:
             conv(f"unet.down_blocks.{l}.downsamplers.0.conv", co, co, 3)
     resnet("unet.mid_block.resnets.0", boc[-1], boc[-1])
+    if variant_b:
+        t2d("unet.mid_block.attentions.0", boc[-1]); resnet("unet.mid_block.resnets.1", boc[-1], boc[-1])
     rev = boc[::-1]
     oc = rev[0]
     for l in range(L):
@@ -145,6 +169,8 @@ def param_shapes(block_out_channels, in_channels: int, out_channels: int, layers
         ic = rev[min(l + 1, L - 1)]
         for i in range(layers_per_block + 1):
             resnet(f"unet.up_blocks.{l}.resnets.{i}", (prev if i == 0 else oc) + (ic if i == layers_per_block else oc), oc)
+            if variant_b and l != 0:
+                t2d(f"unet.up_blocks.{l}.attentions.{i}", oc)
         if l != L - 1:
             conv(f"unet.up_blocks.{l}.upsamplers.0.conv", oc, oc, 3)
     norm("unet.conv_norm_out", boc[0]); conv("unet.conv_out", out_channels, boc[0], 3)
@@ -187,14 +213,17 @@ class _Handle:
 
 
 class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
-    """Drop-in for reference ``MultiViewUNet`` (mvunet.py:43-208), Variant A (``pretrained_from=None``)."""
+    """Drop-in for reference ``MultiViewUNet`` (mvunet.py:43-208).
+
+    ``pretrained_from=None`` (Variant A) builds the topology ``cfg.autoencoder`` names (DownBlock2D / UNetMidBlock2D /
+    UpBlock2D).  ``pretrained_from=<hub id>`` (Variant B) builds the SD-2.1 UNet2DConditionModel topology the reference
+    downloads (mvunet.py:64-72) — WITHOUT the download: there is no hub access in the library, the parameters are
+    random-initialised and the checkpoint arrives through ``load_state_dict`` like any Lightning checkpoint."""
 
     def __init__(self, cfg: MultiViewUNetCfg, in_channels: int, out_channels: int, *, impl: int = _lib.IMPL_TC,
                  use_cuda_graph: bool = True) -> None:
         super().__init__(cfg)
-        if cfg.pretrained_from is not None:
-            raise ValueError("mvldm_b200 builds the pretrained_from=None topology (SURVEY.md §0 Variant A); the SD-2.1 "
-                             "hub topology is not supported yet")
+        self.variant_b = cfg.pretrained_from is not None
         if cfg.multi_view_attention.name != "spatial_transformer_3d":
             raise ValueError("only multi_view_attention.name == 'spatial_transformer_3d' is supported")
         if cfg.multi_view_attention.num_layers != 1 or cfg.multi_view_attention.d_dot is not None:
@@ -202,14 +231,25 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
         if not (cfg.encoder_conditioning and cfg.mid_conditioning and cfg.decoder_conditioning):
             raise ValueError("encoder/mid/decoder_conditioning must all be true")
         ae = cfg.autoencoder
-        if any(t != "DownBlock2D" for t in ae.down_block_types) or any(t != "UpBlock2D" for t in ae.up_block_types) \
-                or ae.mid_block_type != "UNetMidBlock2D":
-            raise ValueError("only DownBlock2D / UNetMidBlock2D / UpBlock2D topologies are supported")
+        if self.variant_b:
+            # from_pretrained ignores cfg.autoencoder's block types; only block_out_channels[0] is read (conv_in/out)
+            if "stable-diffusion-2" not in cfg.pretrained_from:
+                raise ValueError("pretrained_from: only the stabilityai/stable-diffusion-2* UNet topology is known "
+                                 "(mvunet.py:127 hard-codes its 1024-wide context)")
+            if ae.block_out_channels[0] != SD21_BLOCK_OUT_CHANNELS[0]:
+                raise ValueError("autoencoder.block_out_channels[0] must be 320 with an SD-2.1 UNet")
+            self._boc = list(SD21_BLOCK_OUT_CHANNELS)
+        else:
+            if any(t != "DownBlock2D" for t in ae.down_block_types) or any(t != "UpBlock2D" for t in ae.up_block_types) \
+                    or ae.mid_block_type != "UNetMidBlock2D":
+                raise ValueError("pretrained_from=None: only DownBlock2D / UNetMidBlock2D / UpBlock2D topologies are "
+                                 "supported")
+            self._boc = list(ae.block_out_channels)
         self.use_ray_encoding = cfg.use_ray_encoding
         self.pretrained_from = cfg.pretrained_from
         self.in_channels, self.out_channels = in_channels, out_channels
         self.impl, self.use_cuda_graph = impl, use_cuda_graph
-        self._shapes = param_shapes(ae.block_out_channels, in_channels, out_channels)
+        self._shapes = param_shapes(self._boc, in_channels, out_channels, variant_b=self.variant_b)
         for key, shape in self._shapes.items():
             self._register(key, self._init_param(key, shape))
         self._h = _Handle()
@@ -231,7 +271,7 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
         is_norm = ".norm" in key or key.endswith("conv_norm_out.weight") or key.endswith("conv_norm_out.bias")
         if is_norm:
             t = torch.ones(shape) if leaf == "weight" else torch.zeros(shape)
-        elif key.endswith("proj_out.weight") or key.endswith("proj_out.bias"):
+        elif key.startswith("cross_attn_blocks_") and (key.endswith("proj_out.weight") or key.endswith("proj_out.bias")):
             t = torch.zeros(shape)                       # zero_module(): mvdream/attention.py:90-96,406-411
         else:
             wshape = self._shapes[key.rsplit(".", 1)[0] + ".weight"]
@@ -255,7 +295,7 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
             return h
         h.close()
         lib = _lib.load()
-        boc = list(self.cfg.autoencoder.block_out_channels)
+        boc = self._boc
         c = _lib.Config()
         c.in_channels, c.out_channels, c.num_levels = self.in_channels, self.out_channels, len(boc)
         for i, v in enumerate(boc):
@@ -265,6 +305,10 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
         c.max_attn_res = 32
         c.impl = self.impl
         c.use_cuda_graph = 1 if self.use_cuda_graph else 0
+        if self.variant_b:
+            c.variant, c.cross_attention_dim = 1, SD21_CROSS_ATTENTION_DIM
+            for i, v in enumerate(SD21_HEADS):
+                c.t2d_heads[i] = v
         ptr = ctypes.c_void_p()
         _lib.check(lib.mvldm_create(ctypes.byref(c), device.index or 0, ctypes.byref(ptr)))
         h.ptr, h.device, h.synced_versions = ptr, device, None
@@ -303,8 +347,8 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
     # ---- Denoiser.forward -----------------------------------------------------------------
     @torch.no_grad()
     def forward(self, latents: Tensor, timestep: Tensor, cond_state: Optional[Tensor] = None) -> Tensor:
-        if cond_state is not None:
-            raise ValueError("cond_state is unused by the DownBlock2D/UpBlock2D topology (mvunet.py:122)")
+        # cond_state never reaches a kernel, as in the reference: Variant A has no cross-attention block to feed
+        # (mvunet.py:119), Variant B overwrites it with one zero token (mvunet.py:127-128)
         if latents.dim() != 5:
             raise ValueError("latents must be [batch, view, channel, height, width]")
         if not latents.is_cuda:

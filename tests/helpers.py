@@ -107,7 +107,8 @@ def pack_qkv(q, k, v, heads, dpad):
     for t, x in enumerate((q, k, v)):
         xs = x.reshape(B * N, heads, d)
         out.view(B * N, 3, heads, dpad)[:, t, :, :d] = xs
-    out.view(B * N, 3, heads, dpad)[:, 2, :, d] = 1.0     # V's ones column: row sums come out of P.V (include/mvldm_b200.h)
+    if d < dpad:
+        out.view(B * N, 3, heads, dpad)[:, 2, :, d] = 1.0     # V's ones column: row sums come out of P.V (include/mvldm_b200.h)
     return out.to(torch.bfloat16)
 
 

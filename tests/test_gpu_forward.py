@@ -233,3 +233,35 @@ def test_anchored_sampling_batched_equals_sequential(gpu_models):
         k = torch.cat([intr[:, :1], intr[:, 1 + a:2 + a], intr[:, [1 + t for t in tg]]], dim=1)
         ref = path.sample(c, noise[:, tg], e, k)
         assert rel_err(lat[:, tg], ref) < FWD_TOL
+
+
+@pytest.mark.parametrize("impl", [pytest.param(0, id="tcgen05"), pytest.param(1, id="simt")])
+def test_variant_b_forward_matches_reference(impl):
+    """`pretrained_from` set (SD-2.1 topology): per-view Transformer2DModels after the resnets of
+    down blocks 0-2 and inside the mid block; golden g6 is the reference module's own output."""
+    cfg_b = O.OracleCfg(variant_b=True)
+    sd = O.init_weights(cfg_b, seed=0)
+    g = np.load(os.path.join(GOLD, "g6_forward_variant_b_v4.npz"))
+    inp, ts, ref = torch.tensor(g["inputs"]), torch.tensor(g["timesteps"]), torch.tensor(g["eps"])
+    cfg = mv.default_cfg()
+    cfg.pretrained_from = "stabilityai/stable-diffusion-2-1"
+    m = mv.MultiViewUNet(cfg, 11, 4, impl=impl, use_cuda_graph=(impl == 0))
+    m.load_state_dict(sd)                          # strict: all 920 keys, the never-run up-block attentions included
+    m = m.cuda().eval()
+    y = m(inp.cuda(), ts.cuda(), cond_state=torch.ones(1, 1, 1, device="cuda")).cpu()   # cond_state is ignored (mvunet.py:127)
+    drift = _oracle_bf16_drift(sd, cfg_b, inp, ts, ref)
+    err = rel_err(y, ref)
+    print(f"variant B impl={impl}: err {err:.3e}  reference-bf16-autocast drift {drift:.3e}  launches {m.last_launch_count()}")
+    assert err < max(2 * drift, FWD_TOL)
+    assert rms_err(y, ref) < max(2 * drift, FWD_TOL)
+    if impl == 0:
+        assert torch.equal(m(inp.cuda(), ts.cuda()).cpu(), y)      # graph replay is bit-stable
+        # the cross-attention really is a constant: perturbing attn2's q/k/v/norm2 cannot change the output
+        sd2 = dict(sd)
+        for k in sd:
+            if ".attn2.to_" in k and "to_out" not in k or k.endswith("transformer_blocks.0.norm2.weight"):
+                if k.startswith("unet."):
+                    sd2[k] = sd[k] * 1.5 + 0.1
+        with torch.no_grad():
+            y2 = O.unet_forward(sd2, inp, ts, cfg_b)
+        assert rel_err(y2, ref) < 1e-5

@@ -190,6 +190,21 @@ def test_attention(impl, B, N, d):
     assert rel_err(got[..., :d].reshape(B, N, C), ref) < BF16_TOL
 
 
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("B,N,heads", [(4, 1024, 5), (2, 256, 10), (3, 64, 20), (1, 200, 5)])
+def test_attention_unpadded_64_wide_heads(impl, B, N, heads):
+    """Variant B's Transformer2DModel heads: d == dpad == 64, no pad column for the tensor-core row sum, heads != 8"""
+    torch.manual_seed(B + N + heads)
+    d = dpad = 64
+    C = heads * d
+    q, k, v = (torch.randn(B, N, C) for _ in range(3))
+    qkv = pack_qkv(q, k, v, heads, dpad).cuda()
+    out = torch.full((B * N, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(_lib.load().mvldm_op_attention(stream_ptr(), impl, qkv.data_ptr(), out.data_ptr(), B, N, heads, d, dpad))
+    r = lambda t: t.to(torch.bfloat16).float()  # noqa: E731
+    assert rel_err(out.float().cpu().view(B, N, C), attention_ref(r(q), r(k), r(v), heads)) < BF16_TOL
+
+
 def test_attention_rerun_bit_stable_with_wide_score_range():
     """large score range -> the lazily moved softmax reference is rescaled often; reruns must still be bit-identical
     (this caught a barrier-phase race in the double-buffered kernel)"""

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     import ctypes
-    assert ctypes.sizeof(_lib.Config) == 4 * (3 + 4 + 6)
+    assert ctypes.sizeof(_lib.Config) == 4 * (3 + 4 + 6 + 1 + 4 + 1)
     assert ctypes.sizeof(_lib.ASeg) == 8 + 6 * 4 + 9 + 9 + 2 + 9 * 4      # ptr, 6 ints, 2x9 int8 (+2 pad), 9 ints
     assert _lib.GemmDesc.seg.offset == 8 and ctypes.sizeof(_lib.GemmDesc) % 8 == 0
 
@@ -53,9 +53,23 @@ def test_state_dict_keys_match_reference_module(oracle_cfg):
     assert "mv_unet" in mv.DENOISER
 
 
-def test_unsupported_configs_raise():
+def test_variant_b_state_dict_keys_match_reference_module():
+    """`pretrained_from` set: the SD-2.1 topology (920 keys; make_golden loads them into the reference strict=True)."""
     cfg = mv.default_cfg()
     cfg.pretrained_from = "stabilityai/stable-diffusion-2-1"
+    m = mv.MultiViewUNet(cfg, 11, 4)
+    sd = m.state_dict()
+    ref = O.param_shapes(O.OracleCfg(variant_b=True))
+    assert set(sd) == set(ref) and len(sd) == 920
+    assert all(tuple(sd[k].shape) == ref[k][0] for k in ref)
+    # only the multi-view blocks' proj_out is zero-initialised, not the Transformer2DModels'
+    assert float(sd["cross_attn_blocks_mid.0.proj_out.weight"].abs().max()) == 0.0
+    assert float(sd["unet.mid_block.attentions.0.proj_out.weight"].abs().max()) > 0.0
+
+
+def test_unsupported_configs_raise():
+    cfg = mv.default_cfg()
+    cfg.pretrained_from = "runwayml/stable-diffusion-v1-5"     # 768-wide context: mvunet.py:127 cannot drive it either
     with pytest.raises(ValueError):
         mv.MultiViewUNet(cfg, 11, 4)
     cfg = mv.default_cfg()
