@@ -1,9 +1,11 @@
 """Benchmark of the MV-LDM denoising hot path (BASELINE.json metric: DDIM denoise steps/s at 8 views, 32x32 latent).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--cfg] [--scenes-per-gpu S] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--cfg [--no-batch-cfg]] [--scenes-per-gpu S] [--variant a|b]
+                    [--impl reference]
 
 One "step" = one `DiffusionWrapper.step` (reference src/model/diffusion_wrapper.py:413-453) for one scene of
-8 views (2 context + 6 target): input concat + denoiser forward (+ a second, unconditional forward with --cfg)
+8 views (2 context + 6 target): input concat + denoiser forward (with --cfg also the unconditional forward over the 6
+target views: by default both run as ONE pass over two scenes of 8 and 6 views, --no-batch-cfg runs them back to back)
 + CFG compose + DDIM update.  N > 1 (launched by torchrun, one rank per GPU): scenes are independent, every
 rank runs its own scene(s) with no data-path collective (weak scaling); value = all ranks' scene-steps / max
 over ranks of the device time.
@@ -37,13 +39,14 @@ METRIC = "ddim_denoise_steps_per_sec_8views_32x32_latent"
 UNIT = "steps/s"
 
 
-def forward_gflop(v: int) -> float:
-    """Variant A, 2*MAC, head dims un-padded: B*(137.9 V + 3.069 V^2) GFLOP per forward."""
-    return 137.9 * v + 3.069 * v * v
+def forward_gflop(v: int, variant: str = "a") -> float:
+    """2*MAC, head dims un-padded: (137.9 V + 3.069 V^2) GFLOP per forward of one scene for Variant A,
+    (168.2 V + 3.069 V^2) for Variant B."""
+    return (137.9 if variant == "a" else 168.2) * v + 3.069 * v * v
 
 
-def step_gflop(use_cfg: bool) -> float:
-    return forward_gflop(V_C + V_T) + (forward_gflop(V_T) if use_cfg else 0.0)
+def step_gflop(use_cfg: bool, variant: str = "a") -> float:
+    return forward_gflop(V_C + V_T, variant) + (forward_gflop(V_T, variant) if use_cfg else 0.0)
 
 
 def load_peaks():
@@ -102,10 +105,10 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle on the host cores
 # ------------------------------------------------------------------------------------------------------
-def cpu_steps_per_sec(steps: int, warmup: int, use_cfg: bool):
+def cpu_steps_per_sec(steps: int, warmup: int, use_cfg: bool, variant: str = "a"):
     from oracle import mvldm_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    cfg = O.OracleCfg()
+    cfg = O.OracleCfg(variant_b=(variant == "b"))
     sd = O.init_weights(cfg, 0)
     ctx, x_t, extr, intr = O.synthetic_scene(1, V_C, V_T)
     sched = O.DDIMOracle()
@@ -129,7 +132,7 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))   # bounded: ~1-2 s per CPU step
-    v, ms, cores = cpu_steps_per_sec(steps, warmup, args.cfg)
+    v, ms, cores = cpu_steps_per_sec(steps, warmup, args.cfg, args.variant)
     sample = f"{steps} DDIM steps (of {args.steps} requested; bounded for CPU), 1 scene x 8 views, fp32, torch-CPU oracle"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
@@ -143,8 +146,10 @@ def run_reference(args):
 
 
 def workload_name(args):
+    model = "Variant-A MultiViewUNet (764M params)" if args.variant == "a" else \
+        "Variant-B (SD-2.1 topology) MultiViewUNet (1069M params)"
     return (f"25-step DDIM sampling, {args.scenes_per_gpu} scene(s)/GPU x 8 views (2 context + 6 target) at 256x256 "
-            f"(32x32x4 latent), Variant-A MultiViewUNet (764M params), {'CFG 3.0 (2 forwards/step)' if args.cfg else 'no CFG (1 forward/step)'}")
+            f"(32x32x4 latent), {model}, {'CFG 3.0 (cond 8 views + uncond 6 views per step)' if args.cfg else 'no CFG (1 forward/step)'}")
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -153,7 +158,7 @@ def workload_name(args):
 def run_gpu(args):
     import torch.distributed as dist
     import mvldm_b200 as mv
-    from oracle import mvldm_oracle as O     # only for the seeded synthetic weights/scene and the cpu_baseline leg
+    from mvldm_b200 import synthetic
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -171,15 +176,17 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     S = args.scenes_per_gpu
-    cfg = O.OracleCfg()
-    m = mv.MultiViewUNet(mv.default_cfg(), cfg.in_channels, cfg.out_channels, use_cuda_graph=not args.no_graph)
-    m.load_state_dict(O.init_weights(cfg, 0))
+    mcfg = mv.default_cfg()
+    if args.variant == "b":
+        mcfg.pretrained_from = "stabilityai/stable-diffusion-2-1"      # topology only: no hub, random init
+    m = mv.MultiViewUNet(mcfg, 11, 4, use_cuda_graph=not args.no_graph)
+    synthetic.randomise_weights(m, seed=0)
     m = m.to(dev).eval()
     sched = mv.DDIMScheduler(clip_sample=False)
-    path = mv.DenoisingPath(m, sched, use_cfg=args.cfg, cfg_scale=3.0)
+    path = mv.DenoisingPath(m, sched, use_cfg=args.cfg, cfg_scale=3.0, batch_cfg=not args.no_batch_cfg)
     path.set_timesteps(NUM_DDIM_STEPS)
     ts_list = [int(t) for t in sched.timesteps]
-    ctx, x_T, extr, intr = O.synthetic_scene(S, V_C, V_T, seed=1 + rank)
+    ctx, x_T, extr, intr = synthetic.scene(S, V_C, V_T, seed=1 + rank)
     ctx_in = torch.cat([ctx, torch.zeros(S, V_C, 1, H, W)], 2)
     rays = mv.ray_encode(extr.to(dev), intr.to(dev), H, W)
     d_ctx, d_x = ctx_in.to(dev), x_T.to(dev)
@@ -188,7 +195,9 @@ def run_gpu(args):
     x = d_x
     for i in range(args.warmup):
         x = path.step(m, x, ts_list[i % NUM_DDIM_STEPS], d_ctx, rays)
-    launches_per_step = m.last_launch_count() * (2 if args.cfg else 1) + (2 if args.cfg else 1) + 1
+    # kernels of this library per step: forward(s) + one input-concat kernel per pass + the fused CFG/DDIM update
+    n_fwd = 2 if (args.cfg and args.no_batch_cfg) else 1
+    launches_per_step = m.last_launch_count() * n_fwd + (2 if args.cfg else 1) + 1
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
@@ -258,14 +267,14 @@ def run_gpu(args):
 
     if rank == 0:
         peaks = load_peaks()
-        gf = step_gflop(args.cfg) * S
+        gf = step_gflop(args.cfg, args.variant) * S
         step_tf = gf * args.steps / (ms * 1e-3) / 1e3
         conv = prof["gemm_conv3x3"]
         lin = prof["gemm_linear"]
         att = prof["attention_joint"]
         tf = lambda c: c["gflop"] / c["us"]  # noqa: E731  (GFLOP / us = PFLOP/s; x1e3 below -> TFLOP/s)
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM): the conv3x3 launches of one forward "
-                                             f"({conv['launches']} launches, {conv['gflop']:.0f} of {forward_gflop(V_C + V_T) * S:.0f} GFLOP)",
+                                             f"({conv['launches']} launches, {conv['gflop']:.0f} of {forward_gflop(V_C + V_T, args.variant) * S:.0f} GFLOP)",
                 "achieved": tf(conv) * 1e3, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": tf(conv) * 1e3 / peaks["bf16_tflops"], "traffic": None,
                 "how": ("algorithmic FLOPs (2*M*N*K, un-padded) of the launches / sum of their durations; every launch is "
@@ -279,7 +288,7 @@ def run_gpu(args):
         cpu = None
         if not args.no_cpu_baseline:
             n = 3
-            v, s_per, cores = cpu_steps_per_sec(n, 1, args.cfg)
+            v, s_per, cores = cpu_steps_per_sec(n, 1, args.cfg, args.variant)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{n} DDIM steps after 1 warm-up, 1 scene x 8 views, fp32 torch-CPU oracle ({s_per:.2f} s/step)"}
         print(json.dumps({
@@ -287,7 +296,8 @@ def run_gpu(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(args), "views": V_C + V_T, "latent": [H, W], "use_cfg": args.cfg,
-                       "scenes_per_gpu": S, "cuda_graph": not args.no_graph,
+                       "scenes_per_gpu": S, "cuda_graph": not args.no_graph, "variant": args.variant,
+                       "cfg_one_pass": bool(args.cfg and not args.no_batch_cfg),
                        "l2_policy": "inputs larger than L2: 1.53 GB of bf16 weights are streamed every step (L2 = 126 MB)",
                        "weights": "random-init, seed 0, proj_out re-randomised (SURVEY.md §0.5)"},
             "clocks": clocks,
@@ -308,6 +318,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cfg", action="store_true", help="classifier-free guidance: second forward over the target views")
     ap.add_argument("--scenes-per-gpu", type=int, default=1)
+    ap.add_argument("--no-batch-cfg", action="store_true", help="with --cfg: two back-to-back forwards instead of one pass")
+    ap.add_argument("--variant", default="a", choices=["a", "b"], help="a: pretrained_from=None topology (headline); "
+                    "b: SD-2.1 topology with per-view Transformer2D blocks")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -83,6 +83,14 @@ int64_t mvldm_workspace_bytes(mvldm_handle h, int B, int V, int H, int W);
  * [B,V,out_channels,H,W]. */
 int mvldm_forward(mvldm_handle h, void* stream, const float* latents, const int64_t* timesteps, int B, int V,
                   int H, int W, float* out);
+/* Several scenes with DIFFERENT view counts in one pass: `latents` is [sum(views_per_scene), C_in, H, W] with the
+ * views of a scene contiguous, `timesteps` one int64 per view.  Only the joint attention looks across views, and it
+ * runs per scene; everything else is per view.  This is how one DDIM step with classifier-free guidance becomes ONE
+ * forward: the conditional pass (v_c + v_t views, diffusion_wrapper.py:429-435) and the unconditional pass (v_t views,
+ * :437-441) of every scene go through the network together. */
+int mvldm_forward_scenes(mvldm_handle h, void* stream, const float* latents, const int64_t* timesteps, int num_scenes,
+                         const int32_t* views_per_scene, int H, int W, float* out);
+
 /* View-group sharding: a scene whose views are split over several GPUs.  This rank holds V_local
  * contiguous views of ONE scene (B = 1) out of V_total; every op is per view except the joint multi-view
  * attention, which needs all views' K and V.  At each of the 9 multi-view blocks the library packs the local K|V

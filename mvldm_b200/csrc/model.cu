@@ -92,7 +92,8 @@ struct Arena {
 };
 
 struct Plan {
-  int B = 0, V = 0, H = 0, W = 0;
+  std::vector<int> scene_views;  // views per scene; images of a scene are contiguous
+  int H = 0, W = 0;
   DevBuf arena_mem;
   size_t arena_bytes = 0;
   DevBuf in_latents, in_t, out_eps, splitk;
@@ -655,7 +656,26 @@ struct mvldm_handle_s {
     return out;
   }
 
-  Act mv_block(const MvW& m, const Act& x, int B, int V) {
+  // joint attention per scene; runs of scenes with the same view count share one launch (uniform batches: one launch)
+  void joint_attention(const Act& qkv, const Act& o, const MvW& m) {
+    const int hw = qkv.h * qkv.w;
+    size_t i = 0;
+    int img0 = 0;
+    while (i < scene_views.size()) {
+      size_t j = i;
+      while (j < scene_views.size() && scene_views[j] == scene_views[i]) ++j;
+      const int V = scene_views[i], cnt = (int)(j - i);
+      Act q = qkv, oo = o;
+      q.p = qkv.p + (size_t)img0 * hw * qkv.c;
+      oo.p = o.p + (size_t)img0 * hw * o.c;
+      q.n = oo.n = cnt * V;
+      attn(q, oo, cnt, V * hw, m);
+      img0 += cnt * V;
+      i = j;
+    }
+  }
+
+  Act mv_block(const MvW& m, const Act& x) {
     const int n = x.n, h = x.h, w = x.w, C = m.c, H = m.heads;
     const int hw = h * w;
     Act out = new_act(n, h, w, C);
@@ -670,15 +690,15 @@ struct mvldm_handle_s {
     // joint attention over all V*h*w tokens of a scene ("(b f) l c -> b (f l) c")
     ln(t, m.ln_g[0], m.ln_b[0], nrm);
     gemm({seg_1x1(nrm)}, m.qkv1, qkv, nullptr, 0, nullptr, 0, 6.0 * (double)t.tokens() * C * C);
-    if (sharded) joint_attention_sharded(qkv, o, V * hw, m);
-    else attn(qkv, o, B, V * hw, m);
+    if (sharded) joint_attention_sharded(qkv, o, scene_views[0] * hw, m);
+    else joint_attention(qkv, o, m);
     Act t2 = new_act(n, h, w, C);
     gemm({seg_1x1(o)}, m.out1, t2, nullptr, 0, &t, 0, 2.0 * (double)t.tokens() * C * C);
     tap(m.key + ".attn1", t2);
     // per-view attention
     ln(t2, m.ln_g[1], m.ln_b[1], nrm);
     gemm({seg_1x1(nrm)}, m.qkv2, qkv, nullptr, 0, nullptr, 0, 6.0 * (double)t.tokens() * C * C);
-    attn(qkv, o, B * V, hw, m);
+    attn(qkv, o, n, hw, m);
     Act t3 = new_act(n, h, w, C);
     gemm({seg_1x1(o)}, m.out2, t3, nullptr, 0, &t2, 0, 2.0 * (double)t.tokens() * C * C);
     tap(m.key + ".attn2", t3);
@@ -721,8 +741,16 @@ struct mvldm_handle_s {
     return out;
   }
 
-  void run(const float* latents, const int64_t* tsteps, int B, int V, int Hh, int Ww, float* out_eps) {
-    const int L = cfg.num_levels, n = B * V;
+  std::vector<int> scene_views;  // of the forward being recorded / run
+  static int total_views(const std::vector<int>& sv) {
+    int n = 0;
+    for (int v : sv) n += v;
+    return n;
+  }
+
+  void run(const float* latents, const int64_t* tsteps, const std::vector<int>& sv, int Hh, int Ww, float* out_eps) {
+    scene_views = sv;
+    const int L = cfg.num_levels, n = total_views(sv);
     const int* boc = cfg.block_out_channels;
     arena.off = 0;
     // ---- time embedding (K2): sinusoid -> linear -> SiLU -> linear -> SiLU -> all 21 time_emb_proj at once
@@ -757,7 +785,7 @@ struct mvldm_handle_s {
         skips.push_back(x);
       }
       if (x.h <= cfg.max_attn_res && x.w <= cfg.max_attn_res) {
-        x = mv_block(mv_enc[l], x, B, V);
+        x = mv_block(mv_enc[l], x);
         tap("down" + std::to_string(l) + ".mv", x);
       }
       if (l != L - 1) {
@@ -775,7 +803,7 @@ struct mvldm_handle_s {
       x = resnet(mid_res1, x, nullptr, temb);
     }
     tap("mid.res0", x);
-    x = mv_block(mv_mid, x, B, V);
+    x = mv_block(mv_mid, x);
     tap("mid.mv", x);
     // ---- up
     for (int l = 0; l < L; ++l) {
@@ -786,7 +814,7 @@ struct mvldm_handle_s {
         tap("up" + std::to_string(l) + ".res" + std::to_string(i), x);
       }
       if (x.h <= cfg.max_attn_res && x.w <= cfg.max_attn_res) {
-        x = mv_block(mv_dec[l], x, B, V);
+        x = mv_block(mv_dec[l], x);
         tap("up" + std::to_string(l) + ".mv", x);
       }
       if (l != L - 1) {
@@ -814,35 +842,40 @@ struct mvldm_handle_s {
     run_gemm(d, 2.0 * (double)x.tokens() * cfg.out_channels * conv_out.k);
   }
 
-  Plan& plan_for(int B, int V, int H, int W) {
-    std::vector<int> key{B, V, H, W, taps_enabled ? 1 : 0};
+  Plan& plan_for(const std::vector<int>& sv, int H, int W) {
+    std::vector<int> key{H, W, taps_enabled ? 1 : 0};
+    key.insert(key.end(), sv.begin(), sv.end());
+    const int n = total_views(sv);
     auto it = plans.find(key);
     if (it != plans.end()) return *it->second;
     std::unique_ptr<Plan> p(new Plan());
-    p->B = B; p->V = V; p->H = H; p->W = W;
+    p->scene_views = sv; p->H = H; p->W = W;
     dry = true;
     arena = Arena();
     arena.measuring = true;
     splitk_need = 0;
-    run(nullptr, nullptr, B, V, H, W, nullptr);
+    run(nullptr, nullptr, sv, H, W, nullptr);
     p->arena_bytes = arena.peak;
     p->arena_mem.alloc(p->arena_bytes);
     p->splitk.alloc(splitk_need);
     if (splitk_need) MV_CUDA(cudaMemset(p->splitk.p, 0, splitk_need));  // fused split-K counters start (and end) at zero
-    p->in_latents.alloc((size_t)B * V * cfg.in_channels * H * W * sizeof(float));
-    p->in_t.alloc((size_t)B * V * sizeof(int64_t));
-    p->out_eps.alloc((size_t)B * V * cfg.out_channels * H * W * sizeof(float));
+    p->in_latents.alloc((size_t)n * cfg.in_channels * H * W * sizeof(float));
+    p->in_t.alloc((size_t)n * sizeof(int64_t));
+    p->out_eps.alloc((size_t)n * cfg.out_channels * H * W * sizeof(float));
     Plan& ref = *p;
     plans[key] = std::move(p);
     return ref;
   }
 
-  void forward(cudaStream_t s, const float* latents, const int64_t* tsteps, int B, int V, int H, int W, float* out) {
+  void forward(cudaStream_t s, const float* latents, const int64_t* tsteps, const std::vector<int>& sv, int H, int W,
+               float* out) {
     MV_CHECK(finalized, "mvldm_forward before mvldm_finalize_weights");
-    MV_CHECK(B > 0 && V > 0, "empty batch");
+    MV_CHECK(!sv.empty(), "empty batch");
+    for (int v : sv) MV_CHECK(v > 0, "empty scene");
+    const int n = total_views(sv);
     const int down = 1 << (cfg.num_levels - 1);
     MV_CHECK(H % down == 0 && W % down == 0, "latent size must be divisible by 2^(levels-1)");
-    Plan& p = plan_for(B, V, H, W);
+    Plan& p = plan_for(sv, H, W);
     stream = s;
     arena = Arena();
     arena.measuring = false;
@@ -852,25 +885,25 @@ struct mvldm_handle_s {
     splitk_bytes = p.splitk.bytes;
     dry = false;
     g_launch_count = 0;
-    const size_t in_bytes = (size_t)B * V * cfg.in_channels * H * W * sizeof(float);
-    const size_t out_bytes = (size_t)B * V * cfg.out_channels * H * W * sizeof(float);
+    const size_t in_bytes = (size_t)n * cfg.in_channels * H * W * sizeof(float);
+    const size_t out_bytes = (size_t)n * cfg.out_channels * H * W * sizeof(float);
     const bool graph = cfg.use_cuda_graph && !taps_enabled && !profiling;
     if (!graph) {
       taps.clear();
       prof.clear();
       events_used = 0;
-      run(latents, tsteps, B, V, H, W, out);
+      run(latents, tsteps, sv, H, W, out);
       last_launches = g_launch_count;
       return;
     }
     // graph path: stage through fixed buffers so the captured pointers stay valid for any caller tensors
     MV_CUDA(cudaMemcpyAsync(p.in_latents.p, latents, in_bytes, cudaMemcpyDeviceToDevice, s));
-    MV_CUDA(cudaMemcpyAsync(p.in_t.p, tsteps, (size_t)B * V * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    MV_CUDA(cudaMemcpyAsync(p.in_t.p, tsteps, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
     if (!p.graph) {
       cudaStreamCaptureStatus st;
       MV_CUDA(cudaStreamIsCapturing(s, &st));
       if (st != cudaStreamCaptureStatusNone) {  // caller is already capturing: just record into their graph
-        run((const float*)p.in_latents.p, (const int64_t*)p.in_t.p, B, V, H, W, (float*)p.out_eps.p);
+        run((const float*)p.in_latents.p, (const int64_t*)p.in_t.p, sv, H, W, (float*)p.out_eps.p);
         last_launches = g_launch_count;
         MV_CUDA(cudaMemcpyAsync(out, p.out_eps.p, out_bytes, cudaMemcpyDeviceToDevice, s));
         return;
@@ -880,7 +913,7 @@ struct mvldm_handle_s {
       stream = capture_stream;
       MV_CUDA(cudaStreamBeginCapture(capture_stream, cudaStreamCaptureModeThreadLocal));
       try {
-        run((const float*)p.in_latents.p, (const int64_t*)p.in_t.p, B, V, H, W, (float*)p.out_eps.p);
+        run((const float*)p.in_latents.p, (const int64_t*)p.in_t.p, sv, H, W, (float*)p.out_eps.p);
       } catch (...) {
         cudaStreamEndCapture(capture_stream, &g);
         if (g) cudaGraphDestroy(g);
@@ -1041,7 +1074,8 @@ int mvldm_finalize_weights(mvldm_handle h, void* stream) {
 int64_t mvldm_workspace_bytes(mvldm_handle h, int B, int V, int H, int W) {
   try {
     MV_CHECK(h && h->finalized, "finalize weights first");
-    return (int64_t)h->plan_for(B, V, H, W).arena_bytes;
+    MV_CHECK(B > 0 && V > 0, "empty batch");
+    return (int64_t)h->plan_for(std::vector<int>(B, V), H, W).arena_bytes;
   } catch (const std::exception& e) {
     mvldm::g_last_error = e.what();
     return -1;
@@ -1053,7 +1087,19 @@ int mvldm_forward(mvldm_handle h, void* stream, const float* latents, const int6
   MV_API_BEGIN
   MV_CHECK(h && latents && timesteps && out, "null argument");
   MV_CUDA(cudaSetDevice(h->device));
-  h->forward((cudaStream_t)stream, latents, timesteps, B, V, H, W, out);
+  MV_CHECK(B > 0 && V > 0, "empty batch");
+  h->forward((cudaStream_t)stream, latents, timesteps, std::vector<int>(B, V), H, W, out);
+  MV_API_END
+}
+
+int mvldm_forward_scenes(mvldm_handle h, void* stream, const float* latents, const int64_t* timesteps, int num_scenes,
+                         const int32_t* views_per_scene, int H, int W, float* out) {
+  MV_API_BEGIN
+  MV_CHECK(h && latents && timesteps && out && views_per_scene, "null argument");
+  MV_CHECK(num_scenes > 0 && num_scenes <= 4096, "num_scenes out of range");
+  MV_CUDA(cudaSetDevice(h->device));
+  h->forward((cudaStream_t)stream, latents, timesteps, std::vector<int>(views_per_scene, views_per_scene + num_scenes), H, W,
+             out);
   MV_API_END
 }
 
@@ -1066,7 +1112,7 @@ int mvldm_forward_sharded(mvldm_handle h, void* stream, const float* latents, co
   MV_CHECK(h->cfg.impl == MVLDM_IMPL_TC, "view-group sharding needs the tcgen05 kernels");
   MV_CHECK(V_local > 0 && V_total % V_local == 0, "V_total must be a multiple of V_local (equal view groups)");
   MV_CUDA(cudaSetDevice(h->device));
-  Plan& p = h->plan_for(1, V_local, H, W);
+  Plan& p = h->plan_for(std::vector<int>{V_local}, H, W);
   h->stream = (cudaStream_t)stream;
   h->arena = Arena();
   h->arena.measuring = false;
@@ -1084,7 +1130,7 @@ int mvldm_forward_sharded(mvldm_handle h, void* stream, const float* latents, co
   h->exchange_user = user;
   g_launch_count = 0;
   try {
-    h->run(latents, timesteps, 1, V_local, H, W, out);
+    h->run(latents, timesteps, std::vector<int>{V_local}, H, W, out);
   } catch (...) {
     h->sharded = false;
     throw;

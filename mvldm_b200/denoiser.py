@@ -373,6 +373,33 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
         return out
 
     @torch.no_grad()
+    def forward_scenes(self, latents: Tensor, timestep: Tensor, views_per_scene) -> Tensor:
+        """Scenes with different view counts in one pass (``mvldm_forward_scenes``): ``latents`` [N, C, h, w] with the
+        views of a scene contiguous, ``timestep`` int64 [N], ``sum(views_per_scene) == N``.  Returns [N, C_out, h, w].
+        Used by ``DenoisingPath.step`` to run the conditional and the unconditional pass of CFG as one forward."""
+        if latents.dim() != 4:
+            raise ValueError("latents must be [view, channel, height, width]")
+        if not latents.is_cuda:
+            raise RuntimeError("mvldm_b200: inputs must be CUDA tensors (no CPU fallback)")
+        n, c, h, w = latents.shape
+        views = [int(v) for v in views_per_scene]
+        if sum(views) != n or min(views) < 1:
+            raise ValueError("views_per_scene must be positive and sum to the number of views")
+        if c != self.in_channels:
+            raise ValueError(f"expected {self.in_channels} input channels, got {c}")
+        if timestep.dtype != torch.int64 or timestep.numel() != n:
+            raise TypeError("timestep must be int64, one per view")
+        self.refresh_weights(force=False)
+        t = timestep.to(latents.device).reshape(-1).contiguous()
+        lat = latents.detach().to(torch.float32).contiguous()
+        out = torch.empty((n, self.out_channels, h, w), device=latents.device, dtype=torch.float32)
+        vp = (ctypes.c_int32 * len(views))(*views)
+        with torch.cuda.device(latents.device):
+            _lib.check(_lib.load().mvldm_forward_scenes(self._h.ptr, _lib.current_stream_ptr(latents.device), lat.data_ptr(),
+                                                        t.data_ptr(), len(views), vp, h, w, out.data_ptr()))
+        return out
+
+    @torch.no_grad()
     def forward_view_sharded(self, latents: Tensor, timestep: Tensor, v_total: int, exchange) -> Tensor:
         """View-group sharded forward: `latents` [1, V_local, C, h, w] are THIS rank's contiguous views of one scene of
         `v_total` views; `exchange` is a `ViewGroupExchange`.  Returns this rank's [1, V_local, C_out, h, w]."""

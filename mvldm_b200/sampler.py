@@ -32,12 +32,17 @@ def ray_encode(extrinsics: Tensor, intrinsics: Tensor, h: int, w: int, use_pluck
     return out
 
 
-def build_inputs(x_t: Tensor, context_latents: Optional[Tensor], rays: Tensor, ray_view_offset: int = 0) -> Tensor:
-    """[latent | mask | rays] per view, context views first (diffusion_wrapper.py:429-432 / :438)."""
+def build_inputs(x_t: Tensor, context_latents: Optional[Tensor], rays: Tensor, ray_view_offset: int = 0,
+                 out: Optional[Tensor] = None) -> Tensor:
+    """[latent | mask | rays] per view, context views first (diffusion_wrapper.py:429-432 / :438).  ``out``: an optional
+    contiguous fp32 destination of B*(v_c+v_t) views (e.g. a slice of a larger batch)."""
     B, v_t, _, h, w = x_t.shape
     v_c = 0 if context_latents is None else context_latents.shape[1]
     R = rays.shape[2]
-    out = torch.empty((B, v_c + v_t, 5 + R, h, w), device=x_t.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((B, v_c + v_t, 5 + R, h, w), device=x_t.device, dtype=torch.float32)
+    elif out.numel() != B * (v_c + v_t) * (5 + R) * h * w or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("build_inputs: `out` must be a contiguous fp32 buffer of B*(v_c+v_t) views")
     x = x_t.detach().to(torch.float32).contiguous()
     c = context_latents.detach().to(torch.float32).contiguous() if v_c else None
     r = rays.detach().to(torch.float32).contiguous()
@@ -52,9 +57,12 @@ class DenoisingPath:
     """``step`` / ``sample`` of the reference wrapper with the same knobs (use_cfg, cfg_scale, use_plucker)."""
 
     def __init__(self, denoiser, scheduler: DDIMScheduler, use_cfg: bool = False, cfg_scale: float = 3.0,
-                 use_plucker: bool = False):
+                 use_plucker: bool = False, batch_cfg: bool = True):
+        """``batch_cfg``: run the conditional (v_c + v_t views) and unconditional (v_t views) forwards of a CFG step as
+        ONE pass over 2B scenes of unequal view counts (``forward_scenes``) instead of two back-to-back forwards."""
         self.denoiser, self.scheduler = denoiser, scheduler
         self.use_cfg, self.cfg_scale, self.use_plucker = use_cfg, cfg_scale, use_plucker
+        self.batch_cfg = batch_cfg
         self._t_cache = {}     # (B, v_c, v_t, ts, device) -> (timesteps [B, v_c+v_t], target timesteps [B, v_t])
 
     def set_timesteps(self, num: int) -> None:
@@ -74,6 +82,19 @@ class DenoisingPath:
             t_t = torch.full((B, v_t), ts, dtype=torch.long, device=dev)
             self._t_cache[key] = (torch.cat([torch.zeros((B, v_c), dtype=torch.long, device=dev), t_t], dim=1), t_t)
         t_all, t_t = self._t_cache[key]
+        if self.use_cfg and self.batch_cfg and hasattr(model, "forward_scenes"):
+            h, w = x_t.shape[-2:]
+            V, R = v_c + v_t, ray_encodings.shape[2]
+            kb = ("cfg", B, v_c, v_t, ts, dev)
+            if kb not in self._t_cache:
+                self._t_cache[kb] = torch.cat([t_all.reshape(-1), t_t.reshape(-1)])
+            buf = torch.empty((B * (V + v_t), 5 + R, h, w), device=dev, dtype=torch.float32)
+            build_inputs(x_in, context_inputs[:, :, :4], ray_encodings, out=buf[:B * V])
+            build_inputs(x_in, None, ray_encodings, ray_view_offset=v_c, out=buf[B * V:])
+            pred = model.forward_scenes(buf, self._t_cache[kb], [V] * B + [v_t] * B)
+            pred_c = pred[:B * V].view(B, V, -1, h, w)
+            pred_u = pred[B * V:].view(B, v_t, -1, h, w)
+            return fused_cfg_ddim_step(self.scheduler, pred_c, pred_u, self.cfg_scale, v_c, ts, x_t)
         inputs = build_inputs(x_in, context_inputs[:, :, :4], ray_encodings)
         pred_c = model.forward(inputs, t_all)
         pred_u = None

@@ -1,11 +1,12 @@
-"""Exploratory on-GPU check: prints error metrics of every kernel against torch-fp32 / the oracle.
-(Development aid; the asserted versions of these checks live in tests/.)"""
+"""Exploratory on-GPU check (run as a script: `python tests/gpu_check.py`): prints error metrics of every kernel against
+torch-fp32 / the oracle.  Development aid; the asserted versions of these checks are the test_gpu_*.py files.  Lives under
+tests/ because it uses the oracle as its checker."""
 import sys, os, time, ctypes, traceback
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 import torch.nn.functional as F
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from helpers import *  # noqa
 from mvldm_b200 import _lib
 import mvldm_b200 as mv

@@ -265,3 +265,49 @@ def test_variant_b_forward_matches_reference(impl):
         with torch.no_grad():
             y2 = O.unet_forward(sd2, inp, ts, cfg_b)
         assert rel_err(y2, ref) < 1e-5
+
+
+def test_forward_scenes_unequal_view_counts(gpu_models):
+    """mvldm_forward_scenes: scenes of 3, 5 and 3 views in one pass == each scene through the uniform entry point
+    (within the bf16 band: split-K schedules depend on the tile count), reruns bit-identical, bad arguments raise."""
+    m = gpu_models(0, True)
+    torch.manual_seed(21)
+    views = [3, 5, 3]
+    x = torch.randn(sum(views), 11, 32, 32, device="cuda")
+    t = torch.randint(0, 1000, (sum(views),), device="cuda")
+    y = m.forward_scenes(x, t, views)
+    assert torch.equal(y, m.forward_scenes(x, t, views))
+    o = 0
+    for v in views:
+        ref = m(x[o:o + v][None], t[o:o + v][None])[0]
+        assert rel_err(y[o:o + v], ref) < FWD_TOL
+        o += v
+    # a scene's result must not depend on its neighbours: same first scene, different others
+    x2 = x.clone()
+    x2[3:] = torch.randn_like(x2[3:])
+    assert rel_err(m.forward_scenes(x2, t, views)[:3], y[:3]) < 1e-6
+    # uniform counts through the scenes entry == the [B, V] entry, bit for bit (same launches)
+    xu, tu = torch.randn(2, 4, 11, 32, 32, device="cuda"), torch.randint(0, 1000, (2, 4), device="cuda")
+    assert torch.equal(m.forward_scenes(xu.flatten(0, 1), tu.flatten(), [4, 4]), m(xu, tu).flatten(0, 1))
+    with pytest.raises(ValueError):
+        m.forward_scenes(x, t, [3, 5])
+    with pytest.raises(ValueError):
+        m.forward_scenes(x, t, [11, 0])
+
+
+def test_cfg_step_batched_equals_two_forwards(gpu_models):
+    """One CFG step as ONE pass over [cond: 2+6 views | uncond: 6 views] vs the reference's two forwards."""
+    m = gpu_models(0, True)
+    g = np.load(os.path.join(GOLD, "g3_traj25_cfg1.npz"))
+    ctx, x_T = torch.tensor(g["context_latents"]).cuda(), torch.tensor(g["x_T"]).cuda()
+    extr, intr = torch.tensor(g["extr"]).cuda(), torch.tensor(g["intr"]).cuda()
+    rays = mv.ray_encode(extr, intr, 32, 32)
+    cin = torch.cat([ctx, torch.zeros_like(ctx[:, :, :1])], 2)
+    outs = []
+    for batched in (True, False):
+        sched = mv.DDIMScheduler(clip_sample=False)
+        path = mv.DenoisingPath(m, sched, use_cfg=True, cfg_scale=3.0, batch_cfg=batched)
+        path.set_timesteps(25)
+        outs.append(path.step(m, x_T, 960, cin, rays))
+    assert rel_err(outs[0], outs[1]) < FWD_TOL
+    assert rel_err(outs[0], torch.tensor(g["x_after_step0"]).cuda()) < FWD_TOL

@@ -5,7 +5,7 @@ import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import mvldm_b200 as mv
-from oracle import mvldm_oracle as O
+from mvldm_b200 import synthetic
 
 
 def profile_forward(m, x, t, reps=3):
@@ -26,9 +26,8 @@ def profile_forward(m, x, t, reps=3):
 if __name__ == "__main__":
     V = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     out = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/profile_forward.json"
-    cfg = O.OracleCfg()
     m = mv.MultiViewUNet(mv.default_cfg(), 11, 4)
-    m.load_state_dict(O.init_weights(cfg, 0))
+    synthetic.randomise_weights(m, 0)
     m = m.cuda().eval()
     x = torch.randn(1, V, 11, 32, 32, device="cuda")
     t = torch.tensor([[0, 0] + [500] * (V - 2)], device="cuda")

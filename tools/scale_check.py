@@ -3,10 +3,9 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import mvldm_b200 as mv
-from oracle import mvldm_oracle as O
-cfg = O.OracleCfg()
+from mvldm_b200 import synthetic
 m = mv.MultiViewUNet(mv.default_cfg(), 11, 4)
-m.load_state_dict(O.init_weights(cfg, 0))
+synthetic.randomise_weights(m, 0)
 m = m.cuda().eval()
 for (B, V) in [(1, 1), (1, 2), (1, 4), (1, 8), (2, 8), (4, 8), (8, 8)]:
     x = torch.randn(B, V, 11, 32, 32, device="cuda")
