@@ -17,7 +17,8 @@ bool g_use_pdl = []() {  // opt-in: measured 2% slower than plain stream order i
 
 namespace {
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// MUFU.EX2 + MUFU.RCP: the IEEE division this replaces was ~10x the instructions of the rest of a GroupNorm element
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 
 struct alignas(16) bf16x8 {
   __nv_bfloat162 v[4];
@@ -532,6 +533,250 @@ __global__ void __launch_bounds__(GNB_THREADS) gn_block_kernel(const bf16* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// GroupNorm, register-resident: one (image, block of CB = 8*NV channels = whole groups) item is owned by `tpi`
+// threads, thread r holding all CB channels of pixels r, r + tpi, ... (P of them) in registers.  Every load is in flight
+// before the first use, the pixel reduction is a shuffle tree plus (tpi > 32) ONE __syncthreads, and the normalised
+// values are written straight from the registers: no staging slab, no second read, no cluster barrier.  Small images
+// pack several items into a CTA (tpi = 16 for the 4x4 level).  Fixed reduction order -> bit-stable.
+// ---------------------------------------------------------------------------------------------
+template <int NV, int P, int CGN>
+__global__ void __launch_bounds__(512) gn_reg_kernel(const bf16* __restrict__ x0, int c0, const bf16* __restrict__ x1,
+                                                     int c1, int hw, float eps, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, int silu, int tpi, int n_items,
+                                                     bf16* __restrict__ out) {
+  constexpr int CB = NV * 8, GB = CB / CGN;
+  static_assert(CB % CGN == 0, "channel block must hold whole groups");
+  __shared__ float red[16][2 * GB];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int C = c0 + c1, nblk = C / CB;
+  const int t = threadIdx.x, ipc = blockDim.x / tpi;
+  const int item = blockIdx.x * ipc + t / tpi, r = t % tpi;
+  const bool live = item < n_items;
+  const int img = live ? item / nblk : 0, ch0 = live ? (item % nblk) * CB : 0;
+  bf16x8 raw[P][NV];
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const int64_t pix = (int64_t)img * hw + r + j * tpi;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = ch0 + v * 8;
+      const bf16* src = c < c0 ? x0 + pix * c0 + c : x1 + pix * c1 + (c - c0);
+      if (live) raw[j][v] = *reinterpret_cast<const bf16x8*>(src);
+      else raw[j][v] = bf16x8{};
+    }
+  }
+  float S[GB], Q[GB];
+#pragma unroll
+  for (int g = 0; g < GB; ++g) S[g] = Q[g] = 0.f;
+#pragma unroll
+  for (int j = 0; j < P; ++j)
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(raw[j][v].v[e]);
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int ga = (v * 8 + 2 * e) / CGN, gbb = (v * 8 + 2 * e + 1) / CGN;  // compile-time after unrolling
+        S[ga] += f.x; Q[ga] = fmaf(f.x, f.x, Q[ga]);
+        S[gbb] += f.y; Q[gbb] = fmaf(f.y, f.y, Q[gbb]);
+      }
+  const int span = tpi < 32 ? tpi : 32;
+#pragma unroll
+  for (int g = 0; g < GB; ++g)
+    for (int o = span >> 1; o > 0; o >>= 1) {
+      S[g] += __shfl_xor_sync(0xffffffffu, S[g], o);
+      Q[g] += __shfl_xor_sync(0xffffffffu, Q[g], o);
+    }
+  if (tpi > 32) {
+    const int warp = t >> 5, lane = t & 31;
+    if (lane == 0) {
+#pragma unroll
+      for (int g = 0; g < GB; ++g) {
+        red[warp][2 * g] = S[g];
+        red[warp][2 * g + 1] = Q[g];
+      }
+    }
+    __syncthreads();
+    const int w0 = (t / tpi) * (tpi >> 5), nw = tpi >> 5;
+#pragma unroll
+    for (int g = 0; g < GB; ++g) {
+      float s = 0.f, q = 0.f;
+      for (int w = 0; w < nw; ++w) {
+        s += red[w0 + w][2 * g];
+        q += red[w0 + w][2 * g + 1];
+      }
+      S[g] = s;
+      Q[g] = q;
+    }
+  }
+  if (!live) return;
+  const float cnt = (float)hw * (float)CGN;
+  float mean[GB], rstd[GB];
+#pragma unroll
+  for (int g = 0; g < GB; ++g) {
+    mean[g] = S[g] / cnt;
+    rstd[g] = rsqrtf(fmaxf(Q[g] / cnt - mean[g] * mean[g], 0.f) + eps);
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c = ch0 + v * 8;
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int g = (v * 8 + e) / CGN;
+      sc[e] = rstd[g] * gg[e];
+      sh[e] = bb[e] - mean[g] * sc[e];
+    }
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 x = __bfloat1622float2(raw[j][v].v[e]);
+        f[2 * e] = x.x;
+        f[2 * e + 1] = x.y;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float y = fmaf(f[e], sc[e], sh[e]);
+        f[e] = silu ? silu_f(y) : y;
+      }
+      store8(out + ((int64_t)img * hw + r + j * tpi) * C + c, f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm, register-resident, coalesced: one CTA per (image, 40-channel block = whole groups).  The block's
+// hw x 5 sixteen-byte vectors are dealt round-robin to T threads (T a multiple of 5, so a thread always sees the same
+// 8 channels and consecutive threads read consecutive vectors), R = hw*5/T vectors per thread, all in flight at once.
+// Per-channel sums stay in registers; each thread folds its 8 channels into the (at most two) groups they belong to,
+// a shuffle tree + one __syncthreads sums over the CTA, and the output is written from the registers.  ~3x fewer
+// instructions per element than the slab kernel, which is what bounds GroupNorm at large batch.
+// ---------------------------------------------------------------------------------------------
+template <int R, int CGN>
+__global__ void __launch_bounds__(320, 3) gn_flat_kernel(const bf16* __restrict__ x0, int c0, const bf16* __restrict__ x1,
+                                                      int c1, int hw, float eps, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, int silu, bf16* __restrict__ out) {
+  namespace cg = cooperative_groups;
+  constexpr int NV = 5, CB = 40, GB = CB / CGN;
+  __shared__ float red[10][2 * GB];
+  __shared__ float part[2 * GB];   // this CTA's sums; peers of the cluster read it through DSMEM
+  __shared__ float stat[2 * GB];
+  pdl_wait();
+  pdl_launch_dependents();
+  cg::cluster_group cluster = cg::this_cluster();   // CS CTAs along x split the pixels of one (image, channel block)
+  const int CS = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
+  const int C = c0 + c1, nblk = C / CB, T = blockDim.x;
+  const int t = threadIdx.x, item = blockIdx.x / CS, img = item / nblk, ch0 = (item % nblk) * CB;
+  const int cv = t % NV, pstep = T / NV;   // vector j of this thread: pixel p0 + j * pstep, channels c..c+7
+  const int p0 = crank * (hw / CS) + t / NV;
+  const int c = ch0 + cv * 8;
+  const bool first = c < c0;
+  const bf16* src = first ? x0 + ((int64_t)img * hw + p0) * c0 + c : x1 + ((int64_t)img * hw + p0) * c1 + (c - c0);
+  const int64_t sstep = (int64_t)pstep * (first ? c0 : c1);
+  bf16x8 raw[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) raw[j] = *reinterpret_cast<const bf16x8*>(src + j * sstep);
+  float sa[8], qa[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sa[e] = qa[e] = 0.f;
+#pragma unroll
+  for (int j = 0; j < R; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __bfloat1622float2(raw[j].v[e]);
+      sa[2 * e] += f.x; qa[2 * e] = fmaf(f.x, f.x, qa[2 * e]);
+      sa[2 * e + 1] += f.y; qa[2 * e + 1] = fmaf(f.y, f.y, qa[2 * e + 1]);
+    }
+  // channels cv*8 .. cv*8+7 -> groups (CGN >= 8: at most two)
+  float S[GB], Q[GB];
+#pragma unroll
+  for (int g = 0; g < GB; ++g) S[g] = Q[g] = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int ge = (cv * 8 + e) / CGN;
+#pragma unroll
+    for (int g = 0; g < GB; ++g)
+      if (ge == g) {
+        S[g] += sa[e];
+        Q[g] += qa[e];
+      }
+  }
+#pragma unroll
+  for (int g = 0; g < GB; ++g)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      S[g] += __shfl_xor_sync(0xffffffffu, S[g], o);
+      Q[g] += __shfl_xor_sync(0xffffffffu, Q[g], o);
+    }
+  const int warp = t >> 5, lane = t & 31, nw = T >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int g = 0; g < GB; ++g) {
+      red[warp][2 * g] = S[g];
+      red[warp][2 * g + 1] = Q[g];
+    }
+  }
+  __syncthreads();
+  if (t < 2 * GB) {
+    float a = 0.f;
+    for (int w = 0; w < nw; ++w) a += red[w][t];
+    part[t] = a;
+    if (CS == 1) stat[t] = a;
+  }
+  if (CS > 1) {
+    cluster.sync();
+    if (t < 2 * GB) {  // rank order: bit-stable
+      float a = 0.f;
+      for (int r = 0; r < CS; ++r) a += cluster.map_shared_rank(&part[0], r)[t];
+      stat[t] = a;
+    }
+    cluster.sync();    // also keeps `part` alive until every peer has read it
+  } else {
+    __syncthreads();
+  }
+  const float cnt = (float)hw * (float)CGN;
+  const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+  const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
+  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int ge = (cv * 8 + e) / CGN;
+    const float mean = stat[2 * ge] / cnt;
+    const float rstd = rsqrtf(fmaxf(stat[2 * ge + 1] / cnt - mean * mean, 0.f) + eps);
+    sc[e] = rstd * gg[e];
+    sh[e] = bb[e] - mean * sc[e];
+  }
+  bf16* dst = out + ((int64_t)img * hw + p0) * C + c;
+  const int64_t dstep = (int64_t)pstep * C;
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 x = __bfloat1622float2(raw[j].v[e]);
+      f[2 * e] = x.x;
+      f[2 * e + 1] = x.y;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float y = fmaf(f[e], sc[e], sh[e]);
+      f[e] = silu ? silu_f(y) : y;
+    }
+    store8(dst + j * dstep, f);
+  }
+}
+
 // LayerNorm over the channel dim, one warp per token, row cached in registers (C <= 32*8*MAXV).
 template <int MAXV>
 __global__ void layernorm_kernel(const bf16* __restrict__ x, int rows, int c, float eps, const float* __restrict__ gamma,
@@ -788,6 +1033,66 @@ void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, i
   const int C = c0 + c1;
   MV_CHECK(C % groups == 0 && groups <= 64, "groupnorm: channels not divisible by groups (<= 64 groups)");
   MV_CHECK(c0 % 8 == 0 && c1 % 8 == 0 && C <= GN_MAXC, "groupnorm: channel counts must be multiples of 8, <= 2560");
+  // ---- register-resident path (the model's 320/640/1280/2560-channel tensors at every resolution) ----
+  {
+    static const bool use_reg = [] {
+      const char* e = getenv("MVLDM_GN_REG");
+      return !e || atoi(e) != 0;
+    }();
+    const int cgn = C / groups;
+    const int P = (cgn <= 40 && hw >= 512) ? 2 : 1;
+    const int tpi = hw % P == 0 ? hw / P : 0;
+    const bool pow2 = tpi >= 16 && tpi <= 512 && (tpi & (tpi - 1)) == 0;
+    static const bool use_flat = [] {
+      const char* e = getenv("MVLDM_GN_FLAT");
+      return !e || atoi(e) != 0;
+    }();
+    if (use_flat && (cgn == 10 || cgn == 20 || cgn == 40) && C % 40 == 0 && hw % 256 == 0 && hw / 256 <= 8) {
+      // 320 threads x 4 vectors = 256 pixels x 40 channels per CTA; larger images are split over a cluster of hw/256 CTAs.
+      // Small CTAs on purpose: ~50 registers x 320 threads lets four of them share an SM, so the load, reduce and store
+      // phases of different CTAs overlap (one 640-thread CTA per SM ran at 1.6 TB/s at 64 images)
+      const int cs = hw / 256;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((C / 40) * n_img * cs, 1, 1);
+      cfg.blockDim = dim3(320, 1, 1);
+      cfg.dynamicSmemBytes = 0;
+      cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = cs > 1 ? 1 : 0;
+      const int sl = silu ? 1 : 0;
+      if (cgn == 10) MV_CUDA(cudaLaunchKernelEx(&cfg, gn_flat_kernel<4, 10>, x0, c0, x1, c1, hw, eps, gamma, beta, sl, out));
+      else if (cgn == 20) MV_CUDA(cudaLaunchKernelEx(&cfg, gn_flat_kernel<4, 20>, x0, c0, x1, c1, hw, eps, gamma, beta, sl, out));
+      else MV_CUDA(cudaLaunchKernelEx(&cfg, gn_flat_kernel<4, 40>, x0, c0, x1, c1, hw, eps, gamma, beta, sl, out));
+      MV_LAUNCHED();
+      return;
+    }
+    // measured in a CUDA-graph chain (tools/gn_graph_bench.py, 8 images): it wins where a tensor is small (us/launch,
+    // this kernel vs the slab kernel: 16 px x 1280 ch 3.9 / 5.9; 64 px x 1280 5.6 / 7.7; 64 px x 640 4.7 / 6.0;
+    // 256 px x 640 9.7 / 11.2) and loses at 1024 px (32 / 12: its 80-byte-per-lane strided loads waste sectors)
+    const bool wins = hw <= 64 || (hw == 256 && cgn == 20);
+    if (use_reg && wins && pow2 && (cgn == 10 || cgn == 20 || cgn == 40 || cgn == 80) && C % (cgn == 80 ? 80 : 40) == 0) {
+      const int cbk = cgn == 80 ? 80 : 40;
+      const int n_items = (C / cbk) * n_img;
+      const int threads = tpi > 64 ? tpi : 64;
+      const int ipc = threads / tpi;
+      const dim3 grid(ceil_div(n_items, ipc)), block(threads);
+      const int sl = silu ? 1 : 0;
+#define GN_REG(NV, PP, CGN) \
+  launch_pdl(gn_reg_kernel<NV, PP, CGN>, grid, block, 0, s, x0, c0, x1, c1, hw, eps, gamma, beta, sl, tpi, n_items, out)
+      if (cgn == 10 && P == 2) GN_REG(5, 2, 10);
+      else if (cgn == 10) GN_REG(5, 1, 10);
+      else if (cgn == 20 && P == 2) GN_REG(5, 2, 20);
+      else if (cgn == 20) GN_REG(5, 1, 20);
+      else if (cgn == 40 && P == 2) GN_REG(5, 2, 40);
+      else if (cgn == 40) GN_REG(5, 1, 40);
+      else GN_REG(10, 1, 80);
+#undef GN_REG
+      return;
+    }
+  }
   // ---- single-launch path: one CTA per (image, block of whole groups) ----
   {
     const int cgn = C / groups;
@@ -807,7 +1112,14 @@ void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, i
         return e ? atoi(e) : 2;
       }();
       int cs = 1;
-      while (cs < max_cs && (C / cb) * n_img * cs < 148 && hw % (2 * cs) == 0 && hw / (2 * cs) >= 64) cs *= 2;
+      // ... or when its slab (plus 36 KB of reduction scratch) would leave room for only one CTA per SM
+      static const size_t slab_limit = [] {
+        const char* e = getenv("MVLDM_GN_SLAB_KB");
+        return (size_t)(e ? atoi(e) : 64) * 1024;
+      }();
+      while (cs < max_cs && ((C / cb) * n_img * cs < 148 || slab / cs > slab_limit) && hw % (2 * cs) == 0 &&
+             hw / (2 * cs) >= 64)
+        cs *= 2;
       const size_t slab_cs = slab / cs;
       const int cache_cs = slab_cs <= 160 * 1024 ? 1 : 0;
       cudaLaunchConfig_t cfg{};

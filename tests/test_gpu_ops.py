@@ -143,7 +143,12 @@ def test_gemm_rejects_unsupported_shapes():
 
 
 @pytest.mark.parametrize("n,c0,c1,hw,silu,eps", [(4, 320, 0, 1024, 1, 1e-5), (4, 640, 320, 256, 1, 1e-5),
-                                                 (8, 1280, 640, 16, 1, 1e-5), (2, 1280, 0, 64, 0, 1e-6)])
+                                                 (8, 1280, 640, 16, 1, 1e-5), (2, 1280, 0, 64, 0, 1e-6),
+                                                 (8, 1280, 0, 16, 1, 1e-5), (8, 640, 0, 256, 1, 1e-5),
+                                                 (8, 1280, 1280, 16, 1, 1e-5), (3, 640, 0, 1024, 0, 1e-6),
+                                                 (8, 320, 320, 1024, 1, 1e-5), (2, 1280, 0, 1024, 1, 1e-5),
+                                                 (3, 1280, 1280, 64, 1, 1e-5), (5, 320, 0, 256, 1, 1e-5),
+                                                 (1, 640, 0, 64, 1, 1e-5), (7, 1280, 0, 16, 0, 1e-5)])
 def test_groupnorm(n, c0, c1, hw, silu, eps):
     torch.manual_seed(4)
     lib = _lib.load()
