@@ -172,7 +172,8 @@ typedef struct {
   int32_t rowvec_ld;
   const void* residual;         /* bf16 [M, res_ld] or NULL */
   int32_t res_ld;
-  int32_t mode;                 /* 0 bf16 [M,ldo]; 1 GEGLU (16-col interleave) -> bf16 [M, N/2]; 2 fp32 NCHW, n_valid channels */
+  int32_t mode;                 /* 0 bf16 [M,ldo]; 1 GEGLU (16-col interleave) -> bf16 [M, N/2]; 2 fp32 NCHW, n_valid channels;
+                                   3 like 0 with SiLU on the result; 4 fp32 [M,ldo] */
   void* out;
   int32_t ldo;
   int32_t n_valid;

@@ -86,7 +86,8 @@ __global__ void im2col_input_kernel(const float* __restrict__ x, int n_img, int 
 }
 
 // diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): [cos | sin], fp32
-__global__ void sinusoid_kernel(const int64_t* __restrict__ t, int n, int dim, float* __restrict__ out) {
+template <class OutT>
+__global__ void sinusoid_kernel(const int64_t* __restrict__ t, int n, int dim, OutT* __restrict__ out) {
   pdl_wait();
   pdl_launch_dependents();
   const int half = dim / 2;
@@ -95,8 +96,8 @@ __global__ void sinusoid_kernel(const int64_t* __restrict__ t, int n, int dim, f
   const int r = i / half, j = i - r * half;
   const float freq = expf(-logf(10000.f) * (float)j / (float)half);
   const float arg = (float)t[r] * freq;
-  out[(int64_t)r * dim + j] = cosf(arg);
-  out[(int64_t)r * dim + half + j] = sinf(arg);
+  out[(int64_t)r * dim + j] = (OutT)cosf(arg);
+  out[(int64_t)r * dim + half + j] = (OutT)sinf(arg);
 }
 
 // small-M linear: one warp per output column, weights streamed once with 16-byte loads.
@@ -979,7 +980,13 @@ void im2col_input(cudaStream_t s, const float* latents, int n_img, int cin, int 
 
 void timestep_sinusoid(cudaStream_t s, const int64_t* t, int n, int dim, float* out) {
   const int total = n * (dim / 2);
-  launch_pdl(sinusoid_kernel, dim3(ceil_div(total, 128)), dim3(128), 0, s, t, n, dim, out);
+  launch_pdl(sinusoid_kernel<float>, dim3(ceil_div(total, 128)), dim3(128), 0, s, t, n, dim, out);
+}
+
+// bf16 copy of the same embedding: the A operand of the time_embedding GEMMs (what autocast feeds linear_1 in the reference)
+void timestep_sinusoid_bf16(cudaStream_t s, const int64_t* t, int n, int dim, bf16* out) {
+  const int total = n * (dim / 2);
+  launch_pdl(sinusoid_kernel<bf16>, dim3(ceil_div(total, 128)), dim3(128), 0, s, t, n, dim, out);
 }
 
 void small_linear(cudaStream_t s, const float* in, int rows, int k, const bf16* w, const float* b, int n, int act,

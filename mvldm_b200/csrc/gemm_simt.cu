@@ -112,10 +112,13 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const __grid_constant__ 
       if (d.rowvec) v += d.rowvec[(int64_t)im * d.rowvec_ld + nn];
       return v;
     };
-    if (d.mode == 0) {
+    if (d.mode == 0 || d.mode == 3) {
       float v = val(c);
       if (d.residual) v += __bfloat162float(reinterpret_cast<const bf16*>(d.residual)[(int64_t)m * d.res_ld + n]);
+      if (d.mode == 3) v = v / (1.f + expf(-v));
       reinterpret_cast<bf16*>(d.out)[(int64_t)m * d.ldo + n] = __float2bfloat16(v);
+    } else if (d.mode == 4) {
+      reinterpret_cast<float*>(d.out)[(int64_t)m * d.ldo + n] = val(c);
     } else if (d.mode == 1) {
       if ((c & 31) < 16) {  // columns [32j,32j+16) are x, [32j+16,32j+32) the matching gates
         const float x = val(c), g = val(c + 16);

@@ -349,8 +349,8 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
           }
         }
       }
-      if (p.mode == 0) {
-        if (p.residual) {
+      if (p.mode == 0 || p.mode == 3) {
+        if (use_res) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 u = res_cur[j];
@@ -362,6 +362,10 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
               v[j * 8 + e * 2 + 1] += f.y;
             }
           }
+        }
+        if (p.mode == 3) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));  // SiLU
         }
         bf16* op = reinterpret_cast<bf16*>(p.out) + (int64_t)m * p.ldo + n;
 #pragma unroll
@@ -378,6 +382,13 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         st_global_v8(reinterpret_cast<bf16*>(p.out) + (int64_t)m * p.ldo + n / 2, pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]),
                      pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7]), pack_bf16(g[8], g[9]), pack_bf16(g[10], g[11]),
                      pack_bf16(g[12], g[13]), pack_bf16(g[14], g[15]));
+      } else if (p.mode == 4) {
+        float* op = reinterpret_cast<float*>(p.out) + (int64_t)m * p.ldo + n;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          st_global_v8(op + 8 * j, __float_as_uint(v[8 * j]), __float_as_uint(v[8 * j + 1]), __float_as_uint(v[8 * j + 2]),
+                       __float_as_uint(v[8 * j + 3]), __float_as_uint(v[8 * j + 4]), __float_as_uint(v[8 * j + 5]),
+                       __float_as_uint(v[8 * j + 6]), __float_as_uint(v[8 * j + 7]));
       } else {
         const int pix = m - img * p.hw;
         float* op = reinterpret_cast<float*>(p.out) + (int64_t)img * p.n_valid * p.hw + pix;
@@ -721,7 +732,8 @@ void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t w
   p.out = d.out;
   p.ldo = d.ldo;
   p.n_valid = d.n_valid;
-  if (d.mode == 0) MV_CHECK(d.ldo % 8 == 0 && (!d.residual || d.res_ld % 8 == 0), "gemm_tc: row pitch must be a multiple of 8");
+  MV_CHECK(d.mode >= 0 && d.mode <= 4, "gemm_tc: bad output mode");
+  if (d.mode == 0 || d.mode == 3 || d.mode == 4) MV_CHECK(d.ldo % 8 == 0 && (!d.residual || d.res_ld % 8 == 0), "gemm_tc: row pitch must be a multiple of 8");
   if (BN == 256) launch<256, 2>(s, p, splits);        // 2 x 96 KB
   else if (BN == 160) launch<160, 3>(s, p, splits);   // 3 x 72 KB
   else if (BN == 128) launch<128, 3>(s, p, splits);   // 3 x 64 KB

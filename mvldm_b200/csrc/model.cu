@@ -753,18 +753,28 @@ struct mvldm_handle_s {
     const int L = cfg.num_levels, n = total_views(sv);
     const int* boc = cfg.block_out_channels;
     arena.off = 0;
-    // ---- time embedding (K2): sinusoid -> linear -> SiLU -> linear -> SiLU -> all 21 time_emb_proj at once
-    float* sinus = new_f32((size_t)n * boc[0]);
-    float* e1 = new_f32((size_t)n * temb_dim);
-    float* e2 = new_f32((size_t)n * temb_dim);
+    // ---- time embedding (K2): sinusoid -> linear -> SiLU -> linear -> SiLU -> all time_emb_proj of the net at once.
+    // Three tensor-core GEMMs over the n (<= 128 per tile) rows: the SIMT row-by-column kernel this replaces re-read
+    // the activations once per output column (90 us at 8 views, 560 us at 64).
+    Act sinus = new_act(n, 1, 1, boc[0]);
+    Act e1 = new_act(n, 1, 1, temb_dim);
+    Act e2 = new_act(n, 1, 1, temb_dim);
     float* temb = new_f32((size_t)n * temb_total);
     if (!dry) {
-      ProfScope ps(this, "time_embedding", "rows" + std::to_string(n), 2.0 * n * ((double)boc[0] * temb_dim + (double)temb_dim * temb_dim + (double)temb_dim * temb_total),
-                   2.0 * ((double)boc[0] * temb_dim + (double)temb_dim * temb_dim + (double)temb_dim * temb_total));
-      timestep_sinusoid(stream, tsteps, n, boc[0], sinus);
-      small_linear(stream, sinus, n, boc[0], time1.w, time1.bias, temb_dim, 1, e1);
-      small_linear(stream, e1, n, temb_dim, time2.w, time2.bias, temb_dim, 1, e2);  // SiLU(emb): every consumer applies it
-      small_linear(stream, e2, n, temb_dim, temb_all.w, temb_all.bias, temb_total, 0, temb);
+      ProfScope ps(this, "time_embedding", "sinusoid rows" + std::to_string(n), 0.0, 0.0);
+      timestep_sinusoid_bf16(stream, tsteps, n, boc[0], sinus.p);
+    }
+    gemm({seg_1x1(sinus)}, time1, e1, nullptr, 0, nullptr, 3);
+    gemm({seg_1x1(e1)}, time2, e2, nullptr, 0, nullptr, 3);  // SiLU(emb): every consumer (ResnetBlock2D) applies it first
+    {
+      mvldm_gemm_desc d{};
+      d.nseg = 1;
+      d.seg[0] = seg_1x1(e2);
+      d.n_img = n; d.oh = 1; d.ow = 1;
+      d.w = temb_all.w; d.n = temb_all.n; d.k = temb_all.k;
+      d.bias = temb_all.bias;
+      d.mode = 4; d.out = temb; d.ldo = temb_total; d.n_valid = temb_all.n;
+      run_gemm(d);
     }
     // ---- conv_in on the im2col'd fp32 input
     Act col = new_act(n, Hh, Ww, kpad_in);
