@@ -40,6 +40,7 @@ struct AttnParams {
   int heads, d, dpad;
   float scale_log2;  // d^-1/2 * log2(e)
   int trace;
+  int skip_pad;      // MMAs cover only ceil(d/16) K-slices / ceil((d+1)/16)*16 output columns (MVLDM_ATTN_SKIP_PAD=0: all)
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -369,8 +370,11 @@ __global__ void __launch_bounds__(192, 2) attn64_kernel(const __grid_constant__ 
     // instructions.  Keeping the loop convergent lets ptxas keep descriptors in uniform registers and predicate
     // UTCHMMA directly instead of wrapping every issue in an ELECT/branch loop.
     {
+      // The head's pad columns are zeros (Q, K) or unused (V beyond the ones column): the tensor pipe, which two CTAs
+      // per SM keep ~90 % busy, skips them.  d = 40: 3 of the 4 K=16 slices of Q K^T and N = 48 of 64 columns of P V.
       constexpr uint32_t idesc_qk = tc::umma_idesc_bf16(BM, BT, false, false);
-      constexpr uint32_t idesc_pv = tc::umma_idesc_bf16(BM, 64, false, true);
+      const int kq = p.skip_pad ? (p.d + 15) / 16 : 4;
+      const uint32_t idesc_pv = tc::umma_idesc_bf16(BM, p.skip_pad ? (p.d + 1 + 15) / 16 * 16 : 64, false, true);
       const uint64_t qd = tc::umma_desc_k_sw128(q_smem);
       auto issue_qk = [&](int j) {
         const int s = j >> 1, stage = s % ST;
@@ -381,7 +385,8 @@ __global__ void __launch_bounds__(192, 2) attn64_kernel(const __grid_constant__ 
         const uint64_t kd = tc::umma_desc_k_sw128(kv_smem + stage * STAGE_BYTES + (j & 1) * (BT * 128));
         if (tc::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc::umma_ss(tmem + S_COL + (j & 1) * BT, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
+          for (int k = 0; k < 4; ++k)
+            if (k < kq) tc::umma_ss(tmem + S_COL + (j & 1) * BT, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
           tc::umma_commit(tc::smem_u32(&bar_s[j & 1]));
         }
         __syncwarp();
@@ -575,6 +580,11 @@ void fill_params(AttnParams& p, const AttnSrc& a, bf16* out, int batches, int he
   p.dpad = dpad;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
   p.trace = getenv("MVLDM_ATTN_TRACE") != nullptr;
+  static const bool skip = [] {
+    const char* e = getenv("MVLDM_ATTN_SKIP_PAD");
+    return !e || atoi(e) != 0;
+  }();
+  p.skip_pad = skip ? 1 : 0;
 }
 
 template <int DPAD, int BN, int ST, int OCC>
