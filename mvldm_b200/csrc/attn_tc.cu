@@ -109,7 +109,6 @@ __global__ void __launch_bounds__(192, OCC) attn_tc_kernel(const __grid_constant
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
   pdl_wait();
-  pdl_launch_dependents();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -252,6 +251,7 @@ __global__ void __launch_bounds__(192, OCC) attn_tc_kernel(const __grid_constant
     // ---- epilogue: O / l -> bf16, head-padded row
     tc::mbar_wait(tc::smem_u32(&bar_o), (T - 1) & 1);
     tc::tc_fence_after();
+    pdl_launch_dependents();
     const float inv = 1.f / l_sum;
     bf16* dst = p.out + ((int64_t)batch * p.seq + row) * (p.heads * DPAD) + head * DPAD;
 #pragma unroll 1
@@ -346,6 +346,7 @@ __global__ void __launch_bounds__(192, 2) attn64_kernel(const __grid_constant__ 
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -508,6 +509,7 @@ __global__ void __launch_bounds__(192, 2) attn64_kernel(const __grid_constant__ 
     // ---- epilogue: O / l -> bf16, head-padded row
     tc::mbar_wait(tc::smem_u32(&bar_done), 0);
     tc::tc_fence_after();
+    pdl_launch_dependents();
     float inv;
     {  // row sum = column d of O (the ones column of V)
       uint32_t o[16];

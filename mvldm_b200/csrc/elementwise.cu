@@ -1064,11 +1064,22 @@ void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, i
       cfg.blockDim = dim3(320, 1, 1);
       cfg.dynamicSmemBytes = 0;
       cfg.stream = s;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cudaLaunchAttribute at[2];
+      int na = 0;
+      if (cs > 1) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = cs; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
+      }
+#ifdef MVLDM_ENABLE_PDL
+      if (g_use_pdl) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+      }
+#endif
       cfg.attrs = at;
-      cfg.numAttrs = cs > 1 ? 1 : 0;
+      cfg.numAttrs = na;
       const int sl = silu ? 1 : 0;
       if (cgn == 10) MV_CUDA(cudaLaunchKernelEx(&cfg, gn_flat_kernel<4, 10>, x0, c0, x1, c1, hw, eps, gamma, beta, sl, out));
       else if (cgn == 20) MV_CUDA(cudaLaunchKernelEx(&cfg, gn_flat_kernel<4, 20>, x0, c0, x1, c1, hw, eps, gamma, beta, sl, out));
@@ -1134,11 +1145,22 @@ void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, i
       cfg.blockDim = dim3(GNB_THREADS, 1, 1);
       cfg.dynamicSmemBytes = cache_cs ? slab_cs : 0;
       cfg.stream = s;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cudaLaunchAttribute at[2];
+      int na = 0;
+      if (cs > 1) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = cs; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
+      }
+#ifdef MVLDM_ENABLE_PDL
+      if (g_use_pdl) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+      }
+#endif
       cfg.attrs = at;
-      cfg.numAttrs = cs > 1 ? 1 : 0;
+      cfg.numAttrs = na;
       MV_CUDA(cudaLaunchKernelEx(&cfg, gn_block_kernel, x0, c0, x1, c1, hw, groups, eps, gamma, beta, silu ? 1 : 0, cb,
                                  cache_cs, out));
       MV_LAUNCHED();

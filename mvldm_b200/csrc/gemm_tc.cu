@@ -161,7 +161,6 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   const uint32_t tmem_base = tmem_base_slot;
   // everything above overlaps the previous kernel's tail; from here on we read its output
   pdl_wait();
-  pdl_launch_dependents();
   gtrace(tr && threadIdx.x == 0, 1);  // prologue done (barriers, TMEM)
 
   if (warp == 0) {
@@ -299,6 +298,10 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     const float* cvrow = s_colvec[img - img0];
     tc::mbar_wait(tc::smem_u32(&bar_acc_full[ab]), (wi >> 1) & 1);
     tc::tc_fence_after();
+    // last item's main loop is done: let the next kernel's CTAs be scheduled (they set up barriers / TMEM / descriptors
+    // and then block in griddepcontrol.wait until this grid has completed).  Triggering earlier would let them take
+    // shared memory and TMEM this grid still needs.
+    if (w + (int)gridDim.x >= num_work) pdl_launch_dependents();
     gtrace(tr && threadIdx.x == 64, 6);          // accumulator ready
 #pragma unroll 1  // rolled: the unrolled epilogue (x8 chunks x 3 modes) cost 0.5 ms per forward in code size / registers
     for (int c0 = 0; c0 < BN; c0 += 32) {
