@@ -20,23 +20,31 @@ namespace {
 // MUFU.EX2 + MUFU.RCP: the IEEE division this replaces was ~10x the instructions of the rest of a GroupNorm element
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 
+// eight bf16 moved as ONE 16-byte access (a struct of four __nv_bfloat162 is copied member by member: 4 x 32-bit)
 struct alignas(16) bf16x8 {
-  __nv_bfloat162 v[4];
+  uint4 u;
+  __device__ __forceinline__ __nv_bfloat162 h(int i) const {
+    const uint32_t w = i == 0 ? u.x : (i == 1 ? u.y : (i == 2 ? u.z : u.w));
+    return *reinterpret_cast<const __nv_bfloat162*>(&w);
+  }
 };
+__device__ __forceinline__ uint32_t bf162_bits(float a, float b) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
 
 __device__ __forceinline__ void load8(const bf16* p, float* f) {
   bf16x8 r = *reinterpret_cast<const bf16x8*>(p);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(r.v[i]);
+    float2 t = __bfloat1622float2(r.h(i));
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
   }
 }
 __device__ __forceinline__ void store8(bf16* p, const float* f) {
   bf16x8 r;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) r.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  r.u = make_uint4(bf162_bits(f[0], f[1]), bf162_bits(f[2], f[3]), bf162_bits(f[4], f[5]), bf162_bits(f[6], f[7]));
   *reinterpret_cast<bf16x8*>(p) = r;
 }
 
@@ -317,7 +325,7 @@ __global__ void __launch_bounds__(256) gn_cluster_kernel(const bf16* __restrict_
           if (cache) *reinterpret_cast<bf16x8*>(slice + (int64_t)(pp + u * lanes_p) * C + c) = raw[u];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float2 f = __bfloat1622float2(raw[u].v[j]);
+            const float2 f = __bfloat1622float2(raw[u].h(j));
             sa[2 * j] += f.x; sa[2 * j + 1] += f.y;
             qa[2 * j] = fmaf(f.x, f.x, qa[2 * j]); qa[2 * j + 1] = fmaf(f.y, f.y, qa[2 * j + 1]);
           }
@@ -328,7 +336,7 @@ __global__ void __launch_bounds__(256) gn_cluster_kernel(const bf16* __restrict_
         if (cache) *reinterpret_cast<bf16x8*>(slice + (int64_t)pp * C + c) = raw;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 f = __bfloat1622float2(raw.v[j]);
+          const float2 f = __bfloat1622float2(raw.h(j));
           sa[2 * j] += f.x; sa[2 * j + 1] += f.y;
           qa[2 * j] = fmaf(f.x, f.x, qa[2 * j]); qa[2 * j + 1] = fmaf(f.y, f.y, qa[2 * j + 1]);
         }
@@ -438,7 +446,7 @@ __global__ void __launch_bounds__(GNB_THREADS) gn_block_kernel(const bf16* __res
         if (cache) *reinterpret_cast<bf16x8*>(slab + (int64_t)(pp + u * lanes_p) * cb + cv * 8) = raw[u];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 f = __bfloat1622float2(raw[u].v[j]);
+          const float2 f = __bfloat1622float2(raw[u].h(j));
           sa[2 * j] += f.x; sa[2 * j + 1] += f.y;
           qa[2 * j] = fmaf(f.x, f.x, qa[2 * j]); qa[2 * j + 1] = fmaf(f.y, f.y, qa[2 * j + 1]);
         }
@@ -449,7 +457,7 @@ __global__ void __launch_bounds__(GNB_THREADS) gn_block_kernel(const bf16* __res
       if (cache) *reinterpret_cast<bf16x8*>(slab + (int64_t)pp * cb + cv * 8) = raw;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(raw.v[j]);
+        const float2 f = __bfloat1622float2(raw.h(j));
         sa[2 * j] += f.x; sa[2 * j + 1] += f.y;
         qa[2 * j] = fmaf(f.x, f.x, qa[2 * j]); qa[2 * j + 1] = fmaf(f.y, f.y, qa[2 * j + 1]);
       }
@@ -565,7 +573,7 @@ __global__ void __launch_bounds__(512) gn_reg_kernel(const bf16* __restrict__ x0
       const int c = ch0 + v * 8;
       const bf16* src = c < c0 ? x0 + pix * c0 + c : x1 + pix * c1 + (c - c0);
       if (live) raw[j][v] = *reinterpret_cast<const bf16x8*>(src);
-      else raw[j][v] = bf16x8{};
+      else raw[j][v].u = make_uint4(0u, 0u, 0u, 0u);
     }
   }
   float S[GB], Q[GB];
@@ -577,7 +585,7 @@ __global__ void __launch_bounds__(512) gn_reg_kernel(const bf16* __restrict__ x0
     for (int v = 0; v < NV; ++v)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float2 f = __bfloat1622float2(raw[j][v].v[e]);
+        const float2 f = __bfloat1622float2(raw[j][v].h(e));
         constexpr int dummy = 0;
         (void)dummy;
         const int ga = (v * 8 + 2 * e) / CGN, gbb = (v * 8 + 2 * e + 1) / CGN;  // compile-time after unrolling
@@ -614,12 +622,12 @@ __global__ void __launch_bounds__(512) gn_reg_kernel(const bf16* __restrict__ x0
     }
   }
   if (!live) return;
-  const float cnt = (float)hw * (float)CGN;
+  const float inv_cnt = 1.f / ((float)hw * (float)CGN);
   float mean[GB], rstd[GB];
 #pragma unroll
   for (int g = 0; g < GB; ++g) {
-    mean[g] = S[g] / cnt;
-    rstd[g] = rsqrtf(fmaxf(Q[g] / cnt - mean[g] * mean[g], 0.f) + eps);
+    mean[g] = S[g] * inv_cnt;
+    rstd[g] = rsqrtf(fmaxf(Q[g] * inv_cnt - mean[g] * mean[g], 0.f) + eps);
   }
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
@@ -640,7 +648,7 @@ __global__ void __launch_bounds__(512) gn_reg_kernel(const bf16* __restrict__ x0
       float f[8];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float2 x = __bfloat1622float2(raw[j][v].v[e]);
+        const float2 x = __bfloat1622float2(raw[j][v].h(e));
         f[2 * e] = x.x;
         f[2 * e + 1] = x.y;
       }
@@ -693,23 +701,24 @@ __global__ void __launch_bounds__(320, 3) gn_flat_kernel(const bf16* __restrict_
   for (int j = 0; j < R; ++j)
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float2 f = __bfloat1622float2(raw[j].v[e]);
+      const float2 f = __bfloat1622float2(raw[j].h(e));
       sa[2 * e] += f.x; qa[2 * e] = fmaf(f.x, f.x, qa[2 * e]);
       sa[2 * e + 1] += f.y; qa[2 * e + 1] = fmaf(f.y, f.y, qa[2 * e + 1]);
     }
-  // channels cv*8 .. cv*8+7 -> groups (CGN >= 8: at most two)
-  float S[GB], Q[GB];
-#pragma unroll
-  for (int g = 0; g < GB; ++g) S[g] = Q[g] = 0.f;
+  // channels cv*8 .. cv*8+7 belong to at most two groups (CGN >= 8): g_lo for e < eb, g_lo + 1 from eb on
+  const int g_lo = (cv * 8) / CGN, eb = (g_lo + 1) * CGN - cv * 8;
+  float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int ge = (cv * 8 + e) / CGN;
+    const bool lo = e < eb;
+    s_lo += lo ? sa[e] : 0.f; q_lo += lo ? qa[e] : 0.f;
+    s_hi += lo ? 0.f : sa[e]; q_hi += lo ? 0.f : qa[e];
+  }
+  float S[GB], Q[GB];
 #pragma unroll
-    for (int g = 0; g < GB; ++g)
-      if (ge == g) {
-        S[g] += sa[e];
-        Q[g] += qa[e];
-      }
+  for (int g = 0; g < GB; ++g) {
+    S[g] = (g == g_lo ? s_lo : 0.f) + (g == g_lo + 1 ? s_hi : 0.f);
+    Q[g] = (g == g_lo ? q_lo : 0.f) + (g == g_lo + 1 ? q_hi : 0.f);
   }
 #pragma unroll
   for (int g = 0; g < GB; ++g)
@@ -744,7 +753,11 @@ __global__ void __launch_bounds__(320, 3) gn_flat_kernel(const bf16* __restrict_
   } else {
     __syncthreads();
   }
-  const float cnt = (float)hw * (float)CGN;
+  const float inv_cnt = 1.f / ((float)hw * (float)CGN);
+  const int g_hi = min(g_lo + 1, GB - 1);
+  const float mean_lo = stat[2 * g_lo] * inv_cnt, mean_hi = stat[2 * g_hi] * inv_cnt;
+  const float rstd_lo = rsqrtf(fmaxf(stat[2 * g_lo + 1] * inv_cnt - mean_lo * mean_lo, 0.f) + eps);
+  const float rstd_hi = rsqrtf(fmaxf(stat[2 * g_hi + 1] * inv_cnt - mean_hi * mean_hi, 0.f) + eps);
   const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
   const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
   const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
@@ -752,11 +765,9 @@ __global__ void __launch_bounds__(320, 3) gn_flat_kernel(const bf16* __restrict_
   float sc[8], sh[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int ge = (cv * 8 + e) / CGN;
-    const float mean = stat[2 * ge] / cnt;
-    const float rstd = rsqrtf(fmaxf(stat[2 * ge + 1] / cnt - mean * mean, 0.f) + eps);
-    sc[e] = rstd * gg[e];
-    sh[e] = bb[e] - mean * sc[e];
+    const bool lo = e < eb;
+    sc[e] = (lo ? rstd_lo : rstd_hi) * gg[e];
+    sh[e] = bb[e] - (lo ? mean_lo : mean_hi) * sc[e];
   }
   bf16* dst = out + ((int64_t)img * hw + p0) * C + c;
   const int64_t dstep = (int64_t)pstep * C;
@@ -765,7 +776,7 @@ __global__ void __launch_bounds__(320, 3) gn_flat_kernel(const bf16* __restrict_
     float f[8];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float2 x = __bfloat1622float2(raw[j].v[e]);
+      const float2 x = __bfloat1622float2(raw[j].h(e));
       f[2 * e] = x.x;
       f[2 * e + 1] = x.y;
     }
@@ -1040,8 +1051,12 @@ void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, i
   const int C = c0 + c1;
   MV_CHECK(C % groups == 0 && groups <= 64, "groupnorm: channels not divisible by groups (<= 64 groups)");
   MV_CHECK(c0 % 8 == 0 && c1 % 8 == 0 && C <= GN_MAXC, "groupnorm: channel counts must be multiples of 8, <= 2560");
+  static const int force_two = [] {
+    const char* e = getenv("MVLDM_GN_TWO_LAUNCH");
+    return e ? atoi(e) : 0;
+  }();
   // ---- register-resident path (the model's 320/640/1280/2560-channel tensors at every resolution) ----
-  {
+  if (!(force_two && n_img >= force_two)) {
     static const bool use_reg = [] {
       const char* e = getenv("MVLDM_GN_REG");
       return !e || atoi(e) != 0;
@@ -1112,7 +1127,7 @@ void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, i
     }
   }
   // ---- single-launch path: one CTA per (image, block of whole groups) ----
-  {
+  if (!(force_two && n_img >= force_two)) {
     const int cgn = C / groups;
     int cb = cgn;
     while (cb % 8 != 0) cb += cgn;  // lcm(group width, 8)
@@ -1169,7 +1184,7 @@ void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, i
     }
   }
   // ---- cluster path (opt-in): one cluster per image ----
-  int cl = gn_cluster_limit();
+  int cl = (force_two && n_img >= force_two) ? 1 : gn_cluster_limit();
   while (cl > 1 && (hw % cl != 0)) cl /= 2;
   if (cl >= 2) {
     const size_t slice_bytes = (size_t)(hw / cl) * C * sizeof(bf16);
