@@ -78,18 +78,23 @@ __global__ void im2col_input_kernel(const float* __restrict__ x, int n_img, int 
                                     bf16* __restrict__ out) {
   pdl_wait();
   pdl_launch_dependents();
-  const int64_t total = (int64_t)n_img * h * w * kpad;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(i % kpad);
-    const int64_t m = i / kpad;
-    float v = 0.f;
-    if (k < 9 * cin) {
-      const int tap = k / cin, c = k - tap * cin;
-      const int px = (int)(m % w), py = (int)((m / w) % h), img = (int)(m / ((int64_t)w * h));
-      const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
-      if (yy >= 0 && yy < h && xx >= 0 && xx < w) v = x[(((int64_t)img * cin + c) * h + yy) * w + xx];
+  const int kv = kpad / 8;  // one thread = eight consecutive k of one output pixel = one 16-byte store
+  const int total = n_img * h * w * kv;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int m = i / kv, k0 = (i - m * kv) * 8;
+    const int px = m % w, py = (m / w) % h, img = m / (w * h);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + j;
+      v[j] = 0.f;
+      if (k < 9 * cin) {
+        const int tap = k / cin, c = k - tap * cin;
+        const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) v[j] = x[((img * cin + c) * h + yy) * w + xx];
+      }
     }
-    out[i] = __float2bfloat16(v);
+    store8(out + (int64_t)i * 8, v);
   }
 }
 
@@ -985,8 +990,9 @@ inline int grid_for(int64_t total, int threads) {
 
 void im2col_input(cudaStream_t s, const float* latents, int n_img, int cin, int h, int w, int kpad, bf16* out) {
   MV_CHECK(kpad >= 9 * cin, "im2col: kpad too small");
-  const int64_t total = (int64_t)n_img * h * w * kpad;
-  launch_pdl(im2col_input_kernel, dim3(grid_for(total, 256)), dim3(256), 0, s, latents, n_img, cin, h, w, kpad, out);
+  MV_CHECK(kpad % 8 == 0 && (int64_t)n_img * h * w * kpad < (1ll << 31), "im2col: kpad must be a multiple of 8 (32-bit indexing)");
+  const int64_t total = (int64_t)n_img * h * w * (kpad / 8);
+  launch_pdl(im2col_input_kernel, dim3(grid_for(total, 128)), dim3(128), 0, s, latents, n_img, cin, h, w, kpad, out);
 }
 
 void timestep_sinusoid(cudaStream_t s, const int64_t* t, int n, int dim, float* out) {

@@ -48,7 +48,7 @@ namespace {
 constexpr int BM = 128, BK = 64;
 
 // optional in-kernel timeline of CTA 0 (env MVLDM_GEMM_TRACE, tools/gemm_trace.py): clock64() at the hand-offs
-__device__ long long g_gemm_trace[16];
+__device__ long long g_gemm_trace[64];  // 0..10: CTA 0 milestones; 16 + 4*i ..: item i of CTA 0 (acc ready, epilogue done, MMAs issued)
 __device__ __forceinline__ void gtrace(bool on, int slot) {
   if (on) g_gemm_trace[slot] = clock64();
 }
@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         if (tc::elect_one()) tc::umma_commit(tc::smem_u32(&bar_acc_full[ab]));
         __syncwarp();
         gtrace(tr && lane == 0, 5);  // all MMAs of the item issued
+        if (wi < 12) gtrace(tr && lane == 0, 18 + 4 * wi);
       }
     }
   } else {
@@ -303,6 +304,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     // shared memory and TMEM this grid still needs.
     if (w + (int)gridDim.x >= num_work) pdl_launch_dependents();
     gtrace(tr && threadIdx.x == 64, 6);          // accumulator ready
+    if (wi < 12) gtrace(tr && threadIdx.x == 64, 16 + 4 * wi);
 #pragma unroll 1  // rolled: the unrolled epilogue (x8 chunks x 3 modes) cost 0.5 ms per forward in code size / registers
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
@@ -404,6 +406,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     tc::tc_fence_before();
     tc::mbar_arrive(tc::smem_u32(&bar_acc_empty[ab]));  // this thread is done reading the accumulator buffer
     gtrace(tr && threadIdx.x == 64, 7);          // epilogue stores issued
+    if (wi < 12) gtrace(tr && threadIdx.x == 64, 17 + 4 * wi);
     if (p.counters) {
       // ---- split-K reduction fused into the GEMM: all splits of a tile are co-resident (one work item per CTA),
       // so they can meet at a global counter; each then reduces 1/splits of the tile's rows in fixed z order

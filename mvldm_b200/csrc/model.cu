@@ -1243,7 +1243,7 @@ int mvldm_op_attention(void* stream, int impl, const void* qkv, void* out, int b
 
 int mvldm_debug_gemm_trace(int64_t* out, int n) {
   MV_API_BEGIN
-  MV_CHECK(out && n > 0 && n <= 16, "bad arguments");
+  MV_CHECK(out && n > 0 && n <= 64, "bad arguments");
   MV_CUDA(cudaDeviceSynchronize());
   gemm_trace_read(reinterpret_cast<long long*>(out), n);
   MV_API_END
