@@ -18,8 +18,7 @@ PEAK_TF, PEAK_GB = 1395.1, 6453.7
 
 
 def floor_us(o):
-    t = o["gflop"] / PEAK_TF * 1e3 / 1e3  # GF / (TF/s) = ms * 1e-3 ... -> us below
-    t = o["gflop"] / (PEAK_TF * 1e3) * 1e6 / 1e3
+    t = o["gflop"] / PEAK_TF * 1e3   # GFLOP / (TFLOP/s) = ms; x 1e3 -> us
     b = 0.0
     m = re.match(r"M(\d+) N(\d+) K(\d+)", o["what"])
     if m:

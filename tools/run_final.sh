@@ -7,6 +7,8 @@ SMI=$!
 python bench.py > gpurun_out/final/bench_n1.json 2> gpurun_out/final/bench_n1.err
 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/final/bench_reference.json 2>&1
 python bench.py --cfg --no-cpu-baseline > gpurun_out/final/bench_cfg.json 2>&1
+python bench.py --cfg --no-batch-cfg --no-cpu-baseline > gpurun_out/final/bench_cfg_two_forwards.json 2>&1
+python bench.py --variant b --no-cpu-baseline > gpurun_out/final/bench_variant_b.json 2>&1
 python bench.py --scenes-per-gpu 8 --steps 10 --no-cpu-baseline > gpurun_out/final/bench_8scenes.json 2>&1
 kill $SMI
 python tools/scale_check.py > gpurun_out/final/scale_check.txt 2>&1
@@ -16,9 +18,16 @@ python tools/prof_attn.py 1 8192 40 >> gpurun_out/final/prof_ops.txt 2>&1
 python tools/prof_attn.py 8 8192 40 3 >> gpurun_out/final/prof_ops.txt 2>&1
 python tools/attn_trace.py 1 8192 40 >> gpurun_out/final/prof_ops.txt 2>&1
 python tools/gemm_trace.py 8 320 320 32 >> gpurun_out/final/prof_ops.txt 2>&1
+python tools/linear_trace.py 8 32 320 2560 1 >> gpurun_out/final/prof_ops.txt 2>&1
+python tools/gn_graph_bench.py > gpurun_out/final/gn_graph_bench.txt 2>&1
+python tools/gemm_sweep.py > gpurun_out/final/gemm_sweep.txt 2>&1
+python tools/excess.py 8 > gpurun_out/final/excess_v8.txt 2>&1
+tools/micro/mufu > gpurun_out/final/micro.txt 2>&1
+tools/micro/pdl_chain >> gpurun_out/final/micro.txt 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/final/launches_cold.csv python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > /dev/null 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none --csv --log-file gpurun_out/final/launches_warm.csv python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 3 -c 1 -o gpurun_out/final/ncu_gemm_conv_l0 python tools/prof_gemm.py 8 320 320 32 5 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:attn64 -s 3 -c 1 -o gpurun_out/final/ncu_attn_l0 python tools/prof_attn.py 1 8192 40 5 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gn_flat -s 3 -c 1 -o gpurun_out/final/ncu_gn_flat_l0 python tools/prof_gn.py 8 1024 320 0 > /dev/null 2>&1
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/final/smoke.log 2>&1
 tail -n 2 gpurun_out/final/pytest_gpu.log gpurun_out/final/smoke.log
