@@ -675,13 +675,14 @@ __global__ void __launch_bounds__(512) gn_reg_kernel(const bf16* __restrict__ x0
 // a shuffle tree + one __syncthreads sums over the CTA, and the output is written from the registers.  ~3x fewer
 // instructions per element than the slab kernel, which is what bounds GroupNorm at large batch.
 // ---------------------------------------------------------------------------------------------
-template <int R, int CGN>
-__global__ void __launch_bounds__(320, 3) gn_flat_kernel(const bf16* __restrict__ x0, int c0, const bf16* __restrict__ x1,
-                                                      int c1, int hw, float eps, const float* __restrict__ gamma,
-                                                      const float* __restrict__ beta, int silu, bf16* __restrict__ out) {
+template <int NV, int R, int CGN>
+__global__ void __launch_bounds__(NV == 5 ? 320 : 480, NV == 5 ? 3 : 2)
+    gn_flat_kernel(const bf16* __restrict__ x0, int c0, const bf16* __restrict__ x1, int c1, int hw, float eps,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, int silu, bf16* __restrict__ out) {
   namespace cg = cooperative_groups;
-  constexpr int NV = 5, CB = 40, GB = CB / CGN;
-  __shared__ float red[10][2 * GB];
+  constexpr int CB = NV * 8, GB = CB / CGN;   // NV = 5: 40-channel blocks (groups of 10/20/40); NV = 15: 120 (30/60)
+  static_assert(CB % CGN == 0 && CGN >= 8, "a block holds whole groups; a vector spans at most two");
+  __shared__ float red[16][2 * GB];
   __shared__ float part[2 * GB];   // this CTA's sums; peers of the cluster read it through DSMEM
   __shared__ float stat[2 * GB];
   pdl_wait();
@@ -1075,14 +1076,17 @@ void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, i
       const char* e = getenv("MVLDM_GN_FLAT");
       return !e || atoi(e) != 0;
     }();
-    if (use_flat && (cgn == 10 || cgn == 20 || cgn == 40) && C % 40 == 0 && hw % 256 == 0 && hw / 256 <= 8) {
-      // 320 threads x 4 vectors = 256 pixels x 40 channels per CTA; larger images are split over a cluster of hw/256 CTAs.
-      // Small CTAs on purpose: ~50 registers x 320 threads lets four of them share an SM, so the load, reduce and store
-      // phases of different CTAs overlap (one 640-thread CTA per SM ran at 1.6 TB/s at 64 images)
-      const int cs = hw / 256;
+    const bool flat5 = (cgn == 10 || cgn == 20 || cgn == 40) && C % 40 == 0;
+    const bool flat15 = (cgn == 30 || cgn == 60) && C % 120 == 0;   // the 960- / 1920-channel concats of the up path
+    const int px_cta = flat5 ? 256 : 128;   // threads x vectors-per-thread / vectors-per-pixel
+    if (use_flat && (flat5 || flat15) && hw % px_cta == 0 && hw / px_cta <= 8 && hw >= 256) {
+      // one channel block x 256 pixels (320 threads x 4 vectors) or x 128 pixels (480 x 4, the 120-channel blocks) per
+      // CTA; larger images are split over a cluster of CTAs.  Small CTAs on purpose: several share an SM, so the load, reduce
+      // and store phases of different CTAs overlap (one 640-thread CTA per SM ran at 1.6 TB/s at 64 images)
+      const int cs = hw / px_cta, cbk = flat5 ? 40 : 120;
       cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3((C / 40) * n_img * cs, 1, 1);
-      cfg.blockDim = dim3(320, 1, 1);
+      cfg.gridDim = dim3((C / cbk) * n_img * cs, 1, 1);
+      cfg.blockDim = dim3(flat5 ? 320 : 480, 1, 1);
       cfg.dynamicSmemBytes = 0;
       cfg.stream = s;
       cudaLaunchAttribute at[2];
@@ -1102,9 +1106,14 @@ void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, i
       cfg.attrs = at;
       cfg.numAttrs = na;
       const int sl = silu ? 1 : 0;
-      if (cgn == 10) MV_CUDA(cudaLaunchKernelEx(&cfg, gn_flat_kernel<4, 10>, x0, c0, x1, c1, hw, eps, gamma, beta, sl, out));
-      else if (cgn == 20) MV_CUDA(cudaLaunchKernelEx(&cfg, gn_flat_kernel<4, 20>, x0, c0, x1, c1, hw, eps, gamma, beta, sl, out));
-      else MV_CUDA(cudaLaunchKernelEx(&cfg, gn_flat_kernel<4, 40>, x0, c0, x1, c1, hw, eps, gamma, beta, sl, out));
+#define GN_FLAT(NV, RR, CGN) \
+  MV_CUDA(cudaLaunchKernelEx(&cfg, gn_flat_kernel<NV, RR, CGN>, x0, c0, x1, c1, hw, eps, gamma, beta, sl, out))
+      if (cgn == 10) GN_FLAT(5, 4, 10);
+      else if (cgn == 20) GN_FLAT(5, 4, 20);
+      else if (cgn == 40) GN_FLAT(5, 4, 40);
+      else if (cgn == 30) GN_FLAT(15, 4, 30);
+      else GN_FLAT(15, 4, 60);
+#undef GN_FLAT
       MV_LAUNCHED();
       return;
     }

@@ -10,7 +10,7 @@ lib = _lib.load()
 SHAPES = [(8, 1024, 320, 0, 10), (8, 256, 640, 0, 8), (8, 64, 1280, 0, 8), (8, 16, 1280, 0, 12), (8, 1024, 320, 320, 2),
           (8, 16, 1280, 1280, 3), (8, 64, 1280, 1280, 2), (8, 1024, 640, 320, 1), (8, 256, 1280, 640, 1), (8, 256, 640, 320, 1),
           (8, 256, 1280, 0, 1), (8, 256, 320, 0, 1), (8, 64, 640, 0, 1), (8, 64, 1280, 640, 1), (64, 1024, 320, 0, 0), (64, 1024, 320, 320, 0), (64, 256, 640, 0, 0), (64, 256, 1280, 640, 0), (64, 64, 1280, 0, 0),
-          (64, 16, 1280, 0, 0)]
+          (64, 16, 1280, 0, 0), (64, 1024, 640, 320, 0)]
 tot = 0.0
 for (n, hw, c0, c1, count) in SHAPES:
     C = c0 + c1
