@@ -99,6 +99,32 @@ def test_other_latent_size(gpu_models, oracle_weights, oracle_cfg):
     assert rel_err(y, ref) < FWD_TOL
 
 
+@pytest.mark.parametrize("h,w,v", [(64, 64, 2), (32, 16, 3), (8, 8, 5)])
+def test_more_latent_sizes(h, w, v, gpu_models, oracle_weights, oracle_cfg):
+    """512x512 images (64x64 latents: level 0 is above the 32x32 multi-view limit, mvunet.py:137,190, so its two
+    multi-view blocks are skipped), a non-square latent, and the smallest size the 4-level UNet accepts (8x8 -> 1x1)."""
+    torch.manual_seed(h + w + v)
+    x = torch.randn(1, v, 11, h, w)
+    t = torch.randint(0, 1000, (1, v))
+    with torch.no_grad():
+        ref = O.unet_forward(oracle_weights, x, t, oracle_cfg)
+    m = gpu_models(0, True)
+    y = m(x.cuda(), t.cuda())
+    assert rel_err(y, ref) < FWD_TOL
+    assert torch.equal(y, m(x.cuda(), t.cuda()))
+
+
+def test_unsupported_latent_size_raises(gpu_models):
+    """sizes the tile geometry cannot express fail loudly (no fallback): width must be a power of two <= 128 at
+    every level, height divisible by 8"""
+    m = gpu_models(0)
+    for (h, w) in [(24, 24), (32, 12)]:
+        with pytest.raises(RuntimeError):
+            m(torch.randn(1, 2, 11, h, w, device="cuda"), torch.zeros(1, 2, dtype=torch.int64, device="cuda"))
+    torch.cuda.synchronize()
+    m(torch.randn(1, 2, 11, 32, 32, device="cuda"), torch.zeros(1, 2, dtype=torch.int64, device="cuda"))   # still usable
+
+
 def test_weight_reload_is_picked_up(oracle_weights):
     m = mv.MultiViewUNet(mv.default_cfg(), 11, 4).cuda().eval()     # fresh init: zero proj_out (reference default)
     x = torch.randn(1, 2, 11, 32, 32, device="cuda")
