@@ -33,6 +33,7 @@ __device__ __forceinline__ void trace(bool on, int slot, int j) {
 struct AttnParams {
   CUtensorMap tmQ;   // box [64, 128, 1] over (cols, seq, batch)
   CUtensorMap tmKV;  // box [64, BN, 1]
+  CUtensorMap tmKV2; // 4-D (cols, keys, {K,V}, batch), box [64, 128, 2, 1]: one TMA instruction lands a K tile and its V tile
   bf16* out;
   int seq;             // queries per batch (rows of the Q source and of the output)
   int seq_kv;          // keys per batch (rows of the K/V source); == seq for plain self-attention
@@ -40,6 +41,8 @@ struct AttnParams {
   int heads, d, dpad;
   float scale_log2;  // d^-1/2 * log2(e)
   int trace;
+  const bf16* q_ptr; // Q rows for the kernels that stage Q through registers into TMEM
+  int ld_q;
   int skip_pad;      // MMAs cover only ceil(d/16) K-slices / ceil((d+1)/16)*16 output columns (MVLDM_ATTN_SKIP_PAD=0: all)
 };
 
@@ -549,6 +552,266 @@ __global__ void __launch_bounds__(192, 2) attn64_kernel(const __grid_constant__ 
   }
 }
 
+template <int ST>
+__global__ void __launch_bounds__(192, 2) attn64q_kernel(const __grid_constant__ AttnParams p) {
+  constexpr int BT = 64;                       // keys per compute tile
+  constexpr int Q_BYTES = BM * 128;            // 128 queries x 64 cols bf16
+  constexpr int KV_TILE = 128 * 128;           // 128 keys x 64 cols bf16 (one TMA box)
+  constexpr int STAGE_BYTES = 2 * KV_TILE;     // K box + V box
+  // TMEM: Q (bf16 pairs, the A operand of Q K^T) | S0, S1 (P(j) is written over the first half of S(j)) | O = 224 columns
+  constexpr uint32_t Q_COL = 0, S_COL = 32, O_COL = 160;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_q, bar_kv_full[ST], bar_kv_empty[ST], bar_s[2], bar_p[2], bar_o, bar_done;  // bar_q: Q is in TMEM
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t kv_smem = smem_base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BM;
+  const int batch = blockIdx.y / p.heads, head = blockIdx.y % p.heads;
+  const int T = (p.seq_kv + BT - 1) / BT;      // 64-key tiles
+  const int NS = (T + 1) / 2;                  // 128-key stages
+  const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&p.tmKV2);
+    tc::mbar_init(tc::smem_u32(&bar_q), 128);
+    for (int s = 0; s < ST; ++s) {
+      tc::mbar_init(tc::smem_u32(&bar_kv_full[s]), 1);
+      tc::mbar_init(tc::smem_u32(&bar_kv_empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(tc::smem_u32(&bar_s[b]), 1);
+      tc::mbar_init(tc::smem_u32(&bar_p[b]), 128);
+    }
+    tc::mbar_init(tc::smem_u32(&bar_o), 1);
+    tc::mbar_init(tc::smem_u32(&bar_done), 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 1) tc::tmem_alloc<256>(tc::smem_u32(&tmem_slot));
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const int kcol = p.k_col0 + head * 64;
+      for (int s = 0; s < NS; ++s) {
+        const int stage = s % ST;
+        tc::mbar_wait(tc::smem_u32(&bar_kv_empty[stage]), ((s / ST) & 1) ^ 1);
+        const uint32_t full = tc::smem_u32(&bar_kv_full[stage]);
+        tc::mbar_expect_tx(full, STAGE_BYTES);
+        const uint32_t ks = kv_smem + stage * STAGE_BYTES;
+        tc::tma_load_4d(ks, &p.tmKV2, full, kcol, s * 128, 0, batch);  // K tile, then V tile (the TMA box rate is scarce)
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    // The whole warp runs the (warp-uniform) control flow and barrier waits; one elected lane issues the tcgen05
+    // instructions.  Keeping the loop convergent lets ptxas keep descriptors in uniform registers and predicate
+    // UTCHMMA directly instead of wrapping every issue in an ELECT/branch loop.
+    {
+      // The head's pad columns are zeros (Q, K) or unused (V beyond the ones column): the tensor pipe, which two CTAs
+      // per SM keep ~90 % busy, skips them.  d = 40: 3 of the 4 K=16 slices of Q K^T and N = 48 of 64 columns of P V.
+      constexpr uint32_t idesc_qk = tc::umma_idesc_bf16(BM, BT, false, false);
+      const int kq = p.skip_pad ? (p.d + 15) / 16 : 4;
+      const uint32_t idesc_pv = tc::umma_idesc_bf16(BM, p.skip_pad ? (p.d + 1 + 15) / 16 * 16 : 64, false, true);
+      auto issue_qk = [&](int j) {
+        const int s = j >> 1, stage = s % ST;
+        if ((j & 1) == 0) {  // first tile of a stage: its K/V box must have landed
+          tc::mbar_wait(tc::smem_u32(&bar_kv_full[stage]), (s / ST) & 1);
+          tc::tc_fence_after();
+        }
+        const uint64_t kd = tc::umma_desc_k_sw128(kv_smem + stage * STAGE_BYTES + (j & 1) * (BT * 128));
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < kq) tc::umma_ts(tmem + S_COL + (j & 1) * BT, tmem + Q_COL + k * 8, kd + 2 * k, idesc_qk, k != 0);
+          tc::umma_commit(tc::smem_u32(&bar_s[j & 1]));
+        }
+        __syncwarp();
+      };
+      tc::mbar_wait(tc::smem_u32(&bar_q), 0);
+      tc::tc_fence_after();
+      issue_qk(0);
+      if (T > 1) issue_qk(1);
+      for (int j = 0; j < T; ++j) {
+        tc::mbar_wait(tc::smem_u32(&bar_p[j & 1]), (j >> 1) & 1);  // softmax has read S(j) and written P(j)
+        tc::tc_fence_after();
+        trace(tr && lane == 0, 3, j);
+        const int s = j >> 1, stage = s % ST;
+        const uint32_t vs = kv_smem + stage * STAGE_BYTES + KV_TILE + (j & 1) * (BT * 128);
+        const uint64_t vd = tc::umma_desc_mn_sw128(vs, KV_TILE);
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < BT / 16; ++kk)  // 16 keys per MMA: 8 packed-bf16 TMEM columns of P, 16 V rows (2 KB)
+            tc::umma_ts(tmem + O_COL, tmem + S_COL + (j & 1) * BT + kk * 8, vd + kk * 128, idesc_pv, (j | kk) != 0);
+          tc::umma_commit(tc::smem_u32(&bar_o));
+          if ((j & 1) == 1 || j == T - 1) tc::umma_commit(tc::smem_u32(&bar_kv_empty[stage]));  // stage fully consumed
+          // The epilogue needs "every P V has landed".  With S double-buffered a softmax warp can be two bar_o phases
+          // ahead of the tensor pipe, where a parity wait on bar_o is ambiguous, hence a dedicated single-phase barrier.
+          if (j == T - 1) tc::umma_commit(tc::smem_u32(&bar_done));
+        }
+        __syncwarp();
+        trace(tr && lane == 0, 4, j);
+        if (j + 2 < T) issue_qk(j + 2);  // into the S buffer softmax(j) has just released
+        trace(tr && lane == 0, 5, j);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= softmax + epilogue: one query row per thread =================
+    const int quarter = warp & 3;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int row = q0 + quarter * 32 + lane;
+    const float sc = p.scale_log2;
+    float m_ref = -INFINITY;
+    {  // this thread's query row -> TMEM: Q K^T then takes its A operand from TMEM (an SS MMA re-reads the 128-row Q
+       // slice from shared memory for every 64-key tile and measured 2x the issue time of the equally sized TS-form P V)
+      uint32_t qa[16], qb[16];
+      const uint4* qrow = reinterpret_cast<const uint4*>(p.q_ptr + ((int64_t)batch * p.seq + min(row, p.seq - 1)) * p.ld_q +
+                                                         p.q_col0 + head * 64);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 u = row < p.seq ? qrow[i] : make_uint4(0u, 0u, 0u, 0u);
+        qa[4 * i] = u.x; qa[4 * i + 1] = u.y; qa[4 * i + 2] = u.z; qa[4 * i + 3] = u.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 u = row < p.seq ? qrow[4 + i] : make_uint4(0u, 0u, 0u, 0u);
+        qb[4 * i] = u.x; qb[4 * i + 1] = u.y; qb[4 * i + 2] = u.z; qb[4 * i + 3] = u.w;
+      }
+      tc::tmem_st16(tmem + lane_addr + Q_COL, qa);
+      tc::tmem_st16(tmem + lane_addr + Q_COL + 16, qb);
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      tc::mbar_arrive(tc::smem_u32(&bar_q));
+    }
+    for (int j = 0; j < T; ++j) {
+      const uint32_t s_tm = tmem + lane_addr + S_COL + (j & 1) * BT;
+      const uint32_t p_tm = s_tm;  // P(j) overwrites the first 32 columns of S(j): S is in registers by then
+      trace(tr && threadIdx.x == 64, 0, j);
+      tc::mbar_wait(tc::smem_u32(&bar_s[j & 1]), (j >> 1) & 1);
+      tc::tc_fence_after();
+      trace(tr && threadIdx.x == 64, 1, j);
+      const int valid = (j == T - 1) ? p.seq_kv - j * BT : BT;  // ragged tail: keys past the sequence end do not exist
+      uint32_t ra[32], rb[32];
+      tc::tmem_ld32(s_tm, ra);
+      tc::tmem_ld32(s_tm + 32, rb);
+      tc::tmem_ld_wait();
+      if (valid < BT) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i >= valid) ra[i] = 0xff800000u;       // -inf
+          if (32 + i >= valid) rb[i] = 0xff800000u;
+        }
+      }
+      // P = exp2(s * sc - m_ref * sc) against the reference of the EARLIER tiles, with the tile maximum tracked on the
+      // side (independent instruction stream, off the critical path).  Only if this tile would have pushed P beyond 2^8
+      // (always on the first tile) is the reference moved, O rescaled and P recomputed from the registers.
+      // The row sum is not accumulated here: V carries 1.0 in its first pad column, so P V delivers sum_j P_ij (of the
+      // bf16-rounded P the tensor core actually uses) in column d of O.
+      const uint32_t scb = __float_as_uint(sc);
+      const uint64_t sc2 = pack2(scb, scb);
+      float mt0 = -INFINITY, mt1 = -INFINITY;
+      auto half = [&](uint32_t(&r)[32], uint32_t dst, uint64_t nmb2, bool track) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float x0, x1;
+          if (track) {
+            mt0 = fmaxf(mt0, __uint_as_float(r[i]));
+            mt1 = fmaxf(mt1, __uint_as_float(r[i + 1]));
+          }
+          ffma2(x0, x1, pack2(r[i], r[i + 1]), sc2, nmb2);
+          // the MUFU pipe (16 ex2/clk/SM) is busy here: every POLY_EVERY-th pair sends one exponential to the FMA pipe
+          const float e1 = ((i / 2) % POLY_EVERY == POLY_EVERY - 1) ? ex2_poly(x1) : ex2(x1);
+          pk[i / 2] = pack_bf16(ex2(x0), e1);
+        }
+        tc::tmem_st16(dst, pk);
+      };
+      {
+        const uint32_t nmb = __float_as_uint(-m_ref * sc);
+        const uint64_t nmb2 = pack2(nmb, nmb);
+        half(ra, p_tm, nmb2, true);
+        half(rb, p_tm + 16, nmb2, true);
+      }
+      const float mt = fmaxf(mt0, mt1);
+      const bool grow = (mt - m_ref) * sc > 8.f;  // also true on the first tile (m_ref = -inf)
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = grow ? mt : m_ref;
+        if (j > 0) {
+          const float f = ex2((m_ref - m_new) * sc);
+          tc::mbar_wait(tc::smem_u32(&bar_o), (j - 1) & 1);  // P V of the previous tile has landed in O
+          tc::tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tc::tmem_ld32(tmem + lane_addr + O_COL + c * 32, o);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tc::tmem_st16(tmem + lane_addr + O_COL + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&o[0]));
+            tc::tmem_st16(tmem + lane_addr + O_COL + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&o[16]));
+          }
+        }
+        m_ref = m_new;
+        const uint32_t nmb = __float_as_uint(-m_ref * sc);
+        const uint64_t nmb2 = pack2(nmb, nmb);
+        half(ra, p_tm, nmb2, false);   // recompute P(j) against the moved reference (S is still in registers)
+        half(rb, p_tm + 16, nmb2, false);
+      }
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      tc::mbar_arrive(tc::smem_u32(&bar_p[j & 1]));
+      trace(tr && threadIdx.x == 64, 2, j);
+    }
+    // ---- epilogue: O / l -> bf16, head-padded row
+    tc::mbar_wait(tc::smem_u32(&bar_done), 0);
+    tc::tc_fence_after();
+    pdl_launch_dependents();
+    float inv;
+    {  // row sum = column d of O (the ones column of V)
+      uint32_t o[16];
+      tc::tmem_ld16(tmem + lane_addr + O_COL + (p.d / 16) * 16, o);
+      tc::tmem_ld_wait();
+      float l = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) l = (i == (p.d & 15)) ? __uint_as_float(o[i]) : l;
+      inv = 1.f / l;
+    }
+    bf16* dst = p.out + ((int64_t)batch * p.seq + row) * (p.heads * 64) + head * 64;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t o[16];
+      __syncwarp();
+      tc::tmem_ld16(tmem + lane_addr + O_COL + c * 16, o);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i)  // pad columns (including the row-sum column) are written as zeros
+        if (c * 16 + i >= p.d) o[i] = 0u;
+      if (row < p.seq) {
+        uint4* op = reinterpret_cast<uint4*>(dst + c * 16);
+#pragma unroll
+        for (int v = 0; v < 2; ++v)
+          op[v] = make_uint4(pack_bf16(__uint_as_float(o[v * 8]) * inv, __uint_as_float(o[v * 8 + 1]) * inv),
+                             pack_bf16(__uint_as_float(o[v * 8 + 2]) * inv, __uint_as_float(o[v * 8 + 3]) * inv),
+                             pack_bf16(__uint_as_float(o[v * 8 + 4]) * inv, __uint_as_float(o[v * 8 + 5]) * inv),
+                             pack_bf16(__uint_as_float(o[v * 8 + 6]) * inv, __uint_as_float(o[v * 8 + 7]) * inv));
+      }
+    }
+    tc::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<256>(tmem);
+  }
+}
+
 struct AttnSrc {  // where the operands live: Q rows [batches*seq_q, ld_q], K/V rows [batches*seq_kv, ld_kv]
   const bf16* q;
   int ld_q, q_col0;
@@ -571,7 +834,16 @@ void fill_params(AttnParams& p, const AttnSrc& a, bf16* out, int batches, int he
     const uint32_t box[3] = {64, (uint32_t)bn_rows, 1};
     p.tmKV = make_tmap_bf16(a.kv, 3, dims, strides, box, es);
   }
+  {
+    const uint64_t dims[4] = {(uint64_t)a.ld_kv, (uint64_t)a.seq_kv, 2, (uint64_t)batches};
+    const uint64_t strides[3] = {(uint64_t)a.ld_kv * 2, (uint64_t)(a.v_col0 - a.k_col0) * 2, (uint64_t)a.seq_kv * a.ld_kv * 2};
+    const uint32_t box[4] = {64, 128, 2, 1};
+    const uint32_t es4[4] = {1, 1, 1, 1};
+    if (a.v_col0 > a.k_col0 && (a.v_col0 - a.k_col0) % 8 == 0) p.tmKV2 = make_tmap_bf16(a.kv, 4, dims, strides, box, es4);
+  }
   p.out = out;
+  p.q_ptr = a.q;
+  p.ld_q = a.ld_q;
   p.seq = a.seq_q;
   p.seq_kv = a.seq_kv;
   p.q_col0 = a.q_col0;
@@ -607,6 +879,21 @@ void launch64(cudaStream_t s, const AttnSrc& a, bf16* out, int batches, int head
   constexpr int ST = 2;
   AttnParams p{};
   fill_params(p, a, out, batches, heads, d, 64, 128);
+  static const bool q_in_tmem = [] {
+    const char* e = getenv("MVLDM_ATTN_Q_TMEM");
+    return !e || atoi(e) != 0;
+  }();
+  if (q_in_tmem && a.v_col0 > a.k_col0) {
+    constexpr int smem_q = ST * 2 * 128 * 128 + 1024;
+    static bool configured_q = false;
+    if (!configured_q) {
+      MV_CUDA(cudaFuncSetAttribute(attn64q_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_q));
+      configured_q = true;
+    }
+    dim3 grid_q(ceil_div(a.seq_q, BM), batches * heads);
+    launch_pdl(attn64q_kernel<ST>, grid_q, dim3(192), smem_q, s, p);
+    return;
+  }
   constexpr int smem = BM * 128 + ST * 2 * 128 * 128 + 1024;
   static bool configured = false;
   if (!configured) {

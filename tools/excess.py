@@ -34,13 +34,14 @@ def floor_us(o):
 
 def main():
     V = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     m = mv.MultiViewUNet(mv.default_cfg(), 11, 4).cuda().eval()
     for k, p in m.named_parameters():
         if k.endswith("proj_out.weight"):
             torch.nn.init.normal_(p, std=0.02)
     m.mark_dirty()
-    x = torch.randn(1, V, 11, 32, 32, device="cuda")
-    t = torch.full((1, V), 500, dtype=torch.int64, device="cuda")
+    x = torch.randn(B, V, 11, 32, 32, device="cuda")
+    t = torch.full((B, V), 500, dtype=torch.int64, device="cuda")
     for _ in range(3):
         m(x, t)
     p = profile_forward(m, x, t, reps=4)
@@ -51,7 +52,7 @@ def main():
         a[1] += o["us"]
         a[2] += floor_us(o)
     tot = sum(a[1] for a in agg.values())
-    print(f"V={V}: {len(p['ops'])} ops, {tot:.0f} us summed, floor {sum(a[2] for a in agg.values()):.0f} us")
+    print(f"B={B} V={V}: {len(p['ops'])} ops, {tot:.0f} us summed, floor {sum(a[2] for a in agg.values()):.0f} us")
     cats = collections.defaultdict(lambda: [0, 0.0, 0.0])
     for (cat, _), a in agg.items():
         for i in range(3):
@@ -61,7 +62,7 @@ def main():
     print("per shape, by excess:")
     for (cat, what), a in sorted(agg.items(), key=lambda kv: -(kv[1][1] - kv[1][2])):
         print(f"  {cat:18s} {what:28s} n={a[0]:2d} {a[1]:7.1f} us ({a[1] / a[0]:6.1f} each)  floor {a[2] / a[0]:6.1f} each  excess {a[1] - a[2]:7.1f}")
-    json.dump(p, open(f"gpurun_out/excess_v{V}.json", "w"))
+    json.dump(p, open(f"gpurun_out/excess_b{B}_v{V}.json", "w"))
 
 
 if __name__ == "__main__":
