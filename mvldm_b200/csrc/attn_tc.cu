@@ -299,14 +299,19 @@ __device__ __forceinline__ float ex2_poly(float x) {
   const float t = x + 12582912.f;            // 1.5 * 2^23: rounds x to the nearest integer in the low mantissa bits
   const float n = t - 12582912.f;
   const float f = x - n;
-  float pl = fmaf(f, 0.05550411f, 0.24022651f);
-  pl = fmaf(pl, f, 0.69314718f);
-  pl = fmaf(pl, f, 1.0f);
+  float pl = fmaf(f, 0.05517167f, 0.24261113f);   // minimax in relative error on [-0.5, 0.5]: 7.5e-5 (bf16 half-ulp: 2e-3)
+  pl = fmaf(pl, f, 0.69326097f);
+  pl = fmaf(pl, f, 0.99992806f);
   return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
 }
 
-constexpr int POLY_EVERY = 1 << 20;  // FMA-pipe exp2 for one in 2*POLY_EVERY exponentials: measured +3 % at 1/6 and it
-                                    // costs accuracy (fails the 1e-2 parity bound at 1/4), so it is off
+#ifndef MVLDM_POLY_EVERY
+#define MVLDM_POLY_EVERY 2
+#endif
+// One exponential in 2*POLY_EVERY goes to the FMA pipe (ex2_poly) instead of the MUFU pipe.  With Q in TMEM the kernel sits
+// on the MUFU limit (two CTAs x 64 ex2 per thread per tile = 1024 of a 1134-cycle tile period); moving 1/4 of them
+// measured 205.9 -> 189.8 us (1 scene, 8192 tokens) and 1346 -> 1262 us (8 scenes); 1/2 overloads the FMA pipe (207.6 us).
+constexpr int POLY_EVERY = MVLDM_POLY_EVERY;
 
 template <int ST>
 __global__ void __launch_bounds__(192, 2) attn64_kernel(const __grid_constant__ AttnParams p) {
