@@ -282,6 +282,13 @@ def run_gpu(args):
                         "GPU parked behind a spin kernel so the pairs see back-to-back execution; ncu: profiles/"),
                 "peak_source": peaks["source"],
                 "other_kernels_tflops": {"gemm_linear": tf(lin) * 1e3, "attention_joint": tf(att) * 1e3},
+                # "attn TC util" of BASELINE.json's metric: the joint attention is bound by the MUFU pipe (one ex2 per
+                # score, 16 per clock per SM = 4.62 T/s measured, tools/micro/mufu.cu), not by the tensor pipe
+                "attention": {"tflops_unpadded": tf(att) * 1e3, "tflops_padded_tensor_work": tf(att) * 1e3 * 64.0 / 40.0,
+                              "frac_of_bf16_peak_padded": tf(att) * 1e3 * 1.6 / peaks["bf16_tflops"],
+                              "exp2_per_forward": att["gflop"] * 1e9 / (4.0 * 40.0),
+                              "frac_of_mufu_bound": (att["gflop"] * 1e9 / 160.0 / 4.62e12) / (att["us"] * 1e-6),
+                              "note": "level-0 (40-wide heads padded to 64) dominates; padded = x64/40"},
                 "us_per_forward": {k: round(c["us"], 1) for k, c in prof.items()},
                 "whole_step": {"achieved": step_tf, "frac": step_tf / peaks["bf16_tflops"],
                                "how": "algorithmic GFLOP of the step (BASELINE.md) / CUDA-event time of the timed region"}}
