@@ -134,7 +134,9 @@ __global__ void __launch_bounds__(192, OCC) attn_tc_kernel(const __grid_constant
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc_qk = tc::umma_idesc_bf16(BM, BN, false, false);
-      constexpr uint32_t idesc_pv = tc::umma_idesc_bf16(BM, DPAD, false, true);
+      // the pad columns of a head are zeros: skip their K-slices in Q K^T and their output columns in P V
+      const int kq = p.skip_pad ? (p.d + 15) / 16 : DPAD / 16;
+      const uint32_t idesc_pv = tc::umma_idesc_bf16(BM, p.skip_pad ? (p.d + 15) / 16 * 16 : DPAD, false, true);
       auto issue_qk = [&](int j) {
         const int stage = j % ST;
         tc::mbar_wait(tc::smem_u32(&bar_kv_full[stage]), (j / ST) & 1);
@@ -145,7 +147,8 @@ __global__ void __launch_bounds__(192, OCC) attn_tc_kernel(const __grid_constant
           const uint64_t qd = tc::umma_desc_k_sw128(q_smem + c * BM * 128);
           const uint64_t kd = tc::umma_desc_k_sw128(ks + c * KV_CHUNK);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc::umma_ss(tmem + S_COL, qd + 2 * k, kd + 2 * k, idesc_qk, (c | k) != 0);
+          for (int k = 0; k < 4; ++k)
+            if (c * 4 + k < kq) tc::umma_ss(tmem + S_COL, qd + 2 * k, kd + 2 * k, idesc_qk, (c | k) != 0);
         }
         tc::umma_commit(tc::smem_u32(&bar_s));
       };
