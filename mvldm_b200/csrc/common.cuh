@@ -96,11 +96,7 @@ void attention_tc_kv(cudaStream_t s, const bf16* q, int ld_q, int q_col0, const 
 
 // elementwise.cu
 void im2col_input(cudaStream_t s, const float* latents, int n_img, int cin, int h, int w, int kpad, bf16* out);
-void timestep_sinusoid(cudaStream_t s, const int64_t* t, int n, int dim, float* out);
 void timestep_sinusoid_bf16(cudaStream_t s, const int64_t* t, int n, int dim, bf16* out);
-// out[r, n] = act(sum_k in[r,k] * W[n,k] + b[n]); in fp32 [rows, k], W bf16 [n, k]; act: 0 none, 1 silu
-void small_linear(cudaStream_t s, const float* in, int rows, int k, const bf16* w, const float* b, int n, int act,
-                  float* out);
 void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, int n_img, int hw, int groups,
                float eps, const float* gamma, const float* beta, bool silu, bf16* out, float* scratch);
 size_t groupnorm_scratch_floats(int n_img, int groups);

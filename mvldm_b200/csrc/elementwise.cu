@@ -113,45 +113,6 @@ __global__ void sinusoid_kernel(const int64_t* __restrict__ t, int n, int dim, O
   out[(int64_t)r * dim + half + j] = (OutT)sinf(arg);
 }
 
-// small-M linear: one warp per output column, weights streamed once with 16-byte loads.
-template <int RB>
-__global__ void small_linear_kernel(const float* __restrict__ in, int rows, int k, const bf16* __restrict__ w,
-                                    const float* __restrict__ b, int n, int act, float* __restrict__ out) {
-  pdl_wait();
-  pdl_launch_dependents();
-  const int lane = threadIdx.x & 31;
-  const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (col >= n) return;
-  const bf16* wr = w + (int64_t)col * k;
-  for (int r0 = 0; r0 < rows; r0 += RB) {
-    float acc[RB];
-#pragma unroll
-    for (int r = 0; r < RB; ++r) acc[r] = 0.f;
-    for (int kk = lane * 8; kk < k; kk += 256) {
-      float wf[8];
-      load8(wr + kk, wf);
-#pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        if (r0 + r < rows) {
-          const float4 a0 = *reinterpret_cast<const float4*>(in + (int64_t)(r0 + r) * k + kk);
-          const float4 a1 = *reinterpret_cast<const float4*>(in + (int64_t)(r0 + r) * k + kk + 4);
-          acc[r] += a0.x * wf[0] + a0.y * wf[1] + a0.z * wf[2] + a0.w * wf[3] + a1.x * wf[4] + a1.y * wf[5] +
-                    a1.z * wf[6] + a1.w * wf[7];
-        }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      float v = warp_sum(acc[r]);
-      if (lane == 0 && r0 + r < rows) {
-        v += b ? b[col] : 0.f;
-        if (act == 1) v = v / (1.f + expf(-v));
-        out[(int64_t)(r0 + r) * n + col] = v;
-      }
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // GroupNorm over NHWC bf16.  Pass 1 (gn_partial): grid (pixel chunks, images); every thread owns one
 // 8-channel vector column and walks the chunk's pixels with 16-byte loads, per-channel (sum, sum of squares)
@@ -996,21 +957,10 @@ void im2col_input(cudaStream_t s, const float* latents, int n_img, int cin, int 
   launch_pdl(im2col_input_kernel, dim3(grid_for(total, 128)), dim3(128), 0, s, latents, n_img, cin, h, w, kpad, out);
 }
 
-void timestep_sinusoid(cudaStream_t s, const int64_t* t, int n, int dim, float* out) {
-  const int total = n * (dim / 2);
-  launch_pdl(sinusoid_kernel<float>, dim3(ceil_div(total, 128)), dim3(128), 0, s, t, n, dim, out);
-}
-
-// bf16 copy of the same embedding: the A operand of the time_embedding GEMMs (what autocast feeds linear_1 in the reference)
+// timestep embedding in bf16: the A operand of the time_embedding GEMMs (what autocast feeds linear_1 in the reference)
 void timestep_sinusoid_bf16(cudaStream_t s, const int64_t* t, int n, int dim, bf16* out) {
   const int total = n * (dim / 2);
   launch_pdl(sinusoid_kernel<bf16>, dim3(ceil_div(total, 128)), dim3(128), 0, s, t, n, dim, out);
-}
-
-void small_linear(cudaStream_t s, const float* in, int rows, int k, const bf16* w, const float* b, int n, int act,
-                  float* out) {
-  MV_CHECK(k % 8 == 0, "small_linear: K must be a multiple of 8");
-  launch_pdl(small_linear_kernel<8>, dim3(ceil_div(n, 8)), dim3(256), 0, s, in, rows, k, w, b, n, act, out);
 }
 
 size_t groupnorm_scratch_floats(int n_img, int groups) { return (size_t)n_img * GN_MAXP * groups * 2; }
