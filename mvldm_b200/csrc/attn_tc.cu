@@ -874,10 +874,9 @@ void launch(cudaStream_t s, const AttnSrc& a, bf16* out, int batches, int heads,
   AttnParams p{};
   fill_params(p, a, out, batches, heads, d, DPAD, BN);
   constexpr int smem = (DPAD / 64) * BM * 128 + ST * 2 * (DPAD / 64) * BN * 128 + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured)) {
     MV_CUDA(cudaFuncSetAttribute(attn_tc_kernel<DPAD, BN, ST, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   dim3 grid(ceil_div(a.seq_q, BM), batches * heads);
   launch_pdl(attn_tc_kernel<DPAD, BN, ST, OCC>, grid, dim3(192), smem, s, p);
@@ -893,20 +892,18 @@ void launch64(cudaStream_t s, const AttnSrc& a, bf16* out, int batches, int head
   }();
   if (q_in_tmem && a.v_col0 > a.k_col0) {
     constexpr int smem_q = ST * 2 * 128 * 128 + 1024;
-    static bool configured_q = false;
-    if (!configured_q) {
+    static bool configured_q[kMaxDevices] = {};
+    if (first_use_on_device(configured_q)) {
       MV_CUDA(cudaFuncSetAttribute(attn64q_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_q));
-      configured_q = true;
     }
     dim3 grid_q(ceil_div(a.seq_q, BM), batches * heads);
     launch_pdl(attn64q_kernel<ST>, grid_q, dim3(192), smem_q, s, p);
     return;
   }
   constexpr int smem = BM * 128 + ST * 2 * 128 * 128 + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured)) {
     MV_CUDA(cudaFuncSetAttribute(attn64_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   dim3 grid(ceil_div(a.seq_q, BM), batches * heads);
   launch_pdl(attn64_kernel<ST>, grid, dim3(192), smem, s, p);

@@ -43,6 +43,18 @@ extern thread_local int g_launch_count;
     MV_CUDA(cudaPeekAtLastError());   \
   } while (0)
 
+// Function attributes (max dynamic shared memory, ...) belong to a device: a process that drives several GPUs must set
+// them once per device, not once per process.  `flags` is a zero-initialised static array owned by the call site.
+constexpr int kMaxDevices = 64;
+inline bool first_use_on_device(bool (&flags)[kMaxDevices]) {
+  int dev = 0;
+  MV_CUDA(cudaGetDevice(&dev));
+  MV_CHECK(dev >= 0 && dev < kMaxDevices, "device index out of range");
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
+}
+
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
 // Every forward-path kernel is launched with programmaticStreamSerialization: it may be scheduled while its
 // predecessor is still draining, runs its prologue (barrier init, TMEM alloc, descriptor prefetch), then

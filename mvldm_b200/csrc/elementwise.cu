@@ -1099,10 +1099,9 @@ void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, i
     if (C % cb == 0 && cb / 8 <= 16 && cb / cgn <= 16 && c0 % 8 == 0) {
       const size_t slab = (size_t)hw * cb * sizeof(bf16);
       const int cache = slab <= 160 * 1024 ? 1 : 0;
-      static bool configured = false;
-      if (!configured) {
+      static bool configured[kMaxDevices] = {};
+      if (first_use_on_device(configured)) {
         MV_CUDA(cudaFuncSetAttribute(gn_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        configured = true;
       }
       // pixel split over a small cluster when one CTA per (image, channel block) would leave SMs idle
       static const int max_cs = [] {

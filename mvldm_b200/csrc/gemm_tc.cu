@@ -565,10 +565,9 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 template <int BN, int STAGES>
 void launch(cudaStream_t s, const TcParams& p, int splits) {
   constexpr int smem = STAGES * KC * (A_BYTES + BN * BK * 2) + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured)) {
     MV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   static int num_sms = 0;
   if (num_sms == 0) {

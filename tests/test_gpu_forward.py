@@ -337,3 +337,20 @@ def test_cfg_step_batched_equals_two_forwards(gpu_models):
         outs.append(path.step(m, x_T, 960, cin, rays))
     assert rel_err(outs[0], outs[1]) < FWD_TOL
     assert rel_err(outs[0], torch.tensor(g["x_after_step0"]).cuda()) < FWD_TOL
+
+
+def test_two_devices_in_one_process(oracle_weights):
+    """A single process driving two GPUs (the reference runs one process per GPU, but nothing in the library may assume
+    it): per-device kernel attributes, handles and plans; both devices must produce the same bits."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    g = np.load(os.path.join(GOLD, "g1_forward_v4.npz"))
+    inp, ts = torch.tensor(g["inputs"]), torch.tensor(g["timesteps"])
+    outs = []
+    for dev in ("cuda:1", "cuda:0"):           # cuda:1 first: its attributes must not be taken from device 0's
+        m = mv.MultiViewUNet(mv.default_cfg(), 11, 4)
+        m.load_state_dict(oracle_weights)
+        m = m.to(dev).eval()
+        outs.append(m(inp.to(dev), ts.to(dev)).cpu())
+    assert torch.equal(outs[0], outs[1])
+    assert rel_err(outs[0], torch.tensor(g["eps"])) < FWD_TOL
