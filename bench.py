@@ -188,7 +188,7 @@ def run_gpu(args):
     ts_list = [int(t) for t in sched.timesteps]
     ctx, x_T, extr, intr = synthetic.scene(S, V_C, V_T, seed=1 + rank)
     ctx_in = torch.cat([ctx, torch.zeros(S, V_C, 1, H, W)], 2)
-    rays = mv.ray_encode(extr.to(dev), intr.to(dev), H, W)
+    rays = mv.ray_encode(extr.to(dev), intr.to(dev), H, W, use_plucker=args.plucker)
     d_ctx, d_x = ctx_in.to(dev), x_T.to(dev)
 
     # ---- device-resident throughput -------------------------------------------------------------
@@ -303,7 +303,7 @@ def run_gpu(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(args), "views": V_C + V_T, "latent": [H, W], "use_cfg": args.cfg,
-                       "scenes_per_gpu": S, "cuda_graph": not args.no_graph, "variant": args.variant,
+                       "scenes_per_gpu": S, "cuda_graph": not args.no_graph, "variant": args.variant, "plucker": args.plucker,
                        "cfg_one_pass": bool(args.cfg and not args.no_batch_cfg),
                        "l2_policy": "inputs larger than L2: 1.53 GB of bf16 weights are streamed every step (L2 = 126 MB)",
                        "weights": "random-init, seed 0, proj_out re-randomised (SURVEY.md §0.5)"},
@@ -328,6 +328,8 @@ def main():
     ap.add_argument("--no-batch-cfg", action="store_true", help="with --cfg: two back-to-back forwards instead of one pass")
     ap.add_argument("--variant", default="a", choices=["a", "b"], help="a: pretrained_from=None topology (headline); "
                     "b: SD-2.1 topology with per-view Transformer2D blocks")
+    ap.add_argument("--plucker", action="store_true", help="Pluecker ray maps (o x d, d) instead of (o, d): same 6 channels, "
+                    "computed once per sample() outside the step; the denoiser cost is identical")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
