@@ -176,3 +176,19 @@ def test_anchored_plan_matches_reference_index_logic():
     assert p.anchors == [5, 10, 15] and all(a in p.anchors for a, _ in p.chunks)
     with pytest.raises(ValueError):
         mv.anchored_plan([0, 1], 4)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/mvldm_b200.h is the drop-in boundary: it must compile as C (no C++ or torch types in the signatures)
+    and declare exactly the symbols the library exports."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "mvldm_b200.h"\n'
+                   "int main(void) { mvldm_config c; mvldm_gemm_desc d; (void)c; (void)d; return (int)sizeof(mvldm_config) == 0; }\n")
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc, str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
