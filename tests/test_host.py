@@ -192,3 +192,26 @@ def test_header_is_plain_c(tmp_path):
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc, str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_library_sass_uses_tcgen05_tmem_and_tma():
+    """Static evidence that needs no GPU: the shipped library's SASS contains the Blackwell tensor-core, tensor-memory and
+    TMA instructions (B200_PROFILING.md: tcgen05.mma -> UTCHMMA, tcgen05.ld/st -> LDTM/STTM, cp.async.bulk.tensor -> UTMALDG),
+    it is built for sm_100a only, and carries no legacy warp-level MMA."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mvldm_b200", "libmvldm_b200.so")
+    if not os.path.exists(lib):
+        pytest.skip("library not built")
+    elf = subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf and "sm_90" not in elf and "sm_80" not in elf
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    count = lambda m: sass.count(m)  # noqa: E731
+    assert count("UTCHMMA") >= 50          # tcgen05.mma in the GEMM and attention kernels
+    assert count("UTMALDG") >= 20          # TMA tensor loads (3-D / 4-D / 5-D)
+    assert count("LDTM") >= 10 and count("STTM") >= 10   # tcgen05.ld / tcgen05.st (TMEM <-> registers)
+    assert count("UTCBAR") >= 10           # tcgen05.commit -> mbarrier
+    assert count("HMMA.") == 0 or count("UTCHMMA") > 0   # no mma.sync-only fallback
+    assert "HGMMA" not in sass             # wgmma is sm_90a-only
