@@ -197,10 +197,6 @@ int mvldm_op_attention_kv(void* stream, const void* q, int ld_q, int q_col0, con
  * environment; out[slot*512 + tile], slots 0-2 softmax thread (wait S, got S, P handed over), 3-5 MMA thread
  * (got P, PV issued, next QK issued). */
 int mvldm_debug_attn_trace(int64_t* out, int n);
-/* Same for CTA 0 of the last GEMM launch made with MVLDM_GEMM_TRACE set: out[0..8] = kernel entry, prologue done,
- * first TMA issued, last TMA issued, first tile landed, all MMAs issued, accumulator ready, epilogue done, exit. */
-int mvldm_debug_gemm_trace(int64_t* out, int n);
-
 /* GroupNorm (+SiLU) over NHWC bf16, optionally over the channel concat of two sources
  * (torch.cat at mvunet.py:176 + ResnetBlock2D.norm1): out bf16 [n_img, hw, c0+c1]. */
 int mvldm_op_groupnorm(void* stream, const void* x0, int c0, const void* x1, int c1, int n_img, int hw,

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "seq.cuh"
 
 namespace mvldm {
 
@@ -91,21 +92,44 @@ struct Arena {
   }
 };
 
+// One recorded forward for a batch shape: the launch list (fused sequence launches cut at the attention kernels), the device
+// copy of the op descriptors, the activation arena they point into and the CUDA graph of the whole list.
+struct TapRec {
+  Act a;
+};
+struct OpMeta {  // what an op is, for the per-op timing report
+  const char* cat;
+  std::string what;
+  double flops, bytes;
+};
+struct Step {
+  enum Kind { SEQ, ATTN, ATTN_SHARDED, GEMM_SIMT } kind = SEQ;
+  int op_begin = 0, op_end = 0;  // SEQ: ops[op_begin, op_end)
+  // ATTN / ATTN_SHARDED
+  const bf16* qkv = nullptr;
+  bf16* out = nullptr;
+  int batches = 0, seq = 0, heads = 0, d = 0, dpad = 0, seq_local = 0;
+  bool simt = false;
+  mvldm_gemm_desc gemm{};  // GEMM_SIMT
+  OpMeta meta{};
+};
 struct Plan {
   std::vector<int> scene_views;  // views per scene; images of a scene are contiguous
   int H = 0, W = 0;
   DevBuf arena_mem;
   size_t arena_bytes = 0;
   DevBuf in_latents, in_t, out_eps, splitk;
+  std::vector<SeqOp> ops;
+  std::vector<OpMeta> op_meta;
+  std::vector<Step> steps;
+  std::map<std::string, TapRec> taps;  // named intermediate activations (plans recorded with taps enabled keep them all alive)
+  DevBuf dev_ops, sync_words, timing;
+  int launches = 0;  // kernels one execution launches
+  uint64_t last_use = 0;
   cudaGraphExec_t graph = nullptr;
-  int graph_launches = 0;
   ~Plan() {
     if (graph) cudaGraphExecDestroy(graph);
   }
-};
-
-struct TapRec {
-  Act a;
 };
 
 }  // namespace mvldm
@@ -142,48 +166,24 @@ struct mvldm_handle_s {
   std::map<std::vector<int>, std::unique_ptr<Plan>> plans;
   int last_launches = 0;
   bool taps_enabled = false;
-  std::map<std::string, TapRec> taps;
+  Plan* last_plan = nullptr;
 
-  // ---- per-launch profiling (eager mode only): CUDA-event pairs around every op, read back after a sync ----
-  struct ProfRec {
-    const char* cat;
-    std::string what;
-    double flops, bytes;
-    cudaEvent_t e0, e1;
-  };
+  // ---- profiling (mvldm_set_profiling): the launch list runs eagerly with a CUDA-event pair around every launch, and
+  // the sequence kernel stamps %globaltimer / clock64 at every op barrier, so each op inside a fused launch gets its
+  // own in-situ duration ----
   bool profiling = false;
-  std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> event_pool;
-  size_t events_used = 0;
   std::string prof_json;
-  cudaEvent_t next_event() {
-    if (events_used == event_pool.size()) {
-      cudaEvent_t e;
-      MV_CUDA(cudaEventCreate(&e));
-      event_pool.push_back(e);
-    }
-    return event_pool[events_used++];
-  }
-  struct ProfScope {
-    mvldm_handle_s* h;
-    bool on;
-    ProfScope(mvldm_handle_s* h_, const char* cat, const std::string& what, double flops, double bytes)
-        : h(h_), on(h_->profiling && !h_->dry) {
-      if (!on) return;
-      ProfRec r{cat, what, flops, bytes, h->next_event(), h->next_event()};
-      h->prof.push_back(r);
-      cudaEventRecord(r.e0, h->stream);
-    }
-    ~ProfScope() {
-      if (on) cudaEventRecord(h->prof.back().e1, h->stream);
-    }
-  };
+  Plan* prof_plan = nullptr;
 
   // ---- run state ----
   cudaStream_t stream = nullptr;
   cudaStream_t capture_stream = nullptr;  // graphs are recorded here: the caller's stream may be the legacy NULL stream
   Arena arena;
-  bool dry = true;
+  bool dry = true;       // measuring pass: arena offsets and split-K scratch only, nothing is recorded
+  Plan* rec = nullptr;   // plan being recorded
+  int seq_open = -1;     // first op of the sequence launch being assembled, or -1
+  uint64_t use_clock = 0;
   // view-group sharding (mvldm_forward_sharded): local Q against all-gathered K/V in the joint attention
   bool sharded = false;
   int v_total = 0;
@@ -486,7 +486,6 @@ struct mvldm_handle_s {
     for (auto& n : names) MV_CHECK(unused.count(n) || raw.count(n), "mvldm_finalize_weights: missing weight " + n);
     MV_CUDA(cudaStreamSynchronize(s));
     packed_store.clear();
-    groupnorm_init();
     const int L = cfg.num_levels;
     const int* boc = cfg.block_out_channels;
     kpad_in = (9 * cfg.in_channels + 63) / 64 * 64;
@@ -535,6 +534,7 @@ struct mvldm_handle_s {
       it = keep ? std::next(it) : raw.erase(it);
     }
     plans.clear();
+    prof_plan = last_plan = nullptr;
     finalized = true;
   }
 
@@ -547,7 +547,7 @@ struct mvldm_handle_s {
   }
   float* new_f32(size_t count) { return reinterpret_cast<float*>(arena.take(count * sizeof(float))); }
   void tap(const std::string& name, const Act& a) {
-    if (taps_enabled && !dry) taps[name].a = a;
+    if (taps_enabled && !dry) rec->taps[name].a = a;
   }
 
   static mvldm_aseg seg_conv3x3(const Act& a, int stride = 1) {
@@ -565,19 +565,44 @@ struct mvldm_handle_s {
     s.ptr = a.p; s.c = a.c; s.ctot = a.c; s.sh = a.h; s.sw = a.w; s.stride = 1; s.ntaps = 1;
     return s;
   }
+  // ---- recording: every op of the forward lands in the plan's launch list ----
+  void push_op(const SeqOp& op, const char* cat, const std::string& what, double flops, double bytes) {
+    if (seq_open < 0) seq_open = (int)rec->ops.size();
+    rec->ops.push_back(op);
+    rec->op_meta.push_back(OpMeta{cat, what, flops, bytes});
+  }
+  void flush_seq() {  // close the sequence launch under assembly (an attention / callback step follows, or the end)
+    if (seq_open < 0) return;
+    Step st;
+    st.kind = Step::SEQ;
+    st.op_begin = seq_open;
+    st.op_end = (int)rec->ops.size();
+    rec->steps.push_back(st);
+    seq_open = -1;
+  }
   void run_gemm(mvldm_gemm_desc& d, double algo_flops = -1.0) {
     const double M = (double)d.n_img * d.oh * d.ow;
     const char* cat = d.nseg > 0 && d.seg[0].ntaps == 9 ? "gemm_conv3x3" : "gemm_linear";
-    ProfScope ps(this, cat,
-                 "M" + std::to_string((long long)M) + " N" + std::to_string(d.n) + " K" + std::to_string(d.k),
-                 algo_flops >= 0 ? algo_flops : 2.0 * M * d.n * d.k,
-                 2.0 * ((double)d.n * d.k + M * d.n * (d.mode == 1 ? 0.5 : 1.0)));
     if (dry) {
-      if (cfg.impl != MVLDM_IMPL_SIMT) splitk_need = std::max(splitk_need, gemm_tc_workspace_bytes(d));
+      if (cfg.impl != MVLDM_IMPL_SIMT) splitk_need = std::max(splitk_need, seq_gemm_workspace_bytes(d));
       return;
     }
-    if (cfg.impl == MVLDM_IMPL_SIMT) gemm_simt(stream, d);
-    else gemm_tc(stream, d, splitk_ws, splitk_bytes);
+    const std::string what = "M" + std::to_string((long long)M) + " N" + std::to_string(d.n) + " K" + std::to_string(d.k);
+    const double flops = algo_flops >= 0 ? algo_flops : 2.0 * M * d.n * d.k;
+    const double bytes = 2.0 * ((double)d.n * d.k + M * d.n * (d.mode == 1 ? 0.5 : 1.0));
+    if (cfg.impl == MVLDM_IMPL_SIMT) {
+      flush_seq();
+      Step st;
+      st.kind = Step::GEMM_SIMT;
+      st.gemm = d;
+      st.meta = OpMeta{cat, what, flops, bytes};
+      rec->steps.push_back(st);
+      return;
+    }
+    SeqOp op, red;
+    const bool need_reduce = seq_plan_gemm(d, splitk_ws, splitk_bytes, op, red);
+    push_op(op, cat, what, flops, bytes);
+    if (need_reduce) push_op(red, "splitk_reduce", what, 0.0, 0.0);
   }
   // out = A-segments x W^T (+bias +rowvec +residual), bf16 NHWC
   void gemm(std::initializer_list<mvldm_aseg> segs, const Packed& w, const Act& out, const float* rowvec = nullptr,
@@ -593,45 +618,47 @@ struct mvldm_handle_s {
     run_gemm(d, algo_flops);
   }
   void gn(const Act& x0, const Act* x1, const float* g, const float* b, float eps, bool silu, const Act& out) {
-    float* scratch = new_f32(groupnorm_scratch_floats(x0.n, cfg.norm_groups));
-    ProfScope ps(this, "groupnorm", "tokens" + std::to_string(x0.tokens()) + " C" + std::to_string(out.c), 0.0,
-                 4.0 * (double)out.tokens() * out.c);
+    float* scratch = new_f32(seq_groupnorm_scratch_floats(x0.n, out.c, cfg.norm_groups));
     if (dry) return;
-    groupnorm(stream, x0.p, x0.c, x1 ? x1->p : nullptr, x1 ? x1->c : 0, x0.n, x0.h * x0.w, cfg.norm_groups, eps, g, b,
-              silu, out.p, scratch);
+    SeqOp op;
+    seq_plan_groupnorm(x0.p, x0.c, x1 ? x1->p : nullptr, x1 ? x1->c : 0, x0.n, x0.h * x0.w, cfg.norm_groups, eps, g, b, silu,
+                       out.p, scratch, seq_grid(), op);
+    push_op(op, "groupnorm", "tokens" + std::to_string(x0.tokens()) + " C" + std::to_string(out.c), 0.0,
+            4.0 * (double)out.tokens() * out.c);
   }
   void ln(const Act& x, const float* g, const float* b, const Act& out) {
-    ProfScope ps(this, "layernorm", "tokens" + std::to_string(x.tokens()) + " C" + std::to_string(x.c), 0.0,
-                 4.0 * (double)x.tokens() * x.c);
     if (dry) return;
-    layernorm(stream, x.p, (int)x.tokens(), x.c, 1e-5f, g, b, out.p);
+    SeqOp op;
+    seq_plan_layernorm(x.p, (int)x.tokens(), x.c, 1e-5f, g, b, out.p, op);
+    push_op(op, "layernorm", "tokens" + std::to_string(x.tokens()) + " C" + std::to_string(x.c), 0.0,
+            4.0 * (double)x.tokens() * x.c);
   }
   void attn(const Act& qkv, const Act& out, int batches, int seq, const MvW& m) {
-    // algorithmic FLOPs: QK^T and PV over the un-padded head dim, 4 * seq^2 * C per batch
-    ProfScope ps(this, seq > out.h * out.w ? "attention_joint" : "attention_per_view",
-                 "batches" + std::to_string(batches) + " seq" + std::to_string(seq) + " d" + std::to_string(m.d),
-                 4.0 * batches * (double)seq * seq * m.c, 2.0 * (double)out.tokens() * (4.0 * m.heads * m.dpad));
     if (dry) return;
-    if (cfg.impl == MVLDM_IMPL_TC) attention_tc(stream, qkv.p, out.p, batches, seq, m.heads, m.d, m.dpad);
-    else attention_simt(stream, qkv.p, out.p, batches, seq, m.heads, m.d, m.dpad);
+    flush_seq();
+    Step st;
+    st.kind = Step::ATTN;
+    st.qkv = qkv.p; st.out = out.p; st.batches = batches; st.seq = seq; st.heads = m.heads; st.d = m.d; st.dpad = m.dpad;
+    st.simt = cfg.impl != MVLDM_IMPL_TC;
+    // algorithmic FLOPs: QK^T and PV over the un-padded head dim, 4 * seq^2 * C per batch
+    st.meta = OpMeta{seq > out.h * out.w ? "attention_joint" : "attention_per_view",
+                     "batches" + std::to_string(batches) + " seq" + std::to_string(seq) + " d" + std::to_string(m.d),
+                     4.0 * batches * (double)seq * seq * m.c, 2.0 * (double)out.tokens() * (4.0 * m.heads * m.dpad)};
+    rec->steps.push_back(st);
   }
 
   // This rank's views supply the queries; K and V of every view of the scene are all-gathered by the host callback.
   void joint_attention_sharded(const Act& qkv, const Act& out, int seq_local, const MvW& m) {
-    const int H = m.heads, hd = H * m.dpad;
-    const size_t bytes = (size_t)seq_local * 2 * hd * sizeof(bf16);
-    const int world = v_total / (int)(qkv.n);
-    ProfScope ps(this, "attention_joint_sharded", "seq_q" + std::to_string(seq_local) + " seq_kv" + std::to_string(seq_local * world),
-                 4.0 * (double)seq_local * seq_local * world * m.c, 0.0);
     if (dry) return;
-    MV_CHECK(bytes * world <= kv_recv_bytes, "mvldm_forward_sharded: kv_recv buffer too small");
-    // K|V columns of the packed q|k|v rows -> contiguous slab
-    MV_CUDA(cudaMemcpy2DAsync(kv_send, (size_t)2 * hd * sizeof(bf16), qkv.p + hd, (size_t)3 * hd * sizeof(bf16),
-                              (size_t)2 * hd * sizeof(bf16), seq_local, cudaMemcpyDeviceToDevice, stream));
-    const int rc = exchange(exchange_user, kv_send, kv_recv, (int64_t)bytes, stream);
-    MV_CHECK(rc == 0, "mvldm_forward_sharded: K/V exchange callback failed");
-    attention_tc_kv(stream, qkv.p, 3 * hd, 0, reinterpret_cast<const bf16*>(kv_recv), 2 * hd, 0, hd, out.p, 1, seq_local,
-                    seq_local * world, H, m.d, m.dpad);
+    const int world = v_total / (int)(qkv.n);
+    flush_seq();
+    Step st;
+    st.kind = Step::ATTN_SHARDED;
+    st.qkv = qkv.p; st.out = out.p; st.batches = 1; st.seq = seq_local * world; st.seq_local = seq_local;
+    st.heads = m.heads; st.d = m.d; st.dpad = m.dpad;
+    st.meta = OpMeta{"attention_joint_sharded", "seq_q" + std::to_string(seq_local) + " seq_kv" + std::to_string(seq_local * world),
+                     4.0 * (double)seq_local * seq_local * world * m.c, 0.0};
+    rec->steps.push_back(st);
   }
 
   Act resnet(const ResnetW& r, const Act& x0, const Act* x1, const float* temb) {
@@ -761,8 +788,9 @@ struct mvldm_handle_s {
     Act e2 = new_act(n, 1, 1, temb_dim);
     float* temb = new_f32((size_t)n * temb_total);
     if (!dry) {
-      ProfScope ps(this, "time_embedding", "sinusoid rows" + std::to_string(n), 0.0, 0.0);
-      timestep_sinusoid_bf16(stream, tsteps, n, boc[0], sinus.p);
+      SeqOp op;
+      seq_plan_sinusoid(tsteps, n, boc[0], sinus.p, op);
+      push_op(op, "time_embedding", "sinusoid rows" + std::to_string(n), 0.0, 0.0);
     }
     gemm({seg_1x1(sinus)}, time1, e1, nullptr, 0, nullptr, 3);
     gemm({seg_1x1(e1)}, time2, e2, nullptr, 0, nullptr, 3);  // SiLU(emb): every consumer (ResnetBlock2D) applies it first
@@ -779,8 +807,9 @@ struct mvldm_handle_s {
     // ---- conv_in on the im2col'd fp32 input
     Act col = new_act(n, Hh, Ww, kpad_in);
     if (!dry) {
-      ProfScope ps(this, "input_im2col", "", 0.0, (double)col.tokens() * (kpad_in * 2 + cfg.in_channels * 4));
-      im2col_input(stream, latents, n, cfg.in_channels, Hh, Ww, kpad_in, col.p);
+      SeqOp op;
+      seq_plan_im2col(latents, n, cfg.in_channels, Hh, Ww, kpad_in, col.p, op);
+      push_op(op, "input_im2col", "", 0.0, (double)col.tokens() * (kpad_in * 2 + cfg.in_channels * 4));
     }
     Act x = new_act(n, Hh, Ww, boc[0]);
     gemm({seg_1x1(col)}, conv_in, x, nullptr, 0, nullptr, 0, 2.0 * (double)x.tokens() * boc[0] * 9 * cfg.in_channels);
@@ -830,8 +859,9 @@ struct mvldm_handle_s {
       if (l != L - 1) {
         Act u = new_act(n, x.h * 2, x.w * 2, x.c);
         if (!dry) {
-          ProfScope ps(this, "upsample", "", 0.0, 2.5 * (double)u.tokens() * u.c);
-          upsample_nearest2x(stream, x.p, n, x.h, x.w, x.c, u.p);
+          SeqOp op;
+          seq_plan_upsample(x.p, n, x.h, x.w, x.c, u.p, op);
+          push_op(op, "upsample", "", 0.0, 2.5 * (double)u.tokens() * u.c);
         }
         Act y = new_act(n, u.h, u.w, u.c);
         gemm({seg_conv3x3(u)}, up_conv[l], y);
@@ -852,14 +882,39 @@ struct mvldm_handle_s {
     run_gemm(d, 2.0 * (double)x.tokens() * cfg.out_channels * conv_out.k);
   }
 
-  Plan& plan_for(const std::vector<int>& sv, int H, int W) {
-    std::vector<int> key{H, W, taps_enabled ? 1 : 0};
+  // ---- plans: measured, allocated and recorded once per batch shape; a small LRU keeps the device memory bounded ----
+  static constexpr size_t kMaxPlans = 6;
+  Plan& plan_for(const std::vector<int>& sv, int H, int W, bool shard = false) {
+    std::vector<int> key{H, W, taps_enabled ? 1 : 0, shard ? v_total : 0};
+    if (shard) {  // the recorded launch list holds the caller's exchange buffers
+      const uint64_t a = reinterpret_cast<uint64_t>(kv_send), b = reinterpret_cast<uint64_t>(kv_recv);
+      for (uint64_t v : {a, b}) {
+        key.push_back((int)(v & 0xffffffffu));
+        key.push_back((int)(v >> 32));
+      }
+    }
     key.insert(key.end(), sv.begin(), sv.end());
     const int n = total_views(sv);
     auto it = plans.find(key);
-    if (it != plans.end()) return *it->second;
+    if (it != plans.end()) {
+      it->second->last_use = ++use_clock;
+      return *it->second;
+    }
+    if (plans.size() >= kMaxPlans) {  // evict the least recently used plan (arena, scratch, graph)
+      MV_CUDA(cudaDeviceSynchronize());
+      auto victim = plans.begin();
+      for (auto jt = plans.begin(); jt != plans.end(); ++jt)
+        if (jt->second->last_use < victim->second->last_use) victim = jt;
+      if (prof_plan == victim->second.get()) prof_plan = nullptr;
+      if (last_plan == victim->second.get()) last_plan = nullptr;
+      plans.erase(victim);
+    }
+    seq_configure();
     std::unique_ptr<Plan> p(new Plan());
     p->scene_views = sv; p->H = H; p->W = W;
+    p->last_use = ++use_clock;
+    sharded = shard;
+    // pass 1: arena offsets and split-K scratch
     dry = true;
     arena = Arena();
     arena.measuring = true;
@@ -872,9 +927,83 @@ struct mvldm_handle_s {
     p->in_latents.alloc((size_t)n * cfg.in_channels * H * W * sizeof(float));
     p->in_t.alloc((size_t)n * sizeof(int64_t));
     p->out_eps.alloc((size_t)n * cfg.out_channels * H * W * sizeof(float));
+    // pass 2: record the launch list against the real buffers
+    dry = false;
+    arena = Arena();
+    arena.measuring = false;
+    arena.base = reinterpret_cast<char*>(p->arena_mem.p);
+    arena.cap = p->arena_bytes;
+    splitk_ws = p->splitk.p;
+    splitk_bytes = p->splitk.bytes;
+    rec = p.get();
+    seq_open = -1;
+    try {
+      run((const float*)p->in_latents.p, (const int64_t*)p->in_t.p, sv, H, W, (float*)p->out_eps.p);
+      flush_seq();
+    } catch (...) {
+      rec = nullptr;
+      sharded = false;
+      throw;
+    }
+    rec = nullptr;
+    sharded = false;
+    p->dev_ops.alloc(std::max<size_t>(1, p->ops.size()) * sizeof(SeqOp));
+    size_t stamps = 0;
+    for (const Step& st : p->steps) {
+      if (st.kind != Step::SEQ) continue;
+      seq_link_prefetch(p->ops.data() + st.op_begin, st.op_end - st.op_begin, reinterpret_cast<const SeqOp*>(p->dev_ops.p) + st.op_begin);
+      stamps += 2 * (size_t)(st.op_end - st.op_begin) + 2;
+    }
+    if (!p->ops.empty())
+      MV_CUDA(cudaMemcpy(p->dev_ops.p, p->ops.data(), p->ops.size() * sizeof(SeqOp), cudaMemcpyHostToDevice));
+    p->sync_words.alloc(2 * sizeof(unsigned));
+    MV_CUDA(cudaMemset(p->sync_words.p, 0, 2 * sizeof(unsigned)));
+    p->timing.alloc(stamps * 2 * sizeof(long long));
+    p->launches = 0;
+    for (const Step& st : p->steps) p->launches += st.kind == Step::ATTN_SHARDED ? 2 : 1;
     Plan& ref = *p;
     plans[key] = std::move(p);
     return ref;
+  }
+
+  static int op_barriers(const SeqOp& o) { return o.c.type == SEQ_GN && !o.c.gn.warp_mode && o.c.gn.ps > 1 ? 1 : 0; }
+
+  // issue the plan's launches on `s` (eagerly, or into a stream capture); with `events` every launch is bracketed
+  void execute(Plan& p, cudaStream_t s, std::vector<cudaEvent_t>* events) {
+    long long* stamp = events ? reinterpret_cast<long long*>(p.timing.p) : nullptr;
+    size_t ev = 0;
+    for (const Step& st : p.steps) {
+      if (events) MV_CUDA(cudaEventRecord((*events)[ev++], s));
+      switch (st.kind) {
+        case Step::SEQ: {
+          seq_launch(s, reinterpret_cast<const SeqOp*>(p.dev_ops.p) + st.op_begin, st.op_end - st.op_begin,
+                     reinterpret_cast<unsigned*>(p.sync_words.p), stamp);
+          if (stamp) stamp += 2 * (2 * (size_t)(st.op_end - st.op_begin) + 2);
+          break;
+        }
+        case Step::ATTN:
+          if (st.simt) attention_simt(s, st.qkv, st.out, st.batches, st.seq, st.heads, st.d, st.dpad);
+          else attention_tc(s, st.qkv, st.out, st.batches, st.seq, st.heads, st.d, st.dpad);
+          break;
+        case Step::ATTN_SHARDED: {
+          const int hd = st.heads * st.dpad;
+          const size_t bytes = (size_t)st.seq_local * 2 * hd * sizeof(bf16);
+          MV_CHECK(bytes * (st.seq / st.seq_local) <= kv_recv_bytes, "mvldm_forward_sharded: kv_recv buffer too small");
+          // K|V columns of the packed q|k|v rows -> contiguous slab
+          MV_CUDA(cudaMemcpy2DAsync(kv_send, (size_t)2 * hd * sizeof(bf16), st.qkv + hd, (size_t)3 * hd * sizeof(bf16),
+                                    (size_t)2 * hd * sizeof(bf16), st.seq_local, cudaMemcpyDeviceToDevice, s));
+          const int rc = exchange(exchange_user, kv_send, kv_recv, (int64_t)bytes, s);
+          MV_CHECK(rc == 0, "mvldm_forward_sharded: K/V exchange callback failed");
+          attention_tc_kv(s, st.qkv, 3 * hd, 0, reinterpret_cast<const bf16*>(kv_recv), 2 * hd, 0, hd, st.out, 1, st.seq_local,
+                          st.seq, st.heads, st.d, st.dpad);
+          break;
+        }
+        case Step::GEMM_SIMT:
+          gemm_simt(s, st.gemm);
+          break;
+      }
+      if (events) MV_CUDA(cudaEventRecord((*events)[ev++], s));
+    }
   }
 
   void forward(cudaStream_t s, const float* latents, const int64_t* tsteps, const std::vector<int>& sv, int H, int W,
@@ -885,96 +1014,123 @@ struct mvldm_handle_s {
     const int n = total_views(sv);
     const int down = 1 << (cfg.num_levels - 1);
     MV_CHECK(H % down == 0 && W % down == 0, "latent size must be divisible by 2^(levels-1)");
-    Plan& p = plan_for(sv, H, W);
     stream = s;
-    arena = Arena();
-    arena.measuring = false;
-    arena.base = reinterpret_cast<char*>(p.arena_mem.p);
-    arena.cap = p.arena_bytes;
-    splitk_ws = p.splitk.p;
-    splitk_bytes = p.splitk.bytes;
-    dry = false;
-    g_launch_count = 0;
+    Plan& p = plan_for(sv, H, W);
+    last_plan = &p;
     const size_t in_bytes = (size_t)n * cfg.in_channels * H * W * sizeof(float);
     const size_t out_bytes = (size_t)n * cfg.out_channels * H * W * sizeof(float);
-    const bool graph = cfg.use_cuda_graph && !taps_enabled && !profiling;
-    if (!graph) {
-      taps.clear();
-      prof.clear();
-      events_used = 0;
-      run(latents, tsteps, sv, H, W, out);
-      last_launches = g_launch_count;
-      return;
-    }
-    // graph path: stage through fixed buffers so the captured pointers stay valid for any caller tensors
+    // the recorded launches read and write fixed buffers, so the list (and its graph) is valid for any caller tensors
     MV_CUDA(cudaMemcpyAsync(p.in_latents.p, latents, in_bytes, cudaMemcpyDeviceToDevice, s));
     MV_CUDA(cudaMemcpyAsync(p.in_t.p, tsteps, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
-    if (!p.graph) {
-      cudaStreamCaptureStatus st;
-      MV_CUDA(cudaStreamIsCapturing(s, &st));
-      if (st != cudaStreamCaptureStatusNone) {  // caller is already capturing: just record into their graph
-        run((const float*)p.in_latents.p, (const int64_t*)p.in_t.p, sv, H, W, (float*)p.out_eps.p);
-        last_launches = g_launch_count;
-        MV_CUDA(cudaMemcpyAsync(out, p.out_eps.p, out_bytes, cudaMemcpyDeviceToDevice, s));
-        return;
+    last_launches = p.launches;
+    const bool graph = cfg.use_cuda_graph && !taps_enabled && !profiling;
+    cudaStreamCaptureStatus cst;
+    MV_CUDA(cudaStreamIsCapturing(s, &cst));
+    if (!graph || cst != cudaStreamCaptureStatusNone) {  // eager, or the caller is capturing: record into their graph
+      if (profiling && cst == cudaStreamCaptureStatusNone) {
+        while (event_pool.size() < 2 * p.steps.size()) {
+          cudaEvent_t e;
+          MV_CUDA(cudaEventCreate(&e));
+          event_pool.push_back(e);
+        }
+        MV_CUDA(cudaMemsetAsync(p.timing.p, 0, p.timing.bytes, s));
+        execute(p, s, &event_pool);
+        prof_plan = &p;
+      } else {
+        execute(p, s, nullptr);
       }
-      cudaGraph_t g = nullptr;
-      if (!capture_stream) MV_CUDA(cudaStreamCreateWithFlags(&capture_stream, cudaStreamNonBlocking));
-      stream = capture_stream;
-      MV_CUDA(cudaStreamBeginCapture(capture_stream, cudaStreamCaptureModeThreadLocal));
-      try {
-        run((const float*)p.in_latents.p, (const int64_t*)p.in_t.p, sv, H, W, (float*)p.out_eps.p);
-      } catch (...) {
-        cudaStreamEndCapture(capture_stream, &g);
-        if (g) cudaGraphDestroy(g);
-        stream = s;
-        throw;
+    } else {
+      if (!p.graph) {
+        cudaGraph_t g = nullptr;
+        if (!capture_stream) MV_CUDA(cudaStreamCreateWithFlags(&capture_stream, cudaStreamNonBlocking));
+        MV_CUDA(cudaStreamBeginCapture(capture_stream, cudaStreamCaptureModeThreadLocal));
+        try {
+          execute(p, capture_stream, nullptr);
+        } catch (...) {
+          cudaStreamEndCapture(capture_stream, &g);
+          if (g) cudaGraphDestroy(g);
+          throw;
+        }
+        MV_CUDA(cudaStreamEndCapture(capture_stream, &g));
+        cudaError_t e = cudaGraphInstantiate(&p.graph, g, 0);
+        cudaGraphDestroy(g);
+        MV_CUDA(e);
       }
-      MV_CUDA(cudaStreamEndCapture(capture_stream, &g));
-      stream = s;
-      p.graph_launches = g_launch_count;
-      cudaError_t e = cudaGraphInstantiate(&p.graph, g, 0);
-      cudaGraphDestroy(g);
-      MV_CUDA(e);
+      MV_CUDA(cudaGraphLaunch(p.graph, s));
     }
-    MV_CUDA(cudaGraphLaunch(p.graph, s));
-    last_launches = p.graph_launches;
     MV_CUDA(cudaMemcpyAsync(out, p.out_eps.p, out_bytes, cudaMemcpyDeviceToDevice, s));
   }
 };
 
-// (forward_sharded is a thin eager wrapper around run(); see mvldm_forward_sharded below)
-// Folds the event pairs of the last profiled forward into a JSON string (synchronises the device).
+// Folds the timings of the last profiled forward into a JSON string (synchronises the device): every launch has a
+// CUDA-event pair; the ops inside a sequence launch split its event time by their in-kernel clock64 stamps.
 static const char* profile_report(mvldm_handle_s* h) {
   MV_CUDA(cudaDeviceSynchronize());
+  MV_CHECK(h->prof_plan != nullptr, "mvldm_profile_json: run a forward with profiling enabled first");
+  Plan& p = *h->prof_plan;
+  std::vector<long long> stamps(p.timing.bytes / sizeof(long long));
+  if (!stamps.empty()) MV_CUDA(cudaMemcpy(stamps.data(), p.timing.p, p.timing.bytes, cudaMemcpyDeviceToHost));
   struct Agg {
     int n = 0;
-    double ms = 0, flops = 0, bytes = 0;
+    double us = 0, flops = 0, bytes = 0;
   };
   std::map<std::string, Agg> agg;
-  std::string ops = "[";
-  for (size_t i = 0; i < h->prof.size(); ++i) {
-    const auto& r = h->prof[i];
-    float ms = 0.f;
-    MV_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
-    Agg& a = agg[r.cat];
-    a.n++; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
-    char buf[256];
-    snprintf(buf, sizeof buf, "%s{\"cat\":\"%s\",\"what\":\"%s\",\"us\":%.2f,\"gflop\":%.3f}", i ? "," : "", r.cat,
-             r.what.c_str(), ms * 1e3, r.flops * 1e-9);
+  std::string ops = "[", launches = "[";
+  bool first_op = true, first_launch = true;
+  auto add = [&](const OpMeta& m, double us) {
+    Agg& a = agg[m.cat];
+    a.n++; a.us += us; a.flops += m.flops; a.bytes += m.bytes;
+    char buf[320];
+    snprintf(buf, sizeof buf, "%s{\"cat\":\"%s\",\"what\":\"%s\",\"us\":%.2f,\"gflop\":%.3f}", first_op ? "" : ",", m.cat,
+             m.what.c_str(), us, m.flops * 1e-9);
     ops += buf;
+    first_op = false;
+  };
+  size_t ev = 0, so = 0;
+  for (const Step& st : p.steps) {
+    float ms = 0.f;
+    MV_CUDA(cudaEventElapsedTime(&ms, h->event_pool[ev], h->event_pool[ev + 1]));
+    ev += 2;
+    const double us = ms * 1e3;
+    double gflop = 0.0;
+    if (st.kind == Step::SEQ) {
+      const int nops = st.op_end - st.op_begin;
+      const long long* t = stamps.data() + so;  // pairs (globaltimer ns, clock64) at start, after each barrier, at the end
+      so += 2 * (2 * (size_t)nops + 2);
+      int nb = 0;
+      for (int i = 0; i < nops; ++i) nb += mvldm_handle_s::op_barriers(p.ops[st.op_begin + i]) + (i + 1 < nops ? 1 : 0);
+      const double clocks = (double)(t[2 * (nb + 1) + 1] - t[1]);
+      int idx = 0;
+      for (int i = 0; i < nops; ++i) {
+        const int adv = mvldm_handle_s::op_barriers(p.ops[st.op_begin + i]) + 1;
+        const double frac = clocks > 0 ? (double)(t[2 * (idx + adv) + 1] - t[2 * idx + 1]) / clocks : 1.0 / nops;
+        idx += adv;
+        add(p.op_meta[st.op_begin + i], us * frac);   // launch overhead is shared in proportion
+        gflop += p.op_meta[st.op_begin + i].flops * 1e-9;
+      }
+    } else {
+      add(st.meta, us);
+      gflop = st.meta.flops * 1e-9;
+    }
+    char buf[200];
+    snprintf(buf, sizeof buf, "%s{\"kind\":\"%s\",\"ops\":%d,\"us\":%.2f,\"gflop\":%.3f}", first_launch ? "" : ",",
+             st.kind == Step::SEQ ? "seq" : (st.kind == Step::GEMM_SIMT ? "gemm_simt" : "attention"),
+             st.kind == Step::SEQ ? st.op_end - st.op_begin : 1, us, gflop);
+    launches += buf;
+    first_launch = false;
   }
   ops += "]";
+  launches += "]";
   std::string out = "{\"categories\":{";
   bool first = true;
   for (auto& kv : agg) {
     char buf[256];
     snprintf(buf, sizeof buf, "%s\"%s\":{\"launches\":%d,\"us\":%.2f,\"gflop\":%.3f,\"mbytes\":%.3f}", first ? "" : ",",
-             kv.first.c_str(), kv.second.n, kv.second.ms * 1e3, kv.second.flops * 1e-9, kv.second.bytes * 1e-6);
+             kv.first.c_str(), kv.second.n, kv.second.us, kv.second.flops * 1e-9, kv.second.bytes * 1e-6);
     out += buf;
     first = false;
   }
-  out += "},\"ops\":" + ops + "}";
+  out += "},\"ops\":" + ops + ",\"launches\":" + launches + "}";
   h->prof_json = out;
   return h->prof_json.c_str();
 }
@@ -1122,31 +1278,23 @@ int mvldm_forward_sharded(mvldm_handle h, void* stream, const float* latents, co
   MV_CHECK(h->cfg.impl == MVLDM_IMPL_TC, "view-group sharding needs the tcgen05 kernels");
   MV_CHECK(V_local > 0 && V_total % V_local == 0, "V_total must be a multiple of V_local (equal view groups)");
   MV_CUDA(cudaSetDevice(h->device));
-  Plan& p = h->plan_for(std::vector<int>{V_local}, H, W);
   h->stream = (cudaStream_t)stream;
-  h->arena = Arena();
-  h->arena.measuring = false;
-  h->arena.base = reinterpret_cast<char*>(p.arena_mem.p);
-  h->arena.cap = p.arena_bytes;
-  h->splitk_ws = p.splitk.p;
-  h->splitk_bytes = p.splitk.bytes;
-  h->dry = false;
-  h->sharded = true;
   h->v_total = V_total;
   h->kv_send = kv_send;
   h->kv_recv = kv_recv;
   h->kv_recv_bytes = (size_t)kv_recv_bytes;
   h->exchange = exchange;
   h->exchange_user = user;
-  g_launch_count = 0;
-  try {
-    h->run(latents, timesteps, std::vector<int>{V_local}, H, W, out);
-  } catch (...) {
-    h->sharded = false;
-    throw;
-  }
-  h->sharded = false;
-  h->last_launches = g_launch_count;
+  const std::vector<int> sv{V_local};
+  Plan& p = h->plan_for(sv, H, W, true);
+  cudaStream_t s = (cudaStream_t)stream;
+  MV_CUDA(cudaMemcpyAsync(p.in_latents.p, latents, (size_t)V_local * h->cfg.in_channels * H * W * sizeof(float),
+                          cudaMemcpyDeviceToDevice, s));
+  MV_CUDA(cudaMemcpyAsync(p.in_t.p, timesteps, (size_t)V_local * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+  h->execute(p, s, nullptr);  // eager: the exchange callback re-enters the host
+  MV_CUDA(cudaMemcpyAsync(out, p.out_eps.p, (size_t)V_local * h->cfg.out_channels * H * W * sizeof(float),
+                          cudaMemcpyDeviceToDevice, s));
+  h->last_launches = p.launches;
   MV_API_END
 }
 
@@ -1179,8 +1327,9 @@ int mvldm_enable_taps(mvldm_handle h, int enable) {
 int mvldm_debug_tap(mvldm_handle h, void* stream, const char* name, float* out, int64_t* numel) {
   MV_API_BEGIN
   MV_CHECK(h && name && numel, "null argument");
-  auto it = h->taps.find(name);
-  MV_CHECK(it != h->taps.end(), std::string("no such tap (enable taps and run a forward first): ") + name);
+  MV_CHECK(h->last_plan != nullptr, "no forward has run yet");
+  auto it = h->last_plan->taps.find(name);
+  MV_CHECK(it != h->last_plan->taps.end(), std::string("no such tap (enable taps and run a forward first): ") + name);
   const Act& a = it->second.a;
   *numel = a.tokens() * a.c;
   if (out) nhwc_to_nchw_f32((cudaStream_t)stream, a.p, a.n, a.h * a.w, a.c, out);
@@ -1238,14 +1387,6 @@ int mvldm_op_attention(void* stream, int impl, const void* qkv, void* out, int b
     attention_tc((cudaStream_t)stream, (const bf16*)qkv, (bf16*)out, batches, seq, heads, d, dpad);
   else
     attention_simt((cudaStream_t)stream, (const bf16*)qkv, (bf16*)out, batches, seq, heads, d, dpad);
-  MV_API_END
-}
-
-int mvldm_debug_gemm_trace(int64_t* out, int n) {
-  MV_API_BEGIN
-  MV_CHECK(out && n > 0 && n <= 64, "bad arguments");
-  MV_CUDA(cudaDeviceSynchronize());
-  gemm_trace_read(reinterpret_cast<long long*>(out), n);
   MV_API_END
 }
 

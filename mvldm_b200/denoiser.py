@@ -328,8 +328,11 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
         if dev.type != "cuda":
             raise RuntimeError("mvldm_b200: the denoiser must live on a CUDA device (no CPU fallback)")
         h = self._ensure_handle(dev)
-        vers = self._versions() if (force or self._dirty or self.training) else h.synced_versions
-        if not force and h.synced_versions is not None and h.synced_versions == vers:
+        # the (data_ptr, version) tuple is recomputed on every call (~700 entries, microseconds against a multi-ms
+        # forward): in-place updates made in eval mode (EMA copy_to, AveragedModel.update_parameters, p.data.copy_) must
+        # not leave a stale packed copy behind
+        vers = self._versions()
+        if not force and not self._dirty and h.synced_versions is not None and h.synced_versions == vers:
             self._dirty = False
             return
         lib = _lib.load()
