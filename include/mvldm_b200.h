@@ -172,7 +172,7 @@ typedef struct {
   int32_t rowvec_ld;
   const void* residual;         /* bf16 [M, res_ld] or NULL */
   int32_t res_ld;
-  int32_t mode;                 /* 0 bf16 [M,ldo]; 1 GEGLU (16-col interleave) -> bf16 [M, N/2]; 2 fp32 NCHW, n_valid channels;
+  int32_t mode;                 /* 0 bf16 [M,ldo]; 1 GEGLU (8-col interleave: columns [16j,16j+8) values, [16j+8,16j+16) their gates) -> bf16 [M, N/2]; 2 fp32 NCHW, n_valid channels;
                                    3 like 0 with SiLU on the result; 4 fp32 [M,ldo] */
   void* out;
   int32_t ldo;
@@ -197,6 +197,14 @@ int mvldm_op_attention_kv(void* stream, const void* q, int ld_q, int q_col0, con
  * environment; out[slot*512 + tile], slots 0-2 softmax thread (wait S, got S, P handed over), 3-5 MMA thread
  * (got P, PV issued, next QK issued). */
 int mvldm_debug_attn_trace(int64_t* out, int n);
+/* Debug / measurement: one fused sequence launch of `n_ops` empty ops, i.e. n_ops - 1 grid barriers and nothing else
+ * (tools/seq_barrier_bench.py: the cost of an op boundary inside the sequence kernel). */
+int mvldm_debug_seq_empty_ops(void* stream, int n_ops);
+/* Debug: every following sequence launch writes its barrier timeline into `device_buffer` ([barrier][CTA][4] int64:
+ * %globaltimer ns at barrier entry of thread 0, when the whole CTA has arrived, when the barrier released it, clock64);
+ * NULL switches it off.  The buffer must hold barriers x CTAs x 32 bytes of the longest launch (tools/seq_trace.py). */
+int mvldm_debug_seq_trace(void* device_buffer);
+
 /* GroupNorm (+SiLU) over NHWC bf16, optionally over the channel concat of two sources
  * (torch.cat at mvunet.py:176 + ResnetBlock2D.norm1): out bf16 [n_img, hw, c0+c1]. */
 int mvldm_op_groupnorm(void* stream, const void* x0, int c0, const void* x1, int c1, int n_img, int hw,

@@ -70,6 +70,8 @@ SYMBOLS = {
     "mvldm_op_gemm": (c_int, [c_void_p, c_int, POINTER(GemmDesc)]),
     "mvldm_op_attention": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int]),
     "mvldm_debug_attn_trace": (c_int, [POINTER(c_int64), c_int]),
+    "mvldm_debug_seq_empty_ops": (c_int, [c_void_p, c_int]),
+    "mvldm_debug_seq_trace": (c_int, [c_void_p]),
     "mvldm_op_groupnorm": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
                                    c_void_p, c_int, c_void_p, c_void_p]),
     "mvldm_op_layernorm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),

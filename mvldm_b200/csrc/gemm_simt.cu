@@ -120,9 +120,9 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const __grid_constant__ 
     } else if (d.mode == 4) {
       reinterpret_cast<float*>(d.out)[(int64_t)m * d.ldo + n] = val(c);
     } else if (d.mode == 1) {
-      if ((c & 31) < 16) {  // columns [32j,32j+16) are x, [32j+16,32j+32) the matching gates
-        const float x = val(c), g = val(c + 16);
-        const int oc = (n / 32) * 16 + (n & 15);
+      if ((c & 15) < 8) {  // columns [16j,16j+8) are x, [16j+8,16j+16) the matching gates
+        const float x = val(c), g = val(c + 8);
+        const int oc = (n / 16) * 8 + (n & 7);
         reinterpret_cast<bf16*>(d.out)[(int64_t)m * d.ldo + oc] = __float2bfloat16(x * gelu_exact(g));
       }
     } else {

@@ -457,15 +457,15 @@ struct mvldm_handle_s {
       m.qkv2 = pack_qkv(tb + ".attn2", m);
       m.out2 = pack_attn_out(tb + ".attn2", m);
     }
-    // GEGLU: interleave value / gate rows in blocks of 16 so one 32-column accumulator chunk holds both
+    // GEGLU: interleave value / gate rows in blocks of 8 so one 16-column accumulator chunk holds both
     const int c4 = 4 * m.c;
     m.ff1.n = 2 * c4;
     m.ff1.k = m.c;
     m.ff1.w = store<bf16>((size_t)m.ff1.n * m.ff1.k);
     std::vector<int> map(2 * c4);
     for (int ch = 0; ch < c4; ++ch) {
-      map[ch] = (ch / 16) * 32 + ch % 16;
-      map[c4 + ch] = (ch / 16) * 32 + 16 + ch % 16;
+      map[ch] = (ch / 8) * 16 + ch % 8;
+      map[c4 + ch] = (ch / 8) * 16 + 8 + ch % 8;
     }
     pack_rows(stream, rawf(tb + ".ff.net.0.proj.weight"), 2 * c4, m.c, m.c, m.ff1.w, m.c, 0, upload_map(map));
     {
@@ -949,9 +949,10 @@ struct mvldm_handle_s {
     sharded = false;
     p->dev_ops.alloc(std::max<size_t>(1, p->ops.size()) * sizeof(SeqOp));
     size_t stamps = 0;
+    seq_link_prefetch(p->ops.data(), (int)p->ops.size(), reinterpret_cast<const SeqOp*>(p->dev_ops.p));
     for (const Step& st : p->steps) {
       if (st.kind != Step::SEQ) continue;
-      seq_link_prefetch(p->ops.data() + st.op_begin, st.op_end - st.op_begin, reinterpret_cast<const SeqOp*>(p->dev_ops.p) + st.op_begin);
+      seq_link_launch(p->ops.data() + st.op_begin, st.op_end - st.op_begin);
       stamps += 2 * (size_t)(st.op_end - st.op_begin) + 2;
     }
     if (!p->ops.empty())
@@ -966,7 +967,7 @@ struct mvldm_handle_s {
     return ref;
   }
 
-  static int op_barriers(const SeqOp& o) { return o.c.type == SEQ_GN && !o.c.gn.warp_mode && o.c.gn.ps > 1 ? 1 : 0; }
+  static int op_barriers(const SeqOp& o) { return o.c.type == SEQ_GN && o.c.gn.ps > 1 ? 1 : 0; }
 
   // issue the plan's launches on `s` (eagerly, or into a stream capture); with `events` every launch is bracketed
   void execute(Plan& p, cudaStream_t s, std::vector<cudaEvent_t>* events) {
@@ -1387,6 +1388,18 @@ int mvldm_op_attention(void* stream, int impl, const void* qkv, void* out, int b
     attention_tc((cudaStream_t)stream, (const bf16*)qkv, (bf16*)out, batches, seq, heads, d, dpad);
   else
     attention_simt((cudaStream_t)stream, (const bf16*)qkv, (bf16*)out, batches, seq, heads, d, dpad);
+  MV_API_END
+}
+
+int mvldm_debug_seq_trace(void* device_buffer) {
+  mvldm::g_seq_trace = reinterpret_cast<long long*>(device_buffer);
+  return 0;
+}
+
+int mvldm_debug_seq_empty_ops(void* stream, int n_ops) {
+  MV_API_BEGIN
+  MV_CHECK(n_ops > 0 && n_ops <= 4096, "bad op count");
+  seq_debug_empty_ops((cudaStream_t)stream, n_ops);
   MV_API_END
 }
 

@@ -62,7 +62,8 @@ constexpr int NWARPS = SEQ_THREADS / 32;
 constexpr int MAX_STAGES = 8;
 constexpr int CV_IMGS = 8;  // images one 128-pixel tile can span in the bias/row-vector table (hw >= 16)
 constexpr int ACC_COLS = 256;
-constexpr int GN_WARP_MAXV = 10;  // GroupNorm warp mode: 16-byte vectors one lane holds (x 32 lanes = vectors per item)
+// kernel behaviour switches (MVLDM_SEQ_FLAGS, default all on): measured one by one in profiles/
+constexpr int SEQ_F_TMAP_FENCE = 1, SEQ_F_PROXY_FENCE = 2, SEQ_F_PREFETCH = 4;
 
 // ---- shared memory map (dynamic, carved by hand; base rounded up to 1024 B for the SWIZZLE_128B atoms) ----
 //   [0, AUX)                     op descriptor, mbarriers, TMEM slot, reduction scratch
@@ -70,9 +71,9 @@ constexpr int GN_WARP_MAXV = 10;  // GroupNorm warp mode: 16-byte vectors one la
 //                                GroupNorm: the CTA's channel slabs
 constexpr int OFF_DESC = 0;
 constexpr int OFF_BAR_FULL = 512, OFF_BAR_EMPTY = 576, OFF_ACC_FULL = 640, OFF_ACC_EMPTY = 656, OFF_TMEM = 672;
-constexpr int OFF_RED = 704;    // 64 floats
-constexpr int OFF_STAT = 960;   // 16 floats
-constexpr int AUX_BYTES = 1024;
+constexpr int OFF_RED = 704;    // [8 warps][4] floats
+constexpr int OFF_STAT = 832;   // [8 item groups][4][2] floats
+constexpr int AUX_BYTES = 2048;
 constexpr int WORK_BYTES = 3 * KC * (A_BYTES + 160 * 128) + CV_IMGS * 160 * 4;  // 3 stages of the 160-wide tile + its table
 constexpr int SMEM_BYTES = 1024 + AUX_BYTES + WORK_BYTES;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
@@ -81,11 +82,16 @@ inline int stage_bytes_for(int bn) { return KC * (A_BYTES + bn * 128); }
 inline int stages_for(int bn) { return std::min(MAX_STAGES, (WORK_BYTES - CV_IMGS * bn * 4) / stage_bytes_for(bn)); }
 
 // ---- small device helpers ---------------------------------------------------------------------------------
+// CODE SIZE IS A FIRST-ORDER COST HERE.  Every op body runs once per launch position, usually on a cold instruction
+// cache (the kernel is far larger than the 32 KB L1.5 I-cache, and attention kernels run in between): measured on B200,
+// cold straight-line code retires at ~9 cycles per instruction, so a 40 KB unrolled op body cost ~8 us by itself.
+// Hence: rolled loops over shared memory (cp.async staging gives the memory-level parallelism that unrolling would),
+// 16-column epilogue chunks, one code path per op.  Check `cuobjdump -elf build/seq.o` symbol sizes after every change.
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 
 // erf-form GELU (F.gelu default, mvdream/attention.py:60-70) with erf from Abramowitz & Stegun 7.1.26 (|abs err| <
 // 1.5e-7, far below the bf16 the result is stored in): Phi(-|x|) = 0.5 * poly(t) * exp(-x^2/2), t = 1/(1 + p |x|/sqrt2).
-// 18 instructions (2 MUFU) instead of erff's ~35 with branches; the GEGLU epilogue is issue-bound on this.
+// 18 instructions (2 MUFU) instead of erff's ~35 with branches.
 __device__ __forceinline__ float gelu_exact(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
   float t, e;
@@ -115,6 +121,11 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 }
 // activations are written by other CTAs of the SAME launch: read them through L2 only (no stale L1 line can be hit)
 __device__ __forceinline__ uint4 ld_cg16(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+// 16-byte global -> shared copy that bypasses L1 and registers: issued from a rolled loop, all copies stay in flight
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // 256-bit global store: one instruction covers a full 32-byte sector per thread (rows are >= 64 B apart, so 16-byte
 // stores would touch every sector twice)
@@ -123,6 +134,17 @@ __device__ __forceinline__ void st_global_v8(void* ptr, uint32_t a0, uint32_t a1
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a0), "r"(a1), "r"(a2), "r"(a3),
                "r"(a4), "r"(a5), "r"(a6), "r"(a7)
                : "memory");
+}
+// 32 lanes x 8 columns (registers <-> TMEM): the residual row is parked in the accumulator buffer's spare columns
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4& a, const uint4& b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(a.x), "r"(a.y),
+               "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -138,10 +160,9 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 }
 __device__ __forceinline__ long long globaltimer_ns() {
   long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
   return t;
 }
-
 // timeline of CTA 0 for the per-op report: (globaltimer ns, clock64) pairs
 __device__ __forceinline__ void stamp(long long* timing, unsigned k) {
   timing[2 * k] = globaltimer_ns();
@@ -154,16 +175,26 @@ __device__ __forceinline__ void stamp(long long* timing, unsigned k) {
 // orders them against the TMA = async-proxy reads other CTAs will issue), thread 0 arrives with release semantics and
 // polls with acquire semantics, the CTA barrier on either side extends that to the whole CTA (the cooperative-groups
 // grid.sync construction).  While thread 0 polls, warp 1 stages the next op's descriptor in shared memory.
+// Measured (tools/seq_barrier_bench.py, tools/seq_trace.py): ~1 us from the last CTA's arrival to the release.
 struct GridBarrier {
   unsigned* ctr;
   unsigned n;  // barriers passed
   long long* timing;
-  __device__ __forceinline__ void sync(const SeqOp* next, uint8_t* desc_smem) {
-    __threadfence();
-    asm volatile("fence.proxy.async.global;" ::: "memory");
+  int flags;
+  long long* trace;  // debug: [barrier][cta][16] globaltimer stamps (tools/seq_trace.py)
+  int op;
+  __device__ __noinline__ void sync(const SeqOp* next, uint8_t* desc_smem) {
+    long long* tr = trace && threadIdx.x == 0 ? trace + ((size_t)n * gridDim.x + blockIdx.x) * 16 : nullptr;
+    if (tr) tr[0] = globaltimer_ns();
+    if (flags & SEQ_F_PROXY_FENCE) asm volatile("fence.proxy.async.global;" ::: "memory");
     __syncthreads();
+    if (tr) tr[1] = globaltimer_ns();
     ++n;
-    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    if (threadIdx.x == 0) {
+      // cumulative gpu-scope fence: publishes the global writes of the whole CTA (ordered before it by the CTA barrier)
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    }
     if (next != nullptr && threadIdx.x >= 32 && threadIdx.x < 32 + SEQ_OPC_BYTES / 16)
       reinterpret_cast<uint4*>(desc_smem)[threadIdx.x - 32] = __ldg(reinterpret_cast<const uint4*>(next) + (threadIdx.x - 32));
     if (threadIdx.x == 0) {
@@ -173,9 +204,14 @@ struct GridBarrier {
         if (++spins > (1u << 25)) __trap();  // a protocol bug / lost co-residency traps instead of hanging the GPU
       }
       if (timing != nullptr && blockIdx.x == 0) stamp(timing, n);
+      if (tr) {
+        tr[2] = globaltimer_ns();
+        tr[3] = op;
+        tr[5] = spins;
+      }
     }
     __syncthreads();
-    asm volatile("fence.proxy.async.global;" ::: "memory");
+    if (flags & SEQ_F_PROXY_FENCE) asm volatile("fence.proxy.async.global;" ::: "memory");
   }
 };
 
@@ -184,42 +220,102 @@ struct RoleState {
   uint32_t empty_par;  // producer: parity to wait for on bar_empty[s] before refilling slot s
   uint32_t full_par;   // MMA issuer: parity to wait for on bar_full[s]
   uint32_t acc_n;      // MMA issuer / epilogue: accumulator hand-offs so far (buffer = acc_n & 1, phase = (acc_n >> 1) & 1)
+  long long* tr;       // debug timeline row of the barrier that will close this op (slots 8..15), or NULL
 };
 
-// The tensor maps live in global memory (written by cudaMemcpy before the launch) and are read through the tensormap proxy:
-// each CTA acquires them once before first use (CUDA programming guide, "tensor map in global memory").  Done one op ahead.
-__device__ __forceinline__ void acquire_tensormaps(const SeqOp* o, int nseg) {
-  for (int s = 0; s < nseg; ++s)
-    for (int k = 0; k < KC; ++k)
-      asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(&o->tmA[s][k])) : "memory");
-  if (nseg > 0)
-    for (int k = 0; k < KC; ++k)
-      asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(&o->tmB[k])) : "memory");
+// descriptor-cache prefetch of every tensor map op `o` uses (a cold map costs the first TMA ~2 us: the 128-byte
+// descriptors are touched once per forward, so they come from HBM)
+__device__ __forceinline__ void prefetch_tensormaps(const SeqOp* o, int nseg) {
+#pragma unroll 1
+  for (int i = 0; i < (nseg + 1) * KC; ++i) {
+    const CUtensorMap* m = i < nseg * KC ? &o->tmA[0][0] + i : &o->tmB[0] + (i - nseg * KC);
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+  }
 }
 
-// L2 prefetch of the next GEMM op's weight tiles this CTA will consume
+// L2 prefetch of the next GEMM op's weight tiles: its [bn x KC chunk] boxes are dealt round-robin to the CTAs, so every
+// SM's TMA unit carries an equal share (a box costs TMA issue time whether or not the data returns to the SM)
 __device__ __forceinline__ void prefetch_next_weights(const SeqPrefetch& pf) {
   if (pf.map == nullptr) return;
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(pf.map)) : "memory");
-  const int work = pf.mt * pf.nt * pf.splits;
-  for (int w = blockIdx.x; w < work; w += gridDim.x) {
-    if (w % pf.mt != 0) continue;  // the m-tiles of one (n-tile, split) share the weight tile: fetched once
-    const int ntile = (w / pf.mt) % pf.nt, z = w / (pf.mt * pf.nt);
-    const int c_end = pf.chunk0[z + 1];
-    for (int ch = pf.chunk0[z]; ch < c_end; ch += KC)
-      asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
-                       reinterpret_cast<uint64_t>(pf.map)),
-                   "r"(0), "r"(ntile * pf.bn), "r"(ch)
-                   : "memory");
+  const int per_n = (pf.nchunks + KC - 1) / KC;  // boxes along K for one n-tile
+  const int boxes = pf.nt * per_n;
+#pragma unroll 1
+  for (int b = blockIdx.x; b < boxes; b += gridDim.x) {
+    const int ntile = b / per_n, kb = b - ntile * per_n;
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(pf.map)),
+                 "r"(0), "r"(ntile * pf.bn), "r"(kb * KC)
+                 : "memory");
   }
 }
 
 // =====================================================================================================
 // SEQ_GEMM
 // =====================================================================================================
-__device__ __noinline__ void gemm_op(const SeqGemm& g, const SeqPrefetch& pf, int next_nseg, const SeqOp* opg, uint8_t* smem,
-                                        uint32_t smem_base, uint32_t tmem_base, RoleState& st) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// (segment, tap, channel block) walk shared by the producer and the MMA issuer
+struct KWalk {
+  int s, t, cb;
+  __device__ __forceinline__ void start(const SeqGemm& g, int step) {
+    s = 0;
+    cb = step;
+    while (cb >= g.seg[s].ntaps * g.seg[s].spt) {
+      cb -= g.seg[s].ntaps * g.seg[s].spt;
+      ++s;
+    }
+    t = cb / g.seg[s].spt;
+    cb = (cb - t * g.seg[s].spt) * KC;
+  }
+  __device__ __forceinline__ int chunks(const SeqGemm& g) const { return min(KC, (int)g.seg[s].ncblk - cb); }
+  __device__ __forceinline__ void next(const SeqGemm& g, int kc) {
+    cb += kc;
+    if (cb == g.seg[s].ncblk) {
+      cb = 0;
+      if (++t == g.seg[s].ntaps) {
+        t = 0;
+        ++s;
+      }
+    }
+  }
+};
+
+__device__ __noinline__ void gemm_producer(const SeqGemm& g, const SeqOp* opg, uint32_t smem_base, RoleState& st) {
+  const int BN = g.bn;
+  const uint32_t b_bytes = (uint32_t)BN * 128u;
+  const uint32_t stage_bytes = KC * (A_BYTES + b_bytes);
+  const uint32_t ring_base = smem_base + AUX_BYTES;
+  const uint32_t bar_full = smem_base + OFF_BAR_FULL, bar_empty = smem_base + OFF_BAR_EMPTY;
+  const int num_work = g.mt * g.nt * g.splits;
+  int ring = 0;
+#pragma unroll 1
+  for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+    const int mtile = w % g.mt, ntile = (w / g.mt) % g.nt, z = w / (g.mt * g.nt);
+    const int m0 = mtile * BM, n0 = ntile * BN;
+    const int st_begin = z * g.steps_per_split;
+    const int nst = min(g.num_steps - st_begin, g.steps_per_split);
+    const int img0 = m0 / g.hw;
+    const int y0 = (m0 - img0 * g.hw) / g.ow;
+    KWalk k;
+    k.start(g, st_begin);
+#pragma unroll 1
+    for (int i = 0; i < nst; ++i) {
+      const SeqSeg& sg = g.seg[k.s];
+      const int kc = k.chunks(g);
+      tc::mbar_wait(bar_empty + 8 * ring, (st.empty_par >> ring) & 1u);
+      st.empty_par ^= 1u << ring;
+      const uint32_t full = bar_full + 8 * ring;
+      tc::mbar_expect_tx(full, kc * (A_BYTES + b_bytes));
+      const uint32_t sa = ring_base + ring * stage_bytes;
+      tc::tma_load_5d(sa, &opg->tmA[k.s][kc - 1], full, 0, sg.dw[k.t], y0 * sg.stride + sg.dh[k.t], img0, sg.cblk[k.t] + k.cb);
+      tc::tma_load_3d(sa + KC * A_BYTES, &opg->tmB[kc - 1], full, 0, n0, sg.kchunk0 + k.t * sg.ncblk + k.cb);
+      if (st.tr && i == 0 && w == (int)blockIdx.x) st.tr[6] = globaltimer_ns();  // first loads issued
+      ring = ring + 1 == g.stages ? 0 : ring + 1;
+      k.next(g, kc);
+    }
+  }
+}
+
+// the whole warp runs the warp-uniform loop and the barrier waits; one elected lane issues tcgen05.mma / commit,
+// which lets ptxas emit the UTCHMMAs back to back instead of one ELECT/branch loop per instruction
+__device__ __noinline__ void gemm_mma(const SeqGemm& g, uint32_t smem_base, uint32_t tmem_base, RoleState& st) {
   const int BN = g.bn;
   const uint32_t b_bytes = (uint32_t)BN * 128u;
   const uint32_t stage_bytes = KC * (A_BYTES + b_bytes);
@@ -227,732 +323,561 @@ __device__ __noinline__ void gemm_op(const SeqGemm& g, const SeqPrefetch& pf, in
   const uint32_t bar_full = smem_base + OFF_BAR_FULL, bar_empty = smem_base + OFF_BAR_EMPTY;
   const uint32_t bar_acc_full = smem_base + OFF_ACC_FULL, bar_acc_empty = smem_base + OFF_ACC_EMPTY;
   const int num_work = g.mt * g.nt * g.splits;
-
-  if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      int ring = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const int mtile = w % g.mt, ntile = (w / g.mt) % g.nt, z = w / (g.mt * g.nt);
-        const int m0 = mtile * BM, n0 = ntile * BN;
-        const int st_begin = z * g.steps_per_split;
-        const int nst = min(g.num_steps - st_begin, g.steps_per_split);
-        const int img0 = m0 / g.hw;
-        const int y0 = (m0 - img0 * g.hw) / g.ow;
-        // locate (segment, tap, channel block) of the first step
-        int s = 0, t = 0, cb = st_begin;
-        while (cb >= g.seg[s].ntaps * g.seg[s].spt) {
-          cb -= g.seg[s].ntaps * g.seg[s].spt;
-          ++s;
-        }
-        t = cb / g.seg[s].spt;
-        cb = (cb - t * g.seg[s].spt) * KC;
-        for (int i = 0; i < nst; ++i) {
-          const SeqSeg& sg = g.seg[s];
-          const int kc = min(KC, sg.ncblk - cb);
-          tc::mbar_wait(bar_empty + 8 * ring, (st.empty_par >> ring) & 1u);
-          st.empty_par ^= 1u << ring;
-          const uint32_t full = bar_full + 8 * ring;
-          tc::mbar_expect_tx(full, kc * (A_BYTES + b_bytes));
-          const uint32_t sa = ring_base + ring * stage_bytes;
-          tc::tma_load_5d(sa, &opg->tmA[s][kc - 1], full, 0, sg.dw[t], y0 * sg.stride + sg.dh[t], img0, sg.cblk[t] + cb);
-          tc::tma_load_3d(sa + KC * A_BYTES, &opg->tmB[kc - 1], full, 0, n0, sg.kchunk0 + t * sg.ncblk + cb);
-          ring = ring + 1 == g.stages ? 0 : ring + 1;
-          cb += kc;
-          if (cb == sg.ncblk) {
-            cb = 0;
-            if (++t == sg.ntaps) {
-              t = 0;
-              ++s;
-            }
-          }
-        }
-      }
-      acquire_tensormaps(opg + 1, next_nseg);
-      prefetch_next_weights(pf);  // the rest of this op (MMA tail, epilogue, reduction, barrier) hides the HBM latency
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    // the whole warp runs the warp-uniform loop and the barrier waits; one elected lane issues tcgen05.mma / commit,
-    // which lets ptxas emit the UTCHMMAs back to back instead of one ELECT/branch loop per instruction
-    const uint32_t idesc = tc::umma_idesc_bf16(BM, BN, false, false);
-    int ring = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-      const int z = w / (g.mt * g.nt);
-      const int st_begin = z * g.steps_per_split;
-      const int nst = min(g.num_steps - st_begin, g.steps_per_split);
-      int s = 0, t = 0, cb = st_begin;  // same walk as the producer, to know how many chunks each step carries
-      while (cb >= g.seg[s].ntaps * g.seg[s].spt) {
-        cb -= g.seg[s].ntaps * g.seg[s].spt;
-        ++s;
-      }
-      t = cb / g.seg[s].spt;
-      cb = (cb - t * g.seg[s].spt) * KC;
-      const uint32_t ab = st.acc_n & 1u;
-      tc::mbar_wait(bar_acc_empty + 8 * ab, ((st.acc_n >> 1) & 1u) ^ 1u);  // epilogue has drained this buffer
+  const uint32_t idesc = tc::umma_idesc_bf16(BM, BN, false, false);
+  int ring = 0;
+#pragma unroll 1
+  for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+    const int z = w / (g.mt * g.nt);
+    const int st_begin = z * g.steps_per_split;
+    const int nst = min(g.num_steps - st_begin, g.steps_per_split);
+    KWalk k;  // same walk as the producer, to know how many chunks each step carries
+    k.start(g, st_begin);
+    const uint32_t ab = st.acc_n & 1u;
+    tc::mbar_wait(bar_acc_empty + 8 * ab, ((st.acc_n >> 1) & 1u) ^ 1u);  // epilogue has drained this buffer
+    tc::tc_fence_after();
+    const uint32_t tmem_d = tmem_base + ab * ACC_COLS;
+#pragma unroll 1
+    for (int i = 0; i < nst; ++i) {
+      const int kc = k.chunks(g);
+      tc::mbar_wait(bar_full + 8 * ring, (st.full_par >> ring) & 1u);
+      st.full_par ^= 1u << ring;
       tc::tc_fence_after();
-      const uint32_t tmem_d = tmem_base + ab * ACC_COLS;
-      for (int i = 0; i < nst; ++i) {
-        const int kc = min(KC, (int)g.seg[s].ncblk - cb);
-        tc::mbar_wait(bar_full + 8 * ring, (st.full_par >> ring) & 1u);
-        st.full_par ^= 1u << ring;
-        tc::tc_fence_after();
-        const uint32_t sa = ring_base + ring * stage_bytes;
-        if (tc::elect_one()) {
-          for (int c = 0; c < kc; ++c) {
-            const uint64_t adesc = tc::umma_desc_k_sw128(sa + c * A_BYTES);
-            const uint64_t bdesc = tc::umma_desc_k_sw128(sa + KC * A_BYTES + c * b_bytes);
+      if (st.tr && i == 0 && w == (int)blockIdx.x && (threadIdx.x & 31) == 0) st.tr[7] = globaltimer_ns();  // first tile landed
+      const uint32_t sa = ring_base + ring * stage_bytes;
+      if (tc::elect_one()) {
+#pragma unroll 1
+        for (int c = 0; c < kc; ++c) {
+          const uint64_t adesc = tc::umma_desc_k_sw128(sa + c * A_BYTES);
+          const uint64_t bdesc = tc::umma_desc_k_sw128(sa + KC * A_BYTES + c * b_bytes);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)  // +32 bytes (=2 in descriptor units) per K=16 slice inside the swizzle atom
-              tc::umma_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (i | c | k) != 0);
-          }
-          tc::umma_commit(bar_empty + 8 * ring);  // frees the smem slot when these MMAs retire
+          for (int kk = 0; kk < BK / 16; ++kk)  // +32 bytes (=2 in descriptor units) per K=16 slice inside the swizzle atom
+            tc::umma_ss(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (i | c | kk) != 0);
         }
-        __syncwarp();
-        ring = ring + 1 == g.stages ? 0 : ring + 1;
-        cb += kc;
-        if (cb == g.seg[s].ncblk) {
-          cb = 0;
-          if (++t == g.seg[s].ntaps) {
-            t = 0;
-            ++s;
-          }
-        }
+        tc::umma_commit(bar_empty + 8 * ring);  // frees the smem slot when these MMAs retire
       }
-      if (tc::elect_one()) tc::umma_commit(bar_acc_full + 8 * ab);
       __syncwarp();
-      ++st.acc_n;
+      ring = ring + 1 == g.stages ? 0 : ring + 1;
+      k.next(g, kc);
     }
-  } else if (warp < 6) {
-    // ================= epilogue =================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
-    float* colvec = reinterpret_cast<float*>(smem + AUX_BYTES + g.stages * stage_bytes);  // [image in tile][BN]
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-      const int mtile = w % g.mt, ntile = (w / g.mt) % g.nt, z = w / (g.mt * g.nt);
-      const int m0 = mtile * BM, n0 = ntile * BN;
-      const uint32_t ab = st.acc_n & 1u;
-      const uint32_t tmem_d = tmem_base + ab * ACC_COLS;
-      const int m = m0 + row;
-      const bool ok = m < g.M;
-      const int img = m / g.hw;
-      // ---- while the main loop of this item runs: stage everything the epilogue needs that is not the accumulator
-      const int img0 = m0 / g.hw;
-      const int imgs_in_tile = (BM + g.hw - 1) / g.hw;
-      const bool use_table = (!g.partial || g.counters) && (g.bias || g.rowvec) && imgs_in_tile <= CV_IMGS;
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous item's readers of the table are done
-      if (use_table) {
-        for (int i = et; i < imgs_in_tile * BN; i += 128) {
-          const int b = i / BN, c = i - b * BN;
-          float v = g.bias ? g.bias[n0 + c] : 0.f;
-          if (g.rowvec && (int64_t)(img0 + b) * g.hw < g.M) v += __ldcg(g.rowvec + (int64_t)(img0 + b) * g.rowvec_ld + n0 + c);
-          colvec[b * BN + c] = v;
-        }
+    if (tc::elect_one()) tc::umma_commit(bar_acc_full + 8 * ab);
+    __syncwarp();
+    ++st.acc_n;
+  }
+}
+
+// epilogue warps 2..5: each thread owns one accumulator row (TMEM lane).  32 columns per rolled iteration; the TMEM load of
+// chunk c+1 is issued as soon as chunk c has been moved out of the load registers (bias add), so the ~0.25 us TMEM
+// round trip overlaps the conversion / stores of the previous chunk (serialised it made a 160-wide tile take 3 us).
+__device__ __noinline__ void gemm_epilogue(const SeqGemm& g, uint8_t* smem, uint32_t smem_base, uint32_t tmem_base,
+                                           RoleState& st) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = g.bn;
+  const uint32_t stage_bytes = KC * (A_BYTES + (uint32_t)BN * 128u);
+  const uint32_t bar_acc_full = smem_base + OFF_ACC_FULL, bar_acc_empty = smem_base + OFF_ACC_EMPTY;
+  const int num_work = g.mt * g.nt * g.splits;
+  const int q = warp & 3;  // TMEM lane quarter this warp may access
+  const int row = q * 32 + lane;
+  const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
+  float* colvec = reinterpret_cast<float*>(smem + AUX_BYTES + g.stages * stage_bytes);  // [image in tile][BN]
+  const int mode = g.mode;
+  const int imgs_in_tile = (BM + g.hw - 1) / g.hw;
+  const bool table = (g.bias || g.rowvec) && imgs_in_tile <= CV_IMGS;  // else (sub-4x4 maps): bias / rowvec straight from L2
+#pragma unroll 1
+  for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+    const int mtile = w % g.mt, ntile = (w / g.mt) % g.nt, z = w / (g.mt * g.nt);
+    const int m0 = mtile * BM, n0 = ntile * BN;
+    const uint32_t ab = st.acc_n & 1u;
+    const uint32_t trow = tmem_base + ab * ACC_COLS + ((uint32_t)(q * 32) << 16);
+    const int m = m0 + row;
+    const bool ok = m < g.M;
+    const int img = m / g.hw, img0 = m0 / g.hw;
+    // ---- while the main loop of this item runs: stage everything the epilogue needs that is not the accumulator
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // previous item's readers of the table are done
+    if (table) {  // bias[n] + rowvec[image, n] for the images of this tile
+#pragma unroll 1
+      for (int i = et; i < imgs_in_tile * BN; i += 128) {
+        const int b = i / BN, c = i - b * BN;
+        float v = g.bias ? g.bias[n0 + c] : 0.f;
+        if (g.rowvec && (int64_t)(img0 + b) * g.hw < g.M) v += __ldcg(g.rowvec + (int64_t)(img0 + b) * g.rowvec_ld + n0 + c);
+        colvec[b * BN + c] = v;
       }
-      // residual (bf16 row of this thread): chunk c+1 is fetched while chunk c is converted and stored
-      const bool use_res = ok && !g.partial && g.mode == 0 && g.residual;
-      const uint4* res_row = use_res ? reinterpret_cast<const uint4*>(g.residual + (int64_t)m * g.res_ld + n0) : nullptr;
-      uint4 res_next[4];
-      if (use_res) {
+    }
+    // residual row (bf16): all loads in flight now, parked as packed pairs in the spare TMEM columns [BN, BN + BN/2) of this
+    // accumulator buffer (the MMAs write [0, BN)); the rolled chunk loop below reads them back with a dynamic TMEM address
+    const bool use_res = !g.partial && mode == 0 && g.residual != nullptr;
+    if (use_res) {
+      const uint4* rr = reinterpret_cast<const uint4*>(g.residual + (int64_t)min(m, g.M - 1) * g.res_ld + n0);
+      uint4 rv[20];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) res_next[j] = __ldcg(res_row + j);
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const float* cvrow = colvec + (img - img0) * BN;
-      tc::mbar_wait(bar_acc_full + 8 * ab, (st.acc_n >> 1) & 1u);
-      tc::tc_fence_after();
-#pragma unroll 1  // rolled: the unrolled epilogue (x8 chunks x 3 modes) cost 0.5 ms per forward in code size / registers
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        uint4 res_cur[4];
-        if (use_res) {
+      for (int c = 0; c < 20; ++c)
+        if (c * 8 < BN) rv[c] = __ldcg(rr + c);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) res_cur[j] = res_next[j];
-          if (c0 + 32 < BN) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) res_next[j] = __ldcg(res_row + (c0 + 32) / 8 + j);
-          }
-        }
-        __syncwarp();
-        tc::tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + c0, r);
-        tc::tmem_ld_wait();
-        if (ok && g.partial) {  // split-K: raw fp32 partial, reduced (+ epilogue) below or by the SEQ_SPLITK_REDUCE op
-          float* pp = g.partial + ((int64_t)z * g.M + m) * g.N + n0 + c0;
+      for (int c = 0; c < 10; ++c)
+        if (c * 16 < BN) tmem_st8(trow + BN + c * 8, rv[2 * c], rv[2 * c + 1]);
+      tc::tmem_st_wait();
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const float* cvrow = colvec + (table ? img - img0 : 0) * BN;
+    if (st.tr && et == 0) st.tr[8] = globaltimer_ns();  // staged, waiting for the accumulator
+    tc::mbar_wait(bar_acc_full + 8 * ab, (st.acc_n >> 1) & 1u);
+    tc::tc_fence_after();
+    if (st.tr && et == 0) st.tr[9] = globaltimer_ns();  // accumulator ready
+    uint32_t r[32], rs[16];
+    tc::tmem_ld32(trow, r);
+    if (use_res) tc::tmem_ld16(trow + BN, rs);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      const int n = n0 + c0;
+      const bool more = c0 + 32 < BN;
+      tc::tmem_ld_wait();
+      if (g.partial) {  // split-K: raw fp32 partial, reduced (+ epilogue) below or by the SEQ_SPLITK_REDUCE op
+        if (ok) {
+          float* pp = g.partial + ((int64_t)z * g.M + m) * g.N + n;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             st_global_v8(pp + 8 * j, r[8 * j], r[8 * j + 1], r[8 * j + 2], r[8 * j + 3], r[8 * j + 4], r[8 * j + 5], r[8 * j + 6],
                          r[8 * j + 7]);
-        } else if (ok) {
-          const int n = n0 + c0;
-          float v[32];
+        }
+        if (more) tc::tmem_ld32(trow + c0 + 32, r);
+        if (st.tr && et == 0 && c0 == 0) st.tr[13] = globaltimer_ns();  // first chunk done
+        continue;
+      }
+      float v[32];
+      if (table) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (use_table) {
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(cvrow + c0 + j);  // smem, same address across the warp's rows of one image
+          v[j] = __uint_as_float(r[j]) + b.x; v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
+          v[j + 2] = __uint_as_float(r[j + 2]) + b.z; v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
+        }
+      } else {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = *reinterpret_cast<const float4*>(cvrow + c0 + j);  // smem, same address across the warp's rows of one image
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
-          } else {
-            if (g.bias) {
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      }
+      uint32_t rq[16];
+      if (use_res) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b = *reinterpret_cast<const float4*>(g.bias + n + j);
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-              }
-            }
-            if (g.rowvec) {
-              const float* rv = g.rowvec + (int64_t)img * g.rowvec_ld + n;
+        for (int e = 0; e < 16; ++e) rq[e] = rs[e];
+      }
+      if (more) {  // the load registers are free again: next chunk in flight while this one is converted and stored
+        tc::tmem_ld32(trow + c0 + 32, r);
+        if (use_res) tc::tmem_ld16(trow + BN + ((c0 + 32) >> 1), rs);
+      }
+      if (st.tr && et == 0 && c0 == 0) st.tr[13] = globaltimer_ns();  // first chunk out of the load registers
+      if (!ok) continue;
+      if (!table && (g.bias || g.rowvec)) {  // rare: more than CV_IMGS images per tile (maps smaller than 4x4)
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b = __ldcg(reinterpret_cast<const float4*>(rv + j));
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-              }
-            }
+        for (int j = 0; j < 32; j += 4) {
+          if (g.bias) {
+            const float4 b = *reinterpret_cast<const float4*>(g.bias + n + j);
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
           }
-          if (g.mode == 0 || g.mode == 3) {
-            if (use_res) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 u = res_cur[j];
-                const uint32_t wd[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = unpack_bf16(wd[e]);
-                  v[j * 8 + e * 2] += f.x;
-                  v[j * 8 + e * 2 + 1] += f.y;
-                }
-              }
-            }
-            if (g.mode == 3) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-            }
-            bf16* op = reinterpret_cast<bf16*>(g.out) + (int64_t)m * g.ldo + n;
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-              st_global_v8(op + 16 * j, pack_bf16(v[j * 16], v[j * 16 + 1]), pack_bf16(v[j * 16 + 2], v[j * 16 + 3]),
-                           pack_bf16(v[j * 16 + 4], v[j * 16 + 5]), pack_bf16(v[j * 16 + 6], v[j * 16 + 7]),
-                           pack_bf16(v[j * 16 + 8], v[j * 16 + 9]), pack_bf16(v[j * 16 + 10], v[j * 16 + 11]),
-                           pack_bf16(v[j * 16 + 12], v[j * 16 + 13]), pack_bf16(v[j * 16 + 14], v[j * 16 + 15]));
-          } else if (g.mode == 1) {
-            // columns [0,16) = values, [16,32) = gates of the same 16 hidden channels
-            float gl[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) gl[j] = v[j] * gelu_exact(v[16 + j]);
-            st_global_v8(reinterpret_cast<bf16*>(g.out) + (int64_t)m * g.ldo + n / 2, pack_bf16(gl[0], gl[1]),
-                         pack_bf16(gl[2], gl[3]), pack_bf16(gl[4], gl[5]), pack_bf16(gl[6], gl[7]), pack_bf16(gl[8], gl[9]),
-                         pack_bf16(gl[10], gl[11]), pack_bf16(gl[12], gl[13]), pack_bf16(gl[14], gl[15]));
-          } else if (g.mode == 4) {
-            float* op = reinterpret_cast<float*>(g.out) + (int64_t)m * g.ldo + n;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              st_global_v8(op + 8 * j, __float_as_uint(v[8 * j]), __float_as_uint(v[8 * j + 1]), __float_as_uint(v[8 * j + 2]),
-                           __float_as_uint(v[8 * j + 3]), __float_as_uint(v[8 * j + 4]), __float_as_uint(v[8 * j + 5]),
-                           __float_as_uint(v[8 * j + 6]), __float_as_uint(v[8 * j + 7]));
-          } else {
-            const int pix = m - img * g.hw;
-            float* op = reinterpret_cast<float*>(g.out) + (int64_t)img * g.n_valid * g.hw + pix;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n + j < g.n_valid) op[(int64_t)(n + j) * g.hw] = v[j];
+          if (g.rowvec) {
+            const float4 b = __ldcg(reinterpret_cast<const float4*>(g.rowvec + (int64_t)img * g.rowvec_ld + n + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
           }
         }
       }
-      tc::tc_fence_before();
-      tc::mbar_arrive(bar_acc_empty + 8 * ab);  // this thread is done reading the accumulator buffer
-      ++st.acc_n;
-      if (g.counters) {
-        // ---- split-K reduction fused into the op: all splits of a tile are co-resident (one work item per CTA), so
-        // they meet at a global counter; each then reduces 1/splits of the tile's rows in fixed z order (bit-stable)
-        // and applies the epilogue.
-        const int tile = mtile + ntile * g.mt;
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (et == 0) {
-          atomicAdd(&g.counters[tile], 1);
-          uint32_t spins = 0;
-          while (*reinterpret_cast<volatile int*>(&g.counters[tile]) < g.splits) {
-            if (++spins > (1u << 25)) __trap();
+      if (mode == 1) {
+        // GEGLU: columns [16i, 16i+8) = values, [16i+8, 16i+16) = gates of the same 8 hidden channels -> 16 outputs
+        float o[16];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[8 * i + j] = v[16 * i + j] * gelu_exact(v[16 * i + 8 + j]);
+        st_global_v8(reinterpret_cast<bf16*>(g.out) + (int64_t)m * g.ldo + (n >> 1), pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]),
+                     pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]), pack_bf16(o[8], o[9]), pack_bf16(o[10], o[11]),
+                     pack_bf16(o[12], o[13]), pack_bf16(o[14], o[15]));
+      } else if (mode == 4) {
+        float* op = reinterpret_cast<float*>(g.out) + (int64_t)m * g.ldo + n;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          st_global_v8(op + 8 * j, __float_as_uint(v[8 * j]), __float_as_uint(v[8 * j + 1]), __float_as_uint(v[8 * j + 2]),
+                       __float_as_uint(v[8 * j + 3]), __float_as_uint(v[8 * j + 4]), __float_as_uint(v[8 * j + 5]),
+                       __float_as_uint(v[8 * j + 6]), __float_as_uint(v[8 * j + 7]));
+      } else if (mode == 2) {  // fp32 NCHW head
+        const int pix = m - img * g.hw;
+        float* op = reinterpret_cast<float*>(g.out) + (int64_t)img * g.n_valid * g.hw + pix;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n + j < g.n_valid) op[(int64_t)(n + j) * g.hw] = v[j];
+      } else {  // 0: bf16 (+ residual); 3: SiLU then bf16
+        if (use_res) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float2 f = unpack_bf16(rq[e]);
+            v[2 * e] += f.x;
+            v[2 * e + 1] += f.y;
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        __threadfence();
-        const int rows_per = (BM + g.splits - 1) / g.splits;
-        const int r0 = z * rows_per, r1 = min(BM, r0 + rows_per);
-        const int NV = BN / 8;
-        const int items = (r1 - r0) * NV;
-        const int64_t zstride = (int64_t)g.M * g.N;
-        for (int i0 = et; i0 < items; i0 += 128 * 4) {
-          // 4 independent items per thread.  Dead slots (past the end / past M) alias the thread's first item so that
-          // every load below is unconditional and the 4 x 2 x splits requests are all in flight together; only the
-          // final store is predicated.
-          int mmv[4], nnv[4];
-          bool live[4];
-          float v[4][8];
+        if (mode == 3) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * 128;
-            const int mm = m0 + r0 + i / NV;
-            live[u] = i < items && mm < g.M;
-            const int ii = live[u] ? i : i0;
-            mmv[u] = min(m0 + r0 + ii / NV, g.M - 1);
-            nnv[u] = (ii % NV) * 8;
+          for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+        }
+        bf16* op = reinterpret_cast<bf16*>(g.out) + (int64_t)m * g.ldo + n;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
-          }
-          uint4 rres[4];
-          float4 cv0[4], cv1[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            rres[u] = g.residual ? ld_cg16(g.residual + (int64_t)mmv[u] * g.res_ld + n0 + nnv[u]) : make_uint4(0u, 0u, 0u, 0u);
-            if (use_table) {
-              const float* cr = colvec + (mmv[u] / g.hw - img0) * BN + nnv[u];
-              cv0[u] = *reinterpret_cast<const float4*>(cr);
-              cv1[u] = *reinterpret_cast<const float4*>(cr + 4);
-            } else {
-              float t8[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                t8[j] = g.bias ? g.bias[n0 + nnv[u] + j] : 0.f;
-                if (g.rowvec) t8[j] += __ldcg(g.rowvec + (int64_t)(mmv[u] / g.hw) * g.rowvec_ld + n0 + nnv[u] + j);
-              }
-              cv0[u] = make_float4(t8[0], t8[1], t8[2], t8[3]);
-              cv1[u] = make_float4(t8[4], t8[5], t8[6], t8[7]);
-            }
-          }
+        for (int j = 0; j < 2; ++j)
+          st_global_v8(op + 16 * j, pack_bf16(v[j * 16], v[j * 16 + 1]), pack_bf16(v[j * 16 + 2], v[j * 16 + 3]),
+                       pack_bf16(v[j * 16 + 4], v[j * 16 + 5]), pack_bf16(v[j * 16 + 6], v[j * 16 + 7]),
+                       pack_bf16(v[j * 16 + 8], v[j * 16 + 9]), pack_bf16(v[j * 16 + 10], v[j * 16 + 11]),
+                       pack_bf16(v[j * 16 + 12], v[j * 16 + 13]), pack_bf16(v[j * 16 + 14], v[j * 16 + 15]));
+      }
+    }
+    tc::tc_fence_before();
+    tc::mbar_arrive(bar_acc_empty + 8 * ab);  // this thread is done reading the accumulator buffer
+    ++st.acc_n;
+    if (st.tr && et == 0) st.tr[10] = globaltimer_ns();  // epilogue stores issued
+    if (g.counters) {
+      // ---- split-K reduction fused into the op: all splits of a tile are co-resident (one work item per CTA), so they
+      // meet at a global counter; each then reduces 1/splits of the tile's rows in fixed z order (bit-stable) and applies
+      // the epilogue.  The slices of all splits are pulled into the (by now idle) shared-memory ring with cp.async, i.e.
+      // every 16-byte piece is in flight at once: one L2 round trip instead of one per split.
+      const int tile = mtile + ntile * g.mt;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {  // one cumulative fence publishes the 128 threads' partial rows; acquire on the way out
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        atomicAdd(&g.counters[tile], 1);
+        uint32_t spins = 0;
+        while (ld_acquire_u32(reinterpret_cast<const unsigned*>(&g.counters[tile])) < (unsigned)g.splits) {
+          if (++spins > (1u << 25)) __trap();
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (st.tr && et == 0) st.tr[11] = globaltimer_ns();  // all splits arrived
+      const int rows_per = (BM + g.splits - 1) / g.splits;
+      const int r0 = z * rows_per, r1 = min(min(BM, r0 + rows_per), g.M - m0);
+      const int NV4 = BN / 4;                       // 16-byte pieces per row
+      const int per_split = max(r1 - r0, 0) * NV4;  // pieces of one split's slice
+      float4* stage = reinterpret_cast<float4*>(smem + AUX_BYTES);  // [split][row][BN] fp32
+      const int64_t zstride = (int64_t)g.M * g.N;
+      const float* pbase = g.partial + (int64_t)(m0 + r0) * g.N + n0;
+#pragma unroll 1
+      for (int i = et; i < per_split; i += 128) {  // this thread's 16-byte piece of the slice, from every split
+        const int rr = i / NV4, c4 = i - rr * NV4;
+        const float* src = pbase + (int64_t)rr * g.N + c4 * 4;
+        float4* dst = stage + i;
 #pragma unroll 4
-          for (int zz = 0; zz < g.splits; ++zz) {  // fixed z order: bit-stable
-            float4 a[4], b4[4];
+        for (int zz = 0; zz < g.splits; ++zz) cp_async16(dst + zz * per_split, src + zz * zstride);
+      }
+      if (st.tr && et == 0) st.tr[14] = globaltimer_ns();  // slice copies issued
+      cp_async_wait_all();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (st.tr && et == 0) st.tr[15] = globaltimer_ns();  // slices in shared memory
+      const int NV = BN / 8;
+#pragma unroll 1
+      for (int i = et; i < max(r1 - r0, 0) * NV; i += 128) {
+        const int rr = i / NV, nn = (i - rr * NV) * 8;
+        const int mm = m0 + r0 + rr;
+        const uint4 res = g.residual ? ld_cg16(g.residual + (int64_t)mm * g.res_ld + n0 + nn) : make_uint4(0u, 0u, 0u, 0u);
+        float v[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float4* pp = reinterpret_cast<const float4*>(g.partial + zz * zstride + (int64_t)mmv[u] * g.N + n0 + nnv[u]);
-              a[u] = __ldcg(pp);
-              b4[u] = __ldcg(pp + 1);
-            }
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        const float4* sp = stage + rr * NV4 + (nn >> 2);
+#pragma unroll 2
+        for (int zz = 0; zz < g.splits; ++zz) {  // fixed z order: bit-stable
+          const float4 a = sp[zz * per_split], b = sp[zz * per_split + 1];
+          v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+          v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+        }
+        if (table) {
+          const float* cr = colvec + (mm / g.hw - img0) * BN + nn;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              v[u][0] += a[u].x; v[u][1] += a[u].y; v[u][2] += a[u].z; v[u][3] += a[u].w;
-              v[u][4] += b4[u].x; v[u][5] += b4[u].y; v[u][6] += b4[u].z; v[u][7] += b4[u].w;
-            }
-          }
+          for (int j = 0; j < 8; ++j) v[j] += cr[j];
+        } else {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            v[u][0] += cv0[u].x; v[u][1] += cv0[u].y; v[u][2] += cv0[u].z; v[u][3] += cv0[u].w;
-            v[u][4] += cv1[u].x; v[u][5] += cv1[u].y; v[u][6] += cv1[u].z; v[u][7] += cv1[u].w;
-            const uint32_t wds[4] = {rres[u].x, rres[u].y, rres[u].z, rres[u].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = unpack_bf16(wds[e]);
-              v[u][2 * e] += f.x;
-              v[u][2 * e + 1] += f.y;
-            }
-            if (live[u])
-              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(g.out) + (int64_t)mmv[u] * g.ldo + n0 + nnv[u]) = pack8(v[u]);
+          for (int j = 0; j < 8; ++j) {
+            if (g.bias) v[j] += g.bias[n0 + nn + j];
+            if (g.rowvec) v[j] += __ldcg(g.rowvec + (int64_t)(mm / g.hw) * g.rowvec_ld + n0 + nn + j);
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (et == 0) {  // the last split to finish re-arms the counters for the next op
-          if (atomicAdd(&g.counters[g.mt * g.nt + tile], 1) == g.splits - 1) {
-            g.counters[tile] = 0;
-            g.counters[g.mt * g.nt + tile] = 0;
-          }
+        float f[8];
+        unpack8(res, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += f[j];
+        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(g.out) + (int64_t)mm * g.ldo + n0 + nn) = pack8(v);
+      }
+      if (st.tr && et == 0) st.tr[12] = globaltimer_ns();  // slice reduced
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {  // the last split to finish re-arms the counters for the next op
+        if (atomicAdd(&g.counters[g.mt * g.nt + tile], 1) == g.splits - 1) {
+          g.counters[tile] = 0;
+          g.counters[g.mt * g.nt + tile] = 0;
         }
       }
     }
   }
-  // (warps 6, 7 have no GEMM role: they wait at the op barrier)
 }
 
 // =====================================================================================================
 // SEQ_GN  GroupNorm (+SiLU), two-pass (mean, then centred second moment) so that |mean| >> std costs no precision
 // =====================================================================================================
-// block-wide sums of up to 4 per-group values: fixed shuffle tree inside a warp, warps folded in order (bit-stable)
-__device__ __forceinline__ void block_sum4(float (&v)[4], float* red) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-  for (int g = 0; g < 4; ++g) v[g] = warp_sum(v[g]);
-  __syncthreads();  // previous readers of `red` are done
-  if (lane == 0) {
-#pragma unroll
-    for (int g = 0; g < 4; ++g) red[warp * 4 + g] = v[g];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    float a = 0.f;
-#pragma unroll
-    for (int w = 0; w < NWARPS; ++w) a += red[w * 4 + g];
-    v[g] = a;
-  }
-}
-
-// One CTA per (image, channel block, pixel chunk).  Thread t owns vector column cv = t % NV (8 channels, at most two
-// groups) and walks pixels pl, pl + lanes_p, ...; the chunk is cached in shared memory so the centred second pass and the
-// normalisation never go back to L2.  With ps > 1 chunk statistics (mean, M2) meet in global memory across one grid
-// barrier and are merged with Chan's formula in chunk order.
-__device__ __noinline__ void gn_cta(const SeqGN& p, uint8_t* smem, GridBarrier& gb) {
-  float* red = reinterpret_cast<float*>(smem + OFF_RED);
-  float* stat = reinterpret_cast<float*>(smem + OFF_STAT);  // [4][2]: mean, rstd
-  bf16* slab0 = reinterpret_cast<bf16*>(smem + AUX_BYTES);
+// One item = (image, channel block of whole groups, pixel chunk), owned by `gw` warps (1, 2, 4 or 8: small images pack
+// several items into a CTA).  The item is copied to shared memory with cp.async (all copies in flight, no registers),
+// then every pass is a short rolled loop over shared memory: thread t of the item's group owns vector column cv (8
+// channels, at most two groups) and pixels pl, pl + lanes, ...  With ps > 1 (big images split over CTAs) the chunk
+// statistics (mean, M2) meet in global memory across one grid barrier and are merged with Chan's formula in chunk order,
+// while the chunk stays in shared memory for the normalisation.  Fixed reduction orders: bit-stable.
+__device__ __noinline__ void gn_op(const SeqGN& p, uint8_t* smem, GridBarrier& gb) {
+  float* red = reinterpret_cast<float*>(smem + OFF_RED);    // [warp][4]
+  float* stat = reinterpret_cast<float*>(smem + OFF_STAT);  // [group of the CTA][4][2]: mean, rstd
   const int C = p.c0 + p.c1, NV = p.cb / 8, GB = p.cb / p.cgn, nblk = C / p.cb;
-  const int t = threadIdx.x, lanes_p = SEQ_THREADS / NV, cv = t % NV, pl = t / NV;
-  const bool active = pl < lanes_p;
+  const int TG = p.gw * 32, groups = NWARPS / p.gw;          // threads per item, items per CTA and round
+  const int gid = threadIdx.x / TG, tg = threadIdx.x - gid * TG;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, w0 = gid * p.gw;
+  const int lanes = TG / NV, cv = tg % NV, pl = tg / NV;     // pixel lanes of the item; this thread's column and first pixel
+  const bool active = pl < lanes;
   const int g_lo = (cv * 8) / p.cgn, eb = (g_lo + 1) * p.cgn - cv * 8;  // channels e < eb of the vector -> g_lo, the rest g_lo + 1
-  const int slab_elems = p.px * p.cb;
+  const int g_hi = min(g_lo + 1, GB - 1);
+  const int slab_bytes = p.px * p.cb * 2;
   const float inv_cnt = 1.f / ((float)p.px * (float)p.cgn);
+  const int per_round = gridDim.x * groups;
+  const int rounds = (p.n_items + per_round - 1) / per_round;
 
-  auto locate = [&](int item, const bf16*& src, int64_t& pitch, bf16*& dst) {
-    const int chunk = item % p.ps, blk = (item / p.ps) % nblk, img = item / (p.ps * nblk);
-    const int ch = blk * p.cb + cv * 8;
-    const int64_t pix0 = (int64_t)img * p.hw + (int64_t)chunk * p.px;
-    const bool first = ch < p.c0;
-    src = first ? p.x0 + pix0 * p.c0 + ch : p.x1 + pix0 * p.c1 + (ch - p.c0);
-    pitch = first ? p.c0 : p.c1;
-    dst = p.out + pix0 * C + ch;
-  };
-  auto apply = [&](const bf16* src, int64_t pitch, bf16* dst, const bf16* slab, int blk, float m_lo, float r_lo, float m_hi,
-                   float r_hi) {
-    const int ch = blk * p.cb + cv * 8;
-    const float4 g0 = *reinterpret_cast<const float4*>(p.gamma + ch), g1 = *reinterpret_cast<const float4*>(p.gamma + ch + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(p.beta + ch), b1 = *reinterpret_cast<const float4*>(p.beta + ch + 4);
-    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    float sc[8], sh[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const bool lo = e < eb;
-      sc[e] = (lo ? r_lo : r_hi) * gg[e];
-      sh[e] = bb[e] - (lo ? m_lo : m_hi) * sc[e];
-    }
-#pragma unroll 4
-    for (int pp = pl; pp < p.px; pp += lanes_p) {
-      const uint4 u = p.cache ? *reinterpret_cast<const uint4*>(slab + (int64_t)pp * p.cb + cv * 8) : ld_cg16(src + pp * pitch);
-      float f[8];
-      unpack8(u, f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float y = fmaf(f[e], sc[e], sh[e]);
-        f[e] = p.silu ? silu_f(y) : y;
-      }
-      *reinterpret_cast<uint4*>(dst + (int64_t)pp * C) = pack8(f);
-    }
-  };
-
-  int k = 0;
-  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++k) {
-    const bf16* src;
-    int64_t pitch;
-    bf16* dst;
-    locate(item, src, pitch, dst);
-    bf16* slab = slab0 + (int64_t)k * slab_elems;
-    // ---- pass 1: load (and cache) the chunk, per-channel sums -> group means
-    float sa[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) sa[e] = 0.f;
-    if (active) {
-      int pp = pl;
-      for (; pp + 7 * lanes_p < p.px; pp += 8 * lanes_p) {  // 8 independent 16-byte loads in flight per thread
-        uint4 u[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) u[j] = ld_cg16(src + (int64_t)(pp + j * lanes_p) * pitch);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (p.cache) *reinterpret_cast<uint4*>(slab + (int64_t)(pp + j * lanes_p) * p.cb + cv * 8) = u[j];
-          float f[8];
-          unpack8(u[j], f);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) sa[e] += f[e];
-        }
-      }
-      for (; pp < p.px; pp += lanes_p) {
-        const uint4 u = ld_cg16(src + (int64_t)pp * pitch);
-        if (p.cache) *reinterpret_cast<uint4*>(slab + (int64_t)pp * p.cb + cv * 8) = u;
-        float f[8];
-        unpack8(u, f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) sa[e] += f[e];
-      }
-    }
+  // sum `v` (this thread's contribution to groups g_lo / g_lo+1) over the item's threads: v_lo, v_hi -> totals of g_lo, g_hi
+  auto group_sum = [&](float& v_lo, float& v_hi) {
     float S[4];
-    {
-      float s_lo = 0.f, s_hi = 0.f;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        s_lo += e < eb ? sa[e] : 0.f;
-        s_hi += e < eb ? 0.f : sa[e];
-      }
-#pragma unroll
-      for (int g = 0; g < 4; ++g) S[g] = active ? ((g == g_lo ? s_lo : 0.f) + (g == g_lo + 1 ? s_hi : 0.f)) : 0.f;
+    for (int g = 0; g < 4; ++g) S[g] = warp_sum((g == g_lo ? v_lo : 0.f) + (g == g_lo + 1 ? v_hi : 0.f));
+    __syncthreads();  // previous readers of `red` are done
+    if (lane == 0) *reinterpret_cast<float4*>(red + warp * 4) = make_float4(S[0], S[1], S[2], S[3]);
+    __syncthreads();
+    float T[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int w = 0; w < p.gw; ++w) {  // the item's warps, in order
+      const float4 r = *reinterpret_cast<const float4*>(red + (w0 + w) * 4);
+      T[0] += r.x; T[1] += r.y; T[2] += r.z; T[3] += r.w;
     }
-    block_sum4(S, red);
-    const int g_hi = min(g_lo + 1, GB - 1);
-    float mean_lo = 0.f, mean_hi = 0.f;
+    v_lo = v_hi = 0.f;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      mean_lo = g == g_lo ? S[g] * inv_cnt : mean_lo;
-      mean_hi = g == g_hi ? S[g] * inv_cnt : mean_hi;
+      v_lo = g == g_lo ? T[g] : v_lo;
+      v_hi = g == g_hi ? T[g] : v_hi;
     }
-    // ---- pass 2: centred second moment
-    float q_lo = 0.f, q_hi = 0.f;
-    if (active) {
-#pragma unroll 4
-      for (int pp = pl; pp < p.px; pp += lanes_p) {
-        const uint4 u = p.cache ? *reinterpret_cast<const uint4*>(slab + (int64_t)pp * p.cb + cv * 8) : ld_cg16(src + pp * pitch);
-        float f[8];
-        unpack8(u, f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const bool lo = e < eb;
-          const float d = f[e] - (lo ? mean_lo : mean_hi);
-          q_lo = lo ? fmaf(d, d, q_lo) : q_lo;
-          q_hi = lo ? q_hi : fmaf(d, d, q_hi);
-        }
-      }
-    }
-    float Q[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) Q[g] = (g == g_lo ? q_lo : 0.f) + (g == g_lo + 1 ? q_hi : 0.f);
-    block_sum4(Q, red);
-    if (p.ps == 1) {
-      float r_lo = 0.f, r_hi = 0.f;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float r = rsqrtf(Q[g] * inv_cnt + p.eps);
-        r_lo = g == g_lo ? r : r_lo;
-        r_hi = g == g_hi ? r : r_hi;
-      }
-      if (active) apply(src, pitch, dst, slab, (item / p.ps) % nblk, mean_lo, r_lo, mean_hi, r_hi);
-    } else if (t < GB) {
-      float mg = 0.f, qg = 0.f;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        mg = g == t ? S[g] * inv_cnt : mg;
-        qg = g == t ? Q[g] : qg;
-      }
-      *reinterpret_cast<float2*>(p.partial + ((int64_t)item * 4 + t) * 2) = make_float2(mg, qg);
-    }
-  }
-  if (p.ps == 1) return;
-  gb.sync(nullptr, nullptr);
-  k = 0;
-  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++k) {
-    const bf16* src;
-    int64_t pitch;
-    bf16* dst;
-    locate(item, src, pitch, dst);
-    __syncthreads();  // previous item's readers of `stat` are done
-    if (t < GB) {     // merge the image's chunks in chunk order (equal counts): mean of means, M2 += n (mean_c - mean)^2
-      const int64_t first = (int64_t)(item - item % p.ps);
-      float msum = 0.f;
-      for (int c = 0; c < p.ps; ++c) msum += __ldcg(p.partial + ((first + c) * 4 + t) * 2);
-      const float mean = msum / (float)p.ps;
-      float m2 = 0.f;
-      const float n_c = (float)p.px * (float)p.cgn;
-      for (int c = 0; c < p.ps; ++c) {
-        const float2 pr = __ldcg(reinterpret_cast<const float2*>(p.partial + ((first + c) * 4 + t) * 2));
-        const float d = pr.x - mean;
-        m2 += pr.y + n_c * d * d;
-      }
-      stat[2 * t] = mean;
-      stat[2 * t + 1] = rsqrtf(m2 / (n_c * (float)p.ps) + p.eps);
-    }
-    __syncthreads();
-    const int g_hi = min(g_lo + 1, GB - 1);
-    if (active)
-      apply(src, pitch, dst, slab0 + (int64_t)k * slab_elems, (item / p.ps) % nblk, stat[2 * g_lo], stat[2 * g_lo + 1], stat[2 * g_hi],
-            stat[2 * g_hi + 1]);
-  }
-}
+  };
 
-// Small images (<= 320 vectors per (image, channel block)): one WARP per item, the block in registers, shuffle-only
-// reductions, no CTA barrier; the 8 warps of a CTA work on 8 items at once.
-__device__ __noinline__ void gn_warp(const SeqGN& p) {
-  constexpr int MAXV = GN_WARP_MAXV;
-  const int C = p.c0 + p.c1, NV = p.cb / 8, GB = p.cb / p.cgn, nblk = C / p.cb;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * NWARPS + warp, GW = gridDim.x * NWARPS;
-  const int nvec = p.hw * NV;
-  const float inv_cnt = 1.f / ((float)p.hw * (float)p.cgn);
-  for (int item = gw; item < p.n_items; item += GW) {
-    const int blk = item % nblk, img = item / nblk;
-    uint4 raw[MAXV];
-    int cvs[MAXV];  // vector column of slot j (NV is not a power of two: computed once)
-#pragma unroll
-    for (int j = 0; j < MAXV; ++j) {
-      const int v = lane + 32 * j;
-      const int pix = (int)__umulhi((unsigned)v, p.nv_magic);
-      cvs[j] = v - pix * NV;
-      raw[j] = make_uint4(0u, 0u, 0u, 0u);
-      if (v < nvec) {
-        const int ch = blk * p.cb + cvs[j] * 8;
-        const int64_t pixel = (int64_t)img * p.hw + pix;
-        raw[j] = ld_cg16(ch < p.c0 ? p.x0 + pixel * p.c0 + ch : p.x1 + pixel * p.c1 + (ch - p.c0));
-      }
-    }
-    float S[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < MAXV; ++j) {
-      const int g_lo = (cvs[j] * 8) / p.cgn, eb = (g_lo + 1) * p.cgn - cvs[j] * 8;
-      float f[8], s_lo = 0.f, s_hi = 0.f;
-      unpack8(raw[j], f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        s_lo += e < eb ? f[e] : 0.f;
-        s_hi += e < eb ? 0.f : f[e];
-      }
-#pragma unroll
-      for (int g = 0; g < 4; ++g) S[g] += (g == g_lo ? s_lo : 0.f) + (g == g_lo + 1 ? s_hi : 0.f);  // empty slots add zeros
-    }
-    float mean[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) mean[g] = warp_sum(S[g]) * inv_cnt;
-    float Q[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < MAXV; ++j) {
-      if (lane + 32 * j < nvec) {
-        const int g_lo = (cvs[j] * 8) / p.cgn, eb = (g_lo + 1) * p.cgn - cvs[j] * 8;
-        float m_lo = 0.f, m_hi = 0.f;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          m_lo = g == g_lo ? mean[g] : m_lo;
-          m_hi = g == g_lo + 1 ? mean[g] : m_hi;
+#pragma unroll 1
+  for (int phase = 0; phase < (p.ps > 1 ? 2 : 1); ++phase) {
+    if (phase == 1) gb.sync(nullptr, nullptr);
+#pragma unroll 1
+    for (int k = 0; k < rounds; ++k) {
+      const int item = k * per_round + gid * gridDim.x + blockIdx.x;
+      const bool valid = item < p.n_items && active;
+      const int it = min(item, p.n_items - 1);
+      const int chunk = it % p.ps, blk = (it / p.ps) % nblk, img = it / (p.ps * nblk);
+      const int ch = blk * p.cb + cv * 8;
+      const int64_t pix0 = (int64_t)img * p.hw + (int64_t)chunk * p.px;
+      const bool first = ch < p.c0;
+      const bf16* src = first ? p.x0 + pix0 * p.c0 + ch : p.x1 + pix0 * p.c1 + (ch - p.c0);
+      const int pitch = first ? p.c0 : p.c1;
+      const uint4* slab = reinterpret_cast<const uint4*>(smem + AUX_BYTES + (size_t)(k * groups + gid) * slab_bytes) + cv;
+      float m_lo, m_hi, r_lo, r_hi;
+      if (phase == 0) {
+        if (valid) {
+#pragma unroll 1
+          for (int pp = pl; pp < p.px; pp += lanes) cp_async16(const_cast<uint4*>(slab) + pp * NV, src + (int64_t)pp * pitch);
         }
-        float f[8], q_lo = 0.f, q_hi = 0.f;
-        unpack8(raw[j], f);
+        cp_async_wait_all();
+        __syncthreads();
+        // ---- pass 1: per-channel sums -> group means
+        float sa[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sa[e] = 0.f;
+        if (valid) {
+#pragma unroll 2
+          for (int pp = pl; pp < p.px; pp += lanes) {
+            float f[8];
+            unpack8(slab[pp * NV], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sa[e] += f[e];
+          }
+        }
+        m_lo = m_hi = 0.f;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const bool lo = e < eb;
-          const float d = f[e] - (lo ? m_lo : m_hi);
-          q_lo = lo ? fmaf(d, d, q_lo) : q_lo;
-          q_hi = lo ? q_hi : fmaf(d, d, q_hi);
+          m_lo += e < eb ? sa[e] : 0.f;
+          m_hi += e < eb ? 0.f : sa[e];
         }
+        group_sum(m_lo, m_hi);
+        m_lo *= inv_cnt;
+        m_hi *= inv_cnt;
+        // ---- pass 2: centred second moment
+        r_lo = r_hi = 0.f;
+        if (valid) {
+#pragma unroll 2
+          for (int pp = pl; pp < p.px; pp += lanes) {
+            float f[8];
+            unpack8(slab[pp * NV], f);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) Q[g] += (g == g_lo ? q_lo : 0.f) + (g == g_lo + 1 ? q_hi : 0.f);
+            for (int e = 0; e < 8; ++e) {
+              const bool lo = e < eb;
+              const float d = f[e] - (lo ? m_lo : m_hi);
+              r_lo = lo ? fmaf(d, d, r_lo) : r_lo;
+              r_hi = lo ? r_hi : fmaf(d, d, r_hi);
+            }
+          }
+        }
+        group_sum(r_lo, r_hi);
+        if (p.ps > 1) {  // (mean, M2) of this chunk per group; merged after the grid barrier
+          if (valid && pl == 0) {  // one thread per vector column reports the group(s) its channels belong to (every group is
+            float* po = p.partial + (int64_t)item * 8;  // some column's first or second group; duplicates store equal values)
+            *reinterpret_cast<float2*>(po + 2 * g_lo) = make_float2(m_lo, r_lo);
+            if (eb < 8 && g_lo + 1 < GB) *reinterpret_cast<float2*>(po + 2 * (g_lo + 1)) = make_float2(m_hi, r_hi);
+          }
+          continue;
+        }
+        r_lo = rsqrtf(r_lo * inv_cnt + p.eps);
+        r_hi = rsqrtf(r_hi * inv_cnt + p.eps);
+      } else {
+        // ---- merge the image's chunks in chunk order (equal counts): mean of means, M2 += n (mean_c - mean)^2
+        __syncthreads();  // previous round's readers of `stat` are done
+        if (item < p.n_items && tg < GB) {
+          const float* pi = p.partial + (int64_t)(item - chunk) * 8 + 2 * tg;
+          float msum = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < p.ps; ++c) msum += __ldcg(pi + c * 8);
+          const float mean = msum / (float)p.ps;
+          const float n_c = (float)p.px * (float)p.cgn;
+          float m2 = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < p.ps; ++c) {
+            const float2 pr = __ldcg(reinterpret_cast<const float2*>(pi + c * 8));
+            const float d = pr.x - mean;
+            m2 += pr.y + n_c * d * d;
+          }
+          stat[(gid * 4 + tg) * 2] = mean;
+          stat[(gid * 4 + tg) * 2 + 1] = rsqrtf(m2 / (n_c * (float)p.ps) + p.eps);
+        }
+        __syncthreads();
+        m_lo = stat[(gid * 4 + g_lo) * 2];
+        r_lo = stat[(gid * 4 + g_lo) * 2 + 1];
+        m_hi = stat[(gid * 4 + g_hi) * 2];
+        r_hi = stat[(gid * 4 + g_hi) * 2 + 1];
       }
-    }
-    float rstd[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) rstd[g] = rsqrtf(warp_sum(Q[g]) * inv_cnt + p.eps);
-    (void)GB;
-#pragma unroll
-    for (int j = 0; j < MAXV; ++j) {
-      const int v = lane + 32 * j;
-      if (v < nvec) {
-        const int pix = (int)__umulhi((unsigned)v, p.nv_magic);
-        const int g_lo = (cvs[j] * 8) / p.cgn, eb = (g_lo + 1) * p.cgn - cvs[j] * 8;
-        float m_lo = 0.f, m_hi = 0.f, r_lo = 0.f, r_hi = 0.f;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          m_lo = g == g_lo ? mean[g] : m_lo;
-          r_lo = g == g_lo ? rstd[g] : r_lo;
-          m_hi = g == g_lo + 1 ? mean[g] : m_hi;
-          r_hi = g == g_lo + 1 ? rstd[g] : r_hi;
-        }
-        const int ch = blk * p.cb + cvs[j] * 8;
+      // ---- normalise from shared memory
+      if (valid) {
         const float4 g0 = *reinterpret_cast<const float4*>(p.gamma + ch), g1 = *reinterpret_cast<const float4*>(p.gamma + ch + 4);
         const float4 b0 = *reinterpret_cast<const float4*>(p.beta + ch), b1 = *reinterpret_cast<const float4*>(p.beta + ch + 4);
         const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        float f[8];
-        unpack8(raw[j], f);
+        float sc[8], sh[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const bool lo = e < eb;
-          const float y = (f[e] - (lo ? m_lo : m_hi)) * (lo ? r_lo : r_hi) * gg[e] + bb[e];
-          f[e] = p.silu ? silu_f(y) : y;
+          sc[e] = (lo ? r_lo : r_hi) * gg[e];
+          sh[e] = bb[e] - (lo ? m_lo : m_hi) * sc[e];
         }
-        *reinterpret_cast<uint4*>(p.out + ((int64_t)img * p.hw + pix) * C + ch) = pack8(f);
+        bf16* dst = p.out + pix0 * C + ch;
+#pragma unroll 2
+        for (int pp = pl; pp < p.px; pp += lanes) {
+          float f[8];
+          unpack8(slab[pp * NV], f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float y = fmaf(f[e], sc[e], sh[e]);
+            f[e] = p.silu ? silu_f(y) : y;
+          }
+          *reinterpret_cast<uint4*>(dst + (int64_t)pp * C) = pack8(f);
+        }
       }
     }
   }
 }
 
 // =====================================================================================================
-// SEQ_LN  LayerNorm over the channel dim: one warp per token, R tokens in flight per warp, rows in registers
+// SEQ_LN  LayerNorm over the channel dim: one warp per token, R tokens staged in shared memory per warp and pass
 // =====================================================================================================
-template <int MAXV>
-__device__ __noinline__ void ln_rows(const SeqLN& p) {
-  constexpr int R = MAXV >= 8 ? 2 : 4;
+__device__ __noinline__ void ln_op(const SeqLN& p, uint8_t* smem) {
+  constexpr int R = 4;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * NWARPS + warp, GW = gridDim.x * NWARPS;
   const int nv = p.c / 8;
   const float inv_c = 1.f / (float)p.c;
-  for (int r0 = gw; r0 < p.rows; r0 += R * GW) {
-    uint4 raw[R][MAXV];
-#pragma unroll
+  // gamma / beta once per CTA, rows per warp behind them
+  float* gam = reinterpret_cast<float*>(smem + AUX_BYTES);
+  float* bet = gam + p.c;
+  uint4* rows = reinterpret_cast<uint4*>(bet + p.c) + (size_t)warp * R * nv;
+#pragma unroll 1
+  for (int i = threadIdx.x; i < p.c / 4; i += SEQ_THREADS) {
+    cp_async16(gam + 4 * i, p.gamma + 4 * i);
+    cp_async16(bet + 4 * i, p.beta + 4 * i);
+  }
+  auto stage_rows = [&](int r0) {
+#pragma unroll 1
     for (int u = 0; u < R; ++u) {
       const int row = r0 + u * GW;
-#pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        const int v = lane + 32 * i;
-        raw[u][i] = (row < p.rows && v < nv) ? ld_cg16(p.x + (int64_t)row * p.c + v * 8) : make_uint4(0u, 0u, 0u, 0u);
+      if (row < p.rows) {
+#pragma unroll 1
+        for (int v = lane; v < nv; v += 32) cp_async16(rows + u * nv + v, p.x + (int64_t)row * p.c + v * 8);
       }
     }
-#pragma unroll
+  };
+  stage_rows(gw);  // first pass of this warp (if any), in flight together with gamma / beta
+  cp_async_wait_all();
+  __syncthreads();
+#pragma unroll 1
+  for (int r0 = gw; r0 < p.rows; r0 += R * GW) {
+    if (r0 != gw) {
+      stage_rows(r0);
+      cp_async_wait_all();
+      __syncwarp();
+    }
+#pragma unroll 1
     for (int u = 0; u < R; ++u) {
       const int row = r0 + u * GW;
       if (row >= p.rows) break;  // warp-uniform
+      const uint4* xr = rows + u * nv;
       float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
+#pragma unroll 1
+      for (int v = lane; v < nv; v += 32) {
         float f[8];
-        unpack8(raw[u][i], f);
+        unpack8(xr[v], f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += f[j];
       }
       const float mean = warp_sum(s) * inv_c;
       float q = 0.f;
+#pragma unroll 1
+      for (int v = lane; v < nv; v += 32) {
+        float f[8];
+        unpack8(xr[v], f);
 #pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        if (lane + 32 * i < nv) {
-          float f[8];
-          unpack8(raw[u][i], f);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float d = f[j] - mean;
-            q = fmaf(d, d, q);
-          }
+        for (int j = 0; j < 8; ++j) {
+          const float d = f[j] - mean;
+          q = fmaf(d, d, q);
         }
       }
       const float rstd = rsqrtf(warp_sum(q) * inv_c + p.eps);
-#pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        const int v = lane + 32 * i;
-        if (v < nv) {
-          const float4 g0 = *reinterpret_cast<const float4*>(p.gamma + v * 8), g1 = *reinterpret_cast<const float4*>(p.gamma + v * 8 + 4);
-          const float4 b0 = *reinterpret_cast<const float4*>(p.beta + v * 8), b1 = *reinterpret_cast<const float4*>(p.beta + v * 8 + 4);
-          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-          float f[8];
-          unpack8(raw[u][i], f);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * gg[j] + bb[j];
-          *reinterpret_cast<uint4*>(p.out + (int64_t)row * p.c + v * 8) = pack8(f);
-        }
+#pragma unroll 1
+      for (int v = lane; v < nv; v += 32) {
+        float f[8];
+        unpack8(xr[v], f);
+        const float4 g0 = *reinterpret_cast<const float4*>(gam + v * 8), g1 = *reinterpret_cast<const float4*>(gam + v * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(bet + v * 8), b1 = *reinterpret_cast<const float4*>(bet + v * 8 + 4);
+        f[0] = (f[0] - mean) * rstd * g0.x + b0.x; f[1] = (f[1] - mean) * rstd * g0.y + b0.y;
+        f[2] = (f[2] - mean) * rstd * g0.z + b0.z; f[3] = (f[3] - mean) * rstd * g0.w + b0.w;
+        f[4] = (f[4] - mean) * rstd * g1.x + b1.x; f[5] = (f[5] - mean) * rstd * g1.y + b1.y;
+        f[6] = (f[6] - mean) * rstd * g1.z + b1.z; f[7] = (f[7] - mean) * rstd * g1.w + b1.w;
+        *reinterpret_cast<uint4*>(p.out + (int64_t)row * p.c + v * 8) = pack8(f);
       }
     }
+    __syncwarp();  // the row buffers are refilled by the next pass
   }
 }
 
 // =====================================================================================================
 // small elementwise ops
 // =====================================================================================================
-__device__ __noinline__ void upsample_op(const SeqEW& p) {  // nearest 2x, bf16 NHWC
+__device__ __noinline__ void upsample_op(const SeqEW& p) {  // nearest 2x, bf16 NHWC; 32-bit index arithmetic
   const bf16* x = reinterpret_cast<const bf16*>(p.src);
   bf16* out = reinterpret_cast<bf16*>(p.dst);
-  const int cv = p.c / 8;
-  const int64_t total = (int64_t)p.n_img * 4 * p.h * p.w * cv;
-  for (int64_t i = (int64_t)blockIdx.x * SEQ_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * SEQ_THREADS) {
-    const int v = (int)(i % cv);
-    int64_t q = i / cv;
-    const int ox = (int)(q % (2 * p.w));
-    q /= 2 * p.w;
-    const int oy = (int)(q % (2 * p.h));
-    const int img = (int)(q / (2 * p.h));
-    *reinterpret_cast<uint4*>(out + i * 8) = ld_cg16(x + (((int64_t)img * p.h + oy / 2) * p.w + ox / 2) * p.c + v * 8);
+  const int cv = p.c / 8, w2 = 2 * p.w, h2 = 2 * p.h;
+  const int total = p.n_img * h2 * w2 * cv;
+#pragma unroll 1
+  for (int i = blockIdx.x * SEQ_THREADS + threadIdx.x; i < total; i += gridDim.x * SEQ_THREADS) {
+    const int v = i % cv, q = i / cv;
+    const int ox = q % w2, q2 = q / w2;
+    const int oy = q2 % h2, img = q2 / h2;
+    *reinterpret_cast<uint4*>(out + (int64_t)i * 8) = ld_cg16(x + ((int64_t)(img * p.h + oy / 2) * p.w + ox / 2) * p.c + v * 8);
   }
 }
 
@@ -962,23 +887,18 @@ __device__ __noinline__ void im2col_op(const SeqEW& p) {
   const float* x = reinterpret_cast<const float*>(p.src);
   bf16* out = reinterpret_cast<bf16*>(p.dst);
   const int cin = p.c, h = p.h, w = p.w, kpad = p.aux;
-  const int kv = kpad / 8;  // one thread = eight consecutive k of one output pixel = one 16-byte store
-  const int total = p.n_img * h * w * kv;
+  const int total = p.n_img * h * w * kpad;  // one thread = one element: consecutive threads write consecutive bf16
+#pragma unroll 1
   for (int i = blockIdx.x * SEQ_THREADS + threadIdx.x; i < total; i += gridDim.x * SEQ_THREADS) {
-    const int m = i / kv, k0 = (i - m * kv) * 8;
+    const int m = i / kpad, k = i - m * kpad;
     const int px = m % w, py = (m / w) % h, img = m / (w * h);
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = k0 + j;
-      v[j] = 0.f;
-      if (k < 9 * cin) {
-        const int tap = k / cin, c = k - tap * cin;
-        const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
-        if (yy >= 0 && yy < h && xx >= 0 && xx < w) v[j] = __ldcg(x + ((img * cin + c) * h + yy) * w + xx);
-      }
+    float v = 0.f;
+    if (k < 9 * cin) {
+      const int tap = k / cin, c = k - tap * cin;
+      const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w) v = __ldcg(x + ((img * cin + c) * h + yy) * w + xx);
     }
-    *reinterpret_cast<uint4*>(out + (int64_t)i * 8) = pack8(v);
+    out[i] = __float2bfloat16(v);
   }
 }
 
@@ -988,6 +908,7 @@ __device__ __noinline__ void sinusoid_op(const SeqEW& p) {
   const int64_t* t = reinterpret_cast<const int64_t*>(p.src);
   bf16* out = reinterpret_cast<bf16*>(p.dst);
   const int n = p.n_img, dim = p.c, half = dim / 2;
+#pragma unroll 1
   for (int i = blockIdx.x * SEQ_THREADS + threadIdx.x; i < n * half; i += gridDim.x * SEQ_THREADS) {
     const int r = i / half, j = i - r * half;
     const float freq = expf(-logf(10000.f) * (float)j / (float)half);
@@ -1005,23 +926,21 @@ __device__ __noinline__ void splitk_reduce_op(const SeqEW& p) {
   bf16* out = reinterpret_cast<bf16*>(p.dst);
   const int splits = p.aux, M = p.n_img, N = p.c, hw = p.h, rowvec_ld = p.aux2, res_ld = p.aux3, ldo = p.aux4;
   const int nv = N / 8;
-  const int64_t total = (int64_t)M * nv;
-  for (int64_t i = (int64_t)blockIdx.x * SEQ_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * SEQ_THREADS) {
-    const int m = (int)(i / nv), n = (int)(i % nv) * 8;
+  const int total = M * nv;
+#pragma unroll 1
+  for (int i = blockIdx.x * SEQ_THREADS + threadIdx.x; i < total; i += gridDim.x * SEQ_THREADS) {
+    const int m = i / nv, n = (i - m * nv) * 8;
     float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
     for (int z = 0; z < splits; ++z) {
       const float4* pp = reinterpret_cast<const float4*>(partial + ((int64_t)z * M + m) * N + n);
       const float4 a = __ldcg(pp), b = __ldcg(pp + 1);
       v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
     }
-    if (p.bias) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += p.bias[n + j];
-    }
-    if (p.rowvec) {
-      const float* rv = p.rowvec + (int64_t)(m / hw) * rowvec_ld + n;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += __ldcg(rv + j);
+    for (int j = 0; j < 8; ++j) {
+      if (p.bias) v[j] += p.bias[n + j];
+      if (p.rowvec) v[j] += __ldcg(p.rowvec + (int64_t)(m / hw) * rowvec_ld + n + j);
     }
     if (residual) {
       float f[8];
@@ -1037,7 +956,7 @@ __device__ __noinline__ void splitk_reduce_op(const SeqEW& p) {
 // the kernel
 // =====================================================================================================
 __global__ void __launch_bounds__(SEQ_THREADS, 1) seq_kernel(const SeqOp* __restrict__ ops, int n_ops, unsigned* sync,
-                                                             long long* timing) {
+                                                             long long* timing, int flags, long long* trace) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = tc::smem_u32(smem_raw);
   const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
@@ -1064,36 +983,57 @@ __global__ void __launch_bounds__(SEQ_THREADS, 1) seq_kernel(const SeqOp* __rest
   const uint32_t tmem_base = *reinterpret_cast<const uint32_t*>(smem + OFF_TMEM);
   const SeqOpC& op = *reinterpret_cast<const SeqOpC*>(smem + OFF_DESC);
 
-  if (threadIdx.x == 0 && op.type == SEQ_GEMM) acquire_tensormaps(ops, op.g.nseg);
-  GridBarrier gb{sync, 0u, timing};
-  RoleState st{0xffffffffu, 0u, 0u};
+  // The tensor maps live in global memory (written by cudaMemcpy before the launch) and are read through the tensormap
+  // proxy: every CTA acquires them before first use (CUDA programming guide, "tensor map in global memory") - all maps of
+  // the launch here, spread over the threads, so that no op pays for it on its critical path.
+  if (flags & SEQ_F_TMAP_FENCE) {
+    constexpr int MAPS = (MVLDM_MAX_SEGS + 1) * KC;
+#pragma unroll 1
+    for (int i = threadIdx.x; i < n_ops * MAPS; i += SEQ_THREADS) {
+      const CUtensorMap* m = &ops[i / MAPS].tmA[0][0] + (i % MAPS);
+      asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+    }
+    __syncthreads();
+  }
+  // the op descriptors and tensor maps are touched once per forward (cold in L2 behind 1.5 GB of weights): pull the whole
+  // list into L2 now, the first op's maps into the descriptor cache
+  {
+    const char* base = reinterpret_cast<const char*>(ops);
+    const int lines = n_ops * (int)(sizeof(SeqOp) / 128);
+#pragma unroll 1
+    for (int i = threadIdx.x + (blockIdx.x % 4) * SEQ_THREADS; i < lines; i += 4 * SEQ_THREADS)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)i * 128));
+    if (threadIdx.x == 0 && op.type == SEQ_GEMM) prefetch_tensormaps(ops, op.g.nseg);
+  }
+  GridBarrier gb{sync, 0u, timing, flags, trace, 0};
+  RoleState st{0xffffffffu, 0u, 0u, nullptr};
+#pragma unroll 1
   for (int i = 0; i < n_ops; ++i) {
     const int type = op.type;
+    gb.op = i;
+    st.tr = trace ? trace + ((size_t)gb.n * gridDim.x + blockIdx.x) * 16 : nullptr;
     if (type == SEQ_GEMM) {
-      gemm_op(op.g, op.pf, op.next_nseg, ops + i, smem, smem_base, tmem_base, st);
+      if (warp == 0) {
+        if (lane == 0) {
+          gemm_producer(op.g, ops + i, smem_base, st);
+          // the rest of this op (MMA tail, epilogue, reduction, barrier) hides the HBM latency of the next op's weights
+          if (op.next_nseg > 0) prefetch_tensormaps(ops + i + 1, op.next_nseg);
+          if (flags & SEQ_F_PREFETCH) prefetch_next_weights(op.pf);
+        }
+        __syncwarp();
+      } else if (warp == 1) {
+        gemm_mma(op.g, smem_base, tmem_base, st);
+      } else if (warp < 6) {
+        gemm_epilogue(op.g, smem, smem_base, tmem_base, st);
+      }  // (warps 6, 7 have no GEMM role: they wait at the op barrier)
     } else {
-      if (threadIdx.x == 0) {
-        acquire_tensormaps(ops + i + 1, op.next_nseg);
-        prefetch_next_weights(op.pf);
-      }
-      if (type == SEQ_GN) {
-        if (op.gn.warp_mode) gn_warp(op.gn);
-        else gn_cta(op.gn, smem, gb);
-      } else if (type == SEQ_LN) {
-        const int c = op.ln.c;
-        if (c <= 512) ln_rows<2>(op.ln);
-        else if (c <= 768) ln_rows<3>(op.ln);
-        else if (c <= 1280) ln_rows<5>(op.ln);
-        else ln_rows<8>(op.ln);
-      } else if (type == SEQ_UPSAMPLE) {
-        upsample_op(op.ew);
-      } else if (type == SEQ_IM2COL) {
-        im2col_op(op.ew);
-      } else if (type == SEQ_SINUSOID) {
-        sinusoid_op(op.ew);
-      } else if (type == SEQ_SPLITK_REDUCE) {
-        splitk_reduce_op(op.ew);
-      }
+      if (threadIdx.x == 0 && op.next_nseg > 0) prefetch_tensormaps(ops + i + 1, op.next_nseg);
+      if (type == SEQ_GN) gn_op(op.gn, smem, gb);
+      else if (type == SEQ_LN) ln_op(op.ln, smem);
+      else if (type == SEQ_UPSAMPLE) upsample_op(op.ew);
+      else if (type == SEQ_IM2COL) im2col_op(op.ew);
+      else if (type == SEQ_SINUSOID) sinusoid_op(op.ew);
+      else if (type == SEQ_SPLITK_REDUCE) splitk_reduce_op(op.ew);
     }
     if (i + 1 < n_ops) gb.sync(ops + i + 1, smem + OFF_DESC);
   }
@@ -1161,6 +1101,7 @@ TileChoice pick_tiles(const mvldm_gemm_desc& d) {
   for (int bn : kBN) {
     if (d.n % bn != 0) continue;
     if (d.mode == 2 && bn != 32) continue;
+    if (d.residual && bn > 160) continue;  // the epilogue parks the residual row in the accumulator buffer's spare TMEM columns
     if (force_bn && atoi(force_bn) != bn) continue;
     for (int sp : kSplits) {
       if (sp > 1 && (d.mode != 0 || num_steps / sp < 3)) break;
@@ -1306,31 +1247,25 @@ bool seq_plan_gemm(const mvldm_gemm_desc& d, void* workspace, size_t workspace_b
 }
 
 void seq_link_prefetch(SeqOp* ops, int n, const SeqOp* dev_ops) {
-  for (int i = 0; i + 1 < n; ++i) {
-    SeqOp& cur = ops[i];
-    const SeqOp& nx = ops[i + 1];
-    cur.c.next_nseg = 0;
-    cur.c.pf.map = nullptr;
-    if (nx.c.type != SEQ_GEMM) continue;
-    const SeqGemm& g = nx.c.g;
-    cur.c.next_nseg = g.nseg;
-    SeqPrefetch& pf = cur.c.pf;
-    pf.map = &dev_ops[i + 1].tmB[KC - 1];
-    pf.bn = g.bn; pf.mt = g.mt; pf.nt = g.nt; pf.splits = g.splits;
-    // K chunk (64 wide) at which every pipeline step starts: chunks are consecutive along K over (segment, tap, block)
-    std::vector<int> step_chunk;
-    for (int s = 0; s < g.nseg; ++s)
-      for (int t = 0; t < g.seg[s].ntaps; ++t)
-        for (int cb = 0; cb < g.seg[s].ncblk; cb += KC) step_chunk.push_back(g.seg[s].kchunk0 + t * g.seg[s].ncblk + cb);
-    const int total = g.seg[g.nseg - 1].kchunk0 + g.seg[g.nseg - 1].ntaps * g.seg[g.nseg - 1].ncblk;
-    for (int z = 0; z < g.splits; ++z) pf.chunk0[z] = (uint16_t)step_chunk[std::min<size_t>((size_t)z * g.steps_per_split, step_chunk.size() - 1)];
-    pf.chunk0[g.splits] = (uint16_t)total;
+  int next_gemm = -1;
+  for (int i = n - 1; i >= 0; --i) {
+    ops[i].c.index = i;
+    ops[i].c.pf.map = nullptr;
+    if (ops[i].c.type != SEQ_GEMM) continue;
+    if (next_gemm >= 0) {
+      const SeqGemm& g = ops[next_gemm].c.g;
+      SeqPrefetch& pf = ops[i].c.pf;
+      pf.map = &dev_ops[next_gemm].tmB[KC - 1];
+      pf.bn = g.bn;
+      pf.nt = g.nt;
+      pf.nchunks = g.seg[g.nseg - 1].kchunk0 + g.seg[g.nseg - 1].ntaps * g.seg[g.nseg - 1].ncblk;
+    }
+    next_gemm = i;
   }
-  if (n > 0) {
-    ops[n - 1].c.next_nseg = 0;
-    ops[n - 1].c.pf.map = nullptr;
-  }
-  for (int i = 0; i < n; ++i) ops[i].c.index = i;
+}
+
+void seq_link_launch(SeqOp* ops, int n) {
+  for (int i = 0; i < n; ++i) ops[i].c.next_nseg = (i + 1 < n && ops[i + 1].c.type == SEQ_GEMM) ? ops[i + 1].c.g.nseg : 0;
 }
 
 size_t seq_groupnorm_scratch_floats(int n_img, int c, int groups) {
@@ -1356,27 +1291,37 @@ void seq_plan_groupnorm(const bf16* x0, int c0, const bf16* x1, int c1, int n_im
   p.c0 = c0; p.c1 = c1; p.n_img = n_img; p.hw = hw; p.cgn = cgn; p.cb = cb;
   p.silu = silu ? 1 : 0;
   p.eps = eps;
-  p.nv_magic = (uint32_t)((0x100000000ull + NV - 1) / NV);
   const int64_t items0 = (int64_t)n_img * nblk;
-  if (hw * NV <= 32 * GN_WARP_MAXV) {
-    p.warp_mode = 1;
-    p.ps = 1;
-    p.px = hw;
-    p.n_items = (int)items0;
-    return;
-  }
+  // big images on few (image, block) items: split the pixels over CTAs (statistics merged across a grid barrier)
   int ps = 1;
   while (items0 * ps * 2 <= grid && hw % (ps * 2) == 0 && hw / (ps * 2) >= 64) ps *= 2;
   p.ps = ps;
   p.px = hw / ps;
   p.n_items = (int)(items0 * ps);
   MV_CHECK((size_t)p.n_items * 8 <= seq_groupnorm_scratch_floats(n_img, C, groups) || ps == 1, "groupnorm: scratch too small");
-  const int64_t per_cta = (p.n_items + grid - 1) / grid;
-  p.cache = per_cta * p.px * cb * 2 <= WORK_BYTES ? 1 : 0;
+  // warps per item: fewest rounds first (a round costs ~1 us of latency), then fewest vectors per thread
+  const size_t slab = (size_t)p.px * cb * 2;
+  int best_gw = 0;
+  double best_cost = 1e30;
+  for (int gw : {8, 4, 2, 1}) {
+    if (ps > 1 && gw != 8) continue;
+    if (gw * 32 < NV) continue;
+    const int groups_cta = NWARPS / gw;
+    const int64_t rounds = (p.n_items + (int64_t)grid * groups_cta - 1) / ((int64_t)grid * groups_cta);
+    if ((size_t)rounds * groups_cta * slab > (size_t)WORK_BYTES) continue;
+    const double vec_per_thread = (double)p.px / (double)(gw * 32 / NV);
+    const double cost = rounds * (1.0 + 0.05 * vec_per_thread);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best_gw = gw;
+    }
+  }
+  MV_CHECK(best_gw != 0, "groupnorm: image too large for the shared-memory slab (pixels per image x channel block)");
+  p.gw = best_gw;
 }
 
 void seq_plan_layernorm(const bf16* x, int rows, int c, float eps, const float* gamma, const float* beta, bf16* out, SeqOp& op) {
-  MV_CHECK(c % 8 == 0 && c <= 32 * 8 * 8, "layernorm: unsupported channel count");
+  MV_CHECK(c % 8 == 0 && c <= 32 * 8 * 8 && (size_t)c * (8 + NWARPS * 4 * 2) <= (size_t)WORK_BYTES, "layernorm: unsupported channel count");
   memset(&op, 0, sizeof(op));
   op.c.type = SEQ_LN;
   SeqLN& p = op.c.ln;
@@ -1407,6 +1352,8 @@ void seq_plan_sinusoid(const int64_t* t, int n, int dim, bf16* out, SeqOp& op) {
   p.src = t; p.dst = out; p.n_img = n; p.c = dim;
 }
 
+long long* g_seq_trace = nullptr;  // debug: device buffer the next launches write their barrier timeline to (or NULL)
+
 void seq_configure() {  // once per device, outside any stream capture
   static bool configured[kMaxDevices] = {};
   if (first_use_on_device(configured)) {
@@ -1425,7 +1372,14 @@ void seq_launch(cudaStream_t s, const SeqOp* dev_ops, int n_ops, unsigned* sync,
     const char* e = getenv("MVLDM_SEQ_COOP");
     return !e || atoi(e) != 0;
   }();
-  void* args[] = {(void*)&dev_ops, (void*)&n_ops, (void*)&sync, (void*)&timing};
+  static const int env_flags = [] {
+    const char* e = getenv("MVLDM_SEQ_FLAGS");
+    return e ? atoi(e) : 7;
+  }();
+  int flags = env_flags;
+  long long* trace = g_seq_trace;
+  if (g_seq_trace) g_seq_trace += (size_t)2 * n_ops * seq_grid() * 16;  // room for this launch's barriers (<= 2 per op)
+  void* args[] = {(void*)&dev_ops, (void*)&n_ops, (void*)&sync, (void*)&timing, (void*)&flags, (void*)&trace};
   if (coop) {
     MV_CUDA(cudaLaunchCooperativeKernel((const void*)seq_kernel, dim3(seq_grid()), dim3(SEQ_THREADS), args, SMEM_BYTES, s));
   } else {
@@ -1456,8 +1410,16 @@ void seq_run_host_ops(cudaStream_t s, const SeqOp* host_ops, int n_ops) {
   }
   std::vector<SeqOp> tmp(host_ops, host_ops + n_ops);
   seq_link_prefetch(tmp.data(), n_ops, sl.ops);
+  seq_link_launch(tmp.data(), n_ops);
   MV_CUDA(cudaMemcpyAsync(sl.ops, tmp.data(), sizeof(SeqOp) * n_ops, cudaMemcpyHostToDevice, s));
   seq_launch(s, sl.ops, n_ops, sl.sync, nullptr);
+}
+
+// debug / measurement: a launch of `n_ops` empty ops = the bare cost of an op boundary (tools/seq_barrier_bench.py)
+void seq_debug_empty_ops(cudaStream_t s, int n_ops) {
+  std::vector<SeqOp> ops(n_ops);
+  for (auto& o : ops) seq_plan_layernorm(nullptr, 0, 8, 1e-5f, nullptr, nullptr, nullptr, o);
+  seq_run_host_ops(s, ops.data(), n_ops);
 }
 
 // ---- op-level entry points (C ABI mvldm_op_*; the tests drive the same kernel the forward uses) ----------------

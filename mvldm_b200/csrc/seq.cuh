@@ -47,8 +47,8 @@ struct SeqGN {
   int c0, c1, n_img, hw;
   int cgn, cb;     // channels per group; channels per item block = lcm(cgn, 8): whole groups, whole 16-byte vectors
   int ps, px;      // pixel chunks per image and pixels per chunk (ps > 1: statistics meet across CTAs at a grid barrier)
-  int silu, warp_mode, cache, n_items;
-  uint32_t nv_magic;  // ceil(2^32 / (cb / 8)): vector index -> pixel by multiply-high
+  int silu, gw;    // gw: warps that own one item (1, 2, 4 or 8; 8 / gw items are in flight per CTA)
+  int n_items, pad_;
   float eps;
 };
 
@@ -71,16 +71,14 @@ struct SeqEW {  // upsample / im2col / sinusoid / split-K reduce
   int aux, aux2, aux3, aux4;
 };
 
-struct SeqPrefetch {  // weight tiles of the NEXT GEMM op, pulled into L2 by the (otherwise idle) producer lane of this op
+struct SeqPrefetch {  // weight tiles of the NEXT GEMM op, pulled into L2 by the (by then idle) producer lane of this GEMM op
   const CUtensorMap* map;  // that op's 3-D weight map, box [64 k, bn rows, SEQ_KC chunks]
-  int bn, mt, nt, splits;
-  uint16_t chunk0[SEQ_MAX_SPLITS + 1];  // first 64-wide K chunk of split z; chunk0[splits] = all chunks
-  uint16_t pad_;
+  int bn, nt, nchunks, pad_;  // its N tile, N tiles and 64-wide K chunks
 };
 
 struct alignas(16) SeqOpC {  // the part every thread reads: staged in shared memory at each op boundary
   int type, index;
-  int next_nseg;  // K-segments of the next op if it is a GEMM (its tensor maps are acquired ahead of time), else 0
+  int next_nseg;  // K-segments of the next op of this launch if it is a GEMM (its tensor maps are prefetched one op ahead), else 0
   int pad_;
   union {
     SeqGemm g;
@@ -112,8 +110,11 @@ void seq_plan_layernorm(const bf16* x, int rows, int c, float eps, const float* 
 void seq_plan_upsample(const bf16* x, int n_img, int h, int w, int c, bf16* out, SeqOp& op);
 void seq_plan_im2col(const float* latents, int n_img, int cin, int h, int w, int kpad, bf16* out, SeqOp& op);
 void seq_plan_sinusoid(const int64_t* t, int n, int dim, bf16* out, SeqOp& op);
-// after all ops of a list are planned: op i gets the L2 prefetch plan of the next GEMM op's weights
+// after all ops of a forward are planned: every GEMM op gets the L2 prefetch plan of the next GEMM op's weights (also across
+// launch boundaries: the attention kernel in between leaves them in L2)
 void seq_link_prefetch(SeqOp* ops, int n, const SeqOp* dev_ops);
+// per launch (ops[0..n) run in one sequence launch): tensor-map prefetch hints one op ahead
+void seq_link_launch(SeqOp* ops, int n);
 
 void seq_configure();  // kernel attributes, once per device (call outside stream capture)
 int seq_grid();  // CTAs of every sequence launch (= SM count; all co-resident)
@@ -122,5 +123,7 @@ int seq_grid();  // CTAs of every sequence launch (= SM count; all co-resident)
 void seq_launch(cudaStream_t s, const SeqOp* dev_ops, int n_ops, unsigned* sync, long long* timing);
 // one-off launch of host-built ops (op-level C ABI entry points / tests): uploads to a cached device buffer
 void seq_run_host_ops(cudaStream_t s, const SeqOp* host_ops, int n_ops);
+void seq_debug_empty_ops(cudaStream_t s, int n_ops);
+extern long long* g_seq_trace;  // debug: [barrier][cta][4] timeline buffer for the next launches, or NULL
 
 }  // namespace mvldm

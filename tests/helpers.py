@@ -90,12 +90,12 @@ def run_gemm(impl, segs, n_img, oh, ow, w_packed, bias=None, rowvec=None, residu
 
 
 def geglu_interleave(w: torch.Tensor) -> torch.Tensor:
-    """rows [x(0..4C) | gate(0..4C)] -> 16-row interleave used by the GEGLU epilogue"""
+    """rows [x(0..4C) | gate(0..4C)] -> 8-row interleave used by the GEGLU epilogue"""
     c4 = w.shape[0] // 2
     idx = torch.empty(2 * c4, dtype=torch.long)
     ch = torch.arange(c4)
-    idx[(ch // 16) * 32 + ch % 16] = ch
-    idx[(ch // 16) * 32 + 16 + ch % 16] = c4 + ch
+    idx[(ch // 8) * 16 + ch % 8] = ch
+    idx[(ch // 8) * 16 + 8 + ch % 8] = c4 + ch
     return w[idx]
 
 

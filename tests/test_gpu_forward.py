@@ -65,7 +65,7 @@ def test_forward_v8_golden_graph_and_determinism(gpu_models):
     assert rel_err(y, torch.tensor(g["eps"])) < FWD_TOL
     y1, y2, y3 = graph(inp, ts), graph(inp, ts), eager(inp, ts)
     assert torch.equal(y, y1) and torch.equal(y1, y2) and torch.equal(y, y3)
-    assert graph.last_launch_count() > 100          # our kernels, not a library fallback
+    assert graph.last_launch_count() >= 30          # our kernels (fused sequence launches + attention), not a library fallback
 
 
 def test_timestep_broadcast_and_scene_independence(gpu_models):

@@ -34,6 +34,7 @@ if __name__ == "__main__":
     for _ in range(3):
         m(x, t)
     p = profile_forward(m, x, t)
+    json.dump(p, open(out, "w"))
     tot = sum(c["us"] for c in p["categories"].values())
     print(f"forward V={V}: sum of op times {tot:.1f} us over {sum(c['launches'] for c in p['categories'].values())} ops")
     for k, c in sorted(p["categories"].items(), key=lambda kv: -kv[1]["us"]):
@@ -44,3 +45,8 @@ if __name__ == "__main__":
     for o in ops:
         print(f"    {o['cat']:18s} {o['what']:28s} {o['us']:7.1f} us  {o['gflop']/max(o['us'],1e-9)*1e3:7.1f} TF/s")
     json.dump(p, open(out, "w"))
+    with open(out.replace(".json", "_seq.txt"), "w") as f:      # every op in execution order
+        for o in p["ops"]:
+            f.write(f"{o['cat']:18s} {o['what']:30s} {o['us']:7.2f} us\n")
+        for l in p.get("launches", []):
+            f.write(f"launch {l['kind']:10s} ops={l['ops']:3d} {l['us']:8.2f} us  {l['gflop']:8.2f} GF\n")
