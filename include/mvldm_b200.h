@@ -51,6 +51,9 @@ typedef struct {
   int32_t variant;                              /* 0 = A (DownBlock2D/UpBlock2D), 1 = B (SD-2.1 topology) */
   int32_t t2d_heads[MVLDM_MAX_LEVELS];          /* SD-2.1 attention_head_dim [5,10,20,20] (= heads; head dim 64) */
   int32_t cross_attention_dim;                  /* 1024 */
+  /* Ops on at most this many tokens (B*V*h*w) run inside the fused persistent sequence kernel (grid barriers between ops,
+   * weights prefetched across ops), larger ones as stand-alone kernels; -1 = fuse everything, 0 = nothing. */
+  int32_t fuse_max_tokens;
 } mvldm_config;
 
 const char* mvldm_last_error(void);

@@ -25,6 +25,7 @@ class Config(Structure):
         ("norm_groups", c_int32), ("num_heads", c_int32), ("max_attn_res", c_int32), ("impl", c_int32),
         ("use_cuda_graph", c_int32),
         ("variant", c_int32), ("t2d_heads", c_int32 * MVLDM_MAX_LEVELS), ("cross_attention_dim", c_int32),
+        ("fuse_max_tokens", c_int32),
     ]
 
 

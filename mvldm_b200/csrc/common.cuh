@@ -101,6 +101,18 @@ void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, i
 size_t groupnorm_scratch_floats(int n_img, int groups);
 void layernorm(cudaStream_t s, const bf16* x, int rows, int c, float eps, const float* gamma, const float* beta,
                bf16* out);
+// gemm_tc.cu / norm_classic.cu: the same ops as stand-alone kernels (one launch each); the forward picks per resolution
+size_t gemm_classic_workspace_bytes(const mvldm_gemm_desc& d);
+void gemm_classic(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t workspace_bytes);
+void groupnorm_classic(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, int n_img, int hw, int groups,
+                       float eps, const float* gamma, const float* beta, bool silu, bf16* out, float* scratch);
+size_t groupnorm_classic_scratch_floats(int n_img, int groups);
+void groupnorm_classic_init();  // one-time kernel attributes (call outside stream capture)
+void layernorm_classic(cudaStream_t s, const bf16* x, int rows, int c, float eps, const float* gamma, const float* beta,
+                       bf16* out);
+void upsample_classic(cudaStream_t s, const bf16* x, int n_img, int h, int w, int c, bf16* out);
+void im2col_classic(cudaStream_t s, const float* latents, int n_img, int cin, int h, int w, int kpad, bf16* out);
+void sinusoid_classic(cudaStream_t s, const int64_t* t, int n, int dim, bf16* out);
 // gemm_simt.cu / attn_simt.cu: CUDA-core cross-checks (tests only)
 void gemm_simt(cudaStream_t s, const mvldm_gemm_desc& d);
 void attention_simt(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, int heads, int d, int dpad);

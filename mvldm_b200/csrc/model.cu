@@ -103,14 +103,22 @@ struct OpMeta {  // what an op is, for the per-op timing report
   double flops, bytes;
 };
 struct Step {
-  enum Kind { SEQ, ATTN, ATTN_SHARDED, GEMM_SIMT } kind = SEQ;
+  enum Kind { SEQ, ATTN, ATTN_SHARDED, GEMM_SIMT, GEMM_CLASSIC, GEMM_SINGLE, GN_CLASSIC, LN_CLASSIC, UPSAMPLE_CLASSIC, IM2COL_CLASSIC,
+              SINUSOID_CLASSIC } kind = SEQ;
   int op_begin = 0, op_end = 0;  // SEQ: ops[op_begin, op_end)
   // ATTN / ATTN_SHARDED
   const bf16* qkv = nullptr;
   bf16* out = nullptr;
   int batches = 0, seq = 0, heads = 0, d = 0, dpad = 0, seq_local = 0;
   bool simt = false;
-  mvldm_gemm_desc gemm{};  // GEMM_SIMT
+  mvldm_gemm_desc gemm{};  // GEMM_SIMT / GEMM_CLASSIC
+  // *_CLASSIC elementwise steps
+  const void *x0 = nullptr, *x1 = nullptr;
+  const float *gamma = nullptr, *beta = nullptr;
+  void* dst = nullptr;
+  float* scratch = nullptr;
+  int c0 = 0, c1 = 0, n_img = 0, hw = 0, h = 0, w = 0, groups = 0, silu = 0, aux = 0;
+  float eps = 0.f;
   OpMeta meta{};
 };
 struct Plan {
@@ -120,6 +128,7 @@ struct Plan {
   size_t arena_bytes = 0;
   DevBuf in_latents, in_t, out_eps, splitk;
   std::vector<SeqOp> ops;
+  std::vector<SeqOp> single_ops;  // GEMMs launched one per kernel (descriptor passed by value)
   std::vector<OpMeta> op_meta;
   std::vector<Step> steps;
   std::map<std::string, TapRec> taps;  // named intermediate activations (plans recorded with taps enabled keep them all alive)
@@ -580,11 +589,29 @@ struct mvldm_handle_s {
     rec->steps.push_back(st);
     seq_open = -1;
   }
+  // Which ops run inside the fused sequence kernel: those on at most `fuse_max_tokens` tokens (the small, latency-bound
+  // levels, where an op boundary inside one persistent launch is cheaper than a kernel boundary and the weight stream
+  // continues across ops); larger ones run as stand-alone kernels whose multi-CTA-per-SM elementwise passes are faster.
+  // -1 = everything fused, 0 = nothing.  MVLDM_FUSE_MAX_TOKENS overrides the config (measurement sweeps).
+  bool fuse_op(int64_t tokens) const {
+    static const long env = [] {
+      const char* e = getenv("MVLDM_FUSE_MAX_TOKENS");
+      return e ? atol(e) : -2;
+    }();
+    const long lim = env != -2 ? env : (long)cfg.fuse_max_tokens;
+    return lim < 0 || tokens <= lim;
+  }
+  void push_step(const Step& st) {
+    flush_seq();
+    rec->steps.push_back(st);
+  }
   void run_gemm(mvldm_gemm_desc& d, double algo_flops = -1.0) {
     const double M = (double)d.n_img * d.oh * d.ow;
     const char* cat = d.nseg > 0 && d.seg[0].ntaps == 9 ? "gemm_conv3x3" : "gemm_linear";
+    const bool fused = fuse_op((int64_t)M);
     if (dry) {
-      if (cfg.impl != MVLDM_IMPL_SIMT) splitk_need = std::max(splitk_need, seq_gemm_workspace_bytes(d));
+      if (cfg.impl != MVLDM_IMPL_SIMT)
+        splitk_need = std::max(splitk_need, std::max(seq_gemm_workspace_bytes(d), fused ? (size_t)0 : gemm_classic_workspace_bytes(d)));
       return;
     }
     const std::string what = "M" + std::to_string((long long)M) + " N" + std::to_string(d.n) + " K" + std::to_string(d.k);
@@ -597,6 +624,26 @@ struct mvldm_handle_s {
       st.gemm = d;
       st.meta = OpMeta{cat, what, flops, bytes};
       rec->steps.push_back(st);
+      return;
+    }
+    if (!fused) {
+      Step st;
+      st.kind = Step::GEMM_CLASSIC;
+      st.gemm = d;
+      st.meta = OpMeta{cat, what, flops, bytes};
+      static const bool single = [] {
+        const char* e = getenv("MVLDM_GEMM_KERNEL");
+        return !e || atoi(e) != 0;
+      }();
+      if (single) {  // the sequence kernel's GEMM as its own launch (descriptor in parameter space)
+        SeqOp op, red;
+        if (!seq_plan_gemm(d, splitk_ws, splitk_bytes, op, red)) {  // (a two-pass split-K stays with the stand-alone kernels)
+          st.kind = Step::GEMM_SINGLE;
+          st.op_begin = (int)rec->single_ops.size();
+          rec->single_ops.push_back(op);
+        }
+      }
+      push_step(st);
       return;
     }
     SeqOp op, red;
@@ -620,18 +667,36 @@ struct mvldm_handle_s {
   void gn(const Act& x0, const Act* x1, const float* g, const float* b, float eps, bool silu, const Act& out) {
     float* scratch = new_f32(seq_groupnorm_scratch_floats(x0.n, out.c, cfg.norm_groups));
     if (dry) return;
+    const std::string what = "tokens" + std::to_string(x0.tokens()) + " C" + std::to_string(out.c);
+    if (!fuse_op(x0.tokens())) {
+      Step st;
+      st.kind = Step::GN_CLASSIC;
+      st.x0 = x0.p; st.c0 = x0.c; st.x1 = x1 ? x1->p : nullptr; st.c1 = x1 ? x1->c : 0;
+      st.n_img = x0.n; st.hw = x0.h * x0.w; st.groups = cfg.norm_groups; st.eps = eps; st.gamma = g; st.beta = b;
+      st.silu = silu ? 1 : 0; st.dst = out.p; st.scratch = scratch;
+      st.meta = OpMeta{"groupnorm", what, 0.0, 4.0 * (double)out.tokens() * out.c};
+      push_step(st);
+      return;
+    }
     SeqOp op;
     seq_plan_groupnorm(x0.p, x0.c, x1 ? x1->p : nullptr, x1 ? x1->c : 0, x0.n, x0.h * x0.w, cfg.norm_groups, eps, g, b, silu,
                        out.p, scratch, seq_grid(), op);
-    push_op(op, "groupnorm", "tokens" + std::to_string(x0.tokens()) + " C" + std::to_string(out.c), 0.0,
-            4.0 * (double)out.tokens() * out.c);
+    push_op(op, "groupnorm", what, 0.0, 4.0 * (double)out.tokens() * out.c);
   }
   void ln(const Act& x, const float* g, const float* b, const Act& out) {
     if (dry) return;
+    const std::string what = "tokens" + std::to_string(x.tokens()) + " C" + std::to_string(x.c);
+    if (!fuse_op(x.tokens())) {
+      Step st;
+      st.kind = Step::LN_CLASSIC;
+      st.x0 = x.p; st.n_img = (int)x.tokens(); st.c0 = x.c; st.eps = 1e-5f; st.gamma = g; st.beta = b; st.dst = out.p;
+      st.meta = OpMeta{"layernorm", what, 0.0, 4.0 * (double)x.tokens() * x.c};
+      push_step(st);
+      return;
+    }
     SeqOp op;
     seq_plan_layernorm(x.p, (int)x.tokens(), x.c, 1e-5f, g, b, out.p, op);
-    push_op(op, "layernorm", "tokens" + std::to_string(x.tokens()) + " C" + std::to_string(x.c), 0.0,
-            4.0 * (double)x.tokens() * x.c);
+    push_op(op, "layernorm", what, 0.0, 4.0 * (double)x.tokens() * x.c);
   }
   void attn(const Act& qkv, const Act& out, int batches, int seq, const MvW& m) {
     if (dry) return;
@@ -788,9 +853,17 @@ struct mvldm_handle_s {
     Act e2 = new_act(n, 1, 1, temb_dim);
     float* temb = new_f32((size_t)n * temb_total);
     if (!dry) {
-      SeqOp op;
-      seq_plan_sinusoid(tsteps, n, boc[0], sinus.p, op);
-      push_op(op, "time_embedding", "sinusoid rows" + std::to_string(n), 0.0, 0.0);
+      if (fuse_op(n)) {
+        SeqOp op;
+        seq_plan_sinusoid(tsteps, n, boc[0], sinus.p, op);
+        push_op(op, "time_embedding", "sinusoid rows" + std::to_string(n), 0.0, 0.0);
+      } else {
+        Step st;
+        st.kind = Step::SINUSOID_CLASSIC;
+        st.x0 = tsteps; st.n_img = n; st.c0 = boc[0]; st.dst = sinus.p;
+        st.meta = OpMeta{"time_embedding", "sinusoid rows" + std::to_string(n), 0.0, 0.0};
+        push_step(st);
+      }
     }
     gemm({seg_1x1(sinus)}, time1, e1, nullptr, 0, nullptr, 3);
     gemm({seg_1x1(e1)}, time2, e2, nullptr, 0, nullptr, 3);  // SiLU(emb): every consumer (ResnetBlock2D) applies it first
@@ -807,9 +880,18 @@ struct mvldm_handle_s {
     // ---- conv_in on the im2col'd fp32 input
     Act col = new_act(n, Hh, Ww, kpad_in);
     if (!dry) {
-      SeqOp op;
-      seq_plan_im2col(latents, n, cfg.in_channels, Hh, Ww, kpad_in, col.p, op);
-      push_op(op, "input_im2col", "", 0.0, (double)col.tokens() * (kpad_in * 2 + cfg.in_channels * 4));
+      const double bytes = (double)col.tokens() * (kpad_in * 2 + cfg.in_channels * 4);
+      if (fuse_op(col.tokens())) {
+        SeqOp op;
+        seq_plan_im2col(latents, n, cfg.in_channels, Hh, Ww, kpad_in, col.p, op);
+        push_op(op, "input_im2col", "", 0.0, bytes);
+      } else {
+        Step st;
+        st.kind = Step::IM2COL_CLASSIC;
+        st.x0 = latents; st.n_img = n; st.c0 = cfg.in_channels; st.h = Hh; st.w = Ww; st.aux = kpad_in; st.dst = col.p;
+        st.meta = OpMeta{"input_im2col", "", 0.0, bytes};
+        push_step(st);
+      }
     }
     Act x = new_act(n, Hh, Ww, boc[0]);
     gemm({seg_1x1(col)}, conv_in, x, nullptr, 0, nullptr, 0, 2.0 * (double)x.tokens() * boc[0] * 9 * cfg.in_channels);
@@ -859,9 +941,17 @@ struct mvldm_handle_s {
       if (l != L - 1) {
         Act u = new_act(n, x.h * 2, x.w * 2, x.c);
         if (!dry) {
-          SeqOp op;
-          seq_plan_upsample(x.p, n, x.h, x.w, x.c, u.p, op);
-          push_op(op, "upsample", "", 0.0, 2.5 * (double)u.tokens() * u.c);
+          if (fuse_op(u.tokens())) {
+            SeqOp op;
+            seq_plan_upsample(x.p, n, x.h, x.w, x.c, u.p, op);
+            push_op(op, "upsample", "", 0.0, 2.5 * (double)u.tokens() * u.c);
+          } else {
+            Step st;
+            st.kind = Step::UPSAMPLE_CLASSIC;
+            st.x0 = x.p; st.n_img = n; st.h = x.h; st.w = x.w; st.c0 = x.c; st.dst = u.p;
+            st.meta = OpMeta{"upsample", "", 0.0, 2.5 * (double)u.tokens() * u.c};
+            push_step(st);
+          }
         }
         Act y = new_act(n, u.h, u.w, u.c);
         gemm({seg_conv3x3(u)}, up_conv[l], y);
@@ -910,6 +1000,7 @@ struct mvldm_handle_s {
       plans.erase(victim);
     }
     seq_configure();
+    groupnorm_classic_init();
     std::unique_ptr<Plan> p(new Plan());
     p->scene_views = sv; p->H = H; p->W = W;
     p->last_use = ++use_clock;
@@ -950,6 +1041,7 @@ struct mvldm_handle_s {
     p->dev_ops.alloc(std::max<size_t>(1, p->ops.size()) * sizeof(SeqOp));
     size_t stamps = 0;
     seq_link_prefetch(p->ops.data(), (int)p->ops.size(), reinterpret_cast<const SeqOp*>(p->dev_ops.p));
+    seq_link_prefetch(p->single_ops.data(), (int)p->single_ops.size(), nullptr);
     for (const Step& st : p->steps) {
       if (st.kind != Step::SEQ) continue;
       seq_link_launch(p->ops.data() + st.op_begin, st.op_end - st.op_begin);
@@ -1002,6 +1094,28 @@ struct mvldm_handle_s {
         case Step::GEMM_SIMT:
           gemm_simt(s, st.gemm);
           break;
+        case Step::GEMM_CLASSIC:
+          gemm_classic(s, st.gemm, p.splitk.p, p.splitk.bytes);
+          break;
+        case Step::GEMM_SINGLE:
+          seq_launch_gemm(s, p.single_ops[st.op_begin]);
+          break;
+        case Step::GN_CLASSIC:
+          groupnorm_classic(s, (const bf16*)st.x0, st.c0, (const bf16*)st.x1, st.c1, st.n_img, st.hw, st.groups, st.eps, st.gamma,
+                            st.beta, st.silu != 0, (bf16*)st.dst, st.scratch);
+          break;
+        case Step::LN_CLASSIC:
+          layernorm_classic(s, (const bf16*)st.x0, st.n_img, st.c0, st.eps, st.gamma, st.beta, (bf16*)st.dst);
+          break;
+        case Step::UPSAMPLE_CLASSIC:
+          upsample_classic(s, (const bf16*)st.x0, st.n_img, st.h, st.w, st.c0, (bf16*)st.dst);
+          break;
+        case Step::IM2COL_CLASSIC:
+          im2col_classic(s, (const float*)st.x0, st.n_img, st.c0, st.h, st.w, st.aux, (bf16*)st.dst);
+          break;
+        case Step::SINUSOID_CLASSIC:
+          sinusoid_classic(s, (const int64_t*)st.x0, st.n_img, st.c0, (bf16*)st.dst);
+          break;
       }
       if (events) MV_CUDA(cudaEventRecord((*events)[ev++], s));
     }
@@ -1023,7 +1137,6 @@ struct mvldm_handle_s {
     // the recorded launches read and write fixed buffers, so the list (and its graph) is valid for any caller tensors
     MV_CUDA(cudaMemcpyAsync(p.in_latents.p, latents, in_bytes, cudaMemcpyDeviceToDevice, s));
     MV_CUDA(cudaMemcpyAsync(p.in_t.p, tsteps, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
-    last_launches = p.launches;
     const bool graph = cfg.use_cuda_graph && !taps_enabled && !profiling;
     cudaStreamCaptureStatus cst;
     MV_CUDA(cudaStreamIsCapturing(s, &cst));
@@ -1035,10 +1148,14 @@ struct mvldm_handle_s {
           event_pool.push_back(e);
         }
         MV_CUDA(cudaMemsetAsync(p.timing.p, 0, p.timing.bytes, s));
+        g_launch_count = 0;
         execute(p, s, &event_pool);
+        p.launches = g_launch_count;
         prof_plan = &p;
       } else {
+        g_launch_count = 0;
         execute(p, s, nullptr);
+        p.launches = g_launch_count;
       }
     } else {
       if (!p.graph) {
@@ -1046,7 +1163,9 @@ struct mvldm_handle_s {
         if (!capture_stream) MV_CUDA(cudaStreamCreateWithFlags(&capture_stream, cudaStreamNonBlocking));
         MV_CUDA(cudaStreamBeginCapture(capture_stream, cudaStreamCaptureModeThreadLocal));
         try {
+          g_launch_count = 0;
           execute(p, capture_stream, nullptr);
+          p.launches = g_launch_count;
         } catch (...) {
           cudaStreamEndCapture(capture_stream, &g);
           if (g) cudaGraphDestroy(g);
@@ -1059,6 +1178,7 @@ struct mvldm_handle_s {
       }
       MV_CUDA(cudaGraphLaunch(p.graph, s));
     }
+    last_launches = p.launches;
     MV_CUDA(cudaMemcpyAsync(out, p.out_eps.p, out_bytes, cudaMemcpyDeviceToDevice, s));
   }
 };
@@ -1115,7 +1235,7 @@ static const char* profile_report(mvldm_handle_s* h) {
     }
     char buf[200];
     snprintf(buf, sizeof buf, "%s{\"kind\":\"%s\",\"ops\":%d,\"us\":%.2f,\"gflop\":%.3f}", first_launch ? "" : ",",
-             st.kind == Step::SEQ ? "seq" : (st.kind == Step::GEMM_SIMT ? "gemm_simt" : "attention"),
+             st.kind == Step::SEQ ? "seq" : (st.kind == Step::ATTN || st.kind == Step::ATTN_SHARDED ? "attention" : "kernel"),
              st.kind == Step::SEQ ? st.op_end - st.op_begin : 1, us, gflop);
     launches += buf;
     first_launch = false;
@@ -1292,7 +1412,9 @@ int mvldm_forward_sharded(mvldm_handle h, void* stream, const float* latents, co
   MV_CUDA(cudaMemcpyAsync(p.in_latents.p, latents, (size_t)V_local * h->cfg.in_channels * H * W * sizeof(float),
                           cudaMemcpyDeviceToDevice, s));
   MV_CUDA(cudaMemcpyAsync(p.in_t.p, timesteps, (size_t)V_local * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+  g_launch_count = 0;
   h->execute(p, s, nullptr);  // eager: the exchange callback re-enters the host
+  p.launches = g_launch_count;
   MV_CUDA(cudaMemcpyAsync(out, p.out_eps.p, (size_t)V_local * h->cfg.out_channels * H * W * sizeof(float),
                           cudaMemcpyDeviceToDevice, s));
   h->last_launches = p.launches;

@@ -176,51 +176,56 @@ __device__ __forceinline__ void stamp(long long* timing, unsigned k) {
 // polls with acquire semantics, the CTA barrier on either side extends that to the whole CTA (the cooperative-groups
 // grid.sync construction).  While thread 0 polls, warp 1 stages the next op's descriptor in shared memory.
 // Measured (tools/seq_barrier_bench.py, tools/seq_trace.py): ~1 us from the last CTA's arrival to the release.
-struct GridBarrier {
+// All arguments by value (registers): a struct passed by reference would live in local memory, which is L2 here.
+// Returns the new barrier count.
+__device__ __noinline__ unsigned grid_sync(unsigned* ctr, unsigned n, int flags, long long* timing, long long* trace, int op,
+                                           const SeqOp* next, uint8_t* desc_smem) {
+  long long* tr = trace && threadIdx.x == 0 ? trace + ((size_t)n * gridDim.x + blockIdx.x) * 16 : nullptr;
+  if (tr) tr[0] = globaltimer_ns();
+  if (flags & SEQ_F_PROXY_FENCE) asm volatile("fence.proxy.async.global;" ::: "memory");
+  __syncthreads();
+  if (tr) tr[1] = globaltimer_ns();
+  ++n;
+  if (threadIdx.x == 0) {
+    // cumulative gpu-scope fence: publishes the global writes of the whole CTA (ordered before it by the CTA barrier)
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+  }
+  if (next != nullptr && threadIdx.x >= 32 && threadIdx.x < 32 + SEQ_OPC_BYTES / 16)
+    reinterpret_cast<uint4*>(desc_smem)[threadIdx.x - 32] = __ldg(reinterpret_cast<const uint4*>(next) + (threadIdx.x - 32));
+  if (threadIdx.x == 0) {
+    const unsigned target = n * gridDim.x;
+    unsigned spins = 0;
+    while (ld_acquire_u32(ctr) < target) {
+      if (++spins > (1u << 25)) __trap();  // a protocol bug / lost co-residency traps instead of hanging the GPU
+    }
+    if (timing != nullptr && blockIdx.x == 0) stamp(timing, n);
+    if (tr) {
+      tr[2] = globaltimer_ns();
+      tr[3] = op;
+      tr[5] = spins;
+    }
+  }
+  __syncthreads();
+  if (flags & SEQ_F_PROXY_FENCE) asm volatile("fence.proxy.async.global;" ::: "memory");
+  return n;
+}
+
+struct GridBarrier {  // the barrier words of a launch, carried by value
   unsigned* ctr;
   unsigned n;  // barriers passed
   long long* timing;
   int flags;
-  long long* trace;  // debug: [barrier][cta][16] globaltimer stamps (tools/seq_trace.py)
+  long long* trace;  // debug: [barrier][cta][16] stamps (tools/seq_trace.py)
   int op;
-  __device__ __noinline__ void sync(const SeqOp* next, uint8_t* desc_smem) {
-    long long* tr = trace && threadIdx.x == 0 ? trace + ((size_t)n * gridDim.x + blockIdx.x) * 16 : nullptr;
-    if (tr) tr[0] = globaltimer_ns();
-    if (flags & SEQ_F_PROXY_FENCE) asm volatile("fence.proxy.async.global;" ::: "memory");
-    __syncthreads();
-    if (tr) tr[1] = globaltimer_ns();
-    ++n;
-    if (threadIdx.x == 0) {
-      // cumulative gpu-scope fence: publishes the global writes of the whole CTA (ordered before it by the CTA barrier)
-      asm volatile("fence.acq_rel.gpu;" ::: "memory");
-      asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-    }
-    if (next != nullptr && threadIdx.x >= 32 && threadIdx.x < 32 + SEQ_OPC_BYTES / 16)
-      reinterpret_cast<uint4*>(desc_smem)[threadIdx.x - 32] = __ldg(reinterpret_cast<const uint4*>(next) + (threadIdx.x - 32));
-    if (threadIdx.x == 0) {
-      const unsigned target = n * gridDim.x;
-      unsigned spins = 0;
-      while (ld_acquire_u32(ctr) < target) {
-        if (++spins > (1u << 25)) __trap();  // a protocol bug / lost co-residency traps instead of hanging the GPU
-      }
-      if (timing != nullptr && blockIdx.x == 0) stamp(timing, n);
-      if (tr) {
-        tr[2] = globaltimer_ns();
-        tr[3] = op;
-        tr[5] = spins;
-      }
-    }
-    __syncthreads();
-    if (flags & SEQ_F_PROXY_FENCE) asm volatile("fence.proxy.async.global;" ::: "memory");
-  }
 };
 
 // role state that survives from op to op: mbarrier phase parities per ring slot, accumulator-buffer counter
 struct RoleState {
   uint32_t empty_par;  // producer: parity to wait for on bar_empty[s] before refilling slot s
   uint32_t full_par;   // MMA issuer: parity to wait for on bar_full[s]
-  uint32_t acc_n;      // MMA issuer / epilogue: accumulator hand-offs so far (buffer = acc_n & 1, phase = (acc_n >> 1) & 1)
-  long long* tr;       // debug timeline row of the barrier that will close this op (slots 8..15), or NULL
+  long long* tr;       // debug timeline row of the barrier that will close this op (slots 4..15: clock64 since t0), or NULL
+  long long t0;        // clock64 when this op started (debug)
 };
 
 // descriptor-cache prefetch of every tensor map op `o` uses (a cold map costs the first TMA ~2 us: the 128-byte
@@ -284,6 +289,12 @@ __device__ __noinline__ void gemm_producer(const SeqGemm& g, const SeqOp* opg, u
   const uint32_t ring_base = smem_base + AUX_BYTES;
   const uint32_t bar_full = smem_base + OFF_BAR_FULL, bar_empty = smem_base + OFF_BAR_EMPTY;
   const int num_work = g.mt * g.nt * g.splits;
+  // role state and debug pointers live in registers inside this function: `st` sits in local memory (= L2, the L1 is
+  // carved out for shared memory) and every asm with a memory clobber would force a reload
+  uint32_t empty_par = st.empty_par;
+  long long* const tr = st.tr;
+  const long long t0 = st.t0;
+  const int stages = g.stages;
   int ring = 0;
 #pragma unroll 1
   for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
@@ -299,23 +310,24 @@ __device__ __noinline__ void gemm_producer(const SeqGemm& g, const SeqOp* opg, u
     for (int i = 0; i < nst; ++i) {
       const SeqSeg& sg = g.seg[k.s];
       const int kc = k.chunks(g);
-      tc::mbar_wait(bar_empty + 8 * ring, (st.empty_par >> ring) & 1u);
-      st.empty_par ^= 1u << ring;
+      tc::mbar_wait(bar_empty + 8 * ring, (empty_par >> ring) & 1u);
+      empty_par ^= 1u << ring;
       const uint32_t full = bar_full + 8 * ring;
       tc::mbar_expect_tx(full, kc * (A_BYTES + b_bytes));
       const uint32_t sa = ring_base + ring * stage_bytes;
       tc::tma_load_5d(sa, &opg->tmA[k.s][kc - 1], full, 0, sg.dw[k.t], y0 * sg.stride + sg.dh[k.t], img0, sg.cblk[k.t] + k.cb);
       tc::tma_load_3d(sa + KC * A_BYTES, &opg->tmB[kc - 1], full, 0, n0, sg.kchunk0 + k.t * sg.ncblk + k.cb);
-      if (st.tr && i == 0 && w == (int)blockIdx.x) st.tr[6] = globaltimer_ns();  // first loads issued
-      ring = ring + 1 == g.stages ? 0 : ring + 1;
+      if (tr && i == 0 && w == (int)blockIdx.x) tr[6] = clock64() - t0;  // first loads issued
+      ring = ring + 1 == stages ? 0 : ring + 1;
       k.next(g, kc);
     }
   }
+  st.empty_par = empty_par;
 }
 
 // the whole warp runs the warp-uniform loop and the barrier waits; one elected lane issues tcgen05.mma / commit,
 // which lets ptxas emit the UTCHMMAs back to back instead of one ELECT/branch loop per instruction
-__device__ __noinline__ void gemm_mma(const SeqGemm& g, uint32_t smem_base, uint32_t tmem_base, RoleState& st) {
+__device__ __noinline__ void gemm_mma(const SeqGemm& g, uint32_t smem_base, uint32_t tmem_base, RoleState& st, uint32_t acc_n) {
   const int BN = g.bn;
   const uint32_t b_bytes = (uint32_t)BN * 128u;
   const uint32_t stage_bytes = KC * (A_BYTES + b_bytes);
@@ -324,6 +336,10 @@ __device__ __noinline__ void gemm_mma(const SeqGemm& g, uint32_t smem_base, uint
   const uint32_t bar_acc_full = smem_base + OFF_ACC_FULL, bar_acc_empty = smem_base + OFF_ACC_EMPTY;
   const int num_work = g.mt * g.nt * g.splits;
   const uint32_t idesc = tc::umma_idesc_bf16(BM, BN, false, false);
+  uint32_t full_par = st.full_par;  // registers, see gemm_producer
+  long long* const tr = st.tr;
+  const long long t0 = st.t0;
+  const int stages = g.stages;
   int ring = 0;
 #pragma unroll 1
   for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
@@ -332,17 +348,17 @@ __device__ __noinline__ void gemm_mma(const SeqGemm& g, uint32_t smem_base, uint
     const int nst = min(g.num_steps - st_begin, g.steps_per_split);
     KWalk k;  // same walk as the producer, to know how many chunks each step carries
     k.start(g, st_begin);
-    const uint32_t ab = st.acc_n & 1u;
-    tc::mbar_wait(bar_acc_empty + 8 * ab, ((st.acc_n >> 1) & 1u) ^ 1u);  // epilogue has drained this buffer
+    const uint32_t ab = acc_n & 1u;
+    tc::mbar_wait(bar_acc_empty + 8 * ab, ((acc_n >> 1) & 1u) ^ 1u);  // epilogue has drained this buffer
     tc::tc_fence_after();
     const uint32_t tmem_d = tmem_base + ab * ACC_COLS;
 #pragma unroll 1
     for (int i = 0; i < nst; ++i) {
       const int kc = k.chunks(g);
-      tc::mbar_wait(bar_full + 8 * ring, (st.full_par >> ring) & 1u);
-      st.full_par ^= 1u << ring;
+      tc::mbar_wait(bar_full + 8 * ring, (full_par >> ring) & 1u);
+      full_par ^= 1u << ring;
       tc::tc_fence_after();
-      if (st.tr && i == 0 && w == (int)blockIdx.x && (threadIdx.x & 31) == 0) st.tr[7] = globaltimer_ns();  // first tile landed
+      if (tr && i == 0 && w == (int)blockIdx.x && (threadIdx.x & 31) == 0) tr[7] = clock64() - t0;  // first tile landed
       const uint32_t sa = ring_base + ring * stage_bytes;
       if (tc::elect_one()) {
 #pragma unroll 1
@@ -356,90 +372,121 @@ __device__ __noinline__ void gemm_mma(const SeqGemm& g, uint32_t smem_base, uint
         tc::umma_commit(bar_empty + 8 * ring);  // frees the smem slot when these MMAs retire
       }
       __syncwarp();
-      ring = ring + 1 == g.stages ? 0 : ring + 1;
+      ring = ring + 1 == stages ? 0 : ring + 1;
       k.next(g, kc);
     }
     if (tc::elect_one()) tc::umma_commit(bar_acc_full + 8 * ab);
     __syncwarp();
-    ++st.acc_n;
+    ++acc_n;
   }
+  st.full_par = full_par;
 }
 
 // epilogue warps 2..5: each thread owns one accumulator row (TMEM lane).  32 columns per rolled iteration; the TMEM load of
 // chunk c+1 is issued as soon as chunk c has been moved out of the load registers (bias add), so the ~0.25 us TMEM
 // round trip overlaps the conversion / stores of the previous chunk (serialised it made a 160-wide tile take 3 us).
 __device__ __noinline__ void gemm_epilogue(const SeqGemm& g, uint8_t* smem, uint32_t smem_base, uint32_t tmem_base,
-                                           RoleState& st) {
+                                           RoleState& st, uint32_t acc_n) {
+  long long* const tr = st.tr;
+  const long long t0 = st.t0;
+  // hot descriptor fields in registers too (the asm memory clobbers would re-read them from shared memory)
+  const int gM = g.M, gN = g.N, ghw = g.hw, gldo = g.ldo, gsplits = g.splits;
+  float* const gpartial = g.partial;
+  int* const gcounters = g.counters;
+  const float* const gbias = g.bias;
+  const float* const growvec = g.rowvec;
+  void* const gout = g.out;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int BN = g.bn;
   const uint32_t stage_bytes = KC * (A_BYTES + (uint32_t)BN * 128u);
   const uint32_t bar_acc_full = smem_base + OFF_ACC_FULL, bar_acc_empty = smem_base + OFF_ACC_EMPTY;
-  const int num_work = g.mt * g.nt * g.splits;
+  const int num_work = g.mt * g.nt * gsplits;
   const int q = warp & 3;  // TMEM lane quarter this warp may access
   const int row = q * 32 + lane;
-  const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
+  // solo (at most one work item per CTA in this op): the producer and MMA warps are done by the time the accumulator is
+  // ready, so all 8 warps run the epilogue - two per TMEM lane quarter, alternating 32-column chunks.  One warp per
+  // scheduler issues an instruction every ~2.7 cycles (measured), which is what bounds this code.
+  const bool solo = g.solo != 0;
+  const int NE = solo ? SEQ_THREADS : 128;            // epilogue threads
+  const int et = solo ? (int)threadIdx.x : (int)threadIdx.x - 64;
+  const int nh = solo ? 2 : 1, h = solo ? warp >> 2 : 0;  // warps per quarter, this warp's index among them
   float* colvec = reinterpret_cast<float*>(smem + AUX_BYTES + g.stages * stage_bytes);  // [image in tile][BN]
   const int mode = g.mode;
-  const int imgs_in_tile = (BM + g.hw - 1) / g.hw;
-  const bool table = (g.bias || g.rowvec) && imgs_in_tile <= CV_IMGS;  // else (sub-4x4 maps): bias / rowvec straight from L2
+  const int imgs_in_tile = (BM + ghw - 1) / ghw;
+  const bool table = (gbias || growvec) && imgs_in_tile <= CV_IMGS;  // else (sub-4x4 maps): bias / rowvec straight from L2
+  // One item per CTA: once the accumulator is ready the shared-memory ring is idle, so the bf16 tile is assembled there
+  // (row per thread, 16-byte padded pitch: conflict-free) and leaves as whole 128-byte lines.  A row-per-thread global
+  // store touches 32 different lines per instruction, which made the stores of a 128 x 160 tile take ~2 us.
+  const bool staged = g.stage_out != 0 && gpartial == nullptr;
+  const int out_cols = mode == 1 ? BN / 2 : BN;
+  const int TP = out_cols + 8;
+  bf16* tile = reinterpret_cast<bf16*>(smem + AUX_BYTES);
 #pragma unroll 1
   for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
     const int mtile = w % g.mt, ntile = (w / g.mt) % g.nt, z = w / (g.mt * g.nt);
     const int m0 = mtile * BM, n0 = ntile * BN;
-    const uint32_t ab = st.acc_n & 1u;
+    const uint32_t ab = acc_n & 1u;
     const uint32_t trow = tmem_base + ab * ACC_COLS + ((uint32_t)(q * 32) << 16);
     const int m = m0 + row;
-    const bool ok = m < g.M;
-    const int img = m / g.hw, img0 = m0 / g.hw;
-    // ---- while the main loop of this item runs: stage everything the epilogue needs that is not the accumulator
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // previous item's readers of the table are done
-    if (table) {  // bias[n] + rowvec[image, n] for the images of this tile
+    const bool ok = m < gM;
+    const int img = m / ghw, img0 = m0 / ghw;
+    // ---- while the main loop of this item runs: warps 2..5 stage everything the epilogue needs that is not the accumulator
+    const bool use_res = !gpartial && mode == 0 && g.residual != nullptr;
+    const int e4 = (int)threadIdx.x - 64;  // 0..127 among the four staging warps
+    if (warp >= 2 && warp < 6) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous item's readers of the table are done
+      if (table) {  // bias[n] + rowvec[image, n] for the images of this tile
 #pragma unroll 1
-      for (int i = et; i < imgs_in_tile * BN; i += 128) {
-        const int b = i / BN, c = i - b * BN;
-        float v = g.bias ? g.bias[n0 + c] : 0.f;
-        if (g.rowvec && (int64_t)(img0 + b) * g.hw < g.M) v += __ldcg(g.rowvec + (int64_t)(img0 + b) * g.rowvec_ld + n0 + c);
-        colvec[b * BN + c] = v;
+        for (int i = e4; i < imgs_in_tile * BN; i += 128) {
+          const int b = i / BN, c = i - b * BN;
+          float v = gbias ? gbias[n0 + c] : 0.f;
+          if (growvec && (int64_t)(img0 + b) * ghw < gM) v += __ldcg(growvec + (int64_t)(img0 + b) * g.rowvec_ld + n0 + c);
+          colvec[b * BN + c] = v;
+        }
       }
-    }
-    // residual row (bf16): all loads in flight now, parked as packed pairs in the spare TMEM columns [BN, BN + BN/2) of this
-    // accumulator buffer (the MMAs write [0, BN)); the rolled chunk loop below reads them back with a dynamic TMEM address
-    const bool use_res = !g.partial && mode == 0 && g.residual != nullptr;
-    if (use_res) {
-      const uint4* rr = reinterpret_cast<const uint4*>(g.residual + (int64_t)min(m, g.M - 1) * g.res_ld + n0);
-      uint4 rv[20];
+      // residual row (bf16): all loads in flight now, parked as packed pairs in the spare TMEM columns [BN, BN + BN/2) of
+      // this accumulator buffer (the MMAs write [0, BN)); the rolled chunk loop reads them back with a dynamic TMEM address
+      if (use_res) {
+        const uint4* rr = reinterpret_cast<const uint4*>(g.residual + (int64_t)min(m, gM - 1) * g.res_ld + n0);
+        uint4 rv[20];
 #pragma unroll
-      for (int c = 0; c < 20; ++c)
-        if (c * 8 < BN) rv[c] = __ldcg(rr + c);
+        for (int c = 0; c < 20; ++c)
+          if (c * 8 < BN) rv[c] = __ldcg(rr + c);
 #pragma unroll
-      for (int c = 0; c < 10; ++c)
-        if (c * 16 < BN) tmem_st8(trow + BN + c * 8, rv[2 * c], rv[2 * c + 1]);
-      tc::tmem_st_wait();
+        for (int c = 0; c < 10; ++c)
+          if (c * 16 < BN) tmem_st8(trow + BN + c * 8, rv[2 * c], rv[2 * c + 1]);
+        tc::tmem_st_wait();
+        tc::tc_fence_before();  // solo: the other warp of this quarter reads half of these columns back
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (solo) asm volatile("bar.sync 2, %0;" ::"n"(SEQ_THREADS) : "memory");  // all hands: producer / MMA warps have finished their loops
     const float* cvrow = colvec + (table ? img - img0 : 0) * BN;
-    if (st.tr && et == 0) st.tr[8] = globaltimer_ns();  // staged, waiting for the accumulator
-    tc::mbar_wait(bar_acc_full + 8 * ab, (st.acc_n >> 1) & 1u);
+    if (tr && et == 0) tr[8] = clock64() - t0;  // staged, waiting for the accumulator
+    tc::mbar_wait(bar_acc_full + 8 * ab, (acc_n >> 1) & 1u);
     tc::tc_fence_after();
-    if (st.tr && et == 0) st.tr[9] = globaltimer_ns();  // accumulator ready
+    if (tr && et == 0) tr[9] = clock64() - t0;  // accumulator ready
     uint32_t r[32], rs[16];
-    tc::tmem_ld32(trow, r);
-    if (use_res) tc::tmem_ld16(trow + BN, rs);
+    const int cstep = 32 * nh;
+    if (h * 32 < BN) {
+      tc::tmem_ld32(trow + h * 32, r);
+      if (use_res) tc::tmem_ld16(trow + BN + h * 16, rs);
+    }
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = h * 32; c0 < BN; c0 += cstep) {
       const int n = n0 + c0;
-      const bool more = c0 + 32 < BN;
+      const bool more = c0 + cstep < BN;
       tc::tmem_ld_wait();
-      if (g.partial) {  // split-K: raw fp32 partial, reduced (+ epilogue) below or by the SEQ_SPLITK_REDUCE op
+      if (gpartial) {  // split-K: raw fp32 partial, reduced (+ epilogue) below or by the SEQ_SPLITK_REDUCE op
         if (ok) {
-          float* pp = g.partial + ((int64_t)z * g.M + m) * g.N + n;
+          float* pp = gpartial + ((int64_t)z * gM + m) * gN + n;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             st_global_v8(pp + 8 * j, r[8 * j], r[8 * j + 1], r[8 * j + 2], r[8 * j + 3], r[8 * j + 4], r[8 * j + 5], r[8 * j + 6],
                          r[8 * j + 7]);
         }
-        if (more) tc::tmem_ld32(trow + c0 + 32, r);
-        if (st.tr && et == 0 && c0 == 0) st.tr[13] = globaltimer_ns();  // first chunk done
+        if (more) tc::tmem_ld32(trow + c0 + cstep, r);
+        if (tr && et == 0 && c0 == 0) tr[13] = clock64() - t0;  // first chunk done
         continue;
       }
       float v[32];
@@ -460,20 +507,20 @@ __device__ __noinline__ void gemm_epilogue(const SeqGemm& g, uint8_t* smem, uint
         for (int e = 0; e < 16; ++e) rq[e] = rs[e];
       }
       if (more) {  // the load registers are free again: next chunk in flight while this one is converted and stored
-        tc::tmem_ld32(trow + c0 + 32, r);
-        if (use_res) tc::tmem_ld16(trow + BN + ((c0 + 32) >> 1), rs);
+        tc::tmem_ld32(trow + c0 + cstep, r);
+        if (use_res) tc::tmem_ld16(trow + BN + ((c0 + cstep) >> 1), rs);
       }
-      if (st.tr && et == 0 && c0 == 0) st.tr[13] = globaltimer_ns();  // first chunk out of the load registers
+      if (tr && et == 0 && c0 == 0) tr[13] = clock64() - t0;  // first chunk out of the load registers
       if (!ok) continue;
-      if (!table && (g.bias || g.rowvec)) {  // rare: more than CV_IMGS images per tile (maps smaller than 4x4)
+      if (!table && (gbias || growvec)) {  // rare: more than CV_IMGS images per tile (maps smaller than 4x4)
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          if (g.bias) {
-            const float4 b = *reinterpret_cast<const float4*>(g.bias + n + j);
+          if (gbias) {
+            const float4 b = *reinterpret_cast<const float4*>(gbias + n + j);
             v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
           }
-          if (g.rowvec) {
-            const float4 b = __ldcg(reinterpret_cast<const float4*>(g.rowvec + (int64_t)img * g.rowvec_ld + n + j));
+          if (growvec) {
+            const float4 b = __ldcg(reinterpret_cast<const float4*>(growvec + (int64_t)img * g.rowvec_ld + n + j));
             v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
           }
         }
@@ -485,22 +532,28 @@ __device__ __noinline__ void gemm_epilogue(const SeqGemm& g, uint8_t* smem, uint
         for (int i = 0; i < 2; ++i)
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[8 * i + j] = v[16 * i + j] * gelu_exact(v[16 * i + 8 + j]);
-        st_global_v8(reinterpret_cast<bf16*>(g.out) + (int64_t)m * g.ldo + (n >> 1), pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]),
-                     pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]), pack_bf16(o[8], o[9]), pack_bf16(o[10], o[11]),
-                     pack_bf16(o[12], o[13]), pack_bf16(o[14], o[15]));
+        if (staged) {
+          uint4* tp = reinterpret_cast<uint4*>(tile + row * TP + (c0 >> 1));
+          tp[0] = pack8(o);
+          tp[1] = pack8(o + 8);
+        } else {
+          st_global_v8(reinterpret_cast<bf16*>(gout) + (int64_t)m * gldo + (n >> 1), pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]),
+                       pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]), pack_bf16(o[8], o[9]), pack_bf16(o[10], o[11]),
+                       pack_bf16(o[12], o[13]), pack_bf16(o[14], o[15]));
+        }
       } else if (mode == 4) {
-        float* op = reinterpret_cast<float*>(g.out) + (int64_t)m * g.ldo + n;
+        float* op = reinterpret_cast<float*>(gout) + (int64_t)m * gldo + n;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           st_global_v8(op + 8 * j, __float_as_uint(v[8 * j]), __float_as_uint(v[8 * j + 1]), __float_as_uint(v[8 * j + 2]),
                        __float_as_uint(v[8 * j + 3]), __float_as_uint(v[8 * j + 4]), __float_as_uint(v[8 * j + 5]),
                        __float_as_uint(v[8 * j + 6]), __float_as_uint(v[8 * j + 7]));
       } else if (mode == 2) {  // fp32 NCHW head
-        const int pix = m - img * g.hw;
-        float* op = reinterpret_cast<float*>(g.out) + (int64_t)img * g.n_valid * g.hw + pix;
+        const int pix = m - img * ghw;
+        float* op = reinterpret_cast<float*>(gout) + (int64_t)img * g.n_valid * ghw + pix;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (n + j < g.n_valid) op[(int64_t)(n + j) * g.hw] = v[j];
+          if (n + j < g.n_valid) op[(int64_t)(n + j) * ghw] = v[j];
       } else {  // 0: bf16 (+ residual); 3: SiLU then bf16
         if (use_res) {
 #pragma unroll
@@ -514,58 +567,76 @@ __device__ __noinline__ void gemm_epilogue(const SeqGemm& g, uint8_t* smem, uint
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
         }
-        bf16* op = reinterpret_cast<bf16*>(g.out) + (int64_t)m * g.ldo + n;
+        if (staged) {
+          uint4* tp = reinterpret_cast<uint4*>(tile + row * TP + c0);
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-          st_global_v8(op + 16 * j, pack_bf16(v[j * 16], v[j * 16 + 1]), pack_bf16(v[j * 16 + 2], v[j * 16 + 3]),
-                       pack_bf16(v[j * 16 + 4], v[j * 16 + 5]), pack_bf16(v[j * 16 + 6], v[j * 16 + 7]),
-                       pack_bf16(v[j * 16 + 8], v[j * 16 + 9]), pack_bf16(v[j * 16 + 10], v[j * 16 + 11]),
-                       pack_bf16(v[j * 16 + 12], v[j * 16 + 13]), pack_bf16(v[j * 16 + 14], v[j * 16 + 15]));
+          for (int j = 0; j < 4; ++j) tp[j] = pack8(v + 8 * j);
+        } else {
+          bf16* op = reinterpret_cast<bf16*>(gout) + (int64_t)m * gldo + n;
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            st_global_v8(op + 16 * j, pack_bf16(v[j * 16], v[j * 16 + 1]), pack_bf16(v[j * 16 + 2], v[j * 16 + 3]),
+                         pack_bf16(v[j * 16 + 4], v[j * 16 + 5]), pack_bf16(v[j * 16 + 6], v[j * 16 + 7]),
+                         pack_bf16(v[j * 16 + 8], v[j * 16 + 9]), pack_bf16(v[j * 16 + 10], v[j * 16 + 11]),
+                         pack_bf16(v[j * 16 + 12], v[j * 16 + 13]), pack_bf16(v[j * 16 + 14], v[j * 16 + 15]));
+        }
+      }
+    }
+    if (staged) {  // the assembled tile -> global, consecutive threads on consecutive 16-byte pieces of a row
+      asm volatile("bar.sync 3, %0;" ::"r"(NE) : "memory");
+      if (tr && et == 0 && !gcounters) tr[15] = clock64() - t0;
+      const int PV = out_cols / 8;
+      const int rows_valid = min(BM, gM - m0);
+      bf16* obase = reinterpret_cast<bf16*>(gout) + (int64_t)m0 * gldo + (mode == 1 ? n0 / 2 : n0);
+#pragma unroll 2
+      for (int i = et; i < rows_valid * PV; i += NE) {
+        const int rr = i / PV, c8 = i - rr * PV;
+        *reinterpret_cast<uint4*>(obase + (int64_t)rr * gldo + c8 * 8) = *reinterpret_cast<const uint4*>(tile + rr * TP + c8 * 8);
       }
     }
     tc::tc_fence_before();
-    tc::mbar_arrive(bar_acc_empty + 8 * ab);  // this thread is done reading the accumulator buffer
-    ++st.acc_n;
-    if (st.tr && et == 0) st.tr[10] = globaltimer_ns();  // epilogue stores issued
-    if (g.counters) {
+    if (warp >= 2 && warp < 6) tc::mbar_arrive(bar_acc_empty + 8 * ab);  // this thread is done reading the accumulator buffer
+    ++acc_n;
+    if (tr && et == 0) tr[10] = clock64() - t0;  // epilogue stores issued
+    if (gcounters) {
       // ---- split-K reduction fused into the op: all splits of a tile are co-resident (one work item per CTA), so they
       // meet at a global counter; each then reduces 1/splits of the tile's rows in fixed z order (bit-stable) and applies
       // the epilogue.  The slices of all splits are pulled into the (by now idle) shared-memory ring with cp.async, i.e.
       // every 16-byte piece is in flight at once: one L2 round trip instead of one per split.
       const int tile = mtile + ntile * g.mt;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 3, %0;" ::"r"(NE) : "memory");
       if (et == 0) {  // one cumulative fence publishes the 128 threads' partial rows; acquire on the way out
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
-        atomicAdd(&g.counters[tile], 1);
+        atomicAdd(&gcounters[tile], 1);
         uint32_t spins = 0;
-        while (ld_acquire_u32(reinterpret_cast<const unsigned*>(&g.counters[tile])) < (unsigned)g.splits) {
+        while (ld_acquire_u32(reinterpret_cast<const unsigned*>(&gcounters[tile])) < (unsigned)gsplits) {
           if (++spins > (1u << 25)) __trap();
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (st.tr && et == 0) st.tr[11] = globaltimer_ns();  // all splits arrived
-      const int rows_per = (BM + g.splits - 1) / g.splits;
-      const int r0 = z * rows_per, r1 = min(min(BM, r0 + rows_per), g.M - m0);
+      asm volatile("bar.sync 3, %0;" ::"r"(NE) : "memory");
+      if (tr && et == 0) tr[11] = clock64() - t0;  // all splits arrived
+      const int rows_per = (BM + gsplits - 1) / gsplits;
+      const int r0 = z * rows_per, r1 = min(min(BM, r0 + rows_per), gM - m0);
       const int NV4 = BN / 4;                       // 16-byte pieces per row
       const int per_split = max(r1 - r0, 0) * NV4;  // pieces of one split's slice
       float4* stage = reinterpret_cast<float4*>(smem + AUX_BYTES);  // [split][row][BN] fp32
-      const int64_t zstride = (int64_t)g.M * g.N;
-      const float* pbase = g.partial + (int64_t)(m0 + r0) * g.N + n0;
+      const int64_t zstride = (int64_t)gM * gN;
+      const float* pbase = gpartial + (int64_t)(m0 + r0) * gN + n0;
 #pragma unroll 1
-      for (int i = et; i < per_split; i += 128) {  // this thread's 16-byte piece of the slice, from every split
+      for (int i = et; i < per_split; i += NE) {  // this thread's 16-byte piece of the slice, from every split
         const int rr = i / NV4, c4 = i - rr * NV4;
-        const float* src = pbase + (int64_t)rr * g.N + c4 * 4;
+        const float* src = pbase + (int64_t)rr * gN + c4 * 4;
         float4* dst = stage + i;
 #pragma unroll 4
-        for (int zz = 0; zz < g.splits; ++zz) cp_async16(dst + zz * per_split, src + zz * zstride);
+        for (int zz = 0; zz < gsplits; ++zz) cp_async16(dst + zz * per_split, src + zz * zstride);
       }
-      if (st.tr && et == 0) st.tr[14] = globaltimer_ns();  // slice copies issued
+      if (tr && et == 0) tr[14] = clock64() - t0;  // slice copies issued
       cp_async_wait_all();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (st.tr && et == 0) st.tr[15] = globaltimer_ns();  // slices in shared memory
+      asm volatile("bar.sync 3, %0;" ::"r"(NE) : "memory");
+      if (tr && et == 0) tr[15] = clock64() - t0;  // slices in shared memory
       const int NV = BN / 8;
 #pragma unroll 1
-      for (int i = et; i < max(r1 - r0, 0) * NV; i += 128) {
+      for (int i = et; i < max(r1 - r0, 0) * NV; i += NE) {
         const int rr = i / NV, nn = (i - rr * NV) * 8;
         const int mm = m0 + r0 + rr;
         const uint4 res = g.residual ? ld_cg16(g.residual + (int64_t)mm * g.res_ld + n0 + nn) : make_uint4(0u, 0u, 0u, 0u);
@@ -574,34 +645,34 @@ __device__ __noinline__ void gemm_epilogue(const SeqGemm& g, uint8_t* smem, uint
         for (int j = 0; j < 8; ++j) v[j] = 0.f;
         const float4* sp = stage + rr * NV4 + (nn >> 2);
 #pragma unroll 2
-        for (int zz = 0; zz < g.splits; ++zz) {  // fixed z order: bit-stable
+        for (int zz = 0; zz < gsplits; ++zz) {  // fixed z order: bit-stable
           const float4 a = sp[zz * per_split], b = sp[zz * per_split + 1];
           v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
           v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
         }
         if (table) {
-          const float* cr = colvec + (mm / g.hw - img0) * BN + nn;
+          const float* cr = colvec + (mm / ghw - img0) * BN + nn;
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] += cr[j];
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            if (g.bias) v[j] += g.bias[n0 + nn + j];
-            if (g.rowvec) v[j] += __ldcg(g.rowvec + (int64_t)(mm / g.hw) * g.rowvec_ld + n0 + nn + j);
+            if (gbias) v[j] += gbias[n0 + nn + j];
+            if (growvec) v[j] += __ldcg(growvec + (int64_t)(mm / ghw) * g.rowvec_ld + n0 + nn + j);
           }
         }
         float f[8];
         unpack8(res, f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] += f[j];
-        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(g.out) + (int64_t)mm * g.ldo + n0 + nn) = pack8(v);
+        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(gout) + (int64_t)mm * gldo + n0 + nn) = pack8(v);
       }
-      if (st.tr && et == 0) st.tr[12] = globaltimer_ns();  // slice reduced
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tr && et == 0) tr[12] = clock64() - t0;  // slice reduced
+      asm volatile("bar.sync 3, %0;" ::"r"(NE) : "memory");
       if (et == 0) {  // the last split to finish re-arms the counters for the next op
-        if (atomicAdd(&g.counters[g.mt * g.nt + tile], 1) == g.splits - 1) {
-          g.counters[tile] = 0;
-          g.counters[g.mt * g.nt + tile] = 0;
+        if (atomicAdd(&gcounters[g.mt * g.nt + tile], 1) == gsplits - 1) {
+          gcounters[tile] = 0;
+          gcounters[g.mt * g.nt + tile] = 0;
         }
       }
     }
@@ -617,7 +688,7 @@ __device__ __noinline__ void gemm_epilogue(const SeqGemm& g, uint8_t* smem, uint
 // channels, at most two groups) and pixels pl, pl + lanes, ...  With ps > 1 (big images split over CTAs) the chunk
 // statistics (mean, M2) meet in global memory across one grid barrier and are merged with Chan's formula in chunk order,
 // while the chunk stays in shared memory for the normalisation.  Fixed reduction orders: bit-stable.
-__device__ __noinline__ void gn_op(const SeqGN& p, uint8_t* smem, GridBarrier& gb) {
+__device__ __noinline__ unsigned gn_op(const SeqGN& p, uint8_t* smem, GridBarrier gb) {
   float* red = reinterpret_cast<float*>(smem + OFF_RED);    // [warp][4]
   float* stat = reinterpret_cast<float*>(smem + OFF_STAT);  // [group of the CTA][4][2]: mean, rstd
   const int C = p.c0 + p.c1, NV = p.cb / 8, GB = p.cb / p.cgn, nblk = C / p.cb;
@@ -657,7 +728,7 @@ __device__ __noinline__ void gn_op(const SeqGN& p, uint8_t* smem, GridBarrier& g
 
 #pragma unroll 1
   for (int phase = 0; phase < (p.ps > 1 ? 2 : 1); ++phase) {
-    if (phase == 1) gb.sync(nullptr, nullptr);
+    if (phase == 1) gb.n = grid_sync(gb.ctr, gb.n, gb.flags, gb.timing, gb.trace, gb.op, nullptr, nullptr);
 #pragma unroll 1
     for (int k = 0; k < rounds; ++k) {
       const int item = k * per_round + gid * gridDim.x + blockIdx.x;
@@ -781,6 +852,7 @@ __device__ __noinline__ void gn_op(const SeqGN& p, uint8_t* smem, GridBarrier& g
       }
     }
   }
+  return gb.n;
 }
 
 // =====================================================================================================
@@ -1006,13 +1078,16 @@ __global__ void __launch_bounds__(SEQ_THREADS, 1) seq_kernel(const SeqOp* __rest
     if (threadIdx.x == 0 && op.type == SEQ_GEMM) prefetch_tensormaps(ops, op.g.nseg);
   }
   GridBarrier gb{sync, 0u, timing, flags, trace, 0};
-  RoleState st{0xffffffffu, 0u, 0u, nullptr};
+  RoleState st{0xffffffffu, 0u, nullptr, 0};
+  uint32_t acc_base = 0;  // accumulator hand-offs of this CTA so far (buffer = n & 1, phase = (n >> 1) & 1): every thread counts
 #pragma unroll 1
   for (int i = 0; i < n_ops; ++i) {
     const int type = op.type;
     gb.op = i;
     st.tr = trace ? trace + ((size_t)gb.n * gridDim.x + blockIdx.x) * 16 : nullptr;
+    st.t0 = clock64();
     if (type == SEQ_GEMM) {
+      const bool solo = op.g.solo != 0;
       if (warp == 0) {
         if (lane == 0) {
           gemm_producer(op.g, ops + i, smem_base, st);
@@ -1022,20 +1097,23 @@ __global__ void __launch_bounds__(SEQ_THREADS, 1) seq_kernel(const SeqOp* __rest
         }
         __syncwarp();
       } else if (warp == 1) {
-        gemm_mma(op.g, smem_base, tmem_base, st);
-      } else if (warp < 6) {
-        gemm_epilogue(op.g, smem, smem_base, tmem_base, st);
-      }  // (warps 6, 7 have no GEMM role: they wait at the op barrier)
+        gemm_mma(op.g, smem_base, tmem_base, st, acc_base);
+      }
+      if (solo || (warp >= 2 && warp < 6)) gemm_epilogue(op.g, smem, smem_base, tmem_base, st, acc_base);
+      {  // every thread counts this CTA's accumulator hand-offs of the op
+        const int nw = op.g.mt * op.g.nt * op.g.splits;
+        acc_base += (int)blockIdx.x < nw ? (uint32_t)((nw - 1 - (int)blockIdx.x) / (int)gridDim.x + 1) : 0u;
+      }
     } else {
       if (threadIdx.x == 0 && op.next_nseg > 0) prefetch_tensormaps(ops + i + 1, op.next_nseg);
-      if (type == SEQ_GN) gn_op(op.gn, smem, gb);
+      if (type == SEQ_GN) gb.n = gn_op(op.gn, smem, gb);
       else if (type == SEQ_LN) ln_op(op.ln, smem);
       else if (type == SEQ_UPSAMPLE) upsample_op(op.ew);
       else if (type == SEQ_IM2COL) im2col_op(op.ew);
       else if (type == SEQ_SINUSOID) sinusoid_op(op.ew);
       else if (type == SEQ_SPLITK_REDUCE) splitk_reduce_op(op.ew);
     }
-    if (i + 1 < n_ops) gb.sync(ops + i + 1, smem + OFF_DESC);
+    if (i + 1 < n_ops) gb.n = grid_sync(gb.ctr, gb.n, gb.flags, gb.timing, gb.trace, i, ops + i + 1, smem + OFF_DESC);
   }
   // ---- teardown: the last CTA out re-arms the barrier words for the next launch (every CTA that got here has passed
   // every barrier, so nobody can still be polling)
@@ -1053,6 +1131,55 @@ __global__ void __launch_bounds__(SEQ_THREADS, 1) seq_kernel(const SeqOp* __rest
       sync[1] = 0u;
       __threadfence();
     }
+  }
+}
+
+// ONE GEMM op per launch: same roles, the op descriptor and its tensor maps in parameter (constant) space.
+__global__ void __launch_bounds__(SEQ_THREADS, 1) seq_gemm_kernel(const __grid_constant__ SeqOp op, int flags) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw_addr = tc::smem_u32(smem_raw);
+  const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - raw_addr);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const SeqGemm& g = op.c.g;
+  if (threadIdx.x == 0) {
+    prefetch_tensormaps(&op, g.nseg);
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      tc::mbar_init(smem_base + OFF_BAR_FULL + 8 * s, 1);
+      tc::mbar_init(smem_base + OFF_BAR_EMPTY + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(smem_base + OFF_ACC_FULL + 8 * b, 1);
+      tc::mbar_init(smem_base + OFF_ACC_EMPTY + 8 * b, 128);
+    }
+    tc::mbar_fence_init();
+  }
+  if (warp == 1) tc::tmem_alloc<512>(smem_base + OFF_TMEM);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<const uint32_t*>(smem + OFF_TMEM);
+  RoleState st{0xffffffffu, 0u, nullptr, 0};
+  const bool solo = g.solo != 0;
+  if (warp == 0) {
+    if (lane == 0) {
+      gemm_producer(g, &op, smem_base, st);
+      if ((flags & SEQ_F_PREFETCH) && op.c.pf.bn > 0) {  // the next launch's weights -> L2 while this one drains
+        SeqPrefetch pf = op.c.pf;
+        pf.map = &op.tmPf;
+        prefetch_next_weights(pf);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    gemm_mma(g, smem_base, tmem_base, st, 0u);
+  }
+  if (solo || (warp >= 2 && warp < 6)) gemm_epilogue(g, smem, smem_base, tmem_base, st, 0u);
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -1218,6 +1345,8 @@ bool seq_plan_gemm(const mvldm_gemm_desc& d, void* workspace, size_t workspace_b
   const int work = p.mt * p.nt * splits;
   const bool fused = splits > 1 && work <= seq_grid() && p.mt * p.nt <= 4096;
   p.counters = fused ? reinterpret_cast<int*>(workspace) : nullptr;
+  p.solo = work <= seq_grid() ? 1 : 0;
+  p.stage_out = (p.solo && splits == 1 && (d.mode == 0 || d.mode == 1 || d.mode == 3)) ? 1 : 0;
   p.bias = d.bias;
   p.rowvec = d.rowvec;
   p.rowvec_ld = d.rowvec_ld;
@@ -1251,11 +1380,13 @@ void seq_link_prefetch(SeqOp* ops, int n, const SeqOp* dev_ops) {
   for (int i = n - 1; i >= 0; --i) {
     ops[i].c.index = i;
     ops[i].c.pf.map = nullptr;
+    ops[i].c.pf.bn = 0;
     if (ops[i].c.type != SEQ_GEMM) continue;
     if (next_gemm >= 0) {
       const SeqGemm& g = ops[next_gemm].c.g;
       SeqPrefetch& pf = ops[i].c.pf;
-      pf.map = &dev_ops[next_gemm].tmB[KC - 1];
+      pf.map = dev_ops ? &dev_ops[next_gemm].tmB[KC - 1] : nullptr;
+      ops[i].tmPf = ops[next_gemm].tmB[KC - 1];
       pf.bn = g.bn;
       pf.nt = g.nt;
       pf.nchunks = g.seg[g.nseg - 1].kchunk0 + g.seg[g.nseg - 1].ntaps * g.seg[g.nseg - 1].ncblk;
@@ -1358,6 +1489,7 @@ void seq_configure() {  // once per device, outside any stream capture
   static bool configured[kMaxDevices] = {};
   if (first_use_on_device(configured)) {
     MV_CUDA(cudaFuncSetAttribute(seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    MV_CUDA(cudaFuncSetAttribute(seq_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int per_sm = 0;
     MV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seq_kernel, SEQ_THREADS, SMEM_BYTES));
     MV_CHECK(per_sm >= 1, "seq_launch: the sequence kernel does not fit on an SM of this device");
@@ -1385,6 +1517,19 @@ void seq_launch(cudaStream_t s, const SeqOp* dev_ops, int n_ops, unsigned* sync,
   } else {
     MV_CUDA(cudaLaunchKernel((const void*)seq_kernel, dim3(seq_grid()), dim3(SEQ_THREADS), args, SMEM_BYTES, s));
   }
+  MV_LAUNCHED();
+}
+
+void seq_launch_gemm(cudaStream_t s, const SeqOp& op) {
+  MV_CHECK(op.c.type == SEQ_GEMM, "seq_launch_gemm: not a GEMM op");
+  seq_configure();
+  static const int env_flags = [] {
+    const char* e = getenv("MVLDM_SEQ_FLAGS");
+    return e ? atoi(e) : 7;
+  }();
+  const SeqGemm& g = op.c.g;
+  const int work = g.mt * g.nt * g.splits;
+  seq_gemm_kernel<<<dim3(std::min(work, seq_grid())), dim3(SEQ_THREADS), SMEM_BYTES, s>>>(op, env_flags);
   MV_LAUNCHED();
 }
 

@@ -27,8 +27,10 @@ struct SeqGemm {
   int nseg, M, N, num_steps;
   int mt, nt, splits, steps_per_split;  // work items = mt * nt * splits, m fastest
   int hw, ow;                           // output pixels per image / row width
-  int bn, stages;                       // N tile (multiple of 16, <= 256) and smem ring depth for it
-  int mode, ldo, n_valid, rowvec_ld, res_ld, pad_;
+  int bn, stages;                       // N tile (multiple of 32, <= 256) and smem ring depth for it
+  int solo, pad_;                       // solo: at most one work item per CTA (all 8 warps then run the epilogue)
+  int mode, ldo, n_valid, rowvec_ld, res_ld;
+  int stage_out;  // one work item per CTA and a bf16 output: the tile leaves through shared memory as whole 128-byte lines
   float* partial;   // split-K fp32 partial tiles [splits][M][N], or NULL
   int* counters;    // fused split-K reduction: [2][mt*nt] arrive / done counters (zero between ops), or NULL
   const float* bias;
@@ -96,6 +98,7 @@ struct alignas(128) SeqOp {
   uint8_t pad_[SEQ_OPC_BYTES - sizeof(SeqOpC)];
   CUtensorMap tmA[MVLDM_MAX_SEGS][SEQ_KC];  // 5-D (64 ch, w, h, image, chunk), box carrying 1..KC chunks
   CUtensorMap tmB[SEQ_KC];                   // 3-D (64 k, n, chunk)
+  CUtensorMap tmPf;                          // copy of the next GEMM op's tmB[SEQ_KC - 1]: weight prefetch of a single-op launch
 };
 
 // ---- host side ------------------------------------------------------------------------------------------
@@ -123,6 +126,9 @@ int seq_grid();  // CTAs of every sequence launch (= SM count; all co-resident)
 void seq_launch(cudaStream_t s, const SeqOp* dev_ops, int n_ops, unsigned* sync, long long* timing);
 // one-off launch of host-built ops (op-level C ABI entry points / tests): uploads to a cached device buffer
 void seq_run_host_ops(cudaStream_t s, const SeqOp* host_ops, int n_ops);
+// ONE GEMM op as its own launch: the descriptor and tensor maps travel as kernel parameters (no grid barrier, no global
+// descriptor fetch); min(work items, SMs) CTAs
+void seq_launch_gemm(cudaStream_t s, const SeqOp& op);
 void seq_debug_empty_ops(cudaStream_t s, int n_ops);
 extern long long* g_seq_trace;  // debug: [barrier][cta][4] timeline buffer for the next launches, or NULL
 

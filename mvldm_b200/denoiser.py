@@ -212,6 +212,13 @@ class _Handle:
         self.close()
 
 
+# Ops on at most this many tokens run inside the fused persistent sequence kernel (csrc/seq.cu), larger ones as stand-alone
+# kernels; -1 fuses everything.  Measured on B200 at 1 scene x 8 views (profiles/r02_fuse_sweep.txt): 0 -> 3.23 ms/step,
+# 128 -> 3.31, 512 -> 3.39, 2048 -> 3.54, -1 -> 3.78, so the default keeps one launch per op inside a CUDA graph.
+# MVLDM_FUSE_MAX_TOKENS overrides it for measurement sweeps.
+FUSE_MAX_TOKENS = 0
+
+
 class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
     """Drop-in for reference ``MultiViewUNet`` (mvunet.py:43-208).
 
@@ -258,11 +265,14 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
 
     def mark_dirty(self) -> None:
         """Tell the module its parameters changed in place (the packed device copy is rebuilt on the next call).
-        Done automatically after load_state_dict / .to() / .cuda(), and before every call in training mode."""
+        Done automatically after load_state_dict / .to() / .cuda(); in-place updates are also caught by the per-call
+        parameter-version check."""
         self._dirty = True
+        self.__dict__.pop("_plist", None)
 
     def _apply(self, fn, *args, **kwargs):
         self._dirty = True
+        self.__dict__.pop("_plist", None)
         return super()._apply(fn, *args, **kwargs)
 
     # ---- parameters -------------------------------------------------------------------
@@ -305,6 +315,7 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
         c.max_attn_res = 32
         c.impl = self.impl
         c.use_cuda_graph = 1 if self.use_cuda_graph else 0
+        c.fuse_max_tokens = FUSE_MAX_TOKENS
         if self.variant_b:
             c.variant, c.cross_attention_dim = 1, SD21_CROSS_ATTENTION_DIM
             for i, v in enumerate(SD21_HEADS):
@@ -320,7 +331,15 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
         return h
 
     def _versions(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        # (storage pointers change only through _apply / load_state_dict, which mark the module dirty and drop this cache;
+        # walking the module tree on every call cost ~0.4 ms, the flat list ~40 us)
+        n = self.__dict__["_vcalls"] = self.__dict__.get("_vcalls", 0) + 1
+        plist = self.__dict__.get("_plist") if n % 64 else None  # (`p.data = other` swaps storage silently: re-walk now and then)
+        if plist is None:
+            plist = list(self.parameters())
+            self.__dict__["_plist"] = plist
+            self.__dict__["_pptrs"] = tuple(p.data_ptr() for p in plist)
+        return self.__dict__["_pptrs"], tuple(p._version for p in plist)
 
     def refresh_weights(self, force: bool = True) -> None:
         """(Re-)pack the module's parameters into the library's kernel layouts."""

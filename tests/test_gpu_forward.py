@@ -137,6 +137,26 @@ def test_weight_reload_is_picked_up(oracle_weights):
     assert set(sd) == set(oracle_weights)
 
 
+def test_in_place_parameter_update_in_eval_mode_is_picked_up(oracle_weights):
+    """EMA copy_to / AveragedModel.update_parameters / p.data.copy_ mutate parameters in place while the module is in eval
+    mode and without load_state_dict: the packed device copy (and the captured graph) must not go stale"""
+    m = mv.MultiViewUNet(mv.default_cfg(), 11, 4)
+    m.load_state_dict(oracle_weights)
+    m = m.cuda().eval()
+    x = torch.randn(1, 2, 11, 32, 32, device="cuda")
+    t = torch.tensor([10], device="cuda")
+    y0 = m(x, t).clone()
+    assert torch.equal(y0, m(x, t))
+    with torch.no_grad():
+        p = dict(m.named_parameters())["unet.conv_out.bias"]
+        p.add_(1.0)                                        # in place: bumps p._version only
+    y1 = m(x, t)
+    assert torch.allclose(y1, y0 + 1.0, atol=1e-5)         # conv_out.bias is added to every output channel in fp32
+    with torch.no_grad():
+        p.data.copy_(p.data - 1.0)
+    assert torch.equal(m(x, t), y0)
+
+
 @pytest.mark.parametrize("use_cfg", [False, True])
 def test_ddim_trajectory_25_steps(use_cfg, gpu_models, oracle_weights, oracle_cfg):
     """BASELINE config 2: 25-step DDIM, 2 context + 6 target views, against the trajectory the reference module

@@ -58,8 +58,8 @@ for l in launches:
         if names[opi]["cat"].startswith("gemm") and r[lc, 9] > 0:
             e = r[lc]
             b0 = base
-            seq = [e[6], e[7], e[8], e[9], e[13], e[10], e[11], e[14], e[15], e[12]]
-            print("  last CTA: tma0 %.2f tile0 %.2f wait_acc %.2f acc %.2f chunk0 %.2f stored %.2f splits_in %.2f cp_issued %.2f staged %.2f reduced %.2f" % tuple((x - b0) / 1e3 if x > 0 else -1 for x in seq), end="")
+            seq = [e[6], e[7], e[8], e[9], e[13], e[10], e[11], e[14], e[15], e[12], e[4]]
+            print("  last CTA: tma0 %.2f tile0 %.2f wait_acc %.2f acc %.2f chunk0 %.2f stored %.2f splits_in %.2f cp_issued %.2f staged %.2f reduced %.2f c1wait %.2f" % tuple(x / 1965.0 if x > 0 else -1 for x in seq), end="")
         print()
         prev_release = rel.min()
     print("-- launch end --")
