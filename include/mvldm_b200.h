@@ -28,7 +28,8 @@ typedef struct mvldm_handle_s* mvldm_handle;
 enum { MVLDM_F32 = 0, MVLDM_BF16 = 1, MVLDM_F16 = 2 };
 /* kernel family: tcgen05/TMA kernels (product) or the plain CUDA-core kernels kept as an on-device
  * cross-check for the tests (never selected implicitly) */
-enum { MVLDM_IMPL_TC = 0, MVLDM_IMPL_SIMT = 1, MVLDM_IMPL_TC_GEMM_SIMT_ATTN = 2 };
+enum { MVLDM_IMPL_TC = 0, MVLDM_IMPL_SIMT = 1, MVLDM_IMPL_TC_GEMM_SIMT_ATTN = 2,
+       MVLDM_IMPL_TC_SEQ = 3 /* mvldm_op_gemm only: the tcgen05 GEMM as an op of the fused sequence kernel */ };
 
 /* Replaces: MultiViewUNetCfg + UNet2DModelCfg + SpatialTransformer3DCfg
  * (src/model/denoiser/mvunet.py:22-40, src/model/denoiser/mvdream/attention.py:23-32) and the
@@ -215,6 +216,12 @@ int mvldm_op_groupnorm(void* stream, const void* x0, int c0, const void* x1, int
                        float* scratch /* >= n_img*groups*2*64 floats */);
 int mvldm_op_layernorm(void* stream, const void* x, int rows, int c, float eps, const float* gamma,
                        const float* beta, void* out);
+/* The same two ops executed as ops of the fused sequence kernel (the path mvldm_config.fuse_max_tokens selects). */
+int mvldm_op_seq_groupnorm(void* stream, const void* x0, int c0, const void* x1, int c1, int n_img, int hw,
+                           int groups, float eps, const float* gamma, const float* beta, int silu, void* out,
+                           float* scratch /* >= n_img*groups*2*64 floats */);
+int mvldm_op_seq_layernorm(void* stream, const void* x, int rows, int c, float eps, const float* gamma,
+                           const float* beta, void* out);
 
 #ifdef __cplusplus
 }

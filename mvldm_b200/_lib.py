@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libmvldm_b200.so")
 MVLDM_MAX_LEVELS = 4
 MVLDM_MAX_SEGS = 3
 F32, BF16, F16 = 0, 1, 2
-IMPL_TC, IMPL_SIMT, IMPL_TC_GEMM_SIMT_ATTN = 0, 1, 2
+IMPL_TC, IMPL_SIMT, IMPL_TC_GEMM_SIMT_ATTN, IMPL_TC_SEQ = 0, 1, 2, 3
 
 
 class Config(Structure):
@@ -76,6 +76,9 @@ SYMBOLS = {
     "mvldm_op_groupnorm": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
                                    c_void_p, c_int, c_void_p, c_void_p]),
     "mvldm_op_layernorm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "mvldm_op_seq_groupnorm": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                                       c_void_p, c_int, c_void_p, c_void_p]),
+    "mvldm_op_seq_layernorm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
 }
 
 KV_EXCHANGE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p)

@@ -632,8 +632,8 @@ struct mvldm_handle_s {
       st.gemm = d;
       st.meta = OpMeta{cat, what, flops, bytes};
       static const bool single = [] {
-        const char* e = getenv("MVLDM_GEMM_KERNEL");
-        return !e || atoi(e) != 0;
+        const char* e = getenv("MVLDM_GEMM_KERNEL");  // 1: the sequence kernel's GEMM as a stand-alone launch (measured slower)
+        return e && atoi(e) != 0;
       }();
       if (single) {  // the sequence kernel's GEMM as its own launch (descriptor in parameter space)
         SeqOp op, red;
@@ -881,7 +881,7 @@ struct mvldm_handle_s {
     Act col = new_act(n, Hh, Ww, kpad_in);
     if (!dry) {
       const double bytes = (double)col.tokens() * (kpad_in * 2 + cfg.in_channels * 4);
-      if (fuse_op(col.tokens())) {
+      if (fuse_op(col.tokens()) && !getenv("MVLDM_DEBUG_CLASSIC_IM2COL")) {
         SeqOp op;
         seq_plan_im2col(latents, n, cfg.in_channels, Hh, Ww, kpad_in, col.p, op);
         push_op(op, "input_im2col", "", 0.0, bytes);
@@ -1487,15 +1487,16 @@ int mvldm_raymap(void* stream, const float* extr, const float* intr, int n, int 
 int mvldm_op_gemm(void* stream, int impl, const mvldm_gemm_desc* d) {
   MV_API_BEGIN
   MV_CHECK(d, "null argument");
-  if (impl == MVLDM_IMPL_TC) {
+  if (impl == MVLDM_IMPL_TC || impl == MVLDM_IMPL_TC_SEQ) {
     static DevBuf scratch;  // op-level entry point (tests): grown on demand, never shrunk
-    const size_t need = gemm_tc_workspace_bytes(*d);
+    const size_t need = std::max(gemm_tc_workspace_bytes(*d), gemm_classic_workspace_bytes(*d));
     if (need > scratch.bytes) {
       MV_CUDA(cudaDeviceSynchronize());
       scratch.alloc(need);
       MV_CUDA(cudaMemset(scratch.p, 0, need));
     }
-    gemm_tc((cudaStream_t)stream, *d, scratch.p, scratch.bytes);
+    if (impl == MVLDM_IMPL_TC) gemm_classic((cudaStream_t)stream, *d, scratch.p, scratch.bytes);
+    else gemm_tc((cudaStream_t)stream, *d, scratch.p, scratch.bytes);  // the same GEMM as an op of the sequence kernel
   } else {
     gemm_simt((cudaStream_t)stream, *d);
   }
@@ -1546,6 +1547,16 @@ int mvldm_op_groupnorm(void* stream, const void* x0, int c0, const void* x1, int
                        float eps, const float* gamma, const float* beta, int silu, void* out, float* scratch) {
   MV_API_BEGIN
   MV_CHECK(x0 && gamma && beta && out && scratch, "null argument");
+  groupnorm_classic_init();
+  groupnorm_classic((cudaStream_t)stream, (const bf16*)x0, c0, (const bf16*)x1, c1, n_img, hw, groups, eps, gamma, beta,
+                    silu != 0, (bf16*)out, scratch);
+  MV_API_END
+}
+
+int mvldm_op_seq_groupnorm(void* stream, const void* x0, int c0, const void* x1, int c1, int n_img, int hw, int groups,
+                           float eps, const float* gamma, const float* beta, int silu, void* out, float* scratch) {
+  MV_API_BEGIN
+  MV_CHECK(x0 && gamma && beta && out && scratch, "null argument");
   groupnorm((cudaStream_t)stream, (const bf16*)x0, c0, (const bf16*)x1, c1, n_img, hw, groups, eps, gamma, beta,
             silu != 0, (bf16*)out, scratch);
   MV_API_END
@@ -1553,6 +1564,14 @@ int mvldm_op_groupnorm(void* stream, const void* x0, int c0, const void* x1, int
 
 int mvldm_op_layernorm(void* stream, const void* x, int rows, int c, float eps, const float* gamma, const float* beta,
                        void* out) {
+  MV_API_BEGIN
+  MV_CHECK(x && gamma && beta && out, "null argument");
+  layernorm_classic((cudaStream_t)stream, (const bf16*)x, rows, c, eps, gamma, beta, (bf16*)out);
+  MV_API_END
+}
+
+int mvldm_op_seq_layernorm(void* stream, const void* x, int rows, int c, float eps, const float* gamma, const float* beta,
+                           void* out) {
   MV_API_BEGIN
   MV_CHECK(x && gamma && beta && out, "null argument");
   layernorm((cudaStream_t)stream, (const bf16*)x, rows, c, eps, gamma, beta, (bf16*)out);

@@ -147,6 +147,21 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "r"(taddr));
 }
 
+// tcgen05.wait::ld that the compiler cannot move register reads across: the TMEM load writes its destination registers
+// asynchronously, so every use of them must stay behind the wait - which needs a data dependency, not just asm volatile
+// (an fp32 accumulator chunk read as a plain bit cast was hoisted above the wait and picked up in-flight registers)
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])::"memory");
+}
+__device__ __forceinline__ void tmem_ld_dep16(uint32_t (&r)[16]) {  // after the wait: ties a second destination array to it
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+               "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])::"memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -182,7 +197,10 @@ __device__ __noinline__ unsigned grid_sync(unsigned* ctr, unsigned n, int flags,
                                            const SeqOp* next, uint8_t* desc_smem) {
   long long* tr = trace && threadIdx.x == 0 ? trace + ((size_t)n * gridDim.x + blockIdx.x) * 16 : nullptr;
   if (tr) tr[0] = globaltimer_ns();
-  if (flags & SEQ_F_PROXY_FENCE) asm volatile("fence.proxy.async.global;" ::: "memory");
+  // generic-proxy accesses of this op (global stores other CTAs will read with TMA; shared-memory staging tiles, slabs and
+  // row buffers that the next op's TMA loads will overwrite) are ordered before the async-proxy accesses that follow
+  if (flags & 8) __threadfence();  // debug: every thread fences (the pre-rewrite barrier)
+  if (flags & SEQ_F_PROXY_FENCE) asm volatile("fence.proxy.async;" ::: "memory");
   __syncthreads();
   if (tr) tr[1] = globaltimer_ns();
   ++n;
@@ -207,7 +225,7 @@ __device__ __noinline__ unsigned grid_sync(unsigned* ctr, unsigned n, int flags,
     }
   }
   __syncthreads();
-  if (flags & SEQ_F_PROXY_FENCE) asm volatile("fence.proxy.async.global;" ::: "memory");
+  if (flags & SEQ_F_PROXY_FENCE) asm volatile("fence.proxy.async;" ::: "memory");
   return n;
 }
 
@@ -476,7 +494,8 @@ __device__ __noinline__ void gemm_epilogue(const SeqGemm& g, uint8_t* smem, uint
     for (int c0 = h * 32; c0 < BN; c0 += cstep) {
       const int n = n0 + c0;
       const bool more = c0 + cstep < BN;
-      tc::tmem_ld_wait();
+      tmem_ld_wait_dep(r);
+      if (use_res) tmem_ld_dep16(rs);
       if (gpartial) {  // split-K: raw fp32 partial, reduced (+ epilogue) below or by the SEQ_SPLITK_REDUCE op
         if (ok) {
           float* pp = gpartial + ((int64_t)z * gM + m) * gN + n;

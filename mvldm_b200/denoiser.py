@@ -228,7 +228,7 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
     random-initialised and the checkpoint arrives through ``load_state_dict`` like any Lightning checkpoint."""
 
     def __init__(self, cfg: MultiViewUNetCfg, in_channels: int, out_channels: int, *, impl: int = _lib.IMPL_TC,
-                 use_cuda_graph: bool = True) -> None:
+                 use_cuda_graph: bool = True, fuse_max_tokens: Optional[int] = None) -> None:
         super().__init__(cfg)
         self.variant_b = cfg.pretrained_from is not None
         if cfg.multi_view_attention.name != "spatial_transformer_3d":
@@ -256,6 +256,7 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
         self.pretrained_from = cfg.pretrained_from
         self.in_channels, self.out_channels = in_channels, out_channels
         self.impl, self.use_cuda_graph = impl, use_cuda_graph
+        self.fuse_max_tokens = FUSE_MAX_TOKENS if fuse_max_tokens is None else int(fuse_max_tokens)
         self._shapes = param_shapes(self._boc, in_channels, out_channels, variant_b=self.variant_b)
         for key, shape in self._shapes.items():
             self._register(key, self._init_param(key, shape))
@@ -315,7 +316,7 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
         c.max_attn_res = 32
         c.impl = self.impl
         c.use_cuda_graph = 1 if self.use_cuda_graph else 0
-        c.fuse_max_tokens = FUSE_MAX_TOKENS
+        c.fuse_max_tokens = self.fuse_max_tokens
         if self.variant_b:
             c.variant, c.cross_attention_dim = 1, SD21_CROSS_ATTENTION_DIM
             for i, v in enumerate(SD21_HEADS):

@@ -65,7 +65,7 @@ def test_forward_v8_golden_graph_and_determinism(gpu_models):
     assert rel_err(y, torch.tensor(g["eps"])) < FWD_TOL
     y1, y2, y3 = graph(inp, ts), graph(inp, ts), eager(inp, ts)
     assert torch.equal(y, y1) and torch.equal(y1, y2) and torch.equal(y, y3)
-    assert graph.last_launch_count() >= 30          # our kernels (fused sequence launches + attention), not a library fallback
+    assert graph.last_launch_count() > 100          # our kernels, not a library fallback
 
 
 def test_timestep_broadcast_and_scene_independence(gpu_models):
@@ -137,6 +137,23 @@ def test_weight_reload_is_picked_up(oracle_weights):
     assert set(sd) == set(oracle_weights)
 
 
+@pytest.mark.parametrize("fuse", [-1, 512])
+def test_fused_sequence_kernel_forward_matches_golden(fuse, oracle_weights):
+    """mvldm_config.fuse_max_tokens: the same forward with every op (or the ops of the 4x4 / 8x8 levels) executed inside the
+    persistent sequence kernel (grid barriers between ops instead of kernel boundaries): same tolerance, bit-stable, and the
+    launch count shows the fusion"""
+    g = np.load(os.path.join(GOLD, "g2_forward_v8.npz"))
+    inp, ts = torch.tensor(g["inputs"]).cuda(), torch.tensor(g["timesteps"]).cuda()
+    m = mv.MultiViewUNet(mv.default_cfg(), 11, 4, use_cuda_graph=True, fuse_max_tokens=fuse)
+    m.load_state_dict(oracle_weights)
+    m = m.cuda().eval()
+    y = m(inp, ts)
+    assert rel_err(y, torch.tensor(g["eps"])) < FWD_TOL
+    assert torch.equal(y, m(inp, ts)) and torch.equal(y, m(inp, ts))
+    print(f"fuse_max_tokens={fuse}: {m.last_launch_count()} launches per forward")
+    assert m.last_launch_count() < (60 if fuse < 0 else 160)
+
+
 def test_in_place_parameter_update_in_eval_mode_is_picked_up(oracle_weights):
     """EMA copy_to / AveragedModel.update_parameters / p.data.copy_ mutate parameters in place while the module is in eval
     mode and without load_state_dict: the packed device copy (and the captured graph) must not go stale"""
@@ -157,13 +174,32 @@ def test_in_place_parameter_update_in_eval_mode_is_picked_up(oracle_weights):
     assert torch.equal(m(x, t), y0)
 
 
+def _oracle_bf16_trajectory(sd, cfg, g, use_cfg):
+    """the reference arithmetic run the way the reference runs it - eager torch under bf16 autocast, on this GPU - through the
+    same 25 DDIM steps (scheduler in fp32 on the host, as in DiffusionWrapper.step): its per-step drift from the fp32 golden"""
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+
+    def fwd(lat, t):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            return O.unet_forward(sd_gpu, lat.cuda(), t.cuda(), cfg).float().cpu()
+
+    rec = []
+    with torch.no_grad():
+        O.sample(sd, cfg, torch.tensor(g["context_latents"]), torch.tensor(g["x_T"]), torch.tensor(g["extr"]),
+                 torch.tensor(g["intr"]), 25, use_cfg, 3.0, False, forward=fwd, record=rec)
+    return rec
+
+
+TRAJ_FLOOR = 5e-3     # 2.5 bf16 half-ulps: floor for steps where the reference's own bf16 drift happens to be tiny
+
+
 @pytest.mark.parametrize("use_cfg", [False, True])
 def test_ddim_trajectory_25_steps(use_cfg, gpu_models, oracle_weights, oracle_cfg):
     """BASELINE config 2: 25-step DDIM, 2 context + 6 target views, against the trajectory the reference module
     produced in fp32.  With random-init weights the map x_T -> x_0 amplifies (|x| grows from 1 to ~110 because
     eps is not a denoiser's: x0 = (x - s*eps)/sqrt(abar), sqrt(abar_960) = 0.02), so errors are judged
-    relative to the signal at each recorded step, against the same 2 x bf16-drift rule, measured per step on
-    the first step and bounded over the trajectory."""
+    relative to the signal at each recorded step.  SURVEY.md section 8c rule, applied PER RECORDED STEP and at step 25:
+    err(cuda, fp32 reference) <= 2 x err(reference under bf16 autocast, fp32 reference) (with a 5e-3 floor)."""
     g = np.load(os.path.join(GOLD, f"g3_traj25_cfg{int(use_cfg)}.npz"))
     ctx, x_T = torch.tensor(g["context_latents"]).cuda(), torch.tensor(g["x_T"]).cuda()
     extr, intr = torch.tensor(g["extr"]).cuda(), torch.tensor(g["intr"]).cuda()
@@ -173,12 +209,14 @@ def test_ddim_trajectory_25_steps(use_cfg, gpu_models, oracle_weights, oracle_cf
     rec = []
     x0 = path.sample(ctx, x_T, extr, intr, record=rec)
     assert [r[0] for r in rec] == list(g["timesteps"])
-    errs = {}
-    for i in (0, 4, 9, 14, 19, 24):
-        errs[i] = rel_err(rec[i][1], torch.tensor(g[f"x_after_step{i}"]))
-    print("trajectory rel err per recorded step:", {k: f"{v:.2e}" for k, v in errs.items()})
-    assert errs[0] < FWD_TOL                     # one step
-    assert max(errs.values()) < 0.15             # 25 compounded steps (bf16 storage, random-init amplification)
+    ref_rec = _oracle_bf16_trajectory(oracle_weights, oracle_cfg, g, use_cfg)
+    steps = (0, 4, 9, 14, 19, 24)
+    errs = {i: rel_err(rec[i][1], torch.tensor(g[f"x_after_step{i}"])) for i in steps}
+    drift = {i: rel_err(ref_rec[i][1], torch.tensor(g[f"x_after_step{i}"])) for i in steps}
+    print("trajectory rel err per recorded step:      ", {k: f"{v:.2e}" for k, v in errs.items()})
+    print("reference bf16-autocast drift, same steps: ", {k: f"{v:.2e}" for k, v in drift.items()})
+    for i in steps:
+        assert errs[i] <= max(2 * drift[i], TRAJ_FLOOR), f"step {i}: {errs[i]:.3e} vs reference bf16 drift {drift[i]:.3e}"
     assert rel_err(x0, torch.tensor(g["x_0"])) == errs[24]
     assert torch.isfinite(x0).all()
     # bit-stable: the same trajectory twice

@@ -17,7 +17,7 @@ from oracle import mvldm_oracle as O
 
 pytestmark = pytest.mark.gpu
 BF16_TOL = 1e-2
-IMPLS = [pytest.param(0, id="tcgen05"), pytest.param(1, id="simt")]
+IMPLS = [pytest.param(0, id="tcgen05"), pytest.param(3, id="tcgen05-seq"), pytest.param(1, id="simt")]
 
 
 def _conv_ref(xb, wp, b, cout, cin, stride):
@@ -95,6 +95,24 @@ def test_conv_plus_shortcut_segments_and_head(impl):
     assert rel_err(out, ref) < 1e-5           # fp32 out: only summation order differs
 
 
+@pytest.mark.parametrize("impl", IMPLS)
+def test_time_embedding_shaped_gemms(impl):
+    """the time-embedding chain: M = 8 rows of 1x1 'images' (128 images per tile: bias straight from memory, no table),
+    SiLU epilogue (mode 3) and fp32 row-major output (mode 4)"""
+    torch.manual_seed(8)
+    n, K, N = 8, 320, 1280
+    a = torch.randn(n, K).to(torch.bfloat16).cuda()
+    w = (torch.randn(N, K) / K ** 0.5).to(torch.bfloat16).cuda()
+    b = torch.randn(N).cuda()
+    ref = a.float() @ w.float().t() + b
+    out = torch.empty((n, N), device="cuda", dtype=torch.bfloat16)
+    run_gemm(impl, [conv_seg(a.view(n, 1, 1, K), 1, 1)], n, 1, 1, w, bias=b, mode=3, out=out)
+    assert rel_err(out.float(), F.silu(ref)) < BF16_TOL
+    out32 = torch.empty((n, N), device="cuda", dtype=torch.float32)
+    run_gemm(impl, [conv_seg(a.view(n, 1, 1, K), 1, 1)], n, 1, 1, w, bias=b, mode=4, out=out32)
+    assert rel_err(out32, ref) < 1e-5 if impl != 1 else rel_err(out32, ref) < 1e-4
+
+
 def test_splitk_epilogue_and_segments():
     """split-K path with bias + per-image row vector + residual, and with the 3-segment conv+shortcut operand"""
     torch.manual_seed(6)
@@ -108,7 +126,7 @@ def test_splitk_epilogue_and_segments():
     tof = lambda T: T.float().cpu().permute(0, 3, 1, 2)  # noqa: E731
     nhwc = lambda T: T.permute(0, 2, 3, 1).reshape(-1, co)  # noqa: E731
     base = F.conv2d(tof(x), wc.to(torch.bfloat16).float(), padding=1)
-    for impl in (0, 1):
+    for impl in (0, 3, 1):
         out = run_gemm(impl, [conv_seg(x)], n, hw, hw, pack_conv_weight(wc).cuda(), bias=b, rowvec=rv, residual=res)
         ref = nhwc(base + b.cpu()[None, :, None, None] + rv.cpu()[:, :, None, None]) + res.float().cpu()
         assert rel_err(out.float(), ref) < BF16_TOL
@@ -116,8 +134,9 @@ def test_splitk_epilogue_and_segments():
         out = run_gemm(impl, [conv_seg(x), conv_seg(sk, 1, 1)], n, hw, hw, wp)
         ref = nhwc(base + F.conv2d(tof(sk), ws.to(torch.bfloat16).float()))
         assert rel_err(out.float(), ref) < BF16_TOL
-    a = run_gemm(0, [conv_seg(x)], n, hw, hw, pack_conv_weight(wc).cuda())
-    assert torch.equal(a, run_gemm(0, [conv_seg(x)], n, hw, hw, pack_conv_weight(wc).cuda()))   # bit-stable
+    for impl in (0, 3):
+        a = run_gemm(impl, [conv_seg(x)], n, hw, hw, pack_conv_weight(wc).cuda())
+        assert torch.equal(a, run_gemm(impl, [conv_seg(x)], n, hw, hw, pack_conv_weight(wc).cuda()))   # bit-stable
 
 
 def test_tcgen05_matches_simt_bitwise_close():
@@ -149,31 +168,50 @@ def test_gemm_rejects_unsupported_shapes():
                                                  (8, 320, 320, 1024, 1, 1e-5), (2, 1280, 0, 1024, 1, 1e-5),
                                                  (3, 1280, 1280, 64, 1, 1e-5), (5, 320, 0, 256, 1, 1e-5),
                                                  (1, 640, 0, 64, 1, 1e-5), (7, 1280, 0, 16, 0, 1e-5)])
-def test_groupnorm(n, c0, c1, hw, silu, eps):
+@pytest.mark.parametrize("path", ["kernel", "seq"])
+def test_groupnorm(n, c0, c1, hw, silu, eps, path):
     torch.manual_seed(4)
     lib = _lib.load()
+    fn = lib.mvldm_op_groupnorm if path == "kernel" else lib.mvldm_op_seq_groupnorm
     x0 = torch.randn(n, hw, c0).mul(2).add(0.5).to(torch.bfloat16).cuda()
     x1 = torch.randn(n, hw, c1).to(torch.bfloat16).cuda() if c1 else None
     C = c0 + c1
     g, b = torch.randn(C).cuda(), torch.randn(C).cuda()
     out = torch.empty(n, hw, C, dtype=torch.bfloat16, device="cuda")
     scratch = torch.empty(n * 32 * 2 * 64, device="cuda")
-    _lib.check(lib.mvldm_op_groupnorm(stream_ptr(), x0.data_ptr(), c0, x1.data_ptr() if c1 else None, c1, n, hw, 32,
-                                      eps, g.data_ptr(), b.data_ptr(), silu, out.data_ptr(), scratch.data_ptr()))
+    _lib.check(fn(stream_ptr(), x0.data_ptr(), c0, x1.data_ptr() if c1 else None, c1, n, hw, 32,
+                  eps, g.data_ptr(), b.data_ptr(), silu, out.data_ptr(), scratch.data_ptr()))
     xx = torch.cat([x0, x1], -1) if c1 else x0            # groups straddle the concat boundary for 960 / 1920
     ref = F.group_norm(xx.float().permute(0, 2, 1), 32, g, b, eps)
     ref = (F.silu(ref) if silu else ref).permute(0, 2, 1)
     assert rel_err(out.float(), ref) < BF16_TOL
 
 
+def test_groupnorm_large_mean_keeps_precision():
+    """|mean| >> std (real checkpoints, eps 1e-6 in the transformer norms): the sequence kernel's GroupNorm takes the variance
+    in a centred second pass, so it must stay accurate where E[x^2] - mean^2 in fp32 loses every digit"""
+    torch.manual_seed(7)
+    lib = _lib.load()
+    n, c, hw = 4, 320, 256
+    x = (torch.randn(n, hw, c) * 0.05 + 8.0).to(torch.bfloat16).cuda()       # mean / std of the bf16 values ~ 100
+    g, b = torch.randn(c).cuda(), torch.randn(c).cuda()
+    out = torch.empty(n, hw, c, dtype=torch.bfloat16, device="cuda")
+    scratch = torch.empty(n * 32 * 2 * 64, device="cuda")
+    _lib.check(lib.mvldm_op_seq_groupnorm(stream_ptr(), x.data_ptr(), c, None, 0, n, hw, 32, 1e-6, g.data_ptr(),
+                                          b.data_ptr(), 0, out.data_ptr(), scratch.data_ptr()))
+    ref = F.group_norm(x.double().permute(0, 2, 1), 32, g.double(), b.double(), 1e-6).permute(0, 2, 1).float()
+    assert rel_err(out.float(), ref) < BF16_TOL
+
+
+@pytest.mark.parametrize("path", ["kernel", "seq"])
 @pytest.mark.parametrize("c", [320, 640, 1280])
-def test_layernorm(c):
+def test_layernorm(c, path):
     torch.manual_seed(5)
     x = torch.randn(1000, c).mul(3).to(torch.bfloat16).cuda()
     g, b = torch.randn(c).cuda(), torch.randn(c).cuda()
     out = torch.empty_like(x)
-    _lib.check(_lib.load().mvldm_op_layernorm(stream_ptr(), x.data_ptr(), 1000, c, 1e-5, g.data_ptr(), b.data_ptr(),
-                                              out.data_ptr()))
+    fn = _lib.load().mvldm_op_layernorm if path == "kernel" else _lib.load().mvldm_op_seq_layernorm
+    _lib.check(fn(stream_ptr(), x.data_ptr(), 1000, c, 1e-5, g.data_ptr(), b.data_ptr(), out.data_ptr()))
     assert rel_err(out.float(), F.layer_norm(x.float(), (c,), g, b, 1e-5)) < BF16_TOL
 
 
