@@ -28,8 +28,7 @@ typedef struct mvldm_handle_s* mvldm_handle;
 enum { MVLDM_F32 = 0, MVLDM_BF16 = 1, MVLDM_F16 = 2 };
 /* kernel family: tcgen05/TMA kernels (product) or the plain CUDA-core kernels kept as an on-device
  * cross-check for the tests (never selected implicitly) */
-enum { MVLDM_IMPL_TC = 0, MVLDM_IMPL_SIMT = 1, MVLDM_IMPL_TC_GEMM_SIMT_ATTN = 2,
-       MVLDM_IMPL_TC_SEQ = 3 /* mvldm_op_gemm only: the tcgen05 GEMM as an op of the fused sequence kernel */ };
+enum { MVLDM_IMPL_TC = 0, MVLDM_IMPL_SIMT = 1, MVLDM_IMPL_TC_GEMM_SIMT_ATTN = 2 };
 
 /* Replaces: MultiViewUNetCfg + UNet2DModelCfg + SpatialTransformer3DCfg
  * (src/model/denoiser/mvunet.py:22-40, src/model/denoiser/mvdream/attention.py:23-32) and the
@@ -52,9 +51,6 @@ typedef struct {
   int32_t variant;                              /* 0 = A (DownBlock2D/UpBlock2D), 1 = B (SD-2.1 topology) */
   int32_t t2d_heads[MVLDM_MAX_LEVELS];          /* SD-2.1 attention_head_dim [5,10,20,20] (= heads; head dim 64) */
   int32_t cross_attention_dim;                  /* 1024 */
-  /* Ops on at most this many tokens (B*V*h*w) run inside the fused persistent sequence kernel (grid barriers between ops,
-   * weights prefetched across ops), larger ones as stand-alone kernels; -1 = fuse everything, 0 = nothing. */
-  int32_t fuse_max_tokens;
 } mvldm_config;
 
 const char* mvldm_last_error(void);
@@ -201,14 +197,6 @@ int mvldm_op_attention_kv(void* stream, const void* q, int ld_q, int q_col0, con
  * environment; out[slot*512 + tile], slots 0-2 softmax thread (wait S, got S, P handed over), 3-5 MMA thread
  * (got P, PV issued, next QK issued). */
 int mvldm_debug_attn_trace(int64_t* out, int n);
-/* Debug / measurement: one fused sequence launch of `n_ops` empty ops, i.e. n_ops - 1 grid barriers and nothing else
- * (tools/seq_barrier_bench.py: the cost of an op boundary inside the sequence kernel). */
-int mvldm_debug_seq_empty_ops(void* stream, int n_ops);
-/* Debug: every following sequence launch writes its barrier timeline into `device_buffer` ([barrier][CTA][4] int64:
- * %globaltimer ns at barrier entry of thread 0, when the whole CTA has arrived, when the barrier released it, clock64);
- * NULL switches it off.  The buffer must hold barriers x CTAs x 32 bytes of the longest launch (tools/seq_trace.py). */
-int mvldm_debug_seq_trace(void* device_buffer);
-
 /* GroupNorm (+SiLU) over NHWC bf16, optionally over the channel concat of two sources
  * (torch.cat at mvunet.py:176 + ResnetBlock2D.norm1): out bf16 [n_img, hw, c0+c1]. */
 int mvldm_op_groupnorm(void* stream, const void* x0, int c0, const void* x1, int c1, int n_img, int hw,
@@ -216,13 +204,6 @@ int mvldm_op_groupnorm(void* stream, const void* x0, int c0, const void* x1, int
                        float* scratch /* >= n_img*groups*2*64 floats */);
 int mvldm_op_layernorm(void* stream, const void* x, int rows, int c, float eps, const float* gamma,
                        const float* beta, void* out);
-/* The same two ops executed as ops of the fused sequence kernel (the path mvldm_config.fuse_max_tokens selects). */
-int mvldm_op_seq_groupnorm(void* stream, const void* x0, int c0, const void* x1, int c1, int n_img, int hw,
-                           int groups, float eps, const float* gamma, const float* beta, int silu, void* out,
-                           float* scratch /* >= n_img*groups*2*64 floats */);
-int mvldm_op_seq_layernorm(void* stream, const void* x, int rows, int c, float eps, const float* gamma,
-                           const float* beta, void* out);
-
 #ifdef __cplusplus
 }
 #endif

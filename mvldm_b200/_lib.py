@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libmvldm_b200.so")
 MVLDM_MAX_LEVELS = 4
 MVLDM_MAX_SEGS = 3
 F32, BF16, F16 = 0, 1, 2
-IMPL_TC, IMPL_SIMT, IMPL_TC_GEMM_SIMT_ATTN, IMPL_TC_SEQ = 0, 1, 2, 3
+IMPL_TC, IMPL_SIMT, IMPL_TC_GEMM_SIMT_ATTN = 0, 1, 2
 
 
 class Config(Structure):
@@ -25,7 +25,6 @@ class Config(Structure):
         ("norm_groups", c_int32), ("num_heads", c_int32), ("max_attn_res", c_int32), ("impl", c_int32),
         ("use_cuda_graph", c_int32),
         ("variant", c_int32), ("t2d_heads", c_int32 * MVLDM_MAX_LEVELS), ("cross_attention_dim", c_int32),
-        ("fuse_max_tokens", c_int32),
     ]
 
 
@@ -71,14 +70,9 @@ SYMBOLS = {
     "mvldm_op_gemm": (c_int, [c_void_p, c_int, POINTER(GemmDesc)]),
     "mvldm_op_attention": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int]),
     "mvldm_debug_attn_trace": (c_int, [POINTER(c_int64), c_int]),
-    "mvldm_debug_seq_empty_ops": (c_int, [c_void_p, c_int]),
-    "mvldm_debug_seq_trace": (c_int, [c_void_p]),
     "mvldm_op_groupnorm": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
                                    c_void_p, c_int, c_void_p, c_void_p]),
     "mvldm_op_layernorm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
-    "mvldm_op_seq_groupnorm": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
-                                       c_void_p, c_int, c_void_p, c_void_p]),
-    "mvldm_op_seq_layernorm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
 }
 
 KV_EXCHANGE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p)

@@ -92,36 +92,29 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 #endif
 
 // ---- kernels (host launchers) -----------------------------------------------------------------
-// seq.cu: the fused sequence kernel; these run ONE op through it (C ABI mvldm_op_* / tests)
+int sm_count();  // SMs of the current device
+// gemm_simt.cu / gemm_tc.cu
+void gemm_simt(cudaStream_t s, const mvldm_gemm_desc& d);
 // workspace: fp32 split-K scratch (gemm_tc_workspace_bytes(d) bytes, zero-initialised) or NULL/0 to force a single pass
 size_t gemm_tc_workspace_bytes(const mvldm_gemm_desc& d);
 void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t workspace_bytes);
-void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, int n_img, int hw, int groups,
-               float eps, const float* gamma, const float* beta, bool silu, bf16* out, float* scratch);
-size_t groupnorm_scratch_floats(int n_img, int groups);
-void layernorm(cudaStream_t s, const bf16* x, int rows, int c, float eps, const float* gamma, const float* beta,
-               bf16* out);
-// gemm_tc.cu / norm_classic.cu: the same ops as stand-alone kernels (one launch each); the forward picks per resolution
-size_t gemm_classic_workspace_bytes(const mvldm_gemm_desc& d);
-void gemm_classic(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t workspace_bytes);
-void groupnorm_classic(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, int n_img, int hw, int groups,
-                       float eps, const float* gamma, const float* beta, bool silu, bf16* out, float* scratch);
-size_t groupnorm_classic_scratch_floats(int n_img, int groups);
-void groupnorm_classic_init();  // one-time kernel attributes (call outside stream capture)
-void layernorm_classic(cudaStream_t s, const bf16* x, int rows, int c, float eps, const float* gamma, const float* beta,
-                       bf16* out);
-void upsample_classic(cudaStream_t s, const bf16* x, int n_img, int h, int w, int c, bf16* out);
-void im2col_classic(cudaStream_t s, const float* latents, int n_img, int cin, int h, int w, int kpad, bf16* out);
-void sinusoid_classic(cudaStream_t s, const int64_t* t, int n, int dim, bf16* out);
-// gemm_simt.cu / attn_simt.cu: CUDA-core cross-checks (tests only)
-void gemm_simt(cudaStream_t s, const mvldm_gemm_desc& d);
+// attn_simt.cu / attn_tc.cu
 void attention_simt(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, int heads, int d, int dpad);
-// attn_tc.cu
 void attention_trace_read(long long* host, int n);  // debug timeline of CTA (0,0), see MVLDM_ATTN_TRACE
 void attention_tc(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, int heads, int d, int dpad);
 // queries and keys/values from different buffers / of different lengths (view-group sharding: local Q, gathered K/V)
 void attention_tc_kv(cudaStream_t s, const bf16* q, int ld_q, int q_col0, const bf16* kv, int ld_kv, int k_col0, int v_col0,
                      bf16* out, int batches, int seq_q, int seq_kv, int heads, int d, int dpad);
+// norm.cu
+void im2col_input(cudaStream_t s, const float* latents, int n_img, int cin, int h, int w, int kpad, bf16* out);
+void timestep_sinusoid_bf16(cudaStream_t s, const int64_t* t, int n, int dim, bf16* out);
+void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, int n_img, int hw, int groups,
+               float eps, const float* gamma, const float* beta, bool silu, bf16* out, float* scratch);
+size_t groupnorm_scratch_floats(int n_img, int groups);
+void groupnorm_init();  // one-time kernel attributes (call outside stream capture)
+void layernorm(cudaStream_t s, const bf16* x, int rows, int c, float eps, const float* gamma, const float* beta,
+               bf16* out);
+void upsample_nearest2x(cudaStream_t s, const bf16* x, int n_img, int h, int w, int c, bf16* out);
 
 // elementwise.cu
 void nhwc_to_nchw_f32(cudaStream_t s, const bf16* x, int n_img, int hw, int c, float* out);

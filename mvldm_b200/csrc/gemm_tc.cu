@@ -1,5 +1,4 @@
-// Stand-alone (one launch per GEMM) tcgen05 / TMEM / TMA implicit-GEMM for sm_100a - the forward uses it at the resolutions
-// where a launch per op beats the fused sequence kernel (seq.cu, same algorithm inside one persistent launch): conv3x3 (stride 1/2), 1x1 conv and Linear over bf16 NHWC
+// tcgen05 / TMEM / TMA implicit-GEMM for sm_100a: conv3x3 (stride 1/2), 1x1 conv and Linear over bf16 NHWC
 // activations, fp32 accumulation in tensor memory, fused epilogues (bias, per-image time-embedding row,
 // residual add, GEGLU, fp32-NCHW head output).
 //
@@ -19,12 +18,41 @@
 #include <cudaTypedefs.h>
 
 #include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
-#include "seq.cuh"
 #include "tc_common.cuh"
 
 namespace mvldm {
+
+CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                           const uint32_t* box, const uint32_t* elem_strides) {
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  });
+  MV_CHECK(encode != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  CUtensorMap m;
+  CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                      strides_bytes, box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MV_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return m;
+}
+
+// SM count of the current device (one persistent CTA per SM)
+int sm_count() {
+  static int sms[kMaxDevices] = {};
+  int dev = 0;
+  MV_CUDA(cudaGetDevice(&dev));
+  MV_CHECK(dev >= 0 && dev < kMaxDevices, "device index out of range");
+  if (sms[dev] == 0) MV_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
+  return sms[dev];
+}
 
 namespace {
 
@@ -535,7 +563,7 @@ void launch(cudaStream_t s, const TcParams& p, int splits) {
   if (first_use_on_device(configured)) {
     MV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
-  const int num_sms = seq_grid();  // SM count of the current device
+  const int num_sms = sm_count();  // SM count of the current device
   TcParams q = p;
   q.mt = ceil_div(p.M, BM);
   q.nt = p.N / BN;
@@ -578,7 +606,7 @@ TileChoice pick_tiles(const mvldm_gemm_desc& d) {
       if (force_sp && atoi(force_sp) != sp) continue;
       const int st_per = ceil_div(num_steps, sp), splits = ceil_div(num_steps, st_per);
       const double ctas = (double)mt * (d.n / bn) * splits;
-      const double per_sm = std::ceil(ctas / (double)seq_grid());  // work items the busiest SM runs
+      const double per_sm = std::ceil(ctas / (double)sm_count());  // work items the busiest SM runs
       // measured (tools/micro/tma_ingest.cu): ~4.3 TMA boxes/us per SM whatever their size, <= ~150 GB/s per SM
       const double step_bytes = kb_per_step * (A_BYTES + bn * 128.0);
       const double t_step = std::max(std::max(2.0 / 4.3e6, step_bytes / 150e9), kb_per_step * 4.0 * (bn / 2.0) / 1.9e9);
@@ -601,13 +629,13 @@ TileChoice pick_tiles(const mvldm_gemm_desc& d) {
 
 constexpr size_t kCounterBytes = 2 * 4096 * sizeof(int);  // arrive/done counters live at the head of the workspace
 
-size_t gemm_classic_workspace_bytes(const mvldm_gemm_desc& d) {
+size_t gemm_tc_workspace_bytes(const mvldm_gemm_desc& d) {
   if (count_steps(d) == 0) return 0;
   const int splits = pick_tiles(d).splits;
   return splits > 1 ? kCounterBytes + (size_t)splits * d.n_img * d.oh * d.ow * d.n * sizeof(float) : 0;
 }
 
-void gemm_classic(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t workspace_bytes) {
+void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t workspace_bytes) {
   TcParams p{};
   const int hw = d.oh * d.ow;
   p.M = d.n_img * hw;
@@ -671,7 +699,7 @@ void gemm_classic(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, siz
     }
   }
   int splits = tile.splits;
-  if (splits > 1 && gemm_classic_workspace_bytes(d) > workspace_bytes) splits = 1;  // no scratch: plain single-pass GEMM
+  if (splits > 1 && gemm_tc_workspace_bytes(d) > workspace_bytes) splits = 1;  // no scratch: plain single-pass GEMM
   p.steps_per_split = ceil_div(p.num_steps, splits);
   splits = ceil_div(p.num_steps, p.steps_per_split);
   p.partial = splits > 1 ? reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kCounterBytes) : nullptr;
@@ -679,7 +707,7 @@ void gemm_classic(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, siz
   const int work = ceil_div(p.M, BM) * (d.n / BN) * splits;
   // (one CTA per SM: shared memory; the kernel is launched with min(work, #SMs) CTAs, so work <= #SMs means every split
   // of every tile has its own resident CTA on an otherwise idle device; more work takes the two-pass reduction)
-  const bool fused = splits > 1 && work <= seq_grid() && ceil_div(p.M, BM) * (d.n / BN) <= 4096;
+  const bool fused = splits > 1 && work <= sm_count() && ceil_div(p.M, BM) * (d.n / BN) <= 4096;
   p.counters = fused ? reinterpret_cast<int*>(workspace) : nullptr;
   {
     static const int opt = [] {

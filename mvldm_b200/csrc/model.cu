@@ -13,7 +13,6 @@
 #include <vector>
 
 #include "common.cuh"
-#include "seq.cuh"
 
 namespace mvldm {
 
@@ -92,27 +91,25 @@ struct Arena {
   }
 };
 
-// One recorded forward for a batch shape: the launch list (fused sequence launches cut at the attention kernels), the device
-// copy of the op descriptors, the activation arena they point into and the CUDA graph of the whole list.
+// One recorded forward for a batch shape: the launch list (every kernel with its arguments bound to the plan's buffers),
+// the activation arena those point into and the CUDA graph of the whole list.
 struct TapRec {
   Act a;
 };
-struct OpMeta {  // what an op is, for the per-op timing report
+struct OpMeta {  // what a launch is, for the per-op timing report
   const char* cat;
   std::string what;
   double flops, bytes;
 };
 struct Step {
-  enum Kind { SEQ, ATTN, ATTN_SHARDED, GEMM_SIMT, GEMM_CLASSIC, GEMM_SINGLE, GN_CLASSIC, LN_CLASSIC, UPSAMPLE_CLASSIC, IM2COL_CLASSIC,
-              SINUSOID_CLASSIC } kind = SEQ;
-  int op_begin = 0, op_end = 0;  // SEQ: ops[op_begin, op_end)
+  enum Kind { GEMM, GEMM_SIMT, ATTN, ATTN_SHARDED, GN, LN, UPSAMPLE, IM2COL, SINUSOID } kind = GEMM;
+  mvldm_gemm_desc gemm{};  // GEMM / GEMM_SIMT
   // ATTN / ATTN_SHARDED
   const bf16* qkv = nullptr;
   bf16* out = nullptr;
   int batches = 0, seq = 0, heads = 0, d = 0, dpad = 0, seq_local = 0;
   bool simt = false;
-  mvldm_gemm_desc gemm{};  // GEMM_SIMT / GEMM_CLASSIC
-  // *_CLASSIC elementwise steps
+  // elementwise steps
   const void *x0 = nullptr, *x1 = nullptr;
   const float *gamma = nullptr, *beta = nullptr;
   void* dst = nullptr;
@@ -127,12 +124,8 @@ struct Plan {
   DevBuf arena_mem;
   size_t arena_bytes = 0;
   DevBuf in_latents, in_t, out_eps, splitk;
-  std::vector<SeqOp> ops;
-  std::vector<SeqOp> single_ops;  // GEMMs launched one per kernel (descriptor passed by value)
-  std::vector<OpMeta> op_meta;
   std::vector<Step> steps;
   std::map<std::string, TapRec> taps;  // named intermediate activations (plans recorded with taps enabled keep them all alive)
-  DevBuf dev_ops, sync_words, timing;
   int launches = 0;  // kernels one execution launches
   uint64_t last_use = 0;
   cudaGraphExec_t graph = nullptr;
@@ -177,9 +170,7 @@ struct mvldm_handle_s {
   bool taps_enabled = false;
   Plan* last_plan = nullptr;
 
-  // ---- profiling (mvldm_set_profiling): the launch list runs eagerly with a CUDA-event pair around every launch, and
-  // the sequence kernel stamps %globaltimer / clock64 at every op barrier, so each op inside a fused launch gets its
-  // own in-situ duration ----
+  // ---- profiling (mvldm_set_profiling): the launch list runs eagerly with a CUDA-event pair around every launch ----
   bool profiling = false;
   std::vector<cudaEvent_t> event_pool;
   std::string prof_json;
@@ -191,7 +182,6 @@ struct mvldm_handle_s {
   Arena arena;
   bool dry = true;       // measuring pass: arena offsets and split-K scratch only, nothing is recorded
   Plan* rec = nullptr;   // plan being recorded
-  int seq_open = -1;     // first op of the sequence launch being assembled, or -1
   uint64_t use_clock = 0;
   // view-group sharding (mvldm_forward_sharded): local Q against all-gathered K/V in the joint attention
   bool sharded = false;
@@ -575,81 +565,21 @@ struct mvldm_handle_s {
     return s;
   }
   // ---- recording: every op of the forward lands in the plan's launch list ----
-  void push_op(const SeqOp& op, const char* cat, const std::string& what, double flops, double bytes) {
-    if (seq_open < 0) seq_open = (int)rec->ops.size();
-    rec->ops.push_back(op);
-    rec->op_meta.push_back(OpMeta{cat, what, flops, bytes});
-  }
-  void flush_seq() {  // close the sequence launch under assembly (an attention / callback step follows, or the end)
-    if (seq_open < 0) return;
-    Step st;
-    st.kind = Step::SEQ;
-    st.op_begin = seq_open;
-    st.op_end = (int)rec->ops.size();
-    rec->steps.push_back(st);
-    seq_open = -1;
-  }
-  // Which ops run inside the fused sequence kernel: those on at most `fuse_max_tokens` tokens (the small, latency-bound
-  // levels, where an op boundary inside one persistent launch is cheaper than a kernel boundary and the weight stream
-  // continues across ops); larger ones run as stand-alone kernels whose multi-CTA-per-SM elementwise passes are faster.
-  // -1 = everything fused, 0 = nothing.  MVLDM_FUSE_MAX_TOKENS overrides the config (measurement sweeps).
-  bool fuse_op(int64_t tokens) const {
-    static const long env = [] {
-      const char* e = getenv("MVLDM_FUSE_MAX_TOKENS");
-      return e ? atol(e) : -2;
-    }();
-    const long lim = env != -2 ? env : (long)cfg.fuse_max_tokens;
-    return lim < 0 || tokens <= lim;
-  }
-  void push_step(const Step& st) {
-    flush_seq();
-    rec->steps.push_back(st);
-  }
+  void push_step(const Step& st) { rec->steps.push_back(st); }
   void run_gemm(mvldm_gemm_desc& d, double algo_flops = -1.0) {
     const double M = (double)d.n_img * d.oh * d.ow;
     const char* cat = d.nseg > 0 && d.seg[0].ntaps == 9 ? "gemm_conv3x3" : "gemm_linear";
-    const bool fused = fuse_op((int64_t)M);
     if (dry) {
-      if (cfg.impl != MVLDM_IMPL_SIMT)
-        splitk_need = std::max(splitk_need, std::max(seq_gemm_workspace_bytes(d), fused ? (size_t)0 : gemm_classic_workspace_bytes(d)));
+      if (cfg.impl != MVLDM_IMPL_SIMT) splitk_need = std::max(splitk_need, gemm_tc_workspace_bytes(d));
       return;
     }
-    const std::string what = "M" + std::to_string((long long)M) + " N" + std::to_string(d.n) + " K" + std::to_string(d.k);
-    const double flops = algo_flops >= 0 ? algo_flops : 2.0 * M * d.n * d.k;
-    const double bytes = 2.0 * ((double)d.n * d.k + M * d.n * (d.mode == 1 ? 0.5 : 1.0));
-    if (cfg.impl == MVLDM_IMPL_SIMT) {
-      flush_seq();
-      Step st;
-      st.kind = Step::GEMM_SIMT;
-      st.gemm = d;
-      st.meta = OpMeta{cat, what, flops, bytes};
-      rec->steps.push_back(st);
-      return;
-    }
-    if (!fused) {
-      Step st;
-      st.kind = Step::GEMM_CLASSIC;
-      st.gemm = d;
-      st.meta = OpMeta{cat, what, flops, bytes};
-      static const bool single = [] {
-        const char* e = getenv("MVLDM_GEMM_KERNEL");  // 1: the sequence kernel's GEMM as a stand-alone launch (measured slower)
-        return e && atoi(e) != 0;
-      }();
-      if (single) {  // the sequence kernel's GEMM as its own launch (descriptor in parameter space)
-        SeqOp op, red;
-        if (!seq_plan_gemm(d, splitk_ws, splitk_bytes, op, red)) {  // (a two-pass split-K stays with the stand-alone kernels)
-          st.kind = Step::GEMM_SINGLE;
-          st.op_begin = (int)rec->single_ops.size();
-          rec->single_ops.push_back(op);
-        }
-      }
-      push_step(st);
-      return;
-    }
-    SeqOp op, red;
-    const bool need_reduce = seq_plan_gemm(d, splitk_ws, splitk_bytes, op, red);
-    push_op(op, cat, what, flops, bytes);
-    if (need_reduce) push_op(red, "splitk_reduce", what, 0.0, 0.0);
+    Step st;
+    st.kind = cfg.impl == MVLDM_IMPL_SIMT ? Step::GEMM_SIMT : Step::GEMM;
+    st.gemm = d;
+    st.meta = OpMeta{cat, "M" + std::to_string((long long)M) + " N" + std::to_string(d.n) + " K" + std::to_string(d.k),
+                     algo_flops >= 0 ? algo_flops : 2.0 * M * d.n * d.k,
+                     2.0 * ((double)d.n * d.k + M * d.n * (d.mode == 1 ? 0.5 : 1.0))};
+    push_step(st);
   }
   // out = A-segments x W^T (+bias +rowvec +residual), bf16 NHWC
   void gemm(std::initializer_list<mvldm_aseg> segs, const Packed& w, const Act& out, const float* rowvec = nullptr,
@@ -665,42 +595,28 @@ struct mvldm_handle_s {
     run_gemm(d, algo_flops);
   }
   void gn(const Act& x0, const Act* x1, const float* g, const float* b, float eps, bool silu, const Act& out) {
-    float* scratch = new_f32(seq_groupnorm_scratch_floats(x0.n, out.c, cfg.norm_groups));
+    float* scratch = new_f32(groupnorm_scratch_floats(x0.n, cfg.norm_groups));
     if (dry) return;
-    const std::string what = "tokens" + std::to_string(x0.tokens()) + " C" + std::to_string(out.c);
-    if (!fuse_op(x0.tokens())) {
-      Step st;
-      st.kind = Step::GN_CLASSIC;
-      st.x0 = x0.p; st.c0 = x0.c; st.x1 = x1 ? x1->p : nullptr; st.c1 = x1 ? x1->c : 0;
-      st.n_img = x0.n; st.hw = x0.h * x0.w; st.groups = cfg.norm_groups; st.eps = eps; st.gamma = g; st.beta = b;
-      st.silu = silu ? 1 : 0; st.dst = out.p; st.scratch = scratch;
-      st.meta = OpMeta{"groupnorm", what, 0.0, 4.0 * (double)out.tokens() * out.c};
-      push_step(st);
-      return;
-    }
-    SeqOp op;
-    seq_plan_groupnorm(x0.p, x0.c, x1 ? x1->p : nullptr, x1 ? x1->c : 0, x0.n, x0.h * x0.w, cfg.norm_groups, eps, g, b, silu,
-                       out.p, scratch, seq_grid(), op);
-    push_op(op, "groupnorm", what, 0.0, 4.0 * (double)out.tokens() * out.c);
+    Step st;
+    st.kind = Step::GN;
+    st.x0 = x0.p; st.c0 = x0.c; st.x1 = x1 ? x1->p : nullptr; st.c1 = x1 ? x1->c : 0;
+    st.n_img = x0.n; st.hw = x0.h * x0.w; st.groups = cfg.norm_groups; st.eps = eps; st.gamma = g; st.beta = b;
+    st.silu = silu ? 1 : 0; st.dst = out.p; st.scratch = scratch;
+    st.meta = OpMeta{"groupnorm", "tokens" + std::to_string(x0.tokens()) + " C" + std::to_string(out.c), 0.0,
+                     4.0 * (double)out.tokens() * out.c};
+    push_step(st);
   }
   void ln(const Act& x, const float* g, const float* b, const Act& out) {
     if (dry) return;
-    const std::string what = "tokens" + std::to_string(x.tokens()) + " C" + std::to_string(x.c);
-    if (!fuse_op(x.tokens())) {
-      Step st;
-      st.kind = Step::LN_CLASSIC;
-      st.x0 = x.p; st.n_img = (int)x.tokens(); st.c0 = x.c; st.eps = 1e-5f; st.gamma = g; st.beta = b; st.dst = out.p;
-      st.meta = OpMeta{"layernorm", what, 0.0, 4.0 * (double)x.tokens() * x.c};
-      push_step(st);
-      return;
-    }
-    SeqOp op;
-    seq_plan_layernorm(x.p, (int)x.tokens(), x.c, 1e-5f, g, b, out.p, op);
-    push_op(op, "layernorm", what, 0.0, 4.0 * (double)x.tokens() * x.c);
+    Step st;
+    st.kind = Step::LN;
+    st.x0 = x.p; st.n_img = (int)x.tokens(); st.c0 = x.c; st.eps = 1e-5f; st.gamma = g; st.beta = b; st.dst = out.p;
+    st.meta = OpMeta{"layernorm", "tokens" + std::to_string(x.tokens()) + " C" + std::to_string(x.c), 0.0,
+                     4.0 * (double)x.tokens() * x.c};
+    push_step(st);
   }
   void attn(const Act& qkv, const Act& out, int batches, int seq, const MvW& m) {
     if (dry) return;
-    flush_seq();
     Step st;
     st.kind = Step::ATTN;
     st.qkv = qkv.p; st.out = out.p; st.batches = batches; st.seq = seq; st.heads = m.heads; st.d = m.d; st.dpad = m.dpad;
@@ -716,7 +632,6 @@ struct mvldm_handle_s {
   void joint_attention_sharded(const Act& qkv, const Act& out, int seq_local, const MvW& m) {
     if (dry) return;
     const int world = v_total / (int)(qkv.n);
-    flush_seq();
     Step st;
     st.kind = Step::ATTN_SHARDED;
     st.qkv = qkv.p; st.out = out.p; st.batches = 1; st.seq = seq_local * world; st.seq_local = seq_local;
@@ -853,17 +768,11 @@ struct mvldm_handle_s {
     Act e2 = new_act(n, 1, 1, temb_dim);
     float* temb = new_f32((size_t)n * temb_total);
     if (!dry) {
-      if (fuse_op(n)) {
-        SeqOp op;
-        seq_plan_sinusoid(tsteps, n, boc[0], sinus.p, op);
-        push_op(op, "time_embedding", "sinusoid rows" + std::to_string(n), 0.0, 0.0);
-      } else {
-        Step st;
-        st.kind = Step::SINUSOID_CLASSIC;
-        st.x0 = tsteps; st.n_img = n; st.c0 = boc[0]; st.dst = sinus.p;
-        st.meta = OpMeta{"time_embedding", "sinusoid rows" + std::to_string(n), 0.0, 0.0};
-        push_step(st);
-      }
+      Step st;
+      st.kind = Step::SINUSOID;
+      st.x0 = tsteps; st.n_img = n; st.c0 = boc[0]; st.dst = sinus.p;
+      st.meta = OpMeta{"time_embedding", "sinusoid rows" + std::to_string(n), 0.0, 0.0};
+      push_step(st);
     }
     gemm({seg_1x1(sinus)}, time1, e1, nullptr, 0, nullptr, 3);
     gemm({seg_1x1(e1)}, time2, e2, nullptr, 0, nullptr, 3);  // SiLU(emb): every consumer (ResnetBlock2D) applies it first
@@ -880,18 +789,11 @@ struct mvldm_handle_s {
     // ---- conv_in on the im2col'd fp32 input
     Act col = new_act(n, Hh, Ww, kpad_in);
     if (!dry) {
-      const double bytes = (double)col.tokens() * (kpad_in * 2 + cfg.in_channels * 4);
-      if (fuse_op(col.tokens()) && !getenv("MVLDM_DEBUG_CLASSIC_IM2COL")) {
-        SeqOp op;
-        seq_plan_im2col(latents, n, cfg.in_channels, Hh, Ww, kpad_in, col.p, op);
-        push_op(op, "input_im2col", "", 0.0, bytes);
-      } else {
-        Step st;
-        st.kind = Step::IM2COL_CLASSIC;
-        st.x0 = latents; st.n_img = n; st.c0 = cfg.in_channels; st.h = Hh; st.w = Ww; st.aux = kpad_in; st.dst = col.p;
-        st.meta = OpMeta{"input_im2col", "", 0.0, bytes};
-        push_step(st);
-      }
+      Step st;
+      st.kind = Step::IM2COL;
+      st.x0 = latents; st.n_img = n; st.c0 = cfg.in_channels; st.h = Hh; st.w = Ww; st.aux = kpad_in; st.dst = col.p;
+      st.meta = OpMeta{"input_im2col", "", 0.0, (double)col.tokens() * (kpad_in * 2 + cfg.in_channels * 4)};
+      push_step(st);
     }
     Act x = new_act(n, Hh, Ww, boc[0]);
     gemm({seg_1x1(col)}, conv_in, x, nullptr, 0, nullptr, 0, 2.0 * (double)x.tokens() * boc[0] * 9 * cfg.in_channels);
@@ -941,17 +843,11 @@ struct mvldm_handle_s {
       if (l != L - 1) {
         Act u = new_act(n, x.h * 2, x.w * 2, x.c);
         if (!dry) {
-          if (fuse_op(u.tokens())) {
-            SeqOp op;
-            seq_plan_upsample(x.p, n, x.h, x.w, x.c, u.p, op);
-            push_op(op, "upsample", "", 0.0, 2.5 * (double)u.tokens() * u.c);
-          } else {
-            Step st;
-            st.kind = Step::UPSAMPLE_CLASSIC;
-            st.x0 = x.p; st.n_img = n; st.h = x.h; st.w = x.w; st.c0 = x.c; st.dst = u.p;
-            st.meta = OpMeta{"upsample", "", 0.0, 2.5 * (double)u.tokens() * u.c};
-            push_step(st);
-          }
+          Step st;
+          st.kind = Step::UPSAMPLE;
+          st.x0 = x.p; st.n_img = n; st.h = x.h; st.w = x.w; st.c0 = x.c; st.dst = u.p;
+          st.meta = OpMeta{"upsample", "", 0.0, 2.5 * (double)u.tokens() * u.c};
+          push_step(st);
         }
         Act y = new_act(n, u.h, u.w, u.c);
         gemm({seg_conv3x3(u)}, up_conv[l], y);
@@ -999,8 +895,7 @@ struct mvldm_handle_s {
       if (last_plan == victim->second.get()) last_plan = nullptr;
       plans.erase(victim);
     }
-    seq_configure();
-    groupnorm_classic_init();
+    groupnorm_init();
     std::unique_ptr<Plan> p(new Plan());
     p->scene_views = sv; p->H = H; p->W = W;
     p->last_use = ++use_clock;
@@ -1027,10 +922,8 @@ struct mvldm_handle_s {
     splitk_ws = p->splitk.p;
     splitk_bytes = p->splitk.bytes;
     rec = p.get();
-    seq_open = -1;
     try {
       run((const float*)p->in_latents.p, (const int64_t*)p->in_t.p, sv, H, W, (float*)p->out_eps.p);
-      flush_seq();
     } catch (...) {
       rec = nullptr;
       sharded = false;
@@ -1038,42 +931,24 @@ struct mvldm_handle_s {
     }
     rec = nullptr;
     sharded = false;
-    p->dev_ops.alloc(std::max<size_t>(1, p->ops.size()) * sizeof(SeqOp));
-    size_t stamps = 0;
-    seq_link_prefetch(p->ops.data(), (int)p->ops.size(), reinterpret_cast<const SeqOp*>(p->dev_ops.p));
-    seq_link_prefetch(p->single_ops.data(), (int)p->single_ops.size(), nullptr);
-    for (const Step& st : p->steps) {
-      if (st.kind != Step::SEQ) continue;
-      seq_link_launch(p->ops.data() + st.op_begin, st.op_end - st.op_begin);
-      stamps += 2 * (size_t)(st.op_end - st.op_begin) + 2;
-    }
-    if (!p->ops.empty())
-      MV_CUDA(cudaMemcpy(p->dev_ops.p, p->ops.data(), p->ops.size() * sizeof(SeqOp), cudaMemcpyHostToDevice));
-    p->sync_words.alloc(2 * sizeof(unsigned));
-    MV_CUDA(cudaMemset(p->sync_words.p, 0, 2 * sizeof(unsigned)));
-    p->timing.alloc(stamps * 2 * sizeof(long long));
-    p->launches = 0;
-    for (const Step& st : p->steps) p->launches += st.kind == Step::ATTN_SHARDED ? 2 : 1;
+    p->launches = (int)p->steps.size();
     Plan& ref = *p;
     plans[key] = std::move(p);
     return ref;
   }
 
-  static int op_barriers(const SeqOp& o) { return o.c.type == SEQ_GN && o.c.gn.ps > 1 ? 1 : 0; }
-
   // issue the plan's launches on `s` (eagerly, or into a stream capture); with `events` every launch is bracketed
   void execute(Plan& p, cudaStream_t s, std::vector<cudaEvent_t>* events) {
-    long long* stamp = events ? reinterpret_cast<long long*>(p.timing.p) : nullptr;
     size_t ev = 0;
     for (const Step& st : p.steps) {
       if (events) MV_CUDA(cudaEventRecord((*events)[ev++], s));
       switch (st.kind) {
-        case Step::SEQ: {
-          seq_launch(s, reinterpret_cast<const SeqOp*>(p.dev_ops.p) + st.op_begin, st.op_end - st.op_begin,
-                     reinterpret_cast<unsigned*>(p.sync_words.p), stamp);
-          if (stamp) stamp += 2 * (2 * (size_t)(st.op_end - st.op_begin) + 2);
+        case Step::GEMM:
+          gemm_tc(s, st.gemm, p.splitk.p, p.splitk.bytes);
           break;
-        }
+        case Step::GEMM_SIMT:
+          gemm_simt(s, st.gemm);
+          break;
         case Step::ATTN:
           if (st.simt) attention_simt(s, st.qkv, st.out, st.batches, st.seq, st.heads, st.d, st.dpad);
           else attention_tc(s, st.qkv, st.out, st.batches, st.seq, st.heads, st.d, st.dpad);
@@ -1091,30 +966,21 @@ struct mvldm_handle_s {
                           st.seq, st.heads, st.d, st.dpad);
           break;
         }
-        case Step::GEMM_SIMT:
-          gemm_simt(s, st.gemm);
+        case Step::GN:
+          groupnorm(s, (const bf16*)st.x0, st.c0, (const bf16*)st.x1, st.c1, st.n_img, st.hw, st.groups, st.eps, st.gamma,
+                    st.beta, st.silu != 0, (bf16*)st.dst, st.scratch);
           break;
-        case Step::GEMM_CLASSIC:
-          gemm_classic(s, st.gemm, p.splitk.p, p.splitk.bytes);
+        case Step::LN:
+          layernorm(s, (const bf16*)st.x0, st.n_img, st.c0, st.eps, st.gamma, st.beta, (bf16*)st.dst);
           break;
-        case Step::GEMM_SINGLE:
-          seq_launch_gemm(s, p.single_ops[st.op_begin]);
+        case Step::UPSAMPLE:
+          upsample_nearest2x(s, (const bf16*)st.x0, st.n_img, st.h, st.w, st.c0, (bf16*)st.dst);
           break;
-        case Step::GN_CLASSIC:
-          groupnorm_classic(s, (const bf16*)st.x0, st.c0, (const bf16*)st.x1, st.c1, st.n_img, st.hw, st.groups, st.eps, st.gamma,
-                            st.beta, st.silu != 0, (bf16*)st.dst, st.scratch);
+        case Step::IM2COL:
+          im2col_input(s, (const float*)st.x0, st.n_img, st.c0, st.h, st.w, st.aux, (bf16*)st.dst);
           break;
-        case Step::LN_CLASSIC:
-          layernorm_classic(s, (const bf16*)st.x0, st.n_img, st.c0, st.eps, st.gamma, st.beta, (bf16*)st.dst);
-          break;
-        case Step::UPSAMPLE_CLASSIC:
-          upsample_classic(s, (const bf16*)st.x0, st.n_img, st.h, st.w, st.c0, (bf16*)st.dst);
-          break;
-        case Step::IM2COL_CLASSIC:
-          im2col_classic(s, (const float*)st.x0, st.n_img, st.c0, st.h, st.w, st.aux, (bf16*)st.dst);
-          break;
-        case Step::SINUSOID_CLASSIC:
-          sinusoid_classic(s, (const int64_t*)st.x0, st.n_img, st.c0, (bf16*)st.dst);
+        case Step::SINUSOID:
+          timestep_sinusoid_bf16(s, (const int64_t*)st.x0, st.n_img, st.c0, (bf16*)st.dst);
           break;
       }
       if (events) MV_CUDA(cudaEventRecord((*events)[ev++], s));
@@ -1147,7 +1013,6 @@ struct mvldm_handle_s {
           MV_CUDA(cudaEventCreate(&e));
           event_pool.push_back(e);
         }
-        MV_CUDA(cudaMemsetAsync(p.timing.p, 0, p.timing.bytes, s));
         g_launch_count = 0;
         execute(p, s, &event_pool);
         p.launches = g_launch_count;
@@ -1183,65 +1048,31 @@ struct mvldm_handle_s {
   }
 };
 
-// Folds the timings of the last profiled forward into a JSON string (synchronises the device): every launch has a
-// CUDA-event pair; the ops inside a sequence launch split its event time by their in-kernel clock64 stamps.
+// Folds the event pairs of the last profiled forward into a JSON string (synchronises the device).
 static const char* profile_report(mvldm_handle_s* h) {
   MV_CUDA(cudaDeviceSynchronize());
   MV_CHECK(h->prof_plan != nullptr, "mvldm_profile_json: run a forward with profiling enabled first");
   Plan& p = *h->prof_plan;
-  std::vector<long long> stamps(p.timing.bytes / sizeof(long long));
-  if (!stamps.empty()) MV_CUDA(cudaMemcpy(stamps.data(), p.timing.p, p.timing.bytes, cudaMemcpyDeviceToHost));
   struct Agg {
     int n = 0;
     double us = 0, flops = 0, bytes = 0;
   };
   std::map<std::string, Agg> agg;
-  std::string ops = "[", launches = "[";
-  bool first_op = true, first_launch = true;
-  auto add = [&](const OpMeta& m, double us) {
-    Agg& a = agg[m.cat];
-    a.n++; a.us += us; a.flops += m.flops; a.bytes += m.bytes;
-    char buf[320];
-    snprintf(buf, sizeof buf, "%s{\"cat\":\"%s\",\"what\":\"%s\",\"us\":%.2f,\"gflop\":%.3f}", first_op ? "" : ",", m.cat,
-             m.what.c_str(), us, m.flops * 1e-9);
-    ops += buf;
-    first_op = false;
-  };
-  size_t ev = 0, so = 0;
-  for (const Step& st : p.steps) {
+  std::string ops = "[";
+  size_t ev = 0;
+  for (size_t i = 0; i < p.steps.size(); ++i) {
+    const OpMeta& m = p.steps[i].meta;
     float ms = 0.f;
     MV_CUDA(cudaEventElapsedTime(&ms, h->event_pool[ev], h->event_pool[ev + 1]));
     ev += 2;
-    const double us = ms * 1e3;
-    double gflop = 0.0;
-    if (st.kind == Step::SEQ) {
-      const int nops = st.op_end - st.op_begin;
-      const long long* t = stamps.data() + so;  // pairs (globaltimer ns, clock64) at start, after each barrier, at the end
-      so += 2 * (2 * (size_t)nops + 2);
-      int nb = 0;
-      for (int i = 0; i < nops; ++i) nb += mvldm_handle_s::op_barriers(p.ops[st.op_begin + i]) + (i + 1 < nops ? 1 : 0);
-      const double clocks = (double)(t[2 * (nb + 1) + 1] - t[1]);
-      int idx = 0;
-      for (int i = 0; i < nops; ++i) {
-        const int adv = mvldm_handle_s::op_barriers(p.ops[st.op_begin + i]) + 1;
-        const double frac = clocks > 0 ? (double)(t[2 * (idx + adv) + 1] - t[2 * idx + 1]) / clocks : 1.0 / nops;
-        idx += adv;
-        add(p.op_meta[st.op_begin + i], us * frac);   // launch overhead is shared in proportion
-        gflop += p.op_meta[st.op_begin + i].flops * 1e-9;
-      }
-    } else {
-      add(st.meta, us);
-      gflop = st.meta.flops * 1e-9;
-    }
-    char buf[200];
-    snprintf(buf, sizeof buf, "%s{\"kind\":\"%s\",\"ops\":%d,\"us\":%.2f,\"gflop\":%.3f}", first_launch ? "" : ",",
-             st.kind == Step::SEQ ? "seq" : (st.kind == Step::ATTN || st.kind == Step::ATTN_SHARDED ? "attention" : "kernel"),
-             st.kind == Step::SEQ ? st.op_end - st.op_begin : 1, us, gflop);
-    launches += buf;
-    first_launch = false;
+    Agg& a = agg[m.cat];
+    a.n++; a.us += ms * 1e3; a.flops += m.flops; a.bytes += m.bytes;
+    char buf[320];
+    snprintf(buf, sizeof buf, "%s{\"cat\":\"%s\",\"what\":\"%s\",\"us\":%.2f,\"gflop\":%.3f}", i ? "," : "", m.cat,
+             m.what.c_str(), ms * 1e3, m.flops * 1e-9);
+    ops += buf;
   }
   ops += "]";
-  launches += "]";
   std::string out = "{\"categories\":{";
   bool first = true;
   for (auto& kv : agg) {
@@ -1251,7 +1082,7 @@ static const char* profile_report(mvldm_handle_s* h) {
     out += buf;
     first = false;
   }
-  out += "},\"ops\":" + ops + ",\"launches\":" + launches + "}";
+  out += "},\"ops\":" + ops + "}";
   h->prof_json = out;
   return h->prof_json.c_str();
 }
@@ -1487,16 +1318,15 @@ int mvldm_raymap(void* stream, const float* extr, const float* intr, int n, int 
 int mvldm_op_gemm(void* stream, int impl, const mvldm_gemm_desc* d) {
   MV_API_BEGIN
   MV_CHECK(d, "null argument");
-  if (impl == MVLDM_IMPL_TC || impl == MVLDM_IMPL_TC_SEQ) {
+  if (impl == MVLDM_IMPL_TC) {
     static DevBuf scratch;  // op-level entry point (tests): grown on demand, never shrunk
-    const size_t need = std::max(gemm_tc_workspace_bytes(*d), gemm_classic_workspace_bytes(*d));
+    const size_t need = gemm_tc_workspace_bytes(*d);
     if (need > scratch.bytes) {
       MV_CUDA(cudaDeviceSynchronize());
       scratch.alloc(need);
       MV_CUDA(cudaMemset(scratch.p, 0, need));
     }
-    if (impl == MVLDM_IMPL_TC) gemm_classic((cudaStream_t)stream, *d, scratch.p, scratch.bytes);
-    else gemm_tc((cudaStream_t)stream, *d, scratch.p, scratch.bytes);  // the same GEMM as an op of the sequence kernel
+    gemm_tc((cudaStream_t)stream, *d, scratch.p, scratch.bytes);
   } else {
     gemm_simt((cudaStream_t)stream, *d);
   }
@@ -1511,18 +1341,6 @@ int mvldm_op_attention(void* stream, int impl, const void* qkv, void* out, int b
     attention_tc((cudaStream_t)stream, (const bf16*)qkv, (bf16*)out, batches, seq, heads, d, dpad);
   else
     attention_simt((cudaStream_t)stream, (const bf16*)qkv, (bf16*)out, batches, seq, heads, d, dpad);
-  MV_API_END
-}
-
-int mvldm_debug_seq_trace(void* device_buffer) {
-  mvldm::g_seq_trace = reinterpret_cast<long long*>(device_buffer);
-  return 0;
-}
-
-int mvldm_debug_seq_empty_ops(void* stream, int n_ops) {
-  MV_API_BEGIN
-  MV_CHECK(n_ops > 0 && n_ops <= 4096, "bad op count");
-  seq_debug_empty_ops((cudaStream_t)stream, n_ops);
   MV_API_END
 }
 
@@ -1547,16 +1365,7 @@ int mvldm_op_groupnorm(void* stream, const void* x0, int c0, const void* x1, int
                        float eps, const float* gamma, const float* beta, int silu, void* out, float* scratch) {
   MV_API_BEGIN
   MV_CHECK(x0 && gamma && beta && out && scratch, "null argument");
-  groupnorm_classic_init();
-  groupnorm_classic((cudaStream_t)stream, (const bf16*)x0, c0, (const bf16*)x1, c1, n_img, hw, groups, eps, gamma, beta,
-                    silu != 0, (bf16*)out, scratch);
-  MV_API_END
-}
-
-int mvldm_op_seq_groupnorm(void* stream, const void* x0, int c0, const void* x1, int c1, int n_img, int hw, int groups,
-                           float eps, const float* gamma, const float* beta, int silu, void* out, float* scratch) {
-  MV_API_BEGIN
-  MV_CHECK(x0 && gamma && beta && out && scratch, "null argument");
+  groupnorm_init();
   groupnorm((cudaStream_t)stream, (const bf16*)x0, c0, (const bf16*)x1, c1, n_img, hw, groups, eps, gamma, beta,
             silu != 0, (bf16*)out, scratch);
   MV_API_END
@@ -1564,14 +1373,6 @@ int mvldm_op_seq_groupnorm(void* stream, const void* x0, int c0, const void* x1,
 
 int mvldm_op_layernorm(void* stream, const void* x, int rows, int c, float eps, const float* gamma, const float* beta,
                        void* out) {
-  MV_API_BEGIN
-  MV_CHECK(x && gamma && beta && out, "null argument");
-  layernorm_classic((cudaStream_t)stream, (const bf16*)x, rows, c, eps, gamma, beta, (bf16*)out);
-  MV_API_END
-}
-
-int mvldm_op_seq_layernorm(void* stream, const void* x, int rows, int c, float eps, const float* gamma, const float* beta,
-                           void* out) {
   MV_API_BEGIN
   MV_CHECK(x && gamma && beta && out, "null argument");
   layernorm((cudaStream_t)stream, (const bf16*)x, rows, c, eps, gamma, beta, (bf16*)out);

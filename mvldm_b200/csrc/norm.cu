@@ -1,6 +1,5 @@
-// Stand-alone (one launch per op) GroupNorm(+SiLU), LayerNorm, nearest upsample, input im2col and timestep sinusoid:
-// the forward uses these at the resolutions where a multi-CTA-per-SM elementwise kernel beats the same op inside the
-// fused sequence kernel (seq.cu), see DESIGN.md.  bf16 NHWC activations, fp32 statistics, fixed reduction orders.
+// GroupNorm(+SiLU), LayerNorm, nearest upsample, input im2col and timestep sinusoid.
+// bf16 NHWC activations ([image, h, w, channel]), fp32 statistics, fixed reduction orders (bit-stable).
 #include <cooperative_groups.h>
 
 #include <cstdlib>
@@ -419,9 +418,14 @@ __global__ void __launch_bounds__(512) gn_reg_kernel(const bf16* __restrict__ x0
       else raw[j][v].u = make_uint4(0u, 0u, 0u, 0u);
     }
   }
-  float S[GB], Q[GB];
+  float S[GB], Q[GB], K[GB];   // sums about a per-group pivot (the group's first channel at the image's first pixel), see gn_flat
 #pragma unroll
-  for (int g = 0; g < GB; ++g) S[g] = Q[g] = 0.f;
+  for (int g = 0; g < GB; ++g) {
+    S[g] = Q[g] = 0.f;
+    const int c = ch0 + g * CGN;
+    const int64_t pix0 = (int64_t)img * hw;
+    K[g] = __bfloat162float(c < c0 ? x0[pix0 * c0 + c] : x1[pix0 * c1 + (c - c0)]);
+  }
 #pragma unroll
   for (int j = 0; j < P; ++j)
 #pragma unroll
@@ -429,11 +433,10 @@ __global__ void __launch_bounds__(512) gn_reg_kernel(const bf16* __restrict__ x0
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 f = __bfloat1622float2(raw[j][v].h(e));
-        constexpr int dummy = 0;
-        (void)dummy;
         const int ga = (v * 8 + 2 * e) / CGN, gbb = (v * 8 + 2 * e + 1) / CGN;  // compile-time after unrolling
-        S[ga] += f.x; Q[ga] = fmaf(f.x, f.x, Q[ga]);
-        S[gbb] += f.y; Q[gbb] = fmaf(f.y, f.y, Q[gbb]);
+        const float dx = f.x - K[ga], dy = f.y - K[gbb];
+        S[ga] += dx; Q[ga] = fmaf(dx, dx, Q[ga]);
+        S[gbb] += dy; Q[gbb] = fmaf(dy, dy, Q[gbb]);
       }
   const int span = tpi < 32 ? tpi : 32;
 #pragma unroll
@@ -469,8 +472,9 @@ __global__ void __launch_bounds__(512) gn_reg_kernel(const bf16* __restrict__ x0
   float mean[GB], rstd[GB];
 #pragma unroll
   for (int g = 0; g < GB; ++g) {
-    mean[g] = S[g] * inv_cnt;
-    rstd[g] = rsqrtf(fmaxf(Q[g] * inv_cnt - mean[g] * mean[g], 0.f) + eps);
+    const float dm = S[g] * inv_cnt;   // mean - pivot
+    mean[g] = K[g] + dm;
+    rstd[g] = rsqrtf(fmaxf(Q[g] * inv_cnt - dm * dm, 0.f) + eps);
   }
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
@@ -538,6 +542,18 @@ __global__ void __launch_bounds__(NV == 5 ? 320 : 480, NV == 5 ? 3 : 2)
   bf16x8 raw[R];
 #pragma unroll
   for (int j = 0; j < R; ++j) raw[j] = *reinterpret_cast<const bf16x8*>(src + j * sstep);
+  // channels cv*8 .. cv*8+7 belong to at most two groups (CGN >= 8): g_lo for e < eb, g_lo + 1 from eb on
+  const int g_lo = (cv * 8) / CGN, eb = (g_lo + 1) * CGN - cv * 8;
+  // Sums are taken about a pivot K per group - the group's first channel at the image's first pixel, the same value in
+  // every CTA of the cluster: mean = K + S1/n, var = S2/n - (S1/n)^2 then cancels against (mean - K)^2 = O(var) instead
+  // of mean^2, so |mean| >> std (real checkpoints) costs no precision.
+  float k_lo, k_hi;
+  {
+    const int c_lo = ch0 + g_lo * CGN, c_hi = ch0 + min(g_lo + 1, GB - 1) * CGN;
+    const int64_t pix0 = (int64_t)img * hw;
+    k_lo = __bfloat162float(c_lo < c0 ? x0[pix0 * c0 + c_lo] : x1[pix0 * c1 + (c_lo - c0)]);
+    k_hi = __bfloat162float(c_hi < c0 ? x0[pix0 * c0 + c_hi] : x1[pix0 * c1 + (c_hi - c0)]);
+  }
   float sa[8], qa[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) sa[e] = qa[e] = 0.f;
@@ -546,11 +562,10 @@ __global__ void __launch_bounds__(NV == 5 ? 320 : 480, NV == 5 ? 3 : 2)
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float2 f = __bfloat1622float2(raw[j].h(e));
-      sa[2 * e] += f.x; qa[2 * e] = fmaf(f.x, f.x, qa[2 * e]);
-      sa[2 * e + 1] += f.y; qa[2 * e + 1] = fmaf(f.y, f.y, qa[2 * e + 1]);
+      const float dx = f.x - (2 * e < eb ? k_lo : k_hi), dy = f.y - (2 * e + 1 < eb ? k_lo : k_hi);
+      sa[2 * e] += dx; qa[2 * e] = fmaf(dx, dx, qa[2 * e]);
+      sa[2 * e + 1] += dy; qa[2 * e + 1] = fmaf(dy, dy, qa[2 * e + 1]);
     }
-  // channels cv*8 .. cv*8+7 belong to at most two groups (CGN >= 8): g_lo for e < eb, g_lo + 1 from eb on
-  const int g_lo = (cv * 8) / CGN, eb = (g_lo + 1) * CGN - cv * 8;
   float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -599,9 +614,10 @@ __global__ void __launch_bounds__(NV == 5 ? 320 : 480, NV == 5 ? 3 : 2)
   }
   const float inv_cnt = 1.f / ((float)hw * (float)CGN);
   const int g_hi = min(g_lo + 1, GB - 1);
-  const float mean_lo = stat[2 * g_lo] * inv_cnt, mean_hi = stat[2 * g_hi] * inv_cnt;
-  const float rstd_lo = rsqrtf(fmaxf(stat[2 * g_lo + 1] * inv_cnt - mean_lo * mean_lo, 0.f) + eps);
-  const float rstd_hi = rsqrtf(fmaxf(stat[2 * g_hi + 1] * inv_cnt - mean_hi * mean_hi, 0.f) + eps);
+  const float d_lo = stat[2 * g_lo] * inv_cnt, d_hi = stat[2 * g_hi] * inv_cnt;   // mean - pivot
+  const float mean_lo = k_lo + d_lo, mean_hi = k_hi + d_hi;
+  const float rstd_lo = rsqrtf(fmaxf(stat[2 * g_lo + 1] * inv_cnt - d_lo * d_lo, 0.f) + eps);
+  const float rstd_hi = rsqrtf(fmaxf(stat[2 * g_hi + 1] * inv_cnt - d_hi * d_hi, 0.f) + eps);
   const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
   const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
   const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
@@ -708,7 +724,7 @@ inline int grid_for(int64_t total, int threads) {
 
 }  // namespace
 
-void im2col_classic(cudaStream_t s, const float* latents, int n_img, int cin, int h, int w, int kpad, bf16* out) {
+void im2col_input(cudaStream_t s, const float* latents, int n_img, int cin, int h, int w, int kpad, bf16* out) {
   MV_CHECK(kpad >= 9 * cin, "im2col: kpad too small");
   MV_CHECK(kpad % 8 == 0 && (int64_t)n_img * h * w * kpad < (1ll << 31), "im2col: kpad must be a multiple of 8 (32-bit indexing)");
   const int64_t total = (int64_t)n_img * h * w * (kpad / 8);
@@ -716,18 +732,18 @@ void im2col_classic(cudaStream_t s, const float* latents, int n_img, int cin, in
 }
 
 // timestep embedding in bf16: the A operand of the time_embedding GEMMs (what autocast feeds linear_1 in the reference)
-void sinusoid_classic(cudaStream_t s, const int64_t* t, int n, int dim, bf16* out) {
+void timestep_sinusoid_bf16(cudaStream_t s, const int64_t* t, int n, int dim, bf16* out) {
   const int total = n * (dim / 2);
   launch_pdl(sinusoid_kernel<bf16>, dim3(ceil_div(total, 128)), dim3(128), 0, s, t, n, dim, out);
 }
 
-size_t groupnorm_classic_scratch_floats(int n_img, int groups) { return (size_t)n_img * GN_MAXP * groups * 2; }
+size_t groupnorm_scratch_floats(int n_img, int groups) { return (size_t)n_img * GN_MAXP * groups * 2; }
 
-void groupnorm_classic_init() {
+void groupnorm_init() {
   MV_CUDA(cudaFuncSetAttribute(gn_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
 }
 
-void groupnorm_classic(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, int n_img, int hw, int groups,
+void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, int n_img, int hw, int groups,
                float eps, const float* gamma, const float* beta, bool silu, bf16* out, float* scratch) {
   const int C = c0 + c1;
   MV_CHECK(C % groups == 0 && groups <= 64, "groupnorm: channels not divisible by groups (<= 64 groups)");
@@ -879,7 +895,7 @@ void groupnorm_classic(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, i
              gamma, beta, silu ? 1 : 0, out);
 }
 
-void layernorm_classic(cudaStream_t s, const bf16* x, int rows, int c, float eps, const float* gamma, const float* beta,
+void layernorm(cudaStream_t s, const bf16* x, int rows, int c, float eps, const float* gamma, const float* beta,
                bf16* out) {
   MV_CHECK(c % 8 == 0 && c <= 32 * 8 * 8, "layernorm: unsupported channel count");
   const int warps = 4;
@@ -889,7 +905,7 @@ void layernorm_classic(cudaStream_t s, const bf16* x, int rows, int c, float eps
   else launch_pdl(layernorm_kernel<8>, grid, block, 0, s, x, rows, c, eps, gamma, beta, out);
 }
 
-void upsample_classic(cudaStream_t s, const bf16* x, int n_img, int h, int w, int c, bf16* out) {
+void upsample_nearest2x(cudaStream_t s, const bf16* x, int n_img, int h, int w, int c, bf16* out) {
   MV_CHECK(c % 8 == 0, "upsample: channels must be a multiple of 8");
   const int64_t total = (int64_t)n_img * 4 * h * w * (c / 8);
   launch_pdl(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), 0, s, x, n_img, h, w, c, out);

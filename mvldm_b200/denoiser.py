@@ -212,13 +212,6 @@ class _Handle:
         self.close()
 
 
-# Ops on at most this many tokens run inside the fused persistent sequence kernel (csrc/seq.cu), larger ones as stand-alone
-# kernels; -1 fuses everything.  Measured on B200 at 1 scene x 8 views (profiles/r02_fuse_sweep.txt): 0 -> 3.23 ms/step,
-# 128 -> 3.31, 512 -> 3.39, 2048 -> 3.54, -1 -> 3.78, so the default keeps one launch per op inside a CUDA graph.
-# MVLDM_FUSE_MAX_TOKENS overrides it for measurement sweeps.
-FUSE_MAX_TOKENS = 0
-
-
 class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
     """Drop-in for reference ``MultiViewUNet`` (mvunet.py:43-208).
 
@@ -228,7 +221,7 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
     random-initialised and the checkpoint arrives through ``load_state_dict`` like any Lightning checkpoint."""
 
     def __init__(self, cfg: MultiViewUNetCfg, in_channels: int, out_channels: int, *, impl: int = _lib.IMPL_TC,
-                 use_cuda_graph: bool = True, fuse_max_tokens: Optional[int] = None) -> None:
+                 use_cuda_graph: bool = True) -> None:
         super().__init__(cfg)
         self.variant_b = cfg.pretrained_from is not None
         if cfg.multi_view_attention.name != "spatial_transformer_3d":
@@ -256,7 +249,6 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
         self.pretrained_from = cfg.pretrained_from
         self.in_channels, self.out_channels = in_channels, out_channels
         self.impl, self.use_cuda_graph = impl, use_cuda_graph
-        self.fuse_max_tokens = FUSE_MAX_TOKENS if fuse_max_tokens is None else int(fuse_max_tokens)
         self._shapes = param_shapes(self._boc, in_channels, out_channels, variant_b=self.variant_b)
         for key, shape in self._shapes.items():
             self._register(key, self._init_param(key, shape))
@@ -266,8 +258,9 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
 
     def mark_dirty(self) -> None:
         """Tell the module its parameters changed in place (the packed device copy is rebuilt on the next call).
-        Done automatically after load_state_dict / .to() / .cuda(); in-place updates are also caught by the per-call
-        parameter-version check."""
+        Done automatically after load_state_dict / .to() / .cuda(); in-place updates (optimizer steps, EMA / AveragedModel
+        updates, `p.detach().copy_()`) are caught by the per-call parameter-version check.  Writes through `p.data` bypass
+        autograd's version counter and cannot be seen: call this after them."""
         self._dirty = True
         self.__dict__.pop("_plist", None)
 
@@ -316,7 +309,6 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
         c.max_attn_res = 32
         c.impl = self.impl
         c.use_cuda_graph = 1 if self.use_cuda_graph else 0
-        c.fuse_max_tokens = self.fuse_max_tokens
         if self.variant_b:
             c.variant, c.cross_attention_dim = 1, SD21_CROSS_ATTENTION_DIM
             for i, v in enumerate(SD21_HEADS):

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     import ctypes
-    assert ctypes.sizeof(_lib.Config) == 4 * (3 + 4 + 6 + 1 + 4 + 1 + 1)   # ... + fuse_max_tokens
+    assert ctypes.sizeof(_lib.Config) == 4 * (3 + 4 + 6 + 1 + 4 + 1)
     assert ctypes.sizeof(_lib.ASeg) == 8 + 6 * 4 + 9 + 9 + 2 + 9 * 4      # ptr, 6 ints, 2x9 int8 (+2 pad), 9 ints
     assert _lib.GemmDesc.seg.offset == 8 and ctypes.sizeof(_lib.GemmDesc) % 8 == 0
 
