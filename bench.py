@@ -105,10 +105,10 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle on the host cores
 # ------------------------------------------------------------------------------------------------------
-def cpu_steps_per_sec(steps: int, warmup: int, use_cfg: bool, variant: str = "a"):
+def cpu_steps_per_sec(steps: int, warmup: int, use_cfg: bool, variant: str = "a", mv_block: str = "spatial_transformer_3d"):
     from oracle import mvldm_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    cfg = O.OracleCfg(variant_b=(variant == "b"))
+    cfg = O.OracleCfg(variant_b=(variant == "b"), mv_block=mv_block)
     sd = O.init_weights(cfg, 0)
     ctx, x_t, extr, intr = O.synthetic_scene(1, V_C, V_T)
     sched = O.DDIMOracle()
@@ -132,7 +132,7 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))   # bounded: ~1-2 s per CPU step
-    v, ms, cores = cpu_steps_per_sec(steps, warmup, args.cfg, args.variant)
+    v, ms, cores = cpu_steps_per_sec(steps, warmup, args.cfg, args.variant, args.mv_block)
     sample = f"{steps} DDIM steps (of {args.steps} requested; bounded for CPU), 1 scene x 8 views, fp32, torch-CPU oracle"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
@@ -148,13 +148,169 @@ def run_reference(args):
 def workload_name(args):
     model = "Variant-A MultiViewUNet (764M params)" if args.variant == "a" else \
         "Variant-B (SD-2.1 topology) MultiViewUNet (1069M params)"
+    if getattr(args, "mv_block", "") == "standard":
+        model += " with StandardTransformer multi-view blocks"
     return (f"25-step DDIM sampling, {args.scenes_per_gpu} scene(s)/GPU x 8 views (2 context + 6 target) at 256x256 "
             f"(32x32x4 latent), {model}, {'CFG 3.0 (cond 8 views + uncond 6 views per step)' if args.cfg else 'no CFG (1 forward/step)'}")
+
+
+MUFU_EX2_PER_S = 4.62e12      # measured: 16 ex2 / clock / SM x 148 SMs (tools/micro/mufu.cu, profiles/r01_final_micro_mufu_pdl.txt)
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes of the GEMM kernel from the committed ncu capture (tools/summarize_final.py writes it from
+    `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum` over one whole DDIM step)."""
+    p = os.path.join(ROOT, "profiles", "r02_final_traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p))
+
+
+def roofline_record(prof, peaks, step_tf, args):
+    """`frac` covers EVERY launch of the dominant kernel (gemm_tc_kernel: conv3x3 + linear / 1x1), not the conv subset:
+    achieved = sum of their algorithmic FLOPs / sum of their event-pair durations, so it can be recomputed from
+    `by_category` (gflop / us) to the digit."""
+    peak = peaks["bf16_tflops"]
+    cat = {k: {"launches": c["launches"], "gflop": round(c["gflop"], 3), "us": round(c["us"], 2),
+               "algorithmic_mbytes": round(c.get("mbytes", 0.0), 3)} for k, c in prof.items()}
+    gemm_keys = [k for k in prof if k.startswith("gemm_")]
+    g_gf = sum(prof[k]["gflop"] for k in gemm_keys)
+    g_us = sum(prof[k]["us"] for k in gemm_keys)
+    g_n = sum(prof[k]["launches"] for k in gemm_keys)
+    g_mb = sum(prof[k].get("mbytes", 0.0) for k in gemm_keys)
+    achieved = g_gf / g_us * 1e3                     # GFLOP / us = PFLOP/s -> TFLOP/s
+    tr = ncu_traffic()
+    traffic = tr["gemm_tc_kernel"]["dram_bytes_per_launch"] if tr and "gemm_tc_kernel" in tr else None
+    roof = {
+        "bound": "tensor",
+        "kernel": f"gemm_tc_kernel (tcgen05 implicit GEMM): all {g_n} launches of one forward, conv3x3 + linear/1x1",
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+        "traffic": traffic,
+        "traffic_source": (tr or {}).get("source"),
+        "algorithmic_bytes_per_launch": g_mb * 1e6 / g_n,
+        "algorithmic_gflop_per_launch": g_gf / g_n,
+        "avg_launch_us": g_us / g_n,
+        "how": ("algorithmic FLOPs (2*M*N*K, un-padded) of ALL gemm_tc_kernel launches of one forward / sum of their durations; "
+                "each launch is bracketed by a CUDA-event pair on the launching stream inside the library "
+                "(mvldm_set_profiling), GPU parked behind a spin kernel so the host is never the bottleneck; "
+                "frac == sum(by_category[gemm_*].gflop) / sum(by_category[gemm_*].us) / peak"),
+        "peak_source": peaks["source"],
+        "hbm_view": {"achieved_gbs": g_mb * 1e6 / (g_us * 1e-6) / 1e9, "peak_gbs": peaks["hbm_gbs"],
+                     "note": "same launches against the HBM roofline (algorithmic bytes = weights + activations in/out); the 4x4 / "
+                             "8x8-level GEMMs at 1 scene are weight-streaming, the 32x32 / 16x16 ones tensor-bound"},
+        "by_kind": {k: {"launches": prof[k]["launches"], "tflops": prof[k]["gflop"] / prof[k]["us"] * 1e3,
+                        "frac": prof[k]["gflop"] / prof[k]["us"] * 1e3 / peak} for k in gemm_keys},
+        "by_category": cat,
+        "whole_step": {"achieved": step_tf, "frac": step_tf / peak,
+                       "how": "algorithmic GFLOP of the step (BASELINE.md) / CUDA-event time of the timed region (graph replay)"},
+    }
+    # "attn TC util" of BASELINE.json's metric: its own entry against BOTH bounds.  Tensor: QK^T and PV run on 64-wide padded
+    # heads (40 -> 64 at level 0), so the tensor pipe does 1.6x the un-padded FLOPs there.  MUFU: one ex2 per score.
+    for key in ("attention_joint", "attention_per_view", "attention_joint_sharded"):
+        if key not in prof:
+            continue
+        a = prof[key]
+        sec = a["us"] * 1e-6
+        tfl, tfl_pad = a["gflop"] / sec / 1e3, a["gflop_padded"] / sec / 1e3
+        roof[key] = {
+            "kernel": "attn64q_kernel / attn_tc_kernel (flash-style tcgen05 + TMEM, TMA-fed)", "launches": a["launches"],
+            "gflop": a["gflop"], "gflop_padded": a["gflop_padded"], "us": a["us"],
+            "tensor": {"achieved": tfl, "achieved_padded": tfl_pad, "peak": peak, "unit": "TFLOP/s", "frac": tfl / peak,
+                       "frac_padded": tfl_pad / peak,
+                       "note": "achieved = un-padded FLOPs (4*N^2*C); padded = what the tensor pipe executes (40-wide heads run "
+                               "as 64, 80 as 128, 160 as 192)"},
+            "mufu": {"achieved": a["gscores"] * 1e9 / sec / 1e12, "peak": MUFU_EX2_PER_S / 1e12, "unit": "T ex2/s",
+                     "frac": a["gscores"] * 1e9 / sec / MUFU_EX2_PER_S,
+                     "note": "one ex2.approx per attention score; peak = 16 / clk / SM measured on this part "
+                             "(profiles/r01_final_micro_mufu_pdl.txt); the binding bound for 40-wide heads"}}
+    return roof
 
 
 # ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
+def max_over_ranks(ms: float, world: int, dev) -> float:
+    import torch.distributed as dist
+    if world == 1:
+        return ms
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_config4(args, m, sched, rank, world, local, dev, barrier):
+    """BASELINE.json configs[3]: 25-step DDIM sampling of 64 independent scenes x 8 views, scenes split evenly over the
+    ranks (total work fixed = strong scaling), each rank running its scenes 8 at a time (one pass = 64 views).  No
+    data-path collective; the time is the max over ranks of the CUDA-event time of the whole sampling job."""
+    import mvldm_b200 as mv
+    from mvldm_b200 import synthetic
+    total, per_pass = 64, 8
+    mine = total // world
+    per_pass = min(per_pass, mine)
+    passes = mine // per_pass
+    path = mv.DenoisingPath(m, sched, use_cfg=False)
+    path.set_timesteps(NUM_DDIM_STEPS)
+    ts_list = [int(t) for t in sched.timesteps]
+    jobs = []
+    for p in range(passes):
+        ctx, x_T, extr, intr = synthetic.scene(per_pass, V_C, V_T, seed=100 + rank * passes + p)
+        ctx_in = torch.cat([ctx, torch.zeros(per_pass, V_C, 1, H, W)], 2).to(dev)
+        jobs.append((x_T.to(dev), ctx_in, mv.ray_encode(extr.to(dev), intr.to(dev), H, W)))
+    x = jobs[0][0]
+    for i in range(3):                                    # warm-up: plan + graph for the 8-scene shape
+        x = path.step(m, x, ts_list[i], jobs[0][1], jobs[0][2])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for x_T, ctx_in, rays in jobs:
+        x = x_T
+        for t in ts_list:
+            x = path.step(m, x, t, ctx_in, rays)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    assert torch.isfinite(x).all()
+    return {"workload": "25-step DDIM sampling of 64 scenes x 8 views, scenes split evenly over the ranks, 8 scenes per pass",
+            "scaling": "strong", "scenes": total, "scenes_per_rank": mine, "scenes_per_pass": per_pass,
+            "ddim_steps": NUM_DDIM_STEPS, "seconds": ms * 1e-3, "value": total * NUM_DDIM_STEPS / (ms * 1e-3),
+            "unit": "scene-steps/s", "scenes_per_sec": total / (ms * 1e-3)}
+
+
+def run_view_sharded(args, m, rank, world, local, dev, barrier):
+    """ONE scene whose views are split in contiguous groups over the ranks; every joint attention
+    all-gathers the packed K|V slab (NCCL over NVLink) through the library's exchange callback.  Total work is fixed
+    (strong scaling).  world == 1 runs the same sharded code path with a local copy instead of the all-gather."""
+    import mvldm_b200 as mv
+    from mvldm_b200 import synthetic
+    V = args.view_sharded_views
+    a, b = mv.view_slice(V, rank, world)
+    g = torch.Generator().manual_seed(7)
+    inp = torch.randn(1, V, 11, H, W, generator=g)[:, a:b].to(dev)       # same scene on every rank, own view slice
+    ts = torch.full((1, b - a), 500, dtype=torch.long, device=dev)
+    ex = mv.ViewGroupExchange(b - a, V, H, W, 8, dev)
+    for _ in range(2):
+        y = m.forward_view_sharded(inp, ts, V, ex)
+    ex.calls = ex.bytes_sent = 0
+    n = 5
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        y = m.forward_view_sharded(inp, ts, V, ex)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / n
+    assert torch.isfinite(y).all()
+    return {"workload": f"one denoiser forward of 1 scene x {V} views, views split in contiguous groups over the ranks",
+            "scaling": "strong", "views": V, "views_per_rank": b - a, "forwards_timed": n, "ms_per_forward": ms,
+            "value": V / (ms * 1e-3), "unit": "views/s",
+            "gflop_per_forward": forward_gflop(V, args.variant), "tflops": forward_gflop(V, args.variant) / ms,
+            "kv_exchanges_per_forward": ex.calls // n,
+            "kv_bytes_sent_per_rank_per_forward": ex.bytes_sent // n,
+            "kv_bytes_received_per_rank_per_forward": ex.bytes_sent // n * (world - 1),
+            "collective": "ncclAllGather (torch.distributed all_gather_into_tensor) per multi-view block" if world > 1 else "none (local copy)"}
+
+
 def run_gpu(args):
     import torch.distributed as dist
     import mvldm_b200 as mv
@@ -176,7 +332,7 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     S = args.scenes_per_gpu
-    mcfg = mv.default_cfg()
+    mcfg = mv.standard_cfg() if args.mv_block == "standard" else mv.default_cfg()
     if args.variant == "b":
         mcfg.pretrained_from = "stabilityai/stable-diffusion-2-1"      # topology only: no hub, random init
     m = mv.MultiViewUNet(mcfg, 11, 4, use_cuda_graph=not args.no_graph)
@@ -244,6 +400,15 @@ def run_gpu(args):
     value = world * S * args.steps / (ms * 1e-3)
     e2e = world * S * args.steps / (ms_e2e * 1e-3)
 
+    # ---- BASELINE config 4: 64 scenes x 8 views split evenly over the ranks (strong scaling), 8 scenes per pass ---------
+    config4 = None
+    if args.config4 and not args.cfg and S == 1 and 64 % world == 0:
+        config4 = run_config4(args, m, sched, rank, world, local, dev, barrier)
+    # ---- view-group sharding: ONE scene of 64 views split over the ranks, K|V all-gathered at every multi-view block ----
+    view_sharded = None
+    if args.view_sharded_views > 0 and not args.cfg and S == 1 and args.view_sharded_views % world == 0:
+        view_sharded = run_view_sharded(args, m, rank, world, local, dev, barrier)
+
     # ---- per-kernel roofline: CUDA-event pairs around every launch of one more (eager) forward, on its stream
     prof = None
     if rank == 0:
@@ -268,34 +433,14 @@ def run_gpu(args):
     if rank == 0:
         peaks = load_peaks()
         gf = step_gflop(args.cfg, args.variant) * S
+        if args.mv_block == "standard":     # no closed form in BASELINE.md: the library's own per-op algorithmic FLOP count
+            gf = sum(c["gflop"] for c in prof.values()) * (14.0 / 8.0 if args.cfg else 1.0)
         step_tf = gf * args.steps / (ms * 1e-3) / 1e3
-        conv = prof["gemm_conv3x3"]
-        lin = prof["gemm_linear"]
-        att = prof["attention_joint"]
-        tf = lambda c: c["gflop"] / c["us"]  # noqa: E731  (GFLOP / us = PFLOP/s; x1e3 below -> TFLOP/s)
-        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM): the conv3x3 launches of one forward "
-                                             f"({conv['launches']} launches, {conv['gflop']:.0f} of {forward_gflop(V_C + V_T, args.variant) * S:.0f} GFLOP)",
-                "achieved": tf(conv) * 1e3, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": tf(conv) * 1e3 / peaks["bf16_tflops"], "traffic": None,
-                "how": ("algorithmic FLOPs (2*M*N*K, un-padded) of the launches / sum of their durations; every launch is "
-                        "bracketed by a CUDA-event pair on the launching stream inside the library (mvldm_set_profiling), "
-                        "GPU parked behind a spin kernel so the pairs see back-to-back execution; ncu: profiles/"),
-                "peak_source": peaks["source"],
-                "other_kernels_tflops": {"gemm_linear": tf(lin) * 1e3, "attention_joint": tf(att) * 1e3},
-                # "attn TC util" of BASELINE.json's metric: the joint attention is bound by the MUFU pipe (one ex2 per
-                # score, 16 per clock per SM = 4.62 T/s measured, tools/micro/mufu.cu), not by the tensor pipe
-                "attention": {"tflops_unpadded": tf(att) * 1e3, "tflops_padded_tensor_work": tf(att) * 1e3 * 64.0 / 40.0,
-                              "frac_of_bf16_peak_padded": tf(att) * 1e3 * 1.6 / peaks["bf16_tflops"],
-                              "exp2_per_forward": att["gflop"] * 1e9 / (4.0 * 40.0),
-                              "frac_of_mufu_bound": (att["gflop"] * 1e9 / 160.0 / 4.62e12) / (att["us"] * 1e-6),
-                              "note": "level-0 (40-wide heads padded to 64) dominates; padded = x64/40"},
-                "us_per_forward": {k: round(c["us"], 1) for k, c in prof.items()},
-                "whole_step": {"achieved": step_tf, "frac": step_tf / peaks["bf16_tflops"],
-                               "how": "algorithmic GFLOP of the step (BASELINE.md) / CUDA-event time of the timed region"}}
+        roof = roofline_record(prof, peaks, step_tf, args)
         cpu = None
         if not args.no_cpu_baseline:
             n = 3
-            v, s_per, cores = cpu_steps_per_sec(n, 1, args.cfg, args.variant)
+            v, s_per, cores = cpu_steps_per_sec(n, 1, args.cfg, args.variant, args.mv_block)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{n} DDIM steps after 1 warm-up, 1 scene x 8 views, fp32 torch-CPU oracle ({s_per:.2f} s/step)"}
         print(json.dumps({
@@ -303,7 +448,8 @@ def run_gpu(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(args), "views": V_C + V_T, "latent": [H, W], "use_cfg": args.cfg,
-                       "scenes_per_gpu": S, "cuda_graph": not args.no_graph, "variant": args.variant, "plucker": args.plucker,
+                       "scenes_per_gpu": S, "cuda_graph": not args.no_graph, "variant": args.variant, "mv_block": args.mv_block,
+                       "plucker": args.plucker,
                        "cfg_one_pass": bool(args.cfg and not args.no_batch_cfg),
                        "l2_policy": "inputs larger than L2: 1.53 GB of bf16 weights are streamed every step (L2 = 126 MB)",
                        "weights": "random-init, seed 0, proj_out re-randomised (SURVEY.md §0.5)"},
@@ -311,7 +457,7 @@ def run_gpu(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "cpu_baseline": cpu, "config4": config4, "view_sharded": view_sharded,
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -330,8 +476,15 @@ def main():
                     "b: SD-2.1 topology with per-view Transformer2D blocks")
     ap.add_argument("--plucker", action="store_true", help="Pluecker ray maps (o x d, d) instead of (o, d): same 6 channels, "
                     "computed once per sample() outside the step; the denoiser cost is identical")
+    ap.add_argument("--mv-block", default="spatial_transformer_3d", choices=["spatial_transformer_3d", "standard"],
+                    help="multi_view_attention.name: the released experiment's SpatialTransformer3D (headline) or the "
+                         "reference's default StandardTransformer (pre-LN joint attention + GELU MLP)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config4", dest="config4", action="store_false",
+                    help="skip the BASELINE config-4 leg (64 scenes split over the ranks, strong scaling)")
+    ap.add_argument("--view-sharded-views", type=int, default=64,
+                    help="views of the single scene used for the view-group-sharded leg (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -29,6 +29,7 @@ enum { MVLDM_F32 = 0, MVLDM_BF16 = 1, MVLDM_F16 = 2 };
 /* kernel family: tcgen05/TMA kernels (product) or the plain CUDA-core kernels kept as an on-device
  * cross-check for the tests (never selected implicitly) */
 enum { MVLDM_IMPL_TC = 0, MVLDM_IMPL_SIMT = 1, MVLDM_IMPL_TC_GEMM_SIMT_ATTN = 2 };
+enum { MVLDM_MV_SPATIAL_TRANSFORMER_3D = 0, MVLDM_MV_STANDARD = 1 };
 
 /* Replaces: MultiViewUNetCfg + UNet2DModelCfg + SpatialTransformer3DCfg
  * (src/model/denoiser/mvunet.py:22-40, src/model/denoiser/mvdream/attention.py:23-32) and the
@@ -51,6 +52,15 @@ typedef struct {
   int32_t variant;                              /* 0 = A (DownBlock2D/UpBlock2D), 1 = B (SD-2.1 topology) */
   int32_t t2d_heads[MVLDM_MAX_LEVELS];          /* SD-2.1 attention_head_dim [5,10,20,20] (= heads; head dim 64) */
   int32_t cross_attention_dim;                  /* 1024 */
+  /* multi_view_attention.name (src/model/denoiser/attention.py:8-27): which block sits at the 9 multi-view positions.
+   * 1 = StandardTransformer (src/model/denoiser/standard/transformer.py:45-136, the reference's default
+   * config/model/denoiser/multi_view_attention/standard_attention.yaml): per layer  x += to_out(softmax(q k^T / sqrt(d)) v)
+   * over ALL (view, pixel) tokens of a scene on LayerNorm(x), then x += W2 gelu(W1 LayerNorm(x)); no GroupNorm, no
+   * proj_in / proj_out.  Supported: d_dot = d_in / num_heads, downscale = 1, pos_enc = false. */
+  int32_t mv_block;                             /* MVLDM_MV_SPATIAL_TRANSFORMER_3D or MVLDM_MV_STANDARD */
+  int32_t mv_num_layers;                        /* CrossAttentionCfg.num_layers (standard only; >= 1) */
+  int32_t mv_d_mlp;                             /* CrossAttentionCfg.d_mlp, or 0 to use the multiplier */
+  int32_t mv_d_mlp_multiplier;                  /* hidden width = d_in * multiplier when mv_d_mlp == 0 */
 } mvldm_config;
 
 const char* mvldm_last_error(void);
@@ -173,7 +183,7 @@ typedef struct {
   const void* residual;         /* bf16 [M, res_ld] or NULL */
   int32_t res_ld;
   int32_t mode;                 /* 0 bf16 [M,ldo]; 1 GEGLU (8-col interleave: columns [16j,16j+8) values, [16j+8,16j+16) their gates) -> bf16 [M, N/2]; 2 fp32 NCHW, n_valid channels;
-                                   3 like 0 with SiLU on the result; 4 fp32 [M,ldo] */
+                                   3 like 0 with SiLU on the result; 4 fp32 [M,ldo]; 5 like 0 with exact (erf) GELU on the result */
   void* out;
   int32_t ldo;
   int32_t n_valid;

@@ -5,16 +5,17 @@ Python here is plumbing: the reference-facing interfaces (`Denoiser`, `MultiView
 `libmvldm_b200.so` (hand-written CUDA; see include/mvldm_b200.h).
 """
 from . import _lib
-from .denoiser import (DENOISER, Denoiser, DenoiserCfg, MultiViewUNet, MultiViewUNetCfg, SpatialTransformer3DCfg,
-                       UNet2DModelCfg, default_cfg, get_denoiser)
+from .denoiser import (DENOISER, CrossAttentionCfg, Denoiser, DenoiserCfg, MultiViewUNet, MultiViewUNetCfg,
+                       SpatialTransformer3DCfg,
+                       UNet2DModelCfg, default_cfg, get_denoiser, standard_cfg)
 from .anchored import AnchoredPlan, anchored_plan, sample_anchored
 from .sampler import DenoisingPath, build_inputs, ray_encode
 from .scheduler import (SCHEDULER, DDIMScheduler, DDIMSchedulerCfg, SchedulerCfg, fused_cfg_ddim_step, get_scheduler)
 from .sharding import ViewGroupExchange, gather_scenes, scene_slice, view_slice
 
 __all__ = [
-    "DENOISER", "Denoiser", "DenoiserCfg", "MultiViewUNet", "MultiViewUNetCfg", "SpatialTransformer3DCfg",
-    "UNet2DModelCfg", "default_cfg", "get_denoiser", "DenoisingPath", "build_inputs", "ray_encode", "SCHEDULER",
+    "DENOISER", "CrossAttentionCfg", "Denoiser", "DenoiserCfg", "MultiViewUNet", "MultiViewUNetCfg", "SpatialTransformer3DCfg",
+    "UNet2DModelCfg", "default_cfg", "standard_cfg", "get_denoiser", "DenoisingPath", "build_inputs", "ray_encode", "SCHEDULER",
     "DDIMScheduler", "DDIMSchedulerCfg", "SchedulerCfg", "fused_cfg_ddim_step", "get_scheduler", "gather_scenes",
     "scene_slice", "view_slice", "ViewGroupExchange", "AnchoredPlan", "anchored_plan", "sample_anchored",
 ]

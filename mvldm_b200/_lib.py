@@ -16,6 +16,7 @@ MVLDM_MAX_LEVELS = 4
 MVLDM_MAX_SEGS = 3
 F32, BF16, F16 = 0, 1, 2
 IMPL_TC, IMPL_SIMT, IMPL_TC_GEMM_SIMT_ATTN = 0, 1, 2
+MV_SPATIAL_TRANSFORMER_3D, MV_STANDARD = 0, 1
 
 
 class Config(Structure):
@@ -25,6 +26,7 @@ class Config(Structure):
         ("norm_groups", c_int32), ("num_heads", c_int32), ("max_attn_res", c_int32), ("impl", c_int32),
         ("use_cuda_graph", c_int32),
         ("variant", c_int32), ("t2d_heads", c_int32 * MVLDM_MAX_LEVELS), ("cross_attention_dim", c_int32),
+        ("mv_block", c_int32), ("mv_num_layers", c_int32), ("mv_d_mlp", c_int32), ("mv_d_mlp_multiplier", c_int32),
     ]
 
 

@@ -112,10 +112,11 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const __grid_constant__ 
       if (d.rowvec) v += d.rowvec[(int64_t)im * d.rowvec_ld + nn];
       return v;
     };
-    if (d.mode == 0 || d.mode == 3) {
+    if (d.mode == 0 || d.mode == 3 || d.mode == 5) {
       float v = val(c);
       if (d.residual) v += __bfloat162float(reinterpret_cast<const bf16*>(d.residual)[(int64_t)m * d.res_ld + n]);
       if (d.mode == 3) v = v / (1.f + expf(-v));
+      if (d.mode == 5) v = gelu_exact(v);
       reinterpret_cast<bf16*>(d.out)[(int64_t)m * d.ldo + n] = __float2bfloat16(v);
     } else if (d.mode == 4) {
       reinterpret_cast<float*>(d.out)[(int64_t)m * d.ldo + n] = val(c);

@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
           }
         }
       }
-      if (p.mode == 0 || p.mode == 3) {
+      if (p.mode == 0 || p.mode == 3 || p.mode == 5) {
         if (use_res) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -366,6 +366,9 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         if (p.mode == 3) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));  // SiLU
+        } else if (p.mode == 5) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_exact(v[j]);  // nn.GELU() (erf form)
         }
         bf16* op = reinterpret_cast<bf16*>(p.out) + (int64_t)m * p.ldo + n;
 #pragma unroll
@@ -725,8 +728,8 @@ void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t w
   p.out = d.out;
   p.ldo = d.ldo;
   p.n_valid = d.n_valid;
-  MV_CHECK(d.mode >= 0 && d.mode <= 4, "gemm: bad output mode");
-  if (d.mode == 0 || d.mode == 3 || d.mode == 4) MV_CHECK(d.ldo % 8 == 0 && (!d.residual || d.res_ld % 8 == 0), "gemm: row pitch must be a multiple of 8");
+  MV_CHECK(d.mode >= 0 && d.mode <= 5, "gemm: bad output mode");
+  if (d.mode == 0 || d.mode == 3 || d.mode == 4 || d.mode == 5) MV_CHECK(d.ldo % 8 == 0 && (!d.residual || d.res_ld % 8 == 0), "gemm: row pitch must be a multiple of 8");
   if (BN == 256) launch<256, 2>(s, p, splits);        // 2 x 96 KB
   else if (BN == 160) launch<160, 3>(s, p, splits);   // 3 x 72 KB
   else if (BN == 128) launch<128, 3>(s, p, splits);   // 3 x 64 KB

@@ -75,6 +75,14 @@ struct MvW {  // SpatialTransformer3D block, or (t2d) a per-view diffusers Trans
   bool t2d = false;
   const float *gn_g = nullptr, *gn_b = nullptr, *ln_g[3] = {}, *ln_b[3] = {};
   Packed proj_in, qkv1, out1, qkv2, out2, ff1, ff2, proj_out;
+  // StandardTransformer (multi_view_attention.name == "standard"): `layers` pre-norm [joint attention, GELU MLP] pairs
+  struct StdLayer {
+    const float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+    Packed qkv, out, fc1, fc2;
+  };
+  bool standard = false;
+  int d_mlp = 0;
+  std::vector<StdLayer> layers;
 };
 
 struct Arena {
@@ -100,6 +108,7 @@ struct OpMeta {  // what a launch is, for the per-op timing report
   const char* cat;
   std::string what;
   double flops, bytes;
+  double scores = 0, flops_padded = 0;  // attention only: softmax exponentials (one ex2 each) and tensor-pipe FLOPs on padded heads
 };
 struct Step {
   enum Kind { GEMM, GEMM_SIMT, ATTN, ATTN_SHARDED, GN, LN, UPSAMPLE, IM2COL, SINUSOID } kind = GEMM;
@@ -226,7 +235,34 @@ struct mvldm_handle_s {
     temb_total += cout;
     return r;
   }
+  // StandardTransformer state-dict keys: standard/transformer.py:76-84 -> transformer/transformer.py:24-47
+  // (layers.J.0 = PreNorm(Attention: to_qkv no bias, to_out.0), layers.J.1 = PreNorm(FeedForward: net.0, GELU, net.3))
+  MvW reg_standard(const std::string& k, int c) {
+    MvW m;
+    m.key = k;
+    m.c = c;
+    m.standard = true;
+    m.heads = cfg.num_heads;
+    MV_CHECK(c % cfg.num_heads == 0, "channels not divisible by num_heads");
+    m.d = c / cfg.num_heads;
+    m.dpad = (m.d + 63) / 64 * 64;
+    MV_CHECK(m.dpad <= 192, "head dim > 192 unsupported");
+    m.d_mlp = cfg.mv_d_mlp > 0 ? cfg.mv_d_mlp : c * cfg.mv_d_mlp_multiplier;
+    MV_CHECK(m.d_mlp > 0 && m.d_mlp % 64 == 0, "standard transformer: d_mlp must be a positive multiple of 64");
+    m.layers.resize(cfg.mv_num_layers);
+    for (int j = 0; j < cfg.mv_num_layers; ++j) {
+      const std::string lk = k + ".transformer.layers." + std::to_string(j);
+      reg_norm(lk + ".0.norm", c);
+      reg_lin(lk + ".0.fn.to_qkv", 3 * c, c, false);
+      reg_lin(lk + ".0.fn.to_out.0", c, c);
+      reg_norm(lk + ".1.norm", c);
+      reg_lin(lk + ".1.fn.net.0", m.d_mlp, c);
+      reg_lin(lk + ".1.fn.net.3", c, m.d_mlp);
+    }
+    return m;
+  }
   MvW reg_mv(const std::string& k, int c) {
+    if (cfg.mv_block == MVLDM_MV_STANDARD) return reg_standard(k, c);
     reg_norm(k + ".norm", c);
     reg_conv(k + ".proj_in", c, c, 1);
     const std::string tb = k + ".transformer_blocks.0";
@@ -398,7 +434,9 @@ struct mvldm_handle_s {
     MV_CUDA(cudaMemcpyAsync(temb_all.bias + r.temb_off, rawf(r.key + ".time_emb_proj.bias"), r.cout * sizeof(float),
                             cudaMemcpyDeviceToDevice, stream));
   }
-  Packed pack_qkv(const std::string& a, const MvW& m) {
+  // `fused`: the source is ONE [3C, C] matrix (transformer/attention.py:47, chunk(3) = q | k | v rows) instead of the
+  // three to_q / to_k / to_v matrices of mvdream/attention.py:168-170
+  Packed pack_qkv(const std::string& a, const MvW& m, bool fused = false) {
     const int H = m.heads;
     Packed p;
     p.n = 3 * H * m.dpad;
@@ -408,7 +446,8 @@ struct mvldm_handle_s {
     for (int t = 0; t < 3; ++t) {
       std::vector<int> map(m.c);
       for (int r = 0; r < m.c; ++r) map[r] = (t * H + r / m.d) * m.dpad + r % m.d;
-      pack_rows(stream, rawf(a + which[t] + ".weight"), m.c, m.c, m.c, p.w, p.k, 0, upload_map(map));
+      const float* src = fused ? rawf(a + ".to_qkv.weight") + (size_t)t * m.c * m.c : rawf(a + which[t] + ".weight");
+      pack_rows(stream, src, m.c, m.c, m.c, p.w, p.k, 0, upload_map(map));
     }
     // q/k/v have no bias in the reference; the packed GEMM's bias plants 1.0 in the first pad column of every V head,
     // which makes P.V deliver the softmax row sum in column d of the attention accumulator (attn_tc.cu)
@@ -432,7 +471,22 @@ struct mvldm_handle_s {
     p.bias = bias_sum(a + ".to_out.0.bias", "", m.c);
     return p;
   }
+  void pack_standard(MvW& m) {
+    for (size_t j = 0; j < m.layers.size(); ++j) {
+      const std::string lk = m.key + ".transformer.layers." + std::to_string(j);
+      MvW::StdLayer& y = m.layers[j];
+      y.ln1_g = rawf(lk + ".0.norm.weight");
+      y.ln1_b = rawf(lk + ".0.norm.bias");
+      y.ln2_g = rawf(lk + ".1.norm.weight");
+      y.ln2_b = rawf(lk + ".1.norm.bias");
+      y.qkv = pack_qkv(lk + ".0.fn", m, true);
+      y.out = pack_attn_out(lk + ".0.fn", m);
+      y.fc1 = pack_linear(lk + ".1.fn.net.0", m.d_mlp, m.c, true);
+      y.fc2 = pack_linear(lk + ".1.fn.net.3", m.c, m.d_mlp, true);
+    }
+  }
   void pack_mv(MvW& m) {
+    if (m.standard) return pack_standard(m);
     const std::string tb = m.key + ".transformer_blocks.0";
     m.gn_g = rawf(m.key + ".norm.weight");
     m.gn_b = rawf(m.key + ".norm.bias");
@@ -576,9 +630,12 @@ struct mvldm_handle_s {
     Step st;
     st.kind = cfg.impl == MVLDM_IMPL_SIMT ? Step::GEMM_SIMT : Step::GEMM;
     st.gemm = d;
+    // algorithmic bytes: weights once + every input segment once + the output (+ the residual), no re-reads
+    double bytes = 2.0 * (double)d.n * d.k + (d.mode == 2 ? 4.0 * M * d.n_valid : 2.0 * M * d.n * (d.mode == 1 ? 0.5 : 1.0));
+    for (int i = 0; i < d.nseg; ++i) bytes += 2.0 * (double)d.n_img * d.seg[i].sh * d.seg[i].sw * d.seg[i].c;
+    if (d.residual) bytes += 2.0 * M * d.n;
     st.meta = OpMeta{cat, "M" + std::to_string((long long)M) + " N" + std::to_string(d.n) + " K" + std::to_string(d.k),
-                     algo_flops >= 0 ? algo_flops : 2.0 * M * d.n * d.k,
-                     2.0 * ((double)d.n * d.k + M * d.n * (d.mode == 1 ? 0.5 : 1.0))};
+                     algo_flops >= 0 ? algo_flops : 2.0 * M * d.n * d.k, bytes};
     push_step(st);
   }
   // out = A-segments x W^T (+bias +rowvec +residual), bf16 NHWC
@@ -625,6 +682,8 @@ struct mvldm_handle_s {
     st.meta = OpMeta{seq > out.h * out.w ? "attention_joint" : "attention_per_view",
                      "batches" + std::to_string(batches) + " seq" + std::to_string(seq) + " d" + std::to_string(m.d),
                      4.0 * batches * (double)seq * seq * m.c, 2.0 * (double)out.tokens() * (4.0 * m.heads * m.dpad)};
+    st.meta.scores = (double)batches * m.heads * (double)seq * seq;
+    st.meta.flops_padded = 4.0 * batches * (double)seq * seq * m.heads * m.dpad;
     rec->steps.push_back(st);
   }
 
@@ -638,6 +697,8 @@ struct mvldm_handle_s {
     st.heads = m.heads; st.d = m.d; st.dpad = m.dpad;
     st.meta = OpMeta{"attention_joint_sharded", "seq_q" + std::to_string(seq_local) + " seq_kv" + std::to_string(seq_local * world),
                      4.0 * (double)seq_local * seq_local * world * m.c, 0.0};
+    st.meta.scores = (double)m.heads * seq_local * (double)seq_local * world;
+    st.meta.flops_padded = 4.0 * (double)seq_local * seq_local * world * m.heads * m.dpad;
     rec->steps.push_back(st);
   }
 
@@ -682,7 +743,40 @@ struct mvldm_handle_s {
     }
   }
 
+  // StandardTransformer.forward (standard/transformer.py:96-136 with downscale 1, pos_enc off) around
+  // Transformer.forward (transformer/transformer.py:68-72): tokens "b v c h w -> b (v h w) c" are this library's NHWC rows
+  Act standard_block(const MvW& m, const Act& x) {
+    const int n = x.n, h = x.h, w = x.w, C = m.c, H = m.heads;
+    const int hw = h * w;
+    Act cur = x;
+    Act out = new_act(n, h, w, C);
+    const size_t mark = arena.off;
+    Act nrm = new_act(n, h, w, C);
+    Act qkv = new_act(n, h, w, 3 * H * m.dpad);
+    Act o = new_act(n, h, w, H * m.dpad);
+    Act f = new_act(n, h, w, m.d_mlp);
+    for (size_t j = 0; j < m.layers.size(); ++j) {
+      const MvW::StdLayer& y = m.layers[j];
+      const bool last = j + 1 == m.layers.size();
+      ln(cur, y.ln1_g, y.ln1_b, nrm);
+      gemm({seg_1x1(nrm)}, y.qkv, qkv, nullptr, 0, nullptr, 0, 6.0 * (double)x.tokens() * C * C);
+      if (sharded) joint_attention_sharded(qkv, o, scene_views[0] * hw, m);
+      else joint_attention(qkv, o, m);
+      Act t1 = new_act(n, h, w, C);
+      gemm({seg_1x1(o)}, y.out, t1, nullptr, 0, &cur, 0, 2.0 * (double)x.tokens() * C * C);
+      if (j == 0) tap(m.key + ".attn", t1);
+      ln(t1, y.ln2_g, y.ln2_b, nrm);
+      gemm({seg_1x1(nrm)}, y.fc1, f, nullptr, 0, nullptr, 5);
+      Act t2 = last ? out : new_act(n, h, w, C);
+      gemm({seg_1x1(f)}, y.fc2, t2, nullptr, 0, &t1);
+      cur = t2;
+    }
+    if (!taps_enabled) arena.off = mark;
+    return out;
+  }
+
   Act mv_block(const MvW& m, const Act& x) {
+    if (m.standard) return standard_block(m, x);
     const int n = x.n, h = x.h, w = x.w, C = m.c, H = m.heads;
     const int hw = h * w;
     Act out = new_act(n, h, w, C);
@@ -1055,7 +1149,7 @@ static const char* profile_report(mvldm_handle_s* h) {
   Plan& p = *h->prof_plan;
   struct Agg {
     int n = 0;
-    double us = 0, flops = 0, bytes = 0;
+    double us = 0, flops = 0, bytes = 0, scores = 0, flops_padded = 0;
   };
   std::map<std::string, Agg> agg;
   std::string ops = "[";
@@ -1066,7 +1160,7 @@ static const char* profile_report(mvldm_handle_s* h) {
     MV_CUDA(cudaEventElapsedTime(&ms, h->event_pool[ev], h->event_pool[ev + 1]));
     ev += 2;
     Agg& a = agg[m.cat];
-    a.n++; a.us += ms * 1e3; a.flops += m.flops; a.bytes += m.bytes;
+    a.n++; a.us += ms * 1e3; a.flops += m.flops; a.bytes += m.bytes; a.scores += m.scores; a.flops_padded += m.flops_padded;
     char buf[320];
     snprintf(buf, sizeof buf, "%s{\"cat\":\"%s\",\"what\":\"%s\",\"us\":%.2f,\"gflop\":%.3f}", i ? "," : "", m.cat,
              m.what.c_str(), ms * 1e3, m.flops * 1e-9);
@@ -1076,9 +1170,11 @@ static const char* profile_report(mvldm_handle_s* h) {
   std::string out = "{\"categories\":{";
   bool first = true;
   for (auto& kv : agg) {
-    char buf[256];
-    snprintf(buf, sizeof buf, "%s\"%s\":{\"launches\":%d,\"us\":%.2f,\"gflop\":%.3f,\"mbytes\":%.3f}", first ? "" : ",",
-             kv.first.c_str(), kv.second.n, kv.second.us, kv.second.flops * 1e-9, kv.second.bytes * 1e-6);
+    char buf[384];
+    snprintf(buf, sizeof buf,
+             "%s\"%s\":{\"launches\":%d,\"us\":%.2f,\"gflop\":%.3f,\"mbytes\":%.3f,\"gscores\":%.4f,\"gflop_padded\":%.3f}",
+             first ? "" : ",", kv.first.c_str(), kv.second.n, kv.second.us, kv.second.flops * 1e-9, kv.second.bytes * 1e-6,
+             kv.second.scores * 1e-9, kv.second.flops_padded * 1e-9);
     out += buf;
     first = false;
   }
@@ -1129,6 +1225,13 @@ int mvldm_create(const mvldm_config* cfg, int device, mvldm_handle* out) {
   }
   MV_CHECK(cfg->variant == 0 || cfg->variant == 1, "variant must be 0 (A) or 1 (B)");
   if (cfg->variant == 1) MV_CHECK(cfg->cross_attention_dim > 0, "variant B needs cross_attention_dim");
+  MV_CHECK(cfg->mv_block == MVLDM_MV_SPATIAL_TRANSFORMER_3D || cfg->mv_block == MVLDM_MV_STANDARD,
+           "mv_block must be MVLDM_MV_SPATIAL_TRANSFORMER_3D or MVLDM_MV_STANDARD");
+  if (cfg->mv_block == MVLDM_MV_STANDARD) {
+    MV_CHECK(cfg->mv_num_layers >= 1 && cfg->mv_num_layers <= 8, "standard transformer: num_layers must be in [1, 8]");
+    MV_CHECK((cfg->mv_d_mlp > 0) != (cfg->mv_d_mlp_multiplier > 0),
+             "standard transformer: exactly one of d_mlp and d_mlp_multiplier (standard/transformer.py:63-64)");
+  }
   h->build_registry();
   *out = h.release();
   MV_API_END

@@ -50,7 +50,20 @@ class SpatialTransformer3DCfg:
     pos_enc: bool = False
 
 
-MultiViewAttentionCfg = SpatialTransformer3DCfg
+@dataclass
+class CrossAttentionCfg:
+    """reference src/model/denoiser/standard/transformer.py:34-43 (multi_view_attention/standard_attention.yaml)"""
+    name: Literal["standard"]
+    num_heads: int
+    num_layers: int = 1
+    d_dot: int | None = None
+    d_mlp: int | None = None
+    d_mlp_multiplier: int | None = None
+    downscale: int = 1
+    pos_enc: bool = False
+
+
+MultiViewAttentionCfg = CrossAttentionCfg | SpatialTransformer3DCfg    # reference src/model/denoiser/attention.py:6
 
 
 @dataclass
@@ -76,6 +89,15 @@ def default_cfg(num_heads: int = 8) -> MultiViewUNetCfg:
         use_ray_encoding=False)
 
 
+def standard_cfg(num_heads: int = 8, d_mlp_multiplier: int = 1, num_layers: int = 1) -> MultiViewUNetCfg:
+    """mv_unet.yaml's own default `multi_view_attention: standard_attention` (config/model/denoiser/mv_unet.yaml:5,
+    multi_view_attention/standard_attention.yaml): StandardTransformer blocks at the 9 multi-view positions."""
+    cfg = default_cfg(num_heads)
+    cfg.multi_view_attention = CrossAttentionCfg("standard", num_heads=num_heads, num_layers=num_layers,
+                                                 d_mlp_multiplier=d_mlp_multiplier)
+    return cfg
+
+
 class Denoiser(nn.Module, ABC, Generic[T]):
     cfg: T
 
@@ -96,7 +118,7 @@ SD21_CROSS_ATTENTION_DIM = 1024
 
 
 def param_shapes(block_out_channels, in_channels: int, out_channels: int, layers_per_block: int = 2,
-                 variant_b: bool = False) -> "Dict[str, Tuple[int, ...]]":
+                 variant_b: bool = False, standard: "CrossAttentionCfg | None" = None) -> "Dict[str, Tuple[int, ...]]":
     """State-dict keys and shapes of the MultiViewUNet; must equal the registry the C
     library builds in ``mvldm_create`` (checked at handle creation).  ``variant_b`` adds the SD-2.1 pieces:
     ``unet.{down_blocks.0-2,mid_block,up_blocks.1-3}.attentions.*`` and ``unet.mid_block.resnets.1``."""
@@ -124,6 +146,15 @@ def param_shapes(block_out_channels, in_channels: int, out_channels: int, layers
             conv(k + ".conv_shortcut", co, ci, 1)
 
     def mv(k, c):
+        if standard is not None:
+            # StandardTransformer(d_in=c).transformer = Transformer(c, num_layers, heads, c // heads, d_mlp) with
+            # layers.J = [PreNorm(Attention), PreNorm(FeedForward)]  (transformer/transformer.py:24-47)
+            d_mlp = standard.d_mlp or c * standard.d_mlp_multiplier
+            for j in range(standard.num_layers):
+                lk = f"{k}.transformer.layers.{j}"
+                norm(lk + ".0.norm", c); lin(lk + ".0.fn.to_qkv", 3 * c, c, bias=False); lin(lk + ".0.fn.to_out.0", c, c)
+                norm(lk + ".1.norm", c); lin(lk + ".1.fn.net.0", d_mlp, c); lin(lk + ".1.fn.net.3", c, d_mlp)
+            return
         norm(k + ".norm", c); conv(k + ".proj_in", c, c, 1)
         tb = k + ".transformer_blocks.0"
         for a in ("attn1", "attn2"):
@@ -224,9 +255,19 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
                  use_cuda_graph: bool = True) -> None:
         super().__init__(cfg)
         self.variant_b = cfg.pretrained_from is not None
-        if cfg.multi_view_attention.name != "spatial_transformer_3d":
-            raise ValueError("only multi_view_attention.name == 'spatial_transformer_3d' is supported")
-        if cfg.multi_view_attention.num_layers != 1 or cfg.multi_view_attention.d_dot is not None:
+        mva = cfg.multi_view_attention
+        if mva.name not in ("spatial_transformer_3d", "standard"):
+            raise ValueError("multi_view_attention.name must be 'spatial_transformer_3d' or 'standard' "
+                             "(reference src/model/denoiser/attention.py:12-27)")
+        self.standard = mva.name == "standard"
+        if self.standard:
+            # StandardTransformer.__init__ asserts this (standard/transformer.py:63-64)
+            if (mva.d_mlp is None) == (mva.d_mlp_multiplier is None):
+                raise ValueError("Expected exactly one of d_mlp and d_mlp_multiplier")
+            if mva.d_dot is not None or mva.downscale != 1 or mva.pos_enc or not (1 <= mva.num_layers <= 8):
+                raise ValueError("standard multi_view_attention: supported are d_dot None (= d_in // num_heads), "
+                                 "downscale 1, pos_enc false, 1 <= num_layers <= 8")
+        elif mva.num_layers != 1 or mva.d_dot is not None:
             raise ValueError("multi_view_attention: num_layers must be 1 and d_dot None")
         if not (cfg.encoder_conditioning and cfg.mid_conditioning and cfg.decoder_conditioning):
             raise ValueError("encoder/mid/decoder_conditioning must all be true")
@@ -249,7 +290,8 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
         self.pretrained_from = cfg.pretrained_from
         self.in_channels, self.out_channels = in_channels, out_channels
         self.impl, self.use_cuda_graph = impl, use_cuda_graph
-        self._shapes = param_shapes(self._boc, in_channels, out_channels, variant_b=self.variant_b)
+        self._shapes = param_shapes(self._boc, in_channels, out_channels, variant_b=self.variant_b,
+                                    standard=mva if self.standard else None)
         for key, shape in self._shapes.items():
             self._register(key, self._init_param(key, shape))
         self._h = _Handle()
@@ -309,6 +351,10 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
         c.max_attn_res = 32
         c.impl = self.impl
         c.use_cuda_graph = 1 if self.use_cuda_graph else 0
+        if self.standard:
+            mva = self.cfg.multi_view_attention
+            c.mv_block, c.mv_num_layers = _lib.MV_STANDARD, mva.num_layers
+            c.mv_d_mlp, c.mv_d_mlp_multiplier = mva.d_mlp or 0, mva.d_mlp_multiplier or 0
         if self.variant_b:
             c.variant, c.cross_attention_dim = 1, SD21_CROSS_ATTENTION_DIM
             for i, v in enumerate(SD21_HEADS):

@@ -65,13 +65,56 @@ def stats(t):
     return np.concatenate([[f.mean().item(), f.std().item(), f.abs().max().item()], f[idx].numpy()])
 
 
+def golden_standard():
+    """G7: the reference's DEFAULT multi-view block (config/model/denoiser/mv_unet.yaml:5 -> standard_attention.yaml):
+    `StandardTransformer` at the 9 multi-view positions, V = 4 (2 context + 2 target), fp32 CPU.  The reference's
+    Attention pins SDPA to the EFFICIENT_ATTENTION backend (transformer/attention.py:94), which has no CPU
+    implementation; the context manager is made a no-op for this call only (same math: softmax(q k^T / sqrt(d)) v;
+    the reference source is untouched)."""
+    import contextlib
+    import src.model.transformer.attention as ref_attn
+    from src.model.denoiser.standard.transformer import CrossAttentionCfg
+    cfg_s = O.OracleCfg(mv_block="standard")
+    sd_s = O.init_weights(cfg_s, seed=0)
+    ucfg = UNet2DModelCfg("unet", ["DownBlock2D"] * 4, "UNetMidBlock2D", ["UpBlock2D"] * 4, False, [320, 640, 1280, 1280])
+    mcfg = MultiViewUNetCfg("mv_unet", ucfg, CrossAttentionCfg("standard", num_heads=8, d_mlp_multiplier=1),
+                            use_ray_encoding=False)
+    ref_s = MultiViewUNet(mcfg, 11, 4)
+    ref_s.load_state_dict(sd_s, strict=True)      # strict: the oracle's / library's key names == the module's
+    ref_s.eval()
+    ctx, x_T, extr, intr = O.synthetic_scene(1, 2, 2)
+    rays = reference_rays(extr, intr, 32, 32, False)
+    inp, _ = O.build_inputs(x_T, torch.cat([ctx, torch.zeros(1, 2, 1, 32, 32)], 2), rays, torch.ones(1, 2, 1, 32, 32))
+    ts = torch.tensor([[0, 0, 500, 500]])
+    orig = ref_attn.sdpa_kernel
+    ref_attn.sdpa_kernel = lambda *a, **k: contextlib.nullcontext()
+    try:
+        t0 = time.time()
+        y_ref = ref_s.forward(inp, ts)
+    finally:
+        ref_attn.sdpa_kernel = orig
+    taps = {}
+    y_ora = O.unet_forward(sd_s, inp, ts, cfg_s, taps)
+    err = (y_ref - y_ora).abs().max().item()
+    print(f"g7_forward_standard_v4: ref {time.time() - t0:.1f}s  max|ref-oracle| = {err:.3e}  std {y_ref.std().item():.4f}")
+    assert err < 1e-4 * y_ref.abs().max().item() + 1e-5
+    out = {"inputs": inp.numpy(), "timesteps": ts.numpy(), "eps": y_ref.numpy()}
+    for k, v in taps.items():
+        out["tap/" + k] = stats(v)
+    np.savez_compressed(os.path.join(GOLD, "g7_forward_standard_v4.npz"), **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-trajectory", action="store_true")
     ap.add_argument("--skip-variant-b", action="store_true")
+    ap.add_argument("--only-standard", action="store_true", help="(re)generate only g7 (StandardTransformer blocks)")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_grad_enabled(False)
+    golden_standard()
+    if args.only_standard:
+        return
     cfg = O.OracleCfg()
     sd = O.init_weights(cfg, seed=0)
     ref = build_reference(sd)

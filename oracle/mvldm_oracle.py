@@ -57,6 +57,11 @@ class OracleCfg:
     variant_b: bool = False
     t2d_heads: Tuple[int, ...] = (5, 10, 20, 20)
     cross_attention_dim: int = 1024
+    # multi_view_attention.name (src/model/denoiser/attention.py:8-27): "spatial_transformer_3d" (released experiment) or
+    # "standard" (mv_unet.yaml's default): StandardTransformer, standard/transformer.py:45-136
+    mv_block: str = "spatial_transformer_3d"
+    mv_num_layers: int = 1
+    mv_d_mlp_multiplier: int = 1       # multi_view_attention/standard_attention.yaml:8
 
     @property
     def temb_dim(self) -> int:
@@ -110,6 +115,16 @@ def param_shapes(cfg: OracleCfg) -> "Dict[str, Tuple[Tuple[int, ...], str]]":
             conv(k + ".conv_shortcut", cout, cin, 1)
 
     def mvblock(k, c):
+        if cfg.mv_block == "standard":   # Transformer(c, depth, heads, c // heads, c * mult): transformer/transformer.py:24-47
+            for j in range(cfg.mv_num_layers):
+                lk = f"{k}.transformer.layers.{j}"
+                norm(lk + ".0.norm", c)
+                lin(lk + ".0.fn.to_qkv", 3 * c, c, bias=False)
+                lin(lk + ".0.fn.to_out.0", c, c)
+                norm(lk + ".1.norm", c)
+                lin(lk + ".1.fn.net.0", c * cfg.mv_d_mlp_multiplier, c)
+                lin(lk + ".1.fn.net.3", c, c * cfg.mv_d_mlp_multiplier)
+            return
         norm(k + ".norm", c)
         conv(k + ".proj_in", c, c, 1)
         tb = k + ".transformer_blocks.0"
@@ -263,8 +278,34 @@ def _attention(sd, k: str, x: Tensor, heads: int) -> Tensor:
     return F.linear(out, sd[k + ".to_out.0.weight"], sd[k + ".to_out.0.bias"])
 
 
-def mv_block(sd, k: str, x: Tensor, b: int, v: int, heads: int, groups: int,
-             taps: Optional[dict] = None) -> Tensor:
+def standard_block(sd, k: str, x: Tensor, b: int, v: int, heads: int, layers: int,
+                   taps: Optional[dict] = None) -> Tensor:
+    """``StandardTransformer.forward`` (standard/transformer.py:96-136; downscale 1, pos_enc off) around
+    ``Transformer.forward`` (transformer/transformer.py:68-72): per layer ``x = attn(LN(x)) + x; x = ff(LN(x)) + x`` with
+    ``Attention`` (transformer/attention.py:59-99: fused bias-free to_qkv, chunk(3), softmax(q k^T / sqrt(d)) v over ALL
+    (view, pixel) tokens of the scene, to_out Linear) and ``FeedForward`` (feed_forward.py:28-39: Linear, exact GELU,
+    Linear).  ``x`` is [(b v), c, h, w]."""
+    bv, c, h, w = x.shape
+    d = c // heads
+    y = x.reshape(b, v, c, h, w).permute(0, 1, 3, 4, 2).reshape(b, v * h * w, c)     # "b v c h w -> b (v h w) c"
+    for j in range(layers):
+        lk = f"{k}.transformer.layers.{j}"
+        z = F.layer_norm(y, (c,), sd[lk + ".0.norm.weight"], sd[lk + ".0.norm.bias"], eps=1e-5)
+        q, kk, vv = F.linear(z, sd[lk + ".0.fn.to_qkv.weight"]).chunk(3, dim=-1)
+        sp = lambda t: t.reshape(b, -1, heads, d).permute(0, 2, 1, 3)                # noqa: E731  "b n (h d) -> b h n d"
+        att = torch.softmax(sp(q) @ sp(kk).transpose(-1, -2) * d ** -0.5, dim=-1) @ sp(vv)
+        att = att.permute(0, 2, 1, 3).reshape(b, -1, c)
+        y = F.linear(att, sd[lk + ".0.fn.to_out.0.weight"], sd[lk + ".0.fn.to_out.0.bias"]) + y
+        if taps is not None and j == 0:
+            taps[k + ".attn"] = y.reshape(bv, h * w, c)
+        z = F.layer_norm(y, (c,), sd[lk + ".1.norm.weight"], sd[lk + ".1.norm.bias"], eps=1e-5)
+        z = F.gelu(F.linear(z, sd[lk + ".1.fn.net.0.weight"], sd[lk + ".1.fn.net.0.bias"]))
+        y = F.linear(z, sd[lk + ".1.fn.net.3.weight"], sd[lk + ".1.fn.net.3.bias"]) + y
+    return y.reshape(b, v, h, w, c).permute(0, 1, 4, 2, 3).reshape(bv, c, h, w)
+
+
+def _mv_block_3d(sd, k: str, x: Tensor, b: int, v: int, heads: int, groups: int,
+                 taps: Optional[dict] = None) -> Tensor:
     """``SpatialTransformer3D.forward`` (mvdream/attention.py:416-439) with one
     ``BasicTransformerBlock3D`` (:362-368).  ``x`` is [(b v), c, h, w]."""
     bv, c, h, w = x.shape
@@ -348,6 +389,11 @@ def unet_forward(sd: Dict[str, Tensor], latents: Tensor, timestep: Tensor, cfg: 
     def tap(name, t):
         if taps is not None:
             taps[name] = t
+
+    def mv_block(sd_, k, x_, b, v, heads, groups, taps_):       # multi_view_attention.name picks the block
+        if cfg.mv_block == "standard":
+            return standard_block(sd_, k, x_, b, v, heads, cfg.mv_num_layers, taps_)
+        return _mv_block_3d(sd_, k, x_, b, v, heads, groups, taps_)
 
     x = latents.reshape(B * V, *latents.shape[2:])
     x = F.conv2d(x, sd["unet.conv_in.weight"], sd["unet.conv_in.bias"], padding=1)

@@ -337,6 +337,57 @@ def test_variant_b_forward_matches_reference(impl):
         assert rel_err(y2, ref) < 1e-5
 
 
+@pytest.mark.parametrize("impl", [pytest.param(0, id="tcgen05"), pytest.param(1, id="simt")])
+def test_standard_transformer_forward_matches_reference(impl):
+    """multi_view_attention.name == "standard" (the reference's default config):
+    `StandardTransformer` blocks (standard/transformer.py:45-136) at the 9 multi-view positions - pre-LN joint attention over
+    all views' tokens + GELU MLP.  Golden g7 is the reference module's own output; the per-block taps come from the oracle."""
+    cfg_s = O.OracleCfg(mv_block="standard")
+    sd = O.init_weights(cfg_s, seed=0)
+    g = np.load(os.path.join(GOLD, "g7_forward_standard_v4.npz"))
+    inp, ts, ref = torch.tensor(g["inputs"]), torch.tensor(g["timesteps"]), torch.tensor(g["eps"])
+    m = mv.MultiViewUNet(mv.standard_cfg(), 11, 4, impl=impl, use_cuda_graph=(impl == 0))
+    m.load_state_dict(sd)                                           # strict
+    m = m.cuda().eval()
+    m.enable_taps(True)
+    y = m(inp.cuda(), ts.cuda()).cpu()
+    taps = {}
+    with torch.no_grad():
+        y_ora = O.unet_forward(sd, inp, ts, cfg_s, taps)
+    assert rel_err(y_ora, ref) < 1e-4                               # oracle == reference module (golden)
+    drift = _oracle_bf16_drift(sd, cfg_s, inp, ts, ref)
+    err = rel_err(y, ref)
+    print(f"standard impl={impl}: err {err:.3e}  reference-bf16-autocast drift {drift:.3e}  launches {m.last_launch_count()}")
+    assert err < max(2 * drift, FWD_TOL)
+    assert rms_err(y, ref) < max(2 * drift, FWD_TOL)
+    n_attn = 0
+    for k, v in taps.items():
+        t = m.tap(k).cpu()
+        got = t.reshape(v.shape) if v.dim() == 4 else t.reshape(v.shape[0], v.shape[2], v.shape[1]).permute(0, 2, 1)
+        assert rel_err(got, v) < max(2 * drift, FWD_TOL), k
+        n_attn += k.endswith(".attn")
+    assert n_attn == 9
+    m.enable_taps(False)
+    if impl == 0:
+        assert torch.equal(m(inp.cuda(), ts.cuda()).cpu(), y)      # graph replay is bit-stable
+
+
+def test_standard_transformer_two_layers_and_wide_mlp():
+    """num_layers = 2, d_mlp_multiplier = 4 (CrossAttentionCfg fields, standard/transformer.py:34-43) against the oracle"""
+    cfg_s = O.OracleCfg(mv_block="standard", mv_num_layers=2, mv_d_mlp_multiplier=4)
+    sd = O.init_weights(cfg_s, seed=3)
+    torch.manual_seed(4)
+    x = torch.randn(1, 3, 11, 16, 16)
+    t = torch.tensor([[0, 400, 400]])
+    with torch.no_grad():
+        ref = O.unet_forward(sd, x, t, cfg_s)
+    m = mv.MultiViewUNet(mv.standard_cfg(d_mlp_multiplier=4, num_layers=2), 11, 4)
+    m.load_state_dict(sd)
+    y = m.cuda().eval()(x.cuda(), t.cuda()).cpu()
+    drift = _oracle_bf16_drift(sd, cfg_s, x, t, ref)
+    assert rel_err(y, ref) < max(2 * drift, FWD_TOL)
+
+
 def test_forward_scenes_unequal_view_counts(gpu_models):
     """mvldm_forward_scenes: scenes of 3, 5 and 3 views in one pass == each scene through the uniform entry point
     (within the bf16 band: split-K schedules depend on the tile count), reruns bit-identical, bad arguments raise."""

@@ -113,6 +113,21 @@ def test_time_embedding_shaped_gemms(impl):
     assert rel_err(out32, ref) < 1e-5 if impl != 1 else rel_err(out32, ref) < 1e-4
 
 
+@pytest.mark.parametrize("impl", [pytest.param(0, id="tcgen05"), pytest.param(1, id="simt")])
+def test_gelu_epilogue_gemm(impl):
+    """mode 5: bias + exact (erf) GELU, the first Linear of the StandardTransformer FeedForward
+    (reference src/model/transformer/feed_forward.py:31-33)"""
+    torch.manual_seed(9)
+    n, hw, K, N = 2, 16, 640, 640
+    a = torch.randn(n, hw, hw, K).to(torch.bfloat16).cuda()
+    w = (torch.randn(N, K) / K ** 0.5).to(torch.bfloat16).cuda()
+    b = torch.randn(N).cuda()
+    ref = F.gelu(a.float().reshape(-1, K) @ w.float().t() + b)
+    out = torch.empty((n * hw * hw, N), device="cuda", dtype=torch.bfloat16)
+    run_gemm(impl, [conv_seg(a, 1, 1)], n, hw, hw, w, bias=b, mode=5, out=out)
+    assert rel_err(out.float(), ref) < BF16_TOL
+
+
 def test_splitk_epilogue_and_segments():
     """split-K path with bias + per-image row vector + residual, and with the 3-segment conv+shortcut operand"""
     torch.manual_seed(6)

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     import ctypes
-    assert ctypes.sizeof(_lib.Config) == 4 * (3 + 4 + 6 + 1 + 4 + 1)
+    assert ctypes.sizeof(_lib.Config) == 4 * (3 + 4 + 6 + 1 + 4 + 1 + 4)
     assert ctypes.sizeof(_lib.ASeg) == 8 + 6 * 4 + 9 + 9 + 2 + 9 * 4      # ptr, 6 ints, 2x9 int8 (+2 pad), 9 ints
     assert _lib.GemmDesc.seg.offset == 8 and ctypes.sizeof(_lib.GemmDesc) % 8 == 0
 
@@ -65,6 +65,26 @@ def test_variant_b_state_dict_keys_match_reference_module():
     # only the multi-view blocks' proj_out is zero-initialised, not the Transformer2DModels'
     assert float(sd["cross_attn_blocks_mid.0.proj_out.weight"].abs().max()) == 0.0
     assert float(sd["unet.mid_block.attentions.0.proj_out.weight"].abs().max()) > 0.0
+
+
+def test_standard_transformer_state_dict_keys_match_reference_module():
+    """multi_view_attention "standard": keys / shapes of StandardTransformer.transformer (make_golden loads the oracle's
+    dict into the reference module strict=True, so the oracle's table IS the reference's)."""
+    m = mv.MultiViewUNet(mv.standard_cfg(), 11, 4)
+    sd = m.state_dict()
+    ref = O.param_shapes(O.OracleCfg(mv_block="standard"))
+    assert set(sd) == set(ref)
+    assert all(tuple(sd[k].shape) == ref[k][0] for k in ref)
+    assert tuple(sd["cross_attn_blocks_decoder.3.transformer.layers.0.0.fn.to_qkv.weight"].shape) == (960, 320)
+    assert not any(".proj_out." in k or ".transformer_blocks." in k for k in sd if k.startswith("cross_attn_blocks_"))
+    wide = mv.MultiViewUNet(mv.standard_cfg(d_mlp_multiplier=4, num_layers=2), 11, 4).state_dict()
+    assert tuple(wide["cross_attn_blocks_mid.0.transformer.layers.1.1.fn.net.0.weight"].shape) == (5120, 1280)
+    for bad in (dict(d_dot=32), dict(downscale=2), dict(pos_enc=True), dict(d_mlp=640), dict(num_layers=0)):
+        cfg = mv.standard_cfg()
+        for k, v in bad.items():
+            setattr(cfg.multi_view_attention, k, v)                 # d_mlp AND d_mlp_multiplier both set: the reference asserts
+        with pytest.raises(ValueError):
+            mv.MultiViewUNet(cfg, 11, 4)
 
 
 def test_unsupported_configs_raise():

@@ -83,3 +83,20 @@ def test_variant_b_matches_reference():
     with torch.no_grad():
         y = O.unet_forward(sd, torch.tensor(g["inputs"]), torch.tensor(g["timesteps"]), cfg)
     assert rel_err(y, torch.tensor(g["eps"])) < 1e-4
+
+
+def test_standard_transformer_matches_reference():
+    """multi_view_attention "standard" (mv_unet.yaml's default): the oracle's restatement of StandardTransformer
+    (standard/transformer.py:45-136, transformer/{transformer,attention,feed_forward,pre_norm}.py) against golden g7, the
+    reference module's own output (oracle/make_golden.py golden_standard)."""
+    cfg = O.OracleCfg(mv_block="standard")
+    shapes = O.param_shapes(cfg)
+    assert "cross_attn_blocks_mid.0.transformer.layers.0.0.fn.to_qkv.weight" in shapes
+    assert shapes["cross_attn_blocks_encoder.1.transformer.layers.0.1.fn.net.3.weight"][0] == (640, 640)
+    g = np.load(os.path.join(GOLD, "g7_forward_standard_v4.npz"))
+    sd = O.init_weights(cfg, seed=0)
+    taps = {}
+    with torch.no_grad():
+        y = O.unet_forward(sd, torch.tensor(g["inputs"]), torch.tensor(g["timesteps"]), cfg, taps)
+    assert rel_err(y, torch.tensor(g["eps"])) < 1e-4
+    assert sum(k.endswith(".attn") for k in taps) == 9

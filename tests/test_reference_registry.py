@@ -78,3 +78,27 @@ def test_reference_config_variants_are_validated(ref_pkg):
                            SpatialTransformer3DCfg("spatial_transformer_3d", num_heads=8), use_ray_encoding=False)
     with pytest.raises(ValueError):
         mv.MultiViewUNet(bad, 11, 4)
+
+
+def test_standard_attention_config_through_reference_factory(ref_pkg):
+    """the reference's default multi_view_attention (standard_attention.yaml -> CrossAttentionCfg, attention.py:12-19)
+    through the reference's factory with the registry edit; the reference module's state dict loads strictly"""
+    import mvldm_b200 as mv
+    from src.model.denoiser.standard.transformer import CrossAttentionCfg
+    ref_den, MultiViewUNetCfg, UNet2DModelCfg, _ = ref_pkg
+    cfg = MultiViewUNetCfg("mv_unet",
+                           UNet2DModelCfg("unet", ["DownBlock2D"] * 4, "UNetMidBlock2D", ["UpBlock2D"] * 4, False,
+                                          [320, 640, 1280, 1280]),
+                           CrossAttentionCfg("standard", num_heads=8, d_mlp_multiplier=1), use_ray_encoding=False)
+    theirs = ref_den.get_denoiser(cfg, 11, 4)
+    original = ref_den.DENOISER["mv_unet"]
+    ref_den.DENOISER["mv_unet"] = mv.MultiViewUNet
+    try:
+        ours = ref_den.get_denoiser(cfg, 11, 4)
+    finally:
+        ref_den.DENOISER["mv_unet"] = original
+    sd = theirs.state_dict()
+    res = ours.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert set(ours.state_dict()) == set(sd)
+    assert sum(p.numel() for p in ours.parameters()) == sum(p.numel() for p in theirs.parameters())

@@ -1,34 +1,79 @@
-"""Turn gpurun_out/final (tools/run_final.sh) into the tracked summaries under profiles/ (prefix r01_final_)."""
+"""Turn gpurun_out/final (tools/run_final.sh) into the tracked summaries under profiles/ (prefix rNN_final_; the round
+is argv[1], default 2)."""
 import collections, csv, io, json, os, re, shutil, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC, DST, PRE = os.path.join(ROOT, "gpurun_out", "final"), os.path.join(ROOT, "profiles"), "r01_final_"
+ROUND = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+SRC, DST, PRE = os.path.join(ROOT, "gpurun_out", "final"), os.path.join(ROOT, "profiles"), f"r{ROUND:02d}_final_"
 
 
 def copy(src, dst):
     shutil.copyfile(os.path.join(SRC, src), os.path.join(DST, PRE + dst))
 
 
-def launch_summary(name, header):
+def short_name(k):
+    return re.sub(r"^void |\(.*$|mvldm::|<unnamed>::|unnamed>::|at::native::.*?::", "", k)[:46]
+
+
+def read_launches(name):
+    """ncu --csv raw rows (one per launch x metric) -> list of {name, us, dram_bytes} in launch order"""
     rows = [l for l in open(os.path.join(SRC, name)) if l.startswith('"')]
     rd = list(csv.DictReader(io.StringIO("".join(rows))))
+    out, by_id = [], {}
+    for r in rd:
+        e = by_id.get(r["ID"])
+        if e is None:
+            e = by_id[r["ID"]] = {"name": r["Kernel Name"], "us": 0.0, "dram_bytes": 0.0}
+            out.append(e)
+        v, u = float(r["Metric Value"].replace(",", "")), r["Metric Unit"]
+        if r["Metric Name"] == "gpu__time_duration.sum":
+            e["us"] = v * {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3}.get(u, 1.0)
+        elif r["Metric Name"].startswith("dram__bytes"):
+            e["dram_bytes"] += v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1.0)
+    return out
+
+
+def one_step(launches):
     # one whole DDIM step = build_inputs_kernel ... ddim_step_kernel; take the last complete one (the launches after it
     # belong to bench.py's per-op profiling pass)
-    ends = [i for i, r in enumerate(rd) if "ddim_step_kernel" in r["Kernel Name"]]
-    begins = [i for i, r in enumerate(rd) if "build_inputs_kernel" in r["Kernel Name"] and i < ends[-1]]
-    step = rd[begins[-1]:ends[-1] + 1]
+    ends = [i for i, r in enumerate(launches) if "ddim_step_kernel" in r["name"]]
+    begins = [i for i, r in enumerate(launches) if "build_inputs_kernel" in r["name"] and i < ends[-1]]
+    return launches[begins[-1]:ends[-1] + 1]
+
+
+def launch_summary(name, header):
+    step = one_step(read_launches(name))
     agg = collections.OrderedDict()
     for r in step:
-        k = re.sub(r"^void |\(.*$|mvldm::|<unnamed>::|unnamed>::|at::native::.*?::", "", r["Kernel Name"])[:46]
-        a = agg.setdefault(k, [0, 0.0])
+        a = agg.setdefault(short_name(r["name"]), [0, 0.0, 0.0])
         a[0] += 1
-        a[1] += float(r["Metric Value"]) * (1e-3 if r["Metric Unit"] in ("ns", "nsecond") else 1.0)
+        a[1] += r["us"]
+        a[2] += r["dram_bytes"]
     tot = sum(a[1] for a in agg.values())
     out = [header, ""]
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        out.append(f"{k:46s} launches {a[0]:4d} {a[1]:9.1f} us {100 * a[1] / tot:5.1f}%  avg {a[1] / a[0]:6.1f} us")
-    out.append(f"total {tot:.1f} us over {sum(a[0] for a in agg.values())} launches")
+        out.append(f"{k:46s} launches {a[0]:4d} {a[1]:9.1f} us {100 * a[1] / tot:5.1f}%  avg {a[1] / a[0]:6.1f} us"
+                   f"  dram {a[2] / 1e6:9.1f} MB ({a[2] / max(a[0], 1) / 1e6:7.2f} MB/launch)")
+    out.append(f"total {tot:.1f} us over {sum(a[0] for a in agg.values())} launches, "
+               f"dram {sum(a[2] for a in agg.values()) / 1e6:.1f} MB")
     return "\n".join(out) + "\n"
+
+
+def traffic_json(name, source):
+    """per-kernel DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of one DDIM step: bench.py's
+    roofline.traffic reads this file"""
+    step = one_step(read_launches(name))
+    agg = {}
+    for r in step:
+        k = short_name(r["name"]).split("<")[0]
+        a = agg.setdefault(k, {"launches": 0, "dram_bytes": 0.0, "us": 0.0})
+        a["launches"] += 1
+        a["dram_bytes"] += r["dram_bytes"]
+        a["us"] += r["us"]
+    for a in agg.values():
+        a["dram_bytes_per_launch"] = a["dram_bytes"] / a["launches"]
+    agg["source"] = source
+    return agg
 
 
 WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
@@ -68,26 +113,34 @@ def main():
                  ("bench_8scenes.json", "bench_8scenes_per_gpu.json"), ("bench_reference.json", "bench_reference_cpu.json"),
                  ("clocks.csv", "clocks.csv"), ("scale_check.txt", "scale_check.txt"), ("prof_ops.txt", "ops_and_timelines.txt"),
                  ("gn_graph_bench.txt", "groupnorm_in_graph.txt"), ("gemm_sweep.txt", "gemm_config_sweep.txt"),
-                 ("excess_v8.txt", "per_op_vs_floor.txt"), ("micro.txt", "micro_mufu_pdl.txt"), ("launches_cold.csv", "launches_cold.csv")]:
-        copy(a, b)
+                 ("excess_v8.txt", "per_op_vs_floor.txt"), ("micro.txt", "micro_mufu_pdl.txt"), ("launches_cold.csv", "launches_cold.csv"),
+                 ("launches_warm.csv", "launches_warm.csv"), ("pytest_gpu.log", "pytest_gpu.log"), ("smoke.log", "smoke.log")]:
+        if os.path.exists(os.path.join(SRC, a)):
+            copy(a, b)
+    cmd = ("ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none {} "
+           "python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-config4 --view-sharded-views 0")
     b = json.loads(open(os.path.join(SRC, "bench_n1.json")).read().strip().splitlines()[-1])
-    hdr = ("round 1 final, one DDIM step = 1 scene x 8 views, no CFG, the timed step of\n`ncu --metrics gpu__time_duration.sum "
-           "--clock-control none {} python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline`\n"
+    hdr = (f"round {ROUND} final, one DDIM step = 1 scene x 8 views, no CFG, the timed step of\n`" + cmd + "`\n"
            f"bench.py (CUDA-graph replay, CUDA events, not under ncu): {b['ms_per_step']:.2f} ms/step = {b['value']:.1f} steps/s. "
-           "ncu times are serialised{}: compare shares.\n")
-    open(os.path.join(DST, PRE + "launches_warm.summary.txt"), "w").write(
-        launch_summary("launches_warm.csv", hdr.format("--cache-control none", " (caches kept warm)")))
-    open(os.path.join(DST, PRE + "launches_cold.summary.txt"), "w").write(
-        launch_summary("launches_cold.csv", hdr.format("", " and cold-cache")))
-    open(os.path.join(DST, PRE + "ncu_gemm_conv_l0.txt"), "w").write(ncu_summary(
-        "ncu_gemm_conv_l0.ncu-rep", "ncu --set full --clock-control none --import-source on -k regex:gemm_tc, tools/prof_gemm.py 8 320 320 32 "
-        "(level-0 conv3x3 320->320 at 8 views: M=8192 N=320 K=2880, 128 tiles of 128x160)"))
-    open(os.path.join(DST, PRE + "ncu_attn_l0.txt"), "w").write(ncu_summary(
-        "ncu_attn_l0.ncu-rep", "ncu --set full --clock-control none --import-source on -k regex:attn64, tools/prof_attn.py 1 8192 40 "
-        "(joint attention of one scene: 8 views x 1024 tokens, 8 heads, d=40 padded to 64)"))
-    open(os.path.join(DST, PRE + "ncu_groupnorm_l0.txt"), "w").write(ncu_summary(
-        "ncu_gn_flat_l0.ncu-rep", "ncu --set full --clock-control none --import-source on -k regex:gn_flat, tools/prof_gn.py 8 1024 320 0 "
-        "(GroupNorm+SiLU of one level-0 tensor: 8 images x 1024 px x 320 ch)"))
+           "ncu times are serialised{}: compare shares.  dram = dram__bytes_read.sum + dram__bytes_write.sum.\n")
+    if os.path.exists(os.path.join(SRC, "launches_warm.csv")):
+        open(os.path.join(DST, PRE + "launches_warm.summary.txt"), "w").write(
+            launch_summary("launches_warm.csv", hdr.format("--cache-control none", " (caches kept warm)")))
+        json.dump(traffic_json("launches_warm.csv", f"profiles/{PRE}launches_warm.csv: `" + cmd.format("--cache-control none") + "`, "
+                               "the last whole DDIM step (caches not flushed between launches, as in the real step)"),
+                  open(os.path.join(DST, PRE + "traffic.json"), "w"), indent=1)
+    if os.path.exists(os.path.join(SRC, "launches_cold.csv")):
+        open(os.path.join(DST, PRE + "launches_cold.summary.txt"), "w").write(
+            launch_summary("launches_cold.csv", hdr.format("", " and cold-cache")))
+    for rep, dst, what in [
+            ("ncu_gemm_conv_l0.ncu-rep", "ncu_gemm_conv_l0.txt", "ncu --set full --clock-control none --import-source on -k regex:gemm_tc, "
+             "tools/prof_gemm.py 8 320 320 32 (level-0 conv3x3 320->320 at 8 views: M=8192 N=320 K=2880, 128 tiles of 128x160)"),
+            ("ncu_attn_l0.ncu-rep", "ncu_attn_l0.txt", "ncu --set full --clock-control none --import-source on -k regex:attn64, "
+             "tools/prof_attn.py 1 8192 40 (joint attention of one scene: 8 views x 1024 tokens, 8 heads, d=40 padded to 64)"),
+            ("ncu_gn_flat_l0.ncu-rep", "ncu_groupnorm_l0.txt", "ncu --set full --clock-control none --import-source on -k regex:gn_flat, "
+             "tools/prof_gn.py 8 1024 320 0 (GroupNorm+SiLU of one level-0 tensor: 8 images x 1024 px x 320 ch)")]:
+        if os.path.exists(os.path.join(SRC, rep)):
+            open(os.path.join(DST, PRE + dst), "w").write(ncu_summary(rep, what))
 
 
 if __name__ == "__main__":
