@@ -87,7 +87,21 @@ int mvldm_finalize_weights(mvldm_handle h, void* stream);
 /* Bytes of device workspace the handle holds for a (B scenes, V views, h x w latent) call. */
 int64_t mvldm_workspace_bytes(mvldm_handle h, int B, int V, int H, int W);
 
-/* Replaces Denoiser.forward / MultiViewUNet.forward (src/model/denoiser/denoiser.py:22-29,
+/* SUPPORTED SHAPE ENVELOPE (anything outside raises through mvldm_last_error; there is no fallback kernel):
+ *   latent H, W     multiples of 2^(num_levels-1) (8 for the 4-level UNet); at every level the width w_l = W / 2^l must
+ *                   divide 128 (w_l in {1,2,4,...,128}: W = 8, 16, 32, 64, 128, ... x 2^l) and the pixels per view
+ *                   h_l * w_l must divide 128 or be a multiple of 128.  32x32 (256 px), 16x16, 64x64, 32x16, 8x8 are
+ *                   tested; 24x24 / 48x48 latents (w_l = 24, 12, 6, 3) are refused by the implicit-GEMM tiler, whose
+ *                   128-pixel M tile is a box of whole rows (csrc/gemm_tc.cu gemm_tc()).
+ *   channels        block_out_channels multiples of 64 (TMA K-block), divisible by norm_groups (<= 64 groups) and by
+ *                   num_heads; concatenated resnet inputs <= 2560 channels; head dim <= 192 (padded to 64/128/192).
+ *   views / scenes  any B >= 1, V >= 1 (32-bit indexing: B*V*H*W*C < 2^31 per tensor); multi-view blocks run only at
+ *                   levels with h_l, w_l <= max_attn_res (mvunet.py:137,190).
+ *   in/out channels any in_channels (conv_in runs on an explicit im2col operand), out_channels <= 32.
+ *   dtypes          inputs / outputs fp32, timesteps int64, weights fp32/bf16/fp16 at ingestion; arithmetic bf16
+ *                   operands with fp32 accumulation and fp32 normalisation statistics.
+ *
+ * Replaces Denoiser.forward / MultiViewUNet.forward (src/model/denoiser/denoiser.py:22-29,
  * mvunet.py:90-208).  latents: device fp32 [B,V,in_channels,H,W] contiguous; timesteps: device int64
  * [B*V] (the [B] form of mvunet.py:102-105 is expanded by the host); out: device fp32
  * [B,V,out_channels,H,W]. */

@@ -196,6 +196,10 @@ def test_anchored_plan_matches_reference_index_logic():
     assert p.anchors == [5, 10, 15] and all(a in p.anchors for a, _ in p.chunks)
     with pytest.raises(ValueError):
         mv.anchored_plan([0, 1], 4)
+    # more than 4 anchors = the reference's iterative anchor rounds (diffusion_wrapper.py:744-792): refused, not approximated
+    with pytest.raises(ValueError):
+        mv.anchored_plan(list(range(80)), 8)
+    assert mv.anchored_plan(list(range(80)), 2).anchors == [40]
 
 
 def test_header_is_plain_c(tmp_path):
