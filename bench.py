@@ -287,24 +287,32 @@ def run_view_sharded(args, m, rank, world, local, dev, barrier):
     g = torch.Generator().manual_seed(7)
     inp = torch.randn(1, V, 11, H, W, generator=g)[:, a:b].to(dev)       # same scene on every rank, own view slice
     ts = torch.full((1, b - a), 500, dtype=torch.long, device=dev)
-    ex = mv.ViewGroupExchange(b - a, V, H, W, 8, dev)
-    for _ in range(2):
-        y = m.forward_view_sharded(inp, ts, V, ex)
-    ex.calls = ex.bytes_sent = 0
     n = 5
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n):
-        y = m.forward_view_sharded(inp, ts, V, ex)
-    e1.record()
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / n
-    assert torch.isfinite(y).all()
+
+    def timed(overlap):
+        ex = mv.ViewGroupExchange(b - a, V, H, W, 8, dev, overlap=overlap)
+        for _ in range(2):
+            y = m.forward_view_sharded(inp, ts, V, ex)
+        ex.calls = ex.bytes_sent = 0
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            y = m.forward_view_sharded(inp, ts, V, ex)
+        e1.record()
+        barrier()
+        assert torch.isfinite(y).all()
+        return max_over_ranks(e0.elapsed_time(e1), world, dev) / n, ex
+
+    ms, ex = timed(True)
+    ms_exposed = timed(False)[0] if world > 1 else None
     return {"workload": f"one denoiser forward of 1 scene x {V} views, views split in contiguous groups over the ranks",
             "scaling": "strong", "views": V, "views_per_rank": b - a, "forwards_timed": n, "ms_per_forward": ms,
             "value": V / (ms * 1e-3), "unit": "views/s",
             "gflop_per_forward": forward_gflop(V, args.variant), "tflops": forward_gflop(V, args.variant) / ms,
+            "ms_per_forward_exchange_not_overlapped": ms_exposed,
+            "overlap": "all-gather on a side stream under the attention over the rank's own keys; three partial softmaxes "
+                       "(own / before / after slabs) merged in fixed order" if world > 1 else "n/a (one rank)",
             "kv_exchanges_per_forward": ex.calls // n,
             "kv_bytes_sent_per_rank_per_forward": ex.bytes_sent // n,
             "kv_bytes_received_per_rank_per_forward": ex.bytes_sent // n * (world - 1),

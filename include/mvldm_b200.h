@@ -115,17 +115,27 @@ int mvldm_forward(mvldm_handle h, void* stream, const float* latents, const int6
 int mvldm_forward_scenes(mvldm_handle h, void* stream, const float* latents, const int64_t* timesteps, int num_scenes,
                          const int32_t* views_per_scene, int H, int W, float* out);
 
-/* View-group sharding: a scene whose views are split over several GPUs.  This rank holds V_local
- * contiguous views of ONE scene (B = 1) out of V_total; every op is per view except the joint multi-view
- * attention, which needs all views' K and V.  At each of the 9 multi-view blocks the library packs the local K|V
- * (bf16 [V_local*h*w, 2*heads*dpad]) into `kv_send`, calls `exchange`, and expects `kv_recv` to then hold the
- * ranks' slabs in view order (bf16 [V_total*h*w, 2*heads*dpad]); the host implements `exchange` with an NCCL
- * all-gather (ring over NVLink) enqueued on `stream`.  Not graph-captured (the callback re-enters the host).
- * kv_send must hold V_local*h*w*2*heads*64*2 bytes at the finest level, kv_recv V_total/V_local times that. */
-typedef int (*mvldm_kv_exchange_fn)(void* user, const void* kv_send, void* kv_recv, int64_t bytes_per_rank, void* stream);
+/* View-group sharding: a scene whose views are split over several GPUs.  This rank holds the
+ * `group_index`-th group of V_local contiguous views of ONE scene (B = 1) out of V_total; every op is per view except
+ * the joint multi-view attention, which needs all views' K and V.  At each of the 9 multi-view blocks the library
+ *   1. packs the local K|V (bf16 [V_local*h*w, 2*heads*dpad]) into `kv_send`,
+ *   2. calls exchange(..., MVLDM_EXCHANGE_BEGIN): the host STARTS the all-gather (NCCL over NVLink) - on a stream of its
+ *      own, ordered after the work already enqueued on `stream` - and returns without waiting,
+ *   3. runs the attention of this rank's queries against its OWN keys (from kv_send) while the slabs are on the wire,
+ *   4. calls exchange(..., MVLDM_EXCHANGE_END): the host makes `stream` wait until `kv_recv` holds every rank's slab in
+ *      view order (bf16 [V_total*h*w, 2*heads*dpad]),
+ *   5. runs the attention against the slabs in front of and behind its own and merges the (up to) three partial
+ *      softmaxes in that fixed order (own, before, after): deterministic, and equal to the one-pass softmax up to
+ *      the rounding of the merge.
+ * A host without a side stream may do the whole exchange on `stream` in BEGIN and nothing in END.  Not graph-captured
+ * (the callback re-enters the host).  kv_send must hold V_local*h*w*2*heads*64*2 bytes at the finest level, kv_recv
+ * V_total/V_local times that. */
+enum { MVLDM_EXCHANGE_BEGIN = 0, MVLDM_EXCHANGE_END = 1 };
+typedef int (*mvldm_kv_exchange_fn)(void* user, const void* kv_send, void* kv_recv, int64_t bytes_per_rank, void* stream,
+                                    int phase);
 int mvldm_forward_sharded(mvldm_handle h, void* stream, const float* latents, const int64_t* timesteps, int V_local,
-                          int V_total, int H, int W, float* out, void* kv_send, void* kv_recv, int64_t kv_recv_bytes,
-                          mvldm_kv_exchange_fn exchange, void* user);
+                          int V_total, int group_index, int H, int W, float* out, void* kv_send, void* kv_recv,
+                          int64_t kv_recv_bytes, mvldm_kv_exchange_fn exchange, void* user);
 
 /* Number of kernels the last mvldm_forward on this handle launched (graph replays count their nodes). */
 int mvldm_last_launch_count(mvldm_handle h);
@@ -213,9 +223,16 @@ int mvldm_op_attention(void* stream, int impl, const void* qkv, void* out, int b
                        int d, int dpad);
 /* Same (tcgen05 path only) with queries and keys/values in different buffers and of different lengths:
  * q bf16 [batches*seq_q, ld_q] (head h at column q_col0 + h*dpad), kv bf16 [batches*seq_kv, ld_kv] (K heads at
- * k_col0 + h*dpad, V heads at v_col0 + h*dpad, ones column as above). */
+ * k_col0 + h*dpad, V heads at v_col0 + h*dpad, ones column as above).
+ * `stats` (NULL or fp32 [batches*seq_q, heads, 2]): also report every row's softmax state (reference max in the log2
+ * domain, row sum against it), so that launches over DISJOINT key ranges can be combined by mvldm_op_attention_merge. */
 int mvldm_op_attention_kv(void* stream, const void* q, int ld_q, int q_col0, const void* kv, int ld_kv, int k_col0,
-                          int v_col0, void* out, int batches, int seq_q, int seq_kv, int heads, int d, int dpad);
+                          int v_col0, void* out, int batches, int seq_q, int seq_kv, int heads, int d, int dpad,
+                          float* stats);
+/* out = softmax over the union of the key ranges of 1..3 partial launches: parts[i] bf16 [rows, heads*dpad] with
+ * stats[i] from mvldm_op_attention_kv; combined in argument order (bit-stable). */
+int mvldm_op_attention_merge(void* stream, int nparts, const void* const* parts, const float* const* stats, int64_t rows,
+                             int heads, int dpad, void* out);
 
 /* Debug: clock64() stamps of CTA (0,0) of the last attention launch made with MVLDM_ATTN_TRACE set in the
  * environment; out[slot*512 + tile], slots 0-2 softmax thread (wait S, got S, P handed over), 3-5 MMA thread

@@ -77,13 +77,16 @@ SYMBOLS = {
     "mvldm_op_layernorm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
 }
 
-KV_EXCHANGE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p)
-SYMBOLS["mvldm_forward_sharded"] = (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
-                                            c_void_p, c_void_p, c_int64, KV_EXCHANGE_FN, c_void_p])
+EXCHANGE_BEGIN, EXCHANGE_END = 0, 1
+KV_EXCHANGE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int)
+SYMBOLS["mvldm_forward_sharded"] = (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                            c_void_p, c_void_p, c_void_p, c_int64, KV_EXCHANGE_FN, c_void_p])
 SYMBOLS["mvldm_forward_scenes"] = (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, POINTER(c_int32), c_int, c_int,
                                            c_void_p])
 SYMBOLS["mvldm_op_attention_kv"] = (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
-                                            c_int, c_int, c_int, c_int, c_int])
+                                            c_int, c_int, c_int, c_int, c_int, c_void_p])
+SYMBOLS["mvldm_op_attention_merge"] = (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), c_int64, c_int, c_int,
+                                               c_void_p])
 
 _lib = None
 

@@ -104,7 +104,11 @@ void attention_trace_read(long long* host, int n);  // debug timeline of CTA (0,
 void attention_tc(cudaStream_t s, const bf16* qkv, bf16* out, int batches, int seq, int heads, int d, int dpad);
 // queries and keys/values from different buffers / of different lengths (view-group sharding: local Q, gathered K/V)
 void attention_tc_kv(cudaStream_t s, const bf16* q, int ld_q, int q_col0, const bf16* kv, int ld_kv, int k_col0, int v_col0,
-                     bf16* out, int batches, int seq_q, int seq_kv, int heads, int d, int dpad);
+                     bf16* out, int batches, int seq_q, int seq_kv, int heads, int d, int dpad, float* stats = nullptr);
+// `stats` (optional, fp32 [batches*seq_q, heads, 2]): the launch also reports each row's softmax reference and row sum so that
+// launches over disjoint key ranges can be merged into the softmax over their union (parts in argument order)
+void attention_merge(cudaStream_t s, int nparts, const bf16* const* parts, const float* const* stats, int64_t rows, int heads,
+                     int dpad, bf16* out);
 // norm.cu
 void im2col_input(cudaStream_t s, const float* latents, int n_img, int cin, int h, int w, int kpad, bf16* out);
 void timestep_sinusoid_bf16(cudaStream_t s, const int64_t* t, int n, int dim, bf16* out);

@@ -88,7 +88,10 @@ struct TcParams {
   int mode;
   void* out;
   int ldo, n_valid;
-  int opt;  // bit 0: bias/rowvec table in smem, bit 1: residual row prefetch, bit 2: 4-way unrolled fused reduce
+  const bf16* w;  // raw weight matrix [N, K] (L2 prefetch ahead of the dependency wait)
+  int K;
+  int opt;  // bit 0: bias/rowvec table in smem, bit 1: residual row prefetch, bit 2: 4-way unrolled fused reduce,
+            // bit 3: L2-prefetch this CTA's first weight tile before griddepcontrol.wait, bit 4: release dependents at entry
 };
 
 // erf-form GELU (F.gelu default, mvdream/attention.py:60-70) with erf from Abramowitz & Stegun 7.1.26 (|abs err| <
@@ -143,6 +146,8 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-B alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_work = p.mt * p.nt * p.splits;
+  // persistent grid (<= one CTA per SM, all resident): releasing the dependents at entry cannot starve this grid's own CTAs
+  if (p.opt & 16) pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.nseg; ++i) tc::tma_prefetch_desc(&p.tmA[i][KC - 1]);
@@ -162,6 +167,24 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+#ifdef MVLDM_ENABLE_PDL
+  // Weights never depend on the previous kernel: pull this CTA's first weight tile (BN rows x this split's K range) into
+  // L2 while the predecessor is still running.  One bulk prefetch per row, rows dealt over the lanes of the idle warp 1.
+  if ((p.opt & 8) && warp == 1 && (int)blockIdx.x < num_work) {
+    const int w0 = blockIdx.x;
+    const int ntile = (w0 / p.mt) % p.nt, z = w0 / (p.mt * p.nt);
+    // K chunk range of split z: steps are (segment, tap, channel block) in K order, KC chunks per step except at segment ends;
+    // an over-estimate of a few chunks only prefetches a little more of the same rows
+    const int c_begin = min(z * p.steps_per_split * KC, p.K / BK);
+    const int c_end = min((z + 1) * p.steps_per_split * KC, p.K / BK);
+    const uint32_t bytes = (uint32_t)(c_end - c_begin) * BK * 2;
+    if (bytes)
+      for (int r = lane; r < BN; r += 32) {
+        const bf16* src = p.w + (int64_t)(ntile * BN + r) * p.K + (int64_t)c_begin * BK;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+      }
+  }
+#endif
   // everything above overlaps the previous kernel's tail; from here on we read its output
   pdl_wait();
 
@@ -299,7 +322,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     // last item's main loop is done: let the next kernel's CTAs be scheduled (they set up barriers / TMEM / descriptors
     // and then block in griddepcontrol.wait until this grid has completed).  Triggering earlier would let them take
     // shared memory and TMEM this grid still needs.
-    if (w + (int)gridDim.x >= num_work) pdl_launch_dependents();
+    if (!(p.opt & 16) && w + (int)gridDim.x >= num_work) pdl_launch_dependents();
 #pragma unroll 1  // rolled: the unrolled epilogue (x8 chunks x 3 modes) cost 0.5 ms per forward in code size / registers
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
@@ -719,6 +742,8 @@ void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t w
     }();
     p.opt = opt;
   }
+  p.w = reinterpret_cast<const bf16*>(d.w);
+  p.K = d.k;
   p.bias = d.bias;
   p.rowvec = d.rowvec;
   p.rowvec_ld = d.rowvec_ld;

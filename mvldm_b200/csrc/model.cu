@@ -118,6 +118,8 @@ struct Step {
   bf16* out = nullptr;
   int batches = 0, seq = 0, heads = 0, d = 0, dpad = 0, seq_local = 0;
   bool simt = false;
+  bf16* part[3] = {};     // ATTN_SHARDED: partial outputs (local slab, slabs before it, slabs after it) ...
+  float* pstats[3] = {};  // ... and their softmax states, merged in that order
   // elementwise steps
   const void *x0 = nullptr, *x1 = nullptr;
   const float *gamma = nullptr, *beta = nullptr;
@@ -199,6 +201,7 @@ struct mvldm_handle_s {
   size_t kv_recv_bytes = 0;
   mvldm_kv_exchange_fn exchange = nullptr;
   void* exchange_user = nullptr;
+  int group_index = 0;  // which contiguous view group of the scene this rank holds
   size_t splitk_need = 0, splitk_bytes = 0;  // split-K fp32 scratch shared by all GEMMs of a forward
   void* splitk_ws = nullptr;
 
@@ -689,12 +692,24 @@ struct mvldm_handle_s {
 
   // This rank's views supply the queries; K and V of every view of the scene are all-gathered by the host callback.
   void joint_attention_sharded(const Act& qkv, const Act& out, int seq_local, const MvW& m) {
-    if (dry) return;
     const int world = v_total / (int)(qkv.n);
+    // up to three partial softmaxes (own slab while the exchange is in flight, the slabs before, the slabs after)
+    Act parts[3];
+    float* stats[3] = {};
+    if (world > 1)
+      for (int i = 0; i < 3; ++i) {
+        parts[i] = new_act(out.n, out.h, out.w, out.c);
+        stats[i] = new_f32((size_t)seq_local * m.heads * 2);
+      }
+    if (dry) return;
     Step st;
     st.kind = Step::ATTN_SHARDED;
     st.qkv = qkv.p; st.out = out.p; st.batches = 1; st.seq = seq_local * world; st.seq_local = seq_local;
     st.heads = m.heads; st.d = m.d; st.dpad = m.dpad;
+    for (int i = 0; i < 3; ++i) {
+      st.part[i] = parts[i].p;
+      st.pstats[i] = stats[i];
+    }
     st.meta = OpMeta{"attention_joint_sharded", "seq_q" + std::to_string(seq_local) + " seq_kv" + std::to_string(seq_local * world),
                      4.0 * (double)seq_local * seq_local * world * m.c, 0.0};
     st.meta.scores = (double)m.heads * seq_local * (double)seq_local * world;
@@ -1049,15 +1064,45 @@ struct mvldm_handle_s {
           break;
         case Step::ATTN_SHARDED: {
           const int hd = st.heads * st.dpad;
+          const int world = st.seq / st.seq_local, g = group_index;
           const size_t bytes = (size_t)st.seq_local * 2 * hd * sizeof(bf16);
-          MV_CHECK(bytes * (st.seq / st.seq_local) <= kv_recv_bytes, "mvldm_forward_sharded: kv_recv buffer too small");
+          MV_CHECK(bytes * world <= kv_recv_bytes, "mvldm_forward_sharded: kv_recv buffer too small");
           // K|V columns of the packed q|k|v rows -> contiguous slab
           MV_CUDA(cudaMemcpy2DAsync(kv_send, (size_t)2 * hd * sizeof(bf16), st.qkv + hd, (size_t)3 * hd * sizeof(bf16),
                                     (size_t)2 * hd * sizeof(bf16), st.seq_local, cudaMemcpyDeviceToDevice, s));
-          const int rc = exchange(exchange_user, kv_send, kv_recv, (int64_t)bytes, s);
+          int rc = exchange(exchange_user, kv_send, kv_recv, (int64_t)bytes, s, MVLDM_EXCHANGE_BEGIN);
           MV_CHECK(rc == 0, "mvldm_forward_sharded: K/V exchange callback failed");
-          attention_tc_kv(s, st.qkv, 3 * hd, 0, reinterpret_cast<const bf16*>(kv_recv), 2 * hd, 0, hd, st.out, 1, st.seq_local,
-                          st.seq, st.heads, st.d, st.dpad);
+          const bf16* own = reinterpret_cast<const bf16*>(kv_send);
+          const bf16* all = reinterpret_cast<const bf16*>(kv_recv);
+          if (world == 1) {
+            attention_tc_kv(s, st.qkv, 3 * hd, 0, own, 2 * hd, 0, hd, st.out, 1, st.seq_local, st.seq_local, st.heads, st.d,
+                            st.dpad);
+            rc = exchange(exchange_user, kv_send, kv_recv, (int64_t)bytes, s, MVLDM_EXCHANGE_END);
+            MV_CHECK(rc == 0, "mvldm_forward_sharded: K/V exchange callback failed");
+            break;
+          }
+          // this rank's queries against its OWN keys run while the other ranks' slabs are still on the wire ...
+          const bf16* parts[3];
+          const float* stats[3];
+          int np = 0;
+          attention_tc_kv(s, st.qkv, 3 * hd, 0, own, 2 * hd, 0, hd, st.part[0], 1, st.seq_local, st.seq_local, st.heads, st.d,
+                          st.dpad, st.pstats[0]);
+          parts[np] = st.part[0]; stats[np++] = st.pstats[0];
+          rc = exchange(exchange_user, kv_send, kv_recv, (int64_t)bytes, s, MVLDM_EXCHANGE_END);
+          MV_CHECK(rc == 0, "mvldm_forward_sharded: K/V exchange callback failed");
+          // ... then against the slabs in front of and behind its own, and the three softmax states are merged in this
+          // fixed order (deterministic; equal to the one-pass softmax up to fp32 rounding of the merge)
+          if (g > 0) {
+            attention_tc_kv(s, st.qkv, 3 * hd, 0, all, 2 * hd, 0, hd, st.part[1], 1, st.seq_local, g * st.seq_local, st.heads,
+                            st.d, st.dpad, st.pstats[1]);
+            parts[np] = st.part[1]; stats[np++] = st.pstats[1];
+          }
+          if (g < world - 1) {
+            attention_tc_kv(s, st.qkv, 3 * hd, 0, all + (size_t)(g + 1) * st.seq_local * 2 * hd, 2 * hd, 0, hd, st.part[2], 1,
+                            st.seq_local, (world - 1 - g) * st.seq_local, st.heads, st.d, st.dpad, st.pstats[2]);
+            parts[np] = st.part[2]; stats[np++] = st.pstats[2];
+          }
+          attention_merge(s, np, parts, stats, st.seq_local, st.heads, st.dpad, st.out);
           break;
         }
         case Step::GN:
@@ -1325,13 +1370,15 @@ int mvldm_forward_scenes(mvldm_handle h, void* stream, const float* latents, con
 }
 
 int mvldm_forward_sharded(mvldm_handle h, void* stream, const float* latents, const int64_t* timesteps, int V_local,
-                          int V_total, int H, int W, float* out, void* kv_send, void* kv_recv, int64_t kv_recv_bytes,
-                          mvldm_kv_exchange_fn exchange, void* user) {
+                          int V_total, int group_index, int H, int W, float* out, void* kv_send, void* kv_recv,
+                          int64_t kv_recv_bytes, mvldm_kv_exchange_fn exchange, void* user) {
   MV_API_BEGIN
   MV_CHECK(h && latents && timesteps && out && kv_send && kv_recv && exchange, "null argument");
   MV_CHECK(h->finalized, "mvldm_forward_sharded before mvldm_finalize_weights");
   MV_CHECK(h->cfg.impl == MVLDM_IMPL_TC, "view-group sharding needs the tcgen05 kernels");
   MV_CHECK(V_local > 0 && V_total % V_local == 0, "V_total must be a multiple of V_local (equal view groups)");
+  MV_CHECK(group_index >= 0 && group_index < V_total / V_local, "group_index out of range");
+  h->group_index = group_index;
   MV_CUDA(cudaSetDevice(h->device));
   h->stream = (cudaStream_t)stream;
   h->v_total = V_total;
@@ -1456,11 +1503,22 @@ int mvldm_debug_attn_trace(int64_t* out, int n) {
 }
 
 int mvldm_op_attention_kv(void* stream, const void* q, int ld_q, int q_col0, const void* kv, int ld_kv, int k_col0,
-                          int v_col0, void* out, int batches, int seq_q, int seq_kv, int heads, int d, int dpad) {
+                          int v_col0, void* out, int batches, int seq_q, int seq_kv, int heads, int d, int dpad,
+                          float* stats) {
   MV_API_BEGIN
   MV_CHECK(q && kv && out, "null argument");
   attention_tc_kv((cudaStream_t)stream, (const bf16*)q, ld_q, q_col0, (const bf16*)kv, ld_kv, k_col0, v_col0, (bf16*)out,
-                  batches, seq_q, seq_kv, heads, d, dpad);
+                  batches, seq_q, seq_kv, heads, d, dpad, stats);
+  MV_API_END
+}
+
+int mvldm_op_attention_merge(void* stream, int nparts, const void* const* parts, const float* const* stats, int64_t rows,
+                             int heads, int dpad, void* out) {
+  MV_API_BEGIN
+  MV_CHECK(parts && stats && out && nparts >= 1 && nparts <= 3, "bad arguments");
+  for (int i = 0; i < nparts; ++i) MV_CHECK(parts[i] && stats[i], "null part");
+  attention_merge((cudaStream_t)stream, nparts, reinterpret_cast<const bf16* const*>(parts), stats, rows, heads, dpad,
+                  (bf16*)out);
   MV_API_END
 }
 

@@ -477,8 +477,8 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
         lib = _lib.load()
         with torch.cuda.device(latents.device):
             _lib.check(lib.mvldm_forward_sharded(
-                self._h.ptr, _lib.current_stream_ptr(latents.device), lat.data_ptr(), t.data_ptr(), v, v_total, h, w,
-                out.data_ptr(), exchange.send.data_ptr(), exchange.recv.data_ptr(),
+                self._h.ptr, _lib.current_stream_ptr(latents.device), lat.data_ptr(), t.data_ptr(), v, v_total,
+                exchange.group_index, h, w, out.data_ptr(), exchange.send.data_ptr(), exchange.recv.data_ptr(),
                 exchange.recv.numel() * exchange.recv.element_size(), exchange.callback, None))
         return out
 

@@ -46,21 +46,33 @@ def view_slice(num_views: int, rank: int, world_size: int) -> Tuple[int, int]:
 
 
 class ViewGroupExchange:
-    """Owns the K|V send / receive buffers and the callback the library invokes at every joint attention."""
+    """Owns the K|V send / receive buffers and the callback the library invokes around every joint attention.
 
-    def __init__(self, v_local: int, v_total: int, h: int, w: int, heads: int, device, group=None):
+    Two-phase protocol (include/mvldm_b200.h, MVLDM_EXCHANGE_BEGIN / _END): BEGIN starts the all-gather on a side stream
+    (ordered after the K|V pack on the compute stream) and returns; the library then runs the attention over this rank's
+    own keys; END makes the compute stream wait for the gathered slabs.  ``overlap=False`` runs the collective on the
+    compute stream inside BEGIN (the transfer is then fully exposed; kept for measurement)."""
+
+    def __init__(self, v_local: int, v_total: int, h: int, w: int, heads: int, device, group=None, overlap: bool = True):
         from . import _lib
         self.group = group
         self.world = v_total // v_local
+        self.group_index = dist.get_rank(group) if (dist.is_initialized() and self.world > 1) else 0
         per_rank = v_local * h * w * 2 * heads * 64          # bf16 elements at the finest level (head_dim_pad 64)
         self.send = torch.empty(per_rank, dtype=torch.bfloat16, device=device)
         self.recv = torch.empty(per_rank * self.world, dtype=torch.bfloat16, device=device)
+        self.overlap = overlap
+        self.side = torch.cuda.Stream(device=device) if (overlap and torch.device(device).type == "cuda") else None
+        self.done = torch.cuda.Event() if self.side is not None else None
         self.calls = 0
         self.bytes_sent = 0
 
-        def _cb(user, send_ptr, recv_ptr, nbytes, stream):
+        def _cb(user, send_ptr, recv_ptr, nbytes, stream, phase):
             try:
-                self.all_gather(nbytes // 2)
+                if phase == _lib.EXCHANGE_BEGIN:
+                    self.begin(nbytes // 2)
+                else:
+                    self.end()
                 return 0
             except Exception:                                  # never unwind through the C frame
                 import traceback
@@ -70,9 +82,25 @@ class ViewGroupExchange:
 
     def all_gather(self, n_elems: int) -> None:
         """recv[r * n : (r + 1) * n] = rank r's send[:n]  (rank order == view order)"""
-        self.calls += 1
-        self.bytes_sent += n_elems * 2
         if self.world == 1 or not dist.is_initialized():
             self.recv[:n_elems].copy_(self.send[:n_elems])
             return
         dist.all_gather_into_tensor(self.recv[: n_elems * self.world], self.send[:n_elems], group=self.group)
+
+    def begin(self, n_elems: int) -> None:
+        self.calls += 1
+        self.bytes_sent += n_elems * 2
+        if self.world == 1:
+            return                                             # the library reads the local slab straight from `send`
+        if self.side is None:
+            self.all_gather(n_elems)
+            return
+        cur = torch.cuda.current_stream(self.send.device)
+        self.side.wait_stream(cur)                             # after the K|V pack (and the previous block's readers)
+        with torch.cuda.stream(self.side):
+            self.all_gather(n_elems)
+            self.done.record(self.side)
+
+    def end(self) -> None:
+        if self.world > 1 and self.side is not None:
+            torch.cuda.current_stream(self.send.device).wait_event(self.done)

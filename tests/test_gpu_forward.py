@@ -227,8 +227,56 @@ def test_attention_split_q_kv_sources():
     qloc = qkv[256:256 + Nq].contiguous()                          # this "rank's" rows (q in the first third of columns)
     part = torch.empty((Nq, heads * dpad), dtype=torch.bfloat16, device="cuda")
     _lib.check(lib.mvldm_op_attention_kv(stream_ptr(), qloc.data_ptr(), 3 * heads * dpad, 0, kv.data_ptr(), 2 * heads * dpad,
-                                         0, heads * dpad, part.data_ptr(), 1, Nq, N, heads, d, dpad))
+                                         0, heads * dpad, part.data_ptr(), 1, Nq, N, heads, d, dpad, None))
     assert torch.equal(part, full[256:256 + Nq])
+
+
+@pytest.mark.parametrize("d,dpad,cuts", [(40, 64, (512, 1536)), (80, 128, (256, 512)), (160, 192, (128, 256)), (64, 64, (384, 1024))])
+def test_partial_softmax_merge_equals_one_pass(d, dpad, cuts):
+    """overlapped view-group exchange: the keys of one softmax are covered by up to three launches (own slab, slabs before,
+    slabs after) whose (max, row-sum) states are merged in a fixed order; the result must equal the one-pass attention
+    up to the bf16 rounding of the parts, and be bit-stable"""
+    import ctypes
+    from helpers import pack_qkv, stream_ptr
+    from mvldm_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(13)
+    heads, N, Nq = 8, 2048, 512
+    q, k, v = (torch.randn(1, N, heads * d) * s for s in (2.0, 2.0, 1.0))       # wide score range: the states differ
+    qkv = pack_qkv(q, k, v, heads, dpad).cuda()
+    hd = heads * dpad
+    full = torch.empty((N, hd), dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.mvldm_op_attention(stream_ptr(), 0, qkv.data_ptr(), full.data_ptr(), 1, N, heads, d, dpad))
+    kv = qkv[:, hd:].contiguous()
+    qloc = qkv[:Nq].contiguous()
+    a, b = cuts
+    ranges = [(a, b), (0, a), (b, N)]                                         # own slab first, then before, then after
+    parts = [torch.empty((Nq, hd), dtype=torch.bfloat16, device="cuda") for _ in ranges]
+    stats = [torch.empty((Nq, heads, 2), dtype=torch.float32, device="cuda") for _ in ranges]
+
+    def run():
+        for (lo, hi), p, s in zip(ranges, parts, stats):
+            _lib.check(lib.mvldm_op_attention_kv(stream_ptr(), qloc.data_ptr(), 3 * hd, 0, kv[lo:hi].data_ptr(), 2 * hd, 0, hd,
+                                                 p.data_ptr(), 1, Nq, hi - lo, heads, d, dpad, s.data_ptr()))
+        out = torch.empty((Nq, hd), dtype=torch.bfloat16, device="cuda")
+        pp = (ctypes.c_void_p * 3)(*[p.data_ptr() for p in parts])
+        ss = (ctypes.c_void_p * 3)(*[s.data_ptr() for s in stats])
+        _lib.check(lib.mvldm_op_attention_merge(stream_ptr(), 3, pp, ss, Nq, heads, dpad, out.data_ptr()))
+        return out
+
+    out = run()
+    assert rel_err(out.float(), full[:Nq].float()) < 1.5e-2
+    assert torch.equal(out, run())
+    # the row sums add up: sum_i l_i 2^(m_i - m) is the full softmax denominator
+    ref = attention_ref_rows(q, k, v, heads, Nq)
+    assert rel_err(out.float().view(Nq, heads, dpad)[:, :, :d].reshape(Nq, -1), ref) < 2e-2
+
+
+def attention_ref_rows(q, k, v, heads, nq):
+    """fp32 softmax attention of the first nq queries against all keys (inputs rounded to bf16 like the kernel's operands)"""
+    from helpers import attention_ref
+    r = lambda t: t.to(torch.bfloat16).float()  # noqa: E731
+    return attention_ref(r(q), r(k), r(v), heads)[0, :nq]
 
 
 def _view_shard_worker(rank, ws, port, sd, inp, ts, ref):

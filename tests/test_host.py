@@ -158,7 +158,9 @@ def _kv_worker(rank, ws, port):
     n = 4 * 2 * 8 * 64
     assert ex.send.numel() == n and ex.recv.numel() == n * ws
     ex.send[:] = float(rank + 1)
-    ex.all_gather(100)                                   # a coarser level uses a prefix of the buffers
+    assert ex.group_index == rank and ex.side is None    # no CUDA device: the collective runs inline in BEGIN
+    ex.begin(100)                                        # a coarser level uses a prefix of the buffers
+    ex.end()
     for r in range(ws):
         assert torch.all(ex.recv[r * 100:(r + 1) * 100] == float(r + 1))     # rank order == view order
     assert ex.calls == 1 and ex.bytes_sent == 200
