@@ -88,11 +88,14 @@ int mvldm_finalize_weights(mvldm_handle h, void* stream);
 int64_t mvldm_workspace_bytes(mvldm_handle h, int B, int V, int H, int W);
 
 /* SUPPORTED SHAPE ENVELOPE (anything outside raises through mvldm_last_error; there is no fallback kernel):
- *   latent H, W     multiples of 2^(num_levels-1) (8 for the 4-level UNet); at every level the width w_l = W / 2^l must
- *                   divide 128 (w_l in {1,2,4,...,128}: W = 8, 16, 32, 64, 128, ... x 2^l) and the pixels per view
- *                   h_l * w_l must divide 128 or be a multiple of 128.  32x32 (256 px), 16x16, 64x64, 32x16, 8x8 are
- *                   tested; 24x24 / 48x48 latents (w_l = 24, 12, 6, 3) are refused by the implicit-GEMM tiler, whose
- *                   128-pixel M tile is a box of whole rows (csrc/gemm_tc.cu gemm_tc()).
+ *   latent H, W     multiples of 2^(num_levels-1) (8 for the 4-level UNet).  The implicit-GEMM M tile is a TMA box of
+ *                   (columns x rows x images) covering <= 128 rows of the 128-row MMA (csrc/gemm_tc.cu tile_geometry()):
+ *                   widths that divide 128 with h*w | 128 or 128 | h*w tile densely (32x32, 16x16, 64x64, 32x16, 8x8 ...:
+ *                   the fast path); any other width <= 128 (24, 48, 40, 12, 6, 5, 3 ...) uses the box with the fewest
+ *                   tiles whose row count is a multiple of 8, e.g. 24 columns x 5 rows = 120 rows; widths > 128 are split
+ *                   into equal column blocks (256 = 2 x 128, 192 = 2 x 96).  Tested: 32x32, 16x16, 64x64, 32x16, 8x8,
+ *                   24x24, 48x40, 40x24 latents and 256- / 192-wide feature maps at the op level.  Refused: widths with
+ *                   no equal split into <= 128-pixel blocks whose box has a multiple-of-8 row count (e.g. 129).
  *   channels        block_out_channels multiples of 64 (TMA K-block), divisible by norm_groups (<= 64 groups) and by
  *                   num_heads; concatenated resnet inputs <= 2560 channels; head dim <= 192 (padded to 64/128/192).
  *   views / scenes  any B >= 1, V >= 1 (32-bit indexing: B*V*H*W*C < 2^31 per tensor); multi-view blocks run only at

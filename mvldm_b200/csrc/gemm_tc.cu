@@ -80,6 +80,10 @@ struct TcParams {
   float* partial;    // split-K: fp32 partial tiles [splits][M][N]; NULL when not split
   int* counters;     // split-K fused reduction: [2][mt*nt] arrive / done counters (all zero between launches), or NULL
   int hw, ow;        // output pixels per image / row width (tile -> image coordinates)
+  // M tile = TMA box of bw pixels x bh rows x bn images (a_rows = bw*bh*bn <= 128 rows of the 128-row MMA; rows beyond
+  // a_rows / beyond the image are never stored).  dense: the tile is 128 consecutive tokens (row r <-> token m0 + r), the
+  // common case (widths dividing 128 with hw | 128 or 128 | hw); otherwise tiles walk (x block, y block, image block).
+  int dense, bw, bh, bn, tx, ty, a_rows, oh, n_img;
   const float* bias;
   const float* rowvec;
   int rowvec_ld;
@@ -128,7 +132,38 @@ __device__ __forceinline__ void st_global_v8(void* ptr, uint32_t a0, uint32_t a1
                : "memory");
 }
 
-template <int BN, int STAGES>
+// origin (first image, first row, first column) of M tile `mtile`
+template <bool DENSE>
+__device__ __forceinline__ void tile_origin(const TcParams& p, int mtile, int& img0, int& y0, int& x0) {
+  if (DENSE) {
+    const int m0 = mtile * BM;
+    img0 = m0 / p.hw;
+    y0 = (m0 - img0 * p.hw) / p.ow;
+    x0 = 0;
+  } else {
+    const int ix = mtile % p.tx, iy = (mtile / p.tx) % p.ty;
+    x0 = ix * p.bw;
+    y0 = iy * p.bh;
+    img0 = (mtile / (p.tx * p.ty)) * p.bn;
+  }
+}
+// token (row of the [M, N] output) that accumulator row r of the tile holds, or -1; di = image index inside the tile
+template <bool DENSE>
+__device__ __forceinline__ int row_token(const TcParams& p, int mtile, int img0, int y0, int x0, int r, int& di) {
+  if (DENSE) {
+    const int m = mtile * BM + r;
+    di = m / p.hw - img0;
+    return m < p.M ? m : -1;
+  }
+  const int rx = r % p.bw, t = r / p.bw, ry = t % p.bh;
+  di = t / p.bh;
+  const int img = img0 + di, y = y0 + ry;
+  return (r < p.a_rows && img < p.n_img && y < p.oh) ? (img * p.oh + y) * p.ow + x0 + rx : -1;
+}
+
+// DENSE: tiles of 128 consecutive tokens (every shape of the 32x32 / 16x16 / 64x64 configurations) - the index arithmetic of the
+// general (columns x rows x images) box compiles away
+template <int BN, int STAGES, bool DENSE>
 __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = KC * (A_BYTES + B_BYTES);  // smem reserved per stage
@@ -194,11 +229,12 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
       int it = 0;  // k-block counter across work items: smem stage = it % STAGES
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
         const int mtile = w % p.mt, ntile = (w / p.mt) % p.nt, z = w / (p.mt * p.nt);
-        const int m0 = mtile * BM, n0 = ntile * BN;
+        const int n0 = ntile * BN;
         const int st_begin = z * p.steps_per_split;
         const int nst = min(p.num_steps - st_begin, p.steps_per_split);
-        const int img0 = m0 / p.hw;
-        const int y0 = (m0 - img0 * p.hw) / p.ow;
+        int img0, y0, x0;
+        tile_origin<DENSE>(p, mtile, img0, y0, x0);
+        const uint32_t a_chunk = DENSE ? (uint32_t)A_BYTES : (uint32_t)p.a_rows * (BK * 2);  // bytes per 64-channel chunk of the A box
         // locate (segment, tap, channel block) of the first step
         int s = 0, t = 0, cb = st_begin;
         while (cb >= p.seg[s].ntaps * p.seg[s].spt) {
@@ -213,9 +249,10 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
           const int stage = it % STAGES;
           tc::mbar_wait(tc::smem_u32(&bar_empty[stage]), ((it / STAGES) & 1) ^ 1);
           const uint32_t full = tc::smem_u32(&bar_full[stage]);
-          tc::mbar_expect_tx(full, kc * (A_BYTES + B_BYTES));
+          tc::mbar_expect_tx(full, kc * (a_chunk + B_BYTES));
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          tc::tma_load_5d(sa, &p.tmA[s][kc - 1], full, 0, sg.dw[t], y0 * sg.stride + sg.dh[t], img0, sg.coff[t] / BK + cb);
+          tc::tma_load_5d(sa, &p.tmA[s][kc - 1], full, 0, x0 * sg.stride + sg.dw[t], y0 * sg.stride + sg.dh[t], img0,
+                          sg.coff[t] / BK + cb);
           tc::tma_load_3d(sa + B_OFF, &p.tmB[kc - 1], full, 0, n0, sg.kchunk0 + t * sg.ncblk + cb);
           cb += kc;
           if (cb == sg.ncblk) {
@@ -250,6 +287,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         tc::mbar_wait(tc::smem_u32(&bar_acc_empty[ab]), ((wi >> 1) & 1) ^ 1);  // epilogue has drained this buffer
         tc::tc_fence_after();
         const uint32_t tmem_d = tmem_base + ab * ACC_COLS;
+        const uint32_t a_chunk = DENSE ? (uint32_t)A_BYTES : (uint32_t)p.a_rows * (BK * 2);
         for (int i = 0; i < nst; ++i, ++it) {
           const int kc = min(KC, p.seg[s].ncblk - cb);
           const int stage = it % STAGES;
@@ -258,7 +296,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           if (tc::elect_one()) {
             for (int c = 0; c < kc; ++c) {
-              const uint64_t adesc = tc::umma_desc_k_sw128(sa + c * A_BYTES);
+              const uint64_t adesc = tc::umma_desc_k_sw128(sa + c * a_chunk);
               const uint64_t bdesc = tc::umma_desc_k_sw128(sa + B_OFF + c * B_BYTES);
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k)  // +32 bytes (=2 in descriptor units) per K=16 slice inside the swizzle atom
@@ -287,15 +325,18 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     int wi = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wi) {
     const int mtile = w % p.mt, ntile = (w / p.mt) % p.nt, z = w / (p.mt * p.nt);
-    const int m0 = mtile * BM, n0 = ntile * BN;
+    const int n0 = ntile * BN;
     const int ab = wi & 1;
     const uint32_t tmem_d = tmem_base + ab * ACC_COLS;
-    const int m = m0 + row;
-    const bool ok = m < p.M;
-    const int img = m / p.hw;
+    int img0, y0, x0, di;
+    tile_origin<DENSE>(p, mtile, img0, y0, x0);
+    const int mtok = row_token<DENSE>(p, mtile, img0, y0, x0, row, di);
+    const bool ok = mtok >= 0;
+    const int m = ok ? mtok : 0;
+    if (!ok) di = 0;
+    const int img = img0 + di;
     // ---- while the main loop of this item runs: stage everything the epilogue needs that is not the accumulator
-    const int img0 = m0 / p.hw;
-    const int imgs_in_tile = (BM + p.hw - 1) / p.hw;
+    const int imgs_in_tile = DENSE ? (BM + p.hw - 1) / p.hw : p.bn;
     const bool use_table = (p.opt & 1) && (!p.partial || p.counters) && (p.bias || p.rowvec) && imgs_in_tile <= CV_IMGS;
     asm volatile("bar.sync 1, 128;" ::: "memory");  // previous item's readers of s_colvec are done
     if (use_table) {
@@ -303,7 +344,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
       for (int i = et; i < imgs_in_tile * BN; i += 128) {
         const int b = i / BN, c = i - b * BN;
         float v = p.bias ? p.bias[n0 + c] : 0.f;
-        if (p.rowvec && (int64_t)(img0 + b) * p.hw < p.M) v += p.rowvec[(int64_t)(img0 + b) * p.rowvec_ld + n0 + c];
+        if (p.rowvec && img0 + b < p.n_img) v += p.rowvec[(int64_t)(img0 + b) * p.rowvec_ld + n0 + c];
         s_colvec[b][c] = v;
       }
     }
@@ -316,7 +357,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
       for (int j = 0; j < 4; ++j) res_next[j] = res_row[j];
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    const float* cvrow = s_colvec[img - img0];
+    const float* cvrow = s_colvec[use_table ? di : 0];
     tc::mbar_wait(tc::smem_u32(&bar_acc_full[ab]), (wi >> 1) & 1);
     tc::tc_fence_after();
     // last item's main loop is done: let the next kernel's CTAs be scheduled (they set up barriers / TMEM / descriptors
@@ -447,8 +488,9 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         } while (seen < (unsigned)p.splits);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int rows_per = (BM + p.splits - 1) / p.splits;
-      const int r0 = z * rows_per, r1 = min(BM, r0 + rows_per);
+      const int a_rows = DENSE ? BM : p.a_rows;
+      const int rows_per = (a_rows + p.splits - 1) / p.splits;
+      const int r0 = min(a_rows, z * rows_per), r1 = min(a_rows, r0 + rows_per);
       constexpr int NV = BN / 8;
       const int items = (r1 - r0) * NV;
       const int64_t zstride = (int64_t)p.M * p.N;
@@ -456,16 +498,17 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         // 4 independent items per thread.  Dead slots (past the end / past M) alias the thread's first item so that
         // every load below is unconditional and the 4 x 2 x splits requests are all in flight together; only the
         // final store is predicated.
-        int mmv[4], nnv[4];
+        int mmv[4], nnv[4], div[4];
         bool live[4];
         float v[4][8];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int i = i0 + u * 128;
-          const int mm = m0 + r0 + i / NV;
-          live[u] = i < items && mm < p.M;
-          const int ii = live[u] ? i : i0;
-          mmv[u] = min(m0 + r0 + ii / NV, p.M - 1);
+          const int ii = i < items ? i : i0;
+          const int tok = row_token<DENSE>(p, mtile, img0, y0, x0, r0 + ii / NV, div[u]);
+          live[u] = i < items && tok >= 0;
+          mmv[u] = tok >= 0 ? tok : 0;  // dead slots read token 0 (loads stay unconditional), only the store is predicated
+          if (tok < 0) div[u] = 0;
           nnv[u] = (ii % NV) * 8;
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
@@ -477,7 +520,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
           rres[u] = p.residual ? *reinterpret_cast<const uint4*>(p.residual + (int64_t)mmv[u] * p.res_ld + n0 + nnv[u])
                                : make_uint4(0u, 0u, 0u, 0u);
           if (use_table) {
-            const float* cr = s_colvec[mmv[u] / p.hw - img0] + nnv[u];
+            const float* cr = s_colvec[div[u]] + nnv[u];
             cv0[u] = *reinterpret_cast<const float4*>(cr);
             cv1[u] = *reinterpret_cast<const float4*>(cr + 4);
           } else {
@@ -582,20 +625,25 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   }
 }
 
-template <int BN, int STAGES>
-void launch(cudaStream_t s, const TcParams& p, int splits) {
+template <int BN, int STAGES, bool DENSE>
+void launch_geom(cudaStream_t s, const TcParams& q, int grid) {
   constexpr int smem = STAGES * KC * (A_BYTES + BN * BK * 2) + 1024;
   static bool configured[kMaxDevices] = {};
   if (first_use_on_device(configured)) {
-    MV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
+  launch_pdl(gemm_tc_kernel<BN, STAGES, DENSE>, dim3(grid), dim3(192), smem, s, q);
+}
+
+template <int BN, int STAGES>
+void launch(cudaStream_t s, const TcParams& p, int splits) {
   const int num_sms = sm_count();  // SM count of the current device
   TcParams q = p;
-  q.mt = ceil_div(p.M, BM);
   q.nt = p.N / BN;
   q.splits = splits;
-  dim3 grid(std::min(q.mt * q.nt * q.splits, num_sms));
-  launch_pdl(gemm_tc_kernel<BN, STAGES>, grid, dim3(192), smem, s, q);
+  const int grid = std::min(q.mt * q.nt * q.splits, num_sms);
+  if (p.dense) launch_geom<BN, STAGES, true>(s, q, grid);
+  else launch_geom<BN, STAGES, false>(s, q, grid);
 }
 
 // ---- tile / split-K selection ---------------------------------------------------------------------
@@ -607,6 +655,48 @@ struct TileChoice {
   int bn, splits;
 };
 
+// M-tile geometry (see TcParams): dense 128-token tiles when the output width divides 128 and an image is a whole number of
+// tiles (or a tile a whole number of images); otherwise the box of (bw pixels x bh rows x bn images) that needs the fewest
+// tiles, with a_rows = bw*bh*bn <= 128 a multiple of 8 (SWIZZLE_128B atoms are 8 rows: every 64-channel chunk of the box
+// must start on a 1024-byte boundary).
+struct TileGeom {
+  int dense, bw, bh, bn, tx, ty, a_rows, mt;
+};
+bool tile_geometry(int n_img, int oh, int ow, TileGeom& g) {
+  const int hw = oh * ow;
+  if (ow <= BM && BM % ow == 0 && (hw % BM == 0 || BM % hw == 0)) {
+    g.dense = 1;
+    g.bw = ow;
+    g.bh = std::min(oh, BM / ow);
+    g.bn = BM / (g.bw * g.bh);
+    g.tx = 1;
+    g.ty = ceil_div(oh, g.bh);
+    g.a_rows = BM;
+    g.mt = ceil_div(n_img * hw, BM);
+    return true;
+  }
+  g.dense = 0;
+  g.tx = ceil_div(ow, BM);
+  while (g.tx <= ow && ow % g.tx != 0) ++g.tx;  // equal column blocks
+  g.bw = ow / g.tx;
+  if (g.bw > BM) return false;
+  long best_tiles = -1;
+  for (int bh = 1; bh <= std::min(oh, BM / g.bw); ++bh)
+    for (int bn = 1; bn <= BM / (g.bw * bh) && bn <= 256; ++bn) {
+      const int rows = g.bw * bh * bn;
+      if (rows % 8 != 0) continue;
+      const long tiles = (long)g.tx * ceil_div(oh, bh) * ceil_div(n_img, bn);
+      if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && rows > g.a_rows)) {
+        best_tiles = tiles;
+        g.bh = bh; g.bn = bn; g.a_rows = rows;
+      }
+    }
+  if (best_tiles < 0) return false;
+  g.ty = ceil_div(oh, g.bh);
+  g.mt = (int)best_tiles;
+  return true;
+}
+
 int count_steps(const mvldm_gemm_desc& d) {
   int steps = 0;
   for (int i = 0; i < d.nseg; ++i) steps += d.seg[i].ntaps * ceil_div(d.seg[i].c / BK, KC);
@@ -616,7 +706,9 @@ int count_steps(const mvldm_gemm_desc& d) {
 TileChoice pick_tiles(const mvldm_gemm_desc& d) {
   static const int kBN[5] = {256, 160, 128, 64, 32};
   static const int kSplits[12] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 24, 32};
-  const int M = d.n_img * d.oh * d.ow, mt = ceil_div(M, BM), num_steps = count_steps(d);
+  const int M = d.n_img * d.oh * d.ow, num_steps = count_steps(d);
+  TileGeom geom{};
+  const int mt = tile_geometry(d.n_img, d.oh, d.ow, geom) ? geom.mt : ceil_div(M, BM);
   const double kb_per_step = (double)(d.k / BK) / num_steps;  // 64-chunks an average step carries (<= KC)
   TileChoice best{0, 1};
   double best_t = 1e30;
@@ -669,12 +761,13 @@ void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t w
   p.hw = hw;
   p.ow = d.ow;
   MV_CHECK(d.nseg >= 1 && d.nseg <= MVLDM_MAX_SEGS, "gemm: bad segment count");
-  MV_CHECK(d.ow <= BM && BM % d.ow == 0, "gemm: output width must divide 128");
-  MV_CHECK(hw % BM == 0 || BM % hw == 0, "gemm: pixels per image must divide or be a multiple of 128");
-  // 128-pixel tile = bw x bh x bn box of whole rows / whole images
-  const int bw = d.ow;
-  const int bh = std::min(d.oh, BM / bw);
-  const int bn = BM / (bw * bh);
+  TileGeom geom{};
+  MV_CHECK(tile_geometry(d.n_img, d.oh, d.ow, geom),
+           "gemm: no M-tile geometry for this output size (width " + std::to_string(d.ow) + ", height " + std::to_string(d.oh) + ")");
+  // M tile = bw x bh x bn box (whole rows / whole images in the dense case)
+  const int bw = geom.bw, bh = geom.bh, bn = geom.bn;
+  p.dense = geom.dense; p.bw = bw; p.bh = bh; p.bn = bn; p.tx = geom.tx; p.ty = geom.ty; p.a_rows = geom.a_rows;
+  p.mt = geom.mt; p.oh = d.oh; p.n_img = d.n_img;
   for (int i = 0; i < d.nseg; ++i)
     MV_CHECK(d.seg[i].c >= BK && d.seg[i].c % BK == 0, "gemm: segment channels must be a multiple of 64");
   const TileChoice tile = pick_tiles(d);
@@ -730,10 +823,10 @@ void gemm_tc(cudaStream_t s, const mvldm_gemm_desc& d, void* workspace, size_t w
   splits = ceil_div(p.num_steps, p.steps_per_split);
   p.partial = splits > 1 ? reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kCounterBytes) : nullptr;
   // fused reduction needs every split of a tile resident at once: one work item per CTA, grid <= #SMs
-  const int work = ceil_div(p.M, BM) * (d.n / BN) * splits;
+  const int work = p.mt * (d.n / BN) * splits;
   // (one CTA per SM: shared memory; the kernel is launched with min(work, #SMs) CTAs, so work <= #SMs means every split
   // of every tile has its own resident CTA on an otherwise idle device; more work takes the two-pass reduction)
-  const bool fused = splits > 1 && work <= sm_count() && ceil_div(p.M, BM) * (d.n / BN) <= 4096;
+  const bool fused = splits > 1 && work <= sm_count() && p.mt * (d.n / BN) <= 4096;
   p.counters = fused ? reinterpret_cast<int*>(workspace) : nullptr;
   {
     static const int opt = [] {

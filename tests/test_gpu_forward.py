@@ -99,10 +99,11 @@ def test_other_latent_size(gpu_models, oracle_weights, oracle_cfg):
     assert rel_err(y, ref) < FWD_TOL
 
 
-@pytest.mark.parametrize("h,w,v", [(64, 64, 2), (32, 16, 3), (8, 8, 5)])
+@pytest.mark.parametrize("h,w,v", [(64, 64, 2), (32, 16, 3), (8, 8, 5), (24, 24, 3), (48, 40, 1), (40, 24, 2)])
 def test_more_latent_sizes(h, w, v, gpu_models, oracle_weights, oracle_cfg):
     """512x512 images (64x64 latents: level 0 is above the 32x32 multi-view limit, mvunet.py:137,190, so its two
-    multi-view blocks are skipped), a non-square latent, and the smallest size the 4-level UNet accepts (8x8 -> 1x1)."""
+    multi-view blocks are skipped), a non-square latent, the smallest size the 4-level UNet accepts (8x8 -> 1x1), and
+    sizes whose widths do not divide 128 (192 / 384 / 320-pixel images: 24, 48, 40-wide latents and their coarser levels)."""
     torch.manual_seed(h + w + v)
     x = torch.randn(1, v, 11, h, w)
     t = torch.randint(0, 1000, (1, v))

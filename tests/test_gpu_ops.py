@@ -164,11 +164,52 @@ def test_tcgen05_matches_simt_bitwise_close():
     assert torch.equal(a, run_gemm(0, [conv_seg(x)], 8, 16, 16, wp).float())   # bit-stable rerun
 
 
+@pytest.mark.parametrize("n,cin,cout,h,w,stride", [
+    (2, 64, 64, 24, 24, 1),      # 24-wide rows: tile = 24 x 5 rows = 120 of the 128 MMA rows, ragged last tile (24 = 4*5 + 4)
+    (3, 128, 96, 12, 12, 1),     # 12 x 10 rows
+    (5, 64, 64, 6, 6, 1),        # 6 x 6 x 2 images = 72 rows, odd image count
+    (7, 64, 32, 3, 3, 1),        # 9-pixel images: 3 x 1 x 8 images = 24 rows per tile
+    (2, 64, 64, 5, 5, 1),        # 5 x 5
+    (2, 64, 64, 48, 24, 2),      # stride 2 onto 24 x 12
+    (1, 64, 64, 8, 256, 1),      # 256-wide rows split into two 128-pixel column blocks (VAE resolution)
+    (1, 128, 64, 6, 192, 1),     # 192 = 2 x 96
+    (2, 1280, 128, 12, 12, 1),   # K = 11520: split-K with the general geometry (fused fixed-order reduce)
+    (8, 640, 256, 6, 6, 1),
+])
+def test_conv3x3_general_tile_geometry(n, cin, cout, h, w, stride):
+    """output sizes whose width does not divide 128 (24x24 / 48x48 / 40x40 latents and their coarser levels) or exceeds it
+    (256-wide feature maps): the M tile is a (columns x rows x images) TMA box covering <= 128 rows of the MMA"""
+    torch.manual_seed(n + cin + cout + h + w)
+    x = torch.randn(n, cin, h, w)
+    wt = torch.randn(cout, cin, 3, 3) / (3 * cin ** 0.5)
+    b = torch.randn(cout)
+    xb, wp = nhwc_bf16(x).cuda(), pack_conv_weight(wt).cuda()
+    oh, ow = h // stride, w // stride
+    res = torch.randn(n * oh * ow, cout).to(torch.bfloat16).cuda()
+    rv = torch.randn(n, cout).cuda()
+    ref = _conv_ref(xb, wp, b, cout, cin, stride)
+    ref = ref + rv.cpu()[:, :, None, None] + res.float().cpu().reshape(n, oh, ow, cout).permute(0, 3, 1, 2)
+    outs = []
+    for impl in (0, 1):
+        out = run_gemm(impl, [conv_seg(xb, stride)], n, oh, ow, wp, bias=b.cuda(), rowvec=rv, residual=res)
+        got = out.float().cpu().reshape(n, oh, ow, cout).permute(0, 3, 1, 2)
+        assert rel_err(got, ref) < BF16_TOL, impl
+        outs.append(out)
+    assert torch.equal(outs[0], run_gemm(0, [conv_seg(xb, stride)], n, oh, ow, wp, bias=b.cuda(), rowvec=rv, residual=res))
+    if stride == 1 and cout == 64:     # fp32 NCHW head (mode 2) on the same geometry
+        wh = torch.zeros(32, 9 * cin)
+        wh[:4] = torch.randn(4, 9 * cin) / (3 * cin ** 0.5)
+        o2 = run_gemm(0, [conv_seg(xb)], n, oh, ow, wh.to(torch.bfloat16).cuda(), mode=2, n_valid=4)
+        r2 = F.conv2d(xb.float().permute(0, 3, 1, 2).cpu(), wh[:4].to(torch.bfloat16).float().reshape(4, 3, 3, cin).permute(0, 3, 1, 2),
+                      padding=1)
+        assert rel_err(o2, r2) < 1e-4
+
+
 def test_gemm_rejects_unsupported_shapes():
-    x = nhwc_bf16(torch.randn(1, 64, 12, 12)).cuda()          # 12 does not divide 128
+    x = nhwc_bf16(torch.randn(1, 64, 1, 129)).cuda()          # 129-wide rows: no equal column blocks of <= 128 pixels ...
     wp = pack_conv_weight(torch.randn(64, 64, 3, 3)).cuda()
-    with pytest.raises(RuntimeError):
-        run_gemm(0, [conv_seg(x)], 1, 12, 12, wp)
+    with pytest.raises(RuntimeError):                         # ... with a row count that is a multiple of 8
+        run_gemm(0, [conv_seg(x)], 1, 1, 129, wp)
     x = nhwc_bf16(torch.randn(1, 48, 8, 8)).cuda()            # channels not a multiple of 64
     wp = pack_conv_weight(torch.randn(64, 48, 3, 3)).cuda()
     with pytest.raises(RuntimeError):
