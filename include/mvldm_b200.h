@@ -30,6 +30,7 @@ enum { MVLDM_F32 = 0, MVLDM_BF16 = 1, MVLDM_F16 = 2 };
  * cross-check for the tests (never selected implicitly) */
 enum { MVLDM_IMPL_TC = 0, MVLDM_IMPL_SIMT = 1, MVLDM_IMPL_TC_GEMM_SIMT_ATTN = 2 };
 enum { MVLDM_MV_SPATIAL_TRANSFORMER_3D = 0, MVLDM_MV_STANDARD = 1 };
+enum { MVLDM_MODEL_DENOISER = 0, MVLDM_MODEL_VAE = 1 };
 
 /* Replaces: MultiViewUNetCfg + UNet2DModelCfg + SpatialTransformer3DCfg
  * (src/model/denoiser/mvunet.py:22-40, src/model/denoiser/mvdream/attention.py:23-32) and the
@@ -61,6 +62,13 @@ typedef struct {
   int32_t mv_num_layers;                        /* CrossAttentionCfg.num_layers (standard only; >= 1) */
   int32_t mv_d_mlp;                             /* CrossAttentionCfg.d_mlp, or 0 to use the multiplier */
   int32_t mv_d_mlp_multiplier;                  /* hidden width = d_in * multiplier when mv_d_mlp == 0 */
+  /* MVLDM_MODEL_VAE: the handle is the first-stage autoencoder instead of the denoiser - diffusers AutoencoderKL as built by
+   * get_autoencoder (src/model/autoencoder/__init__.py:36-43; SD-2.1 "vae" subfolder: block_out_channels [128,256,512,512],
+   * layers_per_block 2, 32 groups, latent_channels 4).  Uses in_channels / out_channels (image channels), num_levels,
+   * block_out_channels, layers_per_block, norm_groups, latent_channels; state-dict keys are diffusers' (encoder.*,
+   * decoder.*, quant_conv.*, post_quant_conv.*).  Entry points: mvldm_vae_encode / mvldm_vae_decode. */
+  int32_t model;                                /* MVLDM_MODEL_DENOISER or MVLDM_MODEL_VAE */
+  int32_t latent_channels;                      /* 4 */
 } mvldm_config;
 
 const char* mvldm_last_error(void);
@@ -117,6 +125,17 @@ int mvldm_forward(mvldm_handle h, void* stream, const float* latents, const int6
  * :437-441) of every scene go through the network together. */
 int mvldm_forward_scenes(mvldm_handle h, void* stream, const float* latents, const int64_t* timesteps, int num_scenes,
                          const int32_t* views_per_scene, int H, int W, float* out);
+
+/* First-stage autoencoder (handle created with cfg.model = MVLDM_MODEL_VAE).
+ * mvldm_vae_decode replaces `self.autoencoder.decode(latents).sample` (src/model/diffusion_wrapper.py:293-295): latents device
+ * fp32 [n, latent_channels, H, W] (already divided by the 0.18215 scaling, as the caller does at :292) -> image fp32
+ * [n, out_channels, H*f, W*f], f = 2^(num_levels-1), values nominally in [-1, 1] (the caller maps to [0, 1], :298).
+ * mvldm_vae_encode replaces `self.autoencoder.encode(inputs).latent_dist` (:283): image fp32 [n, in_channels, H, W] in
+ * [-1, 1] -> moments fp32 [n, 2*latent_channels, H/f, W/f] = (mean | logvar) of the diagonal Gaussian; the caller draws the
+ * sample (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise) so that the host RNG stays the reference's.
+ * H*W/f^2 (tokens per image in the mid-block attention) must be a multiple of 64 and <= 4096. */
+int mvldm_vae_decode(mvldm_handle h, void* stream, const float* latents, int n, int H, int W, float* image);
+int mvldm_vae_encode(mvldm_handle h, void* stream, const float* image, int n, int H, int W, float* moments);
 
 /* View-group sharding: a scene whose views are split over several GPUs.  This rank holds the
  * `group_index`-th group of V_local contiguous views of ONE scene (B = 1) out of V_total; every op is per view except

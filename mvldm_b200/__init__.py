@@ -9,6 +9,8 @@ from .denoiser import (DENOISER, CrossAttentionCfg, Denoiser, DenoiserCfg, Multi
                        SpatialTransformer3DCfg,
                        UNet2DModelCfg, default_cfg, get_denoiser, standard_cfg)
 from .anchored import AnchoredPlan, anchored_plan, sample_anchored
+from .autoencoder import (AUTOENCODERS, AutoencoderCfg, AutoencoderKL, AutoencoderKLCfg, first_stage_encode, get_autoencoder,
+                          last_stage_decode, sd21_vae_cfg)
 from .sampler import DenoisingPath, build_inputs, ray_encode
 from .scheduler import (SCHEDULER, DDIMScheduler, DDIMSchedulerCfg, SchedulerCfg, fused_cfg_ddim_step, get_scheduler)
 from .sharding import ViewGroupExchange, gather_scenes, scene_slice, view_slice
@@ -18,4 +20,6 @@ __all__ = [
     "UNet2DModelCfg", "default_cfg", "standard_cfg", "get_denoiser", "DenoisingPath", "build_inputs", "ray_encode", "SCHEDULER",
     "DDIMScheduler", "DDIMSchedulerCfg", "SchedulerCfg", "fused_cfg_ddim_step", "get_scheduler", "gather_scenes",
     "scene_slice", "view_slice", "ViewGroupExchange", "AnchoredPlan", "anchored_plan", "sample_anchored",
+    "AUTOENCODERS", "AutoencoderCfg", "AutoencoderKL", "AutoencoderKLCfg", "get_autoencoder", "first_stage_encode",
+    "last_stage_decode", "sd21_vae_cfg",
 ]

@@ -17,6 +17,7 @@ MVLDM_MAX_SEGS = 3
 F32, BF16, F16 = 0, 1, 2
 IMPL_TC, IMPL_SIMT, IMPL_TC_GEMM_SIMT_ATTN = 0, 1, 2
 MV_SPATIAL_TRANSFORMER_3D, MV_STANDARD = 0, 1
+MODEL_DENOISER, MODEL_VAE = 0, 1
 
 
 class Config(Structure):
@@ -27,6 +28,7 @@ class Config(Structure):
         ("use_cuda_graph", c_int32),
         ("variant", c_int32), ("t2d_heads", c_int32 * MVLDM_MAX_LEVELS), ("cross_attention_dim", c_int32),
         ("mv_block", c_int32), ("mv_num_layers", c_int32), ("mv_d_mlp", c_int32), ("mv_d_mlp_multiplier", c_int32),
+        ("model", c_int32), ("latent_channels", c_int32),
     ]
 
 
@@ -85,6 +87,8 @@ SYMBOLS["mvldm_forward_scenes"] = (c_int, [c_void_p, c_void_p, c_void_p, c_void_
                                            c_void_p])
 SYMBOLS["mvldm_op_attention_kv"] = (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
                                             c_int, c_int, c_int, c_int, c_int, c_void_p])
+SYMBOLS["mvldm_vae_decode"] = (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p])
+SYMBOLS["mvldm_vae_encode"] = (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p])
 SYMBOLS["mvldm_op_attention_merge"] = (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), c_int64, c_int, c_int,
                                                c_void_p])
 

@@ -110,7 +110,9 @@ void attention_tc_kv(cudaStream_t s, const bf16* q, int ld_q, int q_col0, const 
 void attention_merge(cudaStream_t s, int nparts, const bf16* const* parts, const float* const* stats, int64_t rows, int heads,
                      int dpad, bf16* out);
 // norm.cu
-void im2col_input(cudaStream_t s, const float* latents, int n_img, int cin, int h, int w, int kpad, bf16* out);
+void im2col_input(cudaStream_t s, const float* latents, int n_img, int cin, int h, int w, int kpad, bf16* out,
+                  const float* premix = nullptr);
+void softmax_rows(cudaStream_t s, const float* in, int64_t rows, int cols, float scale, bf16* out);
 void timestep_sinusoid_bf16(cudaStream_t s, const int64_t* t, int n, int dim, bf16* out);
 void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, int n_img, int hw, int groups,
                float eps, const float* gamma, const float* beta, bool silu, bf16* out, float* scratch);

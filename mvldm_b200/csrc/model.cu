@@ -65,6 +65,8 @@ struct ResnetW {
   std::string key;
   int cin = 0, cout = 0, temb_off = 0;
   bool shortcut = false;
+  bool temb = true;    // false: the VAE's ResnetBlock2D(temb_channels=None)
+  float eps = 1e-5f;   // 1e-6 in the VAE
   const float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr;
   Packed conv1, conv2;  // conv2 carries the 1x1 shortcut as extra K columns when present
 };
@@ -83,6 +85,22 @@ struct MvW {  // SpatialTransformer3D block, or (t2d) a per-view diffusers Trans
   bool standard = false;
   int d_mlp = 0;
   std::vector<StdLayer> layers;
+};
+
+// AutoencoderKL mid-block attention (diffusers Attention, 1 head of C channels, GroupNorm 1e-6, residual)
+struct VaeAttnW {
+  std::string key;
+  int c = 0;
+  const float *gn_g = nullptr, *gn_b = nullptr;
+  Packed q, k, v, out;
+};
+struct VaeHalf {  // encoder or decoder
+  Packed conv_in, conv_out;
+  std::vector<std::vector<ResnetW>> blocks;
+  std::vector<Packed> resample;  // downsamplers.0.conv / upsamplers.0.conv per block (w == nullptr: none)
+  ResnetW mid0, mid1;
+  VaeAttnW attn;
+  const float *norm_g = nullptr, *norm_b = nullptr;
 };
 
 struct Arena {
@@ -111,7 +129,7 @@ struct OpMeta {  // what a launch is, for the per-op timing report
   double scores = 0, flops_padded = 0;  // attention only: softmax exponentials (one ex2 each) and tensor-pipe FLOPs on padded heads
 };
 struct Step {
-  enum Kind { GEMM, GEMM_SIMT, ATTN, ATTN_SHARDED, GN, LN, UPSAMPLE, IM2COL, SINUSOID } kind = GEMM;
+  enum Kind { GEMM, GEMM_SIMT, ATTN, ATTN_SHARDED, GN, LN, UPSAMPLE, IM2COL, SINUSOID, SOFTMAX } kind = GEMM;
   mvldm_gemm_desc gemm{};  // GEMM / GEMM_SIMT
   // ATTN / ATTN_SHARDED
   const bf16* qkv = nullptr;
@@ -175,6 +193,10 @@ struct mvldm_handle_s {
   std::set<std::string> unused;  // keys of modules the reference forward never calls (up-block attentions)
   const float *norm_out_g = nullptr, *norm_out_b = nullptr;
   int kpad_in = 0;
+  // cfg.model == MVLDM_MODEL_VAE: AutoencoderKL (SD VAE) encoder / decoder on the same kernels
+  VaeHalf vae_enc, vae_dec;
+  const float* vae_premix = nullptr;  // post_quant_conv as [latent x latent weights | latent biases]
+  int program = 0;                    // what plan_for records: 0 denoiser forward, 1 VAE decode, 2 VAE encode
 
   std::map<std::vector<int>, std::unique_ptr<Plan>> plans;
   int last_launches = 0;
@@ -723,11 +745,12 @@ struct mvldm_handle_s {
     Act out = new_act(n, h, w, r.cout);
     const size_t mark = arena.off;
     Act a = new_act(n, h, w, r.cin);
-    gn(x0, x1, r.g1, r.b1, 1e-5f, true, a);
+    gn(x0, x1, r.g1, r.b1, r.eps, true, a);
     Act hdn = new_act(n, h, w, r.cout);
-    gemm({seg_conv3x3(a)}, r.conv1, hdn, temb + r.temb_off, temb_total);
+    if (r.temb) gemm({seg_conv3x3(a)}, r.conv1, hdn, temb + r.temb_off, temb_total);
+    else gemm({seg_conv3x3(a)}, r.conv1, hdn);
     Act a2 = new_act(n, h, w, r.cout);
-    gn(hdn, nullptr, r.g2, r.b2, 1e-5f, true, a2);
+    gn(hdn, nullptr, r.g2, r.b2, r.eps, true, a2);
     if (r.shortcut) {
       if (x1) gemm({seg_conv3x3(a2), seg_1x1(x0), seg_1x1(*x1)}, r.conv2, out);
       else gemm({seg_conv3x3(a2), seg_1x1(x0)}, r.conv2, out);
@@ -857,6 +880,341 @@ struct mvldm_handle_s {
     return out;
   }
 
+
+  // =========================== AutoencoderKL (cfg.model == MVLDM_MODEL_VAE) ===========================
+  // diffusers AutoencoderKL as the reference constructs it (src/model/autoencoder/__init__.py:40-43) and calls it
+  // (diffusion_wrapper.py:278-298): Encoder / Decoder of ResnetBlock2D(temb=None, eps 1e-6) stacks, one single-head attention
+  // in each mid block, quant_conv / post_quant_conv.  State-dict keys are diffusers' (encoder.*, decoder.*, quant_conv.*,
+  // post_quant_conv.*).  Same kernels as the denoiser: implicit-GEMM conv3x3, GroupNorm(+SiLU), nearest 2x upsample.
+  ResnetW reg_vae_resnet(const std::string& k, int cin, int cout) {
+    reg_norm(k + ".norm1", cin);
+    reg_conv(k + ".conv1", cout, cin, 3);
+    reg_norm(k + ".norm2", cout);
+    reg_conv(k + ".conv2", cout, cout, 3);
+    if (cin != cout) reg_conv(k + ".conv_shortcut", cout, cin, 1);
+    ResnetW r;
+    r.key = k; r.cin = cin; r.cout = cout; r.shortcut = cin != cout; r.temb = false; r.eps = 1e-6f;
+    return r;
+  }
+  VaeAttnW reg_vae_attn(const std::string& k, int c) {
+    reg_norm(k + ".group_norm", c);
+    for (const char* n : {".to_q", ".to_k", ".to_v", ".to_out.0"}) reg_lin(k + n, c, c);
+    VaeAttnW a;
+    a.key = k; a.c = c;
+    return a;
+  }
+  void build_vae_registry() {
+    const int L = cfg.num_levels;
+    const int* boc = cfg.block_out_channels;
+    const int lc = cfg.latent_channels;
+    // ---- encoder: conv_in, L DownEncoderBlock2D (layers_per_block resnets, stride-2 conv except the last), mid, head
+    reg_conv("encoder.conv_in", boc[0], cfg.in_channels, 3);
+    vae_enc.blocks.resize(L);
+    int c = boc[0];
+    for (int l = 0; l < L; ++l) {
+      for (int i = 0; i < cfg.layers_per_block; ++i) {
+        vae_enc.blocks[l].push_back(reg_vae_resnet("encoder.down_blocks." + std::to_string(l) + ".resnets." + std::to_string(i),
+                                                   i == 0 ? c : boc[l], boc[l]));
+      }
+      c = boc[l];
+      if (l != L - 1) reg_conv("encoder.down_blocks." + std::to_string(l) + ".downsamplers.0.conv", c, c, 3);
+    }
+    vae_enc.mid0 = reg_vae_resnet("encoder.mid_block.resnets.0", c, c);
+    vae_enc.attn = reg_vae_attn("encoder.mid_block.attentions.0", c);
+    vae_enc.mid1 = reg_vae_resnet("encoder.mid_block.resnets.1", c, c);
+    reg_norm("encoder.conv_norm_out", c);
+    reg_conv("encoder.conv_out", 2 * lc, c, 3);
+    reg_conv("quant_conv", 2 * lc, 2 * lc, 1);
+    reg_conv("post_quant_conv", lc, lc, 1);
+    // ---- decoder: conv_in, mid, L UpDecoderBlock2D (layers_per_block + 1 resnets, nearest-2x + conv except the last), head
+    reg_conv("decoder.conv_in", boc[L - 1], lc, 3);
+    c = boc[L - 1];
+    vae_dec.mid0 = reg_vae_resnet("decoder.mid_block.resnets.0", c, c);
+    vae_dec.attn = reg_vae_attn("decoder.mid_block.attentions.0", c);
+    vae_dec.mid1 = reg_vae_resnet("decoder.mid_block.resnets.1", c, c);
+    vae_dec.blocks.resize(L);
+    for (int l = 0; l < L; ++l) {
+      const int co = boc[L - 1 - l];
+      for (int i = 0; i < cfg.layers_per_block + 1; ++i)
+        vae_dec.blocks[l].push_back(reg_vae_resnet("decoder.up_blocks." + std::to_string(l) + ".resnets." + std::to_string(i),
+                                                   i == 0 ? c : co, co));
+      c = co;
+      if (l != L - 1) reg_conv("decoder.up_blocks." + std::to_string(l) + ".upsamplers.0.conv", c, c, 3);
+    }
+    reg_norm("decoder.conv_norm_out", c);
+    reg_conv("decoder.conv_out", cfg.out_channels, c, 3);
+  }
+  void pack_vae_resnet(ResnetW& r) {
+    r.g1 = rawf(r.key + ".norm1.weight"); r.b1 = rawf(r.key + ".norm1.bias");
+    r.g2 = rawf(r.key + ".norm2.weight"); r.b2 = rawf(r.key + ".norm2.bias");
+    r.conv1 = pack_conv(r.key + ".conv1", r.cout, r.cin, 3);
+    if (r.shortcut) {  // conv2 and the 1x1 shortcut share one accumulator, as in the UNet
+      r.conv2 = pack_conv(r.key + ".conv2", r.cout, r.cout, 3, r.cin);
+      pack_rows(stream, rawf(r.key + ".conv_shortcut.weight"), r.cout, r.cin, r.cin, r.conv2.w, r.conv2.k, 9 * r.cout, nullptr);
+      r.conv2.bias = bias_sum(r.key + ".conv2.bias", r.key + ".conv_shortcut.bias", r.cout);
+    } else {
+      r.conv2 = pack_conv(r.key + ".conv2", r.cout, r.cout, 3);
+    }
+  }
+  void pack_vae_attn(VaeAttnW& a) {
+    a.gn_g = rawf(a.key + ".group_norm.weight");
+    a.gn_b = rawf(a.key + ".group_norm.bias");
+    a.q = pack_linear(a.key + ".to_q", a.c, a.c, true);
+    a.k = pack_linear(a.key + ".to_k", a.c, a.c, true);
+    a.v = pack_linear(a.key + ".to_v", a.c, a.c, true);
+    a.out = pack_linear(a.key + ".to_out.0", a.c, a.c, true);
+  }
+  std::vector<float> download(const std::string& k, size_t count) {
+    std::vector<float> v(count);
+    MV_CUDA(cudaMemcpyAsync(v.data(), rawf(k), count * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    MV_CUDA(cudaStreamSynchronize(stream));
+    return v;
+  }
+  void finalize_vae(cudaStream_t s) {
+    stream = s;
+    for (auto& n : names) MV_CHECK(raw.count(n), "mvldm_finalize_weights: missing weight " + n);
+    MV_CUDA(cudaStreamSynchronize(s));
+    packed_store.clear();
+    const int L = cfg.num_levels;
+    const int* boc = cfg.block_out_channels;
+    const int lc = cfg.latent_channels;
+    auto pack_in = [&](const std::string& k, int cout, int cin) {  // conv on the explicit im2col operand, K padded to 64
+      Packed p;
+      p.n = cout;
+      p.k = (9 * cin + 63) / 64 * 64;
+      p.w = store<bf16>((size_t)p.n * p.k);
+      pack_conv3x3(stream, rawf(k + ".weight"), cout, cin, 3, p.w, p.k, 0);
+      p.bias = bias_sum(k + ".bias", "", cout);
+      return p;
+    };
+    // ---- encoder
+    vae_enc.conv_in = pack_in("encoder.conv_in", boc[0], cfg.in_channels);
+    vae_enc.resample.assign(L, Packed{});
+    for (int l = 0; l < L; ++l) {
+      for (auto& r : vae_enc.blocks[l]) pack_vae_resnet(r);
+      if (l != L - 1)
+        vae_enc.resample[l] = pack_conv("encoder.down_blocks." + std::to_string(l) + ".downsamplers.0.conv", boc[l], boc[l], 3);
+    }
+    pack_vae_resnet(vae_enc.mid0);
+    pack_vae_attn(vae_enc.attn);
+    pack_vae_resnet(vae_enc.mid1);
+    vae_enc.norm_g = rawf("encoder.conv_norm_out.weight");
+    vae_enc.norm_b = rawf("encoder.conv_norm_out.bias");
+    {  // quant_conv (1x1, 2*lc -> 2*lc) composed into conv_out: both are linear and nothing sits between them
+      const int m2 = 2 * lc, cl = boc[L - 1], kk = 9 * cl;
+      MV_CHECK(m2 <= 32, "latent_channels too large for the fp32 NCHW head (2 * latent_channels <= 32)");
+      const std::vector<float> wc = download("encoder.conv_out.weight", (size_t)m2 * kk);  // [m2, cl, 3, 3]
+      const std::vector<float> bc = download("encoder.conv_out.bias", m2);
+      const std::vector<float> wq = download("quant_conv.weight", (size_t)m2 * m2);
+      const std::vector<float> bq = download("quant_conv.bias", m2);
+      std::vector<float> w2((size_t)m2 * kk, 0.f), b2(32, 0.f);
+      for (int o = 0; o < m2; ++o) {
+        double b = bq[o];
+        for (int i = 0; i < m2; ++i) {
+          b += (double)wq[o * m2 + i] * bc[i];
+          const float f = wq[o * m2 + i];
+          for (int e = 0; e < kk; ++e) w2[(size_t)o * kk + e] += f * wc[(size_t)i * kk + e];
+        }
+        b2[o] = (float)b;
+      }
+      float* dw = store<float>((size_t)m2 * kk);
+      MV_CUDA(cudaMemcpyAsync(dw, w2.data(), w2.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+      vae_enc.conv_out.n = 32;
+      vae_enc.conv_out.k = kk;
+      vae_enc.conv_out.w = store<bf16>((size_t)32 * kk);
+      pack_conv3x3(stream, dw, m2, cl, 3, vae_enc.conv_out.w, kk, 0);
+      vae_enc.conv_out.bias = store<float>(32);
+      MV_CUDA(cudaMemcpyAsync(vae_enc.conv_out.bias, b2.data(), 32 * sizeof(float), cudaMemcpyHostToDevice, stream));
+      MV_CUDA(cudaStreamSynchronize(stream));
+    }
+    // ---- decoder
+    {
+      const std::vector<float> wq = download("post_quant_conv.weight", (size_t)lc * lc);
+      const std::vector<float> bq = download("post_quant_conv.bias", lc);
+      std::vector<float> pm(wq);
+      pm.insert(pm.end(), bq.begin(), bq.end());
+      float* d = store<float>(pm.size());
+      MV_CUDA(cudaMemcpyAsync(d, pm.data(), pm.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+      MV_CUDA(cudaStreamSynchronize(stream));
+      vae_premix = d;
+    }
+    vae_dec.conv_in = pack_in("decoder.conv_in", boc[L - 1], lc);
+    pack_vae_resnet(vae_dec.mid0);
+    pack_vae_attn(vae_dec.attn);
+    pack_vae_resnet(vae_dec.mid1);
+    vae_dec.resample.assign(L, Packed{});
+    for (int l = 0; l < L; ++l) {
+      for (auto& r : vae_dec.blocks[l]) pack_vae_resnet(r);
+      if (l != L - 1)
+        vae_dec.resample[l] = pack_conv("decoder.up_blocks." + std::to_string(l) + ".upsamplers.0.conv", boc[L - 1 - l],
+                                        boc[L - 1 - l], 3);
+    }
+    vae_dec.norm_g = rawf("decoder.conv_norm_out.weight");
+    vae_dec.norm_b = rawf("decoder.conv_norm_out.bias");
+    vae_dec.conv_out = pack_conv("decoder.conv_out", cfg.out_channels, boc[0], 3, 0, 32);
+    MV_CUDA(cudaStreamSynchronize(s));
+    for (auto it = raw.begin(); it != raw.end();) {
+      const bool keep = it->first.find("norm") != std::string::npos;
+      it = keep ? std::next(it) : raw.erase(it);
+    }
+    plans.clear();
+    prof_plan = last_plan = nullptr;
+    finalized = true;
+  }
+
+  void im2col_step(const float* src, int n, int cin, int h, int w, int kpad, const float* premix, const Act& col) {
+    if (dry) return;
+    Step st;
+    st.kind = Step::IM2COL;
+    st.x0 = src; st.n_img = n; st.c0 = cin; st.h = h; st.w = w; st.aux = kpad; st.dst = col.p; st.gamma = premix;
+    st.meta = OpMeta{"input_im2col", "", 0.0, (double)col.tokens() * (kpad * 2 + cin * 4)};
+    push_step(st);
+  }
+  Act upsample2x(const Act& x) {
+    Act u = new_act(x.n, x.h * 2, x.w * 2, x.c);
+    if (!dry) {
+      Step st;
+      st.kind = Step::UPSAMPLE;
+      st.x0 = x.p; st.n_img = x.n; st.h = x.h; st.w = x.w; st.c0 = x.c; st.dst = u.p;
+      st.meta = OpMeta{"upsample", "", 0.0, 2.5 * (double)u.tokens() * u.c};
+      push_step(st);
+    }
+    return u;
+  }
+  // head: GroupNorm -> SiLU -> conv3x3 -> fp32 NCHW
+  void nchw_head(const Act& x, const float* g, const float* b, float eps, const Packed& w, int n_valid, float* out) {
+    Act a = new_act(x.n, x.h, x.w, x.c);
+    gn(x, nullptr, g, b, eps, true, a);
+    mvldm_gemm_desc d{};
+    d.nseg = 1;
+    d.seg[0] = seg_conv3x3(a);
+    d.n_img = x.n; d.oh = x.h; d.ow = x.w;
+    d.w = w.w; d.n = w.n; d.k = w.k;
+    d.bias = w.bias;
+    d.mode = 2; d.out = out; d.n_valid = n_valid;
+    run_gemm(d, 2.0 * (double)x.tokens() * n_valid * w.k);
+  }
+  // diffusers Attention(heads=1, dim_head=C, residual_connection, norm_num_groups, eps 1e-6) over the h*w tokens of each image.
+  // One 512-wide head does not fit the flash kernels (head_dim <= 192), and at 1024 tokens per image the score matrix is 2 MB:
+  // it runs as plain GEMMs on the tcgen05 kernel.  Per image: S = Q K^T (fp32) -> softmax rows (bf16) -> O = P V with V^T
+  // produced directly by a GEMM whose "activation" operand is W_v and whose "weight" operand is the normalised input; b_v is
+  // added after P V (softmax rows sum to 1).
+  Act vae_attention(const VaeAttnW& a, const Act& x) {
+    const int n = x.n, h = x.h, w = x.w, C = a.c, hw = h * w;
+    MV_CHECK(hw % 64 == 0 && hw <= 4096, "VAE attention: tokens per image must be a multiple of 64, <= 4096");
+    Act out = new_act(n, h, w, C);
+    const size_t mark = arena.off;
+    Act g = new_act(n, h, w, C);
+    gn(x, nullptr, a.gn_g, a.gn_b, 1e-6f, false, g);
+    Act q = new_act(n, h, w, C), k = new_act(n, h, w, C), o = new_act(n, h, w, C);
+    gemm({seg_1x1(g)}, a.q, q);
+    gemm({seg_1x1(g)}, a.k, k);
+    float* S = new_f32((size_t)hw * hw);
+    Act P = new_act(1, h, w, hw);       // [hw tokens, hw keys] bf16
+    Act VT = new_act(1, C / 64, 64, hw);  // [C rows, hw] bf16
+    Act wv;                             // W_v [C, C] viewed as an "image" of C pixels with C channels
+    wv.n = 1; wv.h = C / 64; wv.w = 64; wv.c = C; wv.p = a.v.w;
+    for (int i = 0; i < n; ++i) {
+      Act qi = q, oi = o;
+      qi.n = oi.n = 1;
+      qi.p = q.p + (size_t)i * hw * C;
+      oi.p = o.p + (size_t)i * hw * C;
+      {  // S = Q_i K_i^T, fp32 row-major
+        mvldm_gemm_desc d{};
+        d.nseg = 1; d.seg[0] = seg_1x1(qi);
+        d.n_img = 1; d.oh = h; d.ow = w;
+        d.w = k.p + (size_t)i * hw * C; d.n = hw; d.k = C;
+        d.mode = 4; d.out = S; d.ldo = hw; d.n_valid = hw;
+        run_gemm(d);
+      }
+      if (!dry) {
+        Step st;
+        st.kind = Step::SOFTMAX;
+        st.x0 = S; st.n_img = hw; st.c0 = hw; st.eps = 1.f / sqrtf((float)C); st.dst = P.p;
+        st.meta = OpMeta{"softmax", "rows" + std::to_string(hw), 0.0, 6.0 * (double)hw * hw};
+        push_step(st);
+      }
+      {  // V^T = W_v g_i^T   ([C, hw]; b_v is added after P V)
+        mvldm_gemm_desc d{};
+        d.nseg = 1; d.seg[0] = seg_1x1(wv);
+        d.n_img = 1; d.oh = wv.h; d.ow = wv.w;
+        d.w = g.p + (size_t)i * hw * C; d.n = hw; d.k = C;
+        d.mode = 0; d.out = VT.p; d.ldo = hw; d.n_valid = hw;
+        run_gemm(d);
+      }
+      {  // O_i = P V + b_v
+        mvldm_gemm_desc d{};
+        d.nseg = 1; d.seg[0] = seg_1x1(P);
+        d.n_img = 1; d.oh = h; d.ow = w;
+        d.w = VT.p; d.n = C; d.k = hw;
+        d.bias = a.v.bias;
+        d.mode = 0; d.out = oi.p; d.ldo = C; d.n_valid = C;
+        run_gemm(d);
+      }
+    }
+    gemm({seg_1x1(o)}, a.out, out, nullptr, 0, &x);
+    if (!taps_enabled) arena.off = mark;
+    return out;
+  }
+  // AutoencoderKL.decode(z).sample  (diffusion_wrapper.py:293-295; z already divided by the scaling factor by the caller)
+  void run_vae_decode(const float* z, int n, int Hh, int Ww, float* image) {
+    const int L = cfg.num_levels;
+    arena.off = 0;
+    const int kpad = vae_dec.conv_in.k;
+    Act col = new_act(n, Hh, Ww, kpad);
+    im2col_step(z, n, cfg.latent_channels, Hh, Ww, kpad, vae_premix, col);
+    Act x = new_act(n, Hh, Ww, vae_dec.conv_in.n);
+    gemm({seg_1x1(col)}, vae_dec.conv_in, x);
+    tap("decoder.conv_in", x);
+    x = resnet(vae_dec.mid0, x, nullptr, nullptr);
+    x = vae_attention(vae_dec.attn, x);
+    x = resnet(vae_dec.mid1, x, nullptr, nullptr);
+    tap("decoder.mid", x);
+    for (int l = 0; l < L; ++l) {
+      for (auto& r : vae_dec.blocks[l]) x = resnet(r, x, nullptr, nullptr);
+      if (l != L - 1) {
+        Act u = upsample2x(x);
+        Act y = new_act(n, u.h, u.w, u.c);
+        gemm({seg_conv3x3(u)}, vae_dec.resample[l], y);
+        x = y;
+      }
+      tap("decoder.up" + std::to_string(l), x);
+    }
+    nchw_head(x, vae_dec.norm_g, vae_dec.norm_b, 1e-6f, vae_dec.conv_out, cfg.out_channels, image);
+  }
+  // AutoencoderKL.encode(x).latent_dist.parameters: [n, 2*latent, H/f, W/f] = (mean | logvar)  (diffusion_wrapper.py:283)
+  void run_vae_encode(const float* image, int n, int Hh, int Ww, float* moments) {
+    const int L = cfg.num_levels;
+    arena.off = 0;
+    const int kpad = vae_enc.conv_in.k;
+    Act col = new_act(n, Hh, Ww, kpad);
+    im2col_step(image, n, cfg.in_channels, Hh, Ww, kpad, nullptr, col);
+    Act x = new_act(n, Hh, Ww, vae_enc.conv_in.n);
+    gemm({seg_1x1(col)}, vae_enc.conv_in, x);
+    tap("encoder.conv_in", x);
+    for (int l = 0; l < L; ++l) {
+      for (auto& r : vae_enc.blocks[l]) x = resnet(r, x, nullptr, nullptr);
+      if (l != L - 1) {
+        // Downsample2D(padding=0): F.pad(x, (0, 1, 0, 1)) then conv3x3 stride 2 -> taps at +0, +1, +2 from (2y, 2x); the
+        // pad row / column is the TMA's out-of-bounds zero fill
+        Act y = new_act(n, x.h / 2, x.w / 2, x.c);
+        mvldm_aseg sg = seg_conv3x3(x, 2);
+        for (int t = 0; t < 9; ++t) {
+          sg.dh[t] = (int8_t)(t / 3);
+          sg.dw[t] = (int8_t)(t % 3);
+        }
+        gemm({sg}, vae_enc.resample[l], y);
+        x = y;
+      }
+      tap("encoder.down" + std::to_string(l), x);
+    }
+    x = resnet(vae_enc.mid0, x, nullptr, nullptr);
+    x = vae_attention(vae_enc.attn, x);
+    x = resnet(vae_enc.mid1, x, nullptr, nullptr);
+    tap("encoder.mid", x);
+    nchw_head(x, vae_enc.norm_g, vae_enc.norm_b, 1e-6f, vae_enc.conv_out, 2 * cfg.latent_channels, moments);
+  }
+
   std::vector<int> scene_views;  // of the forward being recorded / run
   static int total_views(const std::vector<int>& sv) {
     int n = 0;
@@ -977,10 +1335,25 @@ struct mvldm_handle_s {
     run_gemm(d, 2.0 * (double)x.tokens() * cfg.out_channels * conv_out.k);
   }
 
+  // bytes of the fp32 NCHW tensor a program reads (in) / writes (out) for n images of H x W input pixels
+  size_t io_bytes(int n, int H, int W, bool in) const {
+    const int f = 1 << (cfg.num_levels - 1);
+    size_t per = 0;
+    if (program == 0) per = (size_t)(in ? cfg.in_channels : cfg.out_channels) * H * W;
+    else if (program == 1) per = in ? (size_t)cfg.latent_channels * H * W : (size_t)cfg.out_channels * H * f * W * f;
+    else per = in ? (size_t)cfg.in_channels * H * W : (size_t)2 * cfg.latent_channels * (H / f) * (W / f);
+    return (size_t)n * per * sizeof(float);
+  }
+  void run_program(const float* in, const int64_t* tsteps, const std::vector<int>& sv, int H, int W, float* out) {
+    if (program == 0) run(in, tsteps, sv, H, W, out);
+    else if (program == 1) run_vae_decode(in, total_views(sv), H, W, out);
+    else run_vae_encode(in, total_views(sv), H, W, out);
+  }
+
   // ---- plans: measured, allocated and recorded once per batch shape; a small LRU keeps the device memory bounded ----
   static constexpr size_t kMaxPlans = 6;
   Plan& plan_for(const std::vector<int>& sv, int H, int W, bool shard = false) {
-    std::vector<int> key{H, W, taps_enabled ? 1 : 0, shard ? v_total : 0};
+    std::vector<int> key{H, W, taps_enabled ? 1 : 0, shard ? v_total : 0, program};
     if (shard) {  // the recorded launch list holds the caller's exchange buffers
       const uint64_t a = reinterpret_cast<uint64_t>(kv_send), b = reinterpret_cast<uint64_t>(kv_recv);
       for (uint64_t v : {a, b}) {
@@ -1014,14 +1387,14 @@ struct mvldm_handle_s {
     arena = Arena();
     arena.measuring = true;
     splitk_need = 0;
-    run(nullptr, nullptr, sv, H, W, nullptr);
+    run_program(nullptr, nullptr, sv, H, W, nullptr);
     p->arena_bytes = arena.peak;
     p->arena_mem.alloc(p->arena_bytes);
     p->splitk.alloc(splitk_need);
     if (splitk_need) MV_CUDA(cudaMemset(p->splitk.p, 0, splitk_need));  // fused split-K counters start (and end) at zero
-    p->in_latents.alloc((size_t)n * cfg.in_channels * H * W * sizeof(float));
+    p->in_latents.alloc(io_bytes(n, H, W, true));
     p->in_t.alloc((size_t)n * sizeof(int64_t));
-    p->out_eps.alloc((size_t)n * cfg.out_channels * H * W * sizeof(float));
+    p->out_eps.alloc(io_bytes(n, H, W, false));
     // pass 2: record the launch list against the real buffers
     dry = false;
     arena = Arena();
@@ -1032,7 +1405,7 @@ struct mvldm_handle_s {
     splitk_bytes = p->splitk.bytes;
     rec = p.get();
     try {
-      run((const float*)p->in_latents.p, (const int64_t*)p->in_t.p, sv, H, W, (float*)p->out_eps.p);
+      run_program((const float*)p->in_latents.p, (const int64_t*)p->in_t.p, sv, H, W, (float*)p->out_eps.p);
     } catch (...) {
       rec = nullptr;
       sharded = false;
@@ -1116,7 +1489,10 @@ struct mvldm_handle_s {
           upsample_nearest2x(s, (const bf16*)st.x0, st.n_img, st.h, st.w, st.c0, (bf16*)st.dst);
           break;
         case Step::IM2COL:
-          im2col_input(s, (const float*)st.x0, st.n_img, st.c0, st.h, st.w, st.aux, (bf16*)st.dst);
+          im2col_input(s, (const float*)st.x0, st.n_img, st.c0, st.h, st.w, st.aux, (bf16*)st.dst, st.gamma);
+          break;
+        case Step::SOFTMAX:
+          softmax_rows(s, (const float*)st.x0, st.n_img, st.c0, st.eps, (bf16*)st.dst);
           break;
         case Step::SINUSOID:
           timestep_sinusoid_bf16(s, (const int64_t*)st.x0, st.n_img, st.c0, (bf16*)st.dst);
@@ -1127,21 +1503,23 @@ struct mvldm_handle_s {
   }
 
   void forward(cudaStream_t s, const float* latents, const int64_t* tsteps, const std::vector<int>& sv, int H, int W,
-               float* out) {
+               float* out, int prog = 0) {
     MV_CHECK(finalized, "mvldm_forward before mvldm_finalize_weights");
     MV_CHECK(!sv.empty(), "empty batch");
     for (int v : sv) MV_CHECK(v > 0, "empty scene");
+    MV_CHECK((cfg.model == MVLDM_MODEL_VAE) == (prog != 0), "entry point does not match the handle's model (denoiser / VAE)");
     const int n = total_views(sv);
     const int down = 1 << (cfg.num_levels - 1);
-    MV_CHECK(H % down == 0 && W % down == 0, "latent size must be divisible by 2^(levels-1)");
+    if (prog != 1) MV_CHECK(H % down == 0 && W % down == 0, "input size must be divisible by 2^(levels-1)");
     stream = s;
+    program = prog;
     Plan& p = plan_for(sv, H, W);
     last_plan = &p;
-    const size_t in_bytes = (size_t)n * cfg.in_channels * H * W * sizeof(float);
-    const size_t out_bytes = (size_t)n * cfg.out_channels * H * W * sizeof(float);
+    const size_t in_bytes = io_bytes(n, H, W, true);
+    const size_t out_bytes = io_bytes(n, H, W, false);
     // the recorded launches read and write fixed buffers, so the list (and its graph) is valid for any caller tensors
     MV_CUDA(cudaMemcpyAsync(p.in_latents.p, latents, in_bytes, cudaMemcpyDeviceToDevice, s));
-    MV_CUDA(cudaMemcpyAsync(p.in_t.p, tsteps, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    if (tsteps) MV_CUDA(cudaMemcpyAsync(p.in_t.p, tsteps, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
     const bool graph = cfg.use_cuda_graph && !taps_enabled && !profiling;
     cudaStreamCaptureStatus cst;
     MV_CUDA(cudaStreamIsCapturing(s, &cst));
@@ -1277,7 +1655,17 @@ int mvldm_create(const mvldm_config* cfg, int device, mvldm_handle* out) {
     MV_CHECK((cfg->mv_d_mlp > 0) != (cfg->mv_d_mlp_multiplier > 0),
              "standard transformer: exactly one of d_mlp and d_mlp_multiplier (standard/transformer.py:63-64)");
   }
-  h->build_registry();
+  MV_CHECK(cfg->model == MVLDM_MODEL_DENOISER || cfg->model == MVLDM_MODEL_VAE, "model must be MVLDM_MODEL_DENOISER or _VAE");
+  if (cfg->model == MVLDM_MODEL_VAE) {
+    MV_CHECK(cfg->latent_channels >= 1 && cfg->latent_channels <= 8, "VAE: latent_channels must be in [1, 8]");
+    MV_CHECK(cfg->out_channels >= 1 && cfg->out_channels <= 32 && cfg->in_channels >= 1 && cfg->in_channels <= 7,
+             "VAE: image channels out of range");
+    MV_CHECK(cfg->layers_per_block >= 1, "VAE: layers_per_block must be >= 1");
+    MV_CHECK(cfg->impl == MVLDM_IMPL_TC, "VAE: the tcgen05 kernels only");
+    h->build_vae_registry();
+  } else {
+    h->build_registry();
+  }
   *out = h.release();
   MV_API_END
 }
@@ -1333,7 +1721,8 @@ int mvldm_finalize_weights(mvldm_handle h, void* stream) {
   MV_API_BEGIN
   MV_CHECK(h, "null handle");
   MV_CUDA(cudaSetDevice(h->device));
-  h->finalize((cudaStream_t)stream);
+  if (h->cfg.model == MVLDM_MODEL_VAE) h->finalize_vae((cudaStream_t)stream);
+  else h->finalize((cudaStream_t)stream);
   MV_API_END
 }
 
@@ -1379,6 +1768,7 @@ int mvldm_forward_sharded(mvldm_handle h, void* stream, const float* latents, co
   MV_CHECK(V_local > 0 && V_total % V_local == 0, "V_total must be a multiple of V_local (equal view groups)");
   MV_CHECK(group_index >= 0 && group_index < V_total / V_local, "group_index out of range");
   h->group_index = group_index;
+  h->program = 0;
   MV_CUDA(cudaSetDevice(h->device));
   h->stream = (cudaStream_t)stream;
   h->v_total = V_total;
@@ -1399,6 +1789,22 @@ int mvldm_forward_sharded(mvldm_handle h, void* stream, const float* latents, co
   MV_CUDA(cudaMemcpyAsync(out, p.out_eps.p, (size_t)V_local * h->cfg.out_channels * H * W * sizeof(float),
                           cudaMemcpyDeviceToDevice, s));
   h->last_launches = p.launches;
+  MV_API_END
+}
+
+int mvldm_vae_decode(mvldm_handle h, void* stream, const float* latents, int n, int H, int W, float* image) {
+  MV_API_BEGIN
+  MV_CHECK(h && latents && image && n > 0 && H > 0 && W > 0, "bad argument");
+  MV_CUDA(cudaSetDevice(h->device));
+  h->forward((cudaStream_t)stream, latents, nullptr, std::vector<int>(1, n), H, W, image, 1);
+  MV_API_END
+}
+
+int mvldm_vae_encode(mvldm_handle h, void* stream, const float* image, int n, int H, int W, float* moments) {
+  MV_API_BEGIN
+  MV_CHECK(h && image && moments && n > 0 && H > 0 && W > 0, "bad argument");
+  MV_CUDA(cudaSetDevice(h->device));
+  h->forward((cudaStream_t)stream, image, nullptr, std::vector<int>(1, n), H, W, moments, 2);
   MV_API_END
 }
 

@@ -67,8 +67,11 @@ __device__ __forceinline__ float block_sum(float v, float* red /* >= 33 floats *
 // conv_in operand: explicit im2col of the fp32 NCHW denoiser input (K1 + K3 of SURVEY.md §2.2).
 // out[m, tap*cin + c] = latents[img, c, y+r-1, x+s-1] (zero outside / for k >= 9*cin), m = (img, y, x)
 // ---------------------------------------------------------------------------------------------
+// `premix` (optional, fp32 [cin*cin + cin]): a 1x1 convolution y = W x + b applied to every pixel before the 3x3 gather (the VAE's
+// post_quant_conv in front of decoder.conv_in: its bias must not leak into the zero padding, so it cannot be folded into the
+// 3x3 weights)
 __global__ void im2col_input_kernel(const float* __restrict__ x, int n_img, int cin, int h, int w, int kpad,
-                                    bf16* __restrict__ out) {
+                                    const float* __restrict__ premix, bf16* __restrict__ out) {
   pdl_wait();
   pdl_launch_dependents();
   const int kv = kpad / 8;  // one thread = eight consecutive k of one output pixel = one 16-byte store
@@ -84,10 +87,54 @@ __global__ void im2col_input_kernel(const float* __restrict__ x, int n_img, int 
       if (k < 9 * cin) {
         const int tap = k / cin, c = k - tap * cin;
         const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
-        if (yy >= 0 && yy < h && xx >= 0 && xx < w) v[j] = x[((img * cin + c) * h + yy) * w + xx];
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+          if (premix) {
+            float a = premix[cin * cin + c];
+            for (int e = 0; e < cin; ++e) a = fmaf(premix[c * cin + e], x[((img * cin + e) * h + yy) * w + xx], a);
+            v[j] = a;
+          } else {
+            v[j] = x[((img * cin + c) * h + yy) * w + xx];
+          }
+        }
       }
     }
     store8(out + (int64_t)i * 8, v);
+  }
+}
+
+// out[r, :] = softmax(scale * in[r, :]) for `rows` rows of `cols` fp32 scores -> bf16 (one warp per row, the row in registers;
+// fp32 max / sum like diffusers' upcast_softmax): the VAE's single-head 512-wide mid-block attention runs as plain GEMMs
+template <int PER_LANE>
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ in, int64_t rows, int cols, float scale,
+                                                           bf16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* src = in + row * cols;
+  float v[PER_LANE];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < PER_LANE; ++j) {
+    const int c = j * 32 + lane;
+    v[j] = c < cols ? src[c] * scale : -INFINITY;
+    mx = fmaxf(mx, v[j]);
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < PER_LANE; ++j) {
+    v[j] = __expf(v[j] - mx);
+    sum += v[j];
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.f / sum;
+  bf16* dst = out + row * cols;
+#pragma unroll
+  for (int j = 0; j < PER_LANE; ++j) {
+    const int c = j * 32 + lane;
+    if (c < cols) dst[c] = __float2bfloat16(v[j] * inv);
   }
 }
 
@@ -724,11 +771,20 @@ inline int grid_for(int64_t total, int threads) {
 
 }  // namespace
 
-void im2col_input(cudaStream_t s, const float* latents, int n_img, int cin, int h, int w, int kpad, bf16* out) {
+void softmax_rows(cudaStream_t s, const float* in, int64_t rows, int cols, float scale, bf16* out) {
+  MV_CHECK(cols >= 1 && cols <= 4096, "softmax_rows: 1..4096 columns");
+  const dim3 grid((unsigned)ceil_div64(rows, 8)), block(256);
+  if (cols <= 256) launch_pdl(softmax_rows_kernel<8>, grid, block, 0, s, in, rows, cols, scale, out);
+  else if (cols <= 1024) launch_pdl(softmax_rows_kernel<32>, grid, block, 0, s, in, rows, cols, scale, out);
+  else launch_pdl(softmax_rows_kernel<128>, grid, block, 0, s, in, rows, cols, scale, out);
+}
+
+void im2col_input(cudaStream_t s, const float* latents, int n_img, int cin, int h, int w, int kpad, bf16* out,
+                  const float* premix) {
   MV_CHECK(kpad >= 9 * cin, "im2col: kpad too small");
   MV_CHECK(kpad % 8 == 0 && (int64_t)n_img * h * w * kpad < (1ll << 31), "im2col: kpad must be a multiple of 8 (32-bit indexing)");
   const int64_t total = (int64_t)n_img * h * w * (kpad / 8);
-  launch_pdl(im2col_input_kernel, dim3(grid_for(total, 128)), dim3(128), 0, s, latents, n_img, cin, h, w, kpad, out);
+  launch_pdl(im2col_input_kernel, dim3(grid_for(total, 128)), dim3(128), 0, s, latents, n_img, cin, h, w, kpad, premix, out);
 }
 
 // timestep embedding in bf16: the A operand of the time_embedding GEMMs (what autocast feeds linear_1 in the reference)

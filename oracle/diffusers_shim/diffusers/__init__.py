@@ -307,5 +307,4 @@ class DDPMScheduler:
     pass
 
 
-class AutoencoderKL:
-    pass
+from .vae import AutoencoderKL  # noqa: E402,F401  (restated diffusers AutoencoderKL: see vae.py's header - parity unpinned)

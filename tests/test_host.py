@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     import ctypes
-    assert ctypes.sizeof(_lib.Config) == 4 * (3 + 4 + 6 + 1 + 4 + 1 + 4)
+    assert ctypes.sizeof(_lib.Config) == 4 * (3 + 4 + 6 + 1 + 4 + 1 + 4 + 2)
     assert ctypes.sizeof(_lib.ASeg) == 8 + 6 * 4 + 9 + 9 + 2 + 9 * 4      # ptr, 6 ints, 2x9 int8 (+2 pad), 9 ints
     assert _lib.GemmDesc.seg.offset == 8 and ctypes.sizeof(_lib.GemmDesc) % 8 == 0
 
@@ -85,6 +85,36 @@ def test_standard_transformer_state_dict_keys_match_reference_module():
             setattr(cfg.multi_view_attention, k, v)                 # d_mlp AND d_mlp_multiplier both set: the reference asserts
         with pytest.raises(ValueError):
             mv.MultiViewUNet(cfg, 11, 4)
+
+
+def test_vae_module_matches_the_diffusers_layout():
+    """AutoencoderKL drop-in (reference src/model/autoencoder/__init__.py:15-43): same state-dict keys / shapes as the
+    restated diffusers module (oracle/diffusers_shim/diffusers/vae.py) for the SD-2.1 VAE and for kl.yaml's default config,
+    83.65 M parameters for the SD VAE, strict loading incl. the pre-0.15 attention names, registry + factory."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "diffusers_shim"))
+    from diffusers.vae import AutoencoderKL as RefVAE
+    ref = RefVAE.from_pretrained("stabilityai/stable-diffusion-2-1", subfolder="vae")
+    ours = mv.get_autoencoder(mv.AutoencoderCfg("kl", "stabilityai/stable-diffusion-2-1", mv.AutoencoderKLCfg()))
+    sd = ref.state_dict()
+    assert set(sd) == set(ours.state_dict()) and len(sd) == 248
+    assert all(tuple(sd[k].shape) == tuple(ours.state_dict()[k].shape) for k in sd)
+    assert sum(p.numel() for p in ours.parameters()) == 83653863
+    assert not ours.load_state_dict(sd, strict=True).missing_keys
+    old = {}
+    for k, v in sd.items():                 # a checkpoint written before diffusers 0.15: query/key/value/proj_attn/norm, 1x1 convs
+        for new, dep in (("to_q", "query"), ("to_k", "key"), ("to_v", "value"), ("to_out.0", "proj_attn"), ("group_norm", "norm")):
+            if f".attentions.0.{new}." in k:
+                k = k.replace(f".attentions.0.{new}.", f".attentions.0.{dep}.")
+                v = v[:, :, None, None] if (v.dim() == 2) else v
+        old[k] = v
+    assert set(old) != set(sd)
+    res = ours.load_state_dict(old, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(ours.state_dict()["decoder.mid_block.attentions.0.to_q.weight"], sd["decoder.mid_block.attentions.0.to_q.weight"])
+    small = mv.get_autoencoder(mv.AutoencoderCfg("kl", None, mv.AutoencoderKLCfg()))          # kl.yaml defaults: one 64-wide block
+    assert set(small.state_dict()) == set(RefVAE().state_dict())
+    assert small.config.scaling_factor == 0.18215 and "kl" in mv.AUTOENCODERS
 
 
 def test_unsupported_configs_raise():
