@@ -162,7 +162,7 @@ __global__ void sinusoid_kernel(const int64_t* __restrict__ t, int n, int dim, O
 // The two sources implement GroupNorm over torch.cat((hidden, skip), dim=1) without materialising the cat.
 // ---------------------------------------------------------------------------------------------
 constexpr int GN_MAXC = 2560;
-constexpr int GN_MAXP = 64;
+constexpr int GN_MAXP = 256;
 
 __global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict__ x0, int c0, const bf16* __restrict__ x1,
                                                          int c1, int hw, int groups, int pix, float* __restrict__ partials) {
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
   __syncthreads();
   const int64_t per_img = (int64_t)hw * cv;
   const int64_t lo = per_img * blockIdx.x / gridDim.x, hi = per_img * (blockIdx.x + 1) / gridDim.x;
-#pragma unroll 2
+#pragma unroll 4
   for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const int c = (int)(i % cv) * 8;
     const int64_t pixel = (int64_t)img * hw + i / cv;
@@ -915,6 +915,9 @@ void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, i
         cs *= 2;
       const size_t slab_cs = slab / cs;
       const int cache_cs = slab_cs <= 160 * 1024 ? 1 : 0;
+      // a slab that does not fit shared memory would be streamed twice with 16-byte accesses at a pitch of C channels (half of
+      // every sector wasted): large images (the VAE's 128x128 / 256x256 feature maps) take the coalesced two-launch path below
+      if (cache_cs) {
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3((C / cb) * cs, n_img, 1);
       cfg.blockDim = dim3(GNB_THREADS, 1, 1);
@@ -941,11 +944,13 @@ void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, i
       MV_LAUNCHED();
       (void)cache;
       return;
+      }
     }
   }
-  // ---- two-launch path (no cluster support / odd sizes) ----
+  // ---- two-launch path (large images / odd sizes) ----
   int P = 1;
-  while (P < GN_MAXP && n_img * P < 592 && hw % (2 * P) == 0 && hw / (2 * P) >= 4) P *= 2;
+  // enough CTAs to fill the machine several times over, at least 256 pixels each for the big tensors
+  while (P < GN_MAXP && n_img * P < 2368 && hw % (2 * P) == 0 && hw / (2 * P) >= (hw >= 4096 ? 256 : 4)) P *= 2;
   launch_pdl(gn_partial_kernel, dim3(P, n_img), dim3(256), 0, s, x0, c0, x1, c1, hw, groups, hw / P, scratch);
   launch_pdl(gn_apply_kernel, dim3(P, n_img), dim3(256), 0, s, x0, c0, x1, c1, hw, groups, eps, P, (const float*)scratch,
              gamma, beta, silu ? 1 : 0, out);

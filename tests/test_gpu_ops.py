@@ -222,7 +222,13 @@ def test_gemm_rejects_unsupported_shapes():
                                                  (8, 1280, 1280, 16, 1, 1e-5), (3, 640, 0, 1024, 0, 1e-6),
                                                  (8, 320, 320, 1024, 1, 1e-5), (2, 1280, 0, 1024, 1, 1e-5),
                                                  (3, 1280, 1280, 64, 1, 1e-5), (5, 320, 0, 256, 1, 1e-5),
-                                                 (1, 640, 0, 64, 1, 1e-5), (7, 1280, 0, 16, 0, 1e-5)])
+                                                 (1, 640, 0, 64, 1, 1e-5), (7, 1280, 0, 16, 0, 1e-5),
+                                                 # the VAE's tensors: 4 / 8 / 16-wide groups, up to 256 x 256 pixels
+                                                 (2, 128, 0, 65536, 1, 1e-6), (2, 256, 0, 16384, 1, 1e-6),
+                                                 (3, 512, 0, 4096, 1, 1e-6), (2, 512, 0, 1024, 0, 1e-6), (1, 64, 0, 1024, 1, 1e-6),
+                                                 # widths that do not divide 128: 24 x 24, 12 x 12, 6 x 6, 3 x 3 pixels
+                                                 (3, 320, 0, 576, 1, 1e-5), (3, 640, 320, 144, 1, 1e-5), (2, 1280, 0, 36, 1, 1e-5),
+                                                 (2, 1280, 1280, 9, 1, 1e-5)])
 def test_groupnorm(n, c0, c1, hw, silu, eps):
     torch.manual_seed(4)
     lib = _lib.load()

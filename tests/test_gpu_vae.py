@@ -107,3 +107,28 @@ def test_vae_rejects_what_it_does_not_implement():
         ours.encode(torch.zeros(1, 3, 31, 31, device="cuda"))
     with pytest.raises(RuntimeError):
         ours.decode(torch.zeros(1, 4, 4, 4, device="cuda"))            # 16 tokens in the mid attention: below the 64-token tile
+
+
+def test_anchored_sampling_with_vae_hand_over(gpu_models):
+    """BASELINE config 3 with the reference's image-space hand-over: anchors are decoded, clipped to [0,1] and re-encoded
+    before they condition the chunk calls (diffusion_wrapper.py:722,779 + first/last_stage)."""
+    ref, vae = _pair(SD, seed=5)
+    m = gpu_models(0, True)
+    path = mv.DenoisingPath(m, mv.DDIMScheduler(clip_sample=False), use_cfg=False)
+    path.set_timesteps(3)
+    torch.manual_seed(6)
+    T = 10
+    ctx = torch.randn(1, 1, 4, 32, 32, device="cuda")
+    noise = torch.randn(1, T, 4, 32, 32, device="cuda")
+    extr = torch.eye(4, device="cuda").expand(1, T + 1, 4, 4).clone()
+    extr[0, :, 0, 3] = 0.1 * torch.arange(T + 1, device="cuda")
+    intr = torch.tensor([[1.2, 0, 0.5], [0, 1.2, 0.5], [0, 0, 1.0]], device="cuda").expand(1, T + 1, 3, 3).clone()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    lat_v, done_v, plan = mv.sample_anchored(path, ctx, extr[:, :1], intr[:, :1], extr[:, 1:], intr[:, 1:], noise,
+                                             autoencoder=vae, generator=g)
+    lat_l, done_l, _ = mv.sample_anchored(path, ctx, extr[:, :1], intr[:, :1], extr[:, 1:], intr[:, 1:], noise)
+    assert torch.equal(done_v, done_l) and torch.isfinite(lat_v).all()
+    A = plan.anchors
+    assert torch.equal(lat_v[:, A], lat_l[:, A])                         # phase 1 is the same call
+    rest = [t for _, c in plan.chunks for t in c]
+    assert rest and not torch.equal(lat_v[:, rest], lat_l[:, rest])      # phase 2 saw the round-tripped anchors

@@ -111,6 +111,7 @@ def main():
     for a, b in [("bench_n1.json", "bench_n1.json"), ("bench_cfg.json", "bench_cfg.json"),
                  ("bench_cfg_two_forwards.json", "bench_cfg_two_forwards.json"), ("bench_variant_b.json", "bench_variant_b.json"),
                  ("bench_8scenes.json", "bench_8scenes_per_gpu.json"), ("bench_reference.json", "bench_reference_cpu.json"),
+                 ("bench_standard.json", "bench_standard_transformer.json"), ("bench_vae.json", "bench_vae.json"),
                  ("clocks.csv", "clocks.csv"), ("scale_check.txt", "scale_check.txt"), ("prof_ops.txt", "ops_and_timelines.txt"),
                  ("gn_graph_bench.txt", "groupnorm_in_graph.txt"), ("gemm_sweep.txt", "gemm_config_sweep.txt"),
                  ("excess_v8.txt", "per_op_vs_floor.txt"), ("micro.txt", "micro_mufu_pdl.txt"), ("launches_cold.csv", "launches_cold.csv"),
@@ -135,7 +136,7 @@ def main():
     for rep, dst, what in [
             ("ncu_gemm_conv_l0.ncu-rep", "ncu_gemm_conv_l0.txt", "ncu --set full --clock-control none --import-source on -k regex:gemm_tc, "
              "tools/prof_gemm.py 8 320 320 32 (level-0 conv3x3 320->320 at 8 views: M=8192 N=320 K=2880, 128 tiles of 128x160)"),
-            ("ncu_attn_l0.ncu-rep", "ncu_attn_l0.txt", "ncu --set full --clock-control none --import-source on -k regex:attn64, "
+            ("ncu_attn_l0.ncu-rep", "ncu_attn_l0.txt", "ncu --set full --clock-control none --import-source on -k regex:attn64q, "
              "tools/prof_attn.py 1 8192 40 (joint attention of one scene: 8 views x 1024 tokens, 8 heads, d=40 padded to 64)"),
             ("ncu_gn_flat_l0.ncu-rep", "ncu_groupnorm_l0.txt", "ncu --set full --clock-control none --import-source on -k regex:gn_flat, "
              "tools/prof_gn.py 8 1024 320 0 (GroupNorm+SiLU of one level-0 tensor: 8 images x 1024 px x 320 ch)")]:
