@@ -162,7 +162,7 @@ __global__ void sinusoid_kernel(const int64_t* __restrict__ t, int n, int dim, O
 // The two sources implement GroupNorm over torch.cat((hidden, skip), dim=1) without materialising the cat.
 // ---------------------------------------------------------------------------------------------
 constexpr int GN_MAXC = 2560;
-constexpr int GN_MAXP = 256;
+constexpr int GN_MAXP = 64;
 
 __global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict__ x0, int c0, const bf16* __restrict__ x1,
                                                          int c1, int hw, int groups, int pix, float* __restrict__ partials) {
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
   __syncthreads();
   const int64_t per_img = (int64_t)hw * cv;
   const int64_t lo = per_img * blockIdx.x / gridDim.x, hi = per_img * (blockIdx.x + 1) / gridDim.x;
-#pragma unroll 4
+#pragma unroll 2
   for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const int c = (int)(i % cv) * 8;
     const int64_t pixel = (int64_t)img * hw + i / cv;
@@ -949,8 +949,7 @@ void groupnorm(cudaStream_t s, const bf16* x0, int c0, const bf16* x1, int c1, i
   }
   // ---- two-launch path (large images / odd sizes) ----
   int P = 1;
-  // enough CTAs to fill the machine several times over, at least 256 pixels each for the big tensors
-  while (P < GN_MAXP && n_img * P < 2368 && hw % (2 * P) == 0 && hw / (2 * P) >= (hw >= 4096 ? 256 : 4)) P *= 2;
+  while (P < GN_MAXP && n_img * P < 592 && hw % (2 * P) == 0 && hw / (2 * P) >= 4) P *= 2;
   launch_pdl(gn_partial_kernel, dim3(P, n_img), dim3(256), 0, s, x0, c0, x1, c1, hw, groups, hw / P, scratch);
   launch_pdl(gn_apply_kernel, dim3(P, n_img), dim3(256), 0, s, x0, c0, x1, c1, hw, groups, eps, P, (const float*)scratch,
              gamma, beta, silu ? 1 : 0, out);
