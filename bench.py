@@ -304,15 +304,18 @@ def run_view_sharded(args, m, rank, world, local, dev, barrier):
         assert torch.isfinite(y).all()
         return max_over_ranks(e0.elapsed_time(e1), world, dev) / n, ex
 
-    ms, ex = timed(True)
-    ms_exposed = timed(False)[0] if world > 1 else None
+    ms, ex = timed(False)                                   # the default: one pass over the gathered slabs
+    ms_overlap = timed(True)[0] if world > 1 else None      # all-gather on a side stream under the own-keys attention
+    ms_split = timed("split")[0] if world > 1 else None     # same three-way softmax split, collective on the compute stream
     return {"workload": f"one denoiser forward of 1 scene x {V} views, views split in contiguous groups over the ranks",
             "scaling": "strong", "views": V, "views_per_rank": b - a, "forwards_timed": n, "ms_per_forward": ms,
             "value": V / (ms * 1e-3), "unit": "views/s",
             "gflop_per_forward": forward_gflop(V, args.variant), "tflops": forward_gflop(V, args.variant) / ms,
-            "ms_per_forward_exchange_not_overlapped": ms_exposed,
-            "overlap": "all-gather on a side stream under the attention over the rank's own keys; three partial softmaxes "
-                       "(own / before / after slabs) merged in fixed order" if world > 1 else "n/a (one rank)",
+            "mode": "all-gather on the compute stream, one attention pass over all slabs in view order",
+            "ms_per_forward_overlapped": ms_overlap,
+            "ms_per_forward_split_not_overlapped": ms_split,
+            "overlapped_mode": "all-gather on a side stream under the attention over the rank's own keys; three partial softmaxes "
+                               "(own / before / after slabs) merged in fixed order" if world > 1 else "n/a (one rank)",
             "kv_exchanges_per_forward": ex.calls // n,
             "kv_bytes_sent_per_rank_per_forward": ex.bytes_sent // n,
             "kv_bytes_received_per_rank_per_forward": ex.bytes_sent // n * (world - 1),

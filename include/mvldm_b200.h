@@ -149,10 +149,14 @@ int mvldm_vae_encode(mvldm_handle h, void* stream, const float* image, int n, in
  *   5. runs the attention against the slabs in front of and behind its own and merges the (up to) three partial
  *      softmaxes in that fixed order (own, before, after): deterministic, and equal to the one-pass softmax up to
  *      the rounding of the merge.
- * A host without a side stream may do the whole exchange on `stream` in BEGIN and nothing in END.  Not graph-captured
+ * A host that does not overlap runs the whole exchange on `stream` inside BEGIN and returns MVLDM_EXCHANGE_DONE instead of 0:
+ * the library then makes ONE pass over all slabs in view order (no partial softmaxes, no END call).  Measured on NVLink 5
+ * (1 scene x 64 views, profiles/r02_final_bench_n{2,4,8}.json) the exchange is a few percent of the forward and the
+ * three-way split costs about what it hides, so the one-pass mode is the host's default.  Not graph-captured
  * (the callback re-enters the host).  kv_send must hold V_local*h*w*2*heads*64*2 bytes at the finest level, kv_recv
  * V_total/V_local times that. */
 enum { MVLDM_EXCHANGE_BEGIN = 0, MVLDM_EXCHANGE_END = 1 };
+enum { MVLDM_EXCHANGE_DONE = 2 };  /* return value of the BEGIN call: exchange already complete on `stream` */
 typedef int (*mvldm_kv_exchange_fn)(void* user, const void* kv_send, void* kv_recv, int64_t bytes_per_rank, void* stream,
                                     int phase);
 int mvldm_forward_sharded(mvldm_handle h, void* stream, const float* latents, const int64_t* timesteps, int V_local,

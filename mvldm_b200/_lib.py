@@ -79,7 +79,7 @@ SYMBOLS = {
     "mvldm_op_layernorm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
 }
 
-EXCHANGE_BEGIN, EXCHANGE_END = 0, 1
+EXCHANGE_BEGIN, EXCHANGE_END, EXCHANGE_DONE = 0, 1, 2
 KV_EXCHANGE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int)
 SYMBOLS["mvldm_forward_sharded"] = (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                             c_void_p, c_void_p, c_void_p, c_int64, KV_EXCHANGE_FN, c_void_p])

@@ -132,6 +132,9 @@ void raymap(cudaStream_t s, const float* extr, const float* intr, int n, int h, 
 // weight packing helpers (device side): dst bf16 [rows, ld]; all sources fp32
 void convert_f32(cudaStream_t s, const void* src, int dtype, int64_t n, float* dst);
 // dst[rowmap ? rowmap[r] : r, dst_col0 + j] = src[r, j]; rowmap is a device array of `rows` ints or NULL
+// pack-time fp32 helpers: C = A . B and y = A . x + add
+void matmul_f32(cudaStream_t s, const float* A, const float* B, float* C, int m, int n, int k);
+void matvec_bias(cudaStream_t s, const float* A, const float* x, const float* add, float* y, int m, int k);
 void pack_rows(cudaStream_t s, const float* src, int rows, int cols, int src_ld, bf16* dst, int dst_ld, int dst_col0,
                const int* rowmap);
 void pack_conv3x3(cudaStream_t s, const float* w, int cout, int cin, int ks, bf16* dst, int dst_ld, int dst_col0);

@@ -240,6 +240,40 @@ void pack_conv3x3(cudaStream_t s, const float* w, int cout, int cin, int ks, bf1
   MV_LAUNCHED();
 }
 
+// pack-time only: C[m, n] = A[m, k] . B[k, n] (+ bias_in[k] folded as C_bias[m] = A . bias_in + bias_add), plain fp32, row-major
+__global__ void matmul_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int m, int n,
+                                  int k) {
+  __shared__ float sa[16][17], sb[16][17];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < k; k0 += 16) {
+    sa[ty][tx] = (row < m && k0 + tx < k) ? A[(int64_t)row * k + k0 + tx] : 0.f;
+    sb[ty][tx] = (k0 + ty < k && col < n) ? B[(int64_t)(k0 + ty) * n + col] : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc = fmaf(sa[ty][j], sb[j][tx], acc);
+    __syncthreads();
+  }
+  if (row < m && col < n) C[(int64_t)row * n + col] = acc;
+}
+__global__ void matvec_bias_kernel(const float* __restrict__ A, const float* __restrict__ x, const float* __restrict__ add,
+                                   float* __restrict__ y, int m, int k) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= m) return;
+  float acc = add ? add[row] : 0.f;
+  for (int j = 0; j < k; ++j) acc = fmaf(A[(int64_t)row * k + j], x[j], acc);
+  y[row] = acc;
+}
+void matmul_f32(cudaStream_t s, const float* A, const float* B, float* C, int m, int n, int k) {
+  matmul_f32_kernel<<<dim3(ceil_div(n, 16), ceil_div(m, 16)), dim3(16, 16), 0, s>>>(A, B, C, m, n, k);
+  MV_LAUNCHED();
+}
+void matvec_bias(cudaStream_t s, const float* A, const float* x, const float* add, float* y, int m, int k) {
+  matvec_bias_kernel<<<ceil_div(m, 128), 128, 0, s>>>(A, x, add, y, m, k);
+  MV_LAUNCHED();
+}
+
 void fill_zero(cudaStream_t s, void* p, size_t bytes) { MV_CUDA(cudaMemsetAsync(p, 0, bytes, s)); }
 
 }  // namespace mvldm

@@ -556,7 +556,22 @@ struct mvldm_handle_s {
       MV_CUDA(cudaMemcpyAsync(m.ff1.bias, pb.data(), pb.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
       MV_CUDA(cudaStreamSynchronize(stream));
     }
-    m.ff2 = pack_linear(tb + ".ff.net.2", m.c, c4, true);
+    // ff.net.2 and proj_out are both linear with nothing in between:  proj_out(t3 + W2 f + b2) = (Wp W2) f + Wp t3 + (Wp b2 + bp).
+    // ONE GEMM over the K-segments [f (4C) | t3 (C)] with the pre-multiplied matrix - same FLOPs as the two it replaces, one
+    // launch and one bf16 round trip of the [tokens, C] intermediate less per block
+    {
+      const float* wp = rawf(m.key + ".proj_out.weight");   // [C, C] (1x1 conv or Linear: same layout)
+      const float* w2 = rawf(tb + ".ff.net.2.weight");      // [C, 4C]
+      float* prod = store<float>((size_t)m.c * c4);
+      matmul_f32(stream, wp, w2, prod, m.c, c4, m.c);
+      m.ff2.n = m.c;
+      m.ff2.k = c4 + m.c;
+      m.ff2.w = store<bf16>((size_t)m.ff2.n * m.ff2.k);
+      pack_rows(stream, prod, m.c, c4, c4, m.ff2.w, m.ff2.k, 0, nullptr);
+      pack_rows(stream, wp, m.c, m.c, m.c, m.ff2.w, m.ff2.k, c4, nullptr);
+      m.ff2.bias = store<float>(m.c);
+      matvec_bias(stream, wp, rawf(tb + ".ff.net.2.bias"), rawf(m.key + ".proj_out.bias"), m.ff2.bias, m.c, m.c);
+    }
   }
 
   void finalize(cudaStream_t s) {
@@ -845,9 +860,7 @@ struct mvldm_handle_s {
     ln(t3, m.ln_g[2], m.ln_b[2], nrm);
     Act f = new_act(n, h, w, 4 * C);
     gemm({seg_1x1(nrm)}, m.ff1, f, nullptr, 0, nullptr, 1);
-    Act t4 = new_act(n, h, w, C);
-    gemm({seg_1x1(f)}, m.ff2, t4, nullptr, 0, &t3);
-    gemm({seg_1x1(t4)}, m.proj_out, out, nullptr, 0, &x);
+    gemm({seg_1x1(f), seg_1x1(t3)}, m.ff2, out, nullptr, 0, &x);  // ff.net.2 + residual + proj_out + residual (see pack_mv)
     if (!taps_enabled) arena.off = mark;
     return out;
   }
@@ -873,9 +886,7 @@ struct mvldm_handle_s {
     ln(t3, m.ln_g[2], m.ln_b[2], nrm);
     Act f = new_act(n, h, w, 4 * C);
     gemm({seg_1x1(nrm)}, m.ff1, f, nullptr, 0, nullptr, 1);
-    Act t4 = new_act(n, h, w, C);
-    gemm({seg_1x1(f)}, m.ff2, t4, nullptr, 0, &t3);
-    gemm({seg_1x1(t4)}, m.proj_out, out, nullptr, 0, &x);
+    gemm({seg_1x1(f), seg_1x1(t3)}, m.ff2, out, nullptr, 0, &x);  // ff.net.2 + residual + proj_out + residual (see pack_mv)
     if (!taps_enabled) arena.off = mark;
     return out;
   }
@@ -1444,9 +1455,15 @@ struct mvldm_handle_s {
           MV_CUDA(cudaMemcpy2DAsync(kv_send, (size_t)2 * hd * sizeof(bf16), st.qkv + hd, (size_t)3 * hd * sizeof(bf16),
                                     (size_t)2 * hd * sizeof(bf16), st.seq_local, cudaMemcpyDeviceToDevice, s));
           int rc = exchange(exchange_user, kv_send, kv_recv, (int64_t)bytes, s, MVLDM_EXCHANGE_BEGIN);
-          MV_CHECK(rc == 0, "mvldm_forward_sharded: K/V exchange callback failed");
+          MV_CHECK(rc == 0 || rc == MVLDM_EXCHANGE_DONE, "mvldm_forward_sharded: K/V exchange callback failed");
           const bf16* own = reinterpret_cast<const bf16*>(kv_send);
           const bf16* all = reinterpret_cast<const bf16*>(kv_recv);
+          if (rc == MVLDM_EXCHANGE_DONE && world > 1) {
+            // the host ran the whole exchange on `s`: nothing to overlap, one pass over all slabs in view order (the same
+            // softmax order on every rank, and the one a single GPU would use)
+            attention_tc_kv(s, st.qkv, 3 * hd, 0, all, 2 * hd, 0, hd, st.out, 1, st.seq_local, st.seq, st.heads, st.d, st.dpad);
+            break;
+          }
           if (world == 1) {
             attention_tc_kv(s, st.qkv, 3 * hd, 0, own, 2 * hd, 0, hd, st.out, 1, st.seq_local, st.seq_local, st.heads, st.d,
                             st.dpad);

@@ -48,12 +48,16 @@ def view_slice(num_views: int, rank: int, world_size: int) -> Tuple[int, int]:
 class ViewGroupExchange:
     """Owns the K|V send / receive buffers and the callback the library invokes around every joint attention.
 
-    Two-phase protocol (include/mvldm_b200.h, MVLDM_EXCHANGE_BEGIN / _END): BEGIN starts the all-gather on a side stream
-    (ordered after the K|V pack on the compute stream) and returns; the library then runs the attention over this rank's
-    own keys; END makes the compute stream wait for the gathered slabs.  ``overlap=False`` runs the collective on the
-    compute stream inside BEGIN (the transfer is then fully exposed; kept for measurement)."""
+    ``overlap=False`` (default): the all-gather runs on the compute stream inside BEGIN and the callback answers
+    MVLDM_EXCHANGE_DONE; the library makes one pass over all slabs in view order.
+    ``overlap=True``: two-phase protocol (include/mvldm_b200.h, MVLDM_EXCHANGE_BEGIN / _END): BEGIN starts the all-gather on a
+    side stream (ordered after the K|V pack on the compute stream) and returns; the library runs the attention over this
+    rank's own keys meanwhile; END makes the compute stream wait for the gathered slabs; the partial softmaxes (own / before /
+    after slabs) are merged in a fixed order.  Measured on 2 / 4 / 8 B200 over NVLink 5 the exchange is a few percent of the
+    forward and the split costs about what it hides (bench.py's ``view_sharded`` object reports both), hence the default.
+    ``overlap="split"`` keeps the three-way split but runs the collective on the compute stream (measurement only)."""
 
-    def __init__(self, v_local: int, v_total: int, h: int, w: int, heads: int, device, group=None, overlap: bool = True):
+    def __init__(self, v_local: int, v_total: int, h: int, w: int, heads: int, device, group=None, overlap=False):
         from . import _lib
         self.group = group
         self.world = v_total // v_local
@@ -62,7 +66,7 @@ class ViewGroupExchange:
         self.send = torch.empty(per_rank, dtype=torch.bfloat16, device=device)
         self.recv = torch.empty(per_rank * self.world, dtype=torch.bfloat16, device=device)
         self.overlap = overlap
-        self.side = torch.cuda.Stream(device=device) if (overlap and torch.device(device).type == "cuda") else None
+        self.side = torch.cuda.Stream(device=device) if (overlap is True and torch.device(device).type == "cuda") else None
         self.done = torch.cuda.Event() if self.side is not None else None
         self.calls = 0
         self.bytes_sent = 0
@@ -71,8 +75,8 @@ class ViewGroupExchange:
             try:
                 if phase == _lib.EXCHANGE_BEGIN:
                     self.begin(nbytes // 2)
-                else:
-                    self.end()
+                    return _lib.EXCHANGE_DONE if (self.overlap is False and self.world > 1) else 0
+                self.end()
                 return 0
             except Exception:                                  # never unwind through the C frame
                 import traceback

@@ -290,12 +290,18 @@ def _view_shard_worker(rank, ws, port, sd, inp, ts, ref):
     m = m.cuda().eval()
     V = inp.shape[1]
     a, b = mv.view_slice(V, rank, ws)
-    ex = mv.ViewGroupExchange(b - a, V, 32, 32, 8, torch.device("cuda", rank))
-    y = m.forward_view_sharded(inp[:, a:b].cuda(), ts[:, a:b].cuda(), V, ex)
-    torch.cuda.synchronize()
-    err = rel_err(y, ref[:, a:b])
-    assert ex.calls == 9, ex.calls                                  # one K/V exchange per multi-view block
-    assert err < FWD_TOL, err
+    outs = []
+    for overlap in (False, True, "split"):      # one pass over the gathered slabs / all-gather overlapped with the own-keys pass
+        ex = mv.ViewGroupExchange(b - a, V, 32, 32, 8, torch.device("cuda", rank), overlap=overlap)
+        y = m.forward_view_sharded(inp[:, a:b].cuda(), ts[:, a:b].cuda(), V, ex)
+        torch.cuda.synchronize()
+        err = rel_err(y, ref[:, a:b])
+        assert ex.calls == 9, ex.calls                              # one K/V exchange per multi-view block
+        assert err < FWD_TOL, (overlap, err)
+        assert torch.equal(y, m.forward_view_sharded(inp[:, a:b].cuda(), ts[:, a:b].cuda(), V, ex))    # bit-stable
+        outs.append(y)
+    assert torch.equal(outs[1], outs[2])            # the split result does not depend on which stream carried the exchange
+    assert rel_err(outs[0], outs[1]) < 1e-2         # one-pass vs merged partial softmaxes: bf16 rounding of the parts only
     dist.destroy_process_group()
 
 
@@ -435,6 +441,27 @@ def test_standard_transformer_two_layers_and_wide_mlp():
     y = m.cuda().eval()(x.cuda(), t.cuda()).cpu()
     drift = _oracle_bf16_drift(sd, cfg_s, x, t, ref)
     assert rel_err(y, ref) < max(2 * drift, FWD_TOL)
+
+
+def test_standard_transformer_unequal_scenes_one_pass():
+    """StandardTransformer blocks through `forward_scenes` (CFG as one pass: an 8-view and a 6-view scene together): the
+    joint attention is per scene, so the pass must equal the two separate forwards"""
+    cfg_s = O.OracleCfg(mv_block="standard")
+    sd = O.init_weights(cfg_s, seed=0)
+    m = mv.MultiViewUNet(mv.standard_cfg(), 11, 4)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    torch.manual_seed(17)
+    x = torch.randn(5, 11, 16, 16, device="cuda")
+    t = torch.randint(0, 1000, (5,), device="cuda")
+    y = m.forward_scenes(x, t, [3, 2])
+    a = m(x[None, :3], t[None, :3])[0]
+    b = m(x[None, 3:], t[None, 3:])[0]
+    assert rel_err(y, torch.cat([a, b])) < FWD_TOL
+    assert torch.equal(y, m.forward_scenes(x, t, [3, 2]))
+    with torch.no_grad():
+        ref = O.unet_forward(sd, x[None, :3].cpu(), t[None, :3].cpu(), cfg_s)[0]
+    assert rel_err(y[:3], ref) < FWD_TOL
 
 
 def test_forward_scenes_unequal_view_counts(gpu_models):
