@@ -301,7 +301,7 @@ def _view_shard_worker(rank, ws, port, sd, inp, ts, ref):
         assert torch.equal(y, m.forward_view_sharded(inp[:, a:b].cuda(), ts[:, a:b].cuda(), V, ex))    # bit-stable
         outs.append(y)
     assert torch.equal(outs[1], outs[2])            # the split result does not depend on which stream carried the exchange
-    assert rel_err(outs[0], outs[1]) < 1e-2         # one-pass vs merged partial softmaxes: bf16 rounding of the parts only
+    assert rel_err(outs[0], outs[1]) < FWD_TOL      # one-pass vs merged partial softmaxes: bf16 rounding of the parts, 9 blocks deep
     dist.destroy_process_group()
 
 
