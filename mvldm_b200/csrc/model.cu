@@ -1747,6 +1747,8 @@ int64_t mvldm_workspace_bytes(mvldm_handle h, int B, int V, int H, int W) {
   try {
     MV_CHECK(h && h->finalized, "finalize weights first");
     MV_CHECK(B > 0 && V > 0, "empty batch");
+    MV_CHECK(h->cfg.model == MVLDM_MODEL_DENOISER, "mvldm_workspace_bytes: denoiser handles only");
+    h->program = 0;
     return (int64_t)h->plan_for(std::vector<int>(B, V), H, W).arena_bytes;
   } catch (const std::exception& e) {
     mvldm::g_last_error = e.what();
@@ -1782,6 +1784,7 @@ int mvldm_forward_sharded(mvldm_handle h, void* stream, const float* latents, co
   MV_CHECK(h && latents && timesteps && out && kv_send && kv_recv && exchange, "null argument");
   MV_CHECK(h->finalized, "mvldm_forward_sharded before mvldm_finalize_weights");
   MV_CHECK(h->cfg.impl == MVLDM_IMPL_TC, "view-group sharding needs the tcgen05 kernels");
+  MV_CHECK(h->cfg.model == MVLDM_MODEL_DENOISER, "mvldm_forward_sharded: denoiser handles only");
   MV_CHECK(V_local > 0 && V_total % V_local == 0, "V_total must be a multiple of V_local (equal view groups)");
   MV_CHECK(group_index >= 0 && group_index < V_total / V_local, "group_index out of range");
   h->group_index = group_index;
