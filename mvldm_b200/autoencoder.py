@@ -189,6 +189,7 @@ class AutoencoderKL(nn.Module):
     _register = MultiViewUNet._register
     _versions = MultiViewUNet._versions
     refresh_weights = MultiViewUNet.refresh_weights
+    _launch_checked = MultiViewUNet._launch_checked
 
     def _init_param(self, key: str, shape) -> nn.Parameter:
         leaf = key.rsplit(".", 1)[1]
@@ -270,12 +271,14 @@ class AutoencoderKL(nn.Module):
         f = self.downscale
         if h % f or w % f:
             raise ValueError(f"image size must be divisible by {f}")
-        self.refresh_weights(force=False)
-        moments = torch.empty((n, 2 * self.cfg.latent_channels, h // f, w // f), device=x.device, dtype=torch.float32)
-        with torch.cuda.device(x.device):
-            _lib.check(_lib.load().mvldm_vae_encode(self._h.ptr, _lib.current_stream_ptr(x.device), x.data_ptr(), n, h, w,
-                                                    moments.data_ptr()))
-        dist = DiagonalGaussianDistribution(moments)
+
+        def launch():
+            moments = torch.empty((n, 2 * self.cfg.latent_channels, h // f, w // f), device=x.device, dtype=torch.float32)
+            with torch.cuda.device(x.device):
+                _lib.check(_lib.load().mvldm_vae_encode(self._h.ptr, _lib.current_stream_ptr(x.device), x.data_ptr(), n, h, w,
+                                                        moments.data_ptr()))
+            return moments
+        dist = DiagonalGaussianDistribution(self._launch_checked(launch))
         return SimpleNamespace(latent_dist=dist) if return_dict else (dist,)
 
     @torch.no_grad()
@@ -284,11 +287,14 @@ class AutoencoderKL(nn.Module):
         z = self._check(z, self.cfg.latent_channels, "latents")
         n, _, h, w = z.shape
         f = self.downscale
-        self.refresh_weights(force=False)
-        img = torch.empty((n, self.cfg.out_channels, h * f, w * f), device=z.device, dtype=torch.float32)
-        with torch.cuda.device(z.device):
-            _lib.check(_lib.load().mvldm_vae_decode(self._h.ptr, _lib.current_stream_ptr(z.device), z.data_ptr(), n, h, w,
-                                                    img.data_ptr()))
+
+        def launch():
+            img = torch.empty((n, self.cfg.out_channels, h * f, w * f), device=z.device, dtype=torch.float32)
+            with torch.cuda.device(z.device):
+                _lib.check(_lib.load().mvldm_vae_decode(self._h.ptr, _lib.current_stream_ptr(z.device), z.data_ptr(), n, h, w,
+                                                        img.data_ptr()))
+            return img
+        img = self._launch_checked(launch)
         return SimpleNamespace(sample=img) if return_dict else (img,)
 
     def forward(self, sample: Tensor, sample_posterior: bool = False, generator=None):

@@ -409,6 +409,23 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
         h.synced_versions = vers
         self._dirty = False
 
+    def _launch_checked(self, launch):
+        """Run ``launch()`` (enqueues the library call, returns its output) against up-to-date packed weights.  The cheap
+        state (first use, load_state_dict, .to()) is checked in front of the call; the per-parameter version scan (tens of
+        microseconds of Python that would otherwise sit between the caller and the GPU) runs AFTER the call is enqueued,
+        under the GPU work.  If it finds an in-place update (optimizer / EMA step since the last call) the weights are
+        re-packed and the call is issued again on the same stream: the result returned always reflects the current
+        parameters, only the rare changed-weights call pays for a wasted forward."""
+        h = self._h
+        if self._dirty or h.ptr is None or h.synced_versions is None:
+            self.refresh_weights(force=False)
+            return launch()
+        out = launch()
+        if self._versions() != h.synced_versions:
+            self.refresh_weights(force=True)
+            out = launch()
+        return out
+
     # ---- Denoiser.forward -----------------------------------------------------------------
     @torch.no_grad()
     def forward(self, latents: Tensor, timestep: Tensor, cond_state: Optional[Tensor] = None) -> Tensor:
@@ -423,19 +440,20 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
             raise ValueError(f"expected {self.in_channels} input channels, got {c}")
         if timestep.dtype != torch.int64:
             raise TypeError("timestep must be int64 (jaxtyping Int64 at mvunet.py:94)")
-        self.refresh_weights(force=False)
-        hd = self._h
         # mvunet.py:102-105: [B] -> repeat over views, [B, V] -> flatten
         t = timestep.to(latents.device)
         t = t[:, None].expand(b, v) if t.dim() < 2 else t
         t = t.reshape(-1).contiguous()
         lat = latents.detach().to(torch.float32).contiguous()
-        out = torch.empty((b, v, self.out_channels, h, w), device=latents.device, dtype=torch.float32)
         lib = _lib.load()
-        with torch.cuda.device(latents.device):
-            _lib.check(lib.mvldm_forward(hd.ptr, _lib.current_stream_ptr(latents.device), lat.data_ptr(), t.data_ptr(),
-                                         b, v, h, w, out.data_ptr()))
-        return out
+
+        def launch():
+            out = torch.empty((b, v, self.out_channels, h, w), device=latents.device, dtype=torch.float32)
+            with torch.cuda.device(latents.device):
+                _lib.check(lib.mvldm_forward(self._h.ptr, _lib.current_stream_ptr(latents.device), lat.data_ptr(),
+                                             t.data_ptr(), b, v, h, w, out.data_ptr()))
+            return out
+        return self._launch_checked(launch)
 
     @torch.no_grad()
     def forward_scenes(self, latents: Tensor, timestep: Tensor, views_per_scene) -> Tensor:
@@ -454,15 +472,17 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
             raise ValueError(f"expected {self.in_channels} input channels, got {c}")
         if timestep.dtype != torch.int64 or timestep.numel() != n:
             raise TypeError("timestep must be int64, one per view")
-        self.refresh_weights(force=False)
         t = timestep.to(latents.device).reshape(-1).contiguous()
         lat = latents.detach().to(torch.float32).contiguous()
-        out = torch.empty((n, self.out_channels, h, w), device=latents.device, dtype=torch.float32)
         vp = (ctypes.c_int32 * len(views))(*views)
-        with torch.cuda.device(latents.device):
-            _lib.check(_lib.load().mvldm_forward_scenes(self._h.ptr, _lib.current_stream_ptr(latents.device), lat.data_ptr(),
-                                                        t.data_ptr(), len(views), vp, h, w, out.data_ptr()))
-        return out
+
+        def launch():
+            out = torch.empty((n, self.out_channels, h, w), device=latents.device, dtype=torch.float32)
+            with torch.cuda.device(latents.device):
+                _lib.check(_lib.load().mvldm_forward_scenes(self._h.ptr, _lib.current_stream_ptr(latents.device),
+                                                            lat.data_ptr(), t.data_ptr(), len(views), vp, h, w, out.data_ptr()))
+            return out
+        return self._launch_checked(launch)
 
     @torch.no_grad()
     def forward_view_sharded(self, latents: Tensor, timestep: Tensor, v_total: int, exchange) -> Tensor:
