@@ -121,3 +121,22 @@ def check(rc: int) -> None:
 def current_stream_ptr(device=None) -> int:
     import torch
     return torch.cuda.current_stream(device).cuda_stream
+
+
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def on_device(device):
+    """`with on_device(dev):` == `with torch.cuda.device(dev):` when dev is not the current device, and free otherwise (the
+    context manager's cudaGetDevice / cudaSetDevice pair is ~5 us per library call on the host's critical path)."""
+    import torch
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    return _NO_GUARD if idx == torch.cuda.current_device() else torch.cuda.device(idx)

@@ -274,7 +274,7 @@ class AutoencoderKL(nn.Module):
 
         def launch():
             moments = torch.empty((n, 2 * self.cfg.latent_channels, h // f, w // f), device=x.device, dtype=torch.float32)
-            with torch.cuda.device(x.device):
+            with _lib.on_device(x.device):
                 _lib.check(_lib.load().mvldm_vae_encode(self._h.ptr, _lib.current_stream_ptr(x.device), x.data_ptr(), n, h, w,
                                                         moments.data_ptr()))
             return moments
@@ -290,7 +290,7 @@ class AutoencoderKL(nn.Module):
 
         def launch():
             img = torch.empty((n, self.cfg.out_channels, h * f, w * f), device=z.device, dtype=torch.float32)
-            with torch.cuda.device(z.device):
+            with _lib.on_device(z.device):
                 _lib.check(_lib.load().mvldm_vae_decode(self._h.ptr, _lib.current_stream_ptr(z.device), z.data_ptr(), n, h, w,
                                                         img.data_ptr()))
             return img

@@ -400,7 +400,7 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
         lib = _lib.load()
         stream = _lib.current_stream_ptr(dev)
         dt = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             for key, p in self.state_dict(keep_vars=True).items():
                 t = p.detach().contiguous()
                 shape = (ctypes.c_int64 * t.dim())(*t.shape)
@@ -449,7 +449,7 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
 
         def launch():
             out = torch.empty((b, v, self.out_channels, h, w), device=latents.device, dtype=torch.float32)
-            with torch.cuda.device(latents.device):
+            with _lib.on_device(latents.device):
                 _lib.check(lib.mvldm_forward(self._h.ptr, _lib.current_stream_ptr(latents.device), lat.data_ptr(),
                                              t.data_ptr(), b, v, h, w, out.data_ptr()))
             return out
@@ -478,7 +478,7 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
 
         def launch():
             out = torch.empty((n, self.out_channels, h, w), device=latents.device, dtype=torch.float32)
-            with torch.cuda.device(latents.device):
+            with _lib.on_device(latents.device):
                 _lib.check(_lib.load().mvldm_forward_scenes(self._h.ptr, _lib.current_stream_ptr(latents.device),
                                                             lat.data_ptr(), t.data_ptr(), len(views), vp, h, w, out.data_ptr()))
             return out
@@ -499,7 +499,7 @@ class MultiViewUNet(Denoiser[MultiViewUNetCfg]):
         lat = latents.detach().to(torch.float32).contiguous()
         out = torch.empty((b, v, self.out_channels, h, w), device=latents.device, dtype=torch.float32)
         lib = _lib.load()
-        with torch.cuda.device(latents.device):
+        with _lib.on_device(latents.device):
             _lib.check(lib.mvldm_forward_sharded(
                 self._h.ptr, _lib.current_stream_ptr(latents.device), lat.data_ptr(), t.data_ptr(), v, v_total,
                 exchange.group_index, h, w, out.data_ptr(), exchange.send.data_ptr(), exchange.recv.data_ptr(),

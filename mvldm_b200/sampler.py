@@ -26,7 +26,7 @@ def ray_encode(extrinsics: Tensor, intrinsics: Tensor, h: int, w: int, use_pluck
     e = extrinsics.detach().to(torch.float32).contiguous()
     k = intrinsics.detach().to(torch.float32).contiguous()
     out = torch.empty((B, V, 6, h, w), device=e.device, dtype=torch.float32)
-    with torch.cuda.device(e.device):
+    with _lib.on_device(e.device):
         _lib.check(_lib.load().mvldm_raymap(_lib.current_stream_ptr(e.device), e.data_ptr(), k.data_ptr(), B * V, h, w,
                                             1 if use_plucker else 0, out.data_ptr()))
     return out
@@ -46,7 +46,7 @@ def build_inputs(x_t: Tensor, context_latents: Optional[Tensor], rays: Tensor, r
     x = x_t.detach().to(torch.float32).contiguous()
     c = context_latents.detach().to(torch.float32).contiguous() if v_c else None
     r = rays.detach().to(torch.float32).contiguous()
-    with torch.cuda.device(x.device):
+    with _lib.on_device(x.device):
         _lib.check(_lib.load().mvldm_build_inputs(_lib.current_stream_ptr(x.device), x.data_ptr(),
                                                   c.data_ptr() if v_c else None, r.data_ptr(), B, v_c, v_t,
                                                   rays.shape[1], ray_view_offset, R, h * w, out.data_ptr()))

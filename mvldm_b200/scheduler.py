@@ -133,7 +133,7 @@ def fused_cfg_ddim_step(sched: DDIMScheduler, eps_c: Tensor, eps_u: Optional[Ten
     eu = eps_u.detach().to(torch.float32).contiguous() if eps_u is not None else None
     out = torch.empty_like(x)
     lib = _lib.load()
-    with torch.cuda.device(x.device):
+    with _lib.on_device(x.device):
         _lib.check(lib.mvldm_ddim_step(_lib.current_stream_ptr(x.device), ec.data_ptr(),
                                        eu.data_ptr() if eu is not None else None, float(cfg_scale), B, v_c, v_t, chw,
                                        x.data_ptr(), sa, s1a, sp, s1p, out.data_ptr(), None))
