@@ -145,9 +145,14 @@ struct Step {
   float* scratch = nullptr;
   int c0 = 0, c1 = 0, n_img = 0, hw = 0, h = 0, w = 0, groups = 0, silu = 0, aux = 0;
   float eps = 0.f;
+  // the time-embedding chain does not depend on the latents: it runs on a side lane (second stream / parallel graph branch)
+  // next to im2col -> conv_in -> first GroupNorm, and the first launch that reads it joins the lanes again
+  int lane = 0;
+  bool join_side = false;
   OpMeta meta{};
 };
 struct Plan {
+  bool side_joined = false;      // recording: the side lane has been joined back into the main one
   std::vector<int> scene_views;  // views per scene; images of a scene are contiguous
   int H = 0, W = 0;
   DevBuf arena_mem;
@@ -212,6 +217,8 @@ struct mvldm_handle_s {
   // ---- run state ----
   cudaStream_t stream = nullptr;
   cudaStream_t capture_stream = nullptr;  // graphs are recorded here: the caller's stream may be the legacy NULL stream
+  cudaStream_t side_stream = nullptr;     // side lane of execute() (time-embedding chain)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   Arena arena;
   bool dry = true;       // measuring pass: arena offsets and split-K scratch only, nothing is recorded
   Plan* rec = nullptr;   // plan being recorded
@@ -670,6 +677,10 @@ struct mvldm_handle_s {
     Step st;
     st.kind = cfg.impl == MVLDM_IMPL_SIMT ? Step::GEMM_SIMT : Step::GEMM;
     st.gemm = d;
+    if (d.rowvec && !rec->side_joined) {  // first reader of the time embedding
+      st.join_side = true;
+      rec->side_joined = true;
+    }
     // algorithmic bytes: weights once + every input segment once + the output (+ the residual), no re-reads
     double bytes = 2.0 * (double)d.n * d.k + (d.mode == 2 ? 4.0 * M * d.n_valid : 2.0 * M * d.n * (d.mode == 1 ? 0.5 : 1.0));
     for (int i = 0; i < d.nseg; ++i) bytes += 2.0 * (double)d.n_img * d.seg[i].sh * d.seg[i].sw * d.seg[i].c;
@@ -1245,6 +1256,7 @@ struct mvldm_handle_s {
     Act e1 = new_act(n, 1, 1, temb_dim);
     Act e2 = new_act(n, 1, 1, temb_dim);
     float* temb = new_f32((size_t)n * temb_total);
+    const size_t temb_first = dry ? 0 : rec->steps.size();
     if (!dry) {
       Step st;
       st.kind = Step::SINUSOID;
@@ -1264,6 +1276,8 @@ struct mvldm_handle_s {
       d.mode = 4; d.out = temb; d.ldo = temb_total; d.n_valid = temb_all.n;
       run_gemm(d);
     }
+    if (!dry)  // (none of these GEMMs is split-K - modes 3 / 4 never are - so they do not touch the shared split-K scratch)
+      for (size_t i = temb_first; i < rec->steps.size(); ++i) rec->steps[i].lane = 1;
     // ---- conv_in on the im2col'd fp32 input
     Act col = new_act(n, Hh, Ww, kpad_in);
     if (!dry) {
@@ -1431,9 +1445,38 @@ struct mvldm_handle_s {
   }
 
   // issue the plan's launches on `s` (eagerly, or into a stream capture); with `events` every launch is bracketed
-  void execute(Plan& p, cudaStream_t s, std::vector<cudaEvent_t>* events) {
+  void execute(Plan& p, cudaStream_t main_s, std::vector<cudaEvent_t>* events) {
     size_t ev = 0;
+    // lanes: under the per-op profiler everything stays on one stream (event pairs must bracket single launches)
+    static const bool lanes_on = [] {
+      const char* e = getenv("MVLDM_LANES");
+      return !e || atoi(e) != 0;
+    }();
+    const bool lanes = lanes_on && !events;
+    if (lanes && !side_stream) {
+      MV_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+      MV_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      MV_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+    bool forked = false;
+    auto join = [&] {
+      if (!forked) return;
+      MV_CUDA(cudaEventRecord(ev_join, side_stream));
+      MV_CUDA(cudaStreamWaitEvent(main_s, ev_join, 0));
+      forked = false;
+    };
     for (const Step& st : p.steps) {
+      cudaStream_t s = main_s;
+      if (lanes && st.lane == 1) {
+        if (!forked) {  // the side lane starts after everything already enqueued on the main one (input staging copies)
+          MV_CUDA(cudaEventRecord(ev_fork, main_s));
+          MV_CUDA(cudaStreamWaitEvent(side_stream, ev_fork, 0));
+          forked = true;
+        }
+        s = side_stream;
+      } else if (st.join_side) {
+        join();
+      }
       if (events) MV_CUDA(cudaEventRecord((*events)[ev++], s));
       switch (st.kind) {
         case Step::GEMM:
@@ -1517,6 +1560,7 @@ struct mvldm_handle_s {
       }
       if (events) MV_CUDA(cudaEventRecord((*events)[ev++], s));
     }
+    join();  // (a plan whose side lane nobody read)
   }
 
   void forward(cudaStream_t s, const float* latents, const int64_t* tsteps, const std::vector<int>& sv, int H, int W,
@@ -1693,6 +1737,9 @@ int mvldm_destroy(mvldm_handle h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
     delete h;
   }
