@@ -732,7 +732,10 @@ TileChoice pick_tiles(const mvldm_gemm_desc& d) {
       const double epi = bn * (d.mode == 1 ? 12e-9 : 6e-9);  // TMEM -> registers -> global, per item
       // persistent CTA: ramp once, items back to back (epilogue hidden behind the next main loop), last epilogue exposed
       const double t_sm = 1.5e-6 + per_sm * std::max(main, epi) + epi;
-      const double t_red = splits > 1 ? (splits + 1.0) * M * (double)d.n * 4.0 / 3e12 + 3e-6 : 0.0;
+      double t_red = splits > 1 ? (splits + 1.0) * M * (double)d.n * 4.0 / 3e12 + 3e-6 : 0.0;
+      // more work items than SMs: the splits of a tile are not co-resident, so the reduction is a second kernel over the
+      // partials (profiles/r02_gemm_config_sweep.txt: M512 N1280 K23040 41.6 us at 6 splits = 192 items, 34.8 us at 4 = 128)
+      if (splits > 1 && ctas > (double)sm_count()) t_red += 6e-6;
       const double t = t_sm + t_red;
       if (t < best_t) {
         best_t = t;
