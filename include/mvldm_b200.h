@@ -196,6 +196,15 @@ int mvldm_ddim_step(void* stream, const float* eps_c, const float* eps_u, float 
                     int v_t, int chw, const float* x_t, float sqrt_a_t, float sqrt_1m_a_t, float sqrt_a_prev,
                     float sqrt_1m_a_prev, float* x_prev, float* eps_out /* may be NULL */);
 
+/* Replaces diffusers DDPMScheduler.step (the "ddpm" entry of SCHEDULER, src/model/scheduler/__init__.py:19-22,
+ * config/model/scheduler/ddpm.yaml) fused with the CFG compose: x0 = (x_t - s1a*eps)/sa, clamped to +-clip when clip > 0
+ * (clip_sample / clip_sample_range), x_prev = c_x0*x0 + c_xt*x_t + sigma*noise.  The host computes the scalars
+ * (c_x0 = sqrt(a_prev)*beta_t/(1-a_t), c_xt = sqrt(alpha_t)*(1-a_prev)/(1-a_t), sigma = sqrt(variance), 0 at t = 0) and
+ * draws `noise` (fp32, x_t's shape, NULL when sigma == 0) on the caller's generator. */
+int mvldm_ddpm_step(void* stream, const float* eps_c, const float* eps_u, float cfg_scale, int B, int v_c, int v_t,
+                    int chw, const float* x_t, const float* noise, float sa, float s1a, float c_x0, float c_xt, float sigma,
+                    float clip, float* x_prev);
+
 /* Replaces DiffusionWrapper.ray_encode / generate_image_rays (diffusion_wrapper.py:169-190,301-322) with
  * get_world_rays / sample_image_grid (src/geometry/projection.py:91-138) for use_ray_encoding=false,
  * srt_ray_encoding=false: extr [n,4,4] cam-to-world, intr [n,3,3] normalised (fp32, device);

@@ -12,13 +12,15 @@ from .anchored import AnchoredPlan, anchored_plan, sample_anchored
 from .autoencoder import (AUTOENCODERS, AutoencoderCfg, AutoencoderKL, AutoencoderKLCfg, first_stage_encode, get_autoencoder,
                           last_stage_decode, sd21_vae_cfg)
 from .sampler import DenoisingPath, build_inputs, ray_encode
-from .scheduler import (SCHEDULER, DDIMScheduler, DDIMSchedulerCfg, SchedulerCfg, fused_cfg_ddim_step, get_scheduler)
+from .scheduler import (SCHEDULER, DDIMScheduler, DDIMSchedulerCfg, DDPMScheduler, DDPMSchedulerCfg, SchedulerCfg,
+                        fused_cfg_ddim_step, fused_cfg_ddpm_step, get_scheduler)
 from .sharding import ViewGroupExchange, gather_scenes, scene_slice, view_slice
 
 __all__ = [
     "DENOISER", "CrossAttentionCfg", "Denoiser", "DenoiserCfg", "MultiViewUNet", "MultiViewUNetCfg", "SpatialTransformer3DCfg",
     "UNet2DModelCfg", "default_cfg", "standard_cfg", "get_denoiser", "DenoisingPath", "build_inputs", "ray_encode", "SCHEDULER",
-    "DDIMScheduler", "DDIMSchedulerCfg", "SchedulerCfg", "fused_cfg_ddim_step", "get_scheduler", "gather_scenes",
+    "DDIMScheduler", "DDIMSchedulerCfg", "DDPMScheduler", "DDPMSchedulerCfg", "SchedulerCfg", "fused_cfg_ddim_step",
+    "fused_cfg_ddpm_step", "get_scheduler", "gather_scenes",
     "scene_slice", "view_slice", "ViewGroupExchange", "AnchoredPlan", "anchored_plan", "sample_anchored",
     "AUTOENCODERS", "AutoencoderCfg", "AutoencoderKL", "AutoencoderKLCfg", "get_autoencoder", "first_stage_encode",
     "last_stage_decode", "sd21_vae_cfg",

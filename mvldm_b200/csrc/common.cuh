@@ -126,6 +126,9 @@ void upsample_nearest2x(cudaStream_t s, const bf16* x, int n_img, int h, int w, 
 void nhwc_to_nchw_f32(cudaStream_t s, const bf16* x, int n_img, int hw, int c, float* out);
 void build_inputs(cudaStream_t s, const float* x_t, const float* ctx, const float* rays, int B, int v_c, int v_t,
                   int ray_views, int ray_off, int R, int hw, float* out);
+void ddpm_step(cudaStream_t s, const float* eps_c, const float* eps_u, float scale, int B, int v_c, int v_t, int chw,
+               const float* x_t, const float* noise, float sa, float s1a, float c_x0, float c_xt, float sigma, float clip,
+               float* x_prev);
 void ddim_step(cudaStream_t s, const float* eps_c, const float* eps_u, float scale, int B, int v_c, int v_t, int chw,
                const float* x_t, float sa, float s1a, float sp, float s1p, float* x_prev, float* eps_out);
 void raymap(cudaStream_t s, const float* extr, const float* intr, int n, int h, int w, bool plucker, float* out);

@@ -122,6 +122,30 @@ __global__ void ddim_step_kernel(const float* __restrict__ eps_c, const float* _
   }
 }
 
+// CFG compose + DDPM ancestral update (diffusers DDPMScheduler.step, epsilon prediction): x0 = (x - sqrt(1-a_t) e) / sqrt(a_t),
+// optionally clamped to +-clip, x_prev = c_x0 x0 + c_xt x + sigma z
+__global__ void ddpm_step_kernel(const float* __restrict__ eps_c, const float* __restrict__ eps_u, float scale, int B,
+                                 int v_c, int v_t, int chw, const float* __restrict__ x_t, const float* __restrict__ noise,
+                                 float sa, float s1a, float c_x0, float c_xt, float sigma, float clip,
+                                 float* __restrict__ x_prev) {
+  const int64_t per_scene = (int64_t)v_t * chw;
+  const int64_t total = (int64_t)B * per_scene;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / per_scene, r = i - b * per_scene;
+    float e = eps_c[(b * (v_c + v_t) + v_c) * chw + r];
+    if (eps_u) {
+      const float u = eps_u[i];
+      e = u + scale * (e - u);
+    }
+    const float x = x_t[i];
+    float x0 = (x - s1a * e) / sa;
+    if (clip > 0.f) x0 = fminf(fmaxf(x0, -clip), clip);
+    float y = c_x0 * x0 + c_xt * x;
+    if (noise) y = fmaf(sigma, noise[i], y);
+    x_prev[i] = y;
+  }
+}
+
 // K17: pixel-centre grid -> K^-1 -> normalise -> rotate; origin broadcast; optional Pluecker moment
 __global__ void raymap_kernel(const float* __restrict__ extr, const float* __restrict__ intr, int n, int h, int w,
                               int plucker, float* __restrict__ out) {
@@ -215,6 +239,15 @@ void ddim_step(cudaStream_t s, const float* eps_c, const float* eps_u, float sca
   const int64_t total = (int64_t)B * v_t * chw;
   ddim_step_kernel<<<grid_for(total, 256), 256, 0, s>>>(eps_c, eps_u, scale, B, v_c, v_t, chw, x_t, sa, s1a, sp, s1p,
                                                          x_prev, eps_out);
+  MV_LAUNCHED();
+}
+
+void ddpm_step(cudaStream_t s, const float* eps_c, const float* eps_u, float scale, int B, int v_c, int v_t, int chw,
+               const float* x_t, const float* noise, float sa, float s1a, float c_x0, float c_xt, float sigma, float clip,
+               float* x_prev) {
+  const int64_t total = (int64_t)B * v_t * chw;
+  ddpm_step_kernel<<<grid_for(total, 256), 256, 0, s>>>(eps_c, eps_u, scale, B, v_c, v_t, chw, x_t, noise, sa, s1a, c_x0, c_xt,
+                                                         sigma, clip, x_prev);
   MV_LAUNCHED();
 }
 

@@ -1931,6 +1931,18 @@ int mvldm_ddim_step(void* stream, const float* eps_c, const float* eps_u, float 
   MV_API_END
 }
 
+int mvldm_ddpm_step(void* stream, const float* eps_c, const float* eps_u, float cfg_scale, int B, int v_c, int v_t,
+                    int chw, const float* x_t, const float* noise, float sa, float s1a, float c_x0, float c_xt, float sigma,
+                    float clip, float* x_prev) {
+  MV_API_BEGIN
+  MV_CHECK(eps_c && x_t && x_prev, "null argument");
+  MV_CHECK(sa > 0.f, "sqrt(alpha_t) must be positive");
+  MV_CHECK(noise || sigma == 0.f, "a non-zero sigma needs the noise tensor");
+  ddpm_step((cudaStream_t)stream, eps_c, eps_u, cfg_scale, B, v_c, v_t, chw, x_t, noise, sa, s1a, c_x0, c_xt, sigma, clip,
+            x_prev);
+  MV_API_END
+}
+
 int mvldm_raymap(void* stream, const float* extr, const float* intr, int n, int h, int w, int plucker, float* out) {
   MV_API_BEGIN
   MV_CHECK(extr && intr && out, "null argument");

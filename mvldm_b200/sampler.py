@@ -14,7 +14,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from .scheduler import DDIMScheduler, fused_cfg_ddim_step
+from .scheduler import DDIMScheduler, DDPMScheduler, fused_cfg_ddim_step, fused_cfg_ddpm_step
 
 
 def ray_encode(extrinsics: Tensor, intrinsics: Tensor, h: int, w: int, use_plucker: bool = False) -> Tensor:
@@ -63,6 +63,7 @@ class DenoisingPath:
         self.denoiser, self.scheduler = denoiser, scheduler
         self.use_cfg, self.cfg_scale, self.use_plucker = use_cfg, cfg_scale, use_plucker
         self.batch_cfg = batch_cfg
+        self.generator = None  # torch.Generator for the DDPM scheduler's variance noise (None: the default CUDA generator)
         self._t_cache = {}     # (B, v_c, v_t, ts, device) -> (timesteps [B, v_c+v_t], target timesteps [B, v_t])
 
     def set_timesteps(self, num: int) -> None:
@@ -94,12 +95,18 @@ class DenoisingPath:
             pred = model.forward_scenes(buf, self._t_cache[kb], [V] * B + [v_t] * B)
             pred_c = pred[:B * V].view(B, V, -1, h, w)
             pred_u = pred[B * V:].view(B, v_t, -1, h, w)
-            return fused_cfg_ddim_step(self.scheduler, pred_c, pred_u, self.cfg_scale, v_c, ts, x_t)
+            return self._update(pred_c, pred_u, v_c, ts, x_t)
         inputs = build_inputs(x_in, context_inputs[:, :, :4], ray_encodings)
         pred_c = model.forward(inputs, t_all)
         pred_u = None
         if self.use_cfg:
             pred_u = model.forward(build_inputs(x_in, None, ray_encodings, ray_view_offset=v_c), t_t)
+        return self._update(pred_c, pred_u, v_c, ts, x_t)
+
+    def _update(self, pred_c: Tensor, pred_u: Optional[Tensor], v_c: int, ts: int, x_t: Tensor) -> Tensor:
+        """CFG compose + scheduler step (diffusion_wrapper.py:444-451) as one kernel, for either scheduler of the registry"""
+        if isinstance(self.scheduler, DDPMScheduler):
+            return fused_cfg_ddpm_step(self.scheduler, pred_c, pred_u, self.cfg_scale, v_c, ts, x_t, self.generator)
         return fused_cfg_ddim_step(self.scheduler, pred_c, pred_u, self.cfg_scale, v_c, ts, x_t)
 
     @torch.no_grad()

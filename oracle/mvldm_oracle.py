@@ -486,6 +486,33 @@ class DDIMOracle:
         return sa * x + s1 * noise
 
 
+class DDPMOracle(DDIMOracle):
+    """diffusers ``DDPMScheduler`` with config/model/scheduler/ddpm.yaml (linear betas, fixed_small variance, clip_sample true,
+    leading spacing), restated from knowledge of diffusers 0.27.2 ``DDPMScheduler.step`` - parity unpinned, like every
+    diffusers piece (the reference only constructs it: src/model/scheduler/__init__.py:19-22)."""
+
+    def __init__(self, clip_sample=True, clip_sample_range=1.0, variance_type="fixed_small", **kw):
+        super().__init__(**kw)
+        self.clip_sample, self.clip_range, self.variance_type = clip_sample, clip_sample_range, variance_type
+
+    def step(self, eps: Tensor, t, x: Tensor, noise: Optional[Tensor] = None) -> Tensor:
+        t = int(t)
+        n = len(self.timesteps)
+        prev = t - 1000 // n
+        a_t = self.alphas_cumprod[t].double()
+        a_p = self.alphas_cumprod[prev].double() if prev >= 0 else torch.tensor(1.0, dtype=torch.float64)
+        cur_alpha = a_t / a_p
+        cur_beta = 1 - cur_alpha
+        x0 = (x.double() - (1 - a_t).sqrt() * eps.double()) / a_t.sqrt()
+        if self.clip_sample:
+            x0 = x0.clamp(-self.clip_range, self.clip_range)
+        prev_sample = (a_p.sqrt() * cur_beta / (1 - a_t)) * x0 + (cur_alpha.sqrt() * (1 - a_p) / (1 - a_t)) * x.double()
+        if t > 0:
+            var = (1 - a_p) / (1 - a_t) * cur_beta if self.variance_type == "fixed_small" else cur_beta
+            prev_sample = prev_sample + var.clamp(min=1e-20).sqrt() * noise.double()
+        return prev_sample.float()
+
+
 # --------------------------------------------------------------------------------------
 # geometry (projection.py:74-138, camera_utils.py:7-27, diffusion_wrapper.py:169-190,301-322)
 # --------------------------------------------------------------------------------------

@@ -363,6 +363,46 @@ def test_ddim_step_and_cfg():
     assert rel_err(got2, 2 * ref) < 1e-5
 
 
+def test_ddpm_step_and_cfg():
+    """the "ddpm" entry of the reference's scheduler registry (src/model/scheduler/__init__.py:19-22, ddpm.yaml: clip_sample
+    true, fixed_small variance): fused CFG compose + ancestral step against the restated diffusers DDPMScheduler.step, with the
+    variance noise drawn from a seeded CUDA generator on both sides"""
+    torch.manual_seed(12)
+    B, v_c, v_t = 2, 2, 3
+    ec, eu = torch.randn(B, v_c + v_t, 4, 32, 32), torch.randn(B, v_t, 4, 32, 32)
+    xt = torch.randn(B, v_t, 4, 32, 32) * 2.0                     # wide enough that the x0 clamp bites
+    for n_steps, t, vt in ((50, 480, "fixed_small"), (1000, 999, "fixed_small"), (50, 0, "fixed_small"), (25, 440, "fixed_large")):
+        s = mv.DDPMScheduler(variance_type=vt)
+        s.set_timesteps(n_steps)
+        o = O.DDPMOracle(variance_type=vt)
+        o.set_timesteps(n_steps)
+        assert torch.equal(s.timesteps, o.timesteps)
+        g1 = torch.Generator(device="cuda").manual_seed(5)
+        got = mv.fused_cfg_ddpm_step(s, ec.cuda(), eu.cuda(), 3.0, v_c, t, xt.cuda(), g1)
+        g2 = torch.Generator(device="cuda").manual_seed(5)
+        z = torch.randn(xt.shape, generator=g2, device="cuda").cpu() if t > 0 else None
+        ref = o.step(eu + 3.0 * (ec[:, v_c:] - eu), t, xt, z)
+        assert rel_err(got, ref) < 1e-5, (n_steps, t, vt)
+        # scheduler.step surface (no CFG): `.prev_sample`
+        g3 = torch.Generator(device="cuda").manual_seed(5)
+        got1 = s.step(eu.cuda(), t, xt.cuda(), generator=g3).prev_sample
+        assert rel_err(got1, o.step(eu, t, xt, z)) < 1e-5
+    # no clipping: linear in (x, eps, z)
+    s = mv.DDPMScheduler(clip_sample=False)
+    s.set_timesteps(50)
+    o = O.DDPMOracle(clip_sample=False)
+    o.set_timesteps(50)
+    g1 = torch.Generator(device="cuda").manual_seed(6)
+    got = s.step(eu.cuda(), 480, xt.cuda(), generator=g1).prev_sample
+    g2 = torch.Generator(device="cuda").manual_seed(6)
+    z = torch.randn(xt.shape, generator=g2, device="cuda").cpu()
+    assert rel_err(got, o.step(eu, 480, xt, z)) < 1e-5
+    with pytest.raises(NotImplementedError):
+        mv.DDPMScheduler(thresholding=True)
+    with pytest.raises(RuntimeError):
+        s.step(eu, 480, xt)                                         # CPU tensors: no fallback
+
+
 def test_raymap_and_build_inputs():
     g = np.load(os.path.join(GOLD, "g5_rays.npz"))
     extr, intr = torch.tensor(g["extr"]).cuda(), torch.tensor(g["intr"]).cuda()

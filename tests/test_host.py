@@ -117,6 +117,24 @@ def test_vae_module_matches_the_diffusers_layout():
     assert small.config.scaling_factor == 0.18215 and "kl" in mv.AUTOENCODERS
 
 
+def test_scheduler_registry_has_both_reference_entries():
+    """reference src/model/scheduler/__init__.py:19-40: SCHEDULER = {"ddim", "ddpm"}, built from the dataclass kwargs"""
+    assert set(mv.SCHEDULER) == {"ddim", "ddpm"}
+    s = mv.get_scheduler(mv.SchedulerCfg("ddpm", 1000, 1000, None, mv.DDPMSchedulerCfg(trained_betas="None")))   # ddpm.yaml:11
+    assert isinstance(s, mv.DDPMScheduler) and s.config.clip_sample and s.config.prediction_type == "epsilon"
+    s.set_timesteps(50)
+    o = O.DDPMOracle()
+    o.set_timesteps(50)
+    assert torch.equal(s.timesteps, o.timesteps) and s.init_noise_sigma == 1.0
+    sa, s1a, c0, ct, sg = s.coefficients(0)
+    assert sg == 0.0 and abs(c0 - 1.0) < 1e-12 and ct == 0.0                     # the last step returns the (clipped) x0
+    x, n = torch.randn(2, 3, 4, 8, 8), torch.randn(2, 3, 4, 8, 8)
+    t = torch.tensor([10, 900])
+    assert torch.allclose(s.add_noise(x, n, t), o.add_noise(x, n, t))
+    d = mv.get_scheduler(mv.SchedulerCfg("ddim", 1000, 25, None, mv.DDIMSchedulerCfg(clip_sample=False)))
+    assert isinstance(d, mv.DDIMScheduler)
+
+
 def test_unsupported_configs_raise():
     cfg = mv.default_cfg()
     cfg.pretrained_from = "runwayml/stable-diffusion-v1-5"     # 768-wide context: mvunet.py:127 cannot drive it either
