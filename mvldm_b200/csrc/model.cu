@@ -1931,6 +1931,15 @@ int mvldm_ddim_step(void* stream, const float* eps_c, const float* eps_u, float 
   MV_API_END
 }
 
+int mvldm_raymap_encoded(void* stream, const float* extr, const float* intr, int n, int h, int w, int plucker,
+                         int origin_octaves, int direction_octaves, float* out) {
+  MV_API_BEGIN
+  MV_CHECK(extr && intr && out, "null argument");
+  MV_CHECK(origin_octaves >= 0 && origin_octaves <= 32 && direction_octaves >= 0 && direction_octaves <= 32, "octaves out of range");
+  raymap((cudaStream_t)stream, extr, intr, n, h, w, plucker != 0, out, origin_octaves, direction_octaves);
+  MV_API_END
+}
+
 int mvldm_ddpm_step(void* stream, const float* eps_c, const float* eps_u, float cfg_scale, int B, int v_c, int v_t,
                     int chw, const float* x_t, const float* noise, float sa, float s1a, float c_x0, float c_xt, float sigma,
                     float clip, float* x_prev) {

@@ -65,6 +65,28 @@ def stats(t):
     return np.concatenate([[f.mean().item(), f.std().item(), f.abs().max().item()], f[idx].numpy()])
 
 
+def golden_ray_encoding():
+    """G8: `use_ray_encoding: true` (config/main.yaml:28-33, 10 origin / 8 direction octaves): DiffusionWrapper.ray_encode
+    (diffusion_wrapper.py:301-322) with the reference's own projection.py AND its own PositionalEncoding class."""
+    from src.model.encodings.positional_encoding import PositionalEncoding
+    extr8, intr8 = O.synthetic_cameras(1, 4)
+    h, w = 16, 24                                        # small fixture; non-square on purpose
+    xy, _ = sample_image_grid((h, w))
+    o, d = get_world_rays(rearrange(xy, "h w xy -> (h w) xy"), rearrange(extr8, "b v i j -> b v () i j"),
+                          rearrange(intr8, "b v i j -> b v () i j"))
+    out = {"extr": extr8.numpy(), "intr": intr8.numpy()}
+    for fo, fd in ((10, 8), (4, 0)):
+        oe = PositionalEncoding(fo)(o) if fo > 0 else o
+        de = PositionalEncoding(fd)(d) if fd > 0 else d
+        r_ref = rearrange(torch.cat([oe, de], dim=-1), "b v (h w) c -> b v c h w", h=h, w=w)
+        r_ora = O.raymap(extr8, intr8, h, w, False, fo, fd)
+        err = (r_ref - r_ora).abs().max().item()
+        print(f"ray encoding octaves ({fo},{fd}): {tuple(r_ref.shape)}  max|ref-oracle| = {err:.3e}")
+        assert r_ref.shape == r_ora.shape and err < 1e-4
+        out[f"rays_{fo}_{fd}"] = r_ref.numpy()
+    np.savez_compressed(os.path.join(GOLD, "g8_ray_encoding.npz"), **out)
+
+
 def golden_standard():
     """G7: the reference's DEFAULT multi-view block (config/model/denoiser/mv_unet.yaml:5 -> standard_attention.yaml):
     `StandardTransformer` at the 9 multi-view positions, V = 4 (2 context + 2 target), fp32 CPU.  The reference's
@@ -109,9 +131,13 @@ def main():
     ap.add_argument("--skip-trajectory", action="store_true")
     ap.add_argument("--skip-variant-b", action="store_true")
     ap.add_argument("--only-standard", action="store_true", help="(re)generate only g7 (StandardTransformer blocks)")
+    ap.add_argument("--only-ray-encoding", action="store_true", help="(re)generate only g8 (positionally encoded ray maps)")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_grad_enabled(False)
+    golden_ray_encoding()
+    if args.only_ray_encoding:
+        return
     golden_standard()
     if args.only_standard:
         return

@@ -521,9 +521,20 @@ def absolute_to_relative(extr: Tensor, index: int = 0) -> Tensor:
     return torch.linalg.inv(ref) @ extr
 
 
-def raymap(extr: Tensor, intr: Tensor, h: int, w: int, plucker: bool = False) -> Tensor:
-    """extr [B,V,4,4] cam->world, intr [B,V,3,3] normalised -> [B,V,6,h,w]:
-    channels = origin (or origin x direction if plucker) then direction; pixel centres (i+0.5)/n, x fastest."""
+def positional_encoding(x: Tensor, num_octaves: int) -> Tensor:
+    """``PositionalEncoding(num_octaves)`` (src/model/encodings/positional_encoding.py:28-49): [..., d] -> [..., d*F*2],
+    channel (d f p) = sin(2 pi 2^f x_d + p pi/2)"""
+    freq = 2 * torch.pi * 2 ** torch.arange(num_octaves).float()                      # [F]
+    phase = torch.tensor([0, 0.5 * torch.pi], dtype=torch.float32)                     # [2]
+    arg = x[..., :, None, None] * freq[:, None] + phase                                # [..., d, F, 2]
+    return torch.sin(arg).flatten(-3)
+
+
+def raymap(extr: Tensor, intr: Tensor, h: int, w: int, plucker: bool = False, origin_octaves: int = 0,
+           direction_octaves: int = 0) -> Tensor:
+    """extr [B,V,4,4] cam->world, intr [B,V,3,3] normalised -> [B,V,C,h,w]:
+    channels = origin (or origin x direction if plucker) then direction; pixel centres (i+0.5)/n, x fastest.
+    Octaves > 0 (use_ray_encoding: true, diffusion_wrapper.py:115-126,317-320): each triple is replaced by its encoding."""
     B, V = extr.shape[:2]
     ys = (torch.arange(h, dtype=extr.dtype) + 0.5) / h
     xs = (torch.arange(w, dtype=extr.dtype) + 0.5) / w
@@ -536,8 +547,12 @@ def raymap(extr: Tensor, intr: Tensor, h: int, w: int, plucker: bool = False) ->
     o = extr[..., :3, 3][:, :, None, :].expand_as(d)
     if plucker:
         o = torch.cross(o, d, dim=-1)
-    r = torch.cat([o, d], dim=-1)                                                      # [B,V,n,6]
-    return r.reshape(B, V, h, w, 6).permute(0, 1, 4, 2, 3).contiguous()
+    if origin_octaves > 0:
+        o = positional_encoding(o, origin_octaves)
+    if direction_octaves > 0:
+        d = positional_encoding(d, direction_octaves)
+    r = torch.cat([o, d], dim=-1)                                                      # [B,V,n,C]
+    return r.reshape(B, V, h, w, r.shape[-1]).permute(0, 1, 4, 2, 3).contiguous()
 
 
 # --------------------------------------------------------------------------------------

@@ -414,3 +414,23 @@ def test_raymap_and_build_inputs():
     ref, tgt = O.build_inputs(xT, torch.cat([ctx, torch.zeros(2, 2, 1, 32, 32)], 2), rays, torch.ones(2, 3, 1, 32, 32))
     assert torch.equal(mv.build_inputs(xT.cuda(), ctx.cuda(), rays.cuda()).cpu(), ref)          # byte-exact concat
     assert torch.equal(mv.build_inputs(xT.cuda(), None, rays.cuda(), 2).cpu(), torch.cat([tgt, rays[:, 2:]], 2))
+
+
+def test_positionally_encoded_ray_maps_match_reference():
+    """use_ray_encoding: true (config/main.yaml:28-33): golden g8 comes from the reference's own projection.py and
+    PositionalEncoding; sin() of arguments up to 2 pi 2^9 in fp32 - the tolerance is fp32 argument rounding, not bf16"""
+    g = np.load(os.path.join(GOLD, "g8_ray_encoding.npz"))
+    extr, intr = torch.tensor(g["extr"]).cuda(), torch.tensor(g["intr"]).cuda()
+    for fo, fd in ((10, 8), (4, 0)):
+        ref = torch.tensor(g[f"rays_{fo}_{fd}"])
+        got = mv.ray_encode(extr, intr, ref.shape[-2], ref.shape[-1], False, fo, fd).cpu()
+        assert got.shape == ref.shape
+        assert (got - ref).abs().max() < 2e-3, (fo, fd, (got - ref).abs().max())
+        assert (got[:, :, :6 * min(fo, 4)] - ref[:, :, :6 * min(fo, 4)]).abs().max() < 2e-5   # low octaves: exact to fp32 noise
+    # a denoiser with the matching in_channels (4 latent + 1 mask + 108 ray channels) takes these inputs
+    rays = mv.ray_encode(extr, intr, 16, 24, False, 10, 8)
+    m = mv.MultiViewUNet(mv.default_cfg(), 4 + 1 + 108, 4).cuda().eval()
+    x = mv.build_inputs(torch.randn(1, 2, 4, 16, 24, device="cuda"), torch.randn(1, 2, 4, 16, 24, device="cuda"), rays)
+    assert x.shape == (1, 4, 113, 16, 24)
+    y = m(x, torch.tensor([[0, 0, 500, 500]], device="cuda"))
+    assert y.shape == (1, 4, 4, 16, 24) and torch.isfinite(y).all()

@@ -100,3 +100,14 @@ def test_standard_transformer_matches_reference():
         y = O.unet_forward(sd, torch.tensor(g["inputs"]), torch.tensor(g["timesteps"]), cfg, taps)
     assert rel_err(y, torch.tensor(g["eps"])) < 1e-4
     assert sum(k.endswith(".attn") for k in taps) == 9
+
+
+def test_ray_encoding_matches_reference():
+    """use_ray_encoding: true: the oracle's positional encoding of the ray maps against golden g8 (reference projection.py +
+    reference PositionalEncoding, oracle/make_golden.py golden_ray_encoding)"""
+    g = np.load(os.path.join(GOLD, "g8_ray_encoding.npz"))
+    extr, intr = torch.tensor(g["extr"]), torch.tensor(g["intr"])
+    for fo, fd in ((10, 8), (4, 0)):
+        ref = torch.tensor(g[f"rays_{fo}_{fd}"])
+        got = O.raymap(extr, intr, ref.shape[-2], ref.shape[-1], False, fo, fd)
+        assert got.shape == ref.shape and (got - ref).abs().max() < 1e-5
