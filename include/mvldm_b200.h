@@ -213,9 +213,11 @@ int mvldm_raymap(void* stream, const float* extr, const float* intr, int n_views
                  float* out);
 /* use_ray_encoding=true (config/main.yaml:28-33; diffusion_wrapper.py:115-126,317-320): the origin and the direction triple
  * are each replaced by their PositionalEncoding (src/model/encodings/positional_encoding.py:28-49) when the octave count is
- * > 0: out [n, C, h, w], C = (6*origin_octaves or 3) + (6*direction_octaves or 3), channel (d f p) = sin(2 pi 2^f x_d + p pi/2). */
+ * > 0: out [n, C, h, w], C = (6*origin_octaves or 3) + (6*direction_octaves or 3), channel (d f p) = sin(2 pi 2^f x_d + p pi/2).
+ * srt != 0: srt_ray_encoding=true (diffusion_wrapper.py:104-113,311-315) - RayEncoder (src/model/srt/layers.py:9-58): per triple
+ * [sin(pi 2^f x_d) over (d f) | cos(pi 2^f x_d) over (d f)], origins then directions; both octave counts must be > 0. */
 int mvldm_raymap_encoded(void* stream, const float* extr, const float* intr, int n_views, int h, int w, int plucker,
-                         int origin_octaves, int direction_octaves, float* out);
+                         int origin_octaves, int direction_octaves, int srt, float* out);
 
 /* ---------------------------------------------------------------------------------------------
  * Op-level entry points: the kernels behind mvldm_forward, exposed so tests can check each against

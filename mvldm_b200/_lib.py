@@ -87,7 +87,7 @@ SYMBOLS["mvldm_forward_scenes"] = (c_int, [c_void_p, c_void_p, c_void_p, c_void_
                                            c_void_p])
 SYMBOLS["mvldm_op_attention_kv"] = (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
                                             c_int, c_int, c_int, c_int, c_int, c_void_p])
-SYMBOLS["mvldm_raymap_encoded"] = (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p])
+SYMBOLS["mvldm_raymap_encoded"] = (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p])
 SYMBOLS["mvldm_ddpm_step"] = (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                       c_float, c_float, c_float, c_float, c_float, c_float, c_void_p])
 SYMBOLS["mvldm_vae_decode"] = (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p])

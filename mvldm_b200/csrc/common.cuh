@@ -132,7 +132,7 @@ void ddpm_step(cudaStream_t s, const float* eps_c, const float* eps_u, float sca
 void ddim_step(cudaStream_t s, const float* eps_c, const float* eps_u, float scale, int B, int v_c, int v_t, int chw,
                const float* x_t, float sa, float s1a, float sp, float s1p, float* x_prev, float* eps_out);
 void raymap(cudaStream_t s, const float* extr, const float* intr, int n, int h, int w, bool plucker, float* out,
-            int oct_o = 0, int oct_d = 0);
+            int oct_o = 0, int oct_d = 0, bool srt = false);
 // weight packing helpers (device side): dst bf16 [rows, ld]; all sources fp32
 void convert_f32(cudaStream_t s, const void* src, int dtype, int64_t n, float* dst);
 // dst[rowmap ? rowmap[r] : r, dst_col0 + j] = src[r, j]; rowmap is a device array of `rows` ints or NULL

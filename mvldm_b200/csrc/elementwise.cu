@@ -149,10 +149,19 @@ __global__ void ddpm_step_kernel(const float* __restrict__ eps_c, const float* _
 // K17: pixel-centre grid -> K^-1 -> normalise -> rotate; origin broadcast; optional Pluecker moment
 // oct_o / oct_d > 0: the origin / direction triple is replaced by its PositionalEncoding (use_ray_encoding: true;
 // src/model/encodings/positional_encoding.py:28-49): channel (d f p) = sin(2 pi 2^f x_d + p pi/2), d-major, then f, then p
-__device__ __forceinline__ int write_encoded(float* o, int s, int ch, const float v[3], int oct) {
+__device__ __forceinline__ int write_encoded(float* o, int s, int ch, const float v[3], int oct, int srt) {
   if (oct <= 0) {
     for (int d = 0; d < 3; ++d) o[(int64_t)(ch + d) * s] = v[d];
     return ch + 3;
+  }
+  if (srt) {  // srt_ray_encoding: true - src/model/srt/layers.py:9-32: [sin(pi 2^f x_d) over (d f) | cos(...) over (d f)]
+    for (int d = 0; d < 3; ++d)
+      for (int f = 0; f < oct; ++f) {
+        const float arg = v[d] * (exp2f((float)f) * 3.141592653589793f);
+        o[(int64_t)(ch + d * oct + f) * s] = sinf(arg);
+        o[(int64_t)(ch + 3 * oct + d * oct + f) * s] = cosf(arg);
+      }
+    return ch + 6 * oct;
   }
   for (int d = 0; d < 3; ++d)
     for (int f = 0; f < oct; ++f) {
@@ -165,7 +174,7 @@ __device__ __forceinline__ int write_encoded(float* o, int s, int ch, const floa
 }
 
 __global__ void raymap_kernel(const float* __restrict__ extr, const float* __restrict__ intr, int n, int h, int w,
-                              int plucker, int oct_o, int oct_d, float* __restrict__ out) {
+                              int plucker, int oct_o, int oct_d, int srt, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * h * w) return;
   const int p = i % (h * w), v = i / (h * w);
@@ -195,8 +204,8 @@ __global__ void raymap_kernel(const float* __restrict__ extr, const float* __res
   const int C = (oct_o > 0 ? 6 * oct_o : 3) + (oct_d > 0 ? 6 * oct_d : 3);
   float* o = out + (int64_t)v * C * s + p;
   const float ov[3] = {ox, oy, oz}, dv[3] = {wx, wy, wz};
-  const int ch = write_encoded(o, s, 0, ov, oct_o);
-  write_encoded(o, s, ch, dv, oct_d);
+  const int ch = write_encoded(o, s, 0, ov, oct_o, srt);
+  write_encoded(o, s, ch, dv, oct_d, srt);
 }
 
 __global__ void convert_kernel(const void* __restrict__ src, int dtype, int64_t n, float* __restrict__ dst) {
@@ -272,8 +281,8 @@ void ddpm_step(cudaStream_t s, const float* eps_c, const float* eps_u, float sca
 }
 
 void raymap(cudaStream_t s, const float* extr, const float* intr, int n, int h, int w, bool plucker, float* out, int oct_o,
-            int oct_d) {
-  raymap_kernel<<<ceil_div(n * h * w, 128), 128, 0, s>>>(extr, intr, n, h, w, plucker ? 1 : 0, oct_o, oct_d, out);
+            int oct_d, bool srt) {
+  raymap_kernel<<<ceil_div(n * h * w, 128), 128, 0, s>>>(extr, intr, n, h, w, plucker ? 1 : 0, oct_o, oct_d, srt ? 1 : 0, out);
   MV_LAUNCHED();
 }
 

@@ -1932,11 +1932,12 @@ int mvldm_ddim_step(void* stream, const float* eps_c, const float* eps_u, float 
 }
 
 int mvldm_raymap_encoded(void* stream, const float* extr, const float* intr, int n, int h, int w, int plucker,
-                         int origin_octaves, int direction_octaves, float* out) {
+                         int origin_octaves, int direction_octaves, int srt, float* out) {
   MV_API_BEGIN
   MV_CHECK(extr && intr && out, "null argument");
   MV_CHECK(origin_octaves >= 0 && origin_octaves <= 32 && direction_octaves >= 0 && direction_octaves <= 32, "octaves out of range");
-  raymap((cudaStream_t)stream, extr, intr, n, h, w, plucker != 0, out, origin_octaves, direction_octaves);
+  MV_CHECK(!srt || (origin_octaves > 0 && direction_octaves > 0), "the SRT ray encoder needs both octave counts > 0");
+  raymap((cudaStream_t)stream, extr, intr, n, h, w, plucker != 0, out, origin_octaves, direction_octaves, srt != 0);
   MV_API_END
 }
 

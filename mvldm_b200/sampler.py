@@ -18,11 +18,12 @@ from .scheduler import DDIMScheduler, DDPMScheduler, fused_cfg_ddim_step, fused_
 
 
 def ray_encode(extrinsics: Tensor, intrinsics: Tensor, h: int, w: int, use_plucker: bool = False,
-               num_origin_octaves: int = 0, num_direction_octaves: int = 0) -> Tensor:
+               num_origin_octaves: int = 0, num_direction_octaves: int = 0, srt_ray_encoding: bool = False) -> Tensor:
     """extrinsics [B,V,4,4] (cam-to-world), intrinsics [B,V,3,3] (normalised) -> ray encodings [B,V,C,h,w]
     (diffusion_wrapper.py:301-322, srt_ray_encoding=false).  Octaves 0 / 0: ``use_ray_encoding: false`` (the released settings,
     baseline.yaml:50-51), C = 6.  Octaves > 0: ``use_ray_encoding: true`` (config/main.yaml:28-33): origins / directions are
-    replaced by their ``PositionalEncoding`` (diffusion_wrapper.py:115-126), C = 6*origin_octaves + 6*direction_octaves."""
+    replaced by their ``PositionalEncoding`` (diffusion_wrapper.py:115-126), C = 6*origin_octaves + 6*direction_octaves.
+    ``srt_ray_encoding``: the SRT ``RayEncoder`` instead (diffusion_wrapper.py:104-113,311-315; src/model/srt/layers.py:9-58)."""
     if not extrinsics.is_cuda:
         raise RuntimeError("mvldm_b200: ray_encode needs CUDA tensors (no CPU fallback)")
     B, V = extrinsics.shape[:2]
@@ -33,7 +34,7 @@ def ray_encode(extrinsics: Tensor, intrinsics: Tensor, h: int, w: int, use_pluck
     with _lib.on_device(e.device):
         _lib.check(_lib.load().mvldm_raymap_encoded(_lib.current_stream_ptr(e.device), e.data_ptr(), k.data_ptr(), B * V, h, w,
                                                     1 if use_plucker else 0, num_origin_octaves, num_direction_octaves,
-                                                    out.data_ptr()))
+                                                    1 if srt_ray_encoding else 0, out.data_ptr()))
     return out
 
 
@@ -63,7 +64,7 @@ class DenoisingPath:
 
     def __init__(self, denoiser, scheduler: DDIMScheduler, use_cfg: bool = False, cfg_scale: float = 3.0,
                  use_plucker: bool = False, batch_cfg: bool = True, num_origin_octaves: int = 0,
-                 num_direction_octaves: int = 0):
+                 num_direction_octaves: int = 0, srt_ray_encoding: bool = False):
         """``batch_cfg``: run the conditional (v_c + v_t views) and unconditional (v_t views) forwards of a CFG step as
         ONE pass over 2B scenes of unequal view counts (``forward_scenes``) instead of two back-to-back forwards."""
         self.denoiser, self.scheduler = denoiser, scheduler
@@ -71,6 +72,7 @@ class DenoisingPath:
         self.batch_cfg = batch_cfg
         # use_ray_encoding: true (config/main.yaml:28-33): octave counts of the positional encoding of the ray maps
         self.num_origin_octaves, self.num_direction_octaves = num_origin_octaves, num_direction_octaves
+        self.srt_ray_encoding = srt_ray_encoding
         self.generator = None  # torch.Generator for the DDPM scheduler's variance noise (None: the default CUDA generator)
         self._t_cache = {}     # (B, v_c, v_t, ts, device) -> (timesteps [B, v_c+v_t], target timesteps [B, v_t])
 
@@ -124,7 +126,8 @@ class DenoisingPath:
         B, v_c, _, h, w = context_latents.shape
         x_t = x_T * self.scheduler.init_noise_sigma
         ctx = torch.cat([context_latents, torch.zeros_like(context_latents[:, :, :1])], dim=2)
-        rays = ray_encode(extrinsics, intrinsics, h, w, self.use_plucker, self.num_origin_octaves, self.num_direction_octaves)
+        rays = ray_encode(extrinsics, intrinsics, h, w, self.use_plucker, self.num_origin_octaves, self.num_direction_octaves,
+                          self.srt_ray_encoding)
         for ts in self.scheduler.timesteps:
             x_t = self.step(self.denoiser, x_t, ts, ctx, rays)
             if record is not None:

@@ -84,6 +84,16 @@ def golden_ray_encoding():
         print(f"ray encoding octaves ({fo},{fd}): {tuple(r_ref.shape)}  max|ref-oracle| = {err:.3e}")
         assert r_ref.shape == r_ora.shape and err < 1e-4
         out[f"rays_{fo}_{fd}"] = r_ref.numpy()
+    # srt_ray_encoding: true - the reference's own SRT RayEncoder on "(b v) (h w) c" inputs (diffusion_wrapper.py:311-315)
+    from src.model.srt.layers import RayEncoder
+    enc = RayEncoder(pos_octaves=6, ray_octaves=5)
+    r = enc(rearrange(o, "b v n c -> (b v) n c"), rearrange(d, "b v n c -> (b v) n c"))
+    r_ref = rearrange(r, "(b v) (h w) c -> b v c h w", b=1, h=h, w=w)
+    r_ora = O.raymap(extr8, intr8, h, w, False, 6, 5, srt=True)
+    err = (r_ref - r_ora).abs().max().item()
+    print(f"SRT ray encoder (6,5): {tuple(r_ref.shape)}  max|ref-oracle| = {err:.3e}")
+    assert r_ref.shape == r_ora.shape and err < 1e-4
+    out["rays_srt_6_5"] = r_ref.numpy()
     np.savez_compressed(os.path.join(GOLD, "g8_ray_encoding.npz"), **out)
 
 

@@ -530,8 +530,16 @@ def positional_encoding(x: Tensor, num_octaves: int) -> Tensor:
     return torch.sin(arg).flatten(-3)
 
 
+def srt_positional_encoding(x: Tensor, num_octaves: int) -> Tensor:
+    """SRT ``PositionalEncoding(num_octaves, start_octave=0)`` (src/model/srt/layers.py:9-32): [..., d] -> [..., 2*d*F] =
+    [sin(pi 2^f x_d) over (d f) | cos(pi 2^f x_d) over (d f)]"""
+    mult = 2 ** torch.arange(num_octaves).float() * math.pi
+    sc = x[..., :, None] * mult
+    return torch.cat([torch.sin(sc).flatten(-2), torch.cos(sc).flatten(-2)], dim=-1)
+
+
 def raymap(extr: Tensor, intr: Tensor, h: int, w: int, plucker: bool = False, origin_octaves: int = 0,
-           direction_octaves: int = 0) -> Tensor:
+           direction_octaves: int = 0, srt: bool = False) -> Tensor:
     """extr [B,V,4,4] cam->world, intr [B,V,3,3] normalised -> [B,V,C,h,w]:
     channels = origin (or origin x direction if plucker) then direction; pixel centres (i+0.5)/n, x fastest.
     Octaves > 0 (use_ray_encoding: true, diffusion_wrapper.py:115-126,317-320): each triple is replaced by its encoding."""
@@ -547,10 +555,13 @@ def raymap(extr: Tensor, intr: Tensor, h: int, w: int, plucker: bool = False, or
     o = extr[..., :3, 3][:, :, None, :].expand_as(d)
     if plucker:
         o = torch.cross(o, d, dim=-1)
-    if origin_octaves > 0:
-        o = positional_encoding(o, origin_octaves)
-    if direction_octaves > 0:
-        d = positional_encoding(d, direction_octaves)
+    if srt:                                        # RayEncoder(pos, rays) = cat(pos_enc, ray_enc)  (srt/layers.py:53-56)
+        o, d = srt_positional_encoding(o, origin_octaves), srt_positional_encoding(d, direction_octaves)
+    else:
+        if origin_octaves > 0:
+            o = positional_encoding(o, origin_octaves)
+        if direction_octaves > 0:
+            d = positional_encoding(d, direction_octaves)
     r = torch.cat([o, d], dim=-1)                                                      # [B,V,n,C]
     return r.reshape(B, V, h, w, r.shape[-1]).permute(0, 1, 4, 2, 3).contiguous()
 

@@ -427,6 +427,9 @@ def test_positionally_encoded_ray_maps_match_reference():
         assert got.shape == ref.shape
         assert (got - ref).abs().max() < 2e-3, (fo, fd, (got - ref).abs().max())
         assert (got[:, :, :6 * min(fo, 4)] - ref[:, :, :6 * min(fo, 4)]).abs().max() < 2e-5   # low octaves: exact to fp32 noise
+    ref = torch.tensor(g["rays_srt_6_5"])                           # srt_ray_encoding: true, the reference's own RayEncoder
+    got = mv.ray_encode(extr, intr, ref.shape[-2], ref.shape[-1], False, 6, 5, srt_ray_encoding=True).cpu()
+    assert got.shape == ref.shape and (got - ref).abs().max() < 2e-4
     # a denoiser with the matching in_channels (4 latent + 1 mask + 108 ray channels) takes these inputs
     rays = mv.ray_encode(extr, intr, 16, 24, False, 10, 8)
     m = mv.MultiViewUNet(mv.default_cfg(), 4 + 1 + 108, 4).cuda().eval()

@@ -111,3 +111,6 @@ def test_ray_encoding_matches_reference():
         ref = torch.tensor(g[f"rays_{fo}_{fd}"])
         got = O.raymap(extr, intr, ref.shape[-2], ref.shape[-1], False, fo, fd)
         assert got.shape == ref.shape and (got - ref).abs().max() < 1e-5
+    ref = torch.tensor(g["rays_srt_6_5"])
+    got = O.raymap(extr, intr, ref.shape[-2], ref.shape[-1], False, 6, 5, srt=True)
+    assert got.shape == ref.shape and (got - ref).abs().max() < 1e-5
