@@ -322,6 +322,33 @@ def run_view_sharded(args, m, rank, world, local, dev, barrier):
             "collective": "ncclAllGather (torch.distributed all_gather_into_tensor) per multi-view block" if world > 1 else "none (local copy)"}
 
 
+def run_pipeline(args, m, sched, dev):
+    """DiffusionWrapper.sample end to end (diffusion_wrapper.py:455-490) for one scene: SD-2.1 VAE encode of the 2 context
+    images (256x256) -> 25 DDIM steps over 2 + 6 views -> VAE decode of the 6 target views.  VAE weights random-init."""
+    import mvldm_b200 as mv
+    from mvldm_b200 import synthetic
+    vae = mv.AutoencoderKL.from_pretrained("stabilityai/stable-diffusion-2-1", subfolder="vae").to(dev).eval()
+    path = mv.DenoisingPath(m, sched, use_cfg=False)
+    path.set_timesteps(NUM_DDIM_STEPS)
+    _, x_T, extr, intr = synthetic.scene(1, V_C, V_T, seed=5)
+    imgs = torch.rand(1, V_C, 3, 8 * H, 8 * W, device=dev)
+    x_T, extr, intr = x_T.to(dev), extr.to(dev), intr.to(dev)
+    for _ in range(2):
+        out = path.sample_images(vae, imgs, extr, intr, x_T=x_T)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 3
+    e0.record()
+    for _ in range(n):
+        out = path.sample_images(vae, imgs, extr, intr, x_T=x_T)
+    e1.record()
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    ms = e0.elapsed_time(e1) / n
+    return {"workload": "images in -> images out: VAE encode (2 context views, 256x256) + 25 DDIM steps (8 views) + VAE decode "
+                        "(6 target views)", "ms_per_sample_call": ms, "images_per_sec": V_T / (ms * 1e-3)}
+
+
 def run_gpu(args):
     import torch.distributed as dist
     import mvldm_b200 as mv
@@ -420,6 +447,11 @@ def run_gpu(args):
     if args.view_sharded_views > 0 and not args.cfg and S == 1 and args.view_sharded_views % world == 0:
         view_sharded = run_view_sharded(args, m, rank, world, local, dev, barrier)
 
+    # ---- the whole sampling call (DiffusionWrapper.sample): VAE encode of the context views + 25 steps + VAE decode -------
+    pipeline = None
+    if args.pipeline and not args.cfg and S == 1 and rank == 0:
+        pipeline = run_pipeline(args, m, sched, dev)
+
     # ---- per-kernel roofline: CUDA-event pairs around every launch of one more (eager) forward, on its stream
     prof = None
     if rank == 0:
@@ -469,6 +501,7 @@ def run_gpu(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roof, "cpu_baseline": cpu, "config4": config4, "view_sharded": view_sharded,
+            "sample_images": pipeline,
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -494,6 +527,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config4", dest="config4", action="store_false",
                     help="skip the BASELINE config-4 leg (64 scenes split over the ranks, strong scaling)")
+    ap.add_argument("--no-pipeline", dest="pipeline", action="store_false",
+                    help="skip the images-in / images-out leg (VAE encode + 25 steps + VAE decode)")
     ap.add_argument("--view-sharded-views", type=int, default=64,
                     help="views of the single scene used for the view-group-sharded leg (0 = skip)")
     args = ap.parse_args()

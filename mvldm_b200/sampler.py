@@ -133,3 +133,20 @@ class DenoisingPath:
             if record is not None:
                 record.append((int(ts), x_t.clone()))
         return x_t
+
+    @torch.no_grad()
+    def sample_images(self, autoencoder, context_images: Tensor, extrinsics: Tensor, intrinsics: Tensor,
+                      num_target_views: Optional[int] = None, x_T: Optional[Tensor] = None, generator=None) -> Tensor:
+        """DiffusionWrapper.sample (diffusion_wrapper.py:455-490) end to end: context images [B, v_c, 3, H, W] in [0, 1] ->
+        first_stage_encode (posterior sample x 0.18215) -> DDIM / DDPM loop on the latents -> last_stage_decode -> target
+        images [B, v_t, 3, H, W] in [0, 1].  ``extrinsics`` / ``intrinsics`` hold the context views first, then the targets.
+        ``x_T``: the initial noise [B, v_t, 4, H/8, W/8]; when omitted it is drawn on the CPU generator and moved to the
+        device, as the reference does (:473)."""
+        from .autoencoder import first_stage_encode, last_stage_decode
+        ctx = first_stage_encode(autoencoder, context_images, generator)
+        v_t = (extrinsics.shape[1] - ctx.shape[1]) if num_target_views is None else num_target_views
+        if x_T is None:
+            x_T = torch.randn((ctx.shape[0], v_t, *ctx.shape[2:])).to(ctx.device)
+        lat = self.sample(ctx, x_T, extrinsics, intrinsics)
+        return last_stage_decode(autoencoder, lat)
+

@@ -132,3 +132,23 @@ def test_anchored_sampling_with_vae_hand_over(gpu_models):
     assert torch.equal(lat_v[:, A], lat_l[:, A])                         # phase 1 is the same call
     rest = [t for _, c in plan.chunks for t in c]
     assert rest and not torch.equal(lat_v[:, rest], lat_l[:, rest])      # phase 2 saw the round-tripped anchors
+
+
+def test_sample_images_is_encode_sample_decode(gpu_models):
+    """DiffusionWrapper.sample end to end (diffusion_wrapper.py:455-490): images in -> images out equals the three stages
+    composed by hand with the same posterior noise and the same x_T"""
+    ref, vae = _pair(SD, seed=7)
+    m = gpu_models(0, True)
+    path = mv.DenoisingPath(m, mv.DDIMScheduler(clip_sample=False), use_cfg=False)
+    path.set_timesteps(2)
+    torch.manual_seed(8)
+    imgs = torch.rand(1, 2, 3, 256, 256, device="cuda")
+    extr = torch.eye(4, device="cuda").expand(1, 5, 4, 4).clone()
+    extr[0, :, 0, 3] = 0.2 * torch.arange(5, device="cuda")
+    intr = torch.tensor([[1.2, 0, 0.5], [0, 1.2, 0.5], [0, 0, 1.0]], device="cuda").expand(1, 5, 3, 3).clone()
+    x_T = torch.randn(1, 3, 4, 32, 32, device="cuda")
+    out = path.sample_images(vae, imgs, extr, intr, x_T=x_T, generator=torch.Generator(device="cuda").manual_seed(3))
+    assert out.shape == (1, 3, 3, 256, 256) and float(out.min()) >= 0.0 and float(out.max()) <= 1.0
+    ctx = mv.first_stage_encode(vae, imgs, torch.Generator(device="cuda").manual_seed(3))
+    want = mv.last_stage_decode(vae, path.sample(ctx, x_T, extr, intr))
+    assert torch.equal(out, want)

@@ -7,7 +7,7 @@ nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_rea
 SMI=$!
 python bench.py > gpurun_out/final/bench_n1.json 2> gpurun_out/final/bench_n1.err
 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/final/bench_reference.json 2>&1
-X="--no-cpu-baseline --no-config4 --view-sharded-views 0"
+X="--no-cpu-baseline --no-config4 --no-pipeline --view-sharded-views 0"
 python bench.py --cfg $X > gpurun_out/final/bench_cfg.json 2>&1
 python bench.py --cfg --no-batch-cfg $X > gpurun_out/final/bench_cfg_two_forwards.json 2>&1
 python bench.py --variant b $X > gpurun_out/final/bench_variant_b.json 2>&1
@@ -21,7 +21,7 @@ python tools/prof_gemm.py 64 320 320 32 >> gpurun_out/final/prof_ops.txt 2>&1
 python tools/prof_attn.py 1 8192 40 >> gpurun_out/final/prof_ops.txt 2>&1
 python tools/prof_attn.py 8 8192 40 3 >> gpurun_out/final/prof_ops.txt 2>&1
 python tools/excess.py 8 > gpurun_out/final/excess_v8.txt 2>&1
-NCU="--no-graph --no-cpu-baseline --no-config4 --view-sharded-views 0"
+NCU="--no-graph --no-cpu-baseline --no-config4 --no-pipeline --view-sharded-views 0"
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/final/launches_cold.csv python bench.py --steps 1 --warmup 3 $NCU > /dev/null 2>&1
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none --csv --log-file gpurun_out/final/launches_warm.csv python bench.py --steps 1 --warmup 3 $NCU > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 3 -c 1 -o gpurun_out/final/ncu_gemm_conv_l0 python tools/prof_gemm.py 8 320 320 32 5 > /dev/null 2>&1
